@@ -1,0 +1,198 @@
+/*
+ * pxb200.h -- C ABI of libpxb200.so, the B200 (sm_100a) implementation of the Progressive-X hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types. Every entry point names the
+ * reference interface it replaces (paths relative to the danini/progressive-x tree; gcr/ =
+ * graph-cut-ransac/src/pygcransac/include/, px/ = src/pyprogressivex/). INTEGRATION.md shows the binding a
+ * reference maintainer would add (a gcransac::ScoringFunction subclass and the pybind/ctypes stubs).
+ *
+ * Conventions
+ *   - All functions return 0 on success, a negative pxb_status on failure; pxb_last_error() gives the message
+ *     (thread-local). Nothing throws across the boundary and nothing calls exit().
+ *   - There is NO CPU fallback: if no CUDA device / wrong architecture is present, pxb_ctx_create fails.
+ *   - Host entry points take HOST pointers and perform the H2D/D2H copies themselves on the context's stream,
+ *     synchronising before they return. "_dev" entry points take DEVICE pointers, are asynchronous on the
+ *     context's stream and need pxb_sync() before results are read.
+ *   - Matrices are row-major float64 exactly as the reference holds them: correspondences [N,4] = x1 y1 x2 y2
+ *     (cv::Mat(N,4,CV_64F) view, px/src/progressivex_python.cpp:203); 2D-3D matches [N,5] = u v X Y Z with (u,v)
+ *     K^-1-normalised (progressivex_python.cpp:64-98); models 3x3 (9) or 3x4 (12) row-major, the order in which
+ *     the reference exports descriptors (progressivex_python.cpp:284-301).
+ *   - Arithmetic is IEEE float64 without FMA contraction in the reference's operation order, so residuals,
+ *     inlier masks and labels are bit-identical to the CPU reference; sums use a fixed reduction topology
+ *     (DESIGN.md "Summation order").
+ */
+#ifndef PXB200_H
+#define PXB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pxb_ctx pxb_ctx;
+
+typedef enum pxb_status {
+	PXB_OK = 0,
+	PXB_ERR_CUDA = -1,        /* CUDA runtime error (message has the CUDA string) */
+	PXB_ERR_NO_DEVICE = -2,   /* no usable sm_100 device */
+	PXB_ERR_ARGUMENT = -3,    /* bad shape / null pointer / unknown enum */
+	PXB_ERR_STATE = -4,       /* e.g. points not uploaded */
+	PXB_ERR_UNSUPPORTED = -5
+} pxb_status;
+
+/* Estimator families of the reference (gcr/types.h:78-80,93-95,136-138). */
+typedef enum pxb_model_type {
+	PXB_MODEL_HOMOGRAPHY = 0,  /* RobustHomographyEstimator, 4-point minimal solver */
+	PXB_MODEL_FUNDAMENTAL = 1, /* FundamentalMatrixEstimator, 7-point minimal solver */
+	PXB_MODEL_PNP = 2          /* PerspectiveNPointEstimator, P3P minimal solver */
+} pxb_model_type;
+
+const char *pxb_last_error(void);
+const char *pxb_version(void);
+
+/* ---- context ------------------------------------------------------------------------------------------- */
+int pxb_ctx_create(int device, pxb_ctx **out);
+void pxb_ctx_destroy(pxb_ctx *ctx);
+/* The CUDA stream (cudaStream_t as void*) every kernel of this context is launched on; lets a caller record
+ * events around "_dev" calls. */
+void *pxb_ctx_stream(pxb_ctx *ctx);
+int pxb_sync(pxb_ctx *ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+int64_t pxb_launch_count(pxb_ctx *ctx);
+
+/* Device memory helpers so that non-CUDA hosts (ctypes, cgo) can keep buffers resident. */
+int pxb_dev_alloc(pxb_ctx *ctx, size_t bytes, void **dev_ptr);
+int pxb_dev_free(pxb_ctx *ctx, void *dev_ptr);
+int pxb_memcpy_h2d(pxb_ctx *ctx, void *dev_dst, const void *host_src, size_t bytes);
+int pxb_memcpy_d2h(pxb_ctx *ctx, void *host_dst, const void *dev_src, size_t bytes);
+int pxb_host_alloc_pinned(size_t bytes, void **host_ptr);
+int pxb_host_free_pinned(void *host_ptr);
+
+/* ---- data ---------------------------------------------------------------------------------------------- */
+/* Replaces the cv::Mat view the reference builds over the caller's buffer (progressivex_python.cpp:203).
+ * Copies [N, dim] host doubles to the device and re-tiles them to the kernels' SoA layout. dim is 4 (H, F) or
+ * 5 (PnP). */
+int pxb_upload_points(pxb_ctx *ctx, int model_type, const double *pts_host, int64_t N);
+int64_t pxb_point_count(pxb_ctx *ctx);
+
+/* ---- a1/a2/a3: residual-and-inlier matrix ---------------------------------------------------------------- */
+/* Replaces K calls of Estimator::squaredResidual over all points (gcr/estimators/homography_estimator.h:181-199,
+ * fundamental_estimator.h:195-222, perspective_n_point_estimator.h:148-184).
+ * r2 is hypothesis-major: r2[k*N + i]. mask is a bit matrix: bit (i & 31) of mask[k*words + (i >> 5)],
+ * words = (N+31)/32, set iff r2 < T2 (the reference's inlier test, scoring_function_with_compound_model.h:85).
+ * Either output may be NULL. */
+int pxb_residual_matrix(pxb_ctx *ctx, const double *models_host, int64_t K, double T2, double *r2_host,
+                        uint32_t *mask_host);
+int pxb_residual_matrix_dev(pxb_ctx *ctx, const double *models_dev, int64_t K, double T2, double *r2_dev,
+                            uint32_t *mask_dev);
+/* Screening variant: residuals stored as float32 (rounded from the exact float64 value), mask still exact. */
+int pxb_residual_matrix_f32_dev(pxb_ctx *ctx, const double *models_dev, int64_t K, double T2, float *r2_dev,
+                                uint32_t *mask_dev);
+
+/* ---- a4: compound-aware MSAC score ----------------------------------------------------------------------- */
+/* Replaces MSACScoringFunctionWithCompoundModel::getScore (px/include/scoring_function_with_compound_model.h:61-125)
+ * for K hypotheses at once. Outputs per hypothesis: count (Score::inlier_number), value_sum = sum max(0,1-r2/T2),
+ * shared = sum min(compound_pref_i, pref_i) (0 when compound_pref is NULL). The caller finishes the score as the
+ * reference does: value = value_sum - pow(shared, exponent), and Score() when count + 1 < best.inlier_number
+ * (:105-106). compound_pref has N entries or is NULL (empty compound set, :110). */
+int pxb_score_compound(pxb_ctx *ctx, const double *models_host, int64_t K, double T2,
+                       const double *compound_pref_host, int64_t *count_host, double *value_sum_host,
+                       double *shared_host);
+int pxb_score_compound_dev(pxb_ctx *ctx, const double *models_dev, int64_t K, double T2,
+                           const double *compound_pref_dev, int64_t *count_dev, double *value_sum_dev,
+                           double *shared_dev);
+/* Inlier index list of one model (the std::vector<size_t>& inliers_ of getScore), ascending point order.
+ * inliers_host must hold N entries; *n_inliers receives the count. */
+int pxb_inliers(pxb_ctx *ctx, const double *model_host, double T2, int64_t *inliers_host, int64_t *n_inliers);
+
+/* ---- a5: preference vectors ------------------------------------------------------------------------------ */
+/* progx::Model::setPreferenceVector (px/include/progx_model.h:70-87): pref[i] = max(0, 1 - r2_i / T). */
+int pxb_preference_vector(pxb_ctx *ctx, const double *model_host, double T, double *pref_host);
+/* Tanimoto similarity of isPutativeModelValid (px/include/progressive_x.h:583-588). */
+int pxb_tanimoto(pxb_ctx *ctx, const double *a_host, const double *b_host, int64_t N, double *similarity);
+/* updateCompoundModel (px/include/progressive_x.h:597-624): out[i] = max(0, max_k prefs[k*N + i]). */
+int pxb_compound_max(pxb_ctx *ctx, const double *prefs_host, int64_t L, int64_t N, double *out_host);
+
+/* ---- a6/a7/a8: batched minimal solvers ------------------------------------------------------------------- */
+/* samples: K rows of m point indices (m = 4, 7, 3). models_out: K * max_solutions * model_size doubles
+ * (max_solutions = 1, 3, 4); n_models[k] receives how many leading slots of sample k are filled.
+ * H: HomographyFourPointSolver::estimateMinimalModel + gaussElimination<8> (gcr/estimators/
+ *    solver_homography_four_point.h:109-190, gcr/math_utils.h:45-87); sample_valid[k] =
+ *    RobustHomographyEstimator::isValidSample (homography_estimator.h:346-381); model_valid[k] = isValidModel's
+ *    determinant test (:326-342).
+ * F: FundamentalMatrixSevenPointSolver::estimateModel + the oriented-epipolar filter of
+ *    FundamentalMatrixEstimator::estimateModel (solver_fundamental_matrix_seven_point.h:91-291,
+ *    fundamental_estimator.h:161-184,737-800). Roots in ascending order.
+ * PnP: P3PSolver::estimateModel (solver_p3p.h:177-385).
+ * sample_valid / model_valid may be NULL. */
+int pxb_solve_minimal(pxb_ctx *ctx, const int64_t *samples_host, int64_t K, double *models_out_host,
+                      int32_t *n_models_host, uint8_t *sample_valid_host, uint8_t *model_valid_host);
+
+/* ---- a9/a10/a11/a12: PEARL ------------------------------------------------------------------------------- */
+/* dataEnergyFunctor + EnergyDataStructure (px/include/PEARL.h:17-56,82-128) evaluated densely:
+ * D[i*(L+1) + l], l < L: 2(1-lambda) if r2 > T else (1-lambda) r2 / T, T = 9/4 thr^2; D[i*(L+1)+L] = 1-lambda. */
+int pxb_pearl_datacost(pxb_ctx *ctx, const double *models_host, int64_t L, double thr, double lambda,
+                       double *D_host);
+/* One PEARL::labeling call (px/include/PEARL.h:476-555) = GCoptimizationGeneralGraph::expansion(it, 1000)
+ * (gcr/GCoptimization.cpp:1003-1086) on N sites and L1 = L+1 labels with data costs D [N, L1], Potts smooth
+ * cost lambda on the neighbour lists, and one uniform per-label cost. csr_off [N+1] / csr_idx are the DIRECTED
+ * neighbour lists as getNeighbors(i) returns them (duplicates preserved; each entry adds an undirected edge as
+ * setNeighbors does). lambda == 0 or no edges dispatches to the greedy facility-location solver like
+ * solveSpecialCases/solveGreedy (GCoptimization.cpp:483-555,608-751). init_labels may be NULL (all zero, the
+ * state of a fresh GCoptimization object). */
+int pxb_pearl_label(pxb_ctx *ctx, const double *D_host, int64_t N, int32_t L1, double lambda, double label_cost,
+                    const int32_t *csr_off_host, const int32_t *csr_idx_host, const int32_t *init_labels_host,
+                    int32_t *labels_out_host, double *energy_out);
+/* Sums of residual() over the points of each instance and their counts (px/include/PEARL.h:342-352,369-371,
+ * 388-390). labels: int32 [N]; entries outside [0, L) are ignored (outlier label). */
+int pxb_segment_residual_sums(pxb_ctx *ctx, const double *models_host, int64_t L, const int32_t *labels_host,
+                              double *sums_host, int64_t *counts_host);
+
+/* ---- a13: GC-RANSAC local optimisation terms ------------------------------------------------------------- */
+/* Unary terms of GCRANSAC::labeling (gcr/GCRANSAC.h:937-962): d[i] = clamp(r2/T',0,1), T' = thr*thr*9/4 and the
+ * (E0,E1) pair passed to add_term1. */
+int pxb_lo_unary_terms(pxb_ctx *ctx, const double *model_host, double thr, double lambda, double *d_host,
+                       double *e0_host, double *e1_host);
+/* Tukey bisquare weights of iteratedLeastSquaresFitting (gcr/GCRANSAC.h:658-669) for all points:
+ * w[i] = max(0, 1 - r2_i/T2)^2. */
+int pxb_tukey_weights(pxb_ctx *ctx, const double *model_host, double T2, double *weights_host);
+
+/* ---- self-test --------------------------------------------------------------------------------------------- */
+/* Compares the hot loop's shared-reciprocal double division (two quotients, one Newton reciprocal) with the
+ * IEEE div.rn.f64 on n_triples pseudo-random (a1, a2, b) operands; mode 0 = arbitrary bit patterns, 1 = magnitudes
+ * typical for the residual kernels. *mismatches must come back 0. */
+int pxb_selftest_division(pxb_ctx *ctx, uint64_t seed, int64_t n_triples, int mode, int64_t *mismatches);
+
+/* ---- task level (px/include/progressivex_python.h:4-95) --------------------------------------------------- */
+/* Same scalar argument lists as findHomographies_ / findTwoViewMotions_ / find6DPoses_. Return value = number
+ * of models (>= 0) or a negative pxb_status. labeling_out: N int64 (the reference's std::vector<size_t>),
+ * models_out: capacity max_models_out * 9 (or 12) doubles, row-major.
+ * Extra arguments the reference does not have: `seed` (the reference seeds from std::random_device,
+ * gcr/uniform_random_generator.h:50-54; 0 asks for a time-based seed) . */
+int pxb_find_homographies(pxb_ctx *ctx, const double *correspondences, int64_t N, int64_t *labeling_out,
+                          double *models_out, int64_t max_models_out, size_t source_image_width,
+                          size_t source_image_height, size_t destination_image_width,
+                          size_t destination_image_height, double spatial_coherence_weight, double threshold,
+                          double confidence, double neighborhood_ball_radius, double maximum_tanimoto_similarity,
+                          size_t max_iters, size_t minimum_point_number, int maximum_model_number,
+                          size_t sampler_id, double scoring_exponent, int do_logging, uint64_t seed);
+int pxb_find_two_view_motions(pxb_ctx *ctx, const double *correspondences, int64_t N, int64_t *labeling_out,
+                              double *models_out, int64_t max_models_out, size_t source_image_width,
+                              size_t source_image_height, size_t destination_image_width,
+                              size_t destination_image_height, double spatial_coherence_weight, double threshold,
+                              double confidence, double neighborhood_ball_radius,
+                              double maximum_tanimoto_similarity, size_t max_iters, size_t minimum_point_number,
+                              int maximum_model_number, size_t sampler_id, double scoring_exponent,
+                              int do_logging, uint64_t seed);
+int pxb_find_6d_poses(pxb_ctx *ctx, const double *image_points, const double *world_points,
+                      const double *intrinsics, int64_t N, int64_t *labeling_out, double *poses_out,
+                      int64_t max_models_out, double spatial_coherence_weight, double threshold, double confidence,
+                      double neighborhood_ball_radius, double maximum_tanimoto_similarity, size_t max_iters,
+                      size_t minimum_point_number, int maximum_model_number, uint64_t seed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PXB200_H */

@@ -1,0 +1,267 @@
+"""ctypes loader of the parity oracle. TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module
+(see oracle/pxo_oracle.h). The product package never does.
+
+  libpxoracle.so        CPU restatement of rows a1..a9, a12, a13 (+ a restated greedy UFL)
+  _ref/libgco_ref.so    the reference's own gco-v3 / BK max-flow sources (rows a10/a11, and the LO st-cut)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+ORACLE_LIB = HERE / "libpxoracle.so"
+GCO_REF_LIB = HERE / "_ref" / "libgco_ref.so"
+
+MODEL_H, MODEL_F, MODEL_PNP = 0, 1, 2
+DIM = {0: 4, 1: 4, 2: 5}
+MSIZE = {0: 9, 1: 9, 2: 12}
+SSIZE = {0: 4, 1: 7, 2: 3}
+MAXSOL = {0: 1, 1: 3, 2: 4}
+
+
+def build(ref: bool = True) -> None:
+    """Compile the oracle (and, when /root/reference is present, the reference gco build)."""
+    subprocess.run(["make", "-s", "-C", str(HERE), "oracle"], check=True)
+    if ref and Path("/root/reference").is_dir():
+        subprocess.run(["make", "-s", "-C", str(HERE), "ref"], check=True)
+
+
+_lib = None
+_gco = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not ORACLE_LIB.exists():
+            build(ref=False)
+        L = C.CDLL(str(ORACLE_LIB))
+        vp, i64, f64 = C.c_void_p, C.c_int64, C.c_double
+        L.pxo_squared_residual.restype = f64
+        L.pxo_squared_residual.argtypes = [C.c_int, vp, vp]
+        L.pxo_residual_matrix.argtypes = [C.c_int, vp, i64, vp, i64, f64, vp, vp]
+        L.pxo_residual_matrix.restype = None
+        L.pxo_get_score.restype = f64
+        L.pxo_get_score.argtypes = [C.c_int, vp, i64, vp, f64, vp, C.c_int, i64, C.POINTER(i64), C.POINTER(f64),
+                                    C.POINTER(f64), vp]
+        L.pxo_score_batch.argtypes = [C.c_int, vp, i64, vp, i64, f64, vp, vp, vp, vp, C.c_int]
+        L.pxo_score_batch.restype = None
+        L.pxo_preference_vector.argtypes = [C.c_int, vp, i64, vp, f64, vp]
+        L.pxo_preference_vector.restype = None
+        L.pxo_tanimoto.restype = f64
+        L.pxo_tanimoto.argtypes = [vp, vp, i64]
+        L.pxo_compound_max.argtypes = [vp, i64, i64, vp]
+        L.pxo_compound_max.restype = None
+        L.pxo_h4_solve.argtypes = [vp, vp, vp]
+        L.pxo_h4_is_valid_sample.argtypes = [vp, vp]
+        L.pxo_h_is_valid_model.argtypes = [vp]
+        L.pxo_f7_solve.argtypes = [vp, vp, vp, C.c_int]
+        L.pxo_p3p_solve.argtypes = [vp, vp, vp]
+        L.pxo_pearl_datacost.argtypes = [C.c_int, vp, i64, vp, i64, f64, f64, vp]
+        L.pxo_pearl_datacost.restype = None
+        L.pxo_segment_residual_sums.argtypes = [C.c_int, vp, i64, vp, i64, vp, vp, vp]
+        L.pxo_segment_residual_sums.restype = None
+        L.pxo_lo_unary_terms.argtypes = [C.c_int, vp, i64, vp, f64, f64, vp, vp, vp]
+        L.pxo_lo_unary_terms.restype = None
+        L.pxo_tukey_weights.argtypes = [C.c_int, vp, vp, i64, vp, f64, vp]
+        L.pxo_tukey_weights.restype = None
+        L.pxo_greedy_ufl.restype = f64
+        L.pxo_greedy_ufl.argtypes = [vp, i64, C.c_int32, f64, vp, vp]
+        _lib = L
+    return _lib
+
+
+def have_gco_ref() -> bool:
+    return GCO_REF_LIB.exists()
+
+
+def gco() -> C.CDLL:
+    global _gco
+    if _gco is None:
+        if not GCO_REF_LIB.exists():
+            build(ref=True)
+        G = C.CDLL(str(GCO_REF_LIB))
+        vp, f64 = C.c_void_p, C.c_double
+        G.gco_ref_pearl_label.restype = f64
+        G.gco_ref_pearl_label.argtypes = [C.c_int, C.c_int, vp, f64, f64, vp, vp, vp, vp, C.POINTER(C.c_int)]
+        G.gco_ref_energy.restype = f64
+        G.gco_ref_energy.argtypes = [C.c_int, C.c_int, vp, f64, f64, vp, vp, vp]
+        G.gco_ref_lo_labeling.restype = f64
+        G.gco_ref_lo_labeling.argtypes = [C.c_int, vp, vp, vp, f64, vp, vp, vp]
+        _gco = G
+    return _gco
+
+
+def _f(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def residual_matrix(t, pts, models, T2, want_r2=True, want_mask=True):
+    pts, models = _f(pts), _f(models).reshape(-1, MSIZE[t])
+    N, K = pts.shape[0], models.shape[0]
+    words = (N + 31) // 32
+    r2 = np.empty((K, N)) if want_r2 else None
+    mask = np.zeros((K, words), dtype=np.uint32) if want_mask else None
+    lib().pxo_residual_matrix(t, _p(pts), N, _p(models), K, float(T2), _p(r2), _p(mask))
+    return r2, mask
+
+
+def get_score(t, pts, model, T2, compound_pref=None, exponent=2, best_inlier_number=0):
+    pts, model = _f(pts), _f(model)
+    N = pts.shape[0]
+    cp = None if compound_pref is None else _f(compound_pref)
+    cnt, val, sh = C.c_int64(), C.c_double(), C.c_double()
+    inl = np.empty(N, dtype=np.int64)
+    final = lib().pxo_get_score(t, _p(pts), N, _p(model), float(T2), _p(cp), int(exponent), int(best_inlier_number),
+                                C.byref(cnt), C.byref(val), C.byref(sh), _p(inl))
+    return dict(value=final, count=cnt.value, value_sum=val.value, shared=sh.value, inliers=inl[: cnt.value].copy())
+
+
+def score_batch(t, pts, models, T2, compound_pref=None, threads=1):
+    pts, models = _f(pts), _f(models).reshape(-1, MSIZE[t])
+    N, K = pts.shape[0], models.shape[0]
+    cp = None if compound_pref is None else _f(compound_pref)
+    cnt = np.empty(K, dtype=np.int64)
+    val = np.empty(K)
+    sh = np.empty(K)
+    lib().pxo_score_batch(t, _p(pts), N, _p(models), K, float(T2), _p(cp), _p(cnt), _p(val), _p(sh), int(threads))
+    return cnt, val, sh
+
+
+def preference_vector(t, pts, model, T):
+    pts, model = _f(pts), _f(model)
+    out = np.empty(pts.shape[0])
+    lib().pxo_preference_vector(t, _p(pts), pts.shape[0], _p(model), float(T), _p(out))
+    return out
+
+
+def tanimoto(a, b):
+    a, b = _f(a), _f(b)
+    return lib().pxo_tanimoto(_p(a), _p(b), a.shape[0])
+
+
+def compound_max(prefs):
+    prefs = _f(prefs)
+    out = np.empty(prefs.shape[1])
+    lib().pxo_compound_max(_p(prefs), prefs.shape[0], prefs.shape[1], _p(out))
+    return out
+
+
+def solve_minimal(t, pts, samples):
+    """Same output convention as Context.solve_minimal: (models [K,maxsol,ms], n [K], sample_valid, model_valid)."""
+    pts = _f(pts)
+    s = np.ascontiguousarray(samples, dtype=np.int64).reshape(-1, SSIZE[t])
+    K = s.shape[0]
+    models = np.zeros((K, MAXSOL[t], MSIZE[t]))
+    n = np.zeros(K, dtype=np.int32)
+    sv = np.ones(K, dtype=np.uint8)
+    mv = np.ones(K, dtype=np.uint8)
+    L = lib()
+    buf = np.zeros(MAXSOL[t] * MSIZE[t])
+    for k in range(K):
+        row = np.ascontiguousarray(s[k])
+        if t == MODEL_H:
+            sv[k] = L.pxo_h4_is_valid_sample(_p(pts), _p(row))
+            n[k] = L.pxo_h4_solve(_p(pts), _p(row), _p(buf))
+            if n[k]:
+                models[k, 0] = buf[:9]
+                mv[k] = L.pxo_h_is_valid_model(_p(buf))
+            else:
+                mv[k] = 0
+        elif t == MODEL_F:
+            n[k] = L.pxo_f7_solve(_p(pts), _p(row), _p(buf), 1)
+            models[k].reshape(-1)[: n[k] * 9] = buf[: n[k] * 9]
+        else:
+            n[k] = L.pxo_p3p_solve(_p(pts), _p(row), _p(buf))
+            models[k].reshape(-1)[: n[k] * 12] = buf[: n[k] * 12]
+    return models, n, sv, mv
+
+
+def pearl_datacost(t, pts, models, thr, lam):
+    pts, models = _f(pts), _f(models).reshape(-1, MSIZE[t])
+    N, L = pts.shape[0], models.shape[0]
+    D = np.empty((N, L + 1))
+    lib().pxo_pearl_datacost(t, _p(pts), N, _p(models), L, float(thr), float(lam), _p(D))
+    return D
+
+
+def segment_residual_sums(t, pts, models, labels):
+    pts, models = _f(pts), _f(models).reshape(-1, MSIZE[t])
+    lab = np.ascontiguousarray(labels, dtype=np.int32)
+    L = models.shape[0]
+    sums = np.zeros(L)
+    counts = np.zeros(L, dtype=np.int64)
+    lib().pxo_segment_residual_sums(t, _p(pts), pts.shape[0], _p(models), L, _p(lab), _p(sums), _p(counts))
+    return sums, counts
+
+
+def lo_unary_terms(t, pts, model, thr, lam):
+    pts, model = _f(pts), _f(model)
+    N = pts.shape[0]
+    d, e0, e1 = np.empty(N), np.empty(N), np.empty(N)
+    lib().pxo_lo_unary_terms(t, _p(pts), N, _p(model), float(thr), float(lam), _p(d), _p(e0), _p(e1))
+    return d, e0, e1
+
+
+def tukey_weights(t, pts, model, T2):
+    pts, model = _f(pts), _f(model)
+    N = pts.shape[0]
+    idx = np.arange(N, dtype=np.int64)
+    w = np.zeros(N)
+    lib().pxo_tukey_weights(t, _p(pts), _p(idx), N, _p(model), float(T2), _p(w))
+    return w
+
+
+def greedy_ufl(D, label_cost, init_labels=None):
+    D = _f(D)
+    N, L1 = D.shape
+    init = None if init_labels is None else np.ascontiguousarray(init_labels, dtype=np.int32)
+    out = np.empty(N, dtype=np.int32)
+    e = lib().pxo_greedy_ufl(_p(D), N, L1, float(label_cost), _p(init), _p(out))
+    return out, e
+
+
+def gco_pearl_label(D, lam, label_cost, csr_off=None, csr_idx=None, init_labels=None):
+    """The reference's own gco-v3 driven like PEARL::labeling (oracle/_ref/libgco_ref.so)."""
+    D = _f(D)
+    N, L1 = D.shape
+    if csr_off is None:
+        csr_off = np.zeros(N + 1, dtype=np.int32)
+        csr_idx = np.zeros(1, dtype=np.int32)
+    off = np.ascontiguousarray(csr_off, dtype=np.int32)
+    idx = np.ascontiguousarray(csr_idx, dtype=np.int32)
+    init = None if init_labels is None else np.ascontiguousarray(init_labels, dtype=np.int32)
+    out = np.empty(N, dtype=np.int32)
+    cyc = C.c_int()
+    e = gco().gco_ref_pearl_label(N, L1, _p(D), float(lam), float(label_cost), _p(off), _p(idx), _p(init), _p(out),
+                                  C.byref(cyc))
+    return out, e, cyc.value
+
+
+def gco_energy(D, lam, label_cost, csr_off, csr_idx, labels):
+    D = _f(D)
+    N, L1 = D.shape
+    off = np.ascontiguousarray(csr_off, dtype=np.int32)
+    idx = np.ascontiguousarray(csr_idx, dtype=np.int32)
+    lab = np.ascontiguousarray(labels, dtype=np.int32)
+    return gco().gco_ref_energy(N, L1, _p(D), float(lam), float(label_cost), _p(off), _p(idx), _p(lab))
+
+
+def gco_lo_labeling(e0, e1, d, lam, csr_off, csr_idx):
+    e0, e1, d = _f(e0), _f(e1), _f(d)
+    N = e0.shape[0]
+    off = np.ascontiguousarray(csr_off, dtype=np.int32)
+    idx = np.ascontiguousarray(csr_idx, dtype=np.int32)
+    out = np.empty(N, dtype=np.uint8)
+    en = gco().gco_ref_lo_labeling(N, _p(e0), _p(e1), _p(d), float(lam), _p(off), _p(idx), _p(out))
+    return out, en

@@ -1,0 +1,10 @@
+// pxb_expansion.cu -- alpha-expansion label sweep (row a11). Placeholder until the GPU max-flow lands.
+#include "pxb_internal.h"
+
+namespace pxb {
+int launch_alpha_expansion(pxb_ctx *, const double *, int64_t, int32_t, double, double, const int32_t *,
+                           const int32_t *, int64_t, const int32_t *, int32_t *, double *) {
+	set_error("alpha-expansion (lambda > 0) is not implemented yet");
+	return PXB_ERR_UNSUPPORTED;
+}
+} // namespace pxb

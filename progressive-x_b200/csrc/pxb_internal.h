@@ -1,0 +1,104 @@
+// pxb_internal.h -- shared internals of libpxb200.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "pxb200.h"
+
+namespace pxb {
+
+void set_error(const char *fmt, ...);
+
+#define PXB_CUDA(call)                                                                                  \
+	do {                                                                                                \
+		cudaError_t err__ = (call);                                                                     \
+		if (err__ != cudaSuccess) {                                                                     \
+			pxb::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), __FILE__, __LINE__); \
+			return PXB_ERR_CUDA;                                                                        \
+		}                                                                                               \
+	} while (0)
+
+#define PXB_CHECK_ARG(cond, msg)                    \
+	do {                                            \
+		if (!(cond)) {                              \
+			pxb::set_error("bad argument: %s", msg); \
+			return PXB_ERR_ARGUMENT;                \
+		}                                           \
+	} while (0)
+
+#define PXB_TRY(expr)              \
+	do {                           \
+		int rc__ = (expr);         \
+		if (rc__ != PXB_OK) return rc__; \
+	} while (0)
+
+constexpr int kMaxDim = 5;
+
+inline int point_dim(int t) { return t == PXB_MODEL_PNP ? 5 : 4; }
+inline int model_size(int t) { return t == PXB_MODEL_PNP ? 12 : 9; }
+inline int sample_size(int t) { return t == PXB_MODEL_HOMOGRAPHY ? 4 : (t == PXB_MODEL_FUNDAMENTAL ? 7 : 3); }
+inline int max_solutions(int t) { return t == PXB_MODEL_HOMOGRAPHY ? 1 : (t == PXB_MODEL_FUNDAMENTAL ? 3 : 4); }
+
+// A growable device scratch buffer (never shrinks; freed with the context).
+struct DevBuf {
+	void *ptr = nullptr;
+	size_t cap = 0;
+	int reserve(size_t bytes);
+	void release();
+	template <class T> T *as() { return reinterpret_cast<T *>(ptr); }
+};
+
+// Points live on the device in SoA form: coordinate c of point i at soa[c * stride + i], stride a multiple of 64
+// so that every coordinate row starts 512-byte aligned and warps read 256 contiguous bytes.
+struct Points {
+	int type = -1;
+	int dim = 0;
+	int64_t N = 0;
+	int64_t stride = 0;
+	double *soa = nullptr; // [dim][stride]
+	double *aos = nullptr; // [N][dim] as uploaded (used by the solvers' gathers)
+};
+
+} // namespace pxb
+
+struct pxb_ctx {
+	int device = 0;
+	int sm_count = 0;
+	cudaStream_t stream = nullptr;
+	int64_t launches = 0;
+	pxb::Points pts;
+	// scratch
+	pxb::DevBuf models, pref, pref2, outA, outB, outC, outD, idx, mask, partials, staging;
+	void *pinned = nullptr;
+	size_t pinned_cap = 0;
+	int reserve_pinned(size_t bytes);
+};
+
+namespace pxb {
+// kernel launchers (device pointers, asynchronous on ctx->stream)
+int launch_residual_matrix(pxb_ctx *ctx, const double *models, int64_t K, double T2, double *r2, float *r2f,
+                           uint32_t *mask);
+int launch_score_compound(pxb_ctx *ctx, const double *models, int64_t K, double T2, const double *compound_pref,
+                          int64_t *count, double *value_sum, double *shared);
+int launch_preference(pxb_ctx *ctx, const double *model, double T, double *pref);
+int launch_tanimoto(pxb_ctx *ctx, const double *a, const double *b, int64_t N, double *out3 /*dot,na,nb*/);
+int launch_compound_max(pxb_ctx *ctx, const double *prefs, int64_t L, int64_t N, double *out);
+int launch_pearl_datacost(pxb_ctx *ctx, const double *models, int64_t L, double thr, double lambda, double *D);
+int launch_segment_sums(pxb_ctx *ctx, const double *models, int64_t L, const int32_t *labels, double *sums,
+                        int64_t *counts);
+int launch_lo_unary(pxb_ctx *ctx, const double *model, double thr, double lambda, double *d, double *e0, double *e1);
+int launch_tukey(pxb_ctx *ctx, const double *model, double T2, double *w);
+int launch_inlier_compact(pxb_ctx *ctx, const double *model, double T2, int64_t *inliers, int64_t *n_inliers_dev);
+int launch_solve_minimal(pxb_ctx *ctx, const int64_t *samples, int64_t K, double *models_out, int32_t *n_models,
+                         uint8_t *sample_valid, uint8_t *model_valid);
+int launch_greedy_label(pxb_ctx *ctx, const double *D, int64_t N, int32_t L1, double label_cost,
+                        const int32_t *init_labels, int32_t *labels_out, double *energy_out_dev);
+int launch_alpha_expansion(pxb_ctx *ctx, const double *D, int64_t N, int32_t L1, double lambda, double label_cost,
+                           const int32_t *csr_off, const int32_t *csr_idx, int64_t n_dir_edges,
+                           const int32_t *init_labels, int32_t *labels_out, double *energy_out_host);
+} // namespace pxb

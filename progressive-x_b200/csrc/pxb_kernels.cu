@@ -1,0 +1,647 @@
+// pxb_kernels.cu -- the data-parallel N-point loops of Progressive-X as sm_100a kernels.
+//
+//   k_residual_matrix   a1/a2/a3  N x K squared residuals (f64 or f32) + inlier bit matrix      HBM-write bound
+//   k_score_partial     a4        fused compound-aware MSAC score (no matrix materialised)       FP64-pipe bound
+//   k_score_finalize    a4        ordered combine of the per-chunk partials
+//   k_preference        a5        preference vector of one model
+//   k_tanimoto          a5        dot / squared norms, one block, fixed topology
+//   k_compound_max      a5
+//   k_pearl_datacost    a9        N x (L+1) data-cost matrix
+//   k_segment_sums      a12       per-instance residual sums, one block per instance
+//   k_lo_unary          a13       GC-RANSAC LO unary terms
+//   k_tukey             a13       Tukey weights
+//
+// Layout: points are SoA (coordinate-major, stride padded to 64) so that a warp's 32 lanes read 256 contiguous
+// bytes per coordinate. Models of the current tile are staged in shared memory and read with warp-uniform
+// addresses (LDS broadcast). The residual matrix is hypothesis-major (r2[k*N + i]): lanes map to consecutive
+// points, so every warp store covers two full 128-byte lines; stores are streaming (st.global.cs) because the
+// matrix is never re-read by the producer.
+//
+// Summation order: a thread accumulates its points in increasing index order, lanes combine by a
+// fixed xor-butterfly, warps combine in warp order, chunks combine in chunk order. The topology depends on N
+// only -- never on K, the grid or the device -- so equal inputs always give equal sums.
+#include <cstdio>
+
+#include "pxb_internal.h"
+#include "pxb_residuals.cuh"
+
+namespace pxb {
+
+constexpr int kThreads = 256;
+
+// ------------------------------------------------------------------------------------------------
+// AoS -> SoA re-tiling of the uploaded points
+// ------------------------------------------------------------------------------------------------
+__global__ void k_aos_to_soa(const double *__restrict__ aos, double *__restrict__ soa, int64_t N, int64_t stride,
+                             int dim) {
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= stride) return;
+	for (int c = 0; c < dim; ++c) soa[c * stride + i] = (i < N) ? aos[i * dim + c] : 0.0;
+}
+
+int launch_aos_to_soa(pxb_ctx *ctx) {
+	Points &p = ctx->pts;
+	const int grid = (int)((p.stride + kThreads - 1) / kThreads);
+	k_aos_to_soa<<<grid, kThreads, 0, ctx->stream>>>(p.aos, p.soa, p.N, p.stride, p.dim);
+	ctx->launches++;
+	PXB_CUDA(cudaGetLastError());
+	return PXB_OK;
+}
+
+template <int DIM>
+__device__ __forceinline__ void load_point(const double *__restrict__ soa, int64_t stride, int64_t i, double (&p)[5]) {
+#pragma unroll
+	for (int c = 0; c < DIM; ++c) p[c] = __ldg(soa + c * stride + i);
+}
+
+// ------------------------------------------------------------------------------------------------
+// a1/a2/a3: residual-and-inlier matrix
+// ------------------------------------------------------------------------------------------------
+constexpr int kRmPointsPerWarp = 64;                         // lane handles points base+lane and base+32+lane
+constexpr int kRmPointsPerBlock = (kThreads / 32) * kRmPointsPerWarp; // 512
+constexpr int kRmHypsPerBlock = 64;
+
+template <typename OUT> __device__ __forceinline__ void store_stream(OUT *p, double v);
+template <> __device__ __forceinline__ void store_stream<double>(double *p, double v) { __stcs(p, v); }
+template <> __device__ __forceinline__ void store_stream<float>(float *p, double v) { __stcs(p, __double2float_rn(v)); }
+
+template <int TYPE, typename OUT>
+__global__ void __launch_bounds__(kThreads)
+    k_residual_matrix(const double *__restrict__ soa, int64_t stride, int64_t N, const double *__restrict__ models,
+                      int64_t K, double T2, OUT *__restrict__ r2, uint32_t *__restrict__ mask, int64_t words) {
+	constexpr int DIM = ModelTraits<TYPE>::kDim, MS = ModelTraits<TYPE>::kSize;
+	__shared__ double s_models[kRmHypsPerBlock * MS];
+
+	const int64_t k0 = (int64_t)blockIdx.y * kRmHypsPerBlock;
+	const int nk = (int)min((int64_t)kRmHypsPerBlock, K - k0);
+	for (int t = threadIdx.x; t < nk * MS; t += kThreads) s_models[t] = models[k0 * MS + t];
+	__syncthreads();
+
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int64_t base = (int64_t)blockIdx.x * kRmPointsPerBlock + warp * kRmPointsPerWarp;
+	if (base >= N) return;
+	const int64_t i0 = base + lane, i1 = base + 32 + lane;
+	const bool v0 = i0 < N, v1 = i1 < N;
+	double p0[5], p1[5];
+	// stride is padded to a multiple of 64 and the pad is zero-filled, so the loads are always in bounds
+	load_point<DIM>(soa, stride, i0, p0);
+	load_point<DIM>(soa, stride, i1, p1);
+	const int64_t w0 = base >> 5;
+
+#pragma unroll 2
+	for (int k = 0; k < nk; ++k) {
+		const double *m = s_models + k * MS;
+		const double ra = squared_residual<TYPE>(p0, m);
+		const double rb = squared_residual<TYPE>(p1, m);
+		const int64_t row = k0 + k;
+		if (r2) {
+			if (v0) store_stream<OUT>(r2 + row * N + i0, ra);
+			if (v1) store_stream<OUT>(r2 + row * N + i1, rb);
+		}
+		if (mask) {
+			const uint32_t ba = __ballot_sync(0xffffffffu, v0 && (ra < T2));
+			const uint32_t bb = __ballot_sync(0xffffffffu, v1 && (rb < T2));
+			if (lane == 0) mask[row * words + w0] = ba;
+			if (lane == 1 && (w0 + 1) < words) mask[row * words + w0 + 1] = bb;
+		}
+	}
+}
+
+template <int TYPE, typename OUT>
+static int launch_rm_t(pxb_ctx *ctx, const double *models, int64_t K, double T2, OUT *r2, uint32_t *mask) {
+	const Points &p = ctx->pts;
+	const int64_t words = (p.N + 31) / 32;
+	const int64_t gx = (p.N + kRmPointsPerBlock - 1) / kRmPointsPerBlock;
+	int64_t done = 0;
+	while (done < K) { // gridDim.y is limited to 65535
+		const int64_t kk = std::min<int64_t>(K - done, (int64_t)65535 * kRmHypsPerBlock);
+		dim3 grid((unsigned)gx, (unsigned)((kk + kRmHypsPerBlock - 1) / kRmHypsPerBlock));
+		k_residual_matrix<TYPE, OUT><<<grid, kThreads, 0, ctx->stream>>>(
+		    p.soa, p.stride, p.N, models + done * ModelTraits<TYPE>::kSize, kk, T2, r2 ? r2 + done * p.N : nullptr,
+		    mask ? mask + done * words : nullptr, words);
+		ctx->launches++;
+		done += kk;
+	}
+	PXB_CUDA(cudaGetLastError());
+	return PXB_OK;
+}
+
+int launch_residual_matrix(pxb_ctx *ctx, const double *models, int64_t K, double T2, double *r2, float *r2f,
+                           uint32_t *mask) {
+	if (K <= 0) return PXB_OK;
+	const int t = ctx->pts.type;
+	if (r2f) {
+		switch (t) {
+		case PXB_MODEL_HOMOGRAPHY: return launch_rm_t<PXB_MODEL_HOMOGRAPHY, float>(ctx, models, K, T2, r2f, mask);
+		case PXB_MODEL_FUNDAMENTAL: return launch_rm_t<PXB_MODEL_FUNDAMENTAL, float>(ctx, models, K, T2, r2f, mask);
+		default: return launch_rm_t<PXB_MODEL_PNP, float>(ctx, models, K, T2, r2f, mask);
+		}
+	}
+	switch (t) {
+	case PXB_MODEL_HOMOGRAPHY: return launch_rm_t<PXB_MODEL_HOMOGRAPHY, double>(ctx, models, K, T2, r2, mask);
+	case PXB_MODEL_FUNDAMENTAL: return launch_rm_t<PXB_MODEL_FUNDAMENTAL, double>(ctx, models, K, T2, r2, mask);
+	default: return launch_rm_t<PXB_MODEL_PNP, double>(ctx, models, K, T2, r2, mask);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// a4: fused compound-aware MSAC score
+// ------------------------------------------------------------------------------------------------
+constexpr int kScChunk = 4096;                      // points per block (fixes the summation topology)
+constexpr int kScPointsPerThread = kScChunk / kThreads; // 16
+constexpr int kScHyps = 8;                          // hypotheses per block
+
+struct ScorePartial {
+	double value, shared;
+	long long count;
+};
+
+template <int TYPE>
+__global__ void __launch_bounds__(kThreads)
+    k_score_partial(const double *__restrict__ soa, int64_t stride, int64_t N, const double *__restrict__ models,
+                    int64_t K, double T2, const double *__restrict__ compound_pref, ScorePartial *__restrict__ partials,
+                    int nchunks) {
+	constexpr int DIM = ModelTraits<TYPE>::kDim, MS = ModelTraits<TYPE>::kSize;
+	__shared__ double s_models[kScHyps * MS];
+	__shared__ double s_v[kThreads / 32][kScHyps], s_s[kThreads / 32][kScHyps];
+	__shared__ int s_c[kThreads / 32][kScHyps];
+
+	const int64_t k0 = (int64_t)blockIdx.y * kScHyps;
+	const int nk = (int)min((int64_t)kScHyps, K - k0);
+	for (int t = threadIdx.x; t < kScHyps * MS; t += kThreads)
+		s_models[t] = (t < nk * MS) ? models[k0 * MS + t] : 0.0;
+	__syncthreads();
+
+	const int chunk = blockIdx.x;
+	double v[kScHyps], s[kScHyps];
+	int c[kScHyps];
+#pragma unroll
+	for (int h = 0; h < kScHyps; ++h) {
+		v[h] = 0.0;
+		s[h] = 0.0;
+		c[h] = 0;
+	}
+	const int64_t first = (int64_t)chunk * kScChunk + threadIdx.x;
+	for (int j = 0; j < kScPointsPerThread; ++j) {
+		const int64_t i = first + (int64_t)j * kThreads;
+		if (i >= N) break;
+		double p[5];
+		load_point<DIM>(soa, stride, i, p);
+		const double cp = compound_pref ? __ldg(compound_pref + i) : 0.0;
+#pragma unroll
+		for (int h = 0; h < kScHyps; ++h) {
+			const double r2 = squared_residual<TYPE>(p, s_models + h * MS);
+			if (r2 < T2) { // scoring_function_with_compound_model.h:85-102
+				c[h]++;
+				const double sv = cv_max(0.0, sub(1.0, divd(r2, T2)));
+				v[h] = add(v[h], sv);
+				if (compound_pref) s[h] = add(s[h], cv_min(cp, sv)); // :115-117 (pref is 0 off the inlier set)
+			}
+		}
+	}
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+	for (int h = 0; h < kScHyps; ++h) {
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) {
+			v[h] = add(v[h], __shfl_xor_sync(0xffffffffu, v[h], o));
+			s[h] = add(s[h], __shfl_xor_sync(0xffffffffu, s[h], o));
+			c[h] += __shfl_xor_sync(0xffffffffu, c[h], o);
+		}
+		if (lane == 0) {
+			s_v[warp][h] = v[h];
+			s_s[warp][h] = s[h];
+			s_c[warp][h] = c[h];
+		}
+	}
+	__syncthreads();
+	if (threadIdx.x < nk) {
+		const int h = threadIdx.x;
+		double vv = 0.0, ss = 0.0;
+		long long cc = 0;
+		for (int w = 0; w < kThreads / 32; ++w) {
+			vv = add(vv, s_v[w][h]);
+			ss = add(ss, s_s[w][h]);
+			cc += s_c[w][h];
+		}
+		ScorePartial out;
+		out.value = vv;
+		out.shared = ss;
+		out.count = cc;
+		partials[(k0 + h) * nchunks + chunk] = out;
+	}
+}
+
+__global__ void k_score_finalize(const ScorePartial *__restrict__ partials, int64_t K, int nchunks,
+                                 int64_t *__restrict__ count, double *__restrict__ value, double *__restrict__ shared) {
+	const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= K) return;
+	double v = 0.0, s = 0.0;
+	long long c = 0;
+	for (int j = 0; j < nchunks; ++j) {
+		const ScorePartial p = partials[k * nchunks + j];
+		v = add(v, p.value);
+		s = add(s, p.shared);
+		c += p.count;
+	}
+	count[k] = c;
+	value[k] = v;
+	shared[k] = s;
+}
+
+int launch_score_compound(pxb_ctx *ctx, const double *models, int64_t K, double T2, const double *compound_pref,
+                          int64_t *count, double *value_sum, double *shared) {
+	if (K <= 0) return PXB_OK;
+	const Points &p = ctx->pts;
+	const int nchunks = (int)((p.N + kScChunk - 1) / kScChunk);
+	PXB_TRY(ctx->partials.reserve(sizeof(ScorePartial) * (size_t)K * nchunks));
+	ScorePartial *part = ctx->partials.as<ScorePartial>();
+	int64_t done = 0;
+	while (done < K) {
+		const int64_t kk = std::min<int64_t>(K - done, (int64_t)65535 * kScHyps);
+		dim3 grid((unsigned)nchunks, (unsigned)((kk + kScHyps - 1) / kScHyps));
+		const double *m;
+		ScorePartial *pp = part + done * nchunks;
+		switch (p.type) {
+		case PXB_MODEL_HOMOGRAPHY:
+			m = models + done * 9;
+			k_score_partial<PXB_MODEL_HOMOGRAPHY><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, m, kk, T2,
+			                                                                          compound_pref, pp, nchunks);
+			break;
+		case PXB_MODEL_FUNDAMENTAL:
+			m = models + done * 9;
+			k_score_partial<PXB_MODEL_FUNDAMENTAL><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, m, kk, T2,
+			                                                                           compound_pref, pp, nchunks);
+			break;
+		default:
+			m = models + done * 12;
+			k_score_partial<PXB_MODEL_PNP><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, m, kk, T2,
+			                                                                   compound_pref, pp, nchunks);
+			break;
+		}
+		ctx->launches++;
+		done += kk;
+	}
+	k_score_finalize<<<(unsigned)((K + 127) / 128), 128, 0, ctx->stream>>>(part, K, nchunks, count, value_sum, shared);
+	ctx->launches++;
+	PXB_CUDA(cudaGetLastError());
+	return PXB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// a5: preference vector, tanimoto, compound max
+// ------------------------------------------------------------------------------------------------
+template <int TYPE>
+__global__ void k_preference(const double *__restrict__ soa, int64_t stride, int64_t N, const double *__restrict__ model,
+                             double T, double *__restrict__ pref) {
+	constexpr int DIM = ModelTraits<TYPE>::kDim, MS = ModelTraits<TYPE>::kSize;
+	__shared__ double m[MS];
+	if (threadIdx.x < MS) m[threadIdx.x] = model[threadIdx.x];
+	__syncthreads();
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= N) return;
+	double p[5];
+	load_point<DIM>(soa, stride, i, p);
+	const double r2 = squared_residual<TYPE>(p, m);
+	pref[i] = cv_max(0.0, sub(1.0, divd(r2, T))); // progx_model.h:84-85
+}
+
+int launch_preference(pxb_ctx *ctx, const double *model, double T, double *pref) {
+	const Points &p = ctx->pts;
+	const unsigned grid = (unsigned)((p.N + kThreads - 1) / kThreads);
+	switch (p.type) {
+	case PXB_MODEL_HOMOGRAPHY:
+		k_preference<PXB_MODEL_HOMOGRAPHY><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, model, T, pref);
+		break;
+	case PXB_MODEL_FUNDAMENTAL:
+		k_preference<PXB_MODEL_FUNDAMENTAL><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, model, T, pref);
+		break;
+	default:
+		k_preference<PXB_MODEL_PNP><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, model, T, pref);
+		break;
+	}
+	ctx->launches++;
+	PXB_CUDA(cudaGetLastError());
+	return PXB_OK;
+}
+
+constexpr int kOneBlock = 1024;
+
+// block-wide sum with the fixed topology (strided thread partials -> xor butterfly -> warps in order)
+__device__ __forceinline__ double block_sum_1024(double x, double *s_tmp /*32*/) {
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) x = add(x, __shfl_xor_sync(0xffffffffu, x, o));
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	__syncthreads();
+	if (lane == 0) s_tmp[warp] = x;
+	__syncthreads();
+	double t = 0.0;
+	for (int w = 0; w < kOneBlock / 32; ++w) t = add(t, s_tmp[w]);
+	return t;
+}
+
+__global__ void __launch_bounds__(kOneBlock)
+    k_tanimoto(const double *__restrict__ a, const double *__restrict__ b, int64_t N, double *__restrict__ out3) {
+	__shared__ double s_tmp[32];
+	double d = 0.0, na = 0.0, nb = 0.0;
+	for (int64_t i = threadIdx.x; i < N; i += kOneBlock) {
+		const double x = a[i], y = b[i];
+		d = add(d, mul(x, y));
+		na = add(na, mul(x, x));
+		nb = add(nb, mul(y, y));
+	}
+	d = block_sum_1024(d, s_tmp);
+	na = block_sum_1024(na, s_tmp);
+	nb = block_sum_1024(nb, s_tmp);
+	if (threadIdx.x == 0) {
+		out3[0] = d;
+		out3[1] = na;
+		out3[2] = nb;
+	}
+}
+
+int launch_tanimoto(pxb_ctx *ctx, const double *a, const double *b, int64_t N, double *out3) {
+	k_tanimoto<<<1, kOneBlock, 0, ctx->stream>>>(a, b, N, out3);
+	ctx->launches++;
+	PXB_CUDA(cudaGetLastError());
+	return PXB_OK;
+}
+
+__global__ void k_compound_max(const double *__restrict__ prefs, int64_t L, int64_t N, double *__restrict__ out) {
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= N) return;
+	double m = 0.0; // progressive_x.h:604 setConstant(0)
+	for (int64_t k = 0; k < L; ++k) m = cv_max(m, prefs[k * N + i]);
+	out[i] = m;
+}
+
+int launch_compound_max(pxb_ctx *ctx, const double *prefs, int64_t L, int64_t N, double *out) {
+	k_compound_max<<<(unsigned)((N + kThreads - 1) / kThreads), kThreads, 0, ctx->stream>>>(prefs, L, N, out);
+	ctx->launches++;
+	PXB_CUDA(cudaGetLastError());
+	return PXB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// a9: PEARL data-cost matrix, D[i*(L+1) + l]
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxLabels = 64; // the reference never exceeds 11 (outer loop cap 10, progressive_x.h:272)
+
+template <int TYPE>
+__global__ void k_pearl_datacost(const double *__restrict__ soa, int64_t stride, int64_t N,
+                                 const double *__restrict__ models, int L, double T, double one_minus,
+                                 double *__restrict__ D) {
+	constexpr int DIM = ModelTraits<TYPE>::kDim, MS = ModelTraits<TYPE>::kSize;
+	extern __shared__ double s_m[];
+	for (int t = threadIdx.x; t < L * MS; t += blockDim.x) s_m[t] = models[t];
+	__syncthreads();
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= N) return;
+	double p[5];
+	load_point<DIM>(soa, stride, i, p);
+	double *row = D + i * (L + 1);
+	const double two = mul(2.0, one_minus);
+	for (int l = 0; l < L; ++l) {
+		const double r2 = squared_residual<TYPE>(p, s_m + l * MS);
+		// PEARL.h:123-127: r2 > T -> 2(1-lambda); else (1-lambda) * r2 / T  (left-to-right)
+		row[l] = (r2 > T) ? two : divd(mul(one_minus, r2), T);
+	}
+	row[L] = one_minus; // PEARL.h:100-101
+}
+
+int launch_pearl_datacost(pxb_ctx *ctx, const double *models, int64_t L, double thr, double lambda, double *D) {
+	const Points &p = ctx->pts;
+	if (L > kMaxLabels) {
+		set_error("too many labels (%lld > %d)", (long long)L, kMaxLabels);
+		return PXB_ERR_ARGUMENT;
+	}
+	const double T = 9.0 / 4.0 * thr * thr; // PEARL.h:51 spelling
+	const double one_minus = 1.0 - lambda;
+	const unsigned grid = (unsigned)((p.N + kThreads - 1) / kThreads);
+	const size_t smem = sizeof(double) * (size_t)std::max<int64_t>(L, 1) * model_size(p.type);
+	switch (p.type) {
+	case PXB_MODEL_HOMOGRAPHY:
+		k_pearl_datacost<PXB_MODEL_HOMOGRAPHY><<<grid, kThreads, smem, ctx->stream>>>(p.soa, p.stride, p.N, models,
+		                                                                              (int)L, T, one_minus, D);
+		break;
+	case PXB_MODEL_FUNDAMENTAL:
+		k_pearl_datacost<PXB_MODEL_FUNDAMENTAL><<<grid, kThreads, smem, ctx->stream>>>(p.soa, p.stride, p.N, models,
+		                                                                               (int)L, T, one_minus, D);
+		break;
+	default:
+		k_pearl_datacost<PXB_MODEL_PNP><<<grid, kThreads, smem, ctx->stream>>>(p.soa, p.stride, p.N, models, (int)L, T,
+		                                                                       one_minus, D);
+		break;
+	}
+	ctx->launches++;
+	PXB_CUDA(cudaGetLastError());
+	return PXB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// a12: per-instance residual sums (one block per instance, fixed topology)
+// ------------------------------------------------------------------------------------------------
+template <int TYPE>
+__global__ void __launch_bounds__(kOneBlock)
+    k_segment_sums(const double *__restrict__ soa, int64_t stride, int64_t N, const double *__restrict__ models,
+                   const int32_t *__restrict__ labels, double *__restrict__ sums, int64_t *__restrict__ counts) {
+	constexpr int DIM = ModelTraits<TYPE>::kDim, MS = ModelTraits<TYPE>::kSize;
+	__shared__ double m[MS];
+	__shared__ double s_tmp[32];
+	__shared__ int s_cnt[32];
+	const int l = blockIdx.x;
+	if (threadIdx.x < MS) m[threadIdx.x] = models[l * MS + threadIdx.x];
+	__syncthreads();
+	double acc = 0.0;
+	int cnt = 0;
+	for (int64_t i = threadIdx.x; i < N; i += kOneBlock) {
+		if (labels[i] != l) continue;
+		double p[5];
+		load_point<DIM>(soa, stride, i, p);
+		acc = add(acc, __dsqrt_rn(squared_residual<TYPE>(p, m))); // Estimator::residual = sqrt(squaredResidual)
+		cnt++;
+	}
+	acc = block_sum_1024(acc, s_tmp);
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+	if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cnt;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		long long c = 0;
+		for (int w = 0; w < kOneBlock / 32; ++w) c += s_cnt[w];
+		sums[l] = acc;
+		counts[l] = c;
+	}
+}
+
+int launch_segment_sums(pxb_ctx *ctx, const double *models, int64_t L, const int32_t *labels, double *sums,
+                        int64_t *counts) {
+	if (L <= 0) return PXB_OK;
+	const Points &p = ctx->pts;
+	switch (p.type) {
+	case PXB_MODEL_HOMOGRAPHY:
+		k_segment_sums<PXB_MODEL_HOMOGRAPHY><<<(unsigned)L, kOneBlock, 0, ctx->stream>>>(p.soa, p.stride, p.N, models,
+		                                                                                 labels, sums, counts);
+		break;
+	case PXB_MODEL_FUNDAMENTAL:
+		k_segment_sums<PXB_MODEL_FUNDAMENTAL><<<(unsigned)L, kOneBlock, 0, ctx->stream>>>(p.soa, p.stride, p.N, models,
+		                                                                                  labels, sums, counts);
+		break;
+	default:
+		k_segment_sums<PXB_MODEL_PNP><<<(unsigned)L, kOneBlock, 0, ctx->stream>>>(p.soa, p.stride, p.N, models, labels,
+		                                                                          sums, counts);
+		break;
+	}
+	ctx->launches++;
+	PXB_CUDA(cudaGetLastError());
+	return PXB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// a13: GC-RANSAC local-optimisation unary terms and Tukey weights
+// ------------------------------------------------------------------------------------------------
+template <int TYPE>
+__global__ void k_lo_unary(const double *__restrict__ soa, int64_t stride, int64_t N, const double *__restrict__ model,
+                           double T, double one_minus, double *__restrict__ d, double *__restrict__ e0,
+                           double *__restrict__ e1) {
+	constexpr int DIM = ModelTraits<TYPE>::kDim, MS = ModelTraits<TYPE>::kSize;
+	__shared__ double m[MS];
+	if (threadIdx.x < MS) m[threadIdx.x] = model[threadIdx.x];
+	__syncthreads();
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= N) return;
+	double p[5];
+	load_point<DIM>(soa, stride, i, p);
+	const double r2 = squared_residual<TYPE>(p, m);
+	// std::clamp(v, 0.0, 1.0): (v < lo) ? lo : (hi < v) ? hi : v   -- NaN passes through
+	const double q = divd(r2, T);
+	const double dist = (q < 0.0) ? 0.0 : ((1.0 < q) ? 1.0 : q);
+	const double tmp = sub(1.0, dist);
+	d[i] = dist;
+	if (r2 <= T) { // GCRANSAC.h:958-961
+		e0[i] = mul(one_minus, tmp);
+		e1[i] = 0.0;
+	} else {
+		e0[i] = 0.0;
+		e1[i] = mul(one_minus, sub(1.0, tmp));
+	}
+}
+
+int launch_lo_unary(pxb_ctx *ctx, const double *model, double thr, double lambda, double *d, double *e0, double *e1) {
+	const Points &p = ctx->pts;
+	const double T = thr * thr * 9 / 4; // GCRANSAC.h:942 spelling
+	const double one_minus = 1.0 - lambda;
+	const unsigned grid = (unsigned)((p.N + kThreads - 1) / kThreads);
+	switch (p.type) {
+	case PXB_MODEL_HOMOGRAPHY:
+		k_lo_unary<PXB_MODEL_HOMOGRAPHY><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, model, T, one_minus,
+		                                                                     d, e0, e1);
+		break;
+	case PXB_MODEL_FUNDAMENTAL:
+		k_lo_unary<PXB_MODEL_FUNDAMENTAL><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, model, T, one_minus,
+		                                                                      d, e0, e1);
+		break;
+	default:
+		k_lo_unary<PXB_MODEL_PNP><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, model, T, one_minus, d, e0,
+		                                                              e1);
+		break;
+	}
+	ctx->launches++;
+	PXB_CUDA(cudaGetLastError());
+	return PXB_OK;
+}
+
+template <int TYPE>
+__global__ void k_tukey(const double *__restrict__ soa, int64_t stride, int64_t N, const double *__restrict__ model,
+                        double T2, double *__restrict__ w) {
+	constexpr int DIM = ModelTraits<TYPE>::kDim, MS = ModelTraits<TYPE>::kSize;
+	__shared__ double m[MS];
+	if (threadIdx.x < MS) m[threadIdx.x] = model[threadIdx.x];
+	__syncthreads();
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= N) return;
+	double p[5];
+	load_point<DIM>(soa, stride, i, p);
+	const double r2 = squared_residual<TYPE>(p, m);
+	const double t = cv_max(0.0, sub(1.0, divd(r2, T2))); // GCRANSAC.h:667-668
+	w[i] = mul(t, t);
+}
+
+int launch_tukey(pxb_ctx *ctx, const double *model, double T2, double *w) {
+	const Points &p = ctx->pts;
+	const unsigned grid = (unsigned)((p.N + kThreads - 1) / kThreads);
+	switch (p.type) {
+	case PXB_MODEL_HOMOGRAPHY:
+		k_tukey<PXB_MODEL_HOMOGRAPHY><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, model, T2, w);
+		break;
+	case PXB_MODEL_FUNDAMENTAL:
+		k_tukey<PXB_MODEL_FUNDAMENTAL><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, model, T2, w);
+		break;
+	default:
+		k_tukey<PXB_MODEL_PNP><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, model, T2, w);
+		break;
+	}
+	ctx->launches++;
+	PXB_CUDA(cudaGetLastError());
+	return PXB_OK;
+}
+
+} // namespace pxb
+
+// ------------------------------------------------------------------------------------------------
+// self-test: dual_div() against __ddiv_rn on pseudo-random operands (count of mismatching bit patterns)
+// ------------------------------------------------------------------------------------------------
+namespace pxb {
+__device__ __forceinline__ uint64_t splitmix64(uint64_t &x) {
+	uint64_t z = (x += 0x9E3779B97F4A7C15ull);
+	z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+	z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+	return z ^ (z >> 31);
+}
+__global__ void k_selftest_division(uint64_t seed, int iters, int mode, unsigned long long *mismatches) {
+	uint64_t s = seed + 0x1234567ull * ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x + 1);
+	unsigned long long bad = 0;
+	for (int it = 0; it < iters; ++it) {
+		double a1, a2, b;
+		if (mode == 0) { // arbitrary bit patterns (incl. NaN, inf, denormals)
+			a1 = __longlong_as_double((long long)splitmix64(s));
+			a2 = __longlong_as_double((long long)splitmix64(s));
+			b = __longlong_as_double((long long)splitmix64(s));
+		} else { // magnitudes typical for the residual kernels: |x| in [2^-20, 2^20], random sign
+			auto gen = [&]() {
+				const uint64_t r = splitmix64(s);
+				const int e = (int)(r % 41) - 20;
+				const double m = 1.0 + (double)((r >> 11) & ((1ull << 52) - 1)) * (1.0 / 4503599627370496.0);
+				return ((r >> 63) ? -1.0 : 1.0) * ldexp(m, e);
+			};
+			a1 = gen();
+			a2 = gen();
+			b = gen();
+		}
+		double q1, q2;
+		dual_div(a1, a2, b, q1, q2);
+		const double r1 = __ddiv_rn(a1, b), r2 = __ddiv_rn(a2, b);
+		const bool ok1 = (__double_as_longlong(q1) == __double_as_longlong(r1)) || (q1 != q1 && r1 != r1);
+		const bool ok2 = (__double_as_longlong(q2) == __double_as_longlong(r2)) || (q2 != q2 && r2 != r2);
+		bad += (ok1 ? 0 : 1) + (ok2 ? 0 : 1);
+	}
+	if (bad) atomicAdd(mismatches, bad);
+}
+} // namespace pxb
+
+extern "C" int pxb_selftest_division(pxb_ctx *ctx, uint64_t seed, int64_t n_triples, int mode, int64_t *mismatches) {
+	using namespace pxb;
+	PXB_CHECK_ARG(ctx && mismatches && n_triples > 0, "null argument");
+	PXB_TRY(ctx->outA.reserve(sizeof(unsigned long long)));
+	PXB_CUDA(cudaMemsetAsync(ctx->outA.ptr, 0, sizeof(unsigned long long), ctx->stream));
+	const int threads = 256, blocks = 148 * 8;
+	const int iters = (int)((n_triples + (int64_t)threads * blocks - 1) / ((int64_t)threads * blocks));
+	k_selftest_division<<<blocks, threads, 0, ctx->stream>>>(seed, iters, mode, ctx->outA.as<unsigned long long>());
+	ctx->launches++;
+	PXB_CUDA(cudaGetLastError());
+	unsigned long long bad = 0;
+	PXB_CUDA(cudaMemcpyAsync(&bad, ctx->outA.ptr, sizeof(bad), cudaMemcpyDeviceToHost, ctx->stream));
+	PXB_CUDA(cudaStreamSynchronize(ctx->stream));
+	*mismatches = (int64_t)bad;
+	return PXB_OK;
+}

@@ -1,0 +1,104 @@
+"""pyprogressivex -- drop-in Python surface of danini/progressive-x backed by libpxb200.so (B200, sm_100a).
+
+Same function names, positional order, keyword names and defaults as the reference's pybind11 module
+(src/pyprogressivex/src/bindings.cpp:410-491); same return convention `(models, labeling)` with models stacked
+as float64 [M*3, 3] (homographies / fundamental matrices) or [M*3, 4] (poses) and labeling as int32 [N]
+(bindings.cpp:152-165). `findFundamentalMatrices` is an alias of `findTwoViewMotions` (the reference only has the
+latter name). One extra keyword everywhere: `seed` (the reference seeds from std::random_device and cannot be
+reproduced; 0 keeps that behaviour), and `device`.
+
+All compute runs through the C ABI in include/pxb200.h; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as _C
+
+import numpy as _np
+
+from . import _native
+from ._native import Context, PxbError  # noqa: F401
+
+__all__ = ["findHomographies", "findTwoViewMotions", "findFundamentalMatrices", "find6DPoses", "Context"]
+
+_contexts = {}
+
+
+def _ctx(device: int) -> Context:
+    if device not in _contexts:
+        _contexts[device] = Context(device)
+    return _contexts[device]
+
+
+def _two_view(fn_name, corrs, w1, h1, w2, h2, threshold, conf, spatial_coherence_weight, neighborhood_ball_radius,
+              maximum_tanimoto_similarity, max_iters, minimum_point_number, maximum_model_number, sampler_id,
+              scoring_exponent, do_logging, seed, device):
+    corrs = _np.ascontiguousarray(corrs, dtype=_np.float64)
+    # bindings.cpp:119-124 / :26-50: shape checks raise std::invalid_argument -> ValueError in Python
+    if corrs.ndim != 2 or corrs.shape[1] != 4:
+        raise ValueError("corrs should be an array with dims [n,4], n>=4")
+    if corrs.shape[0] < 4:
+        raise ValueError("corrs should be an array with dims [n,4], n>=4")
+    ctx = _ctx(device)
+    N = corrs.shape[0]
+    labeling = _np.zeros(N, dtype=_np.int64)
+    cap = 16
+    models = _np.zeros((cap, 9), dtype=_np.float64)
+    fn = getattr(ctx.lib, fn_name)
+    rc = fn(ctx.handle, corrs.ctypes.data_as(_C.c_void_p), N, labeling.ctypes.data_as(_C.c_void_p),
+            models.ctypes.data_as(_C.c_void_p), cap, int(w1), int(h1), int(w2), int(h2),
+            float(spatial_coherence_weight), float(threshold), float(conf), float(neighborhood_ball_radius),
+            float(maximum_tanimoto_similarity), int(max_iters), int(minimum_point_number), int(maximum_model_number),
+            int(sampler_id), float(scoring_exponent), int(bool(do_logging)), int(seed))
+    M = _native._check(rc)
+    return models[:M].reshape(M * 3, 3).copy(), labeling.astype(_np.int32)
+
+
+def findHomographies(corrs, w1, h1, w2, h2, threshold=4.0, conf=0.5, spatial_coherence_weight=0.0,
+                     neighborhood_ball_radius=200.0, maximum_tanimoto_similarity=0.4, max_iters=1000,
+                     minimum_point_number=10, maximum_model_number=-1, sampler_id=3, scoring_exponent=2,
+                     do_logging=False, seed=0, device=0):
+    """bindings.cpp:99-168 / :410-426 -> findHomographies_ (progressivex_python.cpp:173-304)."""
+    return _two_view("pxb_find_homographies", corrs, w1, h1, w2, h2, threshold, conf, spatial_coherence_weight,
+                     neighborhood_ball_radius, maximum_tanimoto_similarity, max_iters, minimum_point_number,
+                     maximum_model_number, sampler_id, scoring_exponent, do_logging, seed, device)
+
+
+def findTwoViewMotions(corrs, w1, h1, w2, h2, threshold=4.0, conf=0.5, spatial_coherence_weight=0.0,
+                       neighborhood_ball_radius=200.0, maximum_tanimoto_similarity=0.4, max_iters=1000,
+                       minimum_point_number=10, maximum_model_number=-1, sampler_id=3, scoring_exponent=3,
+                       do_logging=False, seed=0, device=0):
+    """bindings.cpp:324-393 / :444-460 -> findTwoViewMotions_ (progressivex_python.cpp:535-666)."""
+    return _two_view("pxb_find_two_view_motions", corrs, w1, h1, w2, h2, threshold, conf, spatial_coherence_weight,
+                     neighborhood_ball_radius, maximum_tanimoto_similarity, max_iters, minimum_point_number,
+                     maximum_model_number, sampler_id, scoring_exponent, do_logging, seed, device)
+
+
+findFundamentalMatrices = findTwoViewMotions
+
+
+def find6DPoses(x1y1, x2y2z2, K, threshold=4.0, conf=0.90, spatial_coherence_weight=0.1,
+                neighborhood_ball_radius=20.0, maximum_tanimoto_similarity=0.9, max_iters=400,
+                minimum_point_number=2 * 3, maximum_model_number=-1, seed=0, device=0):
+    """bindings.cpp:9-97 / :462-473 -> find6DPoses_ (progressivex_python.cpp:41-171)."""
+    x1y1 = _np.ascontiguousarray(x1y1, dtype=_np.float64)
+    xyz = _np.ascontiguousarray(x2y2z2, dtype=_np.float64)
+    Km = _np.ascontiguousarray(K, dtype=_np.float64)
+    if x1y1.ndim != 2 or x1y1.shape[1] != 2 or x1y1.shape[0] < 3:
+        raise ValueError("x1y1 should be an array with dims [n,2], n>=3")
+    if xyz.ndim != 2 or xyz.shape[1] != 3 or xyz.shape[0] != x1y1.shape[0]:
+        raise ValueError("x2y2z2 should be an array with dims [n,3], n>=3")
+    if Km.shape != (3, 3):
+        raise ValueError("K should be an array with dims [3,3]")
+    ctx = _ctx(device)
+    N = x1y1.shape[0]
+    labeling = _np.zeros(N, dtype=_np.int64)
+    cap = 16
+    poses = _np.zeros((cap, 12), dtype=_np.float64)
+    rc = ctx.lib.pxb_find_6d_poses(ctx.handle, x1y1.ctypes.data_as(_C.c_void_p), xyz.ctypes.data_as(_C.c_void_p),
+                                   Km.ctypes.data_as(_C.c_void_p), N, labeling.ctypes.data_as(_C.c_void_p),
+                                   poses.ctypes.data_as(_C.c_void_p), cap, float(spatial_coherence_weight),
+                                   float(threshold), float(conf), float(neighborhood_ball_radius),
+                                   float(maximum_tanimoto_similarity), int(max_iters), int(minimum_point_number),
+                                   int(maximum_model_number), int(seed))
+    M = _native._check(rc)
+    return poses[:M].reshape(M * 3, 4).copy(), labeling.astype(_np.int32)

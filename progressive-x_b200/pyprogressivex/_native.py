@@ -1,0 +1,289 @@
+"""ctypes binding of libpxb200.so (the C ABI declared in include/pxb200.h).
+
+This is the only place Python touches the native library. There is no CPU fallback: if the shared library is
+missing, or no sm_100 device is visible, every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+_PKG_ROOT = Path(__file__).resolve().parent.parent
+LIB_PATH = _PKG_ROOT / "libpxb200.so"
+
+MODEL_H, MODEL_F, MODEL_PNP = 0, 1, 2
+POINT_DIM = {MODEL_H: 4, MODEL_F: 4, MODEL_PNP: 5}
+MODEL_SIZE = {MODEL_H: 9, MODEL_F: 9, MODEL_PNP: 12}
+SAMPLE_SIZE = {MODEL_H: 4, MODEL_F: 7, MODEL_PNP: 3}
+MAX_SOLUTIONS = {MODEL_H: 1, MODEL_F: 3, MODEL_PNP: 4}
+
+
+class PxbError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"libpxb200 error {status}: {message}")
+        self.status = status
+
+
+_lib = None
+
+
+def _p(dtype):
+    return np.ctypeslib.ndpointer(dtype=dtype, flags="C_CONTIGUOUS")
+
+
+def load_library() -> C.CDLL:
+    """Load libpxb200.so and declare every prototype of include/pxb200.h. Raises if the library is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(str(LIB_PATH))
+    vp, i64, i32, f64, sz, u64 = C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_size_t, C.c_uint64
+    lib.pxb_last_error.restype = C.c_char_p
+    lib.pxb_version.restype = C.c_char_p
+    lib.pxb_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+    lib.pxb_ctx_destroy.argtypes = [vp]
+    lib.pxb_ctx_destroy.restype = None
+    lib.pxb_ctx_stream.argtypes = [vp]
+    lib.pxb_ctx_stream.restype = vp
+    lib.pxb_sync.argtypes = [vp]
+    lib.pxb_launch_count.argtypes = [vp]
+    lib.pxb_launch_count.restype = i64
+    lib.pxb_dev_alloc.argtypes = [vp, sz, C.POINTER(vp)]
+    lib.pxb_dev_free.argtypes = [vp, vp]
+    lib.pxb_memcpy_h2d.argtypes = [vp, vp, vp, sz]
+    lib.pxb_memcpy_d2h.argtypes = [vp, vp, vp, sz]
+    lib.pxb_host_alloc_pinned.argtypes = [sz, C.POINTER(vp)]
+    lib.pxb_host_free_pinned.argtypes = [vp]
+    lib.pxb_upload_points.argtypes = [vp, C.c_int, vp, i64]
+    lib.pxb_point_count.argtypes = [vp]
+    lib.pxb_point_count.restype = i64
+    lib.pxb_residual_matrix.argtypes = [vp, vp, i64, f64, vp, vp]
+    lib.pxb_residual_matrix_dev.argtypes = [vp, vp, i64, f64, vp, vp]
+    lib.pxb_residual_matrix_f32_dev.argtypes = [vp, vp, i64, f64, vp, vp]
+    lib.pxb_score_compound.argtypes = [vp, vp, i64, f64, vp, vp, vp, vp]
+    lib.pxb_score_compound_dev.argtypes = [vp, vp, i64, f64, vp, vp, vp, vp]
+    lib.pxb_inliers.argtypes = [vp, vp, f64, vp, C.POINTER(i64)]
+    lib.pxb_preference_vector.argtypes = [vp, vp, f64, vp]
+    lib.pxb_tanimoto.argtypes = [vp, vp, vp, i64, C.POINTER(f64)]
+    lib.pxb_compound_max.argtypes = [vp, vp, i64, i64, vp]
+    lib.pxb_solve_minimal.argtypes = [vp, vp, i64, vp, vp, vp, vp]
+    lib.pxb_pearl_datacost.argtypes = [vp, vp, i64, f64, f64, vp]
+    lib.pxb_pearl_label.argtypes = [vp, vp, i64, i32, f64, f64, vp, vp, vp, vp, C.POINTER(f64)]
+    lib.pxb_segment_residual_sums.argtypes = [vp, vp, i64, vp, vp, vp]
+    lib.pxb_lo_unary_terms.argtypes = [vp, vp, f64, f64, vp, vp, vp]
+    lib.pxb_tukey_weights.argtypes = [vp, vp, f64, vp]
+    lib.pxb_selftest_division.argtypes = [vp, u64, i64, C.c_int, C.POINTER(i64)]
+    lib.pxb_find_homographies.argtypes = [vp, vp, i64, vp, vp, i64, sz, sz, sz, sz, f64, f64, f64, f64, f64, sz, sz,
+                                          C.c_int, sz, f64, C.c_int, u64]
+    lib.pxb_find_two_view_motions.argtypes = lib.pxb_find_homographies.argtypes
+    lib.pxb_find_6d_poses.argtypes = [vp, vp, vp, vp, i64, vp, vp, i64, f64, f64, f64, f64, f64, sz, sz, C.c_int, u64]
+    _lib = lib
+    return lib
+
+
+def _check(rc: int):
+    if rc < 0:
+        raise PxbError(rc, load_library().pxb_last_error().decode("utf-8", "replace"))
+    return rc
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class DeviceBuffer:
+    """A raw device allocation owned by a Context (used by bench.py to keep the residual matrix resident)."""
+
+    def __init__(self, ctx: "Context", nbytes: int):
+        self.ctx, self.nbytes = ctx, int(nbytes)
+        p = C.c_void_p()
+        _check(ctx.lib.pxb_dev_alloc(ctx.handle, self.nbytes, C.byref(p)))
+        self.ptr = p.value
+
+    def upload(self, arr: np.ndarray):
+        arr = np.ascontiguousarray(arr)
+        assert arr.nbytes <= self.nbytes
+        _check(self.ctx.lib.pxb_memcpy_h2d(self.ctx.handle, self.ptr, _ptr(arr), arr.nbytes))
+
+    def download(self, dtype, count: int, offset_bytes: int = 0) -> np.ndarray:
+        out = np.empty(count, dtype=dtype)
+        _check(self.ctx.lib.pxb_memcpy_d2h(self.ctx.handle, _ptr(out), self.ptr + offset_bytes, out.nbytes))
+        return out
+
+    def free(self):
+        if self.ptr:
+            self.ctx.lib.pxb_dev_free(self.ctx.handle, self.ptr)
+            self.ptr = None
+
+
+class Context:
+    """One pxb_ctx: a device, a stream, the resident point set and scratch buffers."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        _check(self.lib.pxb_ctx_create(int(device), C.byref(h)))
+        self.handle = h
+        self.model_type = None
+        self.N = 0
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.pxb_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- plumbing ----------------------------------------------------------------------------------------
+    @property
+    def stream(self) -> int:
+        return self.lib.pxb_ctx_stream(self.handle)
+
+    def sync(self):
+        _check(self.lib.pxb_sync(self.handle))
+
+    def launch_count(self) -> int:
+        return int(self.lib.pxb_launch_count(self.handle))
+
+    def alloc(self, nbytes: int) -> DeviceBuffer:
+        return DeviceBuffer(self, nbytes)
+
+    # -- data --------------------------------------------------------------------------------------------
+    def upload_points(self, model_type: int, pts) -> None:
+        pts = _f64(pts)
+        if pts.ndim != 2 or pts.shape[1] != POINT_DIM[model_type]:
+            raise ValueError(f"points must be [N, {POINT_DIM[model_type]}]")
+        _check(self.lib.pxb_upload_points(self.handle, model_type, _ptr(pts), pts.shape[0]))
+        self.model_type, self.N = model_type, pts.shape[0]
+
+    def _models(self, models):
+        ms = MODEL_SIZE[self.model_type]
+        m = _f64(models).reshape(-1, ms)
+        return m, m.shape[0]
+
+    # -- a1/a2/a3 ------------------------------------------------------------------------------------------
+    def residual_matrix(self, models, T2: float, want_r2=True, want_mask=True):
+        m, K = self._models(models)
+        words = (self.N + 31) // 32
+        r2 = np.empty((K, self.N), dtype=np.float64) if want_r2 else None
+        mask = np.empty((K, words), dtype=np.uint32) if want_mask else None
+        _check(self.lib.pxb_residual_matrix(self.handle, _ptr(m), K, float(T2), _ptr(r2), _ptr(mask)))
+        return r2, mask
+
+    # -- a4 ------------------------------------------------------------------------------------------------
+    def score_compound(self, models, T2: float, compound_pref=None):
+        m, K = self._models(models)
+        cp = None if compound_pref is None else _f64(compound_pref)
+        count = np.empty(K, dtype=np.int64)
+        value = np.empty(K, dtype=np.float64)
+        shared = np.empty(K, dtype=np.float64)
+        _check(self.lib.pxb_score_compound(self.handle, _ptr(m), K, float(T2), _ptr(cp), _ptr(count), _ptr(value),
+                                           _ptr(shared)))
+        return count, value, shared
+
+    def inliers(self, model, T2: float) -> np.ndarray:
+        m, _ = self._models(model)
+        out = np.empty(self.N, dtype=np.int64)
+        n = C.c_int64()
+        _check(self.lib.pxb_inliers(self.handle, _ptr(m), float(T2), _ptr(out), C.byref(n)))
+        return out[: n.value].copy()
+
+    # -- a5 ------------------------------------------------------------------------------------------------
+    def preference_vector(self, model, T: float) -> np.ndarray:
+        m, _ = self._models(model)
+        out = np.empty(self.N, dtype=np.float64)
+        _check(self.lib.pxb_preference_vector(self.handle, _ptr(m), float(T), _ptr(out)))
+        return out
+
+    def tanimoto(self, a, b) -> float:
+        a, b = _f64(a), _f64(b)
+        s = C.c_double()
+        _check(self.lib.pxb_tanimoto(self.handle, _ptr(a), _ptr(b), a.shape[0], C.byref(s)))
+        return s.value
+
+    def compound_max(self, prefs) -> np.ndarray:
+        prefs = _f64(prefs)
+        L, N = prefs.shape
+        out = np.empty(N, dtype=np.float64)
+        _check(self.lib.pxb_compound_max(self.handle, _ptr(prefs), L, N, _ptr(out)))
+        return out
+
+    # -- a6/a7/a8 ------------------------------------------------------------------------------------------
+    def solve_minimal(self, samples):
+        t = self.model_type
+        s = np.ascontiguousarray(samples, dtype=np.int64).reshape(-1, SAMPLE_SIZE[t])
+        K = s.shape[0]
+        models = np.zeros((K, MAX_SOLUTIONS[t], MODEL_SIZE[t]), dtype=np.float64)
+        n = np.zeros(K, dtype=np.int32)
+        sv = np.zeros(K, dtype=np.uint8)
+        mv = np.zeros(K, dtype=np.uint8)
+        _check(self.lib.pxb_solve_minimal(self.handle, _ptr(s), K, _ptr(models), _ptr(n), _ptr(sv), _ptr(mv)))
+        return models, n, sv, mv
+
+    # -- a9..a12 -------------------------------------------------------------------------------------------
+    def pearl_datacost(self, models, thr: float, lam: float) -> np.ndarray:
+        m, L = self._models(models)
+        D = np.empty((self.N, L + 1), dtype=np.float64)
+        _check(self.lib.pxb_pearl_datacost(self.handle, _ptr(m), L, float(thr), float(lam), _ptr(D)))
+        return D
+
+    def pearl_label(self, D, lam: float, label_cost: float, csr_off=None, csr_idx=None, init_labels=None):
+        D = _f64(D)
+        N, L1 = D.shape
+        off = None if csr_off is None else np.ascontiguousarray(csr_off, dtype=np.int32)
+        idx = None if csr_idx is None else np.ascontiguousarray(csr_idx, dtype=np.int32)
+        init = None if init_labels is None else np.ascontiguousarray(init_labels, dtype=np.int32)
+        labels = np.empty(N, dtype=np.int32)
+        e = C.c_double()
+        _check(self.lib.pxb_pearl_label(self.handle, _ptr(D), N, L1, float(lam), float(label_cost), _ptr(off),
+                                        _ptr(idx), _ptr(init), _ptr(labels), C.byref(e)))
+        return labels, e.value
+
+    def segment_residual_sums(self, models, labels):
+        m, L = self._models(models)
+        lab = np.ascontiguousarray(labels, dtype=np.int32)
+        sums = np.zeros(L, dtype=np.float64)
+        counts = np.zeros(L, dtype=np.int64)
+        _check(self.lib.pxb_segment_residual_sums(self.handle, _ptr(m), L, _ptr(lab), _ptr(sums), _ptr(counts)))
+        return sums, counts
+
+    # -- a13 -----------------------------------------------------------------------------------------------
+    def lo_unary_terms(self, model, thr: float, lam: float):
+        m, _ = self._models(model)
+        d = np.empty(self.N)
+        e0 = np.empty(self.N)
+        e1 = np.empty(self.N)
+        _check(self.lib.pxb_lo_unary_terms(self.handle, _ptr(m), float(thr), float(lam), _ptr(d), _ptr(e0), _ptr(e1)))
+        return d, e0, e1
+
+    def tukey_weights(self, model, T2: float) -> np.ndarray:
+        m, _ = self._models(model)
+        w = np.empty(self.N)
+        _check(self.lib.pxb_tukey_weights(self.handle, _ptr(m), float(T2), _ptr(w)))
+        return w
+
+    def selftest_division(self, seed: int, n: int, mode: int) -> int:
+        bad = C.c_int64()
+        _check(self.lib.pxb_selftest_division(self.handle, seed, n, mode, C.byref(bad)))
+        return bad.value

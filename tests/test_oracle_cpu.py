@@ -1,0 +1,106 @@
+"""CPU-only checks of the oracle itself: known-answer behaviour on planted structures, the restated greedy UFL
+against the REFERENCE's own gco-v3 build (oracle/_ref), and internal consistency between oracle entry points."""
+import numpy as np
+import pytest
+
+from pyprogressivex import synthetic as syn
+
+
+def test_h_residual_known_answer(oracle):
+    # identity homography: residual is the squared displacement
+    pts = np.array([[1.0, 2.0, 4.0, 6.0]])
+    H = np.eye(3).reshape(-1)
+    r2, mask = oracle.residual_matrix(0, pts, H, 26.0)
+    assert r2[0, 0] == 25.0 and mask[0, 0] == 1
+    r2, mask = oracle.residual_matrix(0, pts, H, 25.0)  # strict <
+    assert mask[0, 0] == 0
+
+
+def test_h4_recovers_planted_homography(oracle):
+    corrs, gt, Hs = syn.multi_homography_scene(500, n_planes=2, outlier_ratio=0.2, noise=0.0, seed=3)
+    idx = np.flatnonzero(gt == 0)[:4]
+    models, n, sv, mv = oracle.solve_minimal(0, corrs, idx[None, :])
+    assert n[0] == 1
+    H = models[0, 0].reshape(3, 3)
+    np.testing.assert_allclose(H, Hs[0], rtol=1e-6, atol=1e-8)
+    r2, _ = oracle.residual_matrix(0, corrs[gt == 0], H, 1.0)
+    assert r2.max() < 1e-12
+
+
+def test_f7_solutions_satisfy_epipolar_constraint(oracle):
+    corrs, gt, Fs = syn.multi_motion_scene(600, noise=0.0, seed=5)
+    S = syn.minimal_samples(gt, 50, 7, within_ratio=1.0, seed=5)
+    models, n, _, _ = oracle.solve_minimal(1, corrs, S)
+    assert n.sum() > 0
+    for k in range(50):
+        for j in range(n[k]):
+            F = models[k, j].reshape(3, 3)
+            assert abs(np.linalg.det(F)) < 1e-6 * max(1.0, np.abs(F).max() ** 3)
+            p = corrs[S[k]]
+            x1 = np.c_[p[:, :2], np.ones(7)]
+            x2 = np.c_[p[:, 2:], np.ones(7)]
+            err = np.abs(np.einsum("ni,ij,nj->n", x2, F, x1))
+            assert err.max() < 1e-6 * np.abs(F).max() * 1e6
+
+
+def test_p3p_recovers_planted_pose(oracle):
+    img, w, K, gt, poses = syn.multi_pose_scene(800, n_objects=3, inlier_ratio_each=0.2, noise_px=0.0, seed=6)
+    pts = syn.normalize_pnp_points(img, w, K)
+    idx = np.flatnonzero(gt == 1)[:3]
+    models, n, _, _ = oracle.solve_minimal(2, pts, idx[None, :])
+    assert n[0] >= 1
+    errs = [np.abs(models[0, j].reshape(3, 4) - poses[1]).max() for j in range(n[0])]
+    assert min(errs) < 1e-7
+
+
+def test_score_matches_residual_matrix(oracle):
+    corrs, gt, Hs = syn.multi_homography_scene(1500, seed=7)
+    T2 = 9.0
+    cp = np.random.default_rng(0).uniform(0, 1, 1500) * (gt == 1)
+    for k in range(3):
+        s = oracle.get_score(0, corrs, Hs[k].reshape(-1), T2, cp, 2)
+        r2, mask = oracle.residual_matrix(0, corrs, Hs[k].reshape(-1), T2)
+        inl = np.flatnonzero(r2[0] < T2)
+        assert s["count"] == inl.size and (s["inliers"] == inl).all()
+        bits = np.unpackbits(mask[0].view(np.uint8), bitorder="little")[:1500]
+        assert (np.flatnonzero(bits) == inl).all()
+        cnt, val, sh = oracle.score_batch(0, corrs, Hs[k].reshape(-1), T2, cp)
+        assert cnt[0] == s["count"] and val[0] == s["value_sum"] and sh[0] == s["shared"]
+        assert s["value"] == s["value_sum"] - s["shared"] ** 2
+
+
+def test_score_early_exit(oracle):
+    corrs, gt, Hs = syn.multi_homography_scene(1000, seed=8)
+    full = oracle.get_score(0, corrs, Hs[0].reshape(-1), 9.0)
+    # the reference returns Score() iff count + 1 < best.inlier_number (scoring_function_with_compound_model.h:105)
+    assert oracle.get_score(0, corrs, Hs[0].reshape(-1), 9.0, best_inlier_number=full["count"] + 1)["count"] == full["count"]
+    z = oracle.get_score(0, corrs, Hs[0].reshape(-1), 9.0, best_inlier_number=full["count"] + 2)
+    assert z["count"] == 0 and z["value"] == 0.0
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_restated_greedy_equals_reference_gco(oracle, seed):
+    if not oracle.have_gco_ref():
+        pytest.skip("oracle/_ref/libgco_ref.so not built (no /root/reference on this box)")
+    rng = np.random.default_rng(seed)
+    corrs, gt, Hs = syn.multi_homography_scene(2500, n_planes=4, seed=seed)
+    models = np.concatenate([Hs.reshape(-1, 9), Hs.reshape(-1, 9)[:2] + rng.normal(0, 1e-4, (2, 9))])
+    D = oracle.pearl_datacost(0, corrs, models, 2.0, 0.0)
+    for label_cost in (10.0, 400.0):
+        for init in (None, rng.integers(0, D.shape[1], D.shape[0])):
+            lab_ref, e_ref, _ = oracle.gco_pearl_label(D, 0.0, label_cost, init_labels=init)
+            lab, e = oracle.greedy_ufl(D, label_cost, init)
+            assert (lab == lab_ref).all()
+            assert e == e_ref
+
+
+def test_gco_ref_alpha_expansion_runs(oracle):
+    if not oracle.have_gco_ref():
+        pytest.skip("oracle/_ref/libgco_ref.so not built")
+    corrs, gt, Hs = syn.multi_homography_scene(800, n_planes=3, seed=11)
+    D = oracle.pearl_datacost(0, corrs, Hs.reshape(-1, 9), 2.0, 0.3)
+    off, idx = syn.knn_graph(corrs, 200.0, 5)
+    lab, e, cyc = oracle.gco_pearl_label(D, 0.3, 10.0, off, idx)
+    assert abs(oracle.gco_energy(D, 0.3, 10.0, off, idx, lab) - e) < 1e-9
+    acc = np.mean(np.where(gt < 0, 3, gt) == lab)
+    assert acc > 0.9
