@@ -57,52 +57,76 @@ __device__ __forceinline__ void load_point(const double *__restrict__ soa, int64
 // ------------------------------------------------------------------------------------------------
 // a1/a2/a3: residual-and-inlier matrix
 // ------------------------------------------------------------------------------------------------
-constexpr int kRmPointsPerWarp = 64;                         // lane handles points base+lane and base+32+lane
-constexpr int kRmPointsPerBlock = (kThreads / 32) * kRmPointsPerWarp; // 512
-constexpr int kRmHypsPerBlock = 64;
+// Register tile: each lane owns kRmP points (base + lane + 32 j), the block walks a tile of hypotheses staged in
+// shared memory (padded to an even number of doubles so that a model is read with LDS.128 broadcasts).
+// Per evaluation: 28 FP64-pipe instructions (H), ~1.5 LDS, 1 STG, 6 range-test instructions, one branch per
+// hypothesis for the whole register tile -> the FP64 pipe (2 issue slots per instruction) is the binding unit.
+constexpr int kRmP = 4;                                     // points per lane
+constexpr int kRmPointsPerWarp = 32 * kRmP;                 // 128
+constexpr int kRmPointsPerBlock = (kThreads / 32) * kRmPointsPerWarp; // 1024
+constexpr int kRmHypsPerBlock = 32;
 
 template <typename OUT> __device__ __forceinline__ void store_stream(OUT *p, double v);
 template <> __device__ __forceinline__ void store_stream<double>(double *p, double v) { __stcs(p, v); }
 template <> __device__ __forceinline__ void store_stream<float>(float *p, double v) { __stcs(p, __double2float_rn(v)); }
 
-template <int TYPE, typename OUT>
-__global__ void __launch_bounds__(kThreads)
+// cold path: operands outside the fast division's domain (zero / tiny numerators, overflowing quotients, ...)
+#define PXB_RESIDUAL_TILE_EXACT(TYPE, P_, p_, m_, r_)                  \
+	do {                                                               \
+		_Pragma("unroll") for (int j_ = 0; j_ < (P_); ++j_)(r_)[j_] = squared_residual<TYPE>((p_)[j_], (m_)); \
+	} while (0)
+
+template <int TYPE, typename OUT, bool HAS_R2, bool HAS_MASK>
+__global__ void __launch_bounds__(kThreads, 2)
     k_residual_matrix(const double *__restrict__ soa, int64_t stride, int64_t N, const double *__restrict__ models,
                       int64_t K, double T2, OUT *__restrict__ r2, uint32_t *__restrict__ mask, int64_t words) {
-	constexpr int DIM = ModelTraits<TYPE>::kDim, MS = ModelTraits<TYPE>::kSize;
-	__shared__ double s_models[kRmHypsPerBlock * MS];
+	constexpr int DIM = ModelTraits<TYPE>::kDim, MS = ModelTraits<TYPE>::kSize, MP = ModelTraits<TYPE>::kPadded;
+	__shared__ __align__(16) double s_models[kRmHypsPerBlock * MP];
 
 	const int64_t k0 = (int64_t)blockIdx.y * kRmHypsPerBlock;
 	const int nk = (int)min((int64_t)kRmHypsPerBlock, K - k0);
-	for (int t = threadIdx.x; t < nk * MS; t += kThreads) s_models[t] = models[k0 * MS + t];
+	for (int t = threadIdx.x; t < nk * MS; t += kThreads) s_models[(t / MS) * MP + (t % MS)] = models[k0 * MS + t];
 	__syncthreads();
 
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int64_t base = (int64_t)blockIdx.x * kRmPointsPerBlock + warp * kRmPointsPerWarp;
 	if (base >= N) return;
-	const int64_t i0 = base + lane, i1 = base + 32 + lane;
-	const bool v0 = i0 < N, v1 = i1 < N;
-	double p0[5], p1[5];
-	// stride is padded to a multiple of 64 and the pad is zero-filled, so the loads are always in bounds
-	load_point<DIM>(soa, stride, i0, p0);
-	load_point<DIM>(soa, stride, i1, p1);
-	const int64_t w0 = base >> 5;
+	double p[kRmP][5];
+	bool valid[kRmP];
+#pragma unroll
+	for (int j = 0; j < kRmP; ++j) {
+		const int64_t i = base + lane + 32 * j;
+		valid[j] = i < N;
+		// rows are padded to a multiple of 64 with zeros; clamp keeps the last tile's loads in bounds
+		load_point<DIM>(soa, stride, valid[j] ? i : (N - 1), p[j]);
+	}
+	OUT *out = HAS_R2 ? r2 + k0 * N + base + lane : nullptr;
+	uint32_t *mout = HAS_MASK ? mask + k0 * words + (base >> 5) : nullptr;
+	const int nwords = (int)min((int64_t)kRmP, words - (base >> 5));
 
-#pragma unroll 2
 	for (int k = 0; k < nk; ++k) {
-		const double *m = s_models + k * MS;
-		const double ra = squared_residual<TYPE>(p0, m);
-		const double rb = squared_residual<TYPE>(p1, m);
-		const int64_t row = k0 + k;
-		if (r2) {
-			if (v0) store_stream<OUT>(r2 + row * N + i0, ra);
-			if (v1) store_stream<OUT>(r2 + row * N + i1, rb);
+		double m[12];
+		load_model_smem<TYPE>(s_models + k * MP, m);
+		double r[kRmP];
+		bool ok = true;
+#pragma unroll
+		for (int j = 0; j < kRmP; ++j) r[j] = squared_residual_fast<TYPE>(p[j], m, ok);
+		if (__builtin_expect(!ok, 0)) PXB_RESIDUAL_TILE_EXACT(TYPE, kRmP, p, m, r);
+		if (HAS_R2) {
+#pragma unroll
+			for (int j = 0; j < kRmP; ++j)
+				if (valid[j]) store_stream<OUT>(out + 32 * j, r[j]);
+			out += N;
 		}
-		if (mask) {
-			const uint32_t ba = __ballot_sync(0xffffffffu, v0 && (ra < T2));
-			const uint32_t bb = __ballot_sync(0xffffffffu, v1 && (rb < T2));
-			if (lane == 0) mask[row * words + w0] = ba;
-			if (lane == 1 && (w0 + 1) < words) mask[row * words + w0 + 1] = bb;
+		if (HAS_MASK) {
+			uint32_t w[kRmP];
+#pragma unroll
+			for (int j = 0; j < kRmP; ++j) w[j] = __ballot_sync(0xffffffffu, valid[j] && (r[j] < T2));
+			uint32_t mine = w[0];
+#pragma unroll
+			for (int j = 1; j < kRmP; ++j) mine = (lane == j) ? w[j] : mine;
+			if (lane < nwords) mout[lane] = mine;
+			mout += words;
 		}
 	}
 }
@@ -116,9 +140,15 @@ static int launch_rm_t(pxb_ctx *ctx, const double *models, int64_t K, double T2,
 	while (done < K) { // gridDim.y is limited to 65535
 		const int64_t kk = std::min<int64_t>(K - done, (int64_t)65535 * kRmHypsPerBlock);
 		dim3 grid((unsigned)gx, (unsigned)((kk + kRmHypsPerBlock - 1) / kRmHypsPerBlock));
-		k_residual_matrix<TYPE, OUT><<<grid, kThreads, 0, ctx->stream>>>(
-		    p.soa, p.stride, p.N, models + done * ModelTraits<TYPE>::kSize, kk, T2, r2 ? r2 + done * p.N : nullptr,
-		    mask ? mask + done * words : nullptr, words);
+		const double *mm = models + done * ModelTraits<TYPE>::kSize;
+		OUT *rr = r2 ? r2 + done * p.N : nullptr;
+		uint32_t *mk = mask ? mask + done * words : nullptr;
+		if (rr && mk)
+			k_residual_matrix<TYPE, OUT, true, true><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, mm, kk, T2, rr, mk, words);
+		else if (rr)
+			k_residual_matrix<TYPE, OUT, true, false><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, mm, kk, T2, rr, mk, words);
+		else if (mk)
+			k_residual_matrix<TYPE, OUT, false, true><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, mm, kk, T2, rr, mk, words);
 		ctx->launches++;
 		done += kk;
 	}
@@ -157,19 +187,20 @@ struct ScorePartial {
 };
 
 template <int TYPE>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
     k_score_partial(const double *__restrict__ soa, int64_t stride, int64_t N, const double *__restrict__ models,
                     int64_t K, double T2, const double *__restrict__ compound_pref, ScorePartial *__restrict__ partials,
                     int nchunks) {
-	constexpr int DIM = ModelTraits<TYPE>::kDim, MS = ModelTraits<TYPE>::kSize;
-	__shared__ double s_models[kScHyps * MS];
+	constexpr int DIM = ModelTraits<TYPE>::kDim, MS = ModelTraits<TYPE>::kSize, MP = ModelTraits<TYPE>::kPadded;
+	constexpr int P = 4; // register tile: 4 points x kScHyps hypotheses
+	__shared__ __align__(16) double s_models[kScHyps * MP];
 	__shared__ double s_v[kThreads / 32][kScHyps], s_s[kThreads / 32][kScHyps];
 	__shared__ int s_c[kThreads / 32][kScHyps];
 
 	const int64_t k0 = (int64_t)blockIdx.y * kScHyps;
 	const int nk = (int)min((int64_t)kScHyps, K - k0);
 	for (int t = threadIdx.x; t < kScHyps * MS; t += kThreads)
-		s_models[t] = (t < nk * MS) ? models[k0 * MS + t] : 0.0;
+		s_models[(t / MS) * MP + (t % MS)] = (t < nk * MS) ? models[k0 * MS + t] : 0.0;
 	__syncthreads();
 
 	const int chunk = blockIdx.x;
@@ -181,21 +212,38 @@ __global__ void __launch_bounds__(kThreads)
 		s[h] = 0.0;
 		c[h] = 0;
 	}
+	const bool has_cp = compound_pref != nullptr;
 	const int64_t first = (int64_t)chunk * kScChunk + threadIdx.x;
-	for (int j = 0; j < kScPointsPerThread; ++j) {
-		const int64_t i = first + (int64_t)j * kThreads;
-		if (i >= N) break;
-		double p[5];
-		load_point<DIM>(soa, stride, i, p);
-		const double cp = compound_pref ? __ldg(compound_pref + i) : 0.0;
+	// a thread visits its points in increasing index order: first + (it*P + j) * kThreads
+	for (int it = 0; it < kScPointsPerThread / P; ++it) {
+		const int64_t i0 = first + (int64_t)it * P * kThreads;
+		if (i0 >= N) break;
+		double p[P][5], cp[P];
+		bool valid[P];
+#pragma unroll
+		for (int j = 0; j < P; ++j) {
+			const int64_t i = i0 + (int64_t)j * kThreads;
+			valid[j] = i < N;
+			load_point<DIM>(soa, stride, valid[j] ? i : (N - 1), p[j]);
+			cp[j] = (has_cp && valid[j]) ? __ldg(compound_pref + i) : 0.0;
+		}
 #pragma unroll
 		for (int h = 0; h < kScHyps; ++h) {
-			const double r2 = squared_residual<TYPE>(p, s_models + h * MS);
-			if (r2 < T2) { // scoring_function_with_compound_model.h:85-102
-				c[h]++;
-				const double sv = cv_max(0.0, sub(1.0, divd(r2, T2)));
-				v[h] = add(v[h], sv);
-				if (compound_pref) s[h] = add(s[h], cv_min(cp, sv)); // :115-117 (pref is 0 off the inlier set)
+			double m[12];
+			load_model_smem<TYPE>(s_models + h * MP, m);
+			double r[P];
+			bool ok = true;
+#pragma unroll
+			for (int j = 0; j < P; ++j) r[j] = squared_residual_fast<TYPE>(p[j], m, ok);
+			if (__builtin_expect(!ok, 0)) PXB_RESIDUAL_TILE_EXACT(TYPE, P, p, m, r);
+#pragma unroll
+			for (int j = 0; j < P; ++j) {
+				if (valid[j] && r[j] < T2) { // scoring_function_with_compound_model.h:85-102
+					c[h]++;
+					const double sv = cv_max(0.0, sub(1.0, divd(r[j], T2)));
+					v[h] = add(v[h], sv);
+					if (has_cp) s[h] = add(s[h], cv_min(cp[j], sv)); // :115-117 (pref is 0 off the inlier set)
+				}
 			}
 		}
 	}
