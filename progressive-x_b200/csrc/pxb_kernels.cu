@@ -1,8 +1,7 @@
 // pxb_kernels.cu -- the data-parallel N-point loops of Progressive-X as sm_100a kernels.
 //
 //   k_residual_matrix   a1/a2/a3  N x K squared residuals (f64 or f32) + inlier bit matrix      HBM-write bound
-//   k_score_partial     a4        fused compound-aware MSAC score (no matrix materialised)       FP64-pipe bound
-//   k_score_finalize    a4        ordered combine of the per-chunk partials
+//   (a4, the fused compound-aware score, lives in pxb_score.cu)
 //   k_preference        a5        preference vector of one model
 //   k_tanimoto          a5        dot / squared norms, one block, fixed topology
 //   k_compound_max      a5
@@ -21,13 +20,13 @@
 // fixed xor-butterfly, warps combine in warp order, chunks combine in chunk order. The topology depends on N
 // only -- never on K, the grid or the device -- so equal inputs always give equal sums.
 #include <cstdio>
+#include <cstdlib>
 
 #include "pxb_internal.h"
 #include "pxb_residuals.cuh"
 
 namespace pxb {
 
-constexpr int kThreads = 256;
 
 // ------------------------------------------------------------------------------------------------
 // AoS -> SoA re-tiling of the uploaded points
@@ -48,11 +47,6 @@ int launch_aos_to_soa(pxb_ctx *ctx) {
 	return PXB_OK;
 }
 
-template <int DIM>
-__device__ __forceinline__ void load_point(const double *__restrict__ soa, int64_t stride, int64_t i, double (&p)[5]) {
-#pragma unroll
-	for (int c = 0; c < DIM; ++c) p[c] = __ldg(soa + c * stride + i);
-}
 
 // ------------------------------------------------------------------------------------------------
 // a1/a2/a3: residual-and-inlier matrix
@@ -61,23 +55,14 @@ __device__ __forceinline__ void load_point(const double *__restrict__ soa, int64
 // shared memory (padded to an even number of doubles so that a model is read with LDS.128 broadcasts).
 // Per evaluation: 28 FP64-pipe instructions (H), ~1.5 LDS, 1 STG, 6 range-test instructions, one branch per
 // hypothesis for the whole register tile -> the FP64 pipe (2 issue slots per instruction) is the binding unit.
-constexpr int kRmP = 4;                                     // points per lane
-constexpr int kRmPointsPerWarp = 32 * kRmP;                 // 128
-constexpr int kRmPointsPerBlock = (kThreads / 32) * kRmPointsPerWarp; // 1024
 constexpr int kRmHypsPerBlock = 32;
 
 template <typename OUT> __device__ __forceinline__ void store_stream(OUT *p, double v);
 template <> __device__ __forceinline__ void store_stream<double>(double *p, double v) { __stcs(p, v); }
 template <> __device__ __forceinline__ void store_stream<float>(float *p, double v) { __stcs(p, __double2float_rn(v)); }
 
-// cold path: operands outside the fast division's domain (zero / tiny numerators, overflowing quotients, ...)
-#define PXB_RESIDUAL_TILE_EXACT(TYPE, P_, p_, m_, r_)                  \
-	do {                                                               \
-		_Pragma("unroll") for (int j_ = 0; j_ < (P_); ++j_)(r_)[j_] = squared_residual<TYPE>((p_)[j_], (m_)); \
-	} while (0)
-
-template <int TYPE, typename OUT, bool HAS_R2, bool HAS_MASK>
-__global__ void __launch_bounds__(kThreads, 2)
+template <int TYPE, typename OUT, bool HAS_R2, bool HAS_MASK, int kRmP, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
     k_residual_matrix(const double *__restrict__ soa, int64_t stride, int64_t N, const double *__restrict__ models,
                       int64_t K, double T2, OUT *__restrict__ r2, uint32_t *__restrict__ mask, int64_t words) {
 	constexpr int DIM = ModelTraits<TYPE>::kDim, MS = ModelTraits<TYPE>::kSize, MP = ModelTraits<TYPE>::kPadded;
@@ -85,21 +70,29 @@ __global__ void __launch_bounds__(kThreads, 2)
 
 	const int64_t k0 = (int64_t)blockIdx.y * kRmHypsPerBlock;
 	const int nk = (int)min((int64_t)kRmHypsPerBlock, K - k0);
-	for (int t = threadIdx.x; t < nk * MS; t += kThreads) s_models[(t / MS) * MP + (t % MS)] = models[k0 * MS + t];
-	__syncthreads();
+	// inputs outside +-2^60 (or NaN/inf) make the whole block take the plain div.rn.f64 loop (see pxb_residuals.cuh)
+	int wild = 0;
+	for (int t = threadIdx.x; t < nk * MS; t += kThreads) {
+		const double v = models[k0 * MS + t];
+		s_models[(t / MS) * MP + (t % MS)] = v;
+		wild |= !(fabs(v) <= kInputMagnitudeLimit);
+	}
 
+	constexpr int kRmPointsPerWarp = 32 * kRmP, kRmPointsPerBlock = (kThreads / 32) * kRmPointsPerWarp;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int64_t base = (int64_t)blockIdx.x * kRmPointsPerBlock + warp * kRmPointsPerWarp;
-	if (base >= N) return;
 	double p[kRmP][5];
 	bool valid[kRmP];
 #pragma unroll
 	for (int j = 0; j < kRmP; ++j) {
 		const int64_t i = base + lane + 32 * j;
 		valid[j] = i < N;
-		// rows are padded to a multiple of 64 with zeros; clamp keeps the last tile's loads in bounds
 		load_point<DIM>(soa, stride, valid[j] ? i : (N - 1), p[j]);
+#pragma unroll
+		for (int c = 0; c < DIM; ++c) wild |= !(fabs(p[j][c]) <= kInputMagnitudeLimit);
 	}
+	wild = __syncthreads_or(wild);
+	if (base >= N) return;
 	OUT *out = HAS_R2 ? r2 + k0 * N + base + lane : nullptr;
 	uint32_t *mout = HAS_MASK ? mask + k0 * words + (base >> 5) : nullptr;
 	const int nwords = (int)min((int64_t)kRmP, words - (base >> 5));
@@ -108,10 +101,10 @@ __global__ void __launch_bounds__(kThreads, 2)
 		double m[12];
 		load_model_smem<TYPE>(s_models + k * MP, m);
 		double r[kRmP];
-		bool ok = true;
+		float lo = __int_as_float(0x7f000000);
 #pragma unroll
-		for (int j = 0; j < kRmP; ++j) r[j] = squared_residual_fast<TYPE>(p[j], m, ok);
-		if (__builtin_expect(!ok, 0)) PXB_RESIDUAL_TILE_EXACT(TYPE, kRmP, p, m, r);
+		for (int j = 0; j < kRmP; ++j) r[j] = squared_residual_tile<TYPE>(p[j], m, lo);
+		if (__builtin_expect(!(lo >= __int_as_float(kHiMinPattern)) || wild, 0)) PXB_RESIDUAL_TILE_EXACT(TYPE, kRmP, p, m, r);
 		if (HAS_R2) {
 #pragma unroll
 			for (int j = 0; j < kRmP; ++j)
@@ -131,11 +124,12 @@ __global__ void __launch_bounds__(kThreads, 2)
 	}
 }
 
-template <int TYPE, typename OUT>
-static int launch_rm_t(pxb_ctx *ctx, const double *models, int64_t K, double T2, OUT *r2, uint32_t *mask) {
+template <int TYPE, typename OUT, int P, int MINB>
+static int launch_rm_v(pxb_ctx *ctx, const double *models, int64_t K, double T2, OUT *r2, uint32_t *mask) {
 	const Points &p = ctx->pts;
 	const int64_t words = (p.N + 31) / 32;
-	const int64_t gx = (p.N + kRmPointsPerBlock - 1) / kRmPointsPerBlock;
+	const int64_t ppb = (int64_t)(kThreads / 32) * 32 * P;
+	const int64_t gx = (p.N + ppb - 1) / ppb;
 	int64_t done = 0;
 	while (done < K) { // gridDim.y is limited to 65535
 		const int64_t kk = std::min<int64_t>(K - done, (int64_t)65535 * kRmHypsPerBlock);
@@ -144,16 +138,35 @@ static int launch_rm_t(pxb_ctx *ctx, const double *models, int64_t K, double T2,
 		OUT *rr = r2 ? r2 + done * p.N : nullptr;
 		uint32_t *mk = mask ? mask + done * words : nullptr;
 		if (rr && mk)
-			k_residual_matrix<TYPE, OUT, true, true><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, mm, kk, T2, rr, mk, words);
+			k_residual_matrix<TYPE, OUT, true, true, P, MINB><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, mm, kk, T2, rr, mk, words);
 		else if (rr)
-			k_residual_matrix<TYPE, OUT, true, false><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, mm, kk, T2, rr, mk, words);
+			k_residual_matrix<TYPE, OUT, true, false, P, MINB><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, mm, kk, T2, rr, mk, words);
 		else if (mk)
-			k_residual_matrix<TYPE, OUT, false, true><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, mm, kk, T2, rr, mk, words);
+			k_residual_matrix<TYPE, OUT, false, true, P, MINB><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, mm, kk, T2, rr, mk, words);
 		ctx->launches++;
 		done += kk;
 	}
 	PXB_CUDA(cudaGetLastError());
 	return PXB_OK;
+}
+
+static int rm_variant() {
+	static int v = -1;
+	if (v < 0) {
+		const char *e = getenv("PXB_RM_VARIANT"); // tuning knob: 0 = (P4, 2 blocks/SM), 1 = (P4, 3), 2 = (P2, 3), 3 = (P2, 4)
+		v = e ? atoi(e) : 0;
+	}
+	return v;
+}
+
+template <int TYPE, typename OUT>
+static int launch_rm_t(pxb_ctx *ctx, const double *models, int64_t K, double T2, OUT *r2, uint32_t *mask) {
+	switch (rm_variant()) {
+	case 1: return launch_rm_v<TYPE, OUT, 4, 3>(ctx, models, K, T2, r2, mask);
+	case 2: return launch_rm_v<TYPE, OUT, 2, 3>(ctx, models, K, T2, r2, mask);
+	case 3: return launch_rm_v<TYPE, OUT, 2, 4>(ctx, models, K, T2, r2, mask);
+	default: return launch_rm_v<TYPE, OUT, 4, 2>(ctx, models, K, T2, r2, mask);
+	}
 }
 
 int launch_residual_matrix(pxb_ctx *ctx, const double *models, int64_t K, double T2, double *r2, float *r2f,
@@ -172,168 +185,6 @@ int launch_residual_matrix(pxb_ctx *ctx, const double *models, int64_t K, double
 	case PXB_MODEL_FUNDAMENTAL: return launch_rm_t<PXB_MODEL_FUNDAMENTAL, double>(ctx, models, K, T2, r2, mask);
 	default: return launch_rm_t<PXB_MODEL_PNP, double>(ctx, models, K, T2, r2, mask);
 	}
-}
-
-// ------------------------------------------------------------------------------------------------
-// a4: fused compound-aware MSAC score
-// ------------------------------------------------------------------------------------------------
-constexpr int kScChunk = 4096;                      // points per block (fixes the summation topology)
-constexpr int kScPointsPerThread = kScChunk / kThreads; // 16
-constexpr int kScHyps = 8;                          // hypotheses per block
-
-struct ScorePartial {
-	double value, shared;
-	long long count;
-};
-
-template <int TYPE>
-__global__ void __launch_bounds__(kThreads, 2)
-    k_score_partial(const double *__restrict__ soa, int64_t stride, int64_t N, const double *__restrict__ models,
-                    int64_t K, double T2, const double *__restrict__ compound_pref, ScorePartial *__restrict__ partials,
-                    int nchunks) {
-	constexpr int DIM = ModelTraits<TYPE>::kDim, MS = ModelTraits<TYPE>::kSize, MP = ModelTraits<TYPE>::kPadded;
-	constexpr int P = 4; // register tile: 4 points x kScHyps hypotheses
-	__shared__ __align__(16) double s_models[kScHyps * MP];
-	__shared__ double s_v[kThreads / 32][kScHyps], s_s[kThreads / 32][kScHyps];
-	__shared__ int s_c[kThreads / 32][kScHyps];
-
-	const int64_t k0 = (int64_t)blockIdx.y * kScHyps;
-	const int nk = (int)min((int64_t)kScHyps, K - k0);
-	for (int t = threadIdx.x; t < kScHyps * MS; t += kThreads)
-		s_models[(t / MS) * MP + (t % MS)] = (t < nk * MS) ? models[k0 * MS + t] : 0.0;
-	__syncthreads();
-
-	const int chunk = blockIdx.x;
-	double v[kScHyps], s[kScHyps];
-	int c[kScHyps];
-#pragma unroll
-	for (int h = 0; h < kScHyps; ++h) {
-		v[h] = 0.0;
-		s[h] = 0.0;
-		c[h] = 0;
-	}
-	const bool has_cp = compound_pref != nullptr;
-	const int64_t first = (int64_t)chunk * kScChunk + threadIdx.x;
-	// a thread visits its points in increasing index order: first + (it*P + j) * kThreads
-	for (int it = 0; it < kScPointsPerThread / P; ++it) {
-		const int64_t i0 = first + (int64_t)it * P * kThreads;
-		if (i0 >= N) break;
-		double p[P][5], cp[P];
-		bool valid[P];
-#pragma unroll
-		for (int j = 0; j < P; ++j) {
-			const int64_t i = i0 + (int64_t)j * kThreads;
-			valid[j] = i < N;
-			load_point<DIM>(soa, stride, valid[j] ? i : (N - 1), p[j]);
-			cp[j] = (has_cp && valid[j]) ? __ldg(compound_pref + i) : 0.0;
-		}
-#pragma unroll
-		for (int h = 0; h < kScHyps; ++h) {
-			double m[12];
-			load_model_smem<TYPE>(s_models + h * MP, m);
-			double r[P];
-			bool ok = true;
-#pragma unroll
-			for (int j = 0; j < P; ++j) r[j] = squared_residual_fast<TYPE>(p[j], m, ok);
-			if (__builtin_expect(!ok, 0)) PXB_RESIDUAL_TILE_EXACT(TYPE, P, p, m, r);
-#pragma unroll
-			for (int j = 0; j < P; ++j) {
-				if (valid[j] && r[j] < T2) { // scoring_function_with_compound_model.h:85-102
-					c[h]++;
-					const double sv = cv_max(0.0, sub(1.0, divd(r[j], T2)));
-					v[h] = add(v[h], sv);
-					if (has_cp) s[h] = add(s[h], cv_min(cp[j], sv)); // :115-117 (pref is 0 off the inlier set)
-				}
-			}
-		}
-	}
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-	for (int h = 0; h < kScHyps; ++h) {
-#pragma unroll
-		for (int o = 16; o > 0; o >>= 1) {
-			v[h] = add(v[h], __shfl_xor_sync(0xffffffffu, v[h], o));
-			s[h] = add(s[h], __shfl_xor_sync(0xffffffffu, s[h], o));
-			c[h] += __shfl_xor_sync(0xffffffffu, c[h], o);
-		}
-		if (lane == 0) {
-			s_v[warp][h] = v[h];
-			s_s[warp][h] = s[h];
-			s_c[warp][h] = c[h];
-		}
-	}
-	__syncthreads();
-	if (threadIdx.x < nk) {
-		const int h = threadIdx.x;
-		double vv = 0.0, ss = 0.0;
-		long long cc = 0;
-		for (int w = 0; w < kThreads / 32; ++w) {
-			vv = add(vv, s_v[w][h]);
-			ss = add(ss, s_s[w][h]);
-			cc += s_c[w][h];
-		}
-		ScorePartial out;
-		out.value = vv;
-		out.shared = ss;
-		out.count = cc;
-		partials[(k0 + h) * nchunks + chunk] = out;
-	}
-}
-
-__global__ void k_score_finalize(const ScorePartial *__restrict__ partials, int64_t K, int nchunks,
-                                 int64_t *__restrict__ count, double *__restrict__ value, double *__restrict__ shared) {
-	const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (k >= K) return;
-	double v = 0.0, s = 0.0;
-	long long c = 0;
-	for (int j = 0; j < nchunks; ++j) {
-		const ScorePartial p = partials[k * nchunks + j];
-		v = add(v, p.value);
-		s = add(s, p.shared);
-		c += p.count;
-	}
-	count[k] = c;
-	value[k] = v;
-	shared[k] = s;
-}
-
-int launch_score_compound(pxb_ctx *ctx, const double *models, int64_t K, double T2, const double *compound_pref,
-                          int64_t *count, double *value_sum, double *shared) {
-	if (K <= 0) return PXB_OK;
-	const Points &p = ctx->pts;
-	const int nchunks = (int)((p.N + kScChunk - 1) / kScChunk);
-	PXB_TRY(ctx->partials.reserve(sizeof(ScorePartial) * (size_t)K * nchunks));
-	ScorePartial *part = ctx->partials.as<ScorePartial>();
-	int64_t done = 0;
-	while (done < K) {
-		const int64_t kk = std::min<int64_t>(K - done, (int64_t)65535 * kScHyps);
-		dim3 grid((unsigned)nchunks, (unsigned)((kk + kScHyps - 1) / kScHyps));
-		const double *m;
-		ScorePartial *pp = part + done * nchunks;
-		switch (p.type) {
-		case PXB_MODEL_HOMOGRAPHY:
-			m = models + done * 9;
-			k_score_partial<PXB_MODEL_HOMOGRAPHY><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, m, kk, T2,
-			                                                                          compound_pref, pp, nchunks);
-			break;
-		case PXB_MODEL_FUNDAMENTAL:
-			m = models + done * 9;
-			k_score_partial<PXB_MODEL_FUNDAMENTAL><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, m, kk, T2,
-			                                                                           compound_pref, pp, nchunks);
-			break;
-		default:
-			m = models + done * 12;
-			k_score_partial<PXB_MODEL_PNP><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, m, kk, T2,
-			                                                                   compound_pref, pp, nchunks);
-			break;
-		}
-		ctx->launches++;
-		done += kk;
-	}
-	k_score_finalize<<<(unsigned)((K + 127) / 128), 128, 0, ctx->stream>>>(part, K, nchunks, count, value_sum, shared);
-	ctx->launches++;
-	PXB_CUDA(cudaGetLastError());
-	return PXB_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
