@@ -159,6 +159,24 @@ int pxb_lo_unary_terms(pxb_ctx *ctx, const double *model_host, double thr, doubl
  * w[i] = max(0, 1 - r2_i/T2)^2. */
 int pxb_tukey_weights(pxb_ctx *ctx, const double *model_host, double T2, double *weights_host);
 
+/* The st-cut of GCRANSAC::labeling (gcr/GCRANSAC.h:964-1018) given the unary terms above: pairwise terms
+ * e00 = 0.5 (d_i + d_j) lambda, e01 = e10 = lambda, e11 = 0 on every undirected pair of the directed neighbour lists
+ * (first occurrence only, like the reference's used_edges matrix), Boykov-Kolmogorov labelling rule
+ * (inlier = SINK = the node can still reach the sink in the residual graph). inlier_out: N bytes (0/1). */
+int pxb_lo_graph_cut(pxb_ctx *ctx, const double *e0_host, const double *e1_host, const double *d_host, int64_t N,
+                     double lambda, const int32_t *csr_off_host, const int32_t *csr_idx_host, uint8_t *inlier_out);
+
+/* ---- "next" rows the task-level driver needs -------------------------------------------------- */
+/* Neighbourhood graph (replaces FlannNeighborhoodGraph, gcr/neighborhood/flann_neighborhood_graph.h:100-139): the
+ * k nearest points within `radius` of every point (self excluded, ties by index), all coordinates of the uploaded
+ * rows. nbr_out: N*k int32 (-1 padded), deg_out: N int32. */
+int pxb_knn_graph(pxb_ctx *ctx, double radius, int k, int32_t *nbr_out_host, int32_t *deg_out_host);
+/* Batched non-minimal homography fits (RobustHomographyEstimator::estimateModelNonminimal,
+ * gcr/estimators/homography_estimator.h:140-173 + solver_homography_four_point.h:192-264): P problems given as CSR
+ * index lists; weights_by_row may be NULL. H_out: P*9, ok_out: P. */
+int pxb_fit_homographies(pxb_ctx *ctx, int32_t P, const int32_t *off_host, const int32_t *idx_host,
+                         const double *weights_by_row_host, double *H_out_host, int32_t *ok_out_host);
+
 /* ---- self-test --------------------------------------------------------------------------------------------- */
 /* Compares the hot loop's shared-reciprocal double division (two quotients, one Newton reciprocal) with the
  * IEEE div.rn.f64 on n_triples pseudo-random (a1, a2, b) operands; mode 0 = arbitrary bit patterns, 1 = magnitudes

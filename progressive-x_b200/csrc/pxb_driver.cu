@@ -1,22 +1,758 @@
-// pxb_driver.cu -- task-level entry points (placeholder).
+// pxb_driver.cu -- host side of the drop-in: the Progressive-X anytime loop, the GC-RANSAC proposal engine and
+// the PEARL optimiser, re-stated as a block-replay driver over the CUDA operators of this library.
+//
+// What stays on the host is exactly what the reference keeps sequential (control flow, RNG state machines, the
+// <= 10 outer proposals); every N-point loop runs on the device through the operators of include/pxb200.h.
+//
+//   ProgressiveX::run            px/include/progressive_x.h:251-489      -> Driver::run
+//   isPutativeModelValid         px/include/progressive_x.h:565-591      -> Driver::putative_model_valid
+//   updateCompoundModel          px/include/progressive_x.h:597-624      -> pxb_compound_max over the stored prefs
+//   GCRANSAC::run                gcr/GCRANSAC.h:203-628                  -> Driver::propose (block replay)
+//   graphCutLocalOptimization    gcr/GCRANSAC.h:781-911                  -> Driver::local_optimization
+//   iteratedLeastSquaresFitting  gcr/GCRANSAC.h:631-759                  -> Driver::irls
+//   PEARL::run / labeling / parameterEstimation / rejectInstances
+//                                px/include/PEARL.h:275-555              -> Driver::pearl
+//
+// Block replay. The reference draws one minimal sample, solves, scores N points, compares, repeats. Here the main
+// sampler is run ahead for a block of B samples; one launch solves them, one launch scores every model against
+// all N points, and the host then replays the reference's sequential bookkeeping (iteration counting incl. failed
+// generations, so-far-the-best updates with the early-exit rule of getScore, adaptive max_iteration, LO trigger)
+// over the pre-evaluated block in sample order. The decisions are those the sequential loop would take on the same
+// sample stream, because a hypothesis' (count, value, shared) does not depend on the state of the loop.
+//
+// Deviations from the reference (documented in DESIGN.md):
+//   * RNG: own seedable generator (the reference seeds std::mt19937 from std::random_device and cannot be replayed);
+//   * neighbourhood graph: exact kNN-in-radius on the GPU instead of randomised FLANN;
+//   * the reference's two-buffer inlier ping-pong (GCRANSAC.h:244-252,:546-552) is replaced by "the inlier list of the
+//     current best model" -- the reference's version depends on list-size coincidences;
+//   * samplers 1 (PROSAC) and 2 (P-NAPSAC) fall back to uniform sampling (host-only RNG state machines, out of scope);
+//   * non-minimal fits: homography only (normal equations); F / PnP task entry points report PXB_ERR_UNSUPPORTED for
+//     the stages that need them ("next").
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <numeric>
+#include <vector>
+
 #include "pxb_internal.h"
-using namespace pxb;
-extern "C" {
-int pxb_find_homographies(pxb_ctx *, const double *, int64_t, int64_t *, double *, int64_t, size_t, size_t, size_t,
-                          size_t, double, double, double, double, double, size_t, size_t, int, size_t, double, int,
-                          uint64_t) {
-	set_error("not implemented yet");
-	return PXB_ERR_UNSUPPORTED;
+
+namespace pxb {
+
+int launch_knn_graph(pxb_ctx *ctx, double radius, int k, int32_t *nbr, int32_t *deg);
+int launch_fit_h(pxb_ctx *ctx, int P, const int32_t *off, const int32_t *idx, const double *weights, double *H_out,
+                 int32_t *ok_out);
+
+namespace {
+
+// ---- RNG -----------------------------------------------------------------------------------------------------
+struct Rng {
+	uint64_t s;
+	explicit Rng(uint64_t seed) : s(seed ? seed : 0x9E3779B97F4A7C15ull) {}
+	uint64_t next() {
+		uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+		z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+		z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+		return z ^ (z >> 31);
+	}
+	// uniform integer in [0, max] (inclusive, like std::uniform_int_distribution(0, max)), rejection sampled
+	size_t uniform(size_t max) {
+		const uint64_t range = (uint64_t)max + 1;
+		if (range == 0) return (size_t)next();
+		const uint64_t limit = UINT64_MAX - (UINT64_MAX % range);
+		uint64_t r;
+		do r = next(); while (r >= limit);
+		return (size_t)(r % range);
+	}
+	// gcr/uniform_random_generator.h:76-122: unique set by rejection, optional value to skip
+	void unique_set(size_t *out, size_t n, size_t max, bool has_skip = false, size_t skip = 0) {
+		for (size_t i = 0; i < n; i++) {
+			out[i] = uniform(max);
+			if (has_skip && out[i] == skip) {
+				i--;
+				continue;
+			}
+			for (int j = (int)i - 1; j >= 0; j--)
+				if (out[i] == out[j]) {
+					i--;
+					break;
+				}
+		}
+	}
+};
+
+struct Graph { // directed neighbour lists, CSR
+	std::vector<int32_t> off, idx;
+	int64_t degree(int64_t i) const { return off[i + 1] - off[i]; }
+	const int32_t *nbrs(int64_t i) const { return idx.data() + off[i]; }
+};
+
+// ---- samplers (gcr/samplers/sampler.h:45-86 contract: sample(pool, subset, m) -> bool) -------------------------
+struct Sampler {
+	virtual ~Sampler() {}
+	virtual bool sample(const std::vector<size_t> &pool, size_t *subset, size_t m) = 0;
+};
+struct UniformSampler : Sampler { // gcr/samplers/uniform_sampler.h:118-134
+	Rng rng;
+	explicit UniformSampler(uint64_t seed) : rng(seed) {}
+	bool sample(const std::vector<size_t> &pool, size_t *subset, size_t m) override {
+		if (m > pool.size()) return false;
+		rng.unique_set(subset, m, pool.size() - 1);
+		for (size_t i = 0; i < m; ++i) subset[i] = pool[subset[i]];
+		return true;
+	}
+};
+struct NapsacSampler : Sampler { // gcr/samplers/napsac_sampler.h:102-151
+	Rng rng;
+	const Graph *g;
+	size_t maximum_iterations = 100;
+	NapsacSampler(uint64_t seed, const Graph *g_) : rng(seed), g(g_) {}
+	bool sample(const std::vector<size_t> &pool, size_t *subset, size_t m) override {
+		if (m > pool.size()) return false;
+		size_t attempts = 0;
+		while (attempts++ < maximum_iterations) {
+			rng.unique_set(subset, 1, pool.size() - 1);
+			const int64_t deg = g->degree((int64_t)subset[0]);
+			const int32_t *nb = g->nbrs((int64_t)subset[0]);
+			if ((size_t)deg < m) continue;
+			if ((size_t)deg == m) {
+				for (size_t i = 0; i < m; ++i) subset[i] = (size_t)nb[i];
+				break;
+			}
+			// :139-142 passes the centre *point index* as the neighbour-list *index* to skip (reference quirk, kept)
+			rng.unique_set(subset + 1, m - 1, (size_t)deg - 1, true, subset[0]);
+			for (size_t i = 1; i < m; ++i) subset[i] = (size_t)nb[subset[i]];
+			break;
+		}
+		return attempts < maximum_iterations;
+	}
+};
+
+struct Score { // gcr/scoring_function.h:48-73
+	int64_t inliers = 0;
+	double value = 0.0;
+};
+
+struct Settings {
+	int type = PXB_MODEL_HOMOGRAPHY;
+	double threshold = 2.0, confidence = 0.95, lambda = 0.14, max_tanimoto = 0.5;
+	size_t min_inliers = 20, max_iters = 5000, max_models = std::numeric_limits<size_t>::max();
+	size_t max_proposals_without_change = 10; // progressive_x.h:63
+	int exponent = 2;                         // scoring_function_with_compound_model.h:20 (int!)
+	size_t sampler_id = 0;
+	bool do_logging = false;
+	uint64_t seed = 1;
+	// gcransac::utils::Settings defaults (gcr/settings.h:66-86) as overridden by progressive_x.h:64-71
+	size_t min_iteration_number = 20, min_iteration_number_before_lo = 20, max_local_optimization_number = 50,
+	       max_graph_cut_number = 10, max_least_squares_iterations = 10, max_unsuccessful_model_generations = 100;
+};
+
+struct Instance {
+	std::vector<double> model;
+	std::vector<double> pref; // preference vector as of acceptance (never refreshed: progressive_x.h:597-624)
+};
+
+class Driver {
+  public:
+	Driver(pxb_ctx *ctx, const Settings &s) : ctx_(ctx), s_(s) {
+		N_ = ctx->pts.N;
+		ms_ = model_size(s.type);
+		m_ = sample_size(s.type);
+		maxsol_ = max_solutions(s.type);
+	}
+	int build_graph(double radius, int k);
+	int run();
+	const std::vector<Instance> &instances() const { return models_; }
+	const std::vector<int64_t> &labeling() const { return labeling_; }
+
+  private:
+	pxb_ctx *ctx_;
+	Settings s_;
+	int64_t N_;
+	int ms_, m_, maxsol_;
+	Graph graph_;
+	std::vector<Instance> models_;
+	std::vector<double> compound_pref_;
+	std::vector<int64_t> labeling_;
+	size_t pearl_outliers_ = 0;
+	// GC-RANSAC statistics of the last proposal
+	size_t iteration_number_ = 0, graph_cut_number_ = 0, lo_number_ = 0;
+	std::vector<int64_t> proposal_inliers_;
+
+	// --- operators (thin wrappers; every N-point loop is a kernel) ---
+	Score finish_score(int64_t count, double value_sum, double shared, int64_t best_inliers) const {
+		Score sc;
+		// scoring_function_with_compound_model.h:105-106: zero score when the candidate cannot reach the best
+		if ((uint64_t)(count + 1) < (uint64_t)best_inliers) return sc;
+		sc.inliers = count;
+		sc.value = value_sum;
+		if (!models_.empty()) sc.value -= std::pow(shared, s_.exponent); // :110-121
+		return sc;
+	}
+	int score_models(const double *models, int64_t K, double T2, std::vector<int64_t> &cnt, std::vector<double> &val,
+	                 std::vector<double> &shr) {
+		cnt.resize(K);
+		val.resize(K);
+		shr.resize(K);
+		if (K == 0) return PXB_OK;
+		return pxb_score_compound(ctx_, models, K, T2, models_.empty() ? nullptr : compound_pref_.data(), cnt.data(),
+		                          val.data(), shr.data());
+	}
+	int inliers_of(const double *model, double T2, std::vector<int64_t> &out) {
+		out.resize(N_);
+		int64_t n = 0;
+		PXB_TRY(pxb_inliers(ctx_, model, T2, out.data(), &n));
+		out.resize(n);
+		return PXB_OK;
+	}
+	// batched non-minimal fits over index lists; weights (may be null) follow the reference's row indexing
+	int fit_nonminimal(const std::vector<std::vector<int64_t>> &sets, const double *weights_by_row,
+	                   std::vector<double> &models_out, std::vector<int32_t> &ok);
+	int lo_labeling(const double *model, std::vector<int64_t> &inliers);
+	size_t iteration_number_for(size_t inliers, double log_probability) const;
+	int propose(uint64_t round_seed, std::vector<double> &model_out, bool &found);
+	int local_optimization(Sampler &lo_sampler, std::vector<double> &best_model, Score &best_score, double T2);
+	int irls(std::vector<int64_t> &inliers, std::vector<double> &model, double T2, bool &success);
+	int putative_model_valid(const std::vector<double> &model, std::vector<double> &pref, bool &valid);
+	int pearl();
+	size_t predicted_unseen_inliers(size_t iterations, size_t compound_inliers) const;
+};
+
+int Driver::build_graph(double radius, int k) {
+	std::vector<int32_t> nbr((size_t)N_ * k), deg((size_t)N_);
+	PXB_TRY(ctx_->idx.reserve(sizeof(int32_t) * (size_t)N_ * (k + 1)));
+	int32_t *d_nbr = ctx_->idx.as<int32_t>(), *d_deg = d_nbr + (size_t)N_ * k;
+	PXB_TRY(launch_knn_graph(ctx_, radius, k, d_nbr, d_deg));
+	PXB_CUDA(cudaMemcpyAsync(nbr.data(), d_nbr, sizeof(int32_t) * nbr.size(), cudaMemcpyDeviceToHost, ctx_->stream));
+	PXB_CUDA(cudaMemcpyAsync(deg.data(), d_deg, sizeof(int32_t) * deg.size(), cudaMemcpyDeviceToHost, ctx_->stream));
+	PXB_CUDA(cudaStreamSynchronize(ctx_->stream));
+	graph_.off.assign((size_t)N_ + 1, 0);
+	for (int64_t i = 0; i < N_; ++i) graph_.off[i + 1] = graph_.off[i] + deg[i];
+	graph_.idx.resize((size_t)graph_.off[N_]);
+	for (int64_t i = 0; i < N_; ++i)
+		for (int t = 0; t < deg[i]; ++t) graph_.idx[graph_.off[i] + t] = nbr[(size_t)i * k + t];
+	return PXB_OK;
 }
+
+int Driver::fit_nonminimal(const std::vector<std::vector<int64_t>> &sets, const double *weights_by_row,
+                           std::vector<double> &models_out, std::vector<int32_t> &ok) {
+	const int P = (int)sets.size();
+	models_out.assign((size_t)P * ms_, 0.0);
+	ok.assign(P, 0);
+	if (P == 0) return PXB_OK;
+	std::vector<int32_t> off(P + 1, 0), idx;
+	for (int p = 0; p < P; ++p) off[p + 1] = off[p] + (int32_t)sets[p].size();
+	idx.reserve(off[P]);
+	for (const auto &st : sets)
+		for (int64_t i : st) idx.push_back((int32_t)i);
+	size_t wcount = 0;
+	if (weights_by_row) wcount = sets[0].size(); // weighted fits are issued one problem at a time (IRLS)
+	const size_t bytes = sizeof(int32_t) * (off.size() + idx.size()) + 64;
+	PXB_TRY(ctx_->idx.reserve(bytes));
+	int32_t *d_off = ctx_->idx.as<int32_t>(), *d_idx = d_off + off.size();
+	PXB_TRY(ctx_->models.reserve(sizeof(double) * (size_t)P * ms_));
+	PXB_TRY(ctx_->outA.reserve(sizeof(int32_t) * (size_t)P));
+	double *d_w = nullptr;
+	if (weights_by_row) {
+		PXB_TRY(ctx_->pref2.reserve(sizeof(double) * wcount));
+		d_w = ctx_->pref2.as<double>();
+		PXB_CUDA(cudaMemcpyAsync(d_w, weights_by_row, sizeof(double) * wcount, cudaMemcpyHostToDevice, ctx_->stream));
+	}
+	PXB_CUDA(cudaMemcpyAsync(d_off, off.data(), sizeof(int32_t) * off.size(), cudaMemcpyHostToDevice, ctx_->stream));
+	PXB_CUDA(cudaMemcpyAsync(d_idx, idx.data(), sizeof(int32_t) * idx.size(), cudaMemcpyHostToDevice, ctx_->stream));
+	PXB_TRY(launch_fit_h(ctx_, P, d_off, d_idx, d_w, ctx_->models.as<double>(), ctx_->outA.as<int32_t>()));
+	PXB_CUDA(cudaMemcpyAsync(models_out.data(), ctx_->models.ptr, sizeof(double) * models_out.size(),
+	                         cudaMemcpyDeviceToHost, ctx_->stream));
+	PXB_CUDA(cudaMemcpyAsync(ok.data(), ctx_->outA.ptr, sizeof(int32_t) * ok.size(), cudaMemcpyDeviceToHost, ctx_->stream));
+	PXB_CUDA(cudaStreamSynchronize(ctx_->stream));
+	return PXB_OK;
+}
+
+// gcr/GCRANSAC.h:914-1022. Unary terms come from the device (k_lo_unary). Without a smoothness term the st-cut
+// decomposes per node: SINK (= inlier) iff the t-link residual source-sink is negative, i.e. e0 > e1.
+int Driver::lo_labeling(const double *model, std::vector<int64_t> &inliers) {
+	std::vector<double> d(N_), e0(N_), e1(N_);
+	PXB_TRY(pxb_lo_unary_terms(ctx_, model, s_.threshold, s_.lambda, d.data(), e0.data(), e1.data()));
+	inliers.clear();
+	if (!(s_.lambda > 0) || graph_.idx.empty()) {
+		for (int64_t i = 0; i < N_; ++i)
+			if (e1[i] - e0[i] < 0) inliers.push_back(i); // tr_cap = cap_source - cap_sink = e1 - e0 (energy.h:204-208)
+		return PXB_OK;
+	}
+	std::vector<uint8_t> seg(N_);
+	PXB_TRY(pxb_lo_graph_cut(ctx_, e0.data(), e1.data(), d.data(), N_, s_.lambda, graph_.off.data(), graph_.idx.data(),
+	                         seg.data()));
+	for (int64_t i = 0; i < N_; ++i)
+		if (seg[i]) inliers.push_back(i);
+	return PXB_OK;
+}
+
+// gcr/GCRANSAC.h:158-173
+size_t Driver::iteration_number_for(size_t inliers, double log_probability) const {
+	const double q = std::pow(static_cast<double>(inliers) / (double)N_, (double)m_);
+	const double log2 = std::log(1 - q);
+	if (std::fabs(log2) < std::numeric_limits<double>::epsilon()) return std::numeric_limits<size_t>::max();
+	const double iter = log_probability / log2;
+	return static_cast<size_t>(iter) + 1;
+}
+
+// gcr/GCRANSAC.h:781-911. The <= 50 inner-RANSAC trials of one graph cut are independent given the cut: their samples
+// are drawn up front (same LO-sampler stream as the sequential loop), fitted in one launch, scored in one launch, and
+// the max_score bookkeeping is replayed in trial order.
+int Driver::local_optimization(Sampler &lo_sampler, std::vector<double> &best_model, Score &best_score, double T2) {
+	const size_t inlier_limit = 7 * (size_t)m_; // estimator.inlierLimit()
+	Score max_score = best_score;
+	std::vector<double> lo_model = best_model;
+	std::vector<int64_t> inliers;
+	++lo_number_;
+	while (++graph_cut_number_ < s_.max_graph_cut_number) {
+		bool updated = false;
+		PXB_TRY(lo_labeling(lo_model.data(), inliers));
+		const size_t sample_size = std::min(inlier_limit, inliers.size());
+		std::vector<std::vector<int64_t>> sets;
+		if (sample_size < inliers.size()) {
+			std::vector<size_t> pool(inliers.begin(), inliers.end()), sub(sample_size);
+			for (size_t trial = 0; trial < s_.max_local_optimization_number; ++trial) {
+				lo_sampler.sample(pool, sub.data(), sample_size);
+				sets.emplace_back(sub.begin(), sub.end());
+			}
+		} else if ((size_t)m_ < inliers.size()) {
+			sets.emplace_back(inliers); // every trial refits the same set: one evaluation is equivalent
+		} else {
+			break;
+		}
+		std::vector<double> fitted;
+		std::vector<int32_t> ok;
+		PXB_TRY(fit_nonminimal(sets, nullptr, fitted, ok));
+		std::vector<int64_t> cnt;
+		std::vector<double> val, shr;
+		PXB_TRY(score_models(fitted.data(), (int64_t)sets.size(), T2, cnt, val, shr));
+		for (size_t t = 0; t < sets.size(); ++t) {
+			if (!ok[t]) continue; // estimateModelNonminimal failed -> `continue` (:851-855)
+			const Score sc = finish_score(cnt[t], val[t], shr[t], max_score.inliers);
+			if (max_score.value < sc.value) {
+				updated = true;
+				max_score = sc;
+				lo_model.assign(fitted.begin() + t * ms_, fitted.begin() + (t + 1) * ms_);
+			}
+		}
+		if (!updated) break;
+	}
+	if (best_score.value < max_score.value) {
+		best_score = max_score;
+		best_model = lo_model;
+	}
+	return PXB_OK;
+}
+
+// gcr/GCRANSAC.h:631-759 (single-model estimators: the models.size()==1 branch)
+int Driver::irls(std::vector<int64_t> &inliers, std::vector<double> &model, double T2, bool &success) {
+	success = false;
+	if (inliers.size() <= (size_t)m_) return PXB_OK;
+	size_t iterations = 0;
+	std::vector<double> weights(N_);
+	while (++iterations < s_.max_least_squares_iterations) {
+		// Tukey bisquare weights of the inliers (:658-669); all other entries are zero (:686-688 resets them)
+		PXB_TRY(pxb_tukey_weights(ctx_, model.data(), T2, weights.data()));
+		std::vector<double> w_point(N_, 0.0);
+		for (int64_t i : inliers) w_point[i] = weights[i];
+		// the solver reads weights_[row], row = 0..n-1 of the gathered sample (see k_fit_h)
+		std::vector<double> w_row(w_point.begin(), w_point.begin() + inliers.size());
+		std::vector<std::vector<int64_t>> sets(1, inliers);
+		std::vector<double> fitted;
+		std::vector<int32_t> ok;
+		PXB_TRY(fit_nonminimal(sets, w_row.data(), fitted, ok));
+		if (!ok[0]) break;
+		std::vector<int64_t> cnt;
+		std::vector<double> val, shr;
+		PXB_TRY(score_models(fitted.data(), 1, T2, cnt, val, shr));
+		const Score sc = finish_score(cnt[0], val[0], shr[0], 0);
+		if ((size_t)sc.inliers < (size_t)m_) break;
+		if ((size_t)sc.inliers <= inliers.size()) break;
+		model = fitted;
+		PXB_TRY(inliers_of(model.data(), T2, inliers));
+	}
+	success = iterations > 1;
+	return PXB_OK;
+}
+
+// gcr/GCRANSAC.h:203-628
+int Driver::propose(uint64_t round_seed, std::vector<double> &model_out, bool &found) {
+	found = false;
+	iteration_number_ = graph_cut_number_ = lo_number_ = 0;
+	proposal_inliers_.clear();
+	const double log_probability = std::log(1.0 - s_.confidence);
+	size_t max_iteration = iteration_number_for(1, log_probability);
+	const double truncated_threshold = 3.0 / 2.0 * s_.threshold;
+	const double T2 = truncated_threshold * truncated_threshold; // :254-255 spelling
+	std::unique_ptr<Sampler> main_sampler;
+	if (s_.sampler_id == 3 && !graph_.idx.empty())
+		main_sampler.reset(new NapsacSampler(round_seed * 2 + 1, &graph_));
+	else
+		main_sampler.reset(new UniformSampler(round_seed * 2 + 1));
+	UniformSampler lo_sampler(round_seed * 2 + 2);
+	std::vector<size_t> pool(N_);
+	std::iota(pool.begin(), pool.end(), 0);
+
+	Score best_score;
+	std::vector<double> best_model;
+
+	// ---- block state ----
+	const size_t B = 512;
+	std::vector<int64_t> samples;       // B x m
+	std::vector<uint8_t> sampled_ok;    // sampler success per slot
+	std::vector<double> blk_models;     // B x maxsol x ms
+	std::vector<int32_t> blk_n;
+	std::vector<uint8_t> blk_sv, blk_mv;
+	std::vector<int64_t> blk_cnt;       // per (slot, solution)
+	std::vector<double> blk_val, blk_shr;
+	size_t cursor = 0, filled = 0;
+	auto refill = [&](size_t want) -> int {
+		want = std::max<size_t>(std::min(want, B), 32);
+		samples.assign(want * m_, 0);
+		sampled_ok.assign(want, 0);
+		std::vector<size_t> sub(m_);
+		for (size_t b = 0; b < want; ++b) {
+			sampled_ok[b] = main_sampler->sample(pool, sub.data(), (size_t)m_) ? 1 : 0;
+			for (int j = 0; j < m_; ++j) samples[b * m_ + j] = sampled_ok[b] ? (int64_t)sub[j] : (int64_t)j;
+		}
+		blk_models.assign(want * maxsol_ * ms_, 0.0);
+		blk_n.assign(want, 0);
+		blk_sv.assign(want, 0);
+		blk_mv.assign(want, 0);
+		PXB_TRY(pxb_solve_minimal(ctx_, samples.data(), (int64_t)want, blk_models.data(), blk_n.data(), blk_sv.data(),
+		                          blk_mv.data()));
+		PXB_TRY(score_models(blk_models.data(), (int64_t)(want * maxsol_), T2, blk_cnt, blk_val, blk_shr));
+		cursor = 0;
+		filled = want;
+		return PXB_OK;
+	};
+
+	while (s_.min_iteration_number > iteration_number_ ||
+	       iteration_number_ < std::min(max_iteration, s_.max_iters)) {
+		bool do_local_optimization = false;
+		++iteration_number_;
+		// :296-339 select a sample that yields at least one model (<= 100 attempts)
+		int unsuccessful = -1;
+		size_t slot = SIZE_MAX;
+		while (++unsuccessful < (int)s_.max_unsuccessful_model_generations) {
+			if (cursor >= filled) {
+				const size_t cap = std::min(max_iteration, s_.max_iters);
+				const size_t remaining = cap > iteration_number_ ? cap - iteration_number_ + 1 : 1;
+				PXB_TRY(refill(std::max(remaining, s_.min_iteration_number)));
+			}
+			const size_t b = cursor++;
+			if (!sampled_ok[b]) continue;        // sampler failure (:300-310)
+			if (!blk_sv[b]) continue;            // isValidSample (:314-323)
+			if (blk_n[b] > 0) {                  // estimateModel (:326-330)
+				slot = b;
+				break;
+			}
+		}
+		iteration_number_ += (size_t)unsuccessful; // :341
+		if (slot != SIZE_MAX) {
+			for (int j = 0; j < blk_n[slot]; ++j) {
+				const size_t q = slot * maxsol_ + j;
+				const Score sc = finish_score(blk_cnt[q], blk_val[q], blk_shr[q], best_score.inliers);
+				// :441-447: better score AND Estimator::isValidModel (H: determinant test, evaluated on the device)
+				if (best_score.value < sc.value && blk_mv[slot]) {
+					best_model.assign(blk_models.begin() + q * ms_, blk_models.begin() + (q + 1) * ms_);
+					best_score = sc;
+					do_local_optimization = iteration_number_ > s_.min_iteration_number_before_lo &&
+					                        (size_t)best_score.inliers > (size_t)m_; // :464-465
+					max_iteration = iteration_number_for((size_t)best_score.inliers, log_probability);
+				}
+			}
+		}
+		if (do_local_optimization) { // :482-503
+			++lo_number_;
+			PXB_TRY(local_optimization(lo_sampler, best_model, best_score, T2));
+			max_iteration = iteration_number_for((size_t)best_score.inliers, log_probability);
+		}
+	}
+	if ((size_t)best_score.inliers <= (size_t)m_) return PXB_OK; // :522-528 no model found
+
+	if (lo_number_ == 0) { // :531-544 final LO if it never ran
+		++lo_number_;
+		PXB_TRY(local_optimization(lo_sampler, best_model, best_score, T2));
+	}
+	std::vector<int64_t> best_inliers;
+	PXB_TRY(inliers_of(best_model.data(), T2, best_inliers));
+	best_score.inliers = (int64_t)best_inliers.size();
+
+	// :561-590 iterated least squares polishing
+	bool refit_applied = false;
+	{
+		std::vector<double> model = best_model;
+		std::vector<int64_t> inl = best_inliers;
+		bool success = false;
+		PXB_TRY(irls(inl, model, T2, success));
+		if (success) {
+			std::vector<int64_t> cnt;
+			std::vector<double> val, shr;
+			PXB_TRY(score_models(model.data(), 1, T2, cnt, val, shr));
+			const Score sc = finish_score(cnt[0], val[0], shr[0], 0);
+			if (best_score.value < sc.value) {
+				refit_applied = true;
+				best_model = model;
+				PXB_TRY(inliers_of(best_model.data(), T2, best_inliers));
+			}
+		}
+	}
+	if (!refit_applied) { // :592-618 one least-squares fit on all inliers
+		std::vector<std::vector<int64_t>> sets(1, best_inliers);
+		std::vector<double> fitted;
+		std::vector<int32_t> ok;
+		PXB_TRY(fit_nonminimal(sets, nullptr, fitted, ok));
+		if (ok[0]) {
+			std::vector<int64_t> cnt;
+			std::vector<double> val, shr;
+			PXB_TRY(score_models(fitted.data(), 1, T2, cnt, val, shr));
+			const Score sc = finish_score(cnt[0], val[0], shr[0], 0);
+			if (best_score.value < sc.value) {
+				best_model = fitted;
+				PXB_TRY(inliers_of(best_model.data(), T2, best_inliers));
+			}
+		}
+	}
+	proposal_inliers_ = best_inliers; // statistics.inliers (:621)
+	model_out = best_model;
+	found = true;
+	return PXB_OK;
+}
+
+// px/include/progressive_x.h:565-591
+int Driver::putative_model_valid(const std::vector<double> &model, std::vector<double> &pref, bool &valid) {
+	valid = false;
+	if (proposal_inliers_.size() < std::max((size_t)m_, s_.min_inliers)) return PXB_OK;
+	const double T = 9.0 / 4.0 * s_.threshold * s_.threshold; // :523 spelling
+	pref.resize(N_);
+	PXB_TRY(pxb_preference_vector(ctx_, model.data(), T, pref.data()));
+	double tanimoto = 0.0;
+	PXB_TRY(pxb_tanimoto(ctx_, pref.data(), compound_pref_.data(), N_, &tanimoto));
+	// `maximum_tanimoto_similarity < similarity` rejects; NaN (0/0 on the first proposal) compares false -> accepted
+	if (s_.max_tanimoto < tanimoto) return PXB_OK;
+	valid = true;
+	return PXB_OK;
+}
+
+// px/include/PEARL.h:405-472 (run), :476-555 (labeling), :319-401 (parameterEstimation), :275-315 (rejectInstances)
+int Driver::pearl() {
+	size_t iteration_number = 0;
+	double energy = std::numeric_limits<double>::max(), previous_energy = -1.0;
+	bool model_rejected = false, convergence = false;
+	std::vector<int32_t> labels(N_, 0), prev_labels;
+	bool have_labels = false;
+	const double label_cost = (double)s_.min_inliers; // model_complexity_weight(minimum_inlier_number_) (:147)
+	while (!convergence && iteration_number++ < 100) {
+		const bool init_with_previous = iteration_number > 1 && !model_rejected;
+		// ---- labeling ----
+		const int64_t L = (int64_t)models_.size();
+		if (L == 0) break;
+		std::vector<double> flat((size_t)L * ms_);
+		for (int64_t l = 0; l < L; ++l) std::copy(models_[l].model.begin(), models_[l].model.end(), flat.begin() + l * ms_);
+		std::vector<double> D((size_t)N_ * (L + 1));
+		PXB_TRY(pxb_pearl_datacost(ctx_, flat.data(), L, s_.threshold, s_.lambda, D.data()));
+		const int32_t *init = (init_with_previous && have_labels) ? labels.data() : nullptr;
+		prev_labels = labels;
+		const bool smooth = s_.lambda > 0.0 && !graph_.idx.empty();
+		PXB_TRY(pxb_pearl_label(ctx_, D.data(), N_, (int32_t)(L + 1), s_.lambda, label_cost,
+		                        smooth ? graph_.off.data() : nullptr, smooth ? graph_.idx.data() : nullptr,
+		                        init ? prev_labels.data() : nullptr, labels.data(), &energy));
+		have_labels = true;
+		// ---- parameterEstimation ----
+		bool model_parameters_changed = false;
+		model_rejected = false;
+		std::vector<std::vector<int64_t>> per_instance((size_t)L);
+		size_t outliers = 0;
+		for (int64_t i = 0; i < N_; ++i) {
+			if (labels[i] < L)
+				per_instance[(size_t)labels[i]].push_back(i);
+			else
+				++outliers;
+		}
+		{
+			std::vector<double> before(L), after(L);
+			std::vector<int64_t> counts(L);
+			PXB_TRY(pxb_segment_residual_sums(ctx_, flat.data(), L, labels.data(), before.data(), counts.data()));
+			std::vector<std::vector<int64_t>> sets;
+			std::vector<int64_t> which;
+			for (int64_t l = 0; l < L; ++l)
+				if (per_instance[l].size() >= (size_t)m_) { // nonMinimalSampleSize() == sampleSize() for H (:363-365)
+					sets.push_back(per_instance[l]);
+					which.push_back(l);
+				}
+			std::vector<double> fitted;
+			std::vector<int32_t> ok;
+			PXB_TRY(fit_nonminimal(sets, nullptr, fitted, ok));
+			std::vector<double> cand = flat;
+			for (size_t t = 0; t < which.size(); ++t)
+				if (ok[t]) std::copy(fitted.begin() + t * ms_, fitted.begin() + (t + 1) * ms_, cand.begin() + which[t] * ms_);
+			PXB_TRY(pxb_segment_residual_sums(ctx_, cand.data(), L, labels.data(), after.data(), counts.data()));
+			for (size_t t = 0; t < which.size(); ++t) {
+				const int64_t l = which[t];
+				if (ok[t] && after[l] < before[l]) { // :393-399
+					models_[l].model.assign(cand.begin() + l * ms_, cand.begin() + (l + 1) * ms_);
+					model_parameters_changed = true;
+				}
+			}
+		}
+		// ---- rejectInstances (back to front) ----
+		for (int64_t l = L - 1; l >= 0; --l)
+			if (per_instance[l].size() < s_.min_inliers) {
+				outliers += per_instance[l].size();
+				models_.erase(models_.begin() + l);
+				per_instance.erase(per_instance.begin() + l);
+				model_rejected = true;
+			}
+		pearl_outliers_ = outliers;
+		if (!model_rejected && !model_parameters_changed && std::fabs(energy - previous_energy) < 1e-5 &&
+		    iteration_number > 1)
+			convergence = true;
+		previous_energy = energy;
+	}
+	labeling_.assign(labels.begin(), labels.end()); // getLabeling (:218-249): raw gco labels of the last labeling
+	return PXB_OK;
+}
+
+// px/include/progressive_x.h:495-513
+size_t Driver::predicted_unseen_inliers(size_t iterations, size_t compound_inliers) const {
+	const size_t unseen_point_number = (size_t)N_ - compound_inliers;
+	const double one_over_iteration_number = 1.0 / (double)iterations;
+	const double one_over_sample_size = 1.0 / (double)m_;
+	const double inlier_ratio =
+	    std::pow(1.0 - std::pow(1.0 - s_.confidence, one_over_iteration_number), one_over_sample_size);
+	return static_cast<size_t>(std::round((double)unseen_point_number * inlier_ratio));
+}
+
+// px/include/progressive_x.h:251-489
+int Driver::run() {
+	labeling_.assign((size_t)N_, 0);
+	compound_pref_.assign((size_t)N_, 0.0);
+	models_.clear();
+	size_t number_of_ransac_iterations = 0, unaccepted = 0, unseen_inliers = (size_t)N_;
+	(void)unseen_inliers;
+	for (size_t it = 0; it < 10; ++it) { // :272 hard cap
+		std::vector<double> model;
+		bool found = false;
+		PXB_TRY(propose(s_.seed * 1000003ull + it, model, found));
+		if (!found) continue; // :301-303
+		number_of_ransac_iterations += iteration_number_;
+		std::vector<double> pref;
+		bool valid = false;
+		PXB_TRY(putative_model_valid(model, pref, valid));
+		if (!valid) { // :334-346 (the counter is never reset)
+			++unaccepted;
+			if (unaccepted == s_.max_proposals_without_change) break;
+			continue;
+		}
+		Instance inst;
+		inst.model = model;
+		inst.pref = pref;
+		models_.push_back(std::move(inst));
+		size_t first_model_inliers_stat = 0;
+		if (models_.size() == 1) { // :375-385
+			std::fill(labeling_.begin(), labeling_.end(), 1);
+			for (int64_t i : proposal_inliers_) labeling_[(size_t)i] = 0;
+			first_model_inliers_stat = 1; // inliers_of_each_model.size(), a model count (:451 quirk)
+		} else {
+			PXB_TRY(pearl()); // :390-396
+		}
+		// updateCompoundModel (:597-624): max over the *stored* preference vectors
+		if (!models_.empty()) {
+			std::vector<double> prefs((size_t)models_.size() * N_);
+			for (size_t k = 0; k < models_.size(); ++k)
+				std::copy(models_[k].pref.begin(), models_[k].pref.end(), prefs.begin() + k * N_);
+			PXB_TRY(pxb_compound_max(ctx_, prefs.data(), (int64_t)models_.size(), N_, compound_pref_.data()));
+		}
+		size_t unseen;
+		if (models_.size() == 1 && first_model_inliers_stat)
+			unseen = predicted_unseen_inliers(number_of_ransac_iterations, first_model_inliers_stat);
+		else
+			unseen = predicted_unseen_inliers(number_of_ransac_iterations, (size_t)N_ - pearl_outliers_);
+		if (s_.do_logging)
+			fprintf(stdout, "[pxb] round %zu: %zu instances, %zu RANSAC iterations, predicted unseen inliers %zu\n", it + 1,
+			        models_.size(), number_of_ransac_iterations, unseen);
+		if (unseen < s_.min_inliers) break;              // :468
+		if (models_.size() >= s_.max_models) break;      // :472
+	}
+	return PXB_OK;
+}
+
+int run_two_view(pxb_ctx *ctx, int type, const double *corr, int64_t N, int64_t *labeling_out, double *models_out,
+                 int64_t max_models_out, double lambda, double threshold, double confidence, double radius,
+                 double max_tanimoto, size_t max_iters, size_t min_points, int max_models, size_t sampler_id,
+                 double scoring_exponent, bool set_exponent, int do_logging, uint64_t seed) {
+	if (!ctx || !corr || !labeling_out || !models_out || N < 4) {
+		set_error("bad argument");
+		return PXB_ERR_ARGUMENT;
+	}
+	if (sampler_id > 3) { // progressivex_python.cpp:240-245
+		fprintf(stderr, "Unknown sampler identifier: %zu. The accepted samplers are 0 (uniform sampling), 1 (PROSAC "
+		                "sampling), 2 (P-NAPSAC sampling)\n", sampler_id);
+		return 0;
+	}
+	PXB_TRY(pxb_upload_points(ctx, type, corr, N));
+	Settings s;
+	s.type = type;
+	s.min_inliers = min_points;
+	s.threshold = threshold;
+	s.confidence = confidence;
+	s.max_tanimoto = max_tanimoto;
+	s.lambda = lambda;
+	s.max_iters = max_iters;
+	if (max_models > 0) s.max_models = (size_t)max_models;
+	s.sampler_id = sampler_id;
+	if (set_exponent) s.exponent = (int)scoring_exponent; // setExponent(const int) truncates (progressive_x.h:551)
+	s.do_logging = do_logging != 0;
+	if (seed == 0) seed = (uint64_t)std::chrono::high_resolution_clock::now().time_since_epoch().count();
+	s.seed = seed;
+	Driver drv(ctx, s);
+	if (lambda > 0.0 || sampler_id == 3) PXB_TRY(drv.build_graph(radius, 8));
+	PXB_TRY(drv.run());
+	const auto &inst = drv.instances();
+	const int ms = model_size(type);
+	const int64_t M = (int64_t)inst.size();
+	for (int64_t k = 0; k < std::min(M, max_models_out); ++k)
+		std::memcpy(models_out + k * ms, inst[k].model.data(), sizeof(double) * ms);
+	std::memcpy(labeling_out, drv.labeling().data(), sizeof(int64_t) * (size_t)N);
+	return (int)M;
+}
+
+} // namespace
+} // namespace pxb
+
+using namespace pxb;
+
+extern "C" {
+
+int pxb_find_homographies(pxb_ctx *ctx, const double *correspondences, int64_t N, int64_t *labeling_out,
+                          double *models_out, int64_t max_models_out, size_t, size_t, size_t, size_t,
+                          double spatial_coherence_weight, double threshold, double confidence,
+                          double neighborhood_ball_radius, double maximum_tanimoto_similarity, size_t max_iters,
+                          size_t minimum_point_number, int maximum_model_number, size_t sampler_id,
+                          double scoring_exponent, int do_logging, uint64_t seed) {
+	return run_two_view(ctx, PXB_MODEL_HOMOGRAPHY, correspondences, N, labeling_out, models_out, max_models_out,
+	                    spatial_coherence_weight, threshold, confidence, neighborhood_ball_radius,
+	                    maximum_tanimoto_similarity, max_iters, minimum_point_number, maximum_model_number, sampler_id,
+	                    scoring_exponent, true, do_logging, seed);
+}
+
 int pxb_find_two_view_motions(pxb_ctx *, const double *, int64_t, int64_t *, double *, int64_t, size_t, size_t,
                               size_t, size_t, double, double, double, double, double, size_t, size_t, int, size_t,
                               double, int, uint64_t) {
-	set_error("not implemented yet");
+	set_error("findTwoViewMotions: the non-minimal F solvers (8-point + LM, SURVEY.md 8f-1) are not implemented yet; "
+	          "the F operators (7-point solver, Sampson matrix, score, PEARL) are available through the operator ABI");
 	return PXB_ERR_UNSUPPORTED;
 }
-int pxb_find_6d_poses(pxb_ctx *, const double *, const double *, const double *, int64_t, int64_t *, double *,
-                      int64_t, double, double, double, double, double, size_t, size_t, int, uint64_t) {
-	set_error("not implemented yet");
+
+int pxb_find_6d_poses(pxb_ctx *, const double *, const double *, const double *, int64_t, int64_t *, double *, int64_t,
+                      double, double, double, double, double, size_t, size_t, int, uint64_t) {
+	set_error("find6DPoses: the non-minimal PnP solvers (EPnP + LM, SURVEY.md 8f-1) are not implemented yet; the PnP "
+	          "operators (P3P solver, reprojection matrix, score, PEARL) are available through the operator ABI");
 	return PXB_ERR_UNSUPPORTED;
 }
-}
+
+} // extern "C"

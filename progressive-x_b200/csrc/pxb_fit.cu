@@ -1,0 +1,301 @@
+// pxb_fit.cu -- the two "next" rows the end-to-end driver cannot live without:
+//
+//   k_knn_graph   f-3  neighbourhood graph: exact radius search truncated to the k nearest, brute force over all
+//                      pairs (N^2 float64 distance evaluations: 2.5e9 at N = 50k, a few ms). Replaces the reference's
+//                      randomised FLANN kd-trees (gcr/neighborhood/flann_neighborhood_graph.h:100-139), which return
+//                      ~5 approximate neighbours per point and differ between two identical calls; this one is
+//                      deterministic (ties broken by index) and yields directed CSR lists.
+//   k_fit_h       f-1  batched non-minimal homography fits: Hartley normalisation (gcr/estimators/
+//                      homography_estimator.h:201-309) + the 2n x 8 inhomogeneous DLT of
+//                      HomographyFourPointSolver::estimateNonMinimalModel (solver_homography_four_point.h:192-264),
+//                      solved through the 8x8 normal equations (the reference calls Eigen's colPivHouseholderQr on the
+//                      2n x 8 system: same least-squares solution, agreement ~1e-9 relative after normalisation).
+//                      One block per problem; A^T A / A^T b are block reductions with the library's fixed topology.
+#include <cfloat>
+
+#include "pxb_internal.h"
+#include "pxb_residuals.cuh"
+
+namespace pxb {
+
+// ------------------------------------------------------------------------------------------------
+// neighbourhood graph
+// ------------------------------------------------------------------------------------------------
+constexpr int kKnnMax = 16;
+constexpr int kKnnTile = 256;
+
+template <int DIM>
+__global__ void __launch_bounds__(kKnnTile)
+    k_knn_graph(const double *__restrict__ aos, int64_t N, double radius2, int k, int32_t *__restrict__ nbr /*N*k*/,
+                int32_t *__restrict__ deg) {
+	__shared__ double s_pts[kKnnTile * DIM];
+	const int64_t i = (int64_t)blockIdx.x * kKnnTile + threadIdx.x;
+	double me[DIM];
+#pragma unroll
+	for (int c = 0; c < DIM; ++c) me[c] = (i < N) ? aos[i * DIM + c] : 0.0;
+	double bd[kKnnMax];
+	int bi[kKnnMax];
+	int cnt = 0;
+	for (int64_t j0 = 0; j0 < N; j0 += kKnnTile) {
+		const int nt = (int)min((int64_t)kKnnTile, N - j0);
+		__syncthreads();
+		for (int t = threadIdx.x; t < nt * DIM; t += kKnnTile) s_pts[t] = aos[j0 * DIM + t];
+		__syncthreads();
+		if (i >= N) continue;
+		for (int t = 0; t < nt; ++t) {
+			double d2 = 0.0;
+#pragma unroll
+			for (int c = 0; c < DIM; ++c) {
+				const double d = me[c] - s_pts[t * DIM + c];
+				d2 += d * d;
+			}
+			const int64_t j = j0 + t;
+			if (j == i || !(d2 <= radius2)) continue;
+			if (cnt == k && !(d2 < bd[k - 1])) continue; // j ascending: on equal distance the lower index stays
+			// insertion into the sorted list (ascending distance, then ascending index)
+			int pos = cnt < k ? cnt : k - 1;
+			while (pos > 0 && bd[pos - 1] > d2) {
+				bd[pos] = bd[pos - 1];
+				bi[pos] = bi[pos - 1];
+				--pos;
+			}
+			bd[pos] = d2;
+			bi[pos] = (int)j;
+			if (cnt < k) ++cnt;
+		}
+	}
+	if (i < N) {
+		deg[i] = cnt;
+		for (int t = 0; t < k; ++t) nbr[i * k + t] = t < cnt ? bi[t] : -1;
+	}
+}
+
+int launch_knn_graph(pxb_ctx *ctx, double radius, int k, int32_t *nbr, int32_t *deg) {
+	const Points &p = ctx->pts;
+	if (k < 1 || k > kKnnMax) {
+		set_error("k must be in [1, %d]", kKnnMax);
+		return PXB_ERR_ARGUMENT;
+	}
+	const unsigned grid = (unsigned)((p.N + kKnnTile - 1) / kKnnTile);
+	if (p.dim == 4)
+		k_knn_graph<4><<<grid, kKnnTile, 0, ctx->stream>>>(p.aos, p.N, radius * radius, k, nbr, deg);
+	else
+		k_knn_graph<5><<<grid, kKnnTile, 0, ctx->stream>>>(p.aos, p.N, radius * radius, k, nbr, deg);
+	ctx->launches++;
+	PXB_CUDA(cudaGetLastError());
+	return PXB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// batched non-minimal homography fit
+// ------------------------------------------------------------------------------------------------
+constexpr int kFitThreads = 256;
+
+__device__ __forceinline__ double fit_block_sum(double x, double *s_tmp /*8*/) {
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) x = add(x, __shfl_xor_sync(0xffffffffu, x, o));
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	__syncthreads();
+	if (lane == 0) s_tmp[warp] = x;
+	__syncthreads();
+	double t = 0.0;
+#pragma unroll
+	for (int w = 0; w < kFitThreads / 32; ++w) t = add(t, s_tmp[w]);
+	return t;
+}
+
+// problems: CSR (off[P+1], idx[]) of point indices; weights: NULL, or an array indexed BY ROW OF THE NORMALISED SAMPLE
+// (the reference passes weights_[i], i = 0..n-1, once the sample has been gathered into `normalized_points` with a null
+// sample pointer -- solver_homography_four_point.h:207-220 with sample_ == nullptr -- i.e. the first n entries of the
+// caller's per-point weight array; replicated as is).
+__global__ void __launch_bounds__(kFitThreads)
+    k_fit_h(const double *__restrict__ aos, const int32_t *__restrict__ off, const int32_t *__restrict__ idx,
+            const double *__restrict__ weights, double *__restrict__ H_out, int32_t *__restrict__ ok_out) {
+	__shared__ double s_tmp[kFitThreads / 32];
+	__shared__ double s_acc[44];
+	const int pb = blockIdx.x;
+	const int beg = off[pb], n = off[pb + 1] - beg;
+	const int tid = threadIdx.x;
+	if (n < 4) { // estimateModelNonminimal: sample_number_ < nonMinimalSampleSize() -> false
+		if (tid == 0) ok_out[pb] = 0;
+		return;
+	}
+	// ---- normalizePoints (homography_estimator.h:201-309): mass points, mean distance, sqrt(2)/mean ----
+	double sx1 = 0, sy1 = 0, sx2 = 0, sy2 = 0;
+	for (int t = tid; t < n; t += kFitThreads) {
+		const double *q = aos + 4 * (int64_t)idx[beg + t];
+		sx1 = add(sx1, q[0]);
+		sy1 = add(sy1, q[1]);
+		sx2 = add(sx2, q[2]);
+		sy2 = add(sy2, q[3]);
+	}
+	const double mx1 = divd(fit_block_sum(sx1, s_tmp), (double)n), my1 = divd(fit_block_sum(sy1, s_tmp), (double)n);
+	const double mx2 = divd(fit_block_sum(sx2, s_tmp), (double)n), my2 = divd(fit_block_sum(sy2, s_tmp), (double)n);
+	double d1 = 0, d2 = 0;
+	for (int t = tid; t < n; t += kFitThreads) {
+		const double *q = aos + 4 * (int64_t)idx[beg + t];
+		const double dx1 = sub(mx1, q[0]), dy1 = sub(my1, q[1]), dx2 = sub(mx2, q[2]), dy2 = sub(my2, q[3]);
+		d1 = add(d1, __dsqrt_rn(add(mul(dx1, dx1), mul(dy1, dy1))));
+		d2 = add(d2, __dsqrt_rn(add(mul(dx2, dx2), mul(dy2, dy2))));
+	}
+	const double avg1 = divd(fit_block_sum(d1, s_tmp), (double)n), avg2 = divd(fit_block_sum(d2, s_tmp), (double)n);
+	const double r1 = divd(1.4142135623730951, avg1), r2 = divd(1.4142135623730951, avg2); // M_SQRT2 / mean distance
+	// ---- A^T A (upper triangle, 36) and A^T b (8) of the 2n x 8 system (solver_homography_four_point.h:207-252)
+	double acc[44];
+#pragma unroll
+	for (int a = 0; a < 44; ++a) acc[a] = 0.0;
+	for (int t = tid; t < n; t += kFitThreads) {
+		const double *q = aos + 4 * (int64_t)idx[beg + t];
+		const double x1 = mul(sub(q[0], mx1), r1), y1 = mul(sub(q[1], my1), r1);
+		const double x2 = mul(sub(q[2], mx2), r2), y2 = mul(sub(q[3], my2), r2);
+		const double w = weights ? weights[t] : 1.0;
+		const double mwx1 = mul(-w, x1), mwy1 = mul(-w, y1), wx2 = mul(w, x2), wy2 = mul(w, y2);
+		double ra[8] = {mwx1, mwy1, -w, 0, 0, 0, mul(wx2, x1), mul(wx2, y1)};
+		double rb[8] = {0, 0, 0, mwx1, mwy1, -w, mul(wy2, x1), mul(wy2, y1)};
+		const double ba = -wx2, bb = -wy2;
+		int a = 0;
+#pragma unroll
+		for (int r = 0; r < 8; ++r)
+#pragma unroll
+			for (int c = r; c < 8; ++c, ++a) acc[a] = add(acc[a], add(mul(ra[r], ra[c]), mul(rb[r], rb[c])));
+#pragma unroll
+		for (int r = 0; r < 8; ++r) acc[36 + r] = add(acc[36 + r], add(mul(ra[r], ba), mul(rb[r], bb)));
+	}
+	for (int a = 0; a < 44; ++a) {
+		const double v = fit_block_sum(acc[a], s_tmp);
+		if (tid == 0) s_acc[a] = v;
+	}
+	__syncthreads();
+	if (tid != 0) return;
+	// ---- solve the 8x8 SPD system: Gaussian elimination with partial pivoting (robust to semi-definite input)
+	double M[8][9];
+	{
+		int a = 0;
+		for (int r = 0; r < 8; ++r)
+			for (int c = r; c < 8; ++c, ++a) {
+				M[r][c] = s_acc[a];
+				M[c][r] = s_acc[a];
+			}
+		for (int r = 0; r < 8; ++r) M[r][8] = s_acc[36 + r];
+	}
+	bool singular = false;
+	for (int c = 0; c < 8; ++c) {
+		int piv = c;
+		double best = fabs(M[c][c]);
+		for (int r = c + 1; r < 8; ++r)
+			if (fabs(M[r][c]) > best) {
+				best = fabs(M[r][c]);
+				piv = r;
+			}
+		if (!(best > 0.0)) {
+			singular = true;
+			break;
+		}
+		if (piv != c)
+			for (int j = 0; j < 9; ++j) {
+				const double t = M[c][j];
+				M[c][j] = M[piv][j];
+				M[piv][j] = t;
+			}
+		for (int r = c + 1; r < 8; ++r) {
+			const double f = divd(M[r][c], M[c][c]);
+			for (int j = c; j < 9; ++j) M[r][j] = sub(M[r][j], mul(f, M[c][j]));
+		}
+	}
+	double h[9];
+	if (!singular)
+		for (int r = 7; r >= 0; --r) {
+			double v = M[r][8];
+			for (int j = r + 1; j < 8; ++j) v = sub(v, mul(M[r][j], h[j]));
+			h[r] = divd(v, M[r][r]);
+		}
+	h[8] = 1.0;
+	bool bad = singular;
+	for (int r = 0; r < 8 && !bad; ++r) bad = !(fabs(h[r]) <= DBL_MAX);
+	// ---- denormalise: H = T2^-1 * Hn * T1 (homography_estimator.h:169-172); T = [r 0 -r*m; 0 r -r*m; 0 0 1]
+	// T2^-1 = [1/r2 0 mx2; 0 1/r2 my2; 0 0 1] (closed form of Eigen's 3x3 cofactor inverse up to rounding)
+	const double t1x = mul(-r1, mx1), t1y = mul(-r1, my1);
+	const double ir2 = divd(1.0, r2);
+	double A[9]; // A = T2^-1 * Hn
+	for (int c = 0; c < 3; ++c) {
+		A[0 + c] = add(mul(ir2, h[0 + c]), mul(mx2, h[6 + c]));
+		A[3 + c] = add(mul(ir2, h[3 + c]), mul(my2, h[6 + c]));
+		A[6 + c] = h[6 + c];
+	}
+	double *out = H_out + 9 * (int64_t)pb;
+	for (int r = 0; r < 3; ++r) {
+		out[3 * r + 0] = mul(A[3 * r + 0], r1);
+		out[3 * r + 1] = mul(A[3 * r + 1], r1);
+		out[3 * r + 2] = add(add(mul(A[3 * r + 0], t1x), mul(A[3 * r + 1], t1y)), A[3 * r + 2]);
+	}
+	ok_out[pb] = bad ? 0 : 1;
+}
+
+int launch_fit_h(pxb_ctx *ctx, int P, const int32_t *off, const int32_t *idx, const double *weights, double *H_out,
+                 int32_t *ok_out) {
+	if (P <= 0) return PXB_OK;
+	if (ctx->pts.type != PXB_MODEL_HOMOGRAPHY) {
+		set_error("non-minimal fitting is implemented for homographies only (F / PnP are SURVEY 8f-1 'next')");
+		return PXB_ERR_UNSUPPORTED;
+	}
+	k_fit_h<<<(unsigned)P, kFitThreads, 0, ctx->stream>>>(ctx->pts.aos, off, idx, weights, H_out, ok_out);
+	ctx->launches++;
+	PXB_CUDA(cudaGetLastError());
+	return PXB_OK;
+}
+
+} // namespace pxb
+
+extern "C" {
+using namespace pxb;
+
+int pxb_knn_graph(pxb_ctx *ctx, double radius, int k, int32_t *nbr_out_host, int32_t *deg_out_host) {
+	PXB_CHECK_ARG(ctx && nbr_out_host && deg_out_host, "null argument");
+	if (ctx->pts.N <= 0) {
+		set_error("no points uploaded");
+		return PXB_ERR_STATE;
+	}
+	const int64_t N = ctx->pts.N;
+	PXB_TRY(ctx->idx.reserve(sizeof(int32_t) * (size_t)N * (k + 1)));
+	int32_t *d_nbr = ctx->idx.as<int32_t>(), *d_deg = d_nbr + (size_t)N * k;
+	PXB_TRY(launch_knn_graph(ctx, radius, k, d_nbr, d_deg));
+	PXB_CUDA(cudaMemcpyAsync(nbr_out_host, d_nbr, sizeof(int32_t) * (size_t)N * k, cudaMemcpyDeviceToHost, ctx->stream));
+	PXB_CUDA(cudaMemcpyAsync(deg_out_host, d_deg, sizeof(int32_t) * (size_t)N, cudaMemcpyDeviceToHost, ctx->stream));
+	PXB_CUDA(cudaStreamSynchronize(ctx->stream));
+	return PXB_OK;
+}
+
+int pxb_fit_homographies(pxb_ctx *ctx, int32_t P, const int32_t *off_host, const int32_t *idx_host,
+                         const double *weights_by_row_host, double *H_out_host, int32_t *ok_out_host) {
+	PXB_CHECK_ARG(ctx && off_host && idx_host && H_out_host && ok_out_host && P >= 0, "null argument");
+	if (P == 0) return PXB_OK;
+	if (ctx->pts.N <= 0) {
+		set_error("no points uploaded");
+		return PXB_ERR_STATE;
+	}
+	const int32_t total = off_host[P];
+	for (int32_t t = 0; t < total; ++t)
+		if (idx_host[t] < 0 || idx_host[t] >= ctx->pts.N) {
+			set_error("point index %d out of range", idx_host[t]);
+			return PXB_ERR_ARGUMENT;
+		}
+	PXB_TRY(ctx->idx.reserve(sizeof(int32_t) * (size_t)(P + 1 + total) + 64));
+	int32_t *d_off = ctx->idx.as<int32_t>(), *d_idx = d_off + (P + 1);
+	PXB_TRY(ctx->models.reserve(sizeof(double) * (size_t)P * 9));
+	PXB_TRY(ctx->outA.reserve(sizeof(int32_t) * (size_t)P));
+	double *d_w = nullptr;
+	if (weights_by_row_host) {
+		PXB_CHECK_ARG(P == 1, "weighted fits are issued one problem at a time");
+		PXB_TRY(ctx->pref2.reserve(sizeof(double) * (size_t)total));
+		d_w = ctx->pref2.as<double>();
+		PXB_CUDA(cudaMemcpyAsync(d_w, weights_by_row_host, sizeof(double) * (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
+	}
+	PXB_CUDA(cudaMemcpyAsync(d_off, off_host, sizeof(int32_t) * (size_t)(P + 1), cudaMemcpyHostToDevice, ctx->stream));
+	PXB_CUDA(cudaMemcpyAsync(d_idx, idx_host, sizeof(int32_t) * (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
+	PXB_TRY(launch_fit_h(ctx, P, d_off, d_idx, d_w, ctx->models.as<double>(), ctx->outA.as<int32_t>()));
+	PXB_CUDA(cudaMemcpyAsync(H_out_host, ctx->models.ptr, sizeof(double) * (size_t)P * 9, cudaMemcpyDeviceToHost, ctx->stream));
+	PXB_CUDA(cudaMemcpyAsync(ok_out_host, ctx->outA.ptr, sizeof(int32_t) * (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
+	PXB_CUDA(cudaStreamSynchronize(ctx->stream));
+	return PXB_OK;
+}
+}

@@ -55,7 +55,7 @@ int launch_aos_to_soa(pxb_ctx *ctx) {
 // shared memory (padded to an even number of doubles so that a model is read with LDS.128 broadcasts).
 // Per evaluation: 28 FP64-pipe instructions (H), ~1.5 LDS, 1 STG, 6 range-test instructions, one branch per
 // hypothesis for the whole register tile -> the FP64 pipe (2 issue slots per instruction) is the binding unit.
-constexpr int kRmHypsPerBlock = 32;
+constexpr int kRmHypsPerBlock = 32; // 128 gains ~1% at K=10k but starves the grid at RANSAC batch sizes
 
 template <typename OUT> __device__ __forceinline__ void store_stream(OUT *p, double v);
 template <> __device__ __forceinline__ void store_stream<double>(double *p, double v) { __stcs(p, v); }

@@ -1,0 +1,76 @@
+"""End-to-end through the pyprogressivex surface (same call a user of the reference makes) on synthetic scenes.
+
+The reference is non-deterministic (std::random_device) and has no golden outputs, so the checks are the
+reference's own acceptance measure: misclassification error against ground-truth labels (dataset_comparison/utils.py)
+-- plus determinism for a fixed seed, the shape/dtype contract of bindings.cpp:152-165, and consistency of the
+returned labeling with the returned models (a point labelled k lies within the truncated threshold of model k)."""
+import itertools
+
+import numpy as np
+import pytest
+
+import pyprogressivex
+from pyprogressivex import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+
+def misclassification(gt, labels, n_models):
+    """best-permutation misclassification error (dataset_comparison/utils.py:50-66 does the same with sympy)"""
+    gt = np.where(gt < 0, -1, gt)
+    est = np.where(labels >= n_models, -1, labels)
+    ks = sorted(set(gt[gt >= 0]))
+    best = 1.0
+    ids = list(range(n_models)) + [-2] * max(0, len(ks) - n_models)
+    for perm in itertools.permutations(ids, len(ks)):
+        mapped = np.full_like(gt, -1)
+        for k, p in zip(ks, perm):
+            if p >= 0:
+                mapped[est == p] = k
+        best = min(best, float(np.mean(mapped != gt)))
+    return best
+
+
+@pytest.mark.parametrize("sampler_id", [0, 3])
+def test_find_homographies_synthetic(sampler_id):
+    corrs, gt, Hs = syn.multi_homography_scene(3000, n_planes=3, outlier_ratio=0.3, noise=0.5, seed=11)
+    models, labels = pyprogressivex.findHomographies(corrs, 1024, 768, 1024, 768, threshold=2.0, conf=0.95,
+                                                     spatial_coherence_weight=0.0, neighborhood_ball_radius=60.0,
+                                                     maximum_tanimoto_similarity=0.4, max_iters=2000,
+                                                     minimum_point_number=50, maximum_model_number=-1,
+                                                     sampler_id=sampler_id, scoring_exponent=2, seed=7)
+    M = models.shape[0] // 3
+    assert models.dtype == np.float64 and models.shape == (3 * M, 3)
+    assert labels.dtype == np.int32 and labels.shape == (3000,)
+    assert 3 <= M <= 4
+    assert misclassification(gt, labels, M) < 0.08
+    # labels are consistent with the models: an assigned point is within the truncated threshold of its model
+    T = 9.0 / 4.0 * 2.0 * 2.0
+    for k in range(M):
+        H = models[3 * k:3 * k + 3]
+        idx = np.flatnonzero(labels == k)
+        p = np.c_[corrs[idx, :2], np.ones(idx.size)] @ H.T
+        r2 = ((corrs[idx, 2:] - p[:, :2] / p[:, 2:3]) ** 2).sum(1)
+        assert (r2 <= T * (1 + 1e-9)).mean() > 0.999
+
+
+def test_find_homographies_is_deterministic_for_a_seed():
+    corrs, gt, Hs = syn.multi_homography_scene(2000, n_planes=2, outlier_ratio=0.3, seed=5)
+    a = pyprogressivex.findHomographies(corrs, 1024, 768, 1024, 768, threshold=2.0, conf=0.9, max_iters=500,
+                                        minimum_point_number=40, sampler_id=0, seed=3)
+    b = pyprogressivex.findHomographies(corrs, 1024, 768, 1024, 768, threshold=2.0, conf=0.9, max_iters=500,
+                                        minimum_point_number=40, sampler_id=0, seed=3)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_shape_errors_match_the_reference_binding():
+    with pytest.raises(ValueError):
+        pyprogressivex.findHomographies(np.zeros((10, 3)), 10, 10, 10, 10)
+    with pytest.raises(ValueError):
+        pyprogressivex.findHomographies(np.zeros((3, 4)), 10, 10, 10, 10)
+
+
+def test_unknown_sampler_returns_no_models(capfd):
+    corrs, gt, Hs = syn.multi_homography_scene(500, n_planes=2, seed=5)
+    models, labels = pyprogressivex.findHomographies(corrs, 1024, 768, 1024, 768, sampler_id=9)
+    assert models.shape[0] == 0  # progressivex_python.cpp:240-245: message on stderr, return 0
