@@ -222,6 +222,17 @@ def tukey_weights(t, pts, model, T2):
     return w
 
 
+def fit_h_nonminimal(pts, idx, weights_by_row=None):
+    pts = _f(pts)
+    idx = np.ascontiguousarray(idx, dtype=np.int64)
+    w = None if weights_by_row is None else _f(weights_by_row)
+    H = np.zeros(9)
+    L = lib()
+    L.pxo_fit_h_nonminimal.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    ok = L.pxo_fit_h_nonminimal(_p(pts), _p(idx), idx.shape[0], _p(w), _p(H))
+    return H, bool(ok)
+
+
 def greedy_ufl(D, label_cost, init_labels=None):
     D = _f(D)
     N, L1 = D.shape

@@ -779,6 +779,108 @@ void pxo_tukey_weights(int type, const double *pts, const int64_t *inliers, int6
 	}
 }
 
+// Non-minimal homography fit: RobustHomographyEstimator::estimateModelNonminimal (gcr/estimators/homography_estimator.h:
+// 140-173) = normalizePoints (:201-309) + HomographyFourPointSolver::estimateNonMinimalModel (solver_homography_four_point.h:
+// 192-264, Eigen colPivHouseholderQr().solve on the 2n x 8 system, restated as an unblocked Householder QR with column
+// pivoting) + denormalisation H = T2^-1 Hn T1. weights_by_row follows the reference's indexing (weights_[i], i = row of
+// the gathered sample). Returns 1 on success.
+int pxo_fit_h_nonminimal(const double *pts, const int64_t *idx, int64_t n, const double *weights_by_row, double *H) {
+	if (n < 4) return 0;
+	double m1x = 0, m1y = 0, m2x = 0, m2y = 0;
+	for (int64_t i = 0; i < n; ++i) {
+		const double *p = pts + 4 * idx[i];
+		m1x += p[0]; m1y += p[1]; m2x += p[2]; m2y += p[3];
+	}
+	m1x /= n; m1y /= n; m2x /= n; m2y /= n;
+	double a1 = 0, a2 = 0;
+	for (int64_t i = 0; i < n; ++i) {
+		const double *p = pts + 4 * idx[i];
+		const double dx1 = m1x - p[0], dy1 = m1y - p[1], dx2 = m2x - p[2], dy2 = m2y - p[3];
+		a1 += std::sqrt(dx1 * dx1 + dy1 * dy1);
+		a2 += std::sqrt(dx2 * dx2 + dy2 * dy2);
+	}
+	a1 /= n; a2 /= n;
+	const double r1 = M_SQRT2 / a1, r2 = M_SQRT2 / a2;
+	const int64_t rows = 2 * n;
+	std::vector<double> A((size_t)rows * 8), b((size_t)rows);
+	for (int64_t i = 0; i < n; ++i) {
+		const double *p = pts + 4 * idx[i];
+		const double x1 = (p[0] - m1x) * r1, y1 = (p[1] - m1y) * r1, x2 = (p[2] - m2x) * r2, y2 = (p[3] - m2y) * r2;
+		const double w = weights_by_row ? weights_by_row[i] : 1.0;
+		const double mwx1 = -w * x1, mwy1 = -w * y1, wx2 = w * x2, wy2 = w * y2;
+		double *ra = &A[(size_t)(2 * i) * 8], *rb = &A[(size_t)(2 * i + 1) * 8];
+		ra[0] = mwx1; ra[1] = mwy1; ra[2] = -w; ra[3] = 0; ra[4] = 0; ra[5] = 0; ra[6] = wx2 * x1; ra[7] = wx2 * y1;
+		b[2 * i] = -wx2;
+		rb[0] = 0; rb[1] = 0; rb[2] = 0; rb[3] = mwx1; rb[4] = mwy1; rb[5] = -w; rb[6] = wy2 * x1; rb[7] = wy2 * y1;
+		b[2 * i + 1] = -wy2;
+	}
+	// Householder QR with column pivoting, then back substitution on the leading rank x rank block
+	int perm[8];
+	for (int j = 0; j < 8; ++j) perm[j] = j;
+	double cn[8];
+	for (int j = 0; j < 8; ++j) {
+		cn[j] = 0;
+		for (int64_t i = 0; i < rows; ++i) cn[j] += A[i * 8 + j] * A[i * 8 + j];
+	}
+	int rank = 0;
+	double maxnorm = 0;
+	for (int k = 0; k < 8 && k < rows; ++k) {
+		int piv = k;
+		for (int j = k; j < 8; ++j) { // recompute trailing norms exactly (small problem)
+			cn[j] = 0;
+			for (int64_t i = k; i < rows; ++i) cn[j] += A[i * 8 + j] * A[i * 8 + j];
+			if (cn[j] > cn[piv]) piv = j;
+		}
+		if (k == 0) maxnorm = cn[piv];
+		if (!(cn[piv] > maxnorm * 1e-28)) break;
+		if (piv != k) {
+			for (int64_t i = 0; i < rows; ++i) std::swap(A[i * 8 + k], A[i * 8 + piv]);
+			std::swap(perm[k], perm[piv]);
+			std::swap(cn[k], cn[piv]);
+		}
+		double alpha = std::sqrt(cn[k]);
+		if (A[(size_t)k * 8 + k] > 0) alpha = -alpha;
+		std::vector<double> v((size_t)(rows - k));
+		for (int64_t i = k; i < rows; ++i) v[i - k] = A[i * 8 + k];
+		v[0] -= alpha;
+		double vnorm2 = 0;
+		for (double t : v) vnorm2 += t * t;
+		if (vnorm2 > 0) {
+			for (int j = k; j < 8; ++j) {
+				double s = 0;
+				for (int64_t i = k; i < rows; ++i) s += v[i - k] * A[i * 8 + j];
+				s = 2.0 * s / vnorm2;
+				for (int64_t i = k; i < rows; ++i) A[i * 8 + j] -= s * v[i - k];
+			}
+			double s = 0;
+			for (int64_t i = k; i < rows; ++i) s += v[i - k] * b[i];
+			s = 2.0 * s / vnorm2;
+			for (int64_t i = k; i < rows; ++i) b[i] -= s * v[i - k];
+		}
+		++rank;
+	}
+	double y[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	for (int k = rank - 1; k >= 0; --k) {
+		double s = b[k];
+		for (int j = k + 1; j < rank; ++j) s -= A[(size_t)k * 8 + j] * y[j];
+		y[k] = s / A[(size_t)k * 8 + k];
+	}
+	double h[9];
+	for (int j = 0; j < 8; ++j) h[perm[j]] = y[j];
+	h[8] = 1.0;
+	for (int j = 0; j < 8; ++j)
+		if (!std::isfinite(h[j])) return 0;
+	// H = T2^-1 * Hn * T1
+	const double T1[9] = {r1, 0, -r1 * m1x, 0, r1, -r1 * m1y, 0, 0, 1};
+	const double T2i[9] = {1.0 / r2, 0, m2x, 0, 1.0 / r2, m2y, 0, 0, 1};
+	double tmp[9];
+	for (int r = 0; r < 3; ++r)
+		for (int c = 0; c < 3; ++c) tmp[3 * r + c] = T2i[3 * r] * h[c] + T2i[3 * r + 1] * h[3 + c] + T2i[3 * r + 2] * h[6 + c];
+	for (int r = 0; r < 3; ++r)
+		for (int c = 0; c < 3; ++c) H[3 * r + c] = tmp[3 * r] * T1[c] + tmp[3 * r + 1] * T1[3 + c] + tmp[3 * r + 2] * T1[6 + c];
+	return 1;
+}
+
 // gcr/GCoptimization.cpp:608-751 for dense costs + one cost per label (restated; the true reference is
 // oracle/_ref/libgco_ref.so and tests cross-check the two)
 double pxo_greedy_ufl(const double *D, int64_t N, int32_t L1, double label_cost, const int32_t *init_labels,

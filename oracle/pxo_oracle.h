@@ -103,6 +103,11 @@ void pxo_lo_unary_terms(int model_type, const double *pts, int64_t N, const doub
 void pxo_tukey_weights(int model_type, const double *pts, const int64_t *inliers, int64_t n, const double *model,
                        double T2, double *weights /*indexed by point*/);
 
+/* f-1 (next row): non-minimal homography fit, gcr/estimators/homography_estimator.h:140-173 +
+ * solver_homography_four_point.h:192-264 (Hartley normalisation, 2n x 8 least squares by column-pivoted Householder
+ * QR, denormalisation). weights_by_row may be NULL. Returns 1 on success. */
+int pxo_fit_h_nonminimal(const double *pts, const int64_t *idx, int64_t n, const double *weights_by_row, double *H);
+
 /* a10 restated (used when oracle/_ref is not available and to cross-check it):
  * GCoptimization::solveGreedy, gcr/GCoptimization.cpp:608-751, for dense data costs and one uniform
  * per-label cost. init_labels gives the start labelling whose energy the greedy result must beat. */

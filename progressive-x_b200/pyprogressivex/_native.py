@@ -80,6 +80,9 @@ def load_library() -> C.CDLL:
     lib.pxb_lo_unary_terms.argtypes = [vp, vp, f64, f64, vp, vp, vp]
     lib.pxb_tukey_weights.argtypes = [vp, vp, f64, vp]
     lib.pxb_selftest_division.argtypes = [vp, u64, i64, C.c_int, C.POINTER(i64)]
+    lib.pxb_lo_graph_cut.argtypes = [vp, vp, vp, vp, i64, f64, vp, vp, vp]
+    lib.pxb_knn_graph.argtypes = [vp, f64, C.c_int, vp, vp]
+    lib.pxb_fit_homographies.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     lib.pxb_find_homographies.argtypes = [vp, vp, i64, vp, vp, i64, sz, sz, sz, sz, f64, f64, f64, f64, f64, sz, sz,
                                           C.c_int, sz, f64, C.c_int, u64]
     lib.pxb_find_two_view_motions.argtypes = lib.pxb_find_homographies.argtypes
@@ -282,6 +285,37 @@ class Context:
         w = np.empty(self.N)
         _check(self.lib.pxb_tukey_weights(self.handle, _ptr(m), float(T2), _ptr(w)))
         return w
+
+    def lo_graph_cut(self, e0, e1, d, lam: float, csr_off, csr_idx) -> np.ndarray:
+        e0, e1, d = _f64(e0), _f64(e1), _f64(d)
+        off = np.ascontiguousarray(csr_off, dtype=np.int32)
+        idx = np.ascontiguousarray(csr_idx, dtype=np.int32)
+        out = np.zeros(e0.shape[0], dtype=np.uint8)
+        _check(self.lib.pxb_lo_graph_cut(self.handle, _ptr(e0), _ptr(e1), _ptr(d), e0.shape[0], float(lam), _ptr(off),
+                                         _ptr(idx), _ptr(out)))
+        return out
+
+    # -- next rows -----------------------------------------------------------------------------------------
+    def knn_graph(self, radius: float, k: int = 8):
+        """Directed neighbour lists as CSR (off, idx), the format pearl_label / lo_graph_cut take."""
+        nbr = np.empty((self.N, k), dtype=np.int32)
+        deg = np.empty(self.N, dtype=np.int32)
+        _check(self.lib.pxb_knn_graph(self.handle, float(radius), int(k), _ptr(nbr), _ptr(deg)))
+        off = np.zeros(self.N + 1, dtype=np.int32)
+        np.cumsum(deg, out=off[1:])
+        idx = nbr[np.arange(k)[None, :] < deg[:, None]]
+        return off, np.ascontiguousarray(idx, dtype=np.int32)
+
+    def fit_homographies(self, index_sets, weights_by_row=None):
+        off = np.zeros(len(index_sets) + 1, dtype=np.int32)
+        off[1:] = np.cumsum([len(s) for s in index_sets])
+        idx = np.ascontiguousarray(np.concatenate([np.asarray(s, dtype=np.int32) for s in index_sets]))
+        w = None if weights_by_row is None else _f64(weights_by_row)
+        H = np.zeros((len(index_sets), 9))
+        ok = np.zeros(len(index_sets), dtype=np.int32)
+        _check(self.lib.pxb_fit_homographies(self.handle, len(index_sets), _ptr(off), _ptr(idx), _ptr(w), _ptr(H),
+                                             _ptr(ok)))
+        return H, ok
 
     def selftest_division(self, seed: int, n: int, mode: int) -> int:
         bad = C.c_int64()

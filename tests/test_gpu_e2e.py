@@ -54,6 +54,20 @@ def test_find_homographies_synthetic(sampler_id):
         assert (r2 <= T * (1 + 1e-9)).mean() > 0.999
 
 
+def test_find_homographies_with_spatial_coherence():
+    """lambda > 0: GC-RANSAC's graph-cut local optimisation and PEARL's alpha-expansion run on the GPU min-cut engine
+    (the AdelaideH configuration of the reference: lambda = 0.05, NAPSAC sampling)."""
+    corrs, gt, Hs = syn.multi_homography_scene(2500, n_planes=3, outlier_ratio=0.3, noise=0.5, seed=21)
+    models, labels = pyprogressivex.findHomographies(corrs, 1024, 768, 1024, 768, threshold=2.0, conf=0.95,
+                                                     spatial_coherence_weight=0.05, neighborhood_ball_radius=60.0,
+                                                     maximum_tanimoto_similarity=0.4, max_iters=1500,
+                                                     minimum_point_number=50, maximum_model_number=6, sampler_id=3,
+                                                     scoring_exponent=2, seed=5)
+    M = models.shape[0] // 3
+    assert 3 <= M <= 4
+    assert misclassification(gt, labels, M) < 0.08
+
+
 def test_find_homographies_is_deterministic_for_a_seed():
     corrs, gt, Hs = syn.multi_homography_scene(2000, n_planes=2, outlier_ratio=0.3, seed=5)
     a = pyprogressivex.findHomographies(corrs, 1024, 768, 1024, 768, threshold=2.0, conf=0.9, max_iters=500,
