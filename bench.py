@@ -331,7 +331,7 @@ def main():
     # ---- hypothesis-summary exchange of the sharded RANSAC loop (N > 1 only) ---------------------------------
     if world > 1:
         summ = torch.stack([cnt.to(torch.float64), val, shr], 1).contiguous()
-        gathered = torch.empty((world,) + tuple(summ.shape), dtype=summ.dtype, device=dev)
+        gathered = torch.empty((world * summ.shape[0], summ.shape[1]), dtype=summ.dtype, device=dev)
 
         def step_exchange():
             with torch.cuda.stream(stream):
@@ -377,6 +377,27 @@ def main():
            "h2d_bytes_per_step": int(pts.nbytes + models_np.nbytes + 72),
            "d2h_bytes_per_step": int(K * 24 + words * 4),
            "call": "pxb_upload_points + pxb_score_compound + pxb_inliers (host pointers, copies inside the timed region)"}
+
+    # ---- second half of the BASELINE metric: complete multi-model fits per second (config C2) ---------------------
+    import pyprogressivex
+    c2_pts, c2_gt, _ = syn.multi_homography_scene(10_000, n_planes=5, outlier_ratio=0.4, noise=0.5, seed=42 + rank)
+    pyprogressivex._contexts[local_rank] = ctx  # reuse this process' context
+    fit_kwargs = dict(threshold=2.0, conf=0.5, spatial_coherence_weight=0.0, neighborhood_ball_radius=200.0,
+                      maximum_tanimoto_similarity=0.4, max_iters=1000, minimum_point_number=100,
+                      maximum_model_number=-1, sampler_id=0, scoring_exponent=2, device=local_rank)
+    pyprogressivex.findHomographies(c2_pts, 1024, 768, 1024, 768, seed=1, **fit_kwargs)
+    n_fits = 5
+    barrier()
+    t0 = time.perf_counter()
+    n_models = []
+    for i in range(n_fits):
+        m_, l_ = pyprogressivex.findHomographies(c2_pts, 1024, 768, 1024, 768, seed=2 + i, **fit_kwargs)
+        n_models.append(m_.shape[0] // 3)
+    barrier()
+    fit_s = time.perf_counter() - t0
+    extras["fits"] = {"fits_per_s": n_fits * world / fit_s, "config": "C2: synthetic multi-H, 10k correspondences, 5 planted "
+                      "planes + 40% outliers, findHomographies(max_iters=1000, conf=0.5, lambda=0), one problem per GPU "
+                      "at a time", "models_found": n_models}
 
     if rank == 0:
         out = {
