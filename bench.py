@@ -183,15 +183,25 @@ def run_reference(args):
     O.score_batch(0, pts, models[:k_cal], T2, None, threads=cores)
     dt = max(time.perf_counter() - t0, 1e-4)
     k = int(min(models.shape[0], max(k_cal, k_cal * 1.5 / dt)))
+    O.score_batch(0, pts, models[:k], T2, None, threads=cores)
+    t0 = time.perf_counter()
+    O.score_batch(0, pts, models[:k], T2, None, threads=cores)
+    one = max(time.perf_counter() - t0, 1e-4)
+    reps = int(max(1, min(100, round(1.0 / one))))  # ~1 s of host work per step
+
+    def step():
+        for _ in range(reps):
+            O.score_batch(0, pts, models[:k], T2, None, threads=cores)
+
     for _ in range(args.warmup):
-        O.score_batch(0, pts, models[:k], T2, None, threads=cores)
+        step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        O.score_batch(0, pts, models[:k], T2, None, threads=cores)
+        step()
     dt = time.perf_counter() - t0
-    value = pts.shape[0] * k * args.steps / dt
+    value = pts.shape[0] * k * reps * args.steps / dt
     sample = (f"oracle port of getScore (scoring_function_with_compound_model.h:61-125) with OpenMP over hypotheses; "
-              f"each step N={pts.shape[0]} x K={k} hypotheses of the bench workload")
+              f"each step = {reps} passes over N={pts.shape[0]} x K={k} hypotheses of the bench workload")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",

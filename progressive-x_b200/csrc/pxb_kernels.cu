@@ -21,6 +21,7 @@
 // only -- never on K, the grid or the device -- so equal inputs always give equal sums.
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "pxb_internal.h"
 #include "pxb_residuals.cuh"
@@ -61,7 +62,7 @@ template <typename OUT> __device__ __forceinline__ void store_stream(OUT *p, dou
 template <> __device__ __forceinline__ void store_stream<double>(double *p, double v) { __stcs(p, v); }
 template <> __device__ __forceinline__ void store_stream<float>(float *p, double v) { __stcs(p, __double2float_rn(v)); }
 
-template <int TYPE, typename OUT, bool HAS_R2, bool HAS_MASK, int kRmP, int MINB>
+template <int TYPE, typename OUT, bool HAS_R2, bool HAS_MASK, int kRmP, int MINB, bool HI_ONLY>
 __global__ void __launch_bounds__(kThreads, MINB)
     k_residual_matrix(const double *__restrict__ soa, int64_t stride, int64_t N, const double *__restrict__ models,
                       int64_t K, double T2, OUT *__restrict__ r2, uint32_t *__restrict__ mask, int64_t words) {
@@ -93,18 +94,21 @@ __global__ void __launch_bounds__(kThreads, MINB)
 	}
 	wild = __syncthreads_or(wild);
 	if (base >= N) return;
+	const unsigned hiT = (unsigned)__double2hiint(T2);
 	OUT *out = HAS_R2 ? r2 + k0 * N + base + lane : nullptr;
 	uint32_t *mout = HAS_MASK ? mask + k0 * words + (base >> 5) : nullptr;
 	const int nwords = (int)min((int64_t)kRmP, words - (base >> 5));
 
+#pragma unroll 2
 	for (int k = 0; k < nk; ++k) {
 		double m[12];
 		load_model_smem<TYPE>(s_models + k * MP, m);
 		double r[kRmP];
-		float lo = __int_as_float(0x7f000000);
+		float lo[kRmP];
 #pragma unroll
-		for (int j = 0; j < kRmP; ++j) r[j] = squared_residual_tile<TYPE>(p[j], m, lo);
-		if (__builtin_expect(!(lo >= __int_as_float(kHiMinPattern)) || wild, 0)) PXB_RESIDUAL_TILE_EXACT(TYPE, kRmP, p, m, r);
+		for (int j = 0; j < kRmP; ++j) r[j] = squared_residual_tile<TYPE>(p[j], m, lo[j]);
+		if (__builtin_expect(!(tile_min4(lo) >= __int_as_float(kHiMinPattern)) || wild, 0))
+			PXB_RESIDUAL_TILE_EXACT(TYPE, kRmP, p, m, r);
 		if (HAS_R2) {
 #pragma unroll
 			for (int j = 0; j < kRmP; ++j)
@@ -114,7 +118,7 @@ __global__ void __launch_bounds__(kThreads, MINB)
 		if (HAS_MASK) {
 			uint32_t w[kRmP];
 #pragma unroll
-			for (int j = 0; j < kRmP; ++j) w[j] = __ballot_sync(0xffffffffu, valid[j] && (r[j] < T2));
+			for (int j = 0; j < kRmP; ++j) w[j] = __ballot_sync(0xffffffffu, valid[j] && below_threshold<HI_ONLY>(r[j], T2, hiT));
 			uint32_t mine = w[0];
 #pragma unroll
 			for (int j = 1; j < kRmP; ++j) mine = (lane == j) ? w[j] : mine;
@@ -124,8 +128,9 @@ __global__ void __launch_bounds__(kThreads, MINB)
 	}
 }
 
-template <int TYPE, typename OUT, int P, int MINB>
+template <int TYPE, typename OUT, bool HI_ONLY>
 static int launch_rm_v(pxb_ctx *ctx, const double *models, int64_t K, double T2, OUT *r2, uint32_t *mask) {
+	constexpr int P = 4, MINB = 2; // tuned on B200: (4,3), (2,3), (2,4) are within 3% but never faster
 	const Points &p = ctx->pts;
 	const int64_t words = (p.N + 31) / 32;
 	const int64_t ppb = (int64_t)(kThreads / 32) * 32 * P;
@@ -138,11 +143,11 @@ static int launch_rm_v(pxb_ctx *ctx, const double *models, int64_t K, double T2,
 		OUT *rr = r2 ? r2 + done * p.N : nullptr;
 		uint32_t *mk = mask ? mask + done * words : nullptr;
 		if (rr && mk)
-			k_residual_matrix<TYPE, OUT, true, true, P, MINB><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, mm, kk, T2, rr, mk, words);
+			k_residual_matrix<TYPE, OUT, true, true, P, MINB, HI_ONLY><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, mm, kk, T2, rr, mk, words);
 		else if (rr)
-			k_residual_matrix<TYPE, OUT, true, false, P, MINB><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, mm, kk, T2, rr, mk, words);
+			k_residual_matrix<TYPE, OUT, true, false, P, MINB, false><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, mm, kk, T2, rr, mk, words);
 		else if (mk)
-			k_residual_matrix<TYPE, OUT, false, true, P, MINB><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, mm, kk, T2, rr, mk, words);
+			k_residual_matrix<TYPE, OUT, false, true, P, MINB, HI_ONLY><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, mm, kk, T2, rr, mk, words);
 		ctx->launches++;
 		done += kk;
 	}
@@ -150,23 +155,10 @@ static int launch_rm_v(pxb_ctx *ctx, const double *models, int64_t K, double T2,
 	return PXB_OK;
 }
 
-static int rm_variant() {
-	static int v = -1;
-	if (v < 0) {
-		const char *e = getenv("PXB_RM_VARIANT"); // tuning knob: 0 = (P4, 2 blocks/SM), 1 = (P4, 3), 2 = (P2, 3), 3 = (P2, 4)
-		v = e ? atoi(e) : 0;
-	}
-	return v;
-}
-
 template <int TYPE, typename OUT>
 static int launch_rm_t(pxb_ctx *ctx, const double *models, int64_t K, double T2, OUT *r2, uint32_t *mask) {
-	switch (rm_variant()) {
-	case 1: return launch_rm_v<TYPE, OUT, 4, 3>(ctx, models, K, T2, r2, mask);
-	case 2: return launch_rm_v<TYPE, OUT, 2, 3>(ctx, models, K, T2, r2, mask);
-	case 3: return launch_rm_v<TYPE, OUT, 2, 4>(ctx, models, K, T2, r2, mask);
-	default: return launch_rm_v<TYPE, OUT, 4, 2>(ctx, models, K, T2, r2, mask);
-	}
+	return threshold_low_word_is_zero(T2) ? launch_rm_v<TYPE, OUT, true>(ctx, models, K, T2, r2, mask)
+	               : launch_rm_v<TYPE, OUT, false>(ctx, models, K, T2, r2, mask);
 }
 
 int launch_residual_matrix(pxb_ctx *ctx, const double *models, int64_t K, double T2, double *r2, float *r2f,

@@ -28,7 +28,7 @@ struct ScorePartial {
 	long long count;
 };
 
-template <int TYPE, bool HAS_CP>
+template <int TYPE, bool HAS_CP, bool HI_ONLY>
 __global__ void __launch_bounds__(kThreads, 2)
     k_score_partial(const double *__restrict__ soa, int64_t stride, int64_t N, const double *__restrict__ models,
                     int64_t K, double T2, const double *__restrict__ compound_pref, ScorePartial *__restrict__ partials,
@@ -63,29 +63,38 @@ __global__ void __launch_bounds__(kThreads, 2)
 		for (int c = 0; c < DIM; ++c) wild |= !(fabs(p[j][c]) <= kInputMagnitudeLimit);
 	}
 	wild = __syncthreads_or(wild); // also orders the s_models writes
+	const unsigned hiT = (unsigned)__double2hiint(T2);
+	// r2 / T2 divides by a launch constant: one Newton reciprocal per thread, then the 3-instruction quotient of
+	// ptxas' own fast path (bit-identical inside its domain: 2^-300 <= r2, T2 within 2^+-200 -- checked by the host;
+	// anything else takes the plain division)
+	const bool fastT = fabs(T2) >= 6.2e-61 && fabs(T2) <= 1.6e60;
+	const double rT = rcp_newton(fastT ? T2 : 1.0);
 
 	for (int ks = 0; ks < nk; ks += kScSub) {
 		const int nsub = min(kScSub, nk - ks);
+#pragma unroll 2
 		for (int h = 0; h < nsub; ++h) {
 			double m[12];
 			load_model_smem<TYPE>(s_models + (ks + h) * MP, m);
 			double r[kScP];
-			float lo = __int_as_float(0x7f000000);
+			float lo[kScP];
 #pragma unroll
-			for (int j = 0; j < kScP; ++j) r[j] = squared_residual_tile<TYPE>(p[j], m, lo);
-			if (__builtin_expect(!(lo >= __int_as_float(kHiMinPattern)) || wild, 0))
+			for (int j = 0; j < kScP; ++j) r[j] = squared_residual_tile<TYPE>(p[j], m, lo[j]);
+			if (__builtin_expect(!(tile_min4(lo) >= __int_as_float(kHiMinPattern)) || wild, 0))
 				PXB_RESIDUAL_TILE_EXACT(TYPE, kScP, p, m, r);
 			int c = 0;
 			double v = 0.0, s = 0.0;
 			bool any = false;
 #pragma unroll
-			for (int j = 0; j < kScP; ++j) any |= valid[j] && (r[j] < T2);
+			for (int j = 0; j < kScP; ++j) any |= valid[j] && below_threshold<HI_ONLY>(r[j], T2, hiT);
 			if (any) { // scoring_function_with_compound_model.h:85-102, points in j order
 #pragma unroll
 				for (int j = 0; j < kScP; ++j) {
-					if (valid[j] && (r[j] < T2)) {
+					if (valid[j] && below_threshold<HI_ONLY>(r[j], T2, hiT)) {
 						++c;
-						const double sv = cv_max(0.0, sub(1.0, divd(r[j], T2)));
+						const double q = (fastT && __double2hiint(r[j]) >= kHiMinPattern) ? fast_quotient_nocheck(r[j], T2, rT)
+						                                                                   : divd(r[j], T2);
+						const double sv = cv_max(0.0, sub(1.0, q));
 						v = add(v, sv);
 						if (HAS_CP) s = add(s, cv_min(cp[j], sv)); // :115-117 (pref is 0 off the inlier set)
 					}
@@ -145,10 +154,15 @@ template <int TYPE>
 static void launch_partial(pxb_ctx *ctx, dim3 grid, const double *m, int64_t kk, double T2, const double *cp,
                            ScorePartial *pp, int nchunks) {
 	const Points &p = ctx->pts;
-	if (cp)
-		k_score_partial<TYPE, true><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, m, kk, T2, cp, pp, nchunks);
+	const bool hi = threshold_low_word_is_zero(T2);
+	if (cp && hi)
+		k_score_partial<TYPE, true, true><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, m, kk, T2, cp, pp, nchunks);
+	else if (cp)
+		k_score_partial<TYPE, true, false><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, m, kk, T2, cp, pp, nchunks);
+	else if (hi)
+		k_score_partial<TYPE, false, true><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, m, kk, T2, cp, pp, nchunks);
 	else
-		k_score_partial<TYPE, false><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, m, kk, T2, cp, pp, nchunks);
+		k_score_partial<TYPE, false, false><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, m, kk, T2, cp, pp, nchunks);
 }
 
 int launch_score_compound(pxb_ctx *ctx, const double *models, int64_t K, double T2, const double *compound_pref,
