@@ -98,6 +98,90 @@ def gco() -> C.CDLL:
     return _gco
 
 
+REF_BODIES_LIB = HERE / "_ref" / "libpx_refbodies.so"
+_refb = None
+
+
+def have_ref_bodies() -> bool:
+    return REF_BODIES_LIB.exists()
+
+
+def refb() -> C.CDLL:
+    """oracle/_ref/libpx_refbodies.so: the reference's own function bodies, compiled verbatim by extract_ref.py."""
+    global _refb
+    if _refb is None:
+        if not REF_BODIES_LIB.exists():
+            subprocess.run(["python", str(HERE / "extract_ref.py")], check=True)
+        B = C.CDLL(str(REF_BODIES_LIB))
+        vp, i64, f64 = C.c_void_p, C.c_int64, C.c_double
+        B.pxr_squared_residual.restype = f64
+        B.pxr_squared_residual.argtypes = [C.c_int, vp, vp]
+        B.pxr_residuals.argtypes = [C.c_int, vp, i64, vp, vp]
+        B.pxr_residuals.restype = None
+        B.pxr_get_score.restype = f64
+        B.pxr_get_score.argtypes = [C.c_int, vp, i64, vp, f64, vp, C.c_int, i64, C.POINTER(i64), vp]
+        B.pxr_preference_vector.argtypes = [C.c_int, vp, i64, vp, f64, vp]
+        B.pxr_preference_vector.restype = None
+        B.pxr_pearl_datacost.argtypes = [C.c_int, vp, i64, vp, i64, f64, f64, vp]
+        B.pxr_pearl_datacost.restype = None
+        B.pxr_h4_solve.argtypes = [vp, i64, vp, vp]
+        B.pxr_h4_is_valid_sample.argtypes = [vp, i64, vp]
+        B.pxr_h_is_valid_model.argtypes = [vp]
+        B.pxr_f_orientation_valid.argtypes = [vp, vp, i64, vp, C.c_int]
+        _refb = B
+    return _refb
+
+
+def ref_residuals(t, pts, model):
+    pts, model = _f(pts), _f(model)
+    out = np.empty(pts.shape[0])
+    refb().pxr_residuals(t, _p(pts), pts.shape[0], _p(model), _p(out))
+    return out
+
+
+def ref_get_score(t, pts, model, T2, compound_pref=None, exponent=2, best_inlier_number=0):
+    pts, model = _f(pts), _f(model)
+    N = pts.shape[0]
+    cp = None if compound_pref is None else _f(compound_pref)
+    cnt = C.c_int64()
+    inl = np.full(N, -1, dtype=np.int64)
+    val = refb().pxr_get_score(t, _p(pts), N, _p(model), float(T2), _p(cp), int(exponent), int(best_inlier_number),
+                               C.byref(cnt), _p(inl))
+    return dict(value=val, count=cnt.value, inliers=inl[: cnt.value].copy())
+
+
+def ref_preference_vector(t, pts, model, T):
+    pts, model = _f(pts), _f(model)
+    out = np.empty(pts.shape[0])
+    refb().pxr_preference_vector(t, _p(pts), pts.shape[0], _p(model), float(T), _p(out))
+    return out
+
+
+def ref_pearl_datacost(t, pts, models, thr, lam):
+    pts, models = _f(pts), _f(models).reshape(-1, MSIZE[t])
+    N, L = pts.shape[0], models.shape[0]
+    D = np.empty((N, L + 1))
+    refb().pxr_pearl_datacost(t, _p(pts), N, _p(models), L, float(thr), float(lam), _p(D))
+    return D
+
+
+def ref_h4(pts, sample):
+    pts = _f(pts)
+    s = np.ascontiguousarray(sample, dtype=np.int64)
+    H = np.zeros(9)
+    B = refb()
+    ok = B.pxr_h4_solve(_p(pts), pts.shape[0], _p(s), _p(H))
+    sv = B.pxr_h4_is_valid_sample(_p(pts), pts.shape[0], _p(s))
+    mv = B.pxr_h_is_valid_model(_p(H)) if ok else 0
+    return H, int(ok), int(sv), int(mv)
+
+
+def ref_f_orientation_valid(F, pts, sample):
+    F, pts = _f(F), _f(pts)
+    s = np.ascontiguousarray(sample, dtype=np.int64)
+    return int(refb().pxr_f_orientation_valid(_p(F), _p(pts), pts.shape[0], _p(s), s.shape[0]))
+
+
 def _f(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 

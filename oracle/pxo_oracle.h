@@ -6,15 +6,18 @@
  * the pyprogressivex host mirror) never links, imports or calls anything under oracle/.
  *
  * PARITY PINNING STATUS
- *   - a10/a11 (greedy UFL label sweep, alpha-expansion, BK max-flow): PINNED against the reference's
- *     own gco-v3 + maxflow sources compiled unchanged into oracle/_ref/libgco_ref.so (see Makefile).
- *   - a1..a9, a12, a13: the reference ships no golden vector, no test and cannot be compiled here
- *     (Eigen / OpenCV C++ headers absent). These restatements follow the reference line by line in
- *     IEEE double, left-to-right operation order, built with -O3 -ffp-contract=off (no FMA
- *     contraction, like the reference's own -O3 x86-64 build). Status: "parity unpinned" unless the
- *     shim build (oracle/shim) is green, in which case the scalar-arithmetic
- *     functions are cross-checked against the reference headers compiled over a minimal
- *     Eigen/OpenCV stand-in.
+ *   - a10/a11 (greedy UFL label sweep, alpha-expansion, BK max-flow, LO st-cut): PINNED against the reference's
+ *     own gco-v3 + maxflow sources compiled unchanged into oracle/_ref/libgco_ref.so (oracle/Makefile).
+ *   - a1, a2, a3 (residuals), a4 (getScore incl. early exit / int exponent), a5 (setPreferenceVector), a6 (four-point
+ *     solver, gaussElimination, isValidSample, isValidModel), the oriented-epipolar test of a7, a9 (PEARL data
+ *     costs): PINNED BIT-EXACT against the reference's own function bodies, compiled verbatim from
+ *     /root/reference by oracle/extract_ref.py into oracle/_ref/libpx_refbodies.so (tests/test_oracle_pinned.py).
+ *   - a7 null space + cubic, a8 (P3P), the Tanimoto reduction order of a5, a12, a13: restated, "parity unpinned"
+ *     beyond tolerance: their arithmetic lives in Eigen (FullPivLU::kernel, PolynomialSolver, redux) / libm, which are
+ *     not on disk; the reference ships no golden vectors for them. Known-answer tests on planted structures
+ *     (tests/test_oracle_cpu.py) cover them.
+ *   Everything is IEEE double, left-to-right operation order, built with -O3 -ffp-contract=off (no FMA contraction,
+ *   like the reference's own -O3 x86-64 build).
  *
  * All matrices are row-major doubles. Points: H/F rows are [x1 y1 x2 y2]; PnP rows are
  * [u v X Y Z] with (u,v) already K^-1-normalised. Models: H/F 9 doubles, PnP 12 doubles (3x4).
