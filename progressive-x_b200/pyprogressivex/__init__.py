@@ -76,6 +76,28 @@ def findTwoViewMotions(corrs, w1, h1, w2, h2, threshold=4.0, conf=0.5, spatial_c
 findFundamentalMatrices = findTwoViewMotions
 
 
+def findHomographiesBatch(pairs, w1, h1, w2, h2, distributed=False, **kwargs):
+    """BASELINE config C4: many independent image pairs. `pairs` is a list of [N_p, 4] correspondence arrays.
+    With distributed=True (inside a torch.distributed job, one process per GPU) pair p is solved on rank p mod world
+    and the surviving instances of every pair are all-gathered (sharding.gather_instances); every rank returns the
+    full list [(models, labeling), ...]. Pairs must then share one N (padding is the caller's business)."""
+    if not distributed:
+        return [findHomographies(c, w1, h1, w2, h2, **kwargs) for c in pairs]
+    import torch
+    import torch.distributed as dist
+    from . import sharding
+    rank, world = dist.get_rank(), dist.get_world_size()
+    n_points = int(pairs[0].shape[0])
+    dev = kwargs.get("device", 0)
+    local = []
+    for p in sharding.pairs_of_rank(len(pairs), rank, world):
+        m, lab = findHomographies(pairs[p], w1, h1, w2, h2, **kwargs)
+        local.append((p, m.reshape(-1, 9), lab))
+    tdev = torch.device("cuda", dev) if dist.get_backend() == "nccl" else None
+    gathered = sharding.gather_instances(local, len(pairs), n_points, 9, 10, tdev)
+    return [(m.reshape(-1, 3), lab) for m, lab in gathered]
+
+
 def find6DPoses(x1y1, x2y2z2, K, threshold=4.0, conf=0.90, spatial_coherence_weight=0.1,
                 neighborhood_ball_radius=20.0, maximum_tanimoto_similarity=0.9, max_iters=400,
                 minimum_point_number=2 * 3, maximum_model_number=-1, seed=0, device=0):

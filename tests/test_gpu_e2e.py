@@ -68,6 +68,24 @@ def test_find_homographies_with_spatial_coherence():
     assert misclassification(gt, labels, M) < 0.08
 
 
+def test_batched_pairs_config_c4():
+    """BASELINE config C4 in miniature: independent pairs through findHomographiesBatch (single process here; the
+    distributed variant shards pairs over ranks and all-gathers the instances, covered at world size 2 in
+    tests/test_sharding_cpu.py and by `bench.py --gpus N`)."""
+    pairs, gts = [], []
+    for p in range(6):
+        c, gt, _ = syn.multi_homography_scene(1500, n_planes=2 + p % 2, outlier_ratio=0.4, seed=300 + p)
+        pairs.append(c)
+        gts.append(gt)
+    out = pyprogressivex.findHomographiesBatch(pairs, 1024, 768, 1024, 768, threshold=2.0, conf=0.95, max_iters=1000,
+                                               minimum_point_number=60, sampler_id=0, seed=9)
+    assert len(out) == 6
+    for (models, labels), gt, p in zip(out, gts, range(6)):
+        M = models.shape[0] // 3
+        assert M >= 2 + p % 2
+        assert misclassification(gt, labels, M) < 0.1
+
+
 def test_find_homographies_is_deterministic_for_a_seed():
     corrs, gt, Hs = syn.multi_homography_scene(2000, n_planes=2, outlier_ratio=0.3, seed=5)
     a = pyprogressivex.findHomographies(corrs, 1024, 768, 1024, 768, threshold=2.0, conf=0.9, max_iters=500,

@@ -237,6 +237,40 @@ def test_errors_are_reported_not_fatal(ctx):
     c2.close()
 
 
+@pytest.mark.parametrize("t,N,K", [(F, 50_000, 1_500), (PNP, 100_000, 1_000)])
+def test_baseline_config_sizes_f_and_pnp(ctx, oracle, t, N, K):
+    """BASELINE configs C3 (multi-F, 50k correspondences) and C5 (P3P, 100k 2D-3D matches) at full N: hypotheses from
+    the GPU minimal solvers; mask == (r2 < T2) everywhere, popcount == fused count, a row sample is bit-exact against
+    the oracle, and sharding the hypotheses into blocks (the multi-GPU mode) reproduces the unsharded sums bit for bit."""
+    pts, gt, planted, thr = scene(t, N, seed=17 + t)
+    m = {F: 7, PNP: 3}[t]
+    S = syn.minimal_samples(gt, K, m, seed=17 + t)
+    ctx.upload_points(t, pts)
+    models, n, _, _ = ctx.solve_minimal(S)
+    filled = np.arange(models.shape[1])[None, :] < n[:, None]
+    hyps = np.ascontiguousarray(models[filled])
+    assert hyps.shape[0] > K // 2
+    T2 = (1.5 * thr) ** 2
+    r2, mask = ctx.residual_matrix(hyps, T2)
+    bits = np.unpackbits(mask.view(np.uint8), axis=1, bitorder="little")[:, :N].astype(bool)
+    assert np.array_equal(bits, r2 < T2)
+    cnt, val, shr = ctx.score_compound(hyps, T2)
+    assert np.array_equal(cnt, bits.sum(1))
+    rows = np.random.default_rng(0).choice(hyps.shape[0], 24, replace=False)
+    r2_o, mask_o = oracle.residual_matrix(t, pts, hyps[rows], T2)
+    assert bits_equal(r2[rows], r2_o) and np.array_equal(mask[rows], mask_o)
+    cnt_o, val_o, _ = oracle.score_batch(t, pts, hyps[rows], T2, None, threads=4)
+    assert np.array_equal(cnt[rows], cnt_o)
+    np.testing.assert_allclose(val[rows], val_o, rtol=SUM_RTOL, atol=1e-13)
+    from pyprogressivex import sharding
+    b = sharding.block_bounds(hyps.shape[0], 8)
+    parts = [ctx.score_compound(hyps[b[r]:b[r + 1]], T2) for r in range(8)]
+    assert np.array_equal(np.concatenate([p[0] for p in parts]), cnt)
+    assert bits_equal(np.concatenate([p[1] for p in parts]), val)
+    best = int(np.argmax(cnt))
+    assert cnt[best] > 0.5 * (gt == gt[S[0][0]]).sum() or cnt[best] > 0.03 * N  # a planted structure was found
+
+
 def test_full_size_properties(ctx, oracle):
     """BASELINE sizes (50k x 10k grid is too big for the CPU oracle): size-independent properties instead.
     (1) mask bit == (r2 < T2) for every entry, (2) popcount(mask row) == fused-score count, (3) a 64-row sample of
