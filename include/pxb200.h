@@ -176,6 +176,13 @@ int pxb_knn_graph(pxb_ctx *ctx, double radius, int k, int32_t *nbr_out_host, int
  * index lists; weights_by_row may be NULL. H_out: P*9, ok_out: P. */
 int pxb_fit_homographies(pxb_ctx *ctx, int32_t P, const int32_t *off_host, const int32_t *idx_host,
                          const double *weights_by_row_host, double *H_out_host, int32_t *ok_out_host);
+/* Same for whatever estimator family the uploaded points belong to (Estimator::estimateModelNonminimal). H: as above.
+ * F: normalised 8-point + rank-2 projection (gcr/estimators/fundamental_estimator.h:574-618 without the LM polish of
+ * solver_fundamental_matrix_bundle_adjustment.h), n >= 8. PnP: normalised DLT + Levenberg-Marquardt on the reprojection
+ * error (stands in for solver_pnp_bundle_adjustment.h:108-225), n >= 6, weights ignored like the reference does.
+ * models_out: P * 9 (H, F) or P * 12 (PnP) doubles. */
+int pxb_fit_nonminimal(pxb_ctx *ctx, int32_t P, const int32_t *off_host, const int32_t *idx_host,
+                       const double *weights_by_row_host, double *models_out_host, int32_t *ok_out_host);
 
 /* ---- self-test --------------------------------------------------------------------------------------------- */
 /* Compares the hot loop's shared-reciprocal double division (two quotients, one Newton reciprocal) with the

@@ -26,8 +26,9 @@
 //   * the reference's two-buffer inlier ping-pong (GCRANSAC.h:244-252,:546-552) is replaced by "the inlier list of the
 //     current best model" -- the reference's version depends on list-size coincidences;
 //   * samplers 1 (PROSAC) and 2 (P-NAPSAC) fall back to uniform sampling (host-only RNG state machines, out of scope);
-//   * non-minimal fits: homography only (normal equations); F / PnP task entry points report PXB_ERR_UNSUPPORTED for
-//     the stages that need them ("next").
+//   * non-minimal fits ("next"): H through the 8x8 normal equations (same least-squares solution as
+//     the reference's QR); F as normalised 8-point + rank-2 projection and PnP as normalised DLT + 10 LM steps, i.e.
+//     without PoseLib's bundle adjustment / OpenCV's EPnP (pxb_fit_fp.cu); DEGENSAC is not applied to F.
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -44,6 +45,10 @@ namespace pxb {
 int launch_knn_graph(pxb_ctx *ctx, double radius, int k, int32_t *nbr, int32_t *deg);
 int launch_fit_h(pxb_ctx *ctx, int P, const int32_t *off, const int32_t *idx, const double *weights, double *H_out,
                  int32_t *ok_out);
+int launch_fit_f(pxb_ctx *ctx, int P, const int32_t *off, const int32_t *idx, const double *weights, double *F_out,
+                 int32_t *ok_out);
+int launch_fit_pnp(pxb_ctx *ctx, int P, const int32_t *off, const int32_t *idx, double *P_out, int32_t *ok_out);
+int launch_f_sym_count(pxb_ctx *ctx, const double *model, double T2, double Tsym2, long long *out2);
 
 namespace {
 
@@ -211,6 +216,10 @@ class Driver {
 	int fit_nonminimal(const std::vector<std::vector<int64_t>> &sets, const double *weights_by_row,
 	                   std::vector<double> &models_out, std::vector<int32_t> &ok);
 	int lo_labeling(const double *model, std::vector<int64_t> &inliers);
+	// Estimator::nonMinimalSampleSize(): H four-point 4, F bundle-adjustment solver 7, PnP bundle adjustment 4
+	size_t non_minimal_sample_size() const { return s_.type == PXB_MODEL_FUNDAMENTAL ? 7 : 4; }
+	bool weighting_applicable() const { return s_.type != PXB_MODEL_PNP; } // Estimator::isWeightingApplicable()
+	int model_is_valid(const double *model, size_t slot_valid, bool &valid);
 	size_t iteration_number_for(size_t inliers, double log_probability) const;
 	int propose(uint64_t round_seed, std::vector<double> &model_out, bool &found);
 	int local_optimization(Sampler &lo_sampler, std::vector<double> &best_model, Score &best_score, double T2);
@@ -262,7 +271,17 @@ int Driver::fit_nonminimal(const std::vector<std::vector<int64_t>> &sets, const 
 	}
 	PXB_CUDA(cudaMemcpyAsync(d_off, off.data(), sizeof(int32_t) * off.size(), cudaMemcpyHostToDevice, ctx_->stream));
 	PXB_CUDA(cudaMemcpyAsync(d_idx, idx.data(), sizeof(int32_t) * idx.size(), cudaMemcpyHostToDevice, ctx_->stream));
-	PXB_TRY(launch_fit_h(ctx_, P, d_off, d_idx, d_w, ctx_->models.as<double>(), ctx_->outA.as<int32_t>()));
+	switch (s_.type) {
+	case PXB_MODEL_HOMOGRAPHY:
+		PXB_TRY(launch_fit_h(ctx_, P, d_off, d_idx, d_w, ctx_->models.as<double>(), ctx_->outA.as<int32_t>()));
+		break;
+	case PXB_MODEL_FUNDAMENTAL:
+		PXB_TRY(launch_fit_f(ctx_, P, d_off, d_idx, d_w, ctx_->models.as<double>(), ctx_->outA.as<int32_t>()));
+		break;
+	default: // PerspectiveNPointEstimator::isWeightingApplicable() is false: weights never reach the solver
+		PXB_TRY(launch_fit_pnp(ctx_, P, d_off, d_idx, ctx_->models.as<double>(), ctx_->outA.as<int32_t>()));
+		break;
+	}
 	PXB_CUDA(cudaMemcpyAsync(models_out.data(), ctx_->models.ptr, sizeof(double) * models_out.size(),
 	                         cudaMemcpyDeviceToHost, ctx_->stream));
 	PXB_CUDA(cudaMemcpyAsync(ok.data(), ctx_->outA.ptr, sizeof(int32_t) * ok.size(), cudaMemcpyDeviceToHost, ctx_->stream));
@@ -286,6 +305,27 @@ int Driver::lo_labeling(const double *model, std::vector<int64_t> &inliers) {
 	                         seg.data()));
 	for (int64_t i = 0; i < N_; ++i)
 		if (seg[i]) inliers.push_back(i);
+	return PXB_OK;
+}
+
+// Estimator::isValidModel as called from GCRANSAC::run (:441-447) with threshold_ = truncated_threshold.
+//   H   determinant test (already evaluated by the solver kernel)          homography_estimator.h:326-342
+//   F   at least max(7, half) of the Sampson inliers must also be inliers under the symmetric epipolar distance
+//       (fundamental_estimator.h:268-325); DEGENSAC (:341-572) is not applied (nested GC-RANSAC, out of scope)
+//   PnP always true                                                         perspective_n_point_estimator.h:210-218
+int Driver::model_is_valid(const double *model, size_t slot_valid, bool &valid) {
+	valid = slot_valid != 0;
+	if (s_.type != PXB_MODEL_FUNDAMENTAL || !valid) return PXB_OK;
+	const double tt = 3.0 / 2.0 * s_.threshold, T2 = tt * tt;
+	PXB_TRY(ctx_->models.reserve(sizeof(double) * 9));
+	PXB_TRY(ctx_->outB.reserve(sizeof(long long) * 2));
+	PXB_CUDA(cudaMemcpyAsync(ctx_->models.ptr, model, sizeof(double) * 9, cudaMemcpyHostToDevice, ctx_->stream));
+	PXB_TRY(launch_f_sym_count(ctx_, ctx_->models.as<double>(), T2, tt * tt, ctx_->outB.as<long long>()));
+	long long c[2];
+	PXB_CUDA(cudaMemcpyAsync(c, ctx_->outB.ptr, sizeof(c), cudaMemcpyDeviceToHost, ctx_->stream));
+	PXB_CUDA(cudaStreamSynchronize(ctx_->stream));
+	const size_t minimum = std::max<size_t>(7, (size_t)((double)c[0] * 0.5));
+	valid = (size_t)c[1] >= minimum;
 	return PXB_OK;
 }
 
@@ -363,7 +403,7 @@ int Driver::irls(std::vector<int64_t> &inliers, std::vector<double> &model, doub
 		std::vector<std::vector<int64_t>> sets(1, inliers);
 		std::vector<double> fitted;
 		std::vector<int32_t> ok;
-		PXB_TRY(fit_nonminimal(sets, w_row.data(), fitted, ok));
+		PXB_TRY(fit_nonminimal(sets, weighting_applicable() ? w_row.data() : nullptr, fitted, ok));
 		if (!ok[0]) break;
 		std::vector<int64_t> cnt;
 		std::vector<double> val, shr;
@@ -456,8 +496,10 @@ int Driver::propose(uint64_t round_seed, std::vector<double> &model_out, bool &f
 			for (int j = 0; j < blk_n[slot]; ++j) {
 				const size_t q = slot * maxsol_ + j;
 				const Score sc = finish_score(blk_cnt[q], blk_val[q], blk_shr[q], best_score.inliers);
-				// :441-447: better score AND Estimator::isValidModel (H: determinant test, evaluated on the device)
-				if (best_score.value < sc.value && blk_mv[slot]) {
+				// :441-447: better score AND Estimator::isValidModel
+				bool model_ok = false;
+				if (best_score.value < sc.value) PXB_TRY(model_is_valid(blk_models.data() + q * ms_, blk_mv[slot], model_ok));
+				if (best_score.value < sc.value && model_ok) {
 					best_model.assign(blk_models.begin() + q * ms_, blk_models.begin() + (q + 1) * ms_);
 					best_score = sc;
 					do_local_optimization = iteration_number_ > s_.min_iteration_number_before_lo &&
@@ -580,7 +622,7 @@ int Driver::pearl() {
 			std::vector<std::vector<int64_t>> sets;
 			std::vector<int64_t> which;
 			for (int64_t l = 0; l < L; ++l)
-				if (per_instance[l].size() >= (size_t)m_) { // nonMinimalSampleSize() == sampleSize() for H (:363-365)
+				if (per_instance[l].size() >= non_minimal_sample_size()) { // :363-365
 					sets.push_back(per_instance[l]);
 					which.push_back(l);
 				}
@@ -740,19 +782,79 @@ int pxb_find_homographies(pxb_ctx *ctx, const double *correspondences, int64_t N
 	                    scoring_exponent, true, do_logging, seed);
 }
 
-int pxb_find_two_view_motions(pxb_ctx *, const double *, int64_t, int64_t *, double *, int64_t, size_t, size_t,
-                              size_t, size_t, double, double, double, double, double, size_t, size_t, int, size_t,
-                              double, int, uint64_t) {
-	set_error("findTwoViewMotions: the non-minimal F solvers (8-point + LM, SURVEY.md 8f-1) are not implemented yet; "
-	          "the F operators (7-point solver, Sampson matrix, score, PEARL) are available through the operator ABI");
-	return PXB_ERR_UNSUPPORTED;
+int pxb_find_two_view_motions(pxb_ctx *ctx, const double *correspondences, int64_t N, int64_t *labeling_out,
+                              double *models_out, int64_t max_models_out, size_t, size_t, size_t, size_t,
+                              double spatial_coherence_weight, double threshold, double confidence,
+                              double neighborhood_ball_radius, double maximum_tanimoto_similarity, size_t max_iters,
+                              size_t minimum_point_number, int maximum_model_number, size_t sampler_id,
+                              double scoring_exponent, int do_logging, uint64_t seed) {
+	// findTwoViewMotions_ never forwards scoring_exponent (progressivex_python.cpp:621-638): the exponent stays 2
+	return run_two_view(ctx, PXB_MODEL_FUNDAMENTAL, correspondences, N, labeling_out, models_out, max_models_out,
+	                    spatial_coherence_weight, threshold, confidence, neighborhood_ball_radius,
+	                    maximum_tanimoto_similarity, max_iters, minimum_point_number, maximum_model_number, sampler_id,
+	                    scoring_exponent, false, do_logging, seed);
 }
 
-int pxb_find_6d_poses(pxb_ctx *, const double *, const double *, const double *, int64_t, int64_t *, double *, int64_t,
-                      double, double, double, double, double, size_t, size_t, int, uint64_t) {
-	set_error("find6DPoses: the non-minimal PnP solvers (EPnP + LM, SURVEY.md 8f-1) are not implemented yet; the PnP "
-	          "operators (P3P solver, reprojection matrix, score, PEARL) are available through the operator ABI");
-	return PXB_ERR_UNSUPPORTED;
+// find6DPoses_ (progressivex_python.cpp:41-171): K^-1-normalised image points for estimation, threshold / f, the
+// neighbourhood graph on the UN-normalised [u v X Y Z] rows (:104 vs :143), uniform samplers.
+int pxb_find_6d_poses(pxb_ctx *ctx, const double *image_points, const double *world_points, const double *K,
+                      int64_t N, int64_t *labeling_out, double *poses_out, int64_t max_models_out,
+                      double spatial_coherence_weight, double threshold, double confidence,
+                      double neighborhood_ball_radius, double maximum_tanimoto_similarity, size_t max_iters,
+                      size_t minimum_point_number, int maximum_model_number, uint64_t seed) {
+	if (!ctx || !image_points || !world_points || !K || !labeling_out || !poses_out || N < 3) {
+		set_error("bad argument");
+		return PXB_ERR_ARGUMENT;
+	}
+	// Eigen Matrix3d::inverse(): cofactors / determinant
+	double Kinv[9];
+	{
+		const double *m = K;
+		const double c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8], c02 = m[3] * m[7] - m[4] * m[6];
+		const double det = m[0] * c00 + m[1] * c01 + m[2] * c02;
+		const double id = 1.0 / det;
+		Kinv[0] = c00 * id;
+		Kinv[1] = (m[2] * m[7] - m[1] * m[8]) * id;
+		Kinv[2] = (m[1] * m[5] - m[2] * m[4]) * id;
+		Kinv[3] = c01 * id;
+		Kinv[4] = (m[0] * m[8] - m[2] * m[6]) * id;
+		Kinv[5] = (m[2] * m[3] - m[0] * m[5]) * id;
+		Kinv[6] = c02 * id;
+		Kinv[7] = (m[1] * m[6] - m[0] * m[7]) * id;
+		Kinv[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+	}
+	std::vector<double> raw((size_t)N * 5), nrm((size_t)N * 5);
+	for (int64_t i = 0; i < N; ++i) {
+		const double u = image_points[2 * i], v = image_points[2 * i + 1];
+		raw[5 * i] = u;
+		raw[5 * i + 1] = v;
+		nrm[5 * i] = Kinv[0] * u + Kinv[1] * v + Kinv[2] * 1;
+		nrm[5 * i + 1] = Kinv[3] * u + Kinv[4] * v + Kinv[5] * 1;
+		for (int c = 0; c < 3; ++c) raw[5 * i + 2 + c] = nrm[5 * i + 2 + c] = world_points[3 * i + c];
+	}
+	const double f = 0.5 * (K[0] + K[4]);
+	Settings s;
+	s.type = PXB_MODEL_PNP;
+	s.min_inliers = minimum_point_number;
+	s.threshold = threshold / f;
+	s.confidence = confidence;
+	s.max_tanimoto = maximum_tanimoto_similarity;
+	s.lambda = spatial_coherence_weight;
+	s.max_iters = max_iters;
+	if (maximum_model_number > 0) s.max_models = (size_t)maximum_model_number;
+	s.sampler_id = 0;
+	if (seed == 0) seed = (uint64_t)std::chrono::high_resolution_clock::now().time_since_epoch().count();
+	s.seed = seed;
+	PXB_TRY(pxb_upload_points(ctx, PXB_MODEL_PNP, raw.data(), N));
+	Driver drv(ctx, s);
+	if (spatial_coherence_weight > 0.0) PXB_TRY(drv.build_graph(neighborhood_ball_radius, 8));
+	PXB_TRY(pxb_upload_points(ctx, PXB_MODEL_PNP, nrm.data(), N));
+	PXB_TRY(drv.run());
+	const auto &inst = drv.instances();
+	const int64_t M = (int64_t)inst.size();
+	for (int64_t k = 0; k < std::min(M, max_models_out); ++k) std::memcpy(poses_out + k * 12, inst[k].model.data(), sizeof(double) * 12);
+	std::memcpy(labeling_out, drv.labeling().data(), sizeof(int64_t) * (size_t)N);
+	return (int)M;
 }
 
 } // extern "C"

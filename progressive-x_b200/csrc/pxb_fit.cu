@@ -234,10 +234,6 @@ __global__ void __launch_bounds__(kFitThreads)
 int launch_fit_h(pxb_ctx *ctx, int P, const int32_t *off, const int32_t *idx, const double *weights, double *H_out,
                  int32_t *ok_out) {
 	if (P <= 0) return PXB_OK;
-	if (ctx->pts.type != PXB_MODEL_HOMOGRAPHY) {
-		set_error("non-minimal fitting is implemented for homographies only (F / PnP are SURVEY 8f-1 'next')");
-		return PXB_ERR_UNSUPPORTED;
-	}
 	k_fit_h<<<(unsigned)P, kFitThreads, 0, ctx->stream>>>(ctx->pts.aos, off, idx, weights, H_out, ok_out);
 	ctx->launches++;
 	PXB_CUDA(cudaGetLastError());
@@ -245,6 +241,12 @@ int launch_fit_h(pxb_ctx *ctx, int P, const int32_t *off, const int32_t *idx, co
 }
 
 } // namespace pxb
+
+namespace pxb {
+int launch_fit_f(pxb_ctx *ctx, int P, const int32_t *off, const int32_t *idx, const double *weights, double *F_out,
+                 int32_t *ok_out);
+int launch_fit_pnp(pxb_ctx *ctx, int P, const int32_t *off, const int32_t *idx, double *P_out, int32_t *ok_out);
+}
 
 extern "C" {
 using namespace pxb;
@@ -265,8 +267,8 @@ int pxb_knn_graph(pxb_ctx *ctx, double radius, int k, int32_t *nbr_out_host, int
 	return PXB_OK;
 }
 
-int pxb_fit_homographies(pxb_ctx *ctx, int32_t P, const int32_t *off_host, const int32_t *idx_host,
-                         const double *weights_by_row_host, double *H_out_host, int32_t *ok_out_host) {
+int pxb_fit_nonminimal(pxb_ctx *ctx, int32_t P, const int32_t *off_host, const int32_t *idx_host,
+                       const double *weights_by_row_host, double *H_out_host, int32_t *ok_out_host) {
 	PXB_CHECK_ARG(ctx && off_host && idx_host && H_out_host && ok_out_host && P >= 0, "null argument");
 	if (P == 0) return PXB_OK;
 	if (ctx->pts.N <= 0) {
@@ -281,7 +283,8 @@ int pxb_fit_homographies(pxb_ctx *ctx, int32_t P, const int32_t *off_host, const
 		}
 	PXB_TRY(ctx->idx.reserve(sizeof(int32_t) * (size_t)(P + 1 + total) + 64));
 	int32_t *d_off = ctx->idx.as<int32_t>(), *d_idx = d_off + (P + 1);
-	PXB_TRY(ctx->models.reserve(sizeof(double) * (size_t)P * 9));
+	const int ms = model_size(ctx->pts.type);
+	PXB_TRY(ctx->models.reserve(sizeof(double) * (size_t)P * ms));
 	PXB_TRY(ctx->outA.reserve(sizeof(int32_t) * (size_t)P));
 	double *d_w = nullptr;
 	if (weights_by_row_host) {
@@ -292,10 +295,23 @@ int pxb_fit_homographies(pxb_ctx *ctx, int32_t P, const int32_t *off_host, const
 	}
 	PXB_CUDA(cudaMemcpyAsync(d_off, off_host, sizeof(int32_t) * (size_t)(P + 1), cudaMemcpyHostToDevice, ctx->stream));
 	PXB_CUDA(cudaMemcpyAsync(d_idx, idx_host, sizeof(int32_t) * (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
-	PXB_TRY(launch_fit_h(ctx, P, d_off, d_idx, d_w, ctx->models.as<double>(), ctx->outA.as<int32_t>()));
-	PXB_CUDA(cudaMemcpyAsync(H_out_host, ctx->models.ptr, sizeof(double) * (size_t)P * 9, cudaMemcpyDeviceToHost, ctx->stream));
+	switch (ctx->pts.type) {
+	case PXB_MODEL_HOMOGRAPHY: PXB_TRY(launch_fit_h(ctx, P, d_off, d_idx, d_w, ctx->models.as<double>(), ctx->outA.as<int32_t>())); break;
+	case PXB_MODEL_FUNDAMENTAL: PXB_TRY(launch_fit_f(ctx, P, d_off, d_idx, d_w, ctx->models.as<double>(), ctx->outA.as<int32_t>())); break;
+	default: PXB_TRY(launch_fit_pnp(ctx, P, d_off, d_idx, ctx->models.as<double>(), ctx->outA.as<int32_t>())); break;
+	}
+	PXB_CUDA(cudaMemcpyAsync(H_out_host, ctx->models.ptr, sizeof(double) * (size_t)P * ms, cudaMemcpyDeviceToHost, ctx->stream));
 	PXB_CUDA(cudaMemcpyAsync(ok_out_host, ctx->outA.ptr, sizeof(int32_t) * (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
 	PXB_CUDA(cudaStreamSynchronize(ctx->stream));
 	return PXB_OK;
+}
+
+int pxb_fit_homographies(pxb_ctx *ctx, int32_t P, const int32_t *off_host, const int32_t *idx_host,
+                         const double *weights_by_row_host, double *H_out_host, int32_t *ok_out_host) {
+	if (ctx && ctx->pts.type != PXB_MODEL_HOMOGRAPHY) {
+		set_error("pxb_fit_homographies needs homography correspondences uploaded");
+		return PXB_ERR_STATE;
+	}
+	return pxb_fit_nonminimal(ctx, P, off_host, idx_host, weights_by_row_host, H_out_host, ok_out_host);
 }
 }

@@ -83,6 +83,7 @@ def load_library() -> C.CDLL:
     lib.pxb_lo_graph_cut.argtypes = [vp, vp, vp, vp, i64, f64, vp, vp, vp]
     lib.pxb_knn_graph.argtypes = [vp, f64, C.c_int, vp, vp]
     lib.pxb_fit_homographies.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    lib.pxb_fit_nonminimal.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     lib.pxb_find_homographies.argtypes = [vp, vp, i64, vp, vp, i64, sz, sz, sz, sz, f64, f64, f64, f64, f64, sz, sz,
                                           C.c_int, sz, f64, C.c_int, u64]
     lib.pxb_find_two_view_motions.argtypes = lib.pxb_find_homographies.argtypes
@@ -311,11 +312,13 @@ class Context:
         off[1:] = np.cumsum([len(s) for s in index_sets])
         idx = np.ascontiguousarray(np.concatenate([np.asarray(s, dtype=np.int32) for s in index_sets]))
         w = None if weights_by_row is None else _f64(weights_by_row)
-        H = np.zeros((len(index_sets), 9))
+        H = np.zeros((len(index_sets), MODEL_SIZE[self.model_type]))
         ok = np.zeros(len(index_sets), dtype=np.int32)
-        _check(self.lib.pxb_fit_homographies(self.handle, len(index_sets), _ptr(off), _ptr(idx), _ptr(w), _ptr(H),
-                                             _ptr(ok)))
+        _check(self.lib.pxb_fit_nonminimal(self.handle, len(index_sets), _ptr(off), _ptr(idx), _ptr(w), _ptr(H),
+                                           _ptr(ok)))
         return H, ok
+
+    fit_nonminimal = fit_homographies
 
     def selftest_division(self, seed: int, n: int, mode: int) -> int:
         bad = C.c_int64()
