@@ -32,6 +32,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <memory>
@@ -440,7 +441,13 @@ int Driver::propose(uint64_t round_seed, std::vector<double> &model_out, bool &f
 	std::vector<double> best_model;
 
 	// ---- block state ----
-	const size_t B = 512;
+	// Block size of the replay. Any value gives the same result for the same seed (the sample stream does not depend
+	// on it); PXB_BLOCK_SIZE=1 *is* the reference's sequential loop and is what tests/test_gpu_e2e.py compares against.
+	size_t B = 512, Bmin = 32;
+	if (const char *e = getenv("PXB_BLOCK_SIZE")) {
+		const long v = atol(e);
+		if (v >= 1) B = Bmin = (size_t)v;
+	}
 	std::vector<int64_t> samples;       // B x m
 	std::vector<uint8_t> sampled_ok;    // sampler success per slot
 	std::vector<double> blk_models;     // B x maxsol x ms
@@ -450,7 +457,7 @@ int Driver::propose(uint64_t round_seed, std::vector<double> &model_out, bool &f
 	std::vector<double> blk_val, blk_shr;
 	size_t cursor = 0, filled = 0;
 	auto refill = [&](size_t want) -> int {
-		want = std::max<size_t>(std::min(want, B), 32);
+		want = std::max<size_t>(std::min(want, B), std::min(Bmin, B));
 		samples.assign(want * m_, 0);
 		sampled_ok.assign(want, 0);
 		std::vector<size_t> sub(m_);
