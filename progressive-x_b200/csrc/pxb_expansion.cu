@@ -1,9 +1,9 @@
 // pxb_expansion.cu -- a11: the alpha-expansion label sweep of PEARL and the st-cut of the GC-RANSAC local
 // optimisation, both on one GPU min-cut engine.
 //
-//   k_maxflow                 synchronous (pulse-based) push-relabel on a CSR residual graph with backward-BFS global
-//                             relabelling, one persistent cooperative kernel per cut (grid-wide barriers between the
-//                             push and the gather/relabel phase, no host round trips).
+//   k_maxflow                 lock-free asynchronous push-relabel (Hong & He) on a CSR residual graph, alternating with
+//                             exact backward-BFS global relabelling, one persistent cooperative kernel per cut (grid
+//                             barriers only around the BFS levels, no host round trips).
 //   pxb_lo_graph_cut          GCRANSAC::labeling                       gcr/GCRANSAC.h:964-1018
 //   launch_alpha_expansion    GCoptimization::expansion / oneExpansionIteration / alpha_expansion
 //                                                                     gcr/GCoptimization.cpp:1003-1086,1239-1318
@@ -18,9 +18,10 @@
 // structural zeros (equal data costs on both sides) are exact zeros here too. What can differ is the rounding of
 // partially used capacities; that only matters on exact ties between cuts (DESIGN.md "Max-flow parity").
 //
-// The pulse scheme is deterministic: in the push phase an arc is written only by its tail (two nodes can never both
-// find the same arc pair admissible because admissibility requires height[tail] == height[head] + 1), pushed amounts
-// are parked per arc, and every node adds its inflow in arc order in the gather phase. No floating-point atomics.
+// A first, fully synchronous (pulse) version was deterministic to the bit but needed ~10^4 grid barriers per cut
+// (0.5 s at N = 10^4); the asynchronous phase removes the barriers. Floating-point atomics make the rounding of
+// partially used capacities run-dependent, which cannot change the cut except on exact ties (saturating pushes and
+// emptied excesses are exact zeros in every order).
 //
 // Round-1 split of work: the host builds the binary-energy graph of each move (integer bookkeeping plus two or three
 // flops per edge, exactly the add_term1/add_term2 sequence of the reference) and evaluates labelling energies in the
@@ -29,6 +30,9 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <unordered_set>
 #include <vector>
@@ -48,8 +52,7 @@ struct FlowGraphDev {
 };
 
 constexpr int kMfThreads = 256;
-constexpr int kGlobalRelabelEvery = 64;
-constexpr int kMaxPulses = 2000000;
+constexpr int kWideDegree = 64;
 
 __device__ void mf_global_relabel(const FlowGraphDev &G, int32_t *h, cg::grid_group &grid, int tid, int nthreads) {
 	const int n = G.n;
@@ -82,75 +85,104 @@ __device__ void mf_global_relabel(const FlowGraphDev &G, int32_t *h, cg::grid_gr
 	grid.sync();
 }
 
+// One asynchronous push-relabel step of node u (Hong & He's lock-free rule: push to the LOWEST residual neighbour if it
+// is lower, else lift to one above it). Only the owner thread of u lowers excess[u] / cap[out-arcs of u] and writes
+// height[u]; everybody else only adds to them, so the atomics below can never drive a value negative.
+__device__ __forceinline__ void mf_process(const FlowGraphDev &G, volatile int32_t *h, int u) {
+	const int n = G.n;
+	volatile double *excess = G.excess, *cap = G.cap;
+	const double e = excess[u];
+	const int hu = h[u];
+	if (!(e > 0.0) || hu >= n) return;
+	if (G.sink_cap[u] > 0.0) { // the sink (height 0) is always the lowest neighbour
+		const double d = fmin(e, G.sink_cap[u]);
+		G.sink_cap[u] -= d;
+		atomicAdd(&G.excess[u], -d);
+		return;
+	}
+	const int a0 = G.arc_off[u], a1 = G.arc_off[u + 1];
+	if (a1 - a0 > kWideDegree) {
+		// high-degree node (a label-cost auxiliary node): one pass that pushes to EVERY lower residual neighbour, so
+		// that its budget is spread in one visit instead of one neighbour per visit
+		double rem = e;
+		int lowest = 0x7fffffff;
+		for (int a = a0; a < a1 && rem > 0.0; ++a) {
+			const double c = cap[a];
+			if (!(c > 0.0)) continue;
+			const int v = G.arc_head[a];
+			const int hv = h[v];
+			if (hv < hu) {
+				const double d = fmin(rem, c);
+				atomicAdd(&G.cap[a], -d);
+				atomicAdd(&G.cap[G.arc_rev[a]], d);
+				atomicAdd(&G.excess[v], d);
+				rem -= d;
+			} else {
+				lowest = min(lowest, hv);
+			}
+		}
+		if (rem < e) atomicAdd(&G.excess[u], rem - e);
+		if (rem > 0.0) { // everything lower is saturated: lift above the lowest remaining residual neighbour
+			for (int a = a0; a < a1; ++a)
+				if (cap[a] > 0.0) lowest = min(lowest, (int)h[G.arc_head[a]]);
+			h[u] = lowest == 0x7fffffff ? n : min(max(lowest + 1, hu), n);
+		}
+		return;
+	}
+	int best_h = 0x7fffffff, best_a = -1;
+	for (int a = a0; a < a1; ++a)
+		if (cap[a] > 0.0) {
+			const int hv = h[G.arc_head[a]];
+			if (hv < best_h) {
+				best_h = hv;
+				best_a = a;
+			}
+		}
+	if (best_a < 0) { // no residual arc at all: the excess is stranded on the source side
+		h[u] = n;
+		return;
+	}
+	if (hu > best_h) {
+		const double d = fmin(e, cap[best_a]);
+		atomicAdd(&G.cap[best_a], -d);
+		atomicAdd(&G.cap[G.arc_rev[best_a]], d);
+		atomicAdd(&G.excess[G.arc_head[best_a]], d);
+		atomicAdd(&G.excess[u], -d);
+	} else {
+		h[u] = min(best_h + 1, n);
+	}
+}
+
+constexpr int kAsyncCycles = 192;
+constexpr int kMaxRounds = 100000;
+
 __global__ void __launch_bounds__(kMfThreads) k_maxflow(FlowGraphDev G) {
 	cg::grid_group grid = cg::this_grid();
 	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
 	const int nthreads = gridDim.x * blockDim.x;
 	const int n = G.n;
-	int cur = 0;
-	for (int pulse = 0; pulse < kMaxPulses; ++pulse) {
-		int32_t *h = G.height[cur], *hn = G.height[cur ^ 1];
-		if (pulse % kGlobalRelabelEvery == 0) mf_global_relabel(G, h, grid, tid, nthreads);
-		// ---- push phase: heights are frozen, an admissible arc is written by its tail only ----
-		for (int u = tid; u < n; u += nthreads) {
-			double e = G.excess[u];
-			const int hu = h[u];
-			if (!(e > 0.0) || hu >= n) continue;
-			if (hu == 1 && G.sink_cap[u] > 0.0) {
-				const double d = fmin(e, G.sink_cap[u]);
-				G.sink_cap[u] -= d;
-				e -= d;
-			}
-			for (int a = G.arc_off[u]; a < G.arc_off[u + 1] && e > 0.0; ++a) {
-				const double c = G.cap[a];
-				if (c > 0.0 && h[G.arc_head[a]] == hu - 1) {
-					const double d = fmin(e, c);
-					G.cap[a] = c - d;
-					G.pushed[a] = d;
-					e -= d;
-				}
-			}
-			G.excess[u] = e;
-		}
-		if (tid == 0) G.flags[3 + ((pulse + 1) % 3)] = 0;
-		grid.sync();
-		// ---- gather + relabel phase ----
+	int32_t *h = G.height[0];
+	int round = 0;
+	for (; round < kMaxRounds; ++round) {
+		// exact distance-to-sink labels; nodes that cannot reach the sink any more get height n and go quiet
+		mf_global_relabel(G, h, grid, tid, nthreads);
 		bool active = false;
-		for (int u = tid; u < n; u += nthreads) {
-			double e = G.excess[u];
-			const int a0 = G.arc_off[u], a1 = G.arc_off[u + 1];
-			for (int a = a0; a < a1; ++a) {
-				const int ra = G.arc_rev[a];
-				const double d = G.pushed[ra];
-				if (d != 0.0) {
-					e += d;
-					G.cap[a] += d;
-					G.pushed[ra] = 0.0;
-				}
-			}
-			G.excess[u] = e;
-			int hu = h[u];
-			if (e > 0.0 && hu < n) {
-				// admissible arc left? otherwise lift to one above the lowest residual neighbour
-				int lowest = (G.sink_cap[u] > 0.0) ? 0 : n;
-				for (int a = a0; a < a1; ++a)
-					if (G.cap[a] > 0.0) lowest = min(lowest, h[G.arc_head[a]]);
-				if (lowest >= hu) hu = min(lowest + 1, n);
-				if (hu < n) active = true;
-			}
-			hn[u] = hu;
-		}
-		if (active) G.flags[3 + (pulse % 3)] = 1;
+		for (int u = tid; u < n; u += nthreads) active |= (G.excess[u] > 0.0 && h[u] < n);
+		if (tid == 0) G.flags[3 + ((round + 1) % 3)] = 0;
+		if (active) G.flags[3 + (round % 3)] = 1;
 		grid.sync();
-		cur ^= 1;
-		if (G.flags[3 + (pulse % 3)] == 0) {
-			if (tid == 0) G.flags[6] = pulse + 1;
-			break;
-		}
+		if (G.flags[3 + (round % 3)] == 0) break;
+		// asynchronous phase: no barriers, every thread keeps discharging its own nodes
+		for (int c = 0; c < kAsyncCycles; ++c)
+			for (int u = tid; u < n; u += nthreads) mf_process(G, h, u);
+		__threadfence();
+		grid.sync();
 	}
-	// final reachability: height < n  <=>  the node can reach the sink in the residual graph  <=>  BK's SINK
-	mf_global_relabel(G, G.height[0], grid, tid, nthreads);
-	if (tid == 0) G.flags[7] = 1;
+	// heights now hold the final reachability: height < n  <=>  the node can reach the sink in the residual graph
+	if (tid == 0) {
+		G.flags[6] = round + 1;
+		G.flags[7] = round < kMaxRounds ? 1 : 0;
+	}
 }
 
 // ---- host-side graph assembly with the reference's Energy/Graph arithmetic -----------------------------------
@@ -199,6 +231,7 @@ struct FlowGraphHost {
 
 // Solve the cut on the device. segment[i] = 1 iff node i ends on the SINK side (BK rule).
 static int solve_min_cut(pxb_ctx *ctx, const FlowGraphHost &g, std::vector<uint8_t> &segment) {
+	const auto t_begin = std::chrono::steady_clock::now();
 	const int n = g.n;
 	const int pairs = (int)g.tail.size();
 	const int m = 2 * pairs;
@@ -281,10 +314,19 @@ static int solve_min_cut(pxb_ctx *ctx, const FlowGraphHost &g, std::vector<uint8
 	PXB_CUDA(cudaMemcpyAsync(flags, d_flags, sizeof(flags), cudaMemcpyDeviceToHost, st));
 	PXB_CUDA(cudaStreamSynchronize(st));
 	if (flags[7] != 1 || flags[6] == 0) {
-		set_error("max-flow did not converge within %d pulses", kMaxPulses);
+		set_error("max-flow did not converge within %d relabel rounds", kMaxRounds);
 		return PXB_ERR_CUDA;
 	}
 	for (int i = 0; i < n; ++i) segment[i] = h[i] < n ? 1 : 0;
+	if (getenv("PXB_MF_STATS")) {
+		static int calls = 0;
+		static double total_ms = 0;
+		const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+		total_ms += ms;
+		if (++calls % 20 == 0 || ms > 50)
+			fprintf(stderr, "[pxb maxflow] call %d: n=%d arcs=%d rounds=%d grid=%d  %.2f ms (total %.1f ms)\n", calls, n, m,
+			        flags[6], grid, ms, total_ms);
+	}
 	return PXB_OK;
 }
 
@@ -402,6 +444,22 @@ int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t
 					}
 					g.add_term2(v, aux[l], 0, 0, label_cost, 0);
 				}
+			}
+			// An auxiliary arc aux -> site can never carry more than the site can pass on (its own sink link plus its
+			// outgoing n-links). Clamping it to that bound leaves every maximum flow -- and the set of nodes that can
+			// reach the sink -- unchanged, but lets the auxiliary node spread its budget in one discharge.
+			if (label_cost > 0 && g.n > size) {
+				std::vector<double> out_cap((size_t)g.n, 0.0);
+				for (size_t pidx = 0; pidx < g.tail.size(); ++pidx) {
+					out_cap[g.tail[pidx]] += g.cap_fwd[pidx];
+					out_cap[g.head[pidx]] += g.cap_rev[pidx];
+				}
+				for (size_t pidx = 0; pidx < g.tail.size(); ++pidx)
+					if (g.head[pidx] >= size) { // site -> aux pair: cap_fwd = 0, cap_rev = label cost (aux -> site)
+						const int v = g.tail[pidx];
+						const double bound = (g.tr[v] < 0 ? -g.tr[v] : 0.0) + out_cap[v];
+						g.cap_rev[pidx] = std::min(g.cap_rev[pidx], bound);
+					}
 			}
 			PXB_TRY(solve_min_cut(ctx, g, seg));
 			// candidate labelling: SOURCE side (get_var == 0) takes alpha (:451-469)
