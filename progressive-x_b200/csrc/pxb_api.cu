@@ -123,6 +123,9 @@ void pxb_ctx_destroy(pxb_ctx *ctx) {
 	cudaStreamSynchronize(ctx->stream);
 	if (ctx->pts.soa) cudaFree(ctx->pts.soa);
 	if (ctx->pts.aos) cudaFree(ctx->pts.aos);
+	if (ctx->pts.f32n) cudaFree(ctx->pts.f32n);
+	if (ctx->pts.q) cudaFree(ctx->pts.q);
+	if (ctx->pts.norm) cudaFree(ctx->pts.norm);
 	DevBuf *bufs[] = {&ctx->models, &ctx->pref, &ctx->pref2, &ctx->outA, &ctx->outB, &ctx->outC,
 	                  &ctx->outD,   &ctx->idx,  &ctx->mask,  &ctx->partials, &ctx->staging};
 	for (DevBuf *b : bufs) b->release();
@@ -184,9 +187,15 @@ int pxb_upload_points(pxb_ctx *ctx, int model_type, const double *pts_host, int6
 		PXB_CUDA(cudaStreamSynchronize(ctx->stream));
 		if (p.soa) PXB_CUDA(cudaFree(p.soa));
 		if (p.aos) PXB_CUDA(cudaFree(p.aos));
+		if (p.f32n) PXB_CUDA(cudaFree(p.f32n));
+		if (p.q) PXB_CUDA(cudaFree(p.q));
 		p.soa = p.aos = nullptr;
+		p.f32n = p.q = nullptr;
 		PXB_CUDA(cudaMalloc(&p.soa, sizeof(double) * (size_t)stride * dim));
 		PXB_CUDA(cudaMalloc(&p.aos, sizeof(double) * (size_t)stride * dim));
+		PXB_CUDA(cudaMalloc(&p.f32n, sizeof(float) * (size_t)stride * dim));
+		PXB_CUDA(cudaMalloc(&p.q, sizeof(float) * (size_t)stride));
+		if (!p.norm) PXB_CUDA(cudaMalloc(&p.norm, 64));
 	}
 	p.type = model_type;
 	p.dim = dim;

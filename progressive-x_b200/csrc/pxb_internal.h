@@ -12,6 +12,7 @@
 
 namespace pxb {
 
+struct NormDev;
 void set_error(const char *fmt, ...);
 
 #define PXB_CUDA(call)                                                                                  \
@@ -62,6 +63,11 @@ struct Points {
 	int64_t stride = 0;
 	double *soa = nullptr; // [dim][stride]
 	double *aos = nullptr; // [N][dim] as uploaded (used by the solvers' gathers)
+	// float32 screening copy (pxb_screen.cuh): normalised coordinates [dim][stride], per-point error scale [stride],
+	// and the normalisation itself (device-resident, written by k_point_stats)
+	float *f32n = nullptr;
+	float *q = nullptr;
+	struct NormDev *norm = nullptr;
 };
 
 } // namespace pxb

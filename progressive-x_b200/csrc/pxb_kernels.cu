@@ -25,6 +25,7 @@
 
 #include "pxb_internal.h"
 #include "pxb_residuals.cuh"
+#include "pxb_screen.cuh"
 
 namespace pxb {
 
@@ -32,17 +33,64 @@ namespace pxb {
 // ------------------------------------------------------------------------------------------------
 // AoS -> SoA re-tiling of the uploaded points
 // ------------------------------------------------------------------------------------------------
-__global__ void k_aos_to_soa(const double *__restrict__ aos, double *__restrict__ soa, int64_t N, int64_t stride,
-                             int dim) {
+// Bounding box of the finite coordinates -> NormDev (centre + common scale) for the float32 screening copy.
+__global__ void __launch_bounds__(1024) k_point_stats(const double *__restrict__ aos, int64_t N, int dim, int type, NormDev *out) {
+	__shared__ double s_lo[32][5], s_hi[32][5];
+	double lo[5], hi[5];
+	for (int c = 0; c < 5; ++c) lo[c] = 1e300, hi[c] = -1e300;
+	for (int64_t i = threadIdx.x; i < N; i += blockDim.x)
+		for (int c = 0; c < dim; ++c) {
+			const double v = aos[i * dim + c];
+			if (fabs(v) <= 1e300) lo[c] = fmin(lo[c], v), hi[c] = fmax(hi[c], v);
+		}
+	for (int c = 0; c < 5; ++c)
+		for (int o = 16; o > 0; o >>= 1) {
+			lo[c] = fmin(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+			hi[c] = fmax(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+		}
+	if ((threadIdx.x & 31) == 0)
+		for (int c = 0; c < 5; ++c) s_lo[threadIdx.x >> 5][c] = lo[c], s_hi[threadIdx.x >> 5][c] = hi[c];
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		NormDev nd;
+		double s = 0.0;
+		for (int c = 0; c < 5; ++c) {
+			double l = 1e300, h = -1e300;
+			for (int w = 0; w < 32; ++w) l = fmin(l, s_lo[w][c]), h = fmax(h, s_hi[w][c]);
+			const bool used = c < dim && !(type == PXB_MODEL_PNP && c < 2) && l <= h;
+			nd.c[c] = used ? 0.5 * (l + h) : 0.0;
+			if (used) s = fmax(s, 0.5 * (h - l));
+		}
+		nd.s = (s > 1e-300 && s < 1e300) ? s : 1.0;
+		nd.inv_s = 1.0 / nd.s;
+		*out = nd;
+	}
+}
+
+__global__ void k_aos_to_soa(const double *__restrict__ aos, double *__restrict__ soa, float *__restrict__ f32n,
+                             float *__restrict__ q, const NormDev *__restrict__ norm, int64_t N, int64_t stride, int dim,
+                             int type) {
 	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= stride) return;
-	for (int c = 0; c < dim; ++c) soa[c * stride + i] = (i < N) ? aos[i * dim + c] : 0.0;
+	double p[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+	for (int c = 0; c < dim; ++c) soa[c * stride + i] = p[c] = (i < N) ? aos[i * dim + c] : 0.0;
+	const NormDev nd = *norm;
+	float pf[5], qq;
+	switch (type) {
+	case PXB_MODEL_HOMOGRAPHY: screen_point<PXB_MODEL_HOMOGRAPHY>(p, nd, pf, qq); break;
+	case PXB_MODEL_FUNDAMENTAL: screen_point<PXB_MODEL_FUNDAMENTAL>(p, nd, pf, qq); break;
+	default: screen_point<PXB_MODEL_PNP>(p, nd, pf, qq); break;
+	}
+	for (int c = 0; c < dim; ++c) f32n[c * stride + i] = pf[c];
+	q[i] = qq;
 }
 
 int launch_aos_to_soa(pxb_ctx *ctx) {
 	Points &p = ctx->pts;
+	k_point_stats<<<1, 1024, 0, ctx->stream>>>(p.aos, p.N, p.dim, p.type, p.norm);
+	ctx->launches++;
 	const int grid = (int)((p.stride + kThreads - 1) / kThreads);
-	k_aos_to_soa<<<grid, kThreads, 0, ctx->stream>>>(p.aos, p.soa, p.N, p.stride, p.dim);
+	k_aos_to_soa<<<grid, kThreads, 0, ctx->stream>>>(p.aos, p.soa, p.f32n, p.q, p.norm, p.N, p.stride, p.dim, p.type);
 	ctx->launches++;
 	PXB_CUDA(cudaGetLastError());
 	return PXB_OK;
@@ -56,13 +104,52 @@ int launch_aos_to_soa(pxb_ctx *ctx) {
 // shared memory (padded to an even number of doubles so that a model is read with LDS.128 broadcasts).
 // Per evaluation: 28 FP64-pipe instructions (H), ~1.5 LDS, 1 STG, 6 range-test instructions, one branch per
 // hypothesis for the whole register tile -> the FP64 pipe (2 issue slots per instruction) is the binding unit.
-constexpr int kRmHypsPerBlock = 32; // 128 gains ~1% at K=10k but starves the grid at RANSAC batch sizes
+// hypotheses per block: 32 keeps the grid full at RANSAC batch sizes (K ~ 500); large batches take 64 (half the
+// per-block prologue: point loads, input screening, barrier)
+constexpr int kRmHypsSmall = 32, kRmHypsLarge = 64;
+constexpr int64_t kRmLargeBatch = 4096;
 
 template <typename OUT> __device__ __forceinline__ void store_stream(OUT *p, double v);
 template <> __device__ __forceinline__ void store_stream<double>(double *p, double v) { __stcs(p, v); }
 template <> __device__ __forceinline__ void store_stream<float>(float *p, double v) { __stcs(p, __double2float_rn(v)); }
 
-template <int TYPE, typename OUT, bool HAS_R2, bool HAS_MASK, int kRmP, int MINB, bool HI_ONLY>
+template <int TYPE, typename OUT, bool HAS_R2, bool HAS_MASK, int kRmP, bool HI_ONLY, bool FULL>
+__device__ __forceinline__ void rm_hypothesis_loop(const double (&p)[kRmP][5], const bool (&valid)[kRmP],
+                                                   const double *s_models, int nk, int wild, double T2, unsigned hiT,
+                                                   OUT *out, uint32_t *mout, int64_t N, int64_t words, int nwords,
+                                                   int lane) {
+	constexpr int MP = ModelTraits<TYPE>::kPadded;
+#pragma unroll 2
+	for (int k = 0; k < nk; ++k) {
+		double m[12];
+		load_model_smem<TYPE>(s_models + k * MP, m);
+		double r[kRmP];
+		float lo[kRmP];
+#pragma unroll
+		for (int j = 0; j < kRmP; ++j) r[j] = squared_residual_tile<TYPE>(p[j], m, lo[j]);
+		if (__builtin_expect(!(tile_min4(lo) >= __int_as_float(kHiMinPattern)) || wild, 0))
+			PXB_RESIDUAL_TILE_EXACT(TYPE, kRmP, p, m, r);
+		if (HAS_R2) {
+#pragma unroll
+			for (int j = 0; j < kRmP; ++j)
+				if (FULL || valid[j]) store_stream<OUT>(out + 32 * j, r[j]);
+			out += N;
+		}
+		if (HAS_MASK) {
+			uint32_t w[kRmP];
+#pragma unroll
+			for (int j = 0; j < kRmP; ++j)
+				w[j] = __ballot_sync(0xffffffffu, (FULL || valid[j]) && below_threshold<HI_ONLY>(r[j], T2, hiT));
+			uint32_t mine = w[0];
+#pragma unroll
+			for (int j = 1; j < kRmP; ++j) mine = (lane == j) ? w[j] : mine;
+			if (lane < (FULL ? kRmP : nwords)) mout[lane] = mine;
+			mout += words;
+		}
+	}
+}
+
+template <int TYPE, typename OUT, bool HAS_R2, bool HAS_MASK, int kRmP, int MINB, bool HI_ONLY, int kRmHypsPerBlock>
 __global__ void __launch_bounds__(kThreads, MINB)
     k_residual_matrix(const double *__restrict__ soa, int64_t stride, int64_t N, const double *__restrict__ models,
                       int64_t K, double T2, OUT *__restrict__ r2, uint32_t *__restrict__ mask, int64_t words) {
@@ -97,38 +184,18 @@ __global__ void __launch_bounds__(kThreads, MINB)
 	const unsigned hiT = (unsigned)__double2hiint(T2);
 	OUT *out = HAS_R2 ? r2 + k0 * N + base + lane : nullptr;
 	uint32_t *mout = HAS_MASK ? mask + k0 * words + (base >> 5) : nullptr;
-	const int nwords = (int)min((int64_t)kRmP, words - (base >> 5));
-
-#pragma unroll 2
-	for (int k = 0; k < nk; ++k) {
-		double m[12];
-		load_model_smem<TYPE>(s_models + k * MP, m);
-		double r[kRmP];
-		float lo[kRmP];
-#pragma unroll
-		for (int j = 0; j < kRmP; ++j) r[j] = squared_residual_tile<TYPE>(p[j], m, lo[j]);
-		if (__builtin_expect(!(tile_min4(lo) >= __int_as_float(kHiMinPattern)) || wild, 0))
-			PXB_RESIDUAL_TILE_EXACT(TYPE, kRmP, p, m, r);
-		if (HAS_R2) {
-#pragma unroll
-			for (int j = 0; j < kRmP; ++j)
-				if (valid[j]) store_stream<OUT>(out + 32 * j, r[j]);
-			out += N;
-		}
-		if (HAS_MASK) {
-			uint32_t w[kRmP];
-#pragma unroll
-			for (int j = 0; j < kRmP; ++j) w[j] = __ballot_sync(0xffffffffu, valid[j] && below_threshold<HI_ONLY>(r[j], T2, hiT));
-			uint32_t mine = w[0];
-#pragma unroll
-			for (int j = 1; j < kRmP; ++j) mine = (lane == j) ? w[j] : mine;
-			if (lane < nwords) mout[lane] = mine;
-			mout += words;
-		}
-	}
+	// Interior warps (all kRmP x 32 points exist) run a loop without any per-point validity predicate: the 64-bit
+	// index compares and predicated stores of the ragged variant cost ~4 issue slots per evaluation. The branch is
+	// warp-uniform; only the single warp straddling N takes the ragged loop.
+	if (base + kRmPointsPerWarp <= N)
+		rm_hypothesis_loop<TYPE, OUT, HAS_R2, HAS_MASK, kRmP, HI_ONLY, true>(p, valid, s_models, nk, wild, T2, hiT, out,
+		                                                                      mout, N, words, kRmP, lane);
+	else
+		rm_hypothesis_loop<TYPE, OUT, HAS_R2, HAS_MASK, kRmP, HI_ONLY, false>(
+		    p, valid, s_models, nk, wild, T2, hiT, out, mout, N, words, (int)min((int64_t)kRmP, words - (base >> 5)), lane);
 }
 
-template <int TYPE, typename OUT, bool HI_ONLY>
+template <int TYPE, typename OUT, bool HI_ONLY, int HYPS>
 static int launch_rm_v(pxb_ctx *ctx, const double *models, int64_t K, double T2, OUT *r2, uint32_t *mask) {
 	constexpr int P = 4, MINB = 2; // tuned on B200: (4,3), (2,3), (2,4) are within 3% but never faster
 	const Points &p = ctx->pts;
@@ -137,17 +204,17 @@ static int launch_rm_v(pxb_ctx *ctx, const double *models, int64_t K, double T2,
 	const int64_t gx = (p.N + ppb - 1) / ppb;
 	int64_t done = 0;
 	while (done < K) { // gridDim.y is limited to 65535
-		const int64_t kk = std::min<int64_t>(K - done, (int64_t)65535 * kRmHypsPerBlock);
-		dim3 grid((unsigned)gx, (unsigned)((kk + kRmHypsPerBlock - 1) / kRmHypsPerBlock));
+		const int64_t kk = std::min<int64_t>(K - done, (int64_t)65535 * HYPS);
+		dim3 grid((unsigned)gx, (unsigned)((kk + HYPS - 1) / HYPS));
 		const double *mm = models + done * ModelTraits<TYPE>::kSize;
 		OUT *rr = r2 ? r2 + done * p.N : nullptr;
 		uint32_t *mk = mask ? mask + done * words : nullptr;
 		if (rr && mk)
-			k_residual_matrix<TYPE, OUT, true, true, P, MINB, HI_ONLY><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, mm, kk, T2, rr, mk, words);
+			k_residual_matrix<TYPE, OUT, true, true, P, MINB, HI_ONLY, HYPS><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, mm, kk, T2, rr, mk, words);
 		else if (rr)
-			k_residual_matrix<TYPE, OUT, true, false, P, MINB, false><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, mm, kk, T2, rr, mk, words);
+			k_residual_matrix<TYPE, OUT, true, false, P, MINB, false, HYPS><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, mm, kk, T2, rr, mk, words);
 		else if (mk)
-			k_residual_matrix<TYPE, OUT, false, true, P, MINB, HI_ONLY><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, mm, kk, T2, rr, mk, words);
+			k_residual_matrix<TYPE, OUT, false, true, P, MINB, HI_ONLY, HYPS><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, mm, kk, T2, rr, mk, words);
 		ctx->launches++;
 		done += kk;
 	}
@@ -157,8 +224,14 @@ static int launch_rm_v(pxb_ctx *ctx, const double *models, int64_t K, double T2,
 
 template <int TYPE, typename OUT>
 static int launch_rm_t(pxb_ctx *ctx, const double *models, int64_t K, double T2, OUT *r2, uint32_t *mask) {
-	return threshold_low_word_is_zero(T2) ? launch_rm_v<TYPE, OUT, true>(ctx, models, K, T2, r2, mask)
-	               : launch_rm_v<TYPE, OUT, false>(ctx, models, K, T2, r2, mask);
+	static const int forced = getenv("PXB_RM_HYPS") ? atoi(getenv("PXB_RM_HYPS")) : 0; // tuning knob (tools/time_kernels.py)
+	const bool large = forced ? forced >= kRmHypsLarge : K >= kRmLargeBatch;
+	const bool hi = threshold_low_word_is_zero(T2);
+	if (large)
+		return hi ? launch_rm_v<TYPE, OUT, true, kRmHypsLarge>(ctx, models, K, T2, r2, mask)
+		          : launch_rm_v<TYPE, OUT, false, kRmHypsLarge>(ctx, models, K, T2, r2, mask);
+	return hi ? launch_rm_v<TYPE, OUT, true, kRmHypsSmall>(ctx, models, K, T2, r2, mask)
+	          : launch_rm_v<TYPE, OUT, false, kRmHypsSmall>(ctx, models, K, T2, r2, mask);
 }
 
 int launch_residual_matrix(pxb_ctx *ctx, const double *models, int64_t K, double T2, double *r2, float *r2f,

@@ -2,134 +2,238 @@
 //
 // Replaces MSACScoringFunctionWithCompoundModel::getScore (px/include/scoring_function_with_compound_model.h:61-125)
 // for K hypotheses at once: per hypothesis the inlier count, sum max(0, 1 - r2/T2) and the support shared with the
-// compound preference vector, sum min(compound_pref_i, pref_i).
+// compound preference vector, sum min(compound_pref_i, pref_i). All three only involve the INLIERS of a hypothesis.
 //
-// Shape of the kernel (same register tile as k_residual_matrix, so the same FP64-dispatch bound applies):
-//   block = 256 threads = 1024 points (lane owns base+lane+32j, j<4, kept in registers) x a tile of 32 hypotheses
-//   staged in shared memory. Inliers are rare, so per hypothesis a thread only tests 4 residuals and -- under one
-//   branch -- accumulates its own (count, value, shared) triple, which it parks in shared memory [hyp][thread].
-//   After every 8 hypotheses the block folds those columns.
+// Shape of the kernel
+//   block = 256 threads = 8 warps x 128 points (lane owns base + lane + 32 j, j < 4) x a tile of 32 hypotheses.
+//   1. Screening (hot loop, float32, pxb_screen.cuh): every (point, hypothesis) pair is tested for "certainly not an
+//      inlier" in normalised coordinates -- ~16 FP32 instructions instead of ~28 FP64 ones. Pairs that cannot be
+//      dismissed (inliers plus a band of up to 2 thresholds around the model, plus anything numerically suspicious)
+//      are pushed into a per-warp queue in shared memory, in (hypothesis, ascending point) order.
+//   2. Exact path (cold, float64): whenever 32 candidates are queued the warp drains them with all lanes busy: one
+//      candidate per lane, the reference's exact residual (plain div.rn.f64), the inlier test r2 < T2, the MSAC terms.
+//      Lane h then adds the terms of hypothesis h of the tile SEQUENTIALLY in queue order.
 //
-// Summation topology (a function of N only -- never of K, the grid or the batch split):
-//   thread partial over its 4 points in j order -> per lane, over the 8 warps in warp order -> xor butterfly over
-//   the 32 lanes -> chunks (blocks of 1024 points) in chunk order (k_score_finalize).
+// Summation topology (a function of N only -- never of K, the batch split, the tile or the grid):
+//   inliers of a 128-point chunk in ascending point order, sequentially (exactly the reference's loop order)
+//   -> the 8 chunks of a block in order -> blocks (1024 points) in order (k_score_finalize).
+// Counts are exact integers. Skipped pairs contribute exactly nothing in the reference as well (r2 >= T2).
 #include "pxb_internal.h"
-#include "pxb_residuals.cuh"
+#include "pxb_screen.cuh"
 
 namespace pxb {
 
-constexpr int kScP = 4;                                   // points per lane
-constexpr int kScChunk = kThreads * kScP;                 // 1024 points per block
-constexpr int kScHypsPerBlock = 32; // 128 gains ~1% at K=10k but starves the grid at RANSAC batch sizes
-constexpr int kScSub = 8;                                 // hypotheses folded per reduction pass
+constexpr int kScP = 4;                   // points per lane
+constexpr int kScWarps = kThreads / 32;   // 8
+constexpr int kScChunk = kThreads * kScP; // 1024 points per block
+constexpr int kScHyps = 32;               // hypotheses per tile = lanes (lane h accumulates hypothesis h)
+constexpr int kScQueue = 256;             // circular candidate queue per warp (>= 31 + 128)
 
 struct ScorePartial {
 	double value, shared;
 	long long count;
 };
 
-template <int TYPE, bool HAS_CP, bool HI_ONLY>
-__global__ void __launch_bounds__(kThreads, 2)
-    k_score_partial(const double *__restrict__ soa, int64_t stride, int64_t N, const double *__restrict__ models,
-                    int64_t K, double T2, const double *__restrict__ compound_pref, ScorePartial *__restrict__ partials,
-                    int nchunks) {
-	constexpr int DIM = ModelTraits<TYPE>::kDim, MS = ModelTraits<TYPE>::kSize, MP = ModelTraits<TYPE>::kPadded;
-	__shared__ __align__(16) double s_models[kScHypsPerBlock * MP];
-	__shared__ double s_v[kScSub][kThreads];
-	__shared__ double s_s[HAS_CP ? kScSub : 1][kThreads];
-	__shared__ int s_c[kScSub][kThreads];
+struct ScoreAcc {
+	double v, s;
+	int c;
+};
 
-	const int64_t k0 = (int64_t)blockIdx.y * kScHypsPerBlock;
-	const int nk = (int)min((int64_t)kScHypsPerBlock, K - k0);
-	int wild = 0;
-	for (int t = threadIdx.x; t < nk * MS; t += kThreads) {
-		const double mv = models[k0 * MS + t];
-		s_models[(t / MS) * MP + (t % MS)] = mv;
-		wild |= !(fabs(mv) <= kInputMagnitudeLimit);
+// Shared-memory plan of one block (dynamic): the block's 1024 points in float64 (the exact path gathers from here),
+// optionally their compound preferences, the tile's models in float64 and in normalised float32, the per-warp
+// candidate queues and the per-warp accumulators.
+template <int TYPE, bool HAS_CP> struct ScoreSmem {
+	static constexpr int DIM = ModelTraits<TYPE>::kDim, MP = ModelTraits<TYPE>::kPadded, MF = ScreenTraits<TYPE>::kFloats;
+	static constexpr size_t kPts = 0;
+	static constexpr size_t kCp = kPts + sizeof(double) * DIM * kScChunk;
+	static constexpr size_t kModels = kCp + (HAS_CP ? sizeof(double) * kScChunk : 0);
+	static constexpr size_t kMf = kModels + sizeof(double) * kScHyps * MP;
+	static constexpr size_t kQueue = kMf + sizeof(float) * kScHyps * MF;
+	static constexpr size_t kAcc = kQueue + sizeof(unsigned short) * kScWarps * kScQueue;
+	static constexpr size_t kRes = kAcc + sizeof(ScoreAcc) * kScWarps * kScHyps; // per warp: 32 values (+32 shared) + 32 segments
+	static constexpr size_t kSeg = kRes + sizeof(double) * kScWarps * 32 * (HAS_CP ? 2 : 1);
+	static constexpr size_t kBytes = kSeg + sizeof(unsigned short) * kScWarps * 32;
+};
+
+// Drains up to 32 queued candidates of one warp: one candidate per lane, the reference's exact float64 residual, the
+// inlier test and the MSAC terms. The queue is sorted by (hypothesis, point), so the candidates of hypothesis h form
+// one contiguous segment; lane h then adds the terms of its segment SEQUENTIALLY (ascending point index). Candidates
+// that turn out not to be inliers contribute an exact +0.0.
+template <int TYPE, bool HAS_CP>
+__device__ __noinline__ ScoreAcc score_drain(const double *s_pts, const double *s_cp, const double *s_models, int pbase,
+                                             double T2, const unsigned short *queue, int head, int n, double *res_v,
+                                             double *res_s, unsigned short *seg, ScoreAcc acc) {
+	constexpr int DIM = ModelTraits<TYPE>::kDim, MP = ModelTraits<TYPE>::kPadded;
+	const int lane = threadIdx.x & 31;
+	int qh = 255;
+	bool inl = false;
+	double sv = 0.0, sh = 0.0;
+	if (lane < n) {
+		const unsigned e = queue[(head + lane) & (kScQueue - 1)];
+		qh = (int)(e >> 7);
+		const int idx = pbase + (int)(e & 127u);
+		double p[5];
+#pragma unroll
+		for (int c = 0; c < DIM; ++c) p[c] = s_pts[c * kScChunk + idx];
+		const double *m = s_models + qh * MP;
+		bool ok = true;
+		double r2 = squared_residual_fast<TYPE>(p, m, ok); // bit-identical to the plain division inside its domain
+		if (!ok) r2 = squared_residual<TYPE>(p, m);
+		inl = r2 < T2; // scoring_function_with_compound_model.h:85
+		if (inl) {
+			sv = cv_max(0.0, sub(1.0, divd(r2, T2)));   // :96-99
+			if (HAS_CP) sh = cv_min(s_cp[idx], sv);     // :115-117 (pref is 0 off the inlier set)
+		}
 	}
+	const unsigned inliers = __ballot_sync(0xffffffffu, inl);
+	if (inliers == 0) return acc;
+	// segment of every hypothesis present in this batch: written by the first lane of the segment, read by lane h
+	const int prev = __shfl_up_sync(0xffffffffu, qh, 1);
+	const bool first = lane < n && (lane == 0 || prev != qh);
+	const unsigned firsts = __ballot_sync(0xffffffffu, first);
+	seg[lane] = 0;
+	res_v[lane] = sv;
+	if (HAS_CP) res_s[lane] = sh;
+	__syncwarp();
+	if (first) {
+		const unsigned later = firsts & ~((2u << lane) - 1u);
+		const int end = later ? (__ffs(later) - 1) : n;
+		seg[qh] = (unsigned short)(lane | ((end - lane) << 8));
+	}
+	__syncwarp();
+	const int start = seg[lane] & 255, len = seg[lane] >> 8;
+	const int maxlen = __reduce_max_sync(0xffffffffu, len);
+	acc.c += __popc(inliers & (len >= 32 ? 0xffffffffu : (((1u << len) - 1u) << start)));
+#pragma unroll 4
+	for (int k = 0; k < maxlen; ++k) {
+		const int i = (start + k) & 31;
+		const double v = res_v[i];
+		const double s2 = HAS_CP ? res_s[i] : 0.0;
+		if (k < len) {
+			acc.v = add(acc.v, v);
+			if (HAS_CP) acc.s = add(acc.s, s2);
+		}
+	}
+	__syncwarp();
+	return acc;
+}
 
+// The hypothesis loop of one warp: screening, queueing, draining.
+template <int TYPE, bool HAS_CP, bool FULL>
+__device__ __forceinline__ ScoreAcc score_tile(const float (&p)[kScP][5], const float (&zq)[kScP], const bool (&valid)[kScP],
+                                               const float *s_mf, int nk, float cT, const double *s_pts, const double *s_cp,
+                                               const double *s_models, int pbase, double T2, unsigned short *queue,
+                                               double *res_v, double *res_s, unsigned short *seg) {
+	constexpr int MF = ScreenTraits<TYPE>::kFloats, M2 = ScreenTraits<TYPE>::kM2;
+	const int lane = threadIdx.x & 31;
+	const unsigned lt = (1u << lane) - 1u;
+	int head = 0, tail = 0;
+	ScoreAcc acc = {0.0, 0.0, 0};
+#pragma unroll 2
+	for (int h = 0; h < nk; ++h) {
+		float m[MF];
+		const float4 *s4 = reinterpret_cast<const float4 *>(s_mf + h * MF);
+#pragma unroll
+		for (int i = 0; i < MF / 4; ++i) {
+			const float4 v = s4[i];
+			m[4 * i] = v.x, m[4 * i + 1] = v.y, m[4 * i + 2] = v.z, m[4 * i + 3] = v.w;
+		}
+		bool cand[kScP];
+		bool any = false;
+#pragma unroll
+		for (int j = 0; j < kScP; ++j) {
+			const bool sure = screen_sure_outlier<TYPE>(p[j], m, cT, m[M2] * zq[j]);
+			cand[j] = FULL ? !sure : (!sure & valid[j]);
+			any |= cand[j];
+		}
+		if (__any_sync(0xffffffffu, any)) {
+#pragma unroll
+			for (int j = 0; j < kScP; ++j) {
+				const unsigned b = __ballot_sync(0xffffffffu, cand[j]);
+				if (cand[j]) queue[(tail + __popc(b & lt)) & (kScQueue - 1)] = (unsigned short)((h << 7) | (32 * j + lane));
+				tail += __popc(b);
+			}
+			__syncwarp();
+			while (tail - head >= 32) {
+				acc = score_drain<TYPE, HAS_CP>(s_pts, s_cp, s_models, pbase, T2, queue, head, 32, res_v, res_s, seg, acc);
+				head += 32;
+			}
+		}
+	}
+	if (tail > head)
+		acc = score_drain<TYPE, HAS_CP>(s_pts, s_cp, s_models, pbase, T2, queue, head, tail - head, res_v, res_s, seg, acc);
+	return acc;
+}
+
+template <int TYPE, bool HAS_CP>
+__global__ void __launch_bounds__(kThreads, 3)
+    k_score_screened(const double *__restrict__ soa, int64_t stride, int64_t N, const float *__restrict__ pf,
+                     const float *__restrict__ pq, const NormDev *__restrict__ norm, const double *__restrict__ models,
+                     int64_t K, double T2, const double *__restrict__ compound_pref, ScorePartial *__restrict__ partials,
+                     int nchunks) {
+	using L = ScoreSmem<TYPE, HAS_CP>;
+	constexpr int DIM = L::DIM, MS = ModelTraits<TYPE>::kSize, MP = L::MP, MF = L::MF;
+	extern __shared__ __align__(16) unsigned char smem[];
+	double *s_pts = reinterpret_cast<double *>(smem + L::kPts);
+	double *s_cp = reinterpret_cast<double *>(smem + L::kCp);
+	double *s_models = reinterpret_cast<double *>(smem + L::kModels);
+	float *s_mf = reinterpret_cast<float *>(smem + L::kMf);
+	unsigned short *s_queue = reinterpret_cast<unsigned short *>(smem + L::kQueue);
+	ScoreAcc *s_acc = reinterpret_cast<ScoreAcc *>(smem + L::kAcc);
+	double *s_res = reinterpret_cast<double *>(smem + L::kRes);
+	unsigned short *s_seg = reinterpret_cast<unsigned short *>(smem + L::kSeg);
+
+	const int64_t k0 = (int64_t)blockIdx.y * kScHyps;
+	const int nk = (int)min((int64_t)kScHyps, K - k0);
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int chunk = blockIdx.x;
-	const int64_t base = (int64_t)chunk * kScChunk + warp * (32 * kScP);
-	double p[kScP][5], cp[kScP];
+	const int64_t block_base = (int64_t)chunk * kScChunk;
+	const NormDev nd = *norm;
+	for (int t = threadIdx.x; t < nk * MS; t += kThreads) s_models[(t / MS) * MP + (t % MS)] = models[k0 * MS + t];
+	if (threadIdx.x < nk) screen_model<TYPE>(models + (k0 + threadIdx.x) * MS, nd, s_mf + threadIdx.x * MF);
+	for (int t = threadIdx.x; t < kScChunk; t += kThreads) { // stride is a multiple of 64 >= N: rows never overrun
+		const int64_t i = min(block_base + t, stride - 1);
+#pragma unroll
+		for (int c = 0; c < DIM; ++c) s_pts[c * kScChunk + t] = __ldg(soa + c * stride + i);
+		if (HAS_CP) s_cp[t] = (block_base + t < N) ? __ldg(compound_pref + block_base + t) : 0.0;
+	}
+	const ScreenConsts sc = screen_consts<TYPE>(T2, nd);
+
+	const int64_t warp_base = block_base + warp * (32 * kScP);
+	float p[kScP][5], zq[kScP];
 	bool valid[kScP];
 #pragma unroll
 	for (int j = 0; j < kScP; ++j) {
-		const int64_t i = base + lane + 32 * j;
+		const int64_t i = warp_base + lane + 32 * j;
 		valid[j] = i < N;
-		load_point<DIM>(soa, stride, valid[j] ? i : (N - 1), p[j]);
-		cp[j] = (HAS_CP && valid[j]) ? __ldg(compound_pref + i) : 0.0;
+		const int64_t ii = valid[j] ? i : (N - 1);
 #pragma unroll
-		for (int c = 0; c < DIM; ++c) wild |= !(fabs(p[j][c]) <= kInputMagnitudeLimit);
+		for (int c = 0; c < DIM; ++c) p[j][c] = __ldg(pf + c * stride + ii);
+		zq[j] = sc.cE * __ldg(pq + ii); // error allowance of this point, to be scaled by M2 of the hypothesis
 	}
-	wild = __syncthreads_or(wild); // also orders the s_models writes
-	const unsigned hiT = (unsigned)__double2hiint(T2);
-	// r2 / T2 divides by a launch constant: one Newton reciprocal per thread, then the 3-instruction quotient of
-	// ptxas' own fast path (bit-identical inside its domain: 2^-300 <= r2, T2 within 2^+-200 -- checked by the host;
-	// anything else takes the plain division)
-	const bool fastT = fabs(T2) >= 6.2e-61 && fabs(T2) <= 1.6e60;
-	const double rT = rcp_newton(fastT ? T2 : 1.0);
+	__syncthreads();
 
-	for (int ks = 0; ks < nk; ks += kScSub) {
-		const int nsub = min(kScSub, nk - ks);
-#pragma unroll 2
-		for (int h = 0; h < nsub; ++h) {
-			double m[12];
-			load_model_smem<TYPE>(s_models + (ks + h) * MP, m);
-			double r[kScP];
-			float lo[kScP];
+	// interior warps (all 128 points exist) run the loop without validity predicates; the branch is warp-uniform
+	ScoreAcc acc;
+	double *res_v = s_res + warp * 32 * (HAS_CP ? 2 : 1), *res_s = res_v + (HAS_CP ? 32 : 0);
+	if (warp_base + 32 * kScP <= N)
+		acc = score_tile<TYPE, HAS_CP, true>(p, zq, valid, s_mf, nk, sc.cT, s_pts, s_cp, s_models, warp * (32 * kScP), T2,
+		                                     s_queue + warp * kScQueue, res_v, res_s, s_seg + warp * 32);
+	else
+		acc = score_tile<TYPE, HAS_CP, false>(p, zq, valid, s_mf, nk, sc.cT, s_pts, s_cp, s_models, warp * (32 * kScP), T2,
+		                                      s_queue + warp * kScQueue, res_v, res_s, s_seg + warp * 32);
+	s_acc[warp * kScHyps + lane] = acc;
+	__syncthreads();
+	if (threadIdx.x < nk) { // the 8 chunks of the block, in order
+		ScorePartial out = {0.0, 0.0, 0};
 #pragma unroll
-			for (int j = 0; j < kScP; ++j) r[j] = squared_residual_tile<TYPE>(p[j], m, lo[j]);
-			if (__builtin_expect(!(tile_min4(lo) >= __int_as_float(kHiMinPattern)) || wild, 0))
-				PXB_RESIDUAL_TILE_EXACT(TYPE, kScP, p, m, r);
-			int c = 0;
-			double v = 0.0, s = 0.0;
-			bool any = false;
-#pragma unroll
-			for (int j = 0; j < kScP; ++j) any |= valid[j] && below_threshold<HI_ONLY>(r[j], T2, hiT);
-			if (any) { // scoring_function_with_compound_model.h:85-102, points in j order
-#pragma unroll
-				for (int j = 0; j < kScP; ++j) {
-					if (valid[j] && below_threshold<HI_ONLY>(r[j], T2, hiT)) {
-						++c;
-						const double q = (fastT && __double2hiint(r[j]) >= kHiMinPattern) ? fast_quotient_nocheck(r[j], T2, rT)
-						                                                                   : divd(r[j], T2);
-						const double sv = cv_max(0.0, sub(1.0, q));
-						v = add(v, sv);
-						if (HAS_CP) s = add(s, cv_min(cp[j], sv)); // :115-117 (pref is 0 off the inlier set)
-					}
-				}
-			}
-			s_v[h][threadIdx.x] = v;
-			if (HAS_CP) s_s[h][threadIdx.x] = s;
-			s_c[h][threadIdx.x] = c;
+		for (int w = 0; w < kScWarps; ++w) {
+			const ScoreAcc a = s_acc[w * kScHyps + threadIdx.x];
+			out.value = add(out.value, a.v);
+			out.shared = add(out.shared, a.s);
+			out.count += a.c;
 		}
-		__syncthreads();
-		// fold: warp w owns hypothesis ks + w of this pass
-		if (warp < nsub) {
-			double v = 0.0, s = 0.0;
-			int c = 0;
-#pragma unroll
-			for (int w = 0; w < kThreads / 32; ++w) {
-				v = add(v, s_v[warp][w * 32 + lane]);
-				if (HAS_CP) s = add(s, s_s[warp][w * 32 + lane]);
-				c += s_c[warp][w * 32 + lane];
-			}
-#pragma unroll
-			for (int o = 16; o > 0; o >>= 1) {
-				v = add(v, __shfl_xor_sync(0xffffffffu, v, o));
-				if (HAS_CP) s = add(s, __shfl_xor_sync(0xffffffffu, s, o));
-				c += __shfl_xor_sync(0xffffffffu, c, o);
-			}
-			if (lane == 0) {
-				ScorePartial out;
-				out.value = v;
-				out.shared = s;
-				out.count = c;
-				partials[(k0 + ks + warp) * nchunks + chunk] = out;
-			}
-		}
-		__syncthreads();
+		partials[(k0 + threadIdx.x) * nchunks + chunk] = out;
 	}
 }
 
@@ -154,15 +258,15 @@ template <int TYPE>
 static void launch_partial(pxb_ctx *ctx, dim3 grid, const double *m, int64_t kk, double T2, const double *cp,
                            ScorePartial *pp, int nchunks) {
 	const Points &p = ctx->pts;
-	const bool hi = threshold_low_word_is_zero(T2);
-	if (cp && hi)
-		k_score_partial<TYPE, true, true><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, m, kk, T2, cp, pp, nchunks);
-	else if (cp)
-		k_score_partial<TYPE, true, false><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, m, kk, T2, cp, pp, nchunks);
-	else if (hi)
-		k_score_partial<TYPE, false, true><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, m, kk, T2, cp, pp, nchunks);
+	// opt in to > 48 KB of dynamic shared memory (per device and function; a host-side attribute write, ~1 us)
+	if (cp)
+		cudaFuncSetAttribute(k_score_screened<TYPE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ScoreSmem<TYPE, true>::kBytes);
 	else
-		k_score_partial<TYPE, false, false><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, m, kk, T2, cp, pp, nchunks);
+		cudaFuncSetAttribute(k_score_screened<TYPE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ScoreSmem<TYPE, false>::kBytes);
+	if (cp)
+		k_score_screened<TYPE, true><<<grid, kThreads, ScoreSmem<TYPE, true>::kBytes, ctx->stream>>>(p.soa, p.stride, p.N, p.f32n, p.q, p.norm, m, kk, T2, cp, pp, nchunks);
+	else
+		k_score_screened<TYPE, false><<<grid, kThreads, ScoreSmem<TYPE, false>::kBytes, ctx->stream>>>(p.soa, p.stride, p.N, p.f32n, p.q, p.norm, m, kk, T2, cp, pp, nchunks);
 }
 
 int launch_score_compound(pxb_ctx *ctx, const double *models, int64_t K, double T2, const double *compound_pref,
@@ -175,8 +279,8 @@ int launch_score_compound(pxb_ctx *ctx, const double *models, int64_t K, double 
 	const int ms = model_size(p.type);
 	int64_t done = 0;
 	while (done < K) { // gridDim.y is limited to 65535
-		const int64_t kk = std::min<int64_t>(K - done, (int64_t)65535 * kScHypsPerBlock);
-		dim3 grid((unsigned)nchunks, (unsigned)((kk + kScHypsPerBlock - 1) / kScHypsPerBlock));
+		const int64_t kk = std::min<int64_t>(K - done, (int64_t)65535 * kScHyps);
+		dim3 grid((unsigned)nchunks, (unsigned)((kk + kScHyps - 1) / kScHyps));
 		const double *m = models + done * ms;
 		ScorePartial *pp = part + done * nchunks;
 		switch (p.type) {
