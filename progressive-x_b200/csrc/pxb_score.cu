@@ -124,7 +124,7 @@ __device__ __forceinline__ ScoreAcc score_tile(const float (&p)[kScP][5], const 
                                                const float *s_mf, int nk, float cT, const double *s_pts, const double *s_cp,
                                                const double *s_models, int pbase, double T2, unsigned short *queue,
                                                double *res_v, double *res_s, unsigned short *seg) {
-	constexpr int MF = ScreenTraits<TYPE>::kFloats, M2 = ScreenTraits<TYPE>::kM2;
+	constexpr int MF = ScreenTraits<TYPE>::kFloats;
 	const int lane = threadIdx.x & 31;
 	const unsigned lt = (1u << lane) - 1u;
 	int head = 0, tail = 0;
@@ -142,7 +142,7 @@ __device__ __forceinline__ ScoreAcc score_tile(const float (&p)[kScP][5], const 
 		bool any = false;
 #pragma unroll
 		for (int j = 0; j < kScP; ++j) {
-			const bool sure = screen_sure_outlier<TYPE>(p[j], m, cT, m[M2] * zq[j]);
+			const bool sure = screen_sure_outlier<TYPE>(p[j], m, cT, zq[j]);
 			cand[j] = FULL ? !sure : (!sure & valid[j]);
 			any |= cand[j];
 		}
@@ -150,6 +150,7 @@ __device__ __forceinline__ ScoreAcc score_tile(const float (&p)[kScP][5], const 
 #pragma unroll
 			for (int j = 0; j < kScP; ++j) {
 				const unsigned b = __ballot_sync(0xffffffffu, cand[j]);
+				if (b == 0) continue; // warp-uniform
 				if (cand[j]) queue[(tail + __popc(b & lt)) & (kScQueue - 1)] = (unsigned short)((h << 7) | (32 * j + lane));
 				tail += __popc(b);
 			}
@@ -165,12 +166,34 @@ __device__ __forceinline__ ScoreAcc score_tile(const float (&p)[kScP][5], const 
 	return acc;
 }
 
-template <int TYPE, bool HAS_CP>
+// Per launch, before the score kernel: the normalised float32 copy of every hypothesis (kFloats each) and the two
+// launch constants of the test. One thread per hypothesis; keeps all float64 conjugation out of the hot kernel.
+template <int TYPE>
+__global__ void k_screen_prepare(const double *__restrict__ models, int64_t K, double T2, const NormDev *__restrict__ norm,
+                                 float *__restrict__ consts, float *__restrict__ mf) {
+	constexpr int MS = ModelTraits<TYPE>::kSize, MF = ScreenTraits<TYPE>::kFloats;
+	const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const NormDev nd = *norm;
+	if (k == 0) {
+		const ScreenConsts sc = screen_consts<TYPE>(T2, nd);
+		consts[0] = sc.cT;
+		consts[1] = sc.cE;
+	}
+	if (k >= K) return;
+	float out[MF];
+#pragma unroll
+	for (int i = 0; i < MF; ++i) out[i] = 0.0f;
+	screen_model<TYPE>(models + k * MS, nd, out);
+#pragma unroll
+	for (int i = 0; i < MF; ++i) mf[k * MF + i] = out[i];
+}
+
+template <int TYPE, bool HAS_CP, int PASSES>
 __global__ void __launch_bounds__(kThreads, 3)
     k_score_screened(const double *__restrict__ soa, int64_t stride, int64_t N, const float *__restrict__ pf,
-                     const float *__restrict__ pq, const NormDev *__restrict__ norm, const double *__restrict__ models,
-                     int64_t K, double T2, const double *__restrict__ compound_pref, ScorePartial *__restrict__ partials,
-                     int nchunks) {
+                     const float *__restrict__ pq, const float *__restrict__ consts, const float *__restrict__ mfg,
+                     const double *__restrict__ models, int64_t K, double T2, const double *__restrict__ compound_pref,
+                     ScorePartial *__restrict__ partials, int nchunks) {
 	using L = ScoreSmem<TYPE, HAS_CP>;
 	constexpr int DIM = L::DIM, MS = ModelTraits<TYPE>::kSize, MP = L::MP, MF = L::MF;
 	extern __shared__ __align__(16) unsigned char smem[];
@@ -183,22 +206,16 @@ __global__ void __launch_bounds__(kThreads, 3)
 	double *s_res = reinterpret_cast<double *>(smem + L::kRes);
 	unsigned short *s_seg = reinterpret_cast<unsigned short *>(smem + L::kSeg);
 
-	const int64_t k0 = (int64_t)blockIdx.y * kScHyps;
-	const int nk = (int)min((int64_t)kScHyps, K - k0);
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int chunk = blockIdx.x;
 	const int64_t block_base = (int64_t)chunk * kScChunk;
-	const NormDev nd = *norm;
-	for (int t = threadIdx.x; t < nk * MS; t += kThreads) s_models[(t / MS) * MP + (t % MS)] = models[k0 * MS + t];
-	if (threadIdx.x < nk) screen_model<TYPE>(models + (k0 + threadIdx.x) * MS, nd, s_mf + threadIdx.x * MF);
 	for (int t = threadIdx.x; t < kScChunk; t += kThreads) { // stride is a multiple of 64 >= N: rows never overrun
 		const int64_t i = min(block_base + t, stride - 1);
 #pragma unroll
 		for (int c = 0; c < DIM; ++c) s_pts[c * kScChunk + t] = __ldg(soa + c * stride + i);
 		if (HAS_CP) s_cp[t] = (block_base + t < N) ? __ldg(compound_pref + block_base + t) : 0.0;
 	}
-	const ScreenConsts sc = screen_consts<TYPE>(T2, nd);
-
+	const float cT = __ldg(consts), cE = __ldg(consts + 1);
 	const int64_t warp_base = block_base + warp * (32 * kScP);
 	float p[kScP][5], zq[kScP];
 	bool valid[kScP];
@@ -209,31 +226,38 @@ __global__ void __launch_bounds__(kThreads, 3)
 		const int64_t ii = valid[j] ? i : (N - 1);
 #pragma unroll
 		for (int c = 0; c < DIM; ++c) p[j][c] = __ldg(pf + c * stride + ii);
-		zq[j] = sc.cE * __ldg(pq + ii); // error allowance of this point, to be scaled by M2 of the hypothesis
+		zq[j] = cE * __ldg(pq + ii); // error allowance of this point
 	}
-	__syncthreads();
-
-	// interior warps (all 128 points exist) run the loop without validity predicates; the branch is warp-uniform
-	ScoreAcc acc;
 	double *res_v = s_res + warp * 32 * (HAS_CP ? 2 : 1), *res_s = res_v + (HAS_CP ? 32 : 0);
-	if (warp_base + 32 * kScP <= N)
-		acc = score_tile<TYPE, HAS_CP, true>(p, zq, valid, s_mf, nk, sc.cT, s_pts, s_cp, s_models, warp * (32 * kScP), T2,
-		                                     s_queue + warp * kScQueue, res_v, res_s, s_seg + warp * 32);
-	else
-		acc = score_tile<TYPE, HAS_CP, false>(p, zq, valid, s_mf, nk, sc.cT, s_pts, s_cp, s_models, warp * (32 * kScP), T2,
-		                                      s_queue + warp * kScQueue, res_v, res_s, s_seg + warp * 32);
-	s_acc[warp * kScHyps + lane] = acc;
-	__syncthreads();
-	if (threadIdx.x < nk) { // the 8 chunks of the block, in order
-		ScorePartial out = {0.0, 0.0, 0};
+	const bool full = warp_base + 32 * kScP <= N; // interior warps run without validity predicates (warp-uniform)
+
+	for (int pass = 0; pass < PASSES; ++pass) {
+		const int64_t k0 = ((int64_t)blockIdx.y * PASSES + pass) * kScHyps;
+		if (k0 >= K) break; // block-uniform
+		const int nk = (int)min((int64_t)kScHyps, K - k0);
+		for (int t = threadIdx.x; t < nk * MS; t += kThreads) s_models[(t / MS) * MP + (t % MS)] = models[k0 * MS + t];
+		for (int t = threadIdx.x; t < nk * MF; t += kThreads) s_mf[t] = __ldg(mfg + k0 * MF + t);
+		__syncthreads();
+		ScoreAcc acc;
+		if (full)
+			acc = score_tile<TYPE, HAS_CP, true>(p, zq, valid, s_mf, nk, cT, s_pts, s_cp, s_models, warp * (32 * kScP), T2,
+			                                     s_queue + warp * kScQueue, res_v, res_s, s_seg + warp * 32);
+		else
+			acc = score_tile<TYPE, HAS_CP, false>(p, zq, valid, s_mf, nk, cT, s_pts, s_cp, s_models, warp * (32 * kScP), T2,
+			                                      s_queue + warp * kScQueue, res_v, res_s, s_seg + warp * 32);
+		s_acc[warp * kScHyps + lane] = acc;
+		__syncthreads();
+		if (threadIdx.x < nk) { // the 8 chunks of the block, in order
+			ScorePartial out = {0.0, 0.0, 0};
 #pragma unroll
-		for (int w = 0; w < kScWarps; ++w) {
-			const ScoreAcc a = s_acc[w * kScHyps + threadIdx.x];
-			out.value = add(out.value, a.v);
-			out.shared = add(out.shared, a.s);
-			out.count += a.c;
+			for (int w = 0; w < kScWarps; ++w) {
+				const ScoreAcc a = s_acc[w * kScHyps + threadIdx.x];
+				out.value = add(out.value, a.v);
+				out.shared = add(out.shared, a.s);
+				out.count += a.c;
+			}
+			partials[(k0 + threadIdx.x) * nchunks + chunk] = out;
 		}
-		partials[(k0 + threadIdx.x) * nchunks + chunk] = out;
 	}
 }
 
@@ -254,19 +278,38 @@ __global__ void k_score_finalize(const ScorePartial *__restrict__ partials, int6
 	shared[k] = s;
 }
 
-template <int TYPE>
-static void launch_partial(pxb_ctx *ctx, dim3 grid, const double *m, int64_t kk, double T2, const double *cp,
-                           ScorePartial *pp, int nchunks) {
+template <int TYPE, bool HAS_CP, int PASSES>
+static void launch_screened(pxb_ctx *ctx, int nchunks, const float *consts, const float *mf, const double *m, int64_t kk,
+                            double T2, const double *cp, ScorePartial *pp) {
 	const Points &p = ctx->pts;
+	constexpr int kBytes = (int)ScoreSmem<TYPE, HAS_CP>::kBytes;
 	// opt in to > 48 KB of dynamic shared memory (per device and function; a host-side attribute write, ~1 us)
-	if (cp)
-		cudaFuncSetAttribute(k_score_screened<TYPE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ScoreSmem<TYPE, true>::kBytes);
-	else
-		cudaFuncSetAttribute(k_score_screened<TYPE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ScoreSmem<TYPE, false>::kBytes);
-	if (cp)
-		k_score_screened<TYPE, true><<<grid, kThreads, ScoreSmem<TYPE, true>::kBytes, ctx->stream>>>(p.soa, p.stride, p.N, p.f32n, p.q, p.norm, m, kk, T2, cp, pp, nchunks);
-	else
-		k_score_screened<TYPE, false><<<grid, kThreads, ScoreSmem<TYPE, false>::kBytes, ctx->stream>>>(p.soa, p.stride, p.N, p.f32n, p.q, p.norm, m, kk, T2, cp, pp, nchunks);
+	cudaFuncSetAttribute(k_score_screened<TYPE, HAS_CP, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBytes);
+	const int64_t tile = (int64_t)kScHyps * PASSES;
+	dim3 grid((unsigned)nchunks, (unsigned)((kk + tile - 1) / tile));
+	k_score_screened<TYPE, HAS_CP, PASSES><<<grid, kThreads, kBytes, ctx->stream>>>(p.soa, p.stride, p.N, p.f32n, p.q, consts, mf, m,
+	                                                                             kk, T2, cp, pp, nchunks);
+}
+
+template <int TYPE>
+static int launch_partial(pxb_ctx *ctx, int nchunks, const double *m, int64_t kk, double T2, const double *cp, ScorePartial *pp) {
+	constexpr int MF = ScreenTraits<TYPE>::kFloats;
+	PXB_TRY(ctx->screen.reserve(sizeof(float) * (4 + (size_t)kk * MF)));
+	float *consts = ctx->screen.as<float>(), *mf = consts + 4;
+	k_screen_prepare<TYPE><<<(unsigned)((kk + 127) / 128), 128, 0, ctx->stream>>>(m, kk, T2, ctx->pts.norm, consts, mf);
+	ctx->launches++;
+	// big batches walk 4 tiles of 32 hypotheses per block (the per-block prologue -- staging 1024 points -- is paid once);
+	// RANSAC-sized batches keep one tile per block so that the grid still fills the GPU
+	const bool big = kk * nchunks >= (int64_t)4 * 32 * 3 * ctx->sm_count * 2;
+	if (cp) {
+		if (big) launch_screened<TYPE, true, 4>(ctx, nchunks, consts, mf, m, kk, T2, cp, pp);
+		else launch_screened<TYPE, true, 1>(ctx, nchunks, consts, mf, m, kk, T2, cp, pp);
+	} else {
+		if (big) launch_screened<TYPE, false, 4>(ctx, nchunks, consts, mf, m, kk, T2, cp, pp);
+		else launch_screened<TYPE, false, 1>(ctx, nchunks, consts, mf, m, kk, T2, cp, pp);
+	}
+	ctx->launches++;
+	return PXB_OK;
 }
 
 int launch_score_compound(pxb_ctx *ctx, const double *models, int64_t K, double T2, const double *compound_pref,
@@ -280,15 +323,13 @@ int launch_score_compound(pxb_ctx *ctx, const double *models, int64_t K, double 
 	int64_t done = 0;
 	while (done < K) { // gridDim.y is limited to 65535
 		const int64_t kk = std::min<int64_t>(K - done, (int64_t)65535 * kScHyps);
-		dim3 grid((unsigned)nchunks, (unsigned)((kk + kScHyps - 1) / kScHyps));
 		const double *m = models + done * ms;
 		ScorePartial *pp = part + done * nchunks;
 		switch (p.type) {
-		case PXB_MODEL_HOMOGRAPHY: launch_partial<PXB_MODEL_HOMOGRAPHY>(ctx, grid, m, kk, T2, compound_pref, pp, nchunks); break;
-		case PXB_MODEL_FUNDAMENTAL: launch_partial<PXB_MODEL_FUNDAMENTAL>(ctx, grid, m, kk, T2, compound_pref, pp, nchunks); break;
-		default: launch_partial<PXB_MODEL_PNP>(ctx, grid, m, kk, T2, compound_pref, pp, nchunks); break;
+		case PXB_MODEL_HOMOGRAPHY: PXB_TRY(launch_partial<PXB_MODEL_HOMOGRAPHY>(ctx, nchunks, m, kk, T2, compound_pref, pp)); break;
+		case PXB_MODEL_FUNDAMENTAL: PXB_TRY(launch_partial<PXB_MODEL_FUNDAMENTAL>(ctx, nchunks, m, kk, T2, compound_pref, pp)); break;
+		default: PXB_TRY(launch_partial<PXB_MODEL_PNP>(ctx, nchunks, m, kk, T2, compound_pref, pp)); break;
 		}
-		ctx->launches++;
 		done += kk;
 	}
 	k_score_finalize<<<(unsigned)((K + 127) / 128), 128, 0, ctx->stream>>>(part, K, nchunks, count, value_sum, shared);

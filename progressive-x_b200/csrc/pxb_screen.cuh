@@ -24,14 +24,17 @@
 // (or |X|+|Y|+|Z|+1), P2 = |x2|+|y2|+1 (or |u|+|v|+1) in normalised coordinates, a standard forward analysis of the
 // FFMA chains (inputs rounded once, <= 4 operations deep, FFMA keeps products unrounded) gives
 //   |t_k,f - t_k| <= 5.1 u M P1,   |a_f - a|, |b_f - b|, |r_f - r| <= 7.1 u M P1 P2.
-// The code uses E = 2^-19 M P1 P2 (32 u: a 4x margin) for every one of them. Then, with (p + q)^2 <= 2 p^2 + 2 q^2:
-//   H/PnP  a_f^2 + b_f^2 >= 2 T t3_f^2 + 2 (sqrt2 + sqrtT)^2 E^2           ==>  a^2 + b^2 >= T t3^2
-//   F      r_f^2 >= 4 T den_f + (16 T + 2) E^2                             ==>  r^2 >= T den
-// i.e. everything farther than sqrt2 (resp. 2) thresholds from the model is dismissed in float32, everything closer
-// goes to the exact path. Constants are rounded UP when converted to float32 and carry a further (1 + 2^-6) factor
+// The code uses E = 2^-19 M P1 P2 (32 u: a 4x margin; M^2 <= 4 after the rescaling below) for every one of them.
+// Then, with the triangle inequality and (p + q)^2 <= (1 + eta) p^2 + (1 + 1/eta) q^2, eta = 1/16:
+//   H/PnP  |(a,b)| >= |(a_f,b_f)| - sqrt2 E,  |t3| <= |t3_f| + E:
+//          a_f^2 + b_f^2 >= (1+eta) T t3_f^2 + (1+1/eta) (sqrt2 + sqrtT)^2 E^2      ==>  a^2 + b^2 >= T t3^2
+//   F      |r| >= |r_f| - E,  sqrt(den) <= sqrt(den_f) (1 + 4u) + 2 E:
+//          r_f^2 >= (1+eta) T den_f + (1+1/eta) (2 sqrtT + 1)^2 E^2                 ==>  r^2 >= T den
+// i.e. everything farther than ~1.03 thresholds from the model is dismissed in float32, everything closer goes to
+// the exact path. Constants are rounded UP when converted to float32 and carry a further (1 + 2^-6) factor
 // that covers the roundings of the test itself. Overflow/underflow are excluded by construction: normalised
-// coordinates are <= 2^10 in magnitude and 2^-20 <= M <= 2^20, else the point / hypothesis is flagged "wild"
-// (bound = +inf) and takes the exact path. NaN anywhere makes the comparison false -> exact path.
+// coordinates are <= 2^10 in magnitude and the model is rescaled to 1 <= M < 2 (the tests are homogeneous in the
+// model), else the point / hypothesis is flagged "wild" (bound = +inf or NaN model) and takes the exact path. NaN anywhere makes the comparison false -> exact path.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -50,9 +53,9 @@ constexpr float kScreenU2 = 1.0f / 274877906944.0f; // (2^-19)^2 = 2^-38
 constexpr double kScreenSlack = 1.0 + 1.0 / 64.0;
 
 template <int TYPE> struct ScreenTraits;
-template <> struct ScreenTraits<PXB_MODEL_HOMOGRAPHY> { static constexpr int kFloats = 12, kM2 = 9; };
-template <> struct ScreenTraits<PXB_MODEL_FUNDAMENTAL> { static constexpr int kFloats = 12, kM2 = 9; };
-template <> struct ScreenTraits<PXB_MODEL_PNP> { static constexpr int kFloats = 16, kM2 = 12; };
+template <> struct ScreenTraits<PXB_MODEL_HOMOGRAPHY> { static constexpr int kFloats = 12; };
+template <> struct ScreenTraits<PXB_MODEL_FUNDAMENTAL> { static constexpr int kFloats = 12; };
+template <> struct ScreenTraits<PXB_MODEL_PNP> { static constexpr int kFloats = 12; };
 
 // Normalised float32 coordinates of one point + its error-scale constant q = ((P1 P2)^2)(1 + 2^-6); +inf marks a
 // point that must always take the exact path (non-finite or out-of-range coordinates).
@@ -82,20 +85,24 @@ __device__ __forceinline__ void screen_point(const double *p, const NormDev &nd,
 	for (int c = 0; c < DIM; ++c) pf[c] = wild ? 0.0f : a[c];
 }
 
-// Conjugates one model into normalised coordinates (float64), rounds it to float32 and returns M2 = M^2 (1 + 2^-6)
-// rounded up, or +inf for a hypothesis that must take the exact path.
+// Conjugates one model into normalised coordinates (float64), rescales it to M in [1, 2) and rounds it to float32.
 template <int TYPE> __device__ __forceinline__ void screen_model(const double *m, const NormDev &nd, float *mf);
 
-__device__ __forceinline__ void screen_model_finish(const double *out, const double *mag, int n, float *mf, int m2_slot) {
+// All three tests are homogeneous in the model (both sides scale with its square), so the normalised model is
+// rescaled by an exact power of two to M in [1, 2): the error allowance then uses the constant M^2 <= 4 and no
+// hypothesis is out of range unless it is zero or non-finite (those get NaN entries: every comparison is false and
+// every point of that hypothesis takes the exact path).
+__device__ __forceinline__ void screen_model_finish(const double *out, const double *mag, int n, float *mf, int) {
 	double M = 0.0;
 	bool wild = false;
 	for (int i = 0; i < n; ++i) {
 		wild |= !(fabs(out[i]) <= 1e300) || !(mag[i] <= 1e300);
 		M = fmax(M, mag[i]);
 	}
-	wild |= !(M >= 9.5367431640625e-07 && M <= 1048576.0); // 2^-20 .. 2^20
-	for (int i = 0; i < n; ++i) mf[i] = wild ? 0.0f : (float)out[i];
-	mf[m2_slot] = wild ? __int_as_float(0x7f800000) : __double2float_ru(M * M * kScreenSlack);
+	wild |= !(M >= 1e-300);
+	int e = 0;
+	frexp(wild ? 1.0 : M, &e); // M = f 2^e, f in [0.5, 1)
+	for (int i = 0; i < n; ++i) mf[i] = wild ? __int_as_float(0x7fc00000) : (float)ldexp(out[i], 1 - e);
 }
 
 template <> __device__ __forceinline__ void screen_model<PXB_MODEL_HOMOGRAPHY>(const double *m, const NormDev &nd, float *mf) {
@@ -159,7 +166,7 @@ template <> __device__ __forceinline__ void screen_model<PXB_MODEL_PNP>(const do
 }
 
 // Launch constants of the test in normalised units (float32, rounded up): cT multiplies the threshold side,
-// cE multiplies M2 * q.
+// cE multiplies q and already contains M^2 <= 4.
 struct ScreenConsts {
 	float cT, cE;
 };
@@ -170,19 +177,18 @@ template <int TYPE> __device__ __forceinline__ ScreenConsts screen_consts(double
 		k.cT = k.cE = __int_as_float(0x7f800000);
 		return k;
 	}
-	if (TYPE == PXB_MODEL_FUNDAMENTAL) {
-		k.cT = __double2float_ru(4.0 * Tn * kScreenSlack);
-		k.cE = __double2float_ru((16.0 * Tn + 2.0) * (double)kScreenU2 * kScreenSlack);
-	} else {
-		const double w = 1.4142135623730951 + sqrt(Tn);
-		k.cT = __double2float_ru(2.0 * Tn * kScreenSlack);
-		k.cE = __double2float_ru(2.0 * w * w * (double)kScreenU2 * kScreenSlack * 1.0000001);
-	}
+	// (p + q)^2 <= (1 + eta) p^2 + (1 + 1/eta) q^2 with eta = 1/16: the threshold side is inflated by 6 %, the (tiny)
+	// error allowance by 17x
+	constexpr double eta = 1.0 / 16.0;
+	const double rT = sqrt(Tn);
+	const double w = (TYPE == PXB_MODEL_FUNDAMENTAL) ? (2.0 * rT + 1.0) : (1.4142135623730951 + rT);
+	k.cT = __double2float_ru((1.0 + eta) * Tn * kScreenSlack);
+	k.cE = __double2float_ru(4.0 * (1.0 + 1.0 / eta) * w * w * (double)kScreenU2 * kScreenSlack * kScreenSlack);
 	return k;
 }
 
 // true => the point is certainly not an inlier. p: normalised float32 coordinates, m: normalised float32 model,
-// Z = cE * M2 * q (per point x hypothesis error allowance), cT as above.
+// Z = cE * q (per point error allowance), cT as above.
 template <int TYPE> __device__ __forceinline__ bool screen_sure_outlier(const float *p, const float *m, float cT, float Z);
 
 template <> __device__ __forceinline__ bool screen_sure_outlier<PXB_MODEL_HOMOGRAPHY>(const float *p, const float *m, float cT, float Z) {

@@ -293,3 +293,81 @@ def test_full_size_properties(ctx, oracle):
     perm = np.random.default_rng(1).permutation(models.shape[0])
     cnt_p, val_p, _ = ctx.score_compound(models[perm], T2)
     assert np.array_equal(cnt_p, cnt[perm]) and bits_equal(val_p, val[perm])
+
+
+# ---- float32 screening of the fused score kernel (pxb_screen.cuh): it may only ever dismiss certain outliers ----------
+def _assert_score_equals_oracle(ctx, oracle, t, pts, models, T2, cp=None):
+    ctx.upload_points(t, pts)
+    cnt, val, sh = ctx.score_compound(models, T2, cp)
+    cnt_o, val_o, sh_o = oracle.score_batch(t, pts, models, T2, cp)
+    assert np.array_equal(cnt, cnt_o)
+    np.testing.assert_allclose(val, val_o, rtol=SUM_RTOL, atol=1e-13)
+    np.testing.assert_allclose(sh, sh_o, rtol=SUM_RTOL, atol=1e-13)
+    return cnt
+
+
+@pytest.mark.parametrize("t", [H, F, PNP])
+def test_score_screening_model_scale_and_garbage(ctx, oracle, t):
+    """The inlier tests are homogeneous in the model, the screening rescales it: hypotheses multiplied by 1e+-150,
+    zero / NaN / inf hypotheses and random garbage must give the oracle's counts."""
+    pts, gt, planted, thr = scene(t, 5000, seed=40 + t)
+    models = hypotheses(oracle, t, pts, gt, planted, 60, seed=4)
+    rng = np.random.default_rng(7)
+    ms = models.shape[1]
+    extra = [models[:20] * 1e150, models[:20] * 1e-150, models[:20] * -3.0, rng.normal(size=(20, ms)),
+             rng.normal(size=(20, ms)) * np.exp(rng.normal(size=(20, ms)) * 8), np.zeros((1, ms)),
+             np.full((1, ms), np.nan), np.full((1, ms), np.inf)]
+    bad = models[:3].copy()
+    bad[0, -3:] = 0.0  # H: t3 == 0 everywhere; F/PnP: a zero last row
+    bad[1, 0] = np.nan
+    bad[2, -1] = np.inf
+    allm = np.concatenate([models] + extra + [bad])
+    T2 = (1.5 * thr) ** 2
+    cnt = _assert_score_equals_oracle(ctx, oracle, t, pts, allm, T2)
+    assert cnt[:len(models)].max() > 100  # the planted structures are found
+
+
+@pytest.mark.parametrize("t", [H, F, PNP])
+def test_score_screening_wild_points_and_offsets(ctx, oracle, t):
+    """Points far from the origin (normalisation must absorb a 1e7 offset), a few non-finite / astronomically large
+    points (they must take the exact path), and a set whose bounding box is degenerate."""
+    pts, gt, planted, thr = scene(t, 3000, seed=50 + t)
+    models = hypotheses(oracle, t, pts, gt, planted, 40, seed=5)
+    T2 = (1.5 * thr) ** 2
+    wild = pts.copy()
+    wild[5, 0] = np.nan
+    wild[6, 1] = np.inf
+    wild[7, :] = 1e200
+    wild[8, 2] = -1e30
+    wild[9, :] = 0.0
+    _assert_score_equals_oracle(ctx, oracle, t, wild, models, T2)
+    if t != PNP:
+        # translate both images by 1e7 px: H' = T2 H T1^-1, F' = T2^-T F T1^-1 keep the geometry; the counts of the
+        # translated problem are whatever the oracle says they are (float64 loses digits too) -- parity is the bar
+        off = pts + 1.0e7
+        _assert_score_equals_oracle(ctx, oracle, t, off, models, T2)
+    same = np.repeat(pts[:1], 700, axis=0)  # zero-extent bounding box
+    _assert_score_equals_oracle(ctx, oracle, t, same, models, T2)
+
+
+@pytest.mark.parametrize("T2", [0.0, -1.0, 1e-30, 1e-9, 1e9, 1e300, float("inf"), float("nan")])
+def test_score_screening_threshold_extremes(ctx, oracle, T2):
+    pts, gt, planted, thr = scene(H, 2000, seed=61)
+    models = hypotheses(oracle, H, pts, gt, planted, 30, seed=6)
+    _assert_score_equals_oracle(ctx, oracle, H, pts, models, T2)
+
+
+@pytest.mark.parametrize("t", [H, F, PNP])
+def test_score_screening_near_threshold_band(ctx, oracle, t):
+    """Points placed a hair inside / outside the threshold of a model (relative 1e-9 .. 1e-3): float32 cannot tell them
+    apart, so they must reach the exact path and be classified exactly like the oracle does."""
+    pts, gt, planted, thr = scene(t, 4000, seed=70 + t)
+    T2 = (1.5 * thr) ** 2
+    r2, _ = oracle.residual_matrix(t, pts, planted[:1], T2)
+    r2 = r2[0]
+    # thresholds chosen as residuals of actual points, nudged by tiny relative amounts
+    order = np.argsort(r2)
+    picks = r2[order[[50, 400, 900, 1500]]]
+    for base in picks:
+        for eps in (0.0, 1e-15, -1e-15, 1e-9, -1e-9, 1e-4, -1e-4):
+            _assert_score_equals_oracle(ctx, oracle, t, pts, planted[:3], float(base * (1.0 + eps)))
