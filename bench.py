@@ -46,6 +46,11 @@ def workload(seed=0, n_points=N_POINTS, k_hyps=K_HYPS):
     return pts, gt, samples
 
 
+def workload_name(n, k):
+    return (f"synthetic multi-H grid: N={n} correspondences (5 planes x 12% + 40% outliers) x K={k} four-point "
+            f"hypotheses per GPU, thr={THRESHOLD}px; exact f64 r2 + inlier bit")
+
+
 def measured_peak():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -76,28 +81,46 @@ class ClockSampler:
         self.index, self.rows, self.proc = index, [], None
         self.nvml_rows, self._stop, self._thr = [], False, None
 
-    def _poll_nvml(self):
-        # In-process NVML polling every ~2 ms: the timed region is tens of milliseconds, far shorter than the
-        # 200 ms period of `nvidia-smi -lms`, so the subprocess alone would miss it.
+    def _init_nvml(self):
+        # NVML is initialised synchronously, BEFORE the timed region: importing pynvml inside the polling thread can take
+        # longer than the whole timed region (tens of milliseconds), which left the N > 1 runs without samples.
         try:
             import pynvml as nv
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            self._nv = nv
+            self._h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self._mx = nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM)
+        except Exception:
+            self._nv = None
+
+    def _sample_nvml(self):
+        nv, h = self._nv, self._h
+        sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        try:
+            reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        self.nvml_rows.append((sm, self._mx, reasons))
+
+    def _poll_nvml(self):
+        # in-process NVML polling every ~2 ms: the timed region is tens of milliseconds, far shorter than the 200 ms
+        # period of `nvidia-smi -lms`, so the subprocess alone would miss it.
+        try:
             while not self._stop:
-                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
-                try:
-                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
-                except Exception:
-                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                self.nvml_rows.append((sm, mx, reasons))
+                self._sample_nvml()
                 time.sleep(0.002)
         except Exception:
             pass
 
     def start(self):
-        self._thr = threading.Thread(target=self._poll_nvml, daemon=True)
-        self._thr.start()
+        self._init_nvml()
+        if self._nv is not None:
+            try:
+                self._sample_nvml()  # at least one sample, taken right at the start of the timed region
+            except Exception:
+                pass
+            self._thr = threading.Thread(target=self._poll_nvml, daemon=True)
+            self._thr.start()
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
@@ -206,8 +229,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"synthetic multi-H grid N={N_POINTS} x K={K_HYPS} (bounded sample per step)",
-                   "threshold": THRESHOLD},
+        "config": {"workload": workload_name(N_POINTS, K_HYPS),
+                   "sample": "bounded sample of that workload per step (see cpu_baseline.sample)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -321,8 +344,9 @@ def main():
     sc_ms, _, _, _ = timed(step_score, max(3, args.steps // 2), 3)
     sc_steps = max(3, args.steps // 2)
     extras = {"score_kernel": {"evals_per_s": evals_per_step * world * sc_steps / (sc_ms * 1e-3),
-                               "note": "k_score_partial+finalize: count / sum score / shared support, no matrix written "
-                                       "(FP64-pipe bound)"}}
+                               "note": "k_screen_prepare + k_score_screened + k_score_finalize: count / sum score / shared "
+                                       "support, no matrix written; float32 screening proves outliers, exact float64 only "
+                                       "for queued candidates (issue bound)"}}
     del r2
     with torch.cuda.stream(stream):
         r2f = torch.empty((K, N), dtype=torch.float32, device=dev)
@@ -414,8 +438,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"synthetic multi-H grid: N={N} correspondences (5 planes x 12% + 40% outliers) x "
-                                   f"K={K} four-point hypotheses per GPU, thr={THRESHOLD}px; exact f64 r2 + inlier bit",
+            "config": {"workload": workload_name(N, K),
                        "cache": "4.06 GB written per step with streaming stores: output far exceeds the 126 MB L2; "
                                 "inputs (2.3 MB) are meant to stay in L2",
                        "sharding": "points replicated, disjoint hypothesis block per GPU, no data-path collective"},

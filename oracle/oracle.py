@@ -18,11 +18,11 @@ HERE = Path(__file__).resolve().parent
 ORACLE_LIB = HERE / "libpxoracle.so"
 GCO_REF_LIB = HERE / "_ref" / "libgco_ref.so"
 
-MODEL_H, MODEL_F, MODEL_PNP = 0, 1, 2
-DIM = {0: 4, 1: 4, 2: 5}
-MSIZE = {0: 9, 1: 9, 2: 12}
-SSIZE = {0: 4, 1: 7, 2: 3}
-MAXSOL = {0: 1, 1: 3, 2: 4}
+MODEL_H, MODEL_F, MODEL_PNP, MODEL_VP, MODEL_LINE = 0, 1, 2, 3, 4
+DIM = {0: 4, 1: 4, 2: 5, 3: 4, 4: 2}
+MSIZE = {0: 9, 1: 9, 2: 12, 3: 3, 4: 3}
+SSIZE = {0: 4, 1: 7, 2: 3, 3: 2, 4: 2}
+MAXSOL = {0: 1, 1: 3, 2: 4, 3: 1, 4: 1}
 
 
 def build(ref: bool = True) -> None:
@@ -71,6 +71,10 @@ def lib() -> C.CDLL:
         L.pxo_lo_unary_terms.restype = None
         L.pxo_tukey_weights.argtypes = [C.c_int, vp, vp, i64, vp, f64, vp]
         L.pxo_tukey_weights.restype = None
+        L.pxo_vp2_solve.argtypes = [vp, vp, vp]
+        L.pxo_line2_solve.argtypes = [vp, vp, vp]
+        L.pxo_fit_vp_nonminimal.argtypes = [vp, vp, i64, vp, vp]
+        L.pxo_fit_line_nonminimal.argtypes = [vp, vp, i64, vp]
         L.pxo_greedy_ufl.restype = f64
         L.pxo_greedy_ufl.argtypes = [vp, i64, C.c_int32, f64, vp, vp]
         _lib = L
@@ -128,6 +132,8 @@ def refb() -> C.CDLL:
         B.pxr_h4_is_valid_sample.argtypes = [vp, i64, vp]
         B.pxr_h_is_valid_model.argtypes = [vp]
         B.pxr_f_orientation_valid.argtypes = [vp, vp, i64, vp, C.c_int]
+        B.pxr_vp2_solve.argtypes = [vp, i64, vp, vp]
+        B.pxr_line2_solve.argtypes = [vp, i64, vp, vp]
         _refb = B
     return _refb
 
@@ -174,6 +180,16 @@ def ref_h4(pts, sample):
     sv = B.pxr_h4_is_valid_sample(_p(pts), pts.shape[0], _p(s))
     mv = B.pxr_h_is_valid_model(_p(H)) if ok else 0
     return H, int(ok), int(sv), int(mv)
+
+
+def ref_minimal_vp_or_line(t, pts, sample):
+    """The reference's own two-segment vanishing-point solver / two-point line solver (verbatim bodies)."""
+    pts = _f(pts)
+    s = np.ascontiguousarray(sample, dtype=np.int64)
+    out = np.zeros(3)
+    fn = refb().pxr_vp2_solve if t == MODEL_VP else refb().pxr_line2_solve
+    ok = fn(_p(pts), pts.shape[0], _p(s), _p(out))
+    return out, int(ok)
 
 
 def ref_f_orientation_valid(F, pts, sample):
@@ -265,9 +281,14 @@ def solve_minimal(t, pts, samples):
         elif t == MODEL_F:
             n[k] = L.pxo_f7_solve(_p(pts), _p(row), _p(buf), 1)
             models[k].reshape(-1)[: n[k] * 9] = buf[: n[k] * 9]
-        else:
+        elif t == MODEL_PNP:
             n[k] = L.pxo_p3p_solve(_p(pts), _p(row), _p(buf))
             models[k].reshape(-1)[: n[k] * 12] = buf[: n[k] * 12]
+        else:
+            n[k] = (L.pxo_vp2_solve if t == MODEL_VP else L.pxo_line2_solve)(_p(pts), _p(row), _p(buf))
+            models[k, 0] = buf[:3]
+            if not np.isfinite(buf[:3]).all():  # the reference pushes the model whatever it contains
+                pass
     return models, n, sv, mv
 
 
@@ -315,6 +336,21 @@ def fit_h_nonminimal(pts, idx, weights_by_row=None):
     L.pxo_fit_h_nonminimal.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     ok = L.pxo_fit_h_nonminimal(_p(pts), _p(idx), idx.shape[0], _p(w), _p(H))
     return H, bool(ok)
+
+
+def fit_nonminimal(t, pts, idx, weights=None):
+    """Non-minimal fit of one problem for the VP (weights indexed by point) and 2D-line families."""
+    pts = _f(pts)
+    idx = np.ascontiguousarray(idx, dtype=np.int64)
+    out = np.zeros(3)
+    if t == MODEL_VP:
+        w = None if weights is None else _f(weights)
+        ok = lib().pxo_fit_vp_nonminimal(_p(pts), _p(idx), idx.size, _p(w) if w is not None else None, _p(out))
+    elif t == MODEL_LINE:
+        ok = lib().pxo_fit_line_nonminimal(_p(pts), _p(idx), idx.size, _p(out))
+    else:
+        raise ValueError("fit_nonminimal: VP and LINE only (H has fit_h_nonminimal)")
+    return out, bool(ok)
 
 
 def greedy_ufl(D, label_cost, init_labels=None):

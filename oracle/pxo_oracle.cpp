@@ -58,10 +58,33 @@ inline double residual_pnp(const double *s, const double *p) {
 	return du * du + dv * dv;
 }
 
+// px/include/vanishing_point_estimator.h:127-189: distance of the segment's start point from the line through the
+// segment's midpoint and the vanishing point; squaredResidual = residual * residual (:135-137)
+inline double residual_vp(const double *s, const double *d) {
+	const double xs = s[0], ys = s[1], xe = s[2], ye = s[3];
+	double lx, ly, lz, mx = (xs + xe) / 2.0, my = (ys + ye) / 2.0;
+	lx = my * d[2] - d[1];
+	ly = -(mx * d[2] - d[0]);
+	lz = mx * d[1] - my * d[0];
+	const double dist = std::fabs(lx * xs + ly * ys + lz) / std::sqrt(lx * lx + ly * ly);
+	return dist * dist;
+}
+
+// gcr/estimators/linear_model_estimator.h:121-131 with _DimensionNumber = 2: (x nx + y ny + c)^2, accumulated from 0
+inline double residual_line(const double *s, const double *d) {
+	double residual = 0;
+	residual += s[0] * d[0];
+	residual += s[1] * d[1];
+	residual += d[2];
+	return residual * residual;
+}
+
 inline double residual(int type, const double *s, const double *m) {
 	switch (type) {
 	case PXO_MODEL_H: return residual_h(s, m);
 	case PXO_MODEL_F: return residual_f(s, m);
+	case PXO_MODEL_VP: return residual_vp(s, m);
+	case PXO_MODEL_LINE: return residual_line(s, m);
 	default: return residual_pnp(s, m);
 	}
 }
@@ -104,9 +127,16 @@ template <class F> double eigen_redux_sum(int64_t n, F f) {
 
 extern "C" {
 
-int pxo_point_dim(int t) { return t == PXO_MODEL_PNP ? 5 : 4; }
-int pxo_model_size(int t) { return t == PXO_MODEL_PNP ? 12 : 9; }
-int pxo_sample_size(int t) { return t == PXO_MODEL_H ? 4 : (t == PXO_MODEL_F ? 7 : 3); }
+int pxo_point_dim(int t) { return t == PXO_MODEL_PNP ? 5 : (t == PXO_MODEL_LINE ? 2 : 4); }
+int pxo_model_size(int t) { return t == PXO_MODEL_PNP ? 12 : (t >= PXO_MODEL_VP ? 3 : 9); }
+int pxo_sample_size(int t) {
+	switch (t) {
+	case PXO_MODEL_H: return 4;
+	case PXO_MODEL_F: return 7;
+	case PXO_MODEL_PNP: return 3;
+	default: return 2;
+	}
+}
 
 double pxo_squared_residual(int type, const double *point, const double *model) {
 	return residual(type, point, model);
@@ -963,6 +993,153 @@ double pxo_greedy_ufl(const double *D, int64_t N, int32_t L1, double label_cost,
 	}
 	for (int64_t i = 0; i < N; ++i) labels_out[i] = init_labels ? init_labels[i] : 0;
 	return estart;
+}
+
+// ---- vanishing points and 2D lines -------------------------------------------------------------------
+
+// VanishingPointTwoLineSolver::estimateModel, minimal branch (px/include/solver_vanishing_point_two_lines.h:146-186):
+// intersection of the two segments' lines, normalised to unit length.
+int pxo_vp2_solve(const double *pts, const int64_t *sample, double *v) {
+	const double *a = pts + 4 * sample[0], *b = pts + 4 * sample[1];
+	const double xs0 = a[0], ys0 = a[1], xe0 = a[2], ye0 = a[3], xs1 = b[0], ys1 = b[1], xe1 = b[2], ye1 = b[3];
+	double l0[3], l1[3];
+	// vec_cross(a1,b1,c1, a2,b2,c2): a3 = b1*c2 - c1*b2; b3 = -(a1*c2 - c1*a2); c3 = a1*b2 - b1*a2   (:100-114)
+	l0[0] = ys0 * 1 - 1 * ye0; l0[1] = -(xs0 * 1 - 1 * xe0); l0[2] = xs0 * ye0 - ys0 * xe0;
+	l1[0] = ys1 * 1 - 1 * ye1; l1[1] = -(xs1 * 1 - 1 * xe1); l1[2] = xs1 * ye1 - ys1 * xe1;
+	v[0] = l0[1] * l1[2] - l0[2] * l1[1];
+	v[1] = -(l0[0] * l1[2] - l0[2] * l1[0]);
+	v[2] = l0[0] * l1[1] - l0[1] * l1[0];
+	const double len = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); // vec_norm (:116-125)
+	v[0] /= len; v[1] /= len; v[2] /= len;
+	return 1;
+}
+
+// LinearModelSolver<2>::estimate2DLine (gcr/estimators/solver_linear_model.h:143-171), INCLUDING its typo
+// `nx = y1 - x2` (a correct normal would be y1 - y2): the reference's minimal line hypotheses are what they are.
+int pxo_line2_solve(const double *pts, const int64_t *sample, double *l) {
+	const double *a = pts + 2 * sample[0], *b = pts + 2 * sample[1];
+	const double x1 = a[0], y1 = a[1], x2 = b[0];
+	double nx = y1 - x2, ny = x2 - x1;
+	const double magnitude = std::sqrt(nx * nx + ny * ny);
+	nx /= magnitude;
+	ny /= magnitude;
+	l[0] = nx; l[1] = ny; l[2] = -nx * x1 - ny * y1;
+	return 1;
+}
+
+// Cyclic Jacobi on a symmetric 3x3 (stands in for Eigen::SelfAdjointEigenSolver<Matrix3d>, which is not on disk):
+// eigenvalues in w, eigenvectors in the columns of V.
+static void jacobi_eig3(double A[3][3], double V[3][3], double w[3]) {
+	for (int i = 0; i < 3; ++i)
+		for (int j = 0; j < 3; ++j) V[i][j] = i == j;
+	for (int sweep = 0; sweep < 60; ++sweep) {
+		const double off = std::fabs(A[0][1]) + std::fabs(A[0][2]) + std::fabs(A[1][2]);
+		if (off == 0.0) break;
+		for (int p = 0; p < 2; ++p)
+			for (int q = p + 1; q < 3; ++q) {
+				if (A[p][q] == 0.0) continue;
+				const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+				const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+				const double c = 1.0 / std::sqrt(t * t + 1.0), sn = t * c;
+				for (int k = 0; k < 3; ++k) { // A <- A J
+					const double akp = A[k][p], akq = A[k][q];
+					A[k][p] = c * akp - sn * akq;
+					A[k][q] = sn * akp + c * akq;
+				}
+				for (int k = 0; k < 3; ++k) { // A <- J^T A
+					const double apk = A[p][k], aqk = A[q][k];
+					A[p][k] = c * apk - sn * aqk;
+					A[q][k] = sn * apk + c * aqk;
+				}
+				for (int k = 0; k < 3; ++k) {
+					const double vkp = V[k][p], vkq = V[k][q];
+					V[k][p] = c * vkp - sn * vkq;
+					V[k][q] = sn * vkp + c * vkq;
+				}
+			}
+	}
+	for (int i = 0; i < 3; ++i) w[i] = A[i][i];
+}
+
+// VanishingPointTwoLineSolver::estimateModel, non-minimal branch (solver_vanishing_point_two_lines.h:187-233): rows
+// [y0 - my, mx - x0, x0 my - y0 mx] * weight, eigenvector of A^T A with the smallest eigenvalue, normalised. The
+// weights are indexed BY POINT when a sample is given (weights_[sample_[i]], :203). The sign of an eigenvector is
+// implementation defined in Eigen; here the largest-magnitude component is made positive ("parity unpinned" beyond
+// tolerance and sign -- the residual is sign invariant).
+int pxo_fit_vp_nonminimal(const double *pts, const int64_t *idx, int64_t n, const double *weights_by_point, double *v) {
+	if (n < 2) return 0;
+	double M[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+	for (int64_t i = 0; i < n; ++i) {
+		const double *p = pts + 4 * idx[i];
+		const double w = weights_by_point ? weights_by_point[idx[i]] : 1.0;
+		const double x0 = p[0], y0 = p[1], x1 = p[2], y1 = p[3];
+		const double mx = (x0 + x1) / 2.0, my = (y0 + y1) / 2.0, mz = 1.0;
+		const double r[3] = {(y0 * mz - my) * w, (mx - x0 * mz) * w, (x0 * my - y0 * mx) * w};
+		for (int a = 0; a < 3; ++a)
+			for (int b = 0; b < 3; ++b) M[a][b] += r[a] * r[b];
+	}
+	double V[3][3], w3[3];
+	jacobi_eig3(M, V, w3);
+	int k = 0;
+	for (int i = 1; i < 3; ++i)
+		if (w3[i] < w3[k]) k = i;
+	double e[3] = {V[0][k], V[1][k], V[2][k]};
+	const double len = std::sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+	int big = 0;
+	for (int i = 1; i < 3; ++i)
+		if (std::fabs(e[i]) > std::fabs(e[big])) big = i;
+	const double sgn = e[big] < 0 ? -1.0 : 1.0;
+	for (int i = 0; i < 3; ++i) v[i] = sgn * e[i] / len;
+	return 1;
+}
+
+// LinearModelEstimator<..., 2>::estimateModelNonminimal (gcr/estimators/linear_model_estimator.h:152-186) =
+// normalizePoints (:189-250: subtract the mass point, scale so that the mean distance is sqrt 2) +
+// LinearModelSolver<2>::estimateModel non-minimal branch (solver_linear_model.h:198-239: C^T C, 2x2,
+// FullPivHouseholderQR, last column of Q, normalised) + w = -mass . n. Weights are not used by this solver.
+// Eigen's FullPivHouseholderQR of a 2x2 restated: pivot = entry of largest magnitude (first maximum in column-major
+// scan order), one Householder reflection, Q = P_rows H.
+int pxo_fit_line_nonminimal(const double *pts, const int64_t *idx, int64_t n, double *l) {
+	if (n < 2) return 0;
+	double mx = 0, my = 0;
+	for (int64_t i = 0; i < n; ++i) { mx += pts[2 * idx[i]]; my += pts[2 * idx[i] + 1]; }
+	mx /= (double)n; my /= (double)n;
+	double avg = 0;
+	for (int64_t i = 0; i < n; ++i) {
+		const double dx = pts[2 * idx[i]] - mx, dy = pts[2 * idx[i] + 1] - my;
+		avg += std::sqrt(dx * dx + dy * dy);
+	}
+	avg /= (double)n;
+	const double ratio = std::sqrt(2.0) / avg;
+	double a = 0, b = 0, c = 0; // C^T C = [[a, b], [b, c]]
+	for (int64_t i = 0; i < n; ++i) {
+		const double dx = (pts[2 * idx[i]] - mx) * ratio, dy = (pts[2 * idx[i] + 1] - my) * ratio;
+		a += dx * dx; b += dx * dy; c += dy * dy;
+	}
+	double Mx[2][2] = {{a, b}, {b, c}};
+	int pr = 0, pc = 0;
+	double best = std::fabs(Mx[0][0]);
+	for (int col = 0; col < 2; ++col)
+		for (int row = 0; row < 2; ++row)
+			if (std::fabs(Mx[row][col]) > best) { best = std::fabs(Mx[row][col]); pr = row; pc = col; }
+	if (best == 0.0 || !(best <= 1e300)) return 0;
+	// after the row swap (0 <-> pr) and column swap (0 <-> pc) the first column is x = (x0, x1)
+	const double x0 = Mx[pr][pc], x1 = Mx[1 - pr][pc];
+	double q[2]; // last column of H = I - tau v v^T, v = (1, ess)
+	if (x1 == 0.0) {
+		q[0] = 0.0; q[1] = 1.0;
+	} else {
+		double beta = std::sqrt(x0 * x0 + x1 * x1);
+		if (x0 >= 0) beta = -beta;
+		const double ess = x1 / (x0 - beta), tau = (beta - x0) / beta;
+		q[0] = -tau * ess;
+		q[1] = 1.0 - tau * ess * ess;
+	}
+	if (pr == 1) std::swap(q[0], q[1]); // Q = P_rows H: undo the row transposition
+	const double len = std::sqrt(q[0] * q[0] + q[1] * q[1]);
+	l[0] = q[0] / len; l[1] = q[1] / len;
+	l[2] = -mx * l[0] - my * l[1];
+	return 1;
 }
 
 } // extern "C"

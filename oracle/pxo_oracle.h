@@ -32,11 +32,11 @@
 extern "C" {
 #endif
 
-enum { PXO_MODEL_H = 0, PXO_MODEL_F = 1, PXO_MODEL_PNP = 2 };
+enum { PXO_MODEL_H = 0, PXO_MODEL_F = 1, PXO_MODEL_PNP = 2, PXO_MODEL_VP = 3, PXO_MODEL_LINE = 4 };
 
-int pxo_point_dim(int model_type);   /* 4, 4, 5 */
-int pxo_model_size(int model_type);  /* 9, 9, 12 */
-int pxo_sample_size(int model_type); /* 4, 7, 3 */
+int pxo_point_dim(int model_type);   /* 4, 4, 5, 4, 2 */
+int pxo_model_size(int model_type);  /* 9, 9, 12, 3, 3 */
+int pxo_sample_size(int model_type); /* 4, 7, 3, 2, 2 */
 
 /* a1/a2/a3: squared residual of one point w.r.t. one model. */
 double pxo_squared_residual(int model_type, const double *point, const double *model);
@@ -110,6 +110,17 @@ void pxo_tukey_weights(int model_type, const double *pts, const int64_t *inliers
  * solver_homography_four_point.h:192-264 (Hartley normalisation, 2n x 8 least squares by column-pivoted Householder
  * QR, denormalisation). weights_by_row may be NULL. Returns 1 on success. */
 int pxo_fit_h_nonminimal(const double *pts, const int64_t *idx, int64_t n, const double *weights_by_row, double *H);
+
+/* f-4 (next row): vanishing points (rows [xs ys xe ye] = line segments, model = homogeneous point) and 2D lines
+ * (rows [x y], model = (nx, ny, c)). Residuals: px/include/vanishing_point_estimator.h:127-189,
+ * gcr/estimators/linear_model_estimator.h:121-131 (reachable through pxo_squared_residual and every operator above).
+ * Minimal solvers: px/include/solver_vanishing_point_two_lines.h:146-186, gcr/estimators/solver_linear_model.h:143-171
+ * (with the reference's `nx = y1 - x2`). Non-minimal: solver_vanishing_point_two_lines.h:187-233 (weights indexed by
+ * point), linear_model_estimator.h:152-250 + solver_linear_model.h:198-239. */
+int pxo_vp2_solve(const double *pts, const int64_t *sample, double *v /*3*/);
+int pxo_line2_solve(const double *pts, const int64_t *sample, double *l /*3*/);
+int pxo_fit_vp_nonminimal(const double *pts, const int64_t *idx, int64_t n, const double *weights_by_point, double *v);
+int pxo_fit_line_nonminimal(const double *pts, const int64_t *idx, int64_t n, double *l);
 
 /* a10 restated (used when oracle/_ref is not available and to cross-check it):
  * GCoptimization::solveGreedy, gcr/GCoptimization.cpp:608-751, for dense data costs and one uniform

@@ -3,6 +3,8 @@
   multi_homography_scene   C2 / C4 / headline grid: planted planes + uniform outliers
   multi_motion_scene       C3: rigid motions -> fundamental matrices
   multi_pose_scene         C5: 2D-3D matches of several rigid objects (T-LESS intrinsics)
+  multi_vanishing_point_scene  line segments converging to a few vanishing points + random segments
+  multi_line_scene         2D points on a few lines + uniform outliers
   minimal_samples          hypothesis samples drawn half within-structure, half at random
   knn_graph                exact radius graph truncated to the k nearest, as directed CSR lists
 
@@ -137,6 +139,67 @@ def normalize_pnp_points(image_points, world_points, Kc):
     out[:, 1] = hom @ Kinv[1]
     out[:, 2:] = world_points
     return np.ascontiguousarray(out)
+
+
+def multi_vanishing_point_scene(N, n_vps=3, outlier_ratio=0.3, noise=0.3, w=1024, h=768, seed=0):
+    """Line segments [xs ys xe ye] whose supporting lines pass (up to `noise` px at the endpoints) through one of
+    n_vps vanishing points placed outside the image. Returns (segments [N,4], gt [N] (-1 outlier), vps [n_vps,3])."""
+    rng = np.random.default_rng(seed)
+    n_out = int(round(N * outlier_ratio))
+    per = (N - n_out) // n_vps
+    seg = np.empty((N, 4))
+    gt = np.full(N, -1, dtype=np.int64)
+    vps = np.empty((n_vps, 3))
+    pos = 0
+    for k in range(n_vps):
+        ang = rng.uniform(0, 2 * np.pi)
+        rad = rng.uniform(1.5, 4.0) * w
+        v = np.array([w / 2 + rad * np.cos(ang), h / 2 + rad * np.sin(ang)])
+        vps[k] = np.array([v[0], v[1], 1.0]) / np.linalg.norm([v[0], v[1], 1.0])
+        n_k = per if k < n_vps - 1 else (N - n_out) - per * (n_vps - 1)
+        mid = np.stack([rng.uniform(0, w, n_k), rng.uniform(0, h, n_k)], 1)
+        d = v[None, :] - mid
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        half = rng.uniform(15, 60, n_k)[:, None]
+        seg[pos:pos + n_k, :2] = mid - half * d + rng.normal(0, noise, (n_k, 2))
+        seg[pos:pos + n_k, 2:] = mid + half * d + rng.normal(0, noise, (n_k, 2))
+        gt[pos:pos + n_k] = k
+        pos += n_k
+    n_k = N - pos
+    mid = np.stack([rng.uniform(0, w, n_k), rng.uniform(0, h, n_k)], 1)
+    a = rng.uniform(0, np.pi, n_k)
+    d = np.stack([np.cos(a), np.sin(a)], 1)
+    half = rng.uniform(15, 60, n_k)[:, None]
+    seg[pos:, :2] = mid - half * d
+    seg[pos:, 2:] = mid + half * d
+    perm = rng.permutation(N)
+    return np.ascontiguousarray(seg[perm]), gt[perm], vps
+
+
+def multi_line_scene(N, n_lines=4, outlier_ratio=0.4, noise=0.5, w=1024, h=768, seed=0):
+    """2D points [x y] on n_lines lines + uniform outliers. Returns (points [N,2], gt [N], lines [n_lines,3] with
+    unit normals, n . p + c = 0)."""
+    rng = np.random.default_rng(seed)
+    n_out = int(round(N * outlier_ratio))
+    per = (N - n_out) // n_lines
+    pts = np.empty((N, 2))
+    gt = np.full(N, -1, dtype=np.int64)
+    lines = np.empty((n_lines, 3))
+    pos = 0
+    for k in range(n_lines):
+        a = rng.uniform(0, np.pi)
+        nrm = np.array([np.cos(a), np.sin(a)])
+        p0 = np.array([rng.uniform(0.3, 0.7) * w, rng.uniform(0.3, 0.7) * h])
+        lines[k] = np.array([nrm[0], nrm[1], -nrm @ p0])
+        n_k = per if k < n_lines - 1 else (N - n_out) - per * (n_lines - 1)
+        t = rng.uniform(-0.45 * w, 0.45 * w, n_k)[:, None]
+        pts[pos:pos + n_k] = p0 + t * np.array([-nrm[1], nrm[0]]) + rng.normal(0, noise, (n_k, 2))
+        gt[pos:pos + n_k] = k
+        pos += n_k
+    pts[pos:, 0] = rng.uniform(0, w, N - pos)
+    pts[pos:, 1] = rng.uniform(0, h, N - pos)
+    perm = rng.permutation(N)
+    return np.ascontiguousarray(pts[perm]), gt[perm], lines
 
 
 def minimal_samples(gt_labels, K, m, within_ratio=0.5, seed=0):

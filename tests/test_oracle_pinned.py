@@ -9,7 +9,7 @@ import pytest
 
 from pyprogressivex import synthetic as syn
 
-H, F, PNP = 0, 1, 2
+H, F, PNP, VP, LINE = 0, 1, 2, 3, 4
 
 
 @pytest.fixture(scope="module")
@@ -32,13 +32,20 @@ def scenes():
     out.append((F, pts, gt, Ms.reshape(-1, 9), 0.75))
     img, w, K, gt, Ms = syn.multi_pose_scene(3000, seed=3)
     out.append((PNP, syn.normalize_pnp_points(img, w, K), gt, Ms.reshape(-1, 12), 4.0 / 1074.0))
+    seg, gt, vps = syn.multi_vanishing_point_scene(3000, seed=4)
+    out.append((VP, seg, gt, vps, 2.0))
+    pts, gt, lines = syn.multi_line_scene(3000, seed=5)
+    out.append((LINE, pts, gt, lines, 2.0))
     return out
 
 
-@pytest.mark.parametrize("case", scenes(), ids=["H", "F", "PnP"])
+IDS = ["H", "F", "PnP", "VP", "Line"]
+
+
+@pytest.mark.parametrize("case", scenes(), ids=IDS)
 def test_residuals_bit_exact(refb, case):
     t, pts, gt, planted, thr = case
-    m = {H: 4, F: 7, PNP: 3}[t]
+    m = {H: 4, F: 7, PNP: 3, VP: 2, LINE: 2}[t]
     S = syn.minimal_samples(gt, 60, m, seed=t)
     models, n, _, _ = refb.solve_minimal(t, pts, S)
     hyps = np.concatenate([planted] + [models[k, :n[k]] for k in range(60)])
@@ -59,7 +66,7 @@ def test_degenerate_models_bit_exact(refb):
         assert np.array_equal(bits(a[~np.isnan(a)]), bits(b[~np.isnan(b)]))
 
 
-@pytest.mark.parametrize("case", scenes(), ids=["H", "F", "PnP"])
+@pytest.mark.parametrize("case", scenes(), ids=IDS)
 def test_get_score_bit_exact(refb, case):
     """MSACScoringFunctionWithCompoundModel::getScore: value, count, inlier list, early exit, int exponent"""
     t, pts, gt, planted, thr = case
@@ -78,7 +85,7 @@ def test_get_score_bit_exact(refb, case):
             assert a["count"] == b["count"] and bits(a["value"]) == bits(b["value"])
 
 
-@pytest.mark.parametrize("case", scenes(), ids=["H", "F", "PnP"])
+@pytest.mark.parametrize("case", scenes(), ids=IDS)
 def test_preference_vector_and_pearl_datacost_bit_exact(refb, case):
     t, pts, gt, planted, thr = case
     T = 9.0 / 4.0 * thr * thr
@@ -121,3 +128,22 @@ def test_f_orientation_test_matches(refb):
         assert kept == n_kept
         checked += n_all
     assert checked > 100
+
+
+@pytest.mark.parametrize("t", [VP, LINE])
+def test_vp_and_line_minimal_solvers_bit_exact(refb, t):
+    """VanishingPointTwoLineSolver (minimal branch) and LinearModelSolver<2>::estimate2DLine -- including the latter's
+    `nx = y1 - x2` -- against the reference's own bodies."""
+    if t == VP:
+        pts, gt, _ = syn.multi_vanishing_point_scene(1500, seed=8)
+    else:
+        pts, gt, _ = syn.multi_line_scene(1500, seed=8)
+    S = syn.minimal_samples(gt, 300, 2, seed=8)
+    S[0] = [5, 5]  # degenerate sample: NaN model, pushed all the same
+    models, n, _, _ = refb.solve_minimal(t, pts, S)
+    for k in range(300):
+        ref, ok = refb.ref_minimal_vp_or_line(t, pts, S[k])
+        assert ok == n[k] == 1
+        assert np.array_equal(np.isnan(ref), np.isnan(models[k, 0]))
+        fin = ~np.isnan(ref)
+        assert np.array_equal(bits(models[k, 0][fin]), bits(ref[fin]))
