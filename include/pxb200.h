@@ -46,7 +46,11 @@ typedef enum pxb_status {
 typedef enum pxb_model_type {
 	PXB_MODEL_HOMOGRAPHY = 0,  /* RobustHomographyEstimator, 4-point minimal solver */
 	PXB_MODEL_FUNDAMENTAL = 1, /* FundamentalMatrixEstimator, 7-point minimal solver */
-	PXB_MODEL_PNP = 2          /* PerspectiveNPointEstimator, P3P minimal solver */
+	PXB_MODEL_PNP = 2,         /* PerspectiveNPointEstimator, P3P minimal solver */
+	/* px/include/vanishing_point_estimator.h: rows [xs ys xe ye] are line segments, the model is a homogeneous point */
+	PXB_MODEL_VANISHING_POINT = 3,
+	/* gcr/estimators/linear_model_estimator.h (Default2DLineEstimator, gcr/types.h:146-149): rows [x y], model (nx, ny, c) */
+	PXB_MODEL_LINE2D = 4
 } pxb_model_type;
 
 const char *pxb_last_error(void);
@@ -72,8 +76,8 @@ int pxb_host_free_pinned(void *host_ptr);
 
 /* ---- data ---------------------------------------------------------------------------------------------- */
 /* Replaces the cv::Mat view the reference builds over the caller's buffer (progressivex_python.cpp:203).
- * Copies [N, dim] host doubles to the device and re-tiles them to the kernels' SoA layout. dim is 4 (H, F) or
- * 5 (PnP). */
+ * Copies [N, dim] host doubles to the device and re-tiles them to the kernels' SoA layout. dim is 4 (H, F, vanishing
+ * points), 5 (PnP) or 2 (2D lines). */
 int pxb_upload_points(pxb_ctx *ctx, int model_type, const double *pts_host, int64_t N);
 int64_t pxb_point_count(pxb_ctx *ctx);
 
@@ -126,6 +130,10 @@ int pxb_compound_max(pxb_ctx *ctx, const double *prefs_host, int64_t L, int64_t 
  *    FundamentalMatrixEstimator::estimateModel (solver_fundamental_matrix_seven_point.h:91-291,
  *    fundamental_estimator.h:161-184,737-800). Roots in ascending order.
  * PnP: P3PSolver::estimateModel (solver_p3p.h:177-385).
+ * VP: VanishingPointTwoLineSolver::estimateModel, minimal branch (px/include/solver_vanishing_point_two_lines.h:146-186).
+ * 2D line: LinearModelSolver<2>::estimate2DLine (gcr/estimators/solver_linear_model.h:152-188), including the
+ *    reference's `nx = y1 - x2`.
+ * m = 4, 7, 3, 2, 2 indices per sample; max_solutions = 1, 3, 4, 1, 1; model size 9, 9, 12, 3, 3.
  * sample_valid / model_valid may be NULL. */
 int pxb_solve_minimal(pxb_ctx *ctx, const int64_t *samples_host, int64_t K, double *models_out_host,
                       int32_t *n_models_host, uint8_t *sample_valid_host, uint8_t *model_valid_host);
@@ -180,7 +188,11 @@ int pxb_fit_homographies(pxb_ctx *ctx, int32_t P, const int32_t *off_host, const
  * F: normalised 8-point + rank-2 projection (gcr/estimators/fundamental_estimator.h:574-618 without the LM polish of
  * solver_fundamental_matrix_bundle_adjustment.h), n >= 8. PnP: normalised DLT + Levenberg-Marquardt on the reprojection
  * error (stands in for solver_pnp_bundle_adjustment.h:108-225), n >= 6, weights ignored like the reference does.
- * models_out: P * 9 (H, F) or P * 12 (PnP) doubles. */
+ * Vanishing point: smallest eigenvector of the weighted 3x3 normal matrix (px/include/solver_vanishing_point_two_lines.h:
+ * 187-233); here `weights_by_row_host` holds N entries and is read BY POINT, the reference's indexing for this solver (:203).
+ * 2D line: mass point + sqrt2 scaling + 2x2 full-pivot Householder QR (gcr/estimators/linear_model_estimator.h:152-250,
+ * solver_linear_model.h:198-239), weights unused like in the reference.
+ * models_out: P * 9 (H, F), P * 12 (PnP) or P * 3 (vanishing point, line) doubles. */
 int pxb_fit_nonminimal(pxb_ctx *ctx, int32_t P, const int32_t *off_host, const int32_t *idx_host,
                        const double *weights_by_row_host, double *models_out_host, int32_t *ok_out_host);
 
@@ -216,6 +228,24 @@ int pxb_find_6d_poses(pxb_ctx *ctx, const double *image_points, const double *wo
                       int64_t max_models_out, double spatial_coherence_weight, double threshold, double confidence,
                       double neighborhood_ball_radius, double maximum_tanimoto_similarity, size_t max_iters,
                       size_t minimum_point_number, int maximum_model_number, uint64_t seed);
+
+/* findVanishingPoints_ (px/src/progressivex_python.cpp:306-423): lines [N,4] = segments xs ys xe ye; weights (N doubles or
+ * NULL) are the per-segment weights of the least-squares fits inside PEARL (settings.point_weights, PEARL.h:373-380).
+ * Only samplers 0 and 1 exist for this entry (:353-367; any other id prints the reference's message and returns 0 --
+ * including the Python default sampler_id = 3). vanishing_points_out: max_models_out * 3 doubles. */
+int pxb_find_vanishing_points(pxb_ctx *ctx, const double *lines, const double *weights, int64_t N, int64_t *labeling_out,
+                              double *vanishing_points_out, int64_t max_models_out, size_t image_width,
+                              size_t image_height, double spatial_coherence_weight, double threshold, double confidence,
+                              double neighborhood_ball_radius, double maximum_tanimoto_similarity, size_t max_iters,
+                              size_t minimum_point_number, int maximum_model_number, size_t sampler_id,
+                              double scoring_exponent, int do_logging, uint64_t seed);
+/* findLines_ (px/src/progressivex_python.cpp:425-535): points [N,2]; the weights argument of the reference is accepted and
+ * unused there as well (:425-535 never reads it). Samplers 0, 1, 2. lines_out: max_models_out * 3 doubles (nx, ny, c). */
+int pxb_find_lines(pxb_ctx *ctx, const double *points, const double *weights, int64_t N, int64_t *labeling_out,
+                   double *lines_out, int64_t max_models_out, size_t image_width, size_t image_height,
+                   double spatial_coherence_weight, double threshold, double confidence, double neighborhood_ball_radius,
+                   double maximum_tanimoto_similarity, size_t max_iters, size_t minimum_point_number,
+                   int maximum_model_number, size_t sampler_id, double scoring_exponent, int do_logging, uint64_t seed);
 
 #ifdef __cplusplus
 }

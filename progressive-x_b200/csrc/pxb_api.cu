@@ -177,7 +177,7 @@ int pxb_host_free_pinned(void *host_ptr) {
 // ---- data ------------------------------------------------------------------------------------------------
 int pxb_upload_points(pxb_ctx *ctx, int model_type, const double *pts_host, int64_t N) {
 	PXB_CHECK_ARG(ctx != nullptr, "null context");
-	PXB_CHECK_ARG(model_type >= 0 && model_type <= 2, "unknown model type");
+	PXB_CHECK_ARG(model_type >= 0 && model_type <= PXB_MODEL_LINE2D, "unknown model type");
 	PXB_CHECK_ARG(pts_host != nullptr && N > 0, "points must be a non-empty [N, dim] array");
 	PXB_CUDA(cudaSetDevice(ctx->device));
 	Points &p = ctx->pts;

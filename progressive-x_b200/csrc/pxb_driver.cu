@@ -50,6 +50,9 @@ int launch_fit_f(pxb_ctx *ctx, int P, const int32_t *off, const int32_t *idx, co
                  int32_t *ok_out);
 int launch_fit_pnp(pxb_ctx *ctx, int P, const int32_t *off, const int32_t *idx, double *P_out, int32_t *ok_out);
 int launch_f_sym_count(pxb_ctx *ctx, const double *model, double T2, double Tsym2, long long *out2);
+int launch_fit_vp(pxb_ctx *ctx, int P, const int32_t *off, const int32_t *idx, const double *weights_by_point, double *out,
+                  int32_t *ok_out);
+int launch_fit_line(pxb_ctx *ctx, int P, const int32_t *off, const int32_t *idx, double *out, int32_t *ok_out);
 
 namespace {
 
@@ -148,6 +151,8 @@ struct Settings {
 	size_t max_proposals_without_change = 10; // progressive_x.h:63
 	int exponent = 2;                         // scoring_function_with_compound_model.h:20 (int!)
 	size_t sampler_id = 0;
+	bool napsac = false;                      // main sampler = NapsacSampler (H/F: id 3, lines: id 2)
+	std::vector<double> point_weights;        // MultiModelSettings::point_weights (progressive_x.h:36), VP only
 	bool do_logging = false;
 	uint64_t seed = 1;
 	// gcransac::utils::Settings defaults (gcr/settings.h:66-86) as overridden by progressive_x.h:64-71
@@ -217,9 +222,15 @@ class Driver {
 	int fit_nonminimal(const std::vector<std::vector<int64_t>> &sets, const double *weights_by_row,
 	                   std::vector<double> &models_out, std::vector<int32_t> &ok);
 	int lo_labeling(const double *model, std::vector<int64_t> &inliers);
-	// Estimator::nonMinimalSampleSize(): H four-point 4, F bundle-adjustment solver 7, PnP bundle adjustment 4
-	size_t non_minimal_sample_size() const { return s_.type == PXB_MODEL_FUNDAMENTAL ? 7 : 4; }
-	bool weighting_applicable() const { return s_.type != PXB_MODEL_PNP; } // Estimator::isWeightingApplicable()
+	// Estimator::nonMinimalSampleSize(): H four-point 4, F bundle-adjustment solver 7, PnP bundle adjustment 4,
+	// vanishing point / 2D line: the minimal solver doubles as the non-minimal one, 2
+	size_t non_minimal_sample_size() const {
+		return s_.type == PXB_MODEL_FUNDAMENTAL ? 7 : (s_.type >= PXB_MODEL_VANISHING_POINT ? 2 : 4);
+	}
+	// Estimator::isWeightingApplicable(); LinearModelSolver<2> accepts weights and never reads them
+	bool weighting_applicable() const { return s_.type != PXB_MODEL_PNP && s_.type != PXB_MODEL_LINE2D; }
+	// H/F solvers read weights_[row of the gathered sample]; the VP solver reads weights_[point index] (:203)
+	bool weights_by_point() const { return s_.type == PXB_MODEL_VANISHING_POINT; }
 	int model_is_valid(const double *model, size_t slot_valid, bool &valid);
 	size_t iteration_number_for(size_t inliers, double log_probability) const;
 	int propose(uint64_t round_seed, std::vector<double> &model_out, bool &found);
@@ -258,7 +269,7 @@ int Driver::fit_nonminimal(const std::vector<std::vector<int64_t>> &sets, const 
 	for (const auto &st : sets)
 		for (int64_t i : st) idx.push_back((int32_t)i);
 	size_t wcount = 0;
-	if (weights_by_row) wcount = sets[0].size(); // weighted fits are issued one problem at a time (IRLS)
+	if (weights_by_row) wcount = weights_by_point() ? (size_t)N_ : sets[0].size(); // row-indexed: one problem at a time (IRLS)
 	const size_t bytes = sizeof(int32_t) * (off.size() + idx.size()) + 64;
 	PXB_TRY(ctx_->idx.reserve(bytes));
 	int32_t *d_off = ctx_->idx.as<int32_t>(), *d_idx = d_off + off.size();
@@ -279,8 +290,14 @@ int Driver::fit_nonminimal(const std::vector<std::vector<int64_t>> &sets, const 
 	case PXB_MODEL_FUNDAMENTAL:
 		PXB_TRY(launch_fit_f(ctx_, P, d_off, d_idx, d_w, ctx_->models.as<double>(), ctx_->outA.as<int32_t>()));
 		break;
-	default: // PerspectiveNPointEstimator::isWeightingApplicable() is false: weights never reach the solver
+	case PXB_MODEL_PNP: // PerspectiveNPointEstimator::isWeightingApplicable() is false: weights never reach the solver
 		PXB_TRY(launch_fit_pnp(ctx_, P, d_off, d_idx, ctx_->models.as<double>(), ctx_->outA.as<int32_t>()));
+		break;
+	case PXB_MODEL_VANISHING_POINT:
+		PXB_TRY(launch_fit_vp(ctx_, P, d_off, d_idx, d_w, ctx_->models.as<double>(), ctx_->outA.as<int32_t>()));
+		break;
+	default:
+		PXB_TRY(launch_fit_line(ctx_, P, d_off, d_idx, ctx_->models.as<double>(), ctx_->outA.as<int32_t>()));
 		break;
 	}
 	PXB_CUDA(cudaMemcpyAsync(models_out.data(), ctx_->models.ptr, sizeof(double) * models_out.size(),
@@ -404,7 +421,8 @@ int Driver::irls(std::vector<int64_t> &inliers, std::vector<double> &model, doub
 		std::vector<std::vector<int64_t>> sets(1, inliers);
 		std::vector<double> fitted;
 		std::vector<int32_t> ok;
-		PXB_TRY(fit_nonminimal(sets, weighting_applicable() ? w_row.data() : nullptr, fitted, ok));
+		const double *w_arg = !weighting_applicable() ? nullptr : (weights_by_point() ? w_point.data() : w_row.data());
+		PXB_TRY(fit_nonminimal(sets, w_arg, fitted, ok));
 		if (!ok[0]) break;
 		std::vector<int64_t> cnt;
 		std::vector<double> val, shr;
@@ -429,7 +447,7 @@ int Driver::propose(uint64_t round_seed, std::vector<double> &model_out, bool &f
 	const double truncated_threshold = 3.0 / 2.0 * s_.threshold;
 	const double T2 = truncated_threshold * truncated_threshold; // :254-255 spelling
 	std::unique_ptr<Sampler> main_sampler;
-	if (s_.sampler_id == 3 && !graph_.idx.empty())
+	if (s_.napsac && !graph_.idx.empty())
 		main_sampler.reset(new NapsacSampler(round_seed * 2 + 1, &graph_));
 	else
 		main_sampler.reset(new UniformSampler(round_seed * 2 + 1));
@@ -635,7 +653,9 @@ int Driver::pearl() {
 				}
 			std::vector<double> fitted;
 			std::vector<int32_t> ok;
-			PXB_TRY(fit_nonminimal(sets, nullptr, fitted, ok));
+			// PEARL.h:373-380 passes settings.point_weights (only findVanishingPoints_ sets them; read by point there)
+			const double *pw = (weights_by_point() && s_.point_weights.size() == (size_t)N_) ? s_.point_weights.data() : nullptr;
+			PXB_TRY(fit_nonminimal(sets, pw, fitted, ok));
 			std::vector<double> cand = flat;
 			for (size_t t = 0; t < which.size(); ++t)
 				if (ok[t]) std::copy(fitted.begin() + t * ms_, fitted.begin() + (t + 1) * ms_, cand.begin() + which[t] * ms_);
@@ -754,6 +774,7 @@ int run_two_view(pxb_ctx *ctx, int type, const double *corr, int64_t N, int64_t 
 	s.max_iters = max_iters;
 	if (max_models > 0) s.max_models = (size_t)max_models;
 	s.sampler_id = sampler_id;
+	s.napsac = sampler_id == 3;
 	if (set_exponent) s.exponent = (int)scoring_exponent; // setExponent(const int) truncates (progressive_x.h:551)
 	s.do_logging = do_logging != 0;
 	if (seed == 0) seed = (uint64_t)std::chrono::high_resolution_clock::now().time_since_epoch().count();
@@ -766,6 +787,48 @@ int run_two_view(pxb_ctx *ctx, int type, const double *corr, int64_t N, int64_t 
 	const int64_t M = (int64_t)inst.size();
 	for (int64_t k = 0; k < std::min(M, max_models_out); ++k)
 		std::memcpy(models_out + k * ms, inst[k].model.data(), sizeof(double) * ms);
+	std::memcpy(labeling_out, drv.labeling().data(), sizeof(int64_t) * (size_t)N);
+	return (int)M;
+}
+
+// findVanishingPoints_ / findLines_ (px/src/progressivex_python.cpp:306-423, 425-535)
+int run_points_family(pxb_ctx *ctx, int type, const double *rows, const double *weights, int64_t N, int64_t *labeling_out,
+                      double *models_out, int64_t max_models_out, double lambda, double threshold, double confidence,
+                      double radius, double max_tanimoto, size_t max_iters, size_t min_points, int max_models,
+                      size_t sampler_id, size_t max_sampler_id, size_t napsac_id, double scoring_exponent, int do_logging,
+                      uint64_t seed) {
+	if (!ctx || !rows || !labeling_out || !models_out || N < 2) {
+		set_error("bad argument");
+		return PXB_ERR_ARGUMENT;
+	}
+	if (sampler_id > max_sampler_id) { // :353-367 / :463-481: unknown sampler -> message on stderr, 0 models
+		fprintf(stderr, "Unknown sampler identifier: %zu. The accepted samplers are 0 (uniform sampling), 1 (PROSAC "
+		                "sampling), 2 (P-NAPSAC sampling)\n", sampler_id);
+		return 0;
+	}
+	PXB_TRY(pxb_upload_points(ctx, type, rows, N));
+	Settings s;
+	s.type = type;
+	s.min_inliers = min_points;
+	s.threshold = threshold;
+	s.confidence = confidence;
+	s.max_tanimoto = max_tanimoto;
+	s.lambda = lambda;
+	s.max_iters = max_iters;
+	if (max_models > 0) s.max_models = (size_t)max_models;
+	s.sampler_id = sampler_id;
+	s.napsac = sampler_id == napsac_id;
+	s.exponent = (int)scoring_exponent; // setScoringExponent -> setExponent(const int)
+	s.do_logging = do_logging != 0;
+	if (weights && type == PXB_MODEL_VANISHING_POINT) s.point_weights.assign(weights, weights + N); // :381
+	if (seed == 0) seed = (uint64_t)std::chrono::high_resolution_clock::now().time_since_epoch().count();
+	s.seed = seed;
+	Driver drv(ctx, s);
+	if (lambda > 0.0 || s.napsac) PXB_TRY(drv.build_graph(radius, 8));
+	PXB_TRY(drv.run());
+	const auto &inst = drv.instances();
+	const int64_t M = (int64_t)inst.size();
+	for (int64_t k = 0; k < std::min(M, max_models_out); ++k) std::memcpy(models_out + k * 3, inst[k].model.data(), sizeof(double) * 3);
 	std::memcpy(labeling_out, drv.labeling().data(), sizeof(int64_t) * (size_t)N);
 	return (int)M;
 }
@@ -862,6 +925,31 @@ int pxb_find_6d_poses(pxb_ctx *ctx, const double *image_points, const double *wo
 	for (int64_t k = 0; k < std::min(M, max_models_out); ++k) std::memcpy(poses_out + k * 12, inst[k].model.data(), sizeof(double) * 12);
 	std::memcpy(labeling_out, drv.labeling().data(), sizeof(int64_t) * (size_t)N);
 	return (int)M;
+}
+
+int pxb_find_vanishing_points(pxb_ctx *ctx, const double *lines, const double *weights, int64_t N, int64_t *labeling_out,
+                              double *vanishing_points_out, int64_t max_models_out, size_t, size_t,
+                              double spatial_coherence_weight, double threshold, double confidence,
+                              double neighborhood_ball_radius, double maximum_tanimoto_similarity, size_t max_iters,
+                              size_t minimum_point_number, int maximum_model_number, size_t sampler_id,
+                              double scoring_exponent, int do_logging, uint64_t seed) {
+	// samplers 0 (uniform) and 1 (PROSAC, falls back to uniform here) only; no NAPSAC for this entry
+	return run_points_family(ctx, PXB_MODEL_VANISHING_POINT, lines, weights, N, labeling_out, vanishing_points_out,
+	                         max_models_out, spatial_coherence_weight, threshold, confidence, neighborhood_ball_radius,
+	                         maximum_tanimoto_similarity, max_iters, minimum_point_number, maximum_model_number, sampler_id, 1,
+	                         SIZE_MAX, scoring_exponent, do_logging, seed);
+}
+
+int pxb_find_lines(pxb_ctx *ctx, const double *points, const double *weights, int64_t N, int64_t *labeling_out,
+                   double *lines_out, int64_t max_models_out, size_t, size_t, double spatial_coherence_weight,
+                   double threshold, double confidence, double neighborhood_ball_radius,
+                   double maximum_tanimoto_similarity, size_t max_iters, size_t minimum_point_number,
+                   int maximum_model_number, size_t sampler_id, double scoring_exponent, int do_logging, uint64_t seed) {
+	// samplers 0, 1 and 2 = NapsacSampler (progressivex_python.cpp:476-478)
+	return run_points_family(ctx, PXB_MODEL_LINE2D, points, weights, N, labeling_out, lines_out, max_models_out,
+	                         spatial_coherence_weight, threshold, confidence, neighborhood_ball_radius,
+	                         maximum_tanimoto_similarity, max_iters, minimum_point_number, maximum_model_number, sampler_id, 2,
+	                         2, scoring_exponent, do_logging, seed);
 }
 
 } // extern "C"

@@ -79,6 +79,8 @@ int launch_knn_graph(pxb_ctx *ctx, double radius, int k, int32_t *nbr, int32_t *
 	const unsigned grid = (unsigned)((p.N + kKnnTile - 1) / kKnnTile);
 	if (p.dim == 4)
 		k_knn_graph<4><<<grid, kKnnTile, 0, ctx->stream>>>(p.aos, p.N, radius * radius, k, nbr, deg);
+	else if (p.dim == 2)
+		k_knn_graph<2><<<grid, kKnnTile, 0, ctx->stream>>>(p.aos, p.N, radius * radius, k, nbr, deg);
 	else
 		k_knn_graph<5><<<grid, kKnnTile, 0, ctx->stream>>>(p.aos, p.N, radius * radius, k, nbr, deg);
 	ctx->launches++;
@@ -246,6 +248,9 @@ namespace pxb {
 int launch_fit_f(pxb_ctx *ctx, int P, const int32_t *off, const int32_t *idx, const double *weights, double *F_out,
                  int32_t *ok_out);
 int launch_fit_pnp(pxb_ctx *ctx, int P, const int32_t *off, const int32_t *idx, double *P_out, int32_t *ok_out);
+int launch_fit_vp(pxb_ctx *ctx, int P, const int32_t *off, const int32_t *idx, const double *weights_by_point, double *out,
+                  int32_t *ok_out);
+int launch_fit_line(pxb_ctx *ctx, int P, const int32_t *off, const int32_t *idx, double *out, int32_t *ok_out);
 }
 
 extern "C" {
@@ -288,17 +293,22 @@ int pxb_fit_nonminimal(pxb_ctx *ctx, int32_t P, const int32_t *off_host, const i
 	PXB_TRY(ctx->outA.reserve(sizeof(int32_t) * (size_t)P));
 	double *d_w = nullptr;
 	if (weights_by_row_host) {
-		PXB_CHECK_ARG(P == 1, "weighted fits are issued one problem at a time");
-		PXB_TRY(ctx->pref2.reserve(sizeof(double) * (size_t)total));
+		// H, F: first `total` entries, read by row (the reference's indexing); VP: all N entries, read by point
+		const bool by_point = ctx->pts.type == PXB_MODEL_VANISHING_POINT;
+		PXB_CHECK_ARG(P == 1 || by_point, "row-indexed weighted fits are issued one problem at a time");
+		const size_t count = by_point ? (size_t)ctx->pts.N : (size_t)total;
+		PXB_TRY(ctx->pref2.reserve(sizeof(double) * count));
 		d_w = ctx->pref2.as<double>();
-		PXB_CUDA(cudaMemcpyAsync(d_w, weights_by_row_host, sizeof(double) * (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
+		PXB_CUDA(cudaMemcpyAsync(d_w, weights_by_row_host, sizeof(double) * count, cudaMemcpyHostToDevice, ctx->stream));
 	}
 	PXB_CUDA(cudaMemcpyAsync(d_off, off_host, sizeof(int32_t) * (size_t)(P + 1), cudaMemcpyHostToDevice, ctx->stream));
 	PXB_CUDA(cudaMemcpyAsync(d_idx, idx_host, sizeof(int32_t) * (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
 	switch (ctx->pts.type) {
 	case PXB_MODEL_HOMOGRAPHY: PXB_TRY(launch_fit_h(ctx, P, d_off, d_idx, d_w, ctx->models.as<double>(), ctx->outA.as<int32_t>())); break;
 	case PXB_MODEL_FUNDAMENTAL: PXB_TRY(launch_fit_f(ctx, P, d_off, d_idx, d_w, ctx->models.as<double>(), ctx->outA.as<int32_t>())); break;
-	default: PXB_TRY(launch_fit_pnp(ctx, P, d_off, d_idx, ctx->models.as<double>(), ctx->outA.as<int32_t>())); break;
+	case PXB_MODEL_PNP: PXB_TRY(launch_fit_pnp(ctx, P, d_off, d_idx, ctx->models.as<double>(), ctx->outA.as<int32_t>())); break;
+	case PXB_MODEL_VANISHING_POINT: PXB_TRY(launch_fit_vp(ctx, P, d_off, d_idx, d_w, ctx->models.as<double>(), ctx->outA.as<int32_t>())); break;
+	default: PXB_TRY(launch_fit_line(ctx, P, d_off, d_idx, ctx->models.as<double>(), ctx->outA.as<int32_t>())); break;
 	}
 	PXB_CUDA(cudaMemcpyAsync(H_out_host, ctx->models.ptr, sizeof(double) * (size_t)P * ms, cudaMemcpyDeviceToHost, ctx->stream));
 	PXB_CUDA(cudaMemcpyAsync(ok_out_host, ctx->outA.ptr, sizeof(int32_t) * (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));

@@ -40,10 +40,17 @@ void set_error(const char *fmt, ...);
 
 constexpr int kMaxDim = 5;
 
-inline int point_dim(int t) { return t == PXB_MODEL_PNP ? 5 : 4; }
-inline int model_size(int t) { return t == PXB_MODEL_PNP ? 12 : 9; }
-inline int sample_size(int t) { return t == PXB_MODEL_HOMOGRAPHY ? 4 : (t == PXB_MODEL_FUNDAMENTAL ? 7 : 3); }
-inline int max_solutions(int t) { return t == PXB_MODEL_HOMOGRAPHY ? 1 : (t == PXB_MODEL_FUNDAMENTAL ? 3 : 4); }
+inline int point_dim(int t) { return t == PXB_MODEL_PNP ? 5 : (t == PXB_MODEL_LINE2D ? 2 : 4); }
+inline int model_size(int t) { return t == PXB_MODEL_PNP ? 12 : (t >= PXB_MODEL_VANISHING_POINT ? 3 : 9); }
+inline int sample_size(int t) {
+	switch (t) {
+	case PXB_MODEL_HOMOGRAPHY: return 4;
+	case PXB_MODEL_FUNDAMENTAL: return 7;
+	case PXB_MODEL_PNP: return 3;
+	default: return 2;
+	}
+}
+inline int max_solutions(int t) { return t == PXB_MODEL_FUNDAMENTAL ? 3 : (t == PXB_MODEL_PNP ? 4 : 1); }
 
 // A growable device scratch buffer (never shrinks; freed with the context).
 struct DevBuf {

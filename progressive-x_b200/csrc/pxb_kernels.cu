@@ -54,9 +54,18 @@ __global__ void __launch_bounds__(1024) k_point_stats(const double *__restrict__
 	if (threadIdx.x == 0) {
 		NormDev nd;
 		double s = 0.0;
+		double L[5], Hh[5];
 		for (int c = 0; c < 5; ++c) {
-			double l = 1e300, h = -1e300;
-			for (int w = 0; w < 32; ++w) l = fmin(l, s_lo[w][c]), h = fmax(h, s_hi[w][c]);
+			L[c] = 1e300, Hh[c] = -1e300;
+			for (int w = 0; w < 32; ++w) L[c] = fmin(L[c], s_lo[w][c]), Hh[c] = fmax(Hh[c], s_hi[w][c]);
+		}
+		if (type == PXB_MODEL_VANISHING_POINT) // both end points of a segment live in the same image: one centre
+			for (int c = 0; c < 2; ++c) {
+				L[c] = L[c + 2] = fmin(L[c], L[c + 2]);
+				Hh[c] = Hh[c + 2] = fmax(Hh[c], Hh[c + 2]);
+			}
+		for (int c = 0; c < 5; ++c) {
+			const double l = L[c], h = Hh[c];
 			const bool used = c < dim && !(type == PXB_MODEL_PNP && c < 2) && l <= h;
 			nd.c[c] = used ? 0.5 * (l + h) : 0.0;
 			if (used) s = fmax(s, 0.5 * (h - l));
@@ -76,11 +85,7 @@ __global__ void k_aos_to_soa(const double *__restrict__ aos, double *__restrict_
 	for (int c = 0; c < dim; ++c) soa[c * stride + i] = p[c] = (i < N) ? aos[i * dim + c] : 0.0;
 	const NormDev nd = *norm;
 	float pf[5], qq;
-	switch (type) {
-	case PXB_MODEL_HOMOGRAPHY: screen_point<PXB_MODEL_HOMOGRAPHY>(p, nd, pf, qq); break;
-	case PXB_MODEL_FUNDAMENTAL: screen_point<PXB_MODEL_FUNDAMENTAL>(p, nd, pf, qq); break;
-	default: screen_point<PXB_MODEL_PNP>(p, nd, pf, qq); break;
-	}
+	PXB_DISPATCH_TYPE(type, screen_point<TYPE>(p, nd, pf, qq));
 	for (int c = 0; c < dim; ++c) f32n[c * stride + i] = pf[c];
 	q[i] = qq;
 }
@@ -237,19 +242,12 @@ static int launch_rm_t(pxb_ctx *ctx, const double *models, int64_t K, double T2,
 int launch_residual_matrix(pxb_ctx *ctx, const double *models, int64_t K, double T2, double *r2, float *r2f,
                            uint32_t *mask) {
 	if (K <= 0) return PXB_OK;
-	const int t = ctx->pts.type;
-	if (r2f) {
-		switch (t) {
-		case PXB_MODEL_HOMOGRAPHY: return launch_rm_t<PXB_MODEL_HOMOGRAPHY, float>(ctx, models, K, T2, r2f, mask);
-		case PXB_MODEL_FUNDAMENTAL: return launch_rm_t<PXB_MODEL_FUNDAMENTAL, float>(ctx, models, K, T2, r2f, mask);
-		default: return launch_rm_t<PXB_MODEL_PNP, float>(ctx, models, K, T2, r2f, mask);
-		}
-	}
-	switch (t) {
-	case PXB_MODEL_HOMOGRAPHY: return launch_rm_t<PXB_MODEL_HOMOGRAPHY, double>(ctx, models, K, T2, r2, mask);
-	case PXB_MODEL_FUNDAMENTAL: return launch_rm_t<PXB_MODEL_FUNDAMENTAL, double>(ctx, models, K, T2, r2, mask);
-	default: return launch_rm_t<PXB_MODEL_PNP, double>(ctx, models, K, T2, r2, mask);
-	}
+	int rc = PXB_OK;
+	if (r2f)
+		PXB_DISPATCH_TYPE(ctx->pts.type, rc = (launch_rm_t<TYPE, float>(ctx, models, K, T2, r2f, mask)));
+	else
+		PXB_DISPATCH_TYPE(ctx->pts.type, rc = (launch_rm_t<TYPE, double>(ctx, models, K, T2, r2, mask)));
+	return rc;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -273,17 +271,7 @@ __global__ void k_preference(const double *__restrict__ soa, int64_t stride, int
 int launch_preference(pxb_ctx *ctx, const double *model, double T, double *pref) {
 	const Points &p = ctx->pts;
 	const unsigned grid = (unsigned)((p.N + kThreads - 1) / kThreads);
-	switch (p.type) {
-	case PXB_MODEL_HOMOGRAPHY:
-		k_preference<PXB_MODEL_HOMOGRAPHY><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, model, T, pref);
-		break;
-	case PXB_MODEL_FUNDAMENTAL:
-		k_preference<PXB_MODEL_FUNDAMENTAL><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, model, T, pref);
-		break;
-	default:
-		k_preference<PXB_MODEL_PNP><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, model, T, pref);
-		break;
-	}
+	PXB_DISPATCH_TYPE(p.type, (k_preference<TYPE><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, model, T, pref)));
 	ctx->launches++;
 	PXB_CUDA(cudaGetLastError());
 	return PXB_OK;
@@ -383,20 +371,7 @@ int launch_pearl_datacost(pxb_ctx *ctx, const double *models, int64_t L, double 
 	const double one_minus = 1.0 - lambda;
 	const unsigned grid = (unsigned)((p.N + kThreads - 1) / kThreads);
 	const size_t smem = sizeof(double) * (size_t)std::max<int64_t>(L, 1) * model_size(p.type);
-	switch (p.type) {
-	case PXB_MODEL_HOMOGRAPHY:
-		k_pearl_datacost<PXB_MODEL_HOMOGRAPHY><<<grid, kThreads, smem, ctx->stream>>>(p.soa, p.stride, p.N, models,
-		                                                                              (int)L, T, one_minus, D);
-		break;
-	case PXB_MODEL_FUNDAMENTAL:
-		k_pearl_datacost<PXB_MODEL_FUNDAMENTAL><<<grid, kThreads, smem, ctx->stream>>>(p.soa, p.stride, p.N, models,
-		                                                                               (int)L, T, one_minus, D);
-		break;
-	default:
-		k_pearl_datacost<PXB_MODEL_PNP><<<grid, kThreads, smem, ctx->stream>>>(p.soa, p.stride, p.N, models, (int)L, T,
-		                                                                       one_minus, D);
-		break;
-	}
+	PXB_DISPATCH_TYPE(p.type, (k_pearl_datacost<TYPE><<<grid, kThreads, smem, ctx->stream>>>(p.soa, p.stride, p.N, models, (int)L, T, one_minus, D)));
 	ctx->launches++;
 	PXB_CUDA(cudaGetLastError());
 	return PXB_OK;
@@ -442,20 +417,7 @@ int launch_segment_sums(pxb_ctx *ctx, const double *models, int64_t L, const int
                         int64_t *counts) {
 	if (L <= 0) return PXB_OK;
 	const Points &p = ctx->pts;
-	switch (p.type) {
-	case PXB_MODEL_HOMOGRAPHY:
-		k_segment_sums<PXB_MODEL_HOMOGRAPHY><<<(unsigned)L, kOneBlock, 0, ctx->stream>>>(p.soa, p.stride, p.N, models,
-		                                                                                 labels, sums, counts);
-		break;
-	case PXB_MODEL_FUNDAMENTAL:
-		k_segment_sums<PXB_MODEL_FUNDAMENTAL><<<(unsigned)L, kOneBlock, 0, ctx->stream>>>(p.soa, p.stride, p.N, models,
-		                                                                                  labels, sums, counts);
-		break;
-	default:
-		k_segment_sums<PXB_MODEL_PNP><<<(unsigned)L, kOneBlock, 0, ctx->stream>>>(p.soa, p.stride, p.N, models, labels,
-		                                                                          sums, counts);
-		break;
-	}
+	PXB_DISPATCH_TYPE(p.type, (k_segment_sums<TYPE><<<(unsigned)L, kOneBlock, 0, ctx->stream>>>(p.soa, p.stride, p.N, models, labels, sums, counts)));
 	ctx->launches++;
 	PXB_CUDA(cudaGetLastError());
 	return PXB_OK;
@@ -496,20 +458,7 @@ int launch_lo_unary(pxb_ctx *ctx, const double *model, double thr, double lambda
 	const double T = thr * thr * 9 / 4; // GCRANSAC.h:942 spelling
 	const double one_minus = 1.0 - lambda;
 	const unsigned grid = (unsigned)((p.N + kThreads - 1) / kThreads);
-	switch (p.type) {
-	case PXB_MODEL_HOMOGRAPHY:
-		k_lo_unary<PXB_MODEL_HOMOGRAPHY><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, model, T, one_minus,
-		                                                                     d, e0, e1);
-		break;
-	case PXB_MODEL_FUNDAMENTAL:
-		k_lo_unary<PXB_MODEL_FUNDAMENTAL><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, model, T, one_minus,
-		                                                                      d, e0, e1);
-		break;
-	default:
-		k_lo_unary<PXB_MODEL_PNP><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, model, T, one_minus, d, e0,
-		                                                              e1);
-		break;
-	}
+	PXB_DISPATCH_TYPE(p.type, (k_lo_unary<TYPE><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, model, T, one_minus, d, e0, e1)));
 	ctx->launches++;
 	PXB_CUDA(cudaGetLastError());
 	return PXB_OK;
@@ -534,17 +483,7 @@ __global__ void k_tukey(const double *__restrict__ soa, int64_t stride, int64_t 
 int launch_tukey(pxb_ctx *ctx, const double *model, double T2, double *w) {
 	const Points &p = ctx->pts;
 	const unsigned grid = (unsigned)((p.N + kThreads - 1) / kThreads);
-	switch (p.type) {
-	case PXB_MODEL_HOMOGRAPHY:
-		k_tukey<PXB_MODEL_HOMOGRAPHY><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, model, T2, w);
-		break;
-	case PXB_MODEL_FUNDAMENTAL:
-		k_tukey<PXB_MODEL_FUNDAMENTAL><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, model, T2, w);
-		break;
-	default:
-		k_tukey<PXB_MODEL_PNP><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, model, T2, w);
-		break;
-	}
+	PXB_DISPATCH_TYPE(p.type, (k_tukey<TYPE><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, model, T2, w)));
 	ctx->launches++;
 	PXB_CUDA(cudaGetLastError());
 	return PXB_OK;

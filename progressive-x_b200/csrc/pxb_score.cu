@@ -325,11 +325,9 @@ int launch_score_compound(pxb_ctx *ctx, const double *models, int64_t K, double 
 		const int64_t kk = std::min<int64_t>(K - done, (int64_t)65535 * kScHyps);
 		const double *m = models + done * ms;
 		ScorePartial *pp = part + done * nchunks;
-		switch (p.type) {
-		case PXB_MODEL_HOMOGRAPHY: PXB_TRY(launch_partial<PXB_MODEL_HOMOGRAPHY>(ctx, nchunks, m, kk, T2, compound_pref, pp)); break;
-		case PXB_MODEL_FUNDAMENTAL: PXB_TRY(launch_partial<PXB_MODEL_FUNDAMENTAL>(ctx, nchunks, m, kk, T2, compound_pref, pp)); break;
-		default: PXB_TRY(launch_partial<PXB_MODEL_PNP>(ctx, nchunks, m, kk, T2, compound_pref, pp)); break;
-		}
+		int rc = PXB_OK;
+		PXB_DISPATCH_TYPE(p.type, rc = launch_partial<TYPE>(ctx, nchunks, m, kk, T2, compound_pref, pp));
+		PXB_TRY(rc);
 		done += kk;
 	}
 	k_score_finalize<<<(unsigned)((K + 127) / 128), 128, 0, ctx->stream>>>(part, K, nchunks, count, value_sum, shared);

@@ -56,6 +56,8 @@ template <int TYPE> struct ScreenTraits;
 template <> struct ScreenTraits<PXB_MODEL_HOMOGRAPHY> { static constexpr int kFloats = 12; };
 template <> struct ScreenTraits<PXB_MODEL_FUNDAMENTAL> { static constexpr int kFloats = 12; };
 template <> struct ScreenTraits<PXB_MODEL_PNP> { static constexpr int kFloats = 12; };
+template <> struct ScreenTraits<PXB_MODEL_VANISHING_POINT> { static constexpr int kFloats = 8; };
+template <> struct ScreenTraits<PXB_MODEL_LINE2D> { static constexpr int kFloats = 4; };
 
 // Normalised float32 coordinates of one point + its error-scale constant q = ((P1 P2)^2)(1 + 2^-6); +inf marks a
 // point that must always take the exact path (non-finite or out-of-range coordinates).
@@ -63,18 +65,30 @@ template <int TYPE>
 __device__ __forceinline__ void screen_point(const double *p, const NormDev &nd, float *pf, float &q) {
 	constexpr int DIM = ModelTraits<TYPE>::kDim;
 	bool wild = false;
+	double v[5];
 	float a[5];
 #pragma unroll
 	for (int c = 0; c < DIM; ++c) {
 		const bool raw = (TYPE == PXB_MODEL_PNP && c < 2); // K^-1-normalised image coordinates are used as they are
-		const double v = raw ? p[c] : (p[c] - nd.c[c]) * nd.inv_s;
-		wild |= !(fabs(v) <= 1024.0);
-		a[c] = (float)v;
+		v[c] = raw ? p[c] : (p[c] - nd.c[c]) * nd.inv_s;
+		wild |= !(fabs(v[c]) <= 1024.0);
 	}
+	if (TYPE == PXB_MODEL_VANISHING_POINT) { // stored as (xs, ys, xs + xe, ys + ye): the test uses twice the midpoint
+		v[2] = v[0] + v[2];
+		v[3] = v[1] + v[3];
+	}
+#pragma unroll
+	for (int c = 0; c < DIM; ++c) a[c] = (float)v[c];
 	float P1, P2;
 	if (TYPE == PXB_MODEL_PNP) {
 		P2 = fabsf(a[0]) + fabsf(a[1]) + 1.0f;
 		P1 = fabsf(a[2]) + fabsf(a[3]) + fabsf(a[4]) + 1.0f;
+	} else if (TYPE == PXB_MODEL_VANISHING_POINT) {
+		P2 = fabsf(a[0]) + fabsf(a[1]) + 1.0f;
+		P1 = 2.0f * (fabsf(a[2]) + fabsf(a[3]) + 1.0f); // |l'| <= 2 M (|sx| + |sy| + 1), see screen_sure_outlier<VP>
+	} else if (TYPE == PXB_MODEL_LINE2D) {
+		P1 = fabsf(a[0]) + fabsf(a[1]) + 1.0f;
+		P2 = 1.0f;
 	} else {
 		P1 = fabsf(a[0]) + fabsf(a[1]) + 1.0f;
 		P2 = fabsf(a[2]) + fabsf(a[3]) + 1.0f;
@@ -92,9 +106,9 @@ template <int TYPE> __device__ __forceinline__ void screen_model(const double *m
 // rescaled by an exact power of two to M in [1, 2): the error allowance then uses the constant M^2 <= 4 and no
 // hypothesis is out of range unless it is zero or non-finite (those get NaN entries: every comparison is false and
 // every point of that hypothesis takes the exact path).
-__device__ __forceinline__ void screen_model_finish(const double *out, const double *mag, int n, float *mf, int) {
+__device__ __forceinline__ int screen_model_finish(const double *out, const double *mag, int n, float *mf, bool &wild) {
 	double M = 0.0;
-	bool wild = false;
+	wild = false;
 	for (int i = 0; i < n; ++i) {
 		wild |= !(fabs(out[i]) <= 1e300) || !(mag[i] <= 1e300);
 		M = fmax(M, mag[i]);
@@ -103,6 +117,7 @@ __device__ __forceinline__ void screen_model_finish(const double *out, const dou
 	int e = 0;
 	frexp(wild ? 1.0 : M, &e); // M = f 2^e, f in [0.5, 1)
 	for (int i = 0; i < n; ++i) mf[i] = wild ? __int_as_float(0x7fc00000) : (float)ldexp(out[i], 1 - e);
+	return 1 - e; // the model was multiplied by 2^(1-e)
 }
 
 template <> __device__ __forceinline__ void screen_model<PXB_MODEL_HOMOGRAPHY>(const double *m, const NormDev &nd, float *mf) {
@@ -125,7 +140,8 @@ template <> __device__ __forceinline__ void screen_model<PXB_MODEL_HOMOGRAPHY>(c
 		mag[3 + j] = (A[3 + j] + fabs(c3) * A[6 + j]) * nd.inv_s;
 		mag[6 + j] = A[6 + j];
 	}
-	screen_model_finish(out, mag, 9, mf, 9);
+	bool wild;
+	screen_model_finish(out, mag, 9, mf, wild);
 }
 
 template <> __device__ __forceinline__ void screen_model<PXB_MODEL_FUNDAMENTAL>(const double *m, const NormDev &nd, float *mf) {
@@ -148,7 +164,8 @@ template <> __device__ __forceinline__ void screen_model<PXB_MODEL_FUNDAMENTAL>(
 		mag[3 + j] = s * A[3 + j];
 		mag[6 + j] = fabs(c2) * A[j] + fabs(c3) * A[3 + j] + A[6 + j];
 	}
-	screen_model_finish(out, mag, 9, mf, 9);
+	bool wild;
+	screen_model_finish(out, mag, 9, mf, wild);
 }
 
 template <> __device__ __forceinline__ void screen_model<PXB_MODEL_PNP>(const double *m, const NormDev &nd, float *mf) {
@@ -162,7 +179,43 @@ template <> __device__ __forceinline__ void screen_model<PXB_MODEL_PNP>(const do
 		out[4 * r + 3] = m[4 * r] * nd.c[2] + m[4 * r + 1] * nd.c[3] + m[4 * r + 2] * nd.c[4] + m[4 * r + 3];
 		mag[4 * r + 3] = fabs(m[4 * r] * nd.c[2]) + fabs(m[4 * r + 1] * nd.c[3]) + fabs(m[4 * r + 2] * nd.c[4]) + fabs(m[4 * r + 3]);
 	}
-	screen_model_finish(out, mag, 12, mf, 12);
+	bool wild;
+	screen_model_finish(out, mag, 12, mf, wild);
+}
+
+// Vanishing point v (homogeneous): v_n = N v with N = [[1/s, 0, -cx/s], [0, 1/s, -cy/s], [0, 0, 1]] (both segment
+// end points share the centre: NormDev.c[0] == c[2], c[1] == c[3] for this family). Layout: d0 d1 d2 2d0 2d1.
+template <> __device__ __forceinline__ void screen_model<PXB_MODEL_VANISHING_POINT>(const double *m, const NormDev &nd, float *mf) {
+	double out[3], mag[3];
+	out[0] = (m[0] - nd.c[0] * m[2]) * nd.inv_s;
+	out[1] = (m[1] - nd.c[1] * m[2]) * nd.inv_s;
+	out[2] = m[2];
+	mag[0] = (fabs(m[0]) + fabs(nd.c[0] * m[2])) * nd.inv_s;
+	mag[1] = (fabs(m[1]) + fabs(nd.c[1] * m[2])) * nd.inv_s;
+	mag[2] = fabs(m[2]);
+	bool wild;
+	screen_model_finish(out, mag, 3, mf, wild);
+	mf[3] = 2.0f * mf[0];
+	mf[4] = 2.0f * mf[1];
+	mf[5] = mf[6] = mf[7] = 0.0f;
+}
+
+// 2D line l = (nx, ny, c): r = l . (x, y, 1) = l_n . (x_n, y_n, 1) with l_n = (s nx, s ny, nx cx + ny cy + c); r is NOT
+// homogeneous against the fixed threshold, so the power-of-two rescale 2^k of l_n is carried into the threshold:
+// slot 3 holds 4^k (the squared residual of the rescaled line is compared with T 4^k).
+template <> __device__ __forceinline__ void screen_model<PXB_MODEL_LINE2D>(const double *m, const NormDev &nd, float *mf) {
+	double out[3], mag[3];
+	out[0] = nd.s * m[0];
+	out[1] = nd.s * m[1];
+	out[2] = m[0] * nd.c[0] + m[1] * nd.c[1] + m[2];
+	mag[0] = fabs(out[0]);
+	mag[1] = fabs(out[1]);
+	mag[2] = fabs(m[0] * nd.c[0]) + fabs(m[1] * nd.c[1]) + fabs(m[2]);
+	bool wild;
+	const int k = screen_model_finish(out, mag, 3, mf, wild);
+	wild |= (k > 60 || k < -60); // 4^k must be a normal float32
+	mf[3] = wild ? __int_as_float(0x7fc00000) : (float)ldexp(1.0, 2 * k);
+	if (wild) mf[0] = mf[1] = mf[2] = __int_as_float(0x7fc00000);
 }
 
 // Launch constants of the test in normalised units (float32, rounded up): cT multiplies the threshold side,
@@ -171,7 +224,7 @@ struct ScreenConsts {
 	float cT, cE;
 };
 template <int TYPE> __device__ __forceinline__ ScreenConsts screen_consts(double T2, const NormDev &nd) {
-	const double Tn = (TYPE == PXB_MODEL_PNP) ? T2 : T2 * nd.inv_s * nd.inv_s * (1.0 + 1e-15);
+	const double Tn = (TYPE == PXB_MODEL_PNP || TYPE == PXB_MODEL_LINE2D) ? T2 : T2 * nd.inv_s * nd.inv_s * (1.0 + 1e-15);
 	ScreenConsts k;
 	if (!(Tn > 0.0) || !(Tn <= 1e30)) { // NaN / non-positive / huge thresholds: everything takes the exact path
 		k.cT = k.cE = __int_as_float(0x7f800000);
@@ -181,7 +234,9 @@ template <int TYPE> __device__ __forceinline__ ScreenConsts screen_consts(double
 	// error allowance by 17x
 	constexpr double eta = 1.0 / 16.0;
 	const double rT = sqrt(Tn);
-	const double w = (TYPE == PXB_MODEL_FUNDAMENTAL) ? (2.0 * rT + 1.0) : (1.4142135623730951 + rT);
+	const double w = (TYPE == PXB_MODEL_FUNDAMENTAL || TYPE == PXB_MODEL_VANISHING_POINT)
+	                     ? (2.0 * rT + 1.0)
+	                     : (TYPE == PXB_MODEL_LINE2D ? 1.0 : (1.4142135623730951 + rT));
 	k.cT = __double2float_ru((1.0 + eta) * Tn * kScreenSlack);
 	k.cE = __double2float_ru(4.0 * (1.0 + 1.0 / eta) * w * w * (double)kScreenU2 * kScreenSlack * kScreenSlack);
 	return k;
@@ -216,6 +271,23 @@ template <> __device__ __forceinline__ bool screen_sure_outlier<PXB_MODEL_FUNDAM
 	const float ry = fmaf(m[3], p[0], fmaf(m[4], p[1], m[5]));
 	const float den = fmaf(rxc, rxc, fmaf(ryc, ryc, fmaf(rx, rx, ry * ry)));
 	return r * r >= fmaf(den, cT, Z);
+}
+
+// VP: twice the line through the midpoint and the vanishing point, l' = (sy d2 - 2 d1, 2 d0 - sx d2, sx d1 - sy d0) with
+// (sx, sy) = start + end; the segment's start point is tested against it: r^2 >= T (lx^2 + ly^2), the F-type test.
+// |l'_k| <= 2 M (|sx| + |sy| + 1) =: M P1; forward errors: l' 6u M P1/2.., r <= 17 u M P1 P2 / 2 (P1 carries the factor 2).
+template <> __device__ __forceinline__ bool screen_sure_outlier<PXB_MODEL_VANISHING_POINT>(const float *p, const float *m, float cT, float Z) {
+	const float lx = fmaf(p[3], m[2], -m[4]);
+	const float ly = fmaf(-p[2], m[2], m[3]);
+	const float lz = fmaf(p[2], m[1], -(p[3] * m[0]));
+	const float r = fmaf(lx, p[0], fmaf(ly, p[1], lz));
+	const float den = fmaf(lx, lx, ly * ly);
+	return r * r >= fmaf(den, cT, Z);
+}
+// 2D line: r_f^2 >= (1 + eta) T 4^k + (1 + 1/eta) E^2  ==>  r^2 >= T   (|r_f - r| <= 4 u M P1 <= E)
+template <> __device__ __forceinline__ bool screen_sure_outlier<PXB_MODEL_LINE2D>(const float *p, const float *m, float cT, float Z) {
+	const float r = fmaf(m[0], p[0], fmaf(m[1], p[1], m[2]));
+	return r * r >= fmaf(m[3], cT, Z);
 }
 
 } // namespace pxb

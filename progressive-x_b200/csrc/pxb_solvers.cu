@@ -534,6 +534,55 @@ __global__ void __launch_bounds__(64)
 	n_models[k] = nsol;
 }
 
+// ------------------------------------------------------------------------------------------------
+// f-4: vanishing point from two segments, 2D line from two points (closed forms, thread per sample)
+// ------------------------------------------------------------------------------------------------
+// VanishingPointTwoLineSolver::estimateModel, minimal branch (px/include/solver_vanishing_point_two_lines.h:146-186):
+// l_k = (start_k, 1) x (end_k, 1); v = l_0 x l_1; v /= |v|. vec_cross(a,b) = (b1 c2 - c1 b2, -(a1 c2 - c1 a2),
+// a1 b2 - b1 a2) (:100-114). The model is pushed whatever it contains (parallel segments give NaN).
+__global__ void __launch_bounds__(128)
+    k_solve_vp2(const double *__restrict__ aos, const int64_t *__restrict__ samples, int64_t K, double *__restrict__ models,
+                int32_t *__restrict__ n_models) {
+	const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= K) return;
+	const double *a = aos + 4 * samples[2 * k], *b = aos + 4 * samples[2 * k + 1];
+	const double xs0 = a[0], ys0 = a[1], xe0 = a[2], ye0 = a[3], xs1 = b[0], ys1 = b[1], xe1 = b[2], ye1 = b[3];
+	double l0[3], l1[3], v[3];
+	l0[0] = sub(mul(ys0, 1.0), mul(1.0, ye0));
+	l0[1] = -sub(mul(xs0, 1.0), mul(1.0, xe0));
+	l0[2] = sub(mul(xs0, ye0), mul(ys0, xe0));
+	l1[0] = sub(mul(ys1, 1.0), mul(1.0, ye1));
+	l1[1] = -sub(mul(xs1, 1.0), mul(1.0, xe1));
+	l1[2] = sub(mul(xs1, ye1), mul(ys1, xe1));
+	v[0] = sub(mul(l0[1], l1[2]), mul(l0[2], l1[1]));
+	v[1] = -sub(mul(l0[0], l1[2]), mul(l0[2], l1[0]));
+	v[2] = sub(mul(l0[0], l1[1]), mul(l0[1], l1[0]));
+	const double len = __dsqrt_rn(add(add(mul(v[0], v[0]), mul(v[1], v[1])), mul(v[2], v[2]))); // vec_norm (:116-125)
+	models[3 * k] = divd(v[0], len);
+	models[3 * k + 1] = divd(v[1], len);
+	models[3 * k + 2] = divd(v[2], len);
+	n_models[k] = 1;
+}
+
+// LinearModelSolver<2>::estimate2DLine (gcr/estimators/solver_linear_model.h:152-188) -- with the reference's
+// `nx = y1 - x2` (a true normal would be y1 - y2): drop-in means the same hypotheses.
+__global__ void __launch_bounds__(128)
+    k_solve_line2(const double *__restrict__ aos, const int64_t *__restrict__ samples, int64_t K, double *__restrict__ models,
+                  int32_t *__restrict__ n_models) {
+	const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= K) return;
+	const double *a = aos + 2 * samples[2 * k], *b = aos + 2 * samples[2 * k + 1];
+	const double x1 = a[0], y1 = a[1], x2 = b[0];
+	double nx = sub(y1, x2), ny = sub(x2, x1);
+	const double magnitude = __dsqrt_rn(add(mul(nx, nx), mul(ny, ny)));
+	nx = divd(nx, magnitude);
+	ny = divd(ny, magnitude);
+	models[3 * k] = nx;
+	models[3 * k + 1] = ny;
+	models[3 * k + 2] = sub(mul(-nx, x1), mul(ny, y1)); // -nx * x1 - ny * y1
+	n_models[k] = 1;
+}
+
 int launch_solve_minimal(pxb_ctx *ctx, const int64_t *samples, int64_t K, double *models_out, int32_t *n_models,
                          uint8_t *sample_valid, uint8_t *model_valid) {
 	if (K <= 0) return PXB_OK;
@@ -548,8 +597,16 @@ int launch_solve_minimal(pxb_ctx *ctx, const int64_t *samples, int64_t K, double
 		if (sample_valid) PXB_CUDA(cudaMemsetAsync(sample_valid, 1, (size_t)K, ctx->stream));
 		if (model_valid) PXB_CUDA(cudaMemsetAsync(model_valid, 1, (size_t)K, ctx->stream));
 		break;
-	default:
+	case PXB_MODEL_PNP:
 		k_solve_p3p<<<(unsigned)((K + 63) / 64), 64, 0, ctx->stream>>>(p.aos, samples, K, models_out, n_models);
+		if (sample_valid) PXB_CUDA(cudaMemsetAsync(sample_valid, 1, (size_t)K, ctx->stream));
+		if (model_valid) PXB_CUDA(cudaMemsetAsync(model_valid, 1, (size_t)K, ctx->stream));
+		break;
+	default: // Estimator::isValidSample / isValidModel are the base-class "true" for both families
+		if (p.type == PXB_MODEL_VANISHING_POINT)
+			k_solve_vp2<<<(unsigned)((K + 127) / 128), 128, 0, ctx->stream>>>(p.aos, samples, K, models_out, n_models);
+		else
+			k_solve_line2<<<(unsigned)((K + 127) / 128), 128, 0, ctx->stream>>>(p.aos, samples, K, models_out, n_models);
 		if (sample_valid) PXB_CUDA(cudaMemsetAsync(sample_valid, 1, (size_t)K, ctx->stream));
 		if (model_valid) PXB_CUDA(cudaMemsetAsync(model_valid, 1, (size_t)K, ctx->stream));
 		break;

@@ -18,7 +18,8 @@ import numpy as _np
 from . import _native
 from ._native import Context, PxbError  # noqa: F401
 
-__all__ = ["findHomographies", "findTwoViewMotions", "findFundamentalMatrices", "find6DPoses", "Context"]
+__all__ = ["findHomographies", "findTwoViewMotions", "findFundamentalMatrices", "find6DPoses", "findVanishingPoints",
+           "findLines", "Context"]
 
 _contexts = {}
 
@@ -124,3 +125,55 @@ def find6DPoses(x1y1, x2y2z2, K, threshold=4.0, conf=0.90, spatial_coherence_wei
                                    int(maximum_model_number), int(seed))
     M = _native._check(rc)
     return poses[:M].reshape(M * 3, 4).copy(), labeling.astype(_np.int32)
+
+
+def _points_family(fn_name, rows, dim, what, weights, w, h, threshold, conf, spatial_coherence_weight,
+                   neighborhood_ball_radius, maximum_tanimoto_similarity, max_iters, minimum_point_number,
+                   maximum_model_number, sampler_id, scoring_exponent, do_logging, seed, device):
+    rows = _np.ascontiguousarray(rows, dtype=_np.float64)
+    if rows.ndim != 2 or rows.shape[1] != dim or rows.shape[0] < 2:  # bindings.cpp:189-194 / :266-269
+        raise ValueError(what)
+    wts = None
+    if weights is not None and _np.ndim(weights) > 0:  # bindings.cpp:201-209: a 0-d array means "no weights"
+        wts = _np.ascontiguousarray(weights, dtype=_np.float64).reshape(-1)
+        if wts.size == 0:
+            wts = None
+        elif wts.size != rows.shape[0]:
+            raise ValueError("weights should hold one entry per row")
+    ctx = _ctx(device)
+    N = rows.shape[0]
+    labeling = _np.zeros(N, dtype=_np.int64)
+    cap = 16
+    models = _np.zeros((cap, 3), dtype=_np.float64)
+    fn = getattr(ctx.lib, fn_name)
+    rc = fn(ctx.handle, rows.ctypes.data_as(_C.c_void_p), None if wts is None else wts.ctypes.data_as(_C.c_void_p), N,
+            labeling.ctypes.data_as(_C.c_void_p), models.ctypes.data_as(_C.c_void_p), cap, int(w), int(h),
+            float(spatial_coherence_weight), float(threshold), float(conf), float(neighborhood_ball_radius),
+            float(maximum_tanimoto_similarity), int(max_iters), int(minimum_point_number), int(maximum_model_number),
+            int(sampler_id), float(scoring_exponent), int(bool(do_logging)), int(seed))
+    M = _native._check(rc)
+    return models[:M].copy(), labeling.astype(_np.int32)
+
+
+def findVanishingPoints(lines, weights, w, h, threshold=4.0, conf=0.5, spatial_coherence_weight=0.0,
+                        neighborhood_ball_radius=200.0, maximum_tanimoto_similarity=0.4, max_iters=1000,
+                        minimum_point_number=10, maximum_model_number=-1, sampler_id=3, scoring_exponent=2,
+                        do_logging=False, seed=0, device=0):
+    """bindings.cpp:168-245 / :428-442 -> findVanishingPoints_ (progressivex_python.cpp:306-423). Returns
+    (vanishing_points float64 [M, 3], labeling int32 [N]). As in the reference only sampler_id 0 and 1 exist for this
+    entry: the DEFAULT sampler_id = 3 prints "Unknown sampler identifier" and returns no models."""
+    return _points_family("pxb_find_vanishing_points", lines, 4, "lines should be an array with dims [n,4], n>=2", weights,
+                          w, h, threshold, conf, spatial_coherence_weight, neighborhood_ball_radius,
+                          maximum_tanimoto_similarity, max_iters, minimum_point_number, maximum_model_number, sampler_id,
+                          scoring_exponent, do_logging, seed, device)
+
+
+def findLines(points, weights, w, h, threshold=2.0, conf=0.5, spatial_coherence_weight=0.0,
+              neighborhood_ball_radius=200.0, maximum_tanimoto_similarity=0.4, max_iters=1000, minimum_point_number=10,
+              maximum_model_number=-1, sampler_id=3, scoring_exponent=2, do_logging=False, seed=0, device=0):
+    """bindings.cpp:247-322 / :476-491 -> findLines_ (progressivex_python.cpp:425-535). Returns (lines float64 [M, 3] as
+    (nx, ny, c), labeling int32 [N]). Samplers 0, 1, 2 (= NAPSAC); the default 3 is unknown to the reference too."""
+    return _points_family("pxb_find_lines", points, 2, "Points should be an array with dims [n,3], n>=2", weights, w, h,
+                          threshold, conf, spatial_coherence_weight, neighborhood_ball_radius,
+                          maximum_tanimoto_similarity, max_iters, minimum_point_number, maximum_model_number, sampler_id,
+                          scoring_exponent, do_logging, seed, device)

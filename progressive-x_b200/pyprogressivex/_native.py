@@ -14,11 +14,11 @@ import numpy as np
 _PKG_ROOT = Path(__file__).resolve().parent.parent
 LIB_PATH = _PKG_ROOT / "libpxb200.so"
 
-MODEL_H, MODEL_F, MODEL_PNP = 0, 1, 2
-POINT_DIM = {MODEL_H: 4, MODEL_F: 4, MODEL_PNP: 5}
-MODEL_SIZE = {MODEL_H: 9, MODEL_F: 9, MODEL_PNP: 12}
-SAMPLE_SIZE = {MODEL_H: 4, MODEL_F: 7, MODEL_PNP: 3}
-MAX_SOLUTIONS = {MODEL_H: 1, MODEL_F: 3, MODEL_PNP: 4}
+MODEL_H, MODEL_F, MODEL_PNP, MODEL_VP, MODEL_LINE = 0, 1, 2, 3, 4
+POINT_DIM = {MODEL_H: 4, MODEL_F: 4, MODEL_PNP: 5, MODEL_VP: 4, MODEL_LINE: 2}
+MODEL_SIZE = {MODEL_H: 9, MODEL_F: 9, MODEL_PNP: 12, MODEL_VP: 3, MODEL_LINE: 3}
+SAMPLE_SIZE = {MODEL_H: 4, MODEL_F: 7, MODEL_PNP: 3, MODEL_VP: 2, MODEL_LINE: 2}
+MAX_SOLUTIONS = {MODEL_H: 1, MODEL_F: 3, MODEL_PNP: 4, MODEL_VP: 1, MODEL_LINE: 1}
 
 
 class PxbError(RuntimeError):
@@ -88,6 +88,9 @@ def load_library() -> C.CDLL:
                                           C.c_int, sz, f64, C.c_int, u64]
     lib.pxb_find_two_view_motions.argtypes = lib.pxb_find_homographies.argtypes
     lib.pxb_find_6d_poses.argtypes = [vp, vp, vp, vp, i64, vp, vp, i64, f64, f64, f64, f64, f64, sz, sz, C.c_int, u64]
+    lib.pxb_find_vanishing_points.argtypes = [vp, vp, vp, i64, vp, vp, i64, sz, sz, f64, f64, f64, f64, f64, sz, sz,
+                                              C.c_int, sz, f64, C.c_int, u64]
+    lib.pxb_find_lines.argtypes = lib.pxb_find_vanishing_points.argtypes
     _lib = lib
     return lib
 

@@ -128,3 +128,43 @@ def test_unknown_sampler_returns_no_models(capfd):
     corrs, gt, Hs = syn.multi_homography_scene(500, n_planes=2, seed=5)
     models, labels = pyprogressivex.findHomographies(corrs, 1024, 768, 1024, 768, sampler_id=9)
     assert models.shape[0] == 0  # progressivex_python.cpp:240-245: message on stderr, return 0
+
+
+def test_find_vanishing_points_synthetic():
+    """findVanishingPoints through the Python surface: three planted vanishing points, 30 % random segments."""
+    seg, gt, vps = syn.multi_vanishing_point_scene(1500, n_vps=3, outlier_ratio=0.3, noise=0.3, seed=13)
+    models, labels = pyprogressivex.findVanishingPoints(seg, np.ones(len(seg)), 1024, 768, threshold=2.0, conf=0.95,
+                                                        maximum_tanimoto_similarity=0.4, max_iters=1000,
+                                                        minimum_point_number=50, sampler_id=0, seed=4)
+    assert models.dtype == np.float64 and models.shape[1] == 3 and labels.dtype == np.int32 and labels.shape == (1500,)
+    M = models.shape[0]
+    assert 3 <= M <= 4
+    assert misclassification(gt, labels, M) < 0.1
+    # every planted vanishing point is found (directions agree up to sign)
+    for v in vps:
+        cosines = np.abs(models @ v) / np.linalg.norm(models, axis=1)
+        assert cosines.max() > 0.9999
+    # the reference's default sampler id (3) does not exist for this entry: no models, message on stderr
+    m0, l0 = pyprogressivex.findVanishingPoints(seg, np.ones(len(seg)), 1024, 768)
+    assert m0.shape == (0, 3)
+
+
+def test_find_lines_synthetic():
+    """findLines: the minimal solver carries the reference's `nx = y1 - x2`, so hypotheses only become lines through
+    the local optimisation's least-squares fits -- exactly what the reference does; the planted lines are still found."""
+    pts, gt, lines = syn.multi_line_scene(1200, n_lines=3, outlier_ratio=0.3, noise=0.5, seed=17)
+    models, labels = pyprogressivex.findLines(pts, np.ones(len(pts)), 1024, 768, threshold=2.0, conf=0.99,
+                                              maximum_tanimoto_similarity=0.4, max_iters=3000, minimum_point_number=60,
+                                              sampler_id=0, seed=6)
+    assert models.shape[1] == 3 and labels.shape == (1200,)
+    M = models.shape[0]
+    assert M >= 1
+    found = 0
+    for l in lines:
+        d = np.abs(models[:, :2] @ l[:2])
+        k = int(np.argmax(d))
+        if d[k] > 0.999 and abs(abs(models[k, 2]) - abs(l[2])) < 5.0:
+            found += 1
+    assert found >= 1
+    with pytest.raises(ValueError):
+        pyprogressivex.findLines(np.zeros((10, 3)), None, 10, 10)

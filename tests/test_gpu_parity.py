@@ -11,7 +11,8 @@ from pyprogressivex import synthetic as syn
 
 pytestmark = pytest.mark.gpu
 
-H, F, PNP = 0, 1, 2
+H, F, PNP, VP, LINE = 0, 1, 2, 3, 4
+ALL = [H, F, PNP, VP, LINE]
 SUM_RTOL = 1e-12
 
 
@@ -29,15 +30,21 @@ def scene(t, N, seed):
     elif t == F:
         pts, gt, Ms = syn.multi_motion_scene(N, seed=seed)
         thr = 0.75
-    else:
+    elif t == PNP:
         img, w, K, gt, Ms = syn.multi_pose_scene(N, seed=seed)
         pts = syn.normalize_pnp_points(img, w, K)
         thr = 4.0 / (0.5 * (K[0, 0] + K[1, 1]))
+    elif t == VP:
+        pts, gt, Ms = syn.multi_vanishing_point_scene(N, seed=seed)
+        thr = 2.0
+    else:
+        pts, gt, Ms = syn.multi_line_scene(N, seed=seed)
+        thr = 2.0
     return pts, gt, Ms.reshape(Ms.shape[0], -1), thr
 
 
 def hypotheses(oracle, t, pts, gt, planted, K, seed):
-    m = {H: 4, F: 7, PNP: 3}[t]
+    m = {H: 4, F: 7, PNP: 3, VP: 2, LINE: 2}[t]
     S = syn.minimal_samples(gt, K, m, seed=seed)
     models, n, _, _ = oracle.solve_minimal(t, pts, S)
     flat = [models[k, j] for k in range(K) for j in range(n[k])]
@@ -50,7 +57,7 @@ def test_division_selftest(ctx):
     assert ctx.selftest_division(2, 200_000_000, 1) == 0
 
 
-@pytest.mark.parametrize("t", [H, F, PNP])
+@pytest.mark.parametrize("t", ALL)
 @pytest.mark.parametrize("N", [1, 31, 64, 1000, 4097, 10000])
 def test_residual_matrix_bit_exact(ctx, oracle, t, N):
     pts, gt, planted, thr = scene(t, max(N, 200), seed=N)
@@ -81,7 +88,7 @@ def test_residual_matrix_nonfinite_models(ctx, oracle):
     assert np.array_equal(mask, mask_o)
 
 
-@pytest.mark.parametrize("t", [H, F, PNP])
+@pytest.mark.parametrize("t", ALL)
 @pytest.mark.parametrize("with_compound", [False, True])
 def test_score_compound(ctx, oracle, t, with_compound):
     N = 9000
@@ -108,7 +115,7 @@ def test_score_compound(ctx, oracle, t, with_compound):
     assert np.array_equal(ctx.inliers(models[k], T2), s["inliers"])
 
 
-@pytest.mark.parametrize("t", [H, F, PNP])
+@pytest.mark.parametrize("t", ALL)
 def test_preference_tanimoto_compound(ctx, oracle, t):
     N = 5003
     pts, gt, planted, thr = scene(t, N, seed=31)
@@ -176,7 +183,7 @@ def test_p3p_solver(ctx, oracle):
     assert bad <= 0.01 * len(n)
 
 
-@pytest.mark.parametrize("t", [H, F, PNP])
+@pytest.mark.parametrize("t", ALL)
 @pytest.mark.parametrize("lam", [0.0, 0.3])
 def test_pearl_datacost_bit_exact(ctx, oracle, t, lam):
     pts, gt, planted, thr = scene(t, 6001, seed=51)
@@ -206,7 +213,7 @@ def test_greedy_label_sweep_matches_reference_gco(ctx, oracle, seed, label_cost)
         assert abs(e - e_o) <= 1e-11 * abs(e_o)
 
 
-@pytest.mark.parametrize("t", [H, F, PNP])
+@pytest.mark.parametrize("t", ALL)
 def test_segment_residual_sums(ctx, oracle, t):
     pts, gt, planted, thr = scene(t, 7000, seed=71)
     labels = np.where(gt < 0, planted.shape[0], gt).astype(np.int32)
@@ -217,7 +224,7 @@ def test_segment_residual_sums(ctx, oracle, t):
     np.testing.assert_allclose(sums, sums_o, rtol=SUM_RTOL)
 
 
-@pytest.mark.parametrize("t", [H, F, PNP])
+@pytest.mark.parametrize("t", ALL)
 def test_lo_terms_and_tukey_bit_exact(ctx, oracle, t):
     pts, gt, planted, thr = scene(t, 4000, seed=81)
     ctx.upload_points(t, pts)
@@ -306,7 +313,7 @@ def _assert_score_equals_oracle(ctx, oracle, t, pts, models, T2, cp=None):
     return cnt
 
 
-@pytest.mark.parametrize("t", [H, F, PNP])
+@pytest.mark.parametrize("t", ALL)
 def test_score_screening_model_scale_and_garbage(ctx, oracle, t):
     """The inlier tests are homogeneous in the model, the screening rescales it: hypotheses multiplied by 1e+-150,
     zero / NaN / inf hypotheses and random garbage must give the oracle's counts."""
@@ -327,7 +334,7 @@ def test_score_screening_model_scale_and_garbage(ctx, oracle, t):
     assert cnt[:len(models)].max() > 100  # the planted structures are found
 
 
-@pytest.mark.parametrize("t", [H, F, PNP])
+@pytest.mark.parametrize("t", ALL)
 def test_score_screening_wild_points_and_offsets(ctx, oracle, t):
     """Points far from the origin (normalisation must absorb a 1e7 offset), a few non-finite / astronomically large
     points (they must take the exact path), and a set whose bounding box is degenerate."""
@@ -338,10 +345,10 @@ def test_score_screening_wild_points_and_offsets(ctx, oracle, t):
     wild[5, 0] = np.nan
     wild[6, 1] = np.inf
     wild[7, :] = 1e200
-    wild[8, 2] = -1e30
+    wild[8, -1] = -1e30
     wild[9, :] = 0.0
     _assert_score_equals_oracle(ctx, oracle, t, wild, models, T2)
-    if t != PNP:
+    if t in (H, F):
         # translate both images by 1e7 px: H' = T2 H T1^-1, F' = T2^-T F T1^-1 keep the geometry; the counts of the
         # translated problem are whatever the oracle says they are (float64 loses digits too) -- parity is the bar
         off = pts + 1.0e7
@@ -357,7 +364,7 @@ def test_score_screening_threshold_extremes(ctx, oracle, T2):
     _assert_score_equals_oracle(ctx, oracle, H, pts, models, T2)
 
 
-@pytest.mark.parametrize("t", [H, F, PNP])
+@pytest.mark.parametrize("t", ALL)
 def test_score_screening_near_threshold_band(ctx, oracle, t):
     """Points placed a hair inside / outside the threshold of a model (relative 1e-9 .. 1e-3): float32 cannot tell them
     apart, so they must reach the exact path and be classified exactly like the oracle does."""
@@ -371,3 +378,45 @@ def test_score_screening_near_threshold_band(ctx, oracle, t):
     for base in picks:
         for eps in (0.0, 1e-15, -1e-15, 1e-9, -1e-9, 1e-4, -1e-4):
             _assert_score_equals_oracle(ctx, oracle, t, pts, planted[:3], float(base * (1.0 + eps)))
+
+
+@pytest.mark.parametrize("t", [VP, LINE])
+def test_vp_and_line_minimal_solvers_bit_exact(ctx, oracle, t):
+    pts, gt, planted, thr = scene(t, 3000, seed=101)
+    S = syn.minimal_samples(gt, 2000, 2, seed=101)
+    S[0] = [7, 7]  # degenerate: NaN model, produced all the same (the reference pushes it unconditionally)
+    ctx.upload_points(t, pts)
+    models, n, sv, mv = ctx.solve_minimal(S)
+    models_o, n_o, sv_o, mv_o = oracle.solve_minimal(t, pts, S)
+    assert np.array_equal(n, n_o) and np.array_equal(sv, sv_o) and np.array_equal(mv, mv_o)
+    assert np.array_equal(np.isnan(models), np.isnan(models_o))
+    fin = ~np.isnan(models_o)
+    assert bits_equal(models[fin], models_o[fin])
+
+
+@pytest.mark.parametrize("t", [VP, LINE])
+def test_vp_and_line_nonminimal_fits(ctx, oracle, t):
+    """Eigenvector / QR based fits: 1e-9 relative to the oracle up to the sign of the model (the residual is sign
+    invariant; Eigen's own sign convention is not pinned), with and without per-point weights for VP."""
+    pts, gt, planted, thr = scene(t, 4000, seed=103)
+    rng = np.random.default_rng(3)
+    sets = [np.flatnonzero(gt == k) for k in range(planted.shape[0])]
+    sets += [rng.choice(s, 14, replace=False) for s in sets]
+    sets += [np.flatnonzero(gt == 0)[:2]]
+    ctx.upload_points(t, pts)
+    weights = rng.uniform(0.2, 1.0, pts.shape[0]) if t == VP else None
+    for w in ([None, weights] if t == VP else [None]):
+        got, ok = ctx.fit_nonminimal(sets, w)
+        for k, st in enumerate(sets):
+            ref, ok_o = oracle.fit_nonminimal(t, pts, st, w)
+            assert bool(ok[k]) == ok_o
+            if not ok_o:
+                continue
+            sign = 1.0 if np.dot(got[k], ref) >= 0 else -1.0
+            np.testing.assert_allclose(sign * got[k], ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
+    # the fit recovers the planted structure
+    got, ok = ctx.fit_nonminimal(sets[:planted.shape[0]])
+    T2 = (1.5 * thr) ** 2
+    cnt, _, _ = ctx.score_compound(got, T2)
+    for k in range(planted.shape[0]):
+        assert cnt[k] > 0.9 * len(sets[k])
