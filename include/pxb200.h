@@ -174,6 +174,12 @@ int pxb_tukey_weights(pxb_ctx *ctx, const double *model_host, double T2, double 
 int pxb_lo_graph_cut(pxb_ctx *ctx, const double *e0_host, const double *e1_host, const double *d_host, int64_t N,
                      double lambda, const int32_t *csr_off_host, const int32_t *csr_idx_host, uint8_t *inlier_out);
 
+/* GCRANSAC::labeling as a whole (gcr/GCRANSAC.h:914-1022): unary terms, the pairwise graph and the st-cut without
+ * leaving the device (the arc skeleton of a neighbourhood graph is cached on the device after the first call). Same
+ * result as pxb_lo_unary_terms followed by pxb_lo_graph_cut. */
+int pxb_lo_labeling(pxb_ctx *ctx, const double *model_host, double thr, double lambda, const int32_t *csr_off_host,
+                    const int32_t *csr_idx_host, uint8_t *inlier_out);
+
 /* ---- "next" rows the task-level driver needs -------------------------------------------------- */
 /* Neighbourhood graph (replaces FlannNeighborhoodGraph, gcr/neighborhood/flann_neighborhood_graph.h:100-139): the
  * k nearest points within `radius` of every point (self excluded, ties by index), all coordinates of the uploaded

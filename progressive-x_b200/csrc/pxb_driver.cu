@@ -160,6 +160,40 @@ struct Settings {
 	       max_graph_cut_number = 10, max_least_squares_iterations = 10, max_unsuccessful_model_generations = 100;
 };
 
+// PXB_PROFILE=1: host wall time per phase of one find* call, printed to stderr when the driver finishes (tuning aid).
+struct PhaseTimes {
+	bool on = getenv("PXB_PROFILE") != nullptr;
+	std::vector<std::pair<const char *, double>> acc;
+	std::vector<long> calls;
+	void add(const char *name, double ms) {
+		for (size_t i = 0; i < acc.size(); ++i)
+			if (acc[i].first == name) {
+				acc[i].second += ms;
+				calls[i]++;
+				return;
+			}
+		acc.emplace_back(name, ms);
+		calls.push_back(1);
+	}
+	void print() const {
+		if (!on) return;
+		double tot = 0;
+		for (auto &a : acc) tot += a.second;
+		fprintf(stderr, "[pxb profile] total %.2f ms\n", tot);
+		for (size_t i = 0; i < acc.size(); ++i)
+			fprintf(stderr, "[pxb profile]   %-22s %8.2f ms  %6ld calls\n", acc[i].first, acc[i].second, calls[i]);
+	}
+};
+struct Scoped {
+	PhaseTimes &pt;
+	const char *name;
+	std::chrono::steady_clock::time_point t0;
+	Scoped(PhaseTimes &p, const char *n) : pt(p), name(n), t0(std::chrono::steady_clock::now()) {}
+	~Scoped() {
+		if (pt.on) pt.add(name, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+	}
+};
+
 struct Instance {
 	std::vector<double> model;
 	std::vector<double> pref; // preference vector as of acceptance (never refreshed: progressive_x.h:597-624)
@@ -177,6 +211,8 @@ class Driver {
 	int run();
 	const std::vector<Instance> &instances() const { return models_; }
 	const std::vector<int64_t> &labeling() const { return labeling_; }
+
+	PhaseTimes prof_;
 
   private:
 	pxb_ctx *ctx_;
@@ -208,12 +244,14 @@ class Driver {
 		val.resize(K);
 		shr.resize(K);
 		if (K == 0) return PXB_OK;
+		Scoped t(prof_, "score_models");
 		return pxb_score_compound(ctx_, models, K, T2, models_.empty() ? nullptr : compound_pref_.data(), cnt.data(),
 		                          val.data(), shr.data());
 	}
 	int inliers_of(const double *model, double T2, std::vector<int64_t> &out) {
 		out.resize(N_);
 		int64_t n = 0;
+		Scoped t(prof_, "inliers_of");
 		PXB_TRY(pxb_inliers(ctx_, model, T2, out.data(), &n));
 		out.resize(n);
 		return PXB_OK;
@@ -263,6 +301,7 @@ int Driver::fit_nonminimal(const std::vector<std::vector<int64_t>> &sets, const 
 	models_out.assign((size_t)P * ms_, 0.0);
 	ok.assign(P, 0);
 	if (P == 0) return PXB_OK;
+	Scoped t(prof_, "fit_nonminimal");
 	std::vector<int32_t> off(P + 1, 0), idx;
 	for (int p = 0; p < P; ++p) off[p + 1] = off[p] + (int32_t)sets[p].size();
 	idx.reserve(off[P]);
@@ -310,17 +349,17 @@ int Driver::fit_nonminimal(const std::vector<std::vector<int64_t>> &sets, const 
 // gcr/GCRANSAC.h:914-1022. Unary terms come from the device (k_lo_unary). Without a smoothness term the st-cut
 // decomposes per node: SINK (= inlier) iff the t-link residual source-sink is negative, i.e. e0 > e1.
 int Driver::lo_labeling(const double *model, std::vector<int64_t> &inliers) {
-	std::vector<double> d(N_), e0(N_), e1(N_);
-	PXB_TRY(pxb_lo_unary_terms(ctx_, model, s_.threshold, s_.lambda, d.data(), e0.data(), e1.data()));
+	Scoped t(prof_, "lo_labeling");
 	inliers.clear();
 	if (!(s_.lambda > 0) || graph_.idx.empty()) {
+		std::vector<double> d(N_), e0(N_), e1(N_);
+		PXB_TRY(pxb_lo_unary_terms(ctx_, model, s_.threshold, s_.lambda, d.data(), e0.data(), e1.data()));
 		for (int64_t i = 0; i < N_; ++i)
 			if (e1[i] - e0[i] < 0) inliers.push_back(i); // tr_cap = cap_source - cap_sink = e1 - e0 (energy.h:204-208)
 		return PXB_OK;
 	}
 	std::vector<uint8_t> seg(N_);
-	PXB_TRY(pxb_lo_graph_cut(ctx_, e0.data(), e1.data(), d.data(), N_, s_.lambda, graph_.off.data(), graph_.idx.data(),
-	                         seg.data()));
+	PXB_TRY(pxb_lo_labeling(ctx_, model, s_.threshold, s_.lambda, graph_.off.data(), graph_.idx.data(), seg.data()));
 	for (int64_t i = 0; i < N_; ++i)
 		if (seg[i]) inliers.push_back(i);
 	return PXB_OK;
@@ -487,6 +526,7 @@ int Driver::propose(uint64_t round_seed, std::vector<double> &model_out, bool &f
 		blk_n.assign(want, 0);
 		blk_sv.assign(want, 0);
 		blk_mv.assign(want, 0);
+		Scoped t(prof_, "refill(sample+solve)");
 		PXB_TRY(pxb_solve_minimal(ctx_, samples.data(), (int64_t)want, blk_models.data(), blk_n.data(), blk_sv.data(),
 		                          blk_mv.data()));
 		PXB_TRY(score_models(blk_models.data(), (int64_t)(want * maxsol_), T2, blk_cnt, blk_val, blk_shr));
@@ -592,6 +632,7 @@ int Driver::propose(uint64_t round_seed, std::vector<double> &model_out, bool &f
 
 // px/include/progressive_x.h:565-591
 int Driver::putative_model_valid(const std::vector<double> &model, std::vector<double> &pref, bool &valid) {
+	Scoped t(prof_, "putative_model_valid");
 	valid = false;
 	if (proposal_inliers_.size() < std::max((size_t)m_, s_.min_inliers)) return PXB_OK;
 	const double T = 9.0 / 4.0 * s_.threshold * s_.threshold; // :523 spelling
@@ -621,7 +662,11 @@ int Driver::pearl() {
 		std::vector<double> flat((size_t)L * ms_);
 		for (int64_t l = 0; l < L; ++l) std::copy(models_[l].model.begin(), models_[l].model.end(), flat.begin() + l * ms_);
 		std::vector<double> D((size_t)N_ * (L + 1));
-		PXB_TRY(pxb_pearl_datacost(ctx_, flat.data(), L, s_.threshold, s_.lambda, D.data()));
+		{
+			Scoped t(prof_, "pearl datacost");
+			PXB_TRY(pxb_pearl_datacost(ctx_, flat.data(), L, s_.threshold, s_.lambda, D.data()));
+		}
+		Scoped tl(prof_, "pearl label+refit");
 		const int32_t *init = (init_with_previous && have_labels) ? labels.data() : nullptr;
 		prev_labels = labels;
 		const bool smooth = s_.lambda > 0.0 && !graph_.idx.empty();
@@ -780,8 +825,15 @@ int run_two_view(pxb_ctx *ctx, int type, const double *corr, int64_t N, int64_t 
 	if (seed == 0) seed = (uint64_t)std::chrono::high_resolution_clock::now().time_since_epoch().count();
 	s.seed = seed;
 	Driver drv(ctx, s);
-	if (lambda > 0.0 || sampler_id == 3) PXB_TRY(drv.build_graph(radius, 8));
-	PXB_TRY(drv.run());
+	if (lambda > 0.0 || sampler_id == 3) {
+		Scoped t(drv.prof_, "build_graph");
+		PXB_TRY(drv.build_graph(radius, 8));
+	}
+	{
+		Scoped t(drv.prof_, "run (inclusive)");
+		PXB_TRY(drv.run());
+	}
+	drv.prof_.print();
 	const auto &inst = drv.instances();
 	const int ms = model_size(type);
 	const int64_t M = (int64_t)inst.size();

@@ -237,15 +237,25 @@ static int solve_min_cut(pxb_ctx *ctx, const FlowGraphHost &g, std::vector<uint8
 	const int m = 2 * pairs;
 	segment.assign((size_t)n, 0);
 	if (n == 0) return PXB_OK;
+	// The whole problem is assembled in ONE pinned host arena that mirrors the device arena (capacities, excess, sink
+	// capacities, CSR offsets / heads / reverse arcs) and goes up in a single DMA.
+	const size_t mm = (size_t)std::max(m, 1);
+	const size_t bytes_d = sizeof(double) * (mm + 2 * (size_t)n);
+	const size_t bytes_up = bytes_d + sizeof(int32_t) * ((size_t)n + 1 + 2 * mm);
+	const size_t bytes_all = bytes_up + sizeof(int32_t) * (2 * (size_t)n + 16) + 64;
+	PXB_TRY(ctx->reserve_pinned(bytes_all));
+	PXB_TRY(ctx->partials.reserve(bytes_all));
+	unsigned char *hp = static_cast<unsigned char *>(ctx->pinned);
+	double *cap = reinterpret_cast<double *>(hp), *excess = cap + mm, *sink_cap = excess + n;
+	int32_t *off = reinterpret_cast<int32_t *>(sink_cap + n), *head = off + (n + 1), *rev = head + mm;
 	// CSR by tail, arcs of a node in insertion order
-	std::vector<int32_t> off((size_t)n + 1, 0), head((size_t)std::max(m, 1)), rev((size_t)std::max(m, 1));
-	std::vector<double> cap((size_t)std::max(m, 1));
+	std::fill(off, off + n + 1, 0);
 	for (int p = 0; p < pairs; ++p) {
 		off[g.tail[p] + 1]++;
 		off[g.head[p] + 1]++;
 	}
 	for (int i = 0; i < n; ++i) off[i + 1] += off[i];
-	std::vector<int32_t> fill(off.begin(), off.end() - 1);
+	std::vector<int32_t> fill(off, off + n);
 	for (int p = 0; p < pairs; ++p) {
 		const int a = fill[g.tail[p]]++, b = fill[g.head[p]]++;
 		head[a] = g.head[p];
@@ -255,38 +265,22 @@ static int solve_min_cut(pxb_ctx *ctx, const FlowGraphHost &g, std::vector<uint8
 		cap[b] = g.cap_rev[p];
 		rev[b] = a;
 	}
-	std::vector<double> excess((size_t)n), sink_cap((size_t)n);
-	bool any_source = false, any_sink = false;
+	bool any_sink = false;
 	for (int i = 0; i < n; ++i) {
 		excess[i] = g.tr[i] > 0 ? g.tr[i] : 0.0;
 		sink_cap[i] = g.tr[i] < 0 ? -g.tr[i] : 0.0;
-		any_source |= excess[i] > 0;
 		any_sink |= sink_cap[i] > 0;
 	}
 	if (!any_sink) return PXB_OK; // nothing can reach the sink: everything is SOURCE
-	// device buffers (one arena)
-	const size_t bytes_i = sizeof(int32_t) * ((size_t)n + 1 + 2 * (size_t)std::max(m, 1) + 2 * (size_t)n + 16);
-	const size_t bytes_d = sizeof(double) * (2 * (size_t)std::max(m, 1) + 2 * (size_t)n);
-	PXB_TRY(ctx->partials.reserve(bytes_d + bytes_i + 256));
-	double *d_cap = ctx->partials.as<double>();
-	double *d_pushed = d_cap + std::max(m, 1);
-	double *d_excess = d_pushed + std::max(m, 1);
-	double *d_sink = d_excess + n;
-	int32_t *d_off = reinterpret_cast<int32_t *>(d_sink + n);
-	int32_t *d_head = d_off + (n + 1);
-	int32_t *d_rev = d_head + std::max(m, 1);
-	int32_t *d_h0 = d_rev + std::max(m, 1);
-	int32_t *d_h1 = d_h0 + n;
-	int32_t *d_flags = d_h1 + n;
+	unsigned char *dp = static_cast<unsigned char *>(ctx->partials.ptr);
+	double *d_cap = reinterpret_cast<double *>(dp), *d_excess = d_cap + mm, *d_sink = d_excess + n;
+	int32_t *d_off = reinterpret_cast<int32_t *>(d_sink + n), *d_head = d_off + (n + 1), *d_rev = d_head + mm;
+	int32_t *d_h0 = d_rev + mm, *d_h1 = d_h0 + n, *d_flags = d_h1 + n;
+	int32_t *h_h0 = reinterpret_cast<int32_t *>(hp + bytes_up), *h_flags = h_h0 + 2 * (size_t)n;
 	cudaStream_t st = ctx->stream;
-	PXB_CUDA(cudaMemcpyAsync(d_cap, cap.data(), sizeof(double) * cap.size(), cudaMemcpyHostToDevice, st));
-	PXB_CUDA(cudaMemsetAsync(d_pushed, 0, sizeof(double) * (size_t)std::max(m, 1), st));
-	PXB_CUDA(cudaMemcpyAsync(d_excess, excess.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
-	PXB_CUDA(cudaMemcpyAsync(d_sink, sink_cap.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
-	PXB_CUDA(cudaMemcpyAsync(d_off, off.data(), sizeof(int32_t) * off.size(), cudaMemcpyHostToDevice, st));
-	PXB_CUDA(cudaMemcpyAsync(d_head, head.data(), sizeof(int32_t) * head.size(), cudaMemcpyHostToDevice, st));
-	PXB_CUDA(cudaMemcpyAsync(d_rev, rev.data(), sizeof(int32_t) * rev.size(), cudaMemcpyHostToDevice, st));
+	PXB_CUDA(cudaMemcpyAsync(dp, hp, bytes_up, cudaMemcpyHostToDevice, st));
 	PXB_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int32_t) * 16, st));
+	double *d_pushed = nullptr;
 	FlowGraphDev G;
 	G.n = n;
 	G.m = m;
@@ -300,7 +294,6 @@ static int solve_min_cut(pxb_ctx *ctx, const FlowGraphHost &g, std::vector<uint8
 	G.height[0] = d_h0;
 	G.height[1] = d_h1;
 	G.flags = d_flags;
-	(void)any_source;
 	int blocks_per_sm = 0;
 	PXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_maxflow, kMfThreads, 0));
 	const int want = (n + kMfThreads - 1) / kMfThreads;
@@ -308,10 +301,9 @@ static int solve_min_cut(pxb_ctx *ctx, const FlowGraphHost &g, std::vector<uint8
 	void *args[] = {&G};
 	PXB_CUDA(cudaLaunchCooperativeKernel((void *)k_maxflow, dim3(grid), dim3(kMfThreads), args, 0, st));
 	ctx->launches++;
-	std::vector<int32_t> h((size_t)n);
-	int32_t flags[16];
-	PXB_CUDA(cudaMemcpyAsync(h.data(), d_h0, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
-	PXB_CUDA(cudaMemcpyAsync(flags, d_flags, sizeof(flags), cudaMemcpyDeviceToHost, st));
+	const int32_t *h = h_h0, *flags = h_flags;
+	PXB_CUDA(cudaMemcpyAsync(h_h0, d_h0, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
+	PXB_CUDA(cudaMemcpyAsync(h_flags, d_flags, sizeof(int32_t) * 16, cudaMemcpyDeviceToHost, st));
 	PXB_CUDA(cudaStreamSynchronize(st));
 	if (flags[7] != 1 || flags[6] == 0) {
 		set_error("max-flow did not converge within %d relabel rounds", kMaxRounds);
@@ -323,9 +315,186 @@ static int solve_min_cut(pxb_ctx *ctx, const FlowGraphHost &g, std::vector<uint8
 		static double total_ms = 0;
 		const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
 		total_ms += ms;
-		if (++calls % 20 == 0 || ms > 50)
+		if (++calls % 20 == 0 || ms > 3 || getenv("PXB_MF_STATS")[0] == '2')
 			fprintf(stderr, "[pxb maxflow] call %d: n=%d arcs=%d rounds=%d grid=%d  %.2f ms (total %.1f ms)\n", calls, n, m,
 			        flags[6], grid, ms, total_ms);
+	}
+	return PXB_OK;
+}
+
+// ---- GC-RANSAC local optimisation entirely on the device --------------------------------------------------------
+// GCRANSAC::labeling (gcr/GCRANSAC.h:914-1022) for one model: unary terms (k_lo_unary), the pairwise graph over the
+// FIRST occurrence of every unordered neighbour pair (the reference's used_edges matrix, :964-1010) and the st-cut.
+// The arc skeleton depends on the neighbourhood graph only, so it is built once per graph and cached on the device;
+// per cut only capacities change, and those are computed by k_lo_assemble with the reference's own add_term1 /
+// add_term2 / add_tweights arithmetic: the terminal capacity of node i is a sequential function of i's own pairs.
+struct LoSkeleton {
+	uint64_t key = 0;
+	int64_t N = 0;
+	int pairs = 0;
+	DevBuf buf; // arc_off[N+1] arc_head[m] arc_rev[m] pair_j[p] pair_fwd[p] pair_rev[p] first_off[N+1]
+	int32_t *arc_off = nullptr, *arc_head = nullptr, *arc_rev = nullptr, *pair_j = nullptr, *pair_fwd = nullptr,
+	        *pair_rev = nullptr, *first_off = nullptr;
+};
+static LoSkeleton g_lo; // one process drives one GPU (bench / tests); re-keyed whenever the graph changes
+
+static uint64_t fnv1a(const void *data, size_t bytes, uint64_t h = 1469598103934665603ull) {
+	const unsigned char *p = static_cast<const unsigned char *>(data);
+	for (size_t i = 0; i < bytes; ++i) h = (h ^ p[i]) * 1099511628211ull;
+	return h;
+}
+
+static int lo_skeleton(pxb_ctx *ctx, int64_t N, const int32_t *off, const int32_t *idx) {
+	uint64_t key = fnv1a(off, sizeof(int32_t) * (size_t)(N + 1));
+	key = fnv1a(idx, sizeof(int32_t) * (size_t)off[N], key) ^ ((uint64_t)ctx->device << 56) ^ (uint64_t)N;
+	if (g_lo.key == key && g_lo.N == N && g_lo.buf.ptr) return PXB_OK;
+	std::unordered_set<uint64_t> used;
+	used.reserve((size_t)off[N] * 2);
+	std::vector<int32_t> pi, pj, first_off((size_t)N + 1, 0);
+	for (int64_t i = 0; i < N; ++i) {
+		for (int32_t e = off[i]; e < off[i + 1]; ++e) {
+			const int64_t j = idx[e];
+			if (j == i || j < 0) continue;
+			const uint64_t k2 = (uint64_t)std::min(i, j) * (uint64_t)N + (uint64_t)std::max(i, j);
+			if (!used.insert(k2).second) continue;
+			pi.push_back((int32_t)i);
+			pj.push_back((int32_t)j);
+		}
+		first_off[i + 1] = (int32_t)pi.size(); // pairs whose first endpoint is i are contiguous
+	}
+	const int pairs = (int)pi.size(), m = 2 * pairs;
+	std::vector<int32_t> aoff((size_t)N + 1, 0), head((size_t)std::max(m, 1)), rev((size_t)std::max(m, 1)), pf((size_t)std::max(pairs, 1)),
+	    pr((size_t)std::max(pairs, 1));
+	for (int p = 0; p < pairs; ++p) {
+		aoff[pi[p] + 1]++;
+		aoff[pj[p] + 1]++;
+	}
+	for (int64_t i = 0; i < N; ++i) aoff[i + 1] += aoff[i];
+	std::vector<int32_t> fill(aoff.begin(), aoff.end() - 1);
+	for (int p = 0; p < pairs; ++p) { // same arc order as solve_min_cut's CSR
+		const int a = fill[pi[p]]++, b = fill[pj[p]]++;
+		head[a] = pj[p];
+		rev[a] = b;
+		head[b] = pi[p];
+		rev[b] = a;
+		pf[p] = a;
+		pr[p] = b;
+	}
+	const size_t ints = 2 * ((size_t)N + 1) + 2 * (size_t)std::max(m, 1) + 3 * (size_t)std::max(pairs, 1);
+	PXB_TRY(g_lo.buf.reserve(sizeof(int32_t) * ints));
+	int32_t *b = g_lo.buf.as<int32_t>();
+	g_lo.arc_off = b;
+	g_lo.arc_head = g_lo.arc_off + (N + 1);
+	g_lo.arc_rev = g_lo.arc_head + std::max(m, 1);
+	g_lo.pair_j = g_lo.arc_rev + std::max(m, 1);
+	g_lo.pair_fwd = g_lo.pair_j + std::max(pairs, 1);
+	g_lo.pair_rev = g_lo.pair_fwd + std::max(pairs, 1);
+	g_lo.first_off = g_lo.pair_rev + std::max(pairs, 1);
+	cudaStream_t st = ctx->stream;
+	PXB_CUDA(cudaMemcpyAsync(g_lo.arc_off, aoff.data(), sizeof(int32_t) * aoff.size(), cudaMemcpyHostToDevice, st));
+	PXB_CUDA(cudaMemcpyAsync(g_lo.arc_head, head.data(), sizeof(int32_t) * head.size(), cudaMemcpyHostToDevice, st));
+	PXB_CUDA(cudaMemcpyAsync(g_lo.arc_rev, rev.data(), sizeof(int32_t) * rev.size(), cudaMemcpyHostToDevice, st));
+	PXB_CUDA(cudaMemcpyAsync(g_lo.pair_j, pj.data(), sizeof(int32_t) * (size_t)pairs, cudaMemcpyHostToDevice, st));
+	PXB_CUDA(cudaMemcpyAsync(g_lo.pair_fwd, pf.data(), sizeof(int32_t) * (size_t)pairs, cudaMemcpyHostToDevice, st));
+	PXB_CUDA(cudaMemcpyAsync(g_lo.pair_rev, pr.data(), sizeof(int32_t) * (size_t)pairs, cudaMemcpyHostToDevice, st));
+	PXB_CUDA(cudaMemcpyAsync(g_lo.first_off, first_off.data(), sizeof(int32_t) * first_off.size(), cudaMemcpyHostToDevice, st));
+	PXB_CUDA(cudaStreamSynchronize(st)); // the host vectors go out of scope
+	g_lo.key = key;
+	g_lo.N = N;
+	g_lo.pairs = pairs;
+	return PXB_OK;
+}
+
+// One thread per node: terminal capacity with the reference's add_tweights sequence (gcr/graph.h), n-link capacities
+// of the pairs this node opens. add_term1(i, e0, e1) = add_tweights(i, e1, e0) (gcr/energy.h:204-208); add_term2(i, j,
+// A = e00 lambda, B = lambda, C = lambda, D = 0) = add_tweights(i, 0, A); edge(i -> j) = B - A, edge(j -> i) = C
+// (:210-256; B - A >= 0 because d <= 1).
+__global__ void k_lo_assemble(int64_t N, double lambda, const double *__restrict__ d, const double *__restrict__ e0,
+                              const double *__restrict__ e1, const int32_t *__restrict__ first_off,
+                              const int32_t *__restrict__ pair_j, const int32_t *__restrict__ pair_fwd,
+                              const int32_t *__restrict__ pair_rev, double *__restrict__ cap, double *__restrict__ excess,
+                              double *__restrict__ sink_cap) {
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= N) return;
+	double tr = 0.0;
+	auto add_tweights = [&](double cap_source, double cap_sink) {
+		const double delta = tr;
+		if (delta > 0) cap_source = __dadd_rn(cap_source, delta);
+		else cap_sink = __dsub_rn(cap_sink, delta);
+		tr = __dsub_rn(cap_source, cap_sink);
+	};
+	add_tweights(e1[i], e0[i]);
+	const double di = d[i];
+	for (int32_t p = first_off[i]; p < first_off[i + 1]; ++p) {
+		const double energy_sum = __dadd_rn(di, d[pair_j[p]]);
+		const double A = __dmul_rn(__dmul_rn(0.5, energy_sum), lambda);
+		add_tweights(0.0, A);
+		double B = __dsub_rn(lambda, A), C = lambda; // B -= A; C -= D (= 0 * lambda)
+		if (B < 0) { // unreachable for d in [0, 1]; kept for exactness of the restatement
+			C = __dadd_rn(B, C);
+			B = 0.0;
+		}
+		cap[pair_fwd[p]] = B;
+		cap[pair_rev[p]] = C;
+	}
+	excess[i] = tr > 0 ? tr : 0.0;
+	sink_cap[i] = tr < 0 ? -tr : 0.0;
+}
+
+__global__ void k_lo_collect(int64_t N, const int32_t *__restrict__ h, int n_nodes, uint8_t *__restrict__ seg) {
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < N) seg[i] = h[i] < n_nodes ? 1 : 0;
+}
+
+int launch_lo_unary(pxb_ctx *ctx, const double *model, double thr, double lambda, double *d, double *e0, double *e1);
+
+// model_dev: device pointer to the model; seg_host: N bytes, 1 = inlier (SINK side)
+int lo_labeling_device(pxb_ctx *ctx, const double *model_dev, double thr, double lambda, const int32_t *csr_off_host,
+                       const int32_t *csr_idx_host, uint8_t *seg_host) {
+	const int64_t N = ctx->pts.N;
+	PXB_TRY(lo_skeleton(ctx, N, csr_off_host, csr_idx_host));
+	const int n = (int)N, m = std::max(2 * g_lo.pairs, 1);
+	const size_t bytes = sizeof(double) * ((size_t)m + 5 * (size_t)n) + sizeof(int32_t) * (2 * (size_t)n + 16) + (size_t)n + 256;
+	PXB_TRY(ctx->partials.reserve(bytes));
+	double *d_cap = ctx->partials.as<double>();
+	double *d_excess = d_cap + m, *d_sink = d_excess + n, *d_d = d_sink + n, *d_e0 = d_d + n, *d_e1 = d_e0 + n;
+	int32_t *d_h0 = reinterpret_cast<int32_t *>(d_e1 + n), *d_h1 = d_h0 + n, *d_flags = d_h1 + n;
+	uint8_t *d_seg = reinterpret_cast<uint8_t *>(d_flags + 16);
+	cudaStream_t st = ctx->stream;
+	PXB_TRY(launch_lo_unary(ctx, model_dev, thr, lambda, d_d, d_e0, d_e1));
+	PXB_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int32_t) * 16, st));
+	k_lo_assemble<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(N, lambda, d_d, d_e0, d_e1, g_lo.first_off, g_lo.pair_j,
+	                                                           g_lo.pair_fwd, g_lo.pair_rev, d_cap, d_excess, d_sink);
+	ctx->launches++;
+	FlowGraphDev G;
+	G.n = n;
+	G.m = 2 * g_lo.pairs;
+	G.arc_off = g_lo.arc_off;
+	G.arc_head = g_lo.arc_head;
+	G.arc_rev = g_lo.arc_rev;
+	G.cap = d_cap;
+	G.pushed = nullptr;
+	G.excess = d_excess;
+	G.sink_cap = d_sink;
+	G.height[0] = d_h0;
+	G.height[1] = d_h1;
+	G.flags = d_flags;
+	int blocks_per_sm = 0;
+	PXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_maxflow, kMfThreads, 0));
+	const int want = (n + kMfThreads - 1) / kMfThreads;
+	const int grid = std::max(1, std::min(want, ctx->sm_count * std::max(1, std::min(blocks_per_sm, 4))));
+	void *args[] = {&G};
+	PXB_CUDA(cudaLaunchCooperativeKernel((void *)k_maxflow, dim3(grid), dim3(kMfThreads), args, 0, st));
+	ctx->launches++;
+	k_lo_collect<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(N, d_h0, n, d_seg);
+	ctx->launches++;
+	int32_t flags[16];
+	PXB_CUDA(cudaMemcpyAsync(seg_host, d_seg, (size_t)N, cudaMemcpyDeviceToHost, st));
+	PXB_CUDA(cudaMemcpyAsync(flags, d_flags, sizeof(flags), cudaMemcpyDeviceToHost, st));
+	PXB_CUDA(cudaStreamSynchronize(st));
+	if (flags[7] != 1 || flags[6] == 0) {
+		set_error("max-flow did not converge within %d relabel rounds", kMaxRounds);
+		return PXB_ERR_CUDA;
 	}
 	return PXB_OK;
 }
@@ -384,22 +553,27 @@ int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t
 	P.lambda = lambda;
 	P.label_cost = label_cost;
 	{ // gco adjacency: per site a list built with addFront, so the last inserted neighbour comes first
-		std::vector<std::vector<int32_t>> lists((size_t)N);
+		P.goff.assign((size_t)N + 1, 0);
 		for (int64_t i = 0; i < N; ++i)
 			for (int32_t e = off[i]; e < off[i + 1]; ++e) {
 				const int32_t j = idx[e];
 				if (j == i) continue; // PEARL.h:535
-				lists[i].push_back(j);
-				lists[j].push_back((int32_t)i);
+				P.goff[i + 1]++;
+				P.goff[j + 1]++;
 			}
-		P.goff.assign((size_t)N + 1, 0);
-		for (int64_t i = 0; i < N; ++i) P.goff[i + 1] = P.goff[i] + (int32_t)lists[i].size();
+		for (int64_t i = 0; i < N; ++i) P.goff[i + 1] += P.goff[i];
 		P.gidx.resize((size_t)P.goff[N]);
+		std::vector<int32_t> next(P.goff.begin() + 1, P.goff.end()); // fill every list from its back: reversed push order
 		for (int64_t i = 0; i < N; ++i)
-			std::copy(lists[i].rbegin(), lists[i].rend(), P.gidx.begin() + P.goff[i]);
+			for (int32_t e = off[i]; e < off[i + 1]; ++e) {
+				const int32_t j = idx[e];
+				if (j == i) continue;
+				P.gidx[--next[i]] = j;
+				P.gidx[--next[j]] = (int32_t)i;
+			}
 	}
 
-	double new_energy = compute_energy(P, lab), old_energy;
+	double new_energy = compute_energy(P, lab), old_energy; // always the energy of `lab` (compute_energy is a pure function)
 	std::vector<int32_t> active, lookup((size_t)N, -1);
 	std::vector<uint8_t> seg;
 	for (int cycle = 1; cycle <= 1000; ++cycle) { // GCoptimization.cpp:1062-1077
@@ -474,10 +648,12 @@ int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t
 			if (!any_switch) continue;
 			// the reference applies the move iff afterExpansionEnergy < m_beforeExpansionEnergy (:1286); both are the
 			// energies of the two labellings, evaluated here directly
-			const double before = compute_energy(P, lab), after = compute_energy(P, cand);
-			if (after < before) lab.swap(cand);
+			const double before = new_energy, after = compute_energy(P, cand);
+			if (after < before) {
+				lab.swap(cand);
+				new_energy = after;
+			}
 		}
-		new_energy = compute_energy(P, lab);
 		if (new_energy == old_energy) break;
 	}
 	*energy_out_host = new_energy;
@@ -519,4 +695,20 @@ extern "C" int pxb_lo_graph_cut(pxb_ctx *ctx, const double *e0, const double *e1
 	PXB_TRY(solve_min_cut(ctx, g, seg));
 	std::memcpy(inlier_out, seg.data(), (size_t)N);
 	return PXB_OK;
+}
+
+// GCRANSAC::labeling as a whole (gcr/GCRANSAC.h:914-1022): unary terms, pairwise graph and st-cut without leaving the
+// device. Same result as pxb_lo_unary_terms + pxb_lo_graph_cut.
+extern "C" int pxb_lo_labeling(pxb_ctx *ctx, const double *model_host, double thr, double lambda, const int32_t *csr_off,
+                               const int32_t *csr_idx, uint8_t *inlier_out) {
+	PXB_CHECK_ARG(ctx && model_host && csr_off && csr_idx && inlier_out, "null argument");
+	if (ctx->pts.N <= 0) {
+		set_error("no points uploaded");
+		return PXB_ERR_STATE;
+	}
+	PXB_CUDA(cudaSetDevice(ctx->device));
+	const int ms = model_size(ctx->pts.type);
+	PXB_TRY(ctx->models.reserve(sizeof(double) * ms));
+	PXB_CUDA(cudaMemcpyAsync(ctx->models.ptr, model_host, sizeof(double) * ms, cudaMemcpyHostToDevice, ctx->stream));
+	return lo_labeling_device(ctx, ctx->models.as<double>(), thr, lambda, csr_off, csr_idx, inlier_out);
 }

@@ -86,7 +86,7 @@ struct pxb_ctx {
 	int64_t launches = 0;
 	pxb::Points pts;
 	// scratch
-	pxb::DevBuf models, pref, pref2, outA, outB, outC, outD, idx, mask, partials, staging, screen;
+	pxb::DevBuf models, pref, pref2, outA, outB, outC, outD, idx, mask, partials, staging, screen, stats;
 	void *pinned = nullptr;
 	size_t pinned_cap = 0;
 	int reserve_pinned(size_t bytes);

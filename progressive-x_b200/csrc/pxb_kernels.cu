@@ -34,11 +34,15 @@ namespace pxb {
 // AoS -> SoA re-tiling of the uploaded points
 // ------------------------------------------------------------------------------------------------
 // Bounding box of the finite coordinates -> NormDev (centre + common scale) for the float32 screening copy.
-__global__ void __launch_bounds__(1024) k_point_stats(const double *__restrict__ aos, int64_t N, int dim, int type, NormDev *out) {
-	__shared__ double s_lo[32][5], s_hi[32][5];
+// Two tiny launches: per-block partial boxes over a grid-strided slice, then one warp folds them.
+constexpr int kStatBlocks = 64, kStatThreads = 256;
+
+__global__ void __launch_bounds__(kStatThreads)
+    k_point_stats(const double *__restrict__ aos, int64_t N, int dim, double *__restrict__ partial /*[blocks][10]*/) {
+	__shared__ double s_lo[kStatThreads / 32][5], s_hi[kStatThreads / 32][5];
 	double lo[5], hi[5];
 	for (int c = 0; c < 5; ++c) lo[c] = 1e300, hi[c] = -1e300;
-	for (int64_t i = threadIdx.x; i < N; i += blockDim.x)
+	for (int64_t i = (int64_t)blockIdx.x * kStatThreads + threadIdx.x; i < N; i += (int64_t)gridDim.x * kStatThreads)
 		for (int c = 0; c < dim; ++c) {
 			const double v = aos[i * dim + c];
 			if (fabs(v) <= 1e300) lo[c] = fmin(lo[c], v), hi[c] = fmax(hi[c], v);
@@ -51,29 +55,38 @@ __global__ void __launch_bounds__(1024) k_point_stats(const double *__restrict__
 	if ((threadIdx.x & 31) == 0)
 		for (int c = 0; c < 5; ++c) s_lo[threadIdx.x >> 5][c] = lo[c], s_hi[threadIdx.x >> 5][c] = hi[c];
 	__syncthreads();
-	if (threadIdx.x == 0) {
-		NormDev nd;
-		double s = 0.0;
-		double L[5], Hh[5];
-		for (int c = 0; c < 5; ++c) {
-			L[c] = 1e300, Hh[c] = -1e300;
-			for (int w = 0; w < 32; ++w) L[c] = fmin(L[c], s_lo[w][c]), Hh[c] = fmax(Hh[c], s_hi[w][c]);
-		}
-		if (type == PXB_MODEL_VANISHING_POINT) // both end points of a segment live in the same image: one centre
-			for (int c = 0; c < 2; ++c) {
-				L[c] = L[c + 2] = fmin(L[c], L[c + 2]);
-				Hh[c] = Hh[c + 2] = fmax(Hh[c], Hh[c + 2]);
-			}
-		for (int c = 0; c < 5; ++c) {
-			const double l = L[c], h = Hh[c];
-			const bool used = c < dim && !(type == PXB_MODEL_PNP && c < 2) && l <= h;
-			nd.c[c] = used ? 0.5 * (l + h) : 0.0;
-			if (used) s = fmax(s, 0.5 * (h - l));
-		}
-		nd.s = (s > 1e-300 && s < 1e300) ? s : 1.0;
-		nd.inv_s = 1.0 / nd.s;
-		*out = nd;
+	if (threadIdx.x < 5) {
+		const int c = threadIdx.x;
+		double l = 1e300, h = -1e300;
+		for (int w = 0; w < kStatThreads / 32; ++w) l = fmin(l, s_lo[w][c]), h = fmax(h, s_hi[w][c]);
+		partial[blockIdx.x * 10 + c] = l;
+		partial[blockIdx.x * 10 + 5 + c] = h;
 	}
+}
+
+__global__ void k_point_norm(const double *__restrict__ partial, int blocks, int dim, int type, NormDev *out) {
+	if (threadIdx.x != 0) return;
+	double L[5], Hh[5];
+	for (int c = 0; c < 5; ++c) {
+		L[c] = 1e300, Hh[c] = -1e300;
+		for (int b = 0; b < blocks; ++b) L[c] = fmin(L[c], partial[b * 10 + c]), Hh[c] = fmax(Hh[c], partial[b * 10 + 5 + c]);
+	}
+	if (type == PXB_MODEL_VANISHING_POINT) // both end points of a segment live in the same image: one centre
+		for (int c = 0; c < 2; ++c) {
+			L[c] = L[c + 2] = fmin(L[c], L[c + 2]);
+			Hh[c] = Hh[c + 2] = fmax(Hh[c], Hh[c + 2]);
+		}
+	NormDev nd;
+	double s = 0.0;
+	for (int c = 0; c < 5; ++c) {
+		const double l = L[c], h = Hh[c];
+		const bool used = c < dim && !(type == PXB_MODEL_PNP && c < 2) && l <= h;
+		nd.c[c] = used ? 0.5 * (l + h) : 0.0;
+		if (used) s = fmax(s, 0.5 * (h - l));
+	}
+	nd.s = (s > 1e-300 && s < 1e300) ? s : 1.0;
+	nd.inv_s = 1.0 / nd.s;
+	*out = nd;
 }
 
 __global__ void k_aos_to_soa(const double *__restrict__ aos, double *__restrict__ soa, float *__restrict__ f32n,
@@ -92,8 +105,11 @@ __global__ void k_aos_to_soa(const double *__restrict__ aos, double *__restrict_
 
 int launch_aos_to_soa(pxb_ctx *ctx) {
 	Points &p = ctx->pts;
-	k_point_stats<<<1, 1024, 0, ctx->stream>>>(p.aos, p.N, p.dim, p.type, p.norm);
-	ctx->launches++;
+	const int blocks = (int)std::min<int64_t>(kStatBlocks, (p.N + kStatThreads - 1) / kStatThreads);
+	PXB_TRY(ctx->stats.reserve(sizeof(double) * 10 * kStatBlocks));
+	k_point_stats<<<blocks, kStatThreads, 0, ctx->stream>>>(p.aos, p.N, p.dim, ctx->stats.as<double>());
+	k_point_norm<<<1, 32, 0, ctx->stream>>>(ctx->stats.as<double>(), blocks, p.dim, p.type, p.norm);
+	ctx->launches += 2;
 	const int grid = (int)((p.stride + kThreads - 1) / kThreads);
 	k_aos_to_soa<<<grid, kThreads, 0, ctx->stream>>>(p.aos, p.soa, p.f32n, p.q, p.norm, p.N, p.stride, p.dim, p.type);
 	ctx->launches++;

@@ -81,6 +81,7 @@ def load_library() -> C.CDLL:
     lib.pxb_tukey_weights.argtypes = [vp, vp, f64, vp]
     lib.pxb_selftest_division.argtypes = [vp, u64, i64, C.c_int, C.POINTER(i64)]
     lib.pxb_lo_graph_cut.argtypes = [vp, vp, vp, vp, i64, f64, vp, vp, vp]
+    lib.pxb_lo_labeling.argtypes = [vp, vp, f64, f64, vp, vp, vp]
     lib.pxb_knn_graph.argtypes = [vp, f64, C.c_int, vp, vp]
     lib.pxb_fit_homographies.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     lib.pxb_fit_nonminimal.argtypes = [vp, i32, vp, vp, vp, vp, vp]
@@ -297,6 +298,15 @@ class Context:
         out = np.zeros(e0.shape[0], dtype=np.uint8)
         _check(self.lib.pxb_lo_graph_cut(self.handle, _ptr(e0), _ptr(e1), _ptr(d), e0.shape[0], float(lam), _ptr(off),
                                          _ptr(idx), _ptr(out)))
+        return out
+
+    def lo_labeling(self, model, thr: float, lam: float, csr_off, csr_idx) -> np.ndarray:
+        """GCRANSAC::labeling in one device-resident call (unary terms + pairwise graph + st-cut)."""
+        m, _ = self._models(model)
+        off = np.ascontiguousarray(csr_off, dtype=np.int32)
+        idx = np.ascontiguousarray(csr_idx, dtype=np.int32)
+        out = np.zeros(self.N, dtype=np.uint8)
+        _check(self.lib.pxb_lo_labeling(self.handle, _ptr(m), float(thr), float(lam), _ptr(off), _ptr(idx), _ptr(out)))
         return out
 
     # -- next rows -----------------------------------------------------------------------------------------

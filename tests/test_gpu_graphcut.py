@@ -74,6 +74,11 @@ def test_lo_graph_cut_matches_reference_bk(ctx, oracle, seed, lam):
     seg_o, _ = oracle.gco_lo_labeling(e0, e1, d, lam, off, idx)
     assert np.array_equal(seg, seg_o)
     assert 0 < seg.sum() < N
+    # the device-resident form (unary terms, graph capacities and cut without leaving the GPU; cached arc skeleton)
+    assert np.array_equal(ctx.lo_labeling(model, 2.0, lam, off, idx), seg_o)
+    other = Hs[(seed + 1) % 3].reshape(-1)  # second model on the same (cached) skeleton
+    d2, e02, e12 = oracle.lo_unary_terms(H, pts, other, 2.0, lam)
+    assert np.array_equal(ctx.lo_labeling(other, 2.0, lam, off, idx), oracle.gco_lo_labeling(e02, e12, d2, lam, off, idx)[0])
 
 
 def test_knn_graph_matches_kdtree(ctx):
