@@ -46,6 +46,7 @@ static int require_points(pxb_ctx *ctx) {
 		set_error("no points uploaded: call pxb_upload_points first");
 		return PXB_ERR_STATE;
 	}
+	PXB_CUDA(cudaSetDevice(ctx->device)); // entry points may be called from any host thread
 	return PXB_OK;
 }
 
@@ -130,6 +131,7 @@ void pxb_ctx_destroy(pxb_ctx *ctx) {
 	                  &ctx->outD,   &ctx->idx,  &ctx->mask,  &ctx->partials, &ctx->staging, &ctx->screen, &ctx->stats};
 	for (DevBuf *b : bufs) b->release();
 	if (ctx->pinned) cudaFreeHost(ctx->pinned);
+	lo_skeleton_free(ctx->lo_skeleton);
 	cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }
@@ -138,6 +140,7 @@ void *pxb_ctx_stream(pxb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr;
 
 int pxb_sync(pxb_ctx *ctx) {
 	PXB_CHECK_ARG(ctx != nullptr, "null context");
+	PXB_CUDA(cudaSetDevice(ctx->device));
 	return sync(ctx);
 }
 
@@ -156,11 +159,13 @@ int pxb_dev_free(pxb_ctx *ctx, void *dev_ptr) {
 }
 int pxb_memcpy_h2d(pxb_ctx *ctx, void *dev_dst, const void *host_src, size_t bytes) {
 	PXB_CHECK_ARG(ctx && dev_dst && host_src, "null argument");
+	PXB_CUDA(cudaSetDevice(ctx->device));
 	PXB_TRY(h2d(ctx, dev_dst, host_src, bytes));
 	return sync(ctx);
 }
 int pxb_memcpy_d2h(pxb_ctx *ctx, void *host_dst, const void *dev_src, size_t bytes) {
 	PXB_CHECK_ARG(ctx && host_dst && dev_src, "null argument");
+	PXB_CUDA(cudaSetDevice(ctx->device));
 	PXB_TRY(d2h(ctx, host_dst, dev_src, bytes));
 	return sync(ctx);
 }
@@ -327,6 +332,7 @@ int pxb_preference_vector(pxb_ctx *ctx, const double *model_host, double T, doub
 
 int pxb_tanimoto(pxb_ctx *ctx, const double *a_host, const double *b_host, int64_t N, double *similarity) {
 	PXB_CHECK_ARG(ctx && a_host && b_host && similarity && N > 0, "null argument");
+	PXB_CUDA(cudaSetDevice(ctx->device));
 	PXB_TRY(ctx->pref.reserve(sizeof(double) * (size_t)N));
 	PXB_TRY(ctx->pref2.reserve(sizeof(double) * (size_t)N));
 	PXB_TRY(ctx->outA.reserve(sizeof(double) * 3));
@@ -343,6 +349,7 @@ int pxb_tanimoto(pxb_ctx *ctx, const double *a_host, const double *b_host, int64
 
 int pxb_compound_max(pxb_ctx *ctx, const double *prefs_host, int64_t L, int64_t N, double *out_host) {
 	PXB_CHECK_ARG(ctx && prefs_host && out_host && L >= 0 && N > 0, "null argument");
+	PXB_CUDA(cudaSetDevice(ctx->device));
 	PXB_TRY(ctx->staging.reserve(sizeof(double) * (size_t)std::max<int64_t>(L, 1) * N));
 	PXB_TRY(ctx->pref.reserve(sizeof(double) * (size_t)N));
 	PXB_TRY(h2d(ctx, ctx->staging.ptr, prefs_host, sizeof(double) * (size_t)L * N));

@@ -280,6 +280,7 @@ class Driver {
 };
 
 int Driver::build_graph(double radius, int k) {
+	PXB_CUDA(cudaSetDevice(ctx_->device));
 	std::vector<int32_t> nbr((size_t)N_ * k), deg((size_t)N_);
 	PXB_TRY(ctx_->idx.reserve(sizeof(int32_t) * (size_t)N_ * (k + 1)));
 	int32_t *d_nbr = ctx_->idx.as<int32_t>(), *d_deg = d_nbr + (size_t)N_ * k;
@@ -743,6 +744,7 @@ size_t Driver::predicted_unseen_inliers(size_t iterations, size_t compound_inlie
 
 // px/include/progressive_x.h:251-489
 int Driver::run() {
+	PXB_CUDA(cudaSetDevice(ctx_->device)); // the driver launches kernels directly as well: bind this host thread
 	labeling_.assign((size_t)N_, 0);
 	compound_pref_.assign((size_t)N_, 0.0);
 	models_.clear();

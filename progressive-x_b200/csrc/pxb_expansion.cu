@@ -45,6 +45,8 @@ namespace pxb {
 
 struct FlowGraphDev {
 	int n, m;
+	int wide_begin, wide_count; // nodes [wide_begin, wide_begin + wide_count) are label-cost auxiliary nodes: thousands
+	                            // of arcs each, handled by a whole thread block instead of one owner thread
 	const int32_t *arc_off, *arc_head, *arc_rev;
 	double *cap, *pushed, *excess, *sink_cap;
 	int32_t *height[2];
@@ -68,7 +70,7 @@ __device__ void mf_global_relabel(const FlowGraphDev &G, int32_t *h, cg::grid_gr
 	for (int level = 1; level < n; ++level) {
 		int32_t *changed = &G.flags[level % 3];
 		bool mine = false;
-		for (int u = tid; u < n; u += nthreads) {
+		for (int u = tid; u < G.wide_begin; u += nthreads) {
 			if (h[u] != n) continue;
 			for (int a = G.arc_off[u]; a < G.arc_off[u + 1]; ++a)
 				if (G.cap[a] > 0.0 && h[G.arc_head[a]] == level) {
@@ -76,6 +78,22 @@ __device__ void mf_global_relabel(const FlowGraphDev &G, int32_t *h, cg::grid_gr
 					mine = true;
 					break;
 				}
+		}
+		for (int w = blockIdx.x; w < G.wide_count; w += gridDim.x) { // block-cooperative scan of a wide node's arcs
+			const int u = G.wide_begin + w;
+			__shared__ int s_hu;
+			if (threadIdx.x == 0) s_hu = h[u];
+			__syncthreads();
+			const bool open = s_hu == n;
+			int found = 0;
+			if (open)
+				for (int a = G.arc_off[u] + threadIdx.x; a < G.arc_off[u + 1] && !found; a += blockDim.x)
+					found = (G.cap[a] > 0.0 && h[G.arc_head[a]] == level);
+			found = __syncthreads_or(found);
+			if (found && threadIdx.x == 0) {
+				h[u] = level + 1;
+				mine = true;
+			}
 		}
 		if (mine) *changed = 1;
 		if (tid == 0) G.flags[(level + 1) % 3] = 0;
@@ -153,6 +171,89 @@ __device__ __forceinline__ void mf_process(const FlowGraphDev &G, volatile int32
 	}
 }
 
+// Block-cooperative discharge of one wide node: every thread looks at a strided share of the arcs, the node's excess is
+// handed out in arc order by a block-wide exclusive prefix sum of the eligible capacities (lower residual neighbours),
+// and the node is lifted when excess remains after every lower neighbour has been saturated. Same rule as the
+// single-thread wide branch of mf_process, ~100x fewer dependent memory round trips per visit.
+__device__ void mf_process_wide_block(const FlowGraphDev &G, volatile int32_t *h, int u) {
+	__shared__ double s_e, s_wsum[kMfThreads / 32], s_gsum[kMfThreads / 32];
+	__shared__ int s_hu, s_wlow[kMfThreads / 32];
+	const int n = G.n, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	volatile double *excess = G.excess, *cap = G.cap;
+	if (threadIdx.x == 0) {
+		s_e = excess[u];
+		s_hu = h[u];
+	}
+	__syncthreads();
+	const double e = s_e;
+	const int hu = s_hu;
+	if (!(e > 0.0) || hu >= n) return; // block-uniform
+	const int a0 = G.arc_off[u], a1 = G.arc_off[u + 1];
+	double rem = e, given = 0.0;
+	int lowest = 0x7fffffff;
+	for (int base = a0; base < a1; base += kMfThreads) { // block-uniform trip count
+		const int a = base + threadIdx.x;
+		double want = 0.0;
+		int v = 0;
+		if (a < a1) {
+			const double c = cap[a];
+			if (c > 0.0) {
+				v = G.arc_head[a];
+				const int hv = h[v];
+				if (hv < hu) want = c;
+				else lowest = min(lowest, hv);
+			}
+		}
+		double incl = want;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const double t = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= o) incl += t;
+		}
+		if (lane == 31) s_wsum[warp] = incl;
+		__syncthreads();
+		double before = 0.0, total = 0.0;
+#pragma unroll
+		for (int w = 0; w < kMfThreads / 32; ++w) {
+			if (w < warp) before += s_wsum[w];
+			total += s_wsum[w];
+		}
+		const double excl = before + incl - want;
+		const double give = fmin(want, fmax(0.0, rem - excl));
+		if (give > 0.0) {
+			atomicAdd(&G.cap[a], -give);
+			atomicAdd(&G.cap[G.arc_rev[a]], give);
+			atomicAdd(&G.excess[v], give);
+		}
+		given += give;
+		rem = fmax(0.0, rem - total);
+		__syncthreads(); // s_wsum is reused by the next chunk
+		if (!(rem > 0.0)) break; // block-uniform
+	}
+	// what left the node, and the lowest neighbour that is still residual but not lower
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		given += __shfl_xor_sync(0xffffffffu, given, o);
+		lowest = min(lowest, __shfl_xor_sync(0xffffffffu, lowest, o));
+	}
+	if (lane == 0) {
+		s_gsum[warp] = given;
+		s_wlow[warp] = lowest;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		double g = 0.0;
+		int low = 0x7fffffff;
+		for (int w = 0; w < kMfThreads / 32; ++w) {
+			g += s_gsum[w];
+			low = min(low, s_wlow[w]);
+		}
+		if (g > 0.0) atomicAdd(&G.excess[u], -fmin(g, e));
+		if (rem > 0.0) h[u] = low == 0x7fffffff ? n : min(max(low + 1, hu), n);
+	}
+	__syncthreads();
+}
+
 constexpr int kAsyncCycles = 192;
 constexpr int kMaxRounds = 100000;
 
@@ -173,8 +274,10 @@ __global__ void __launch_bounds__(kMfThreads) k_maxflow(FlowGraphDev G) {
 		grid.sync();
 		if (G.flags[3 + (round % 3)] == 0) break;
 		// asynchronous phase: no barriers, every thread keeps discharging its own nodes
-		for (int c = 0; c < kAsyncCycles; ++c)
-			for (int u = tid; u < n; u += nthreads) mf_process(G, h, u);
+		for (int c = 0; c < kAsyncCycles; ++c) {
+			for (int w = blockIdx.x; w < G.wide_count; w += gridDim.x) mf_process_wide_block(G, h, G.wide_begin + w);
+			for (int u = tid; u < G.wide_begin; u += nthreads) mf_process(G, h, u);
+		}
 		__threadfence();
 		grid.sync();
 	}
@@ -230,7 +333,7 @@ struct FlowGraphHost {
 };
 
 // Solve the cut on the device. segment[i] = 1 iff node i ends on the SINK side (BK rule).
-static int solve_min_cut(pxb_ctx *ctx, const FlowGraphHost &g, std::vector<uint8_t> &segment) {
+static int solve_min_cut(pxb_ctx *ctx, const FlowGraphHost &g, std::vector<uint8_t> &segment, int n_sites = -1) {
 	const auto t_begin = std::chrono::steady_clock::now();
 	const int n = g.n;
 	const int pairs = (int)g.tail.size();
@@ -284,6 +387,8 @@ static int solve_min_cut(pxb_ctx *ctx, const FlowGraphHost &g, std::vector<uint8
 	FlowGraphDev G;
 	G.n = n;
 	G.m = m;
+	G.wide_begin = n_sites >= 0 ? n_sites : n;
+	G.wide_count = n - G.wide_begin;
 	G.arc_off = d_off;
 	G.arc_head = d_head;
 	G.arc_rev = d_rev;
@@ -336,7 +441,6 @@ struct LoSkeleton {
 	int32_t *arc_off = nullptr, *arc_head = nullptr, *arc_rev = nullptr, *pair_j = nullptr, *pair_fwd = nullptr,
 	        *pair_rev = nullptr, *first_off = nullptr;
 };
-static LoSkeleton g_lo; // one process drives one GPU (bench / tests); re-keyed whenever the graph changes
 
 static uint64_t fnv1a(const void *data, size_t bytes, uint64_t h = 1469598103934665603ull) {
 	const unsigned char *p = static_cast<const unsigned char *>(data);
@@ -344,7 +448,17 @@ static uint64_t fnv1a(const void *data, size_t bytes, uint64_t h = 1469598103934
 	return h;
 }
 
+void lo_skeleton_free(void *p) {
+	if (!p) return;
+	LoSkeleton *sk = static_cast<LoSkeleton *>(p);
+	sk->buf.release();
+	delete sk;
+}
+
+// the skeleton lives in the context (one per context: contexts may be driven by different host threads)
 static int lo_skeleton(pxb_ctx *ctx, int64_t N, const int32_t *off, const int32_t *idx) {
+	if (!ctx->lo_skeleton) ctx->lo_skeleton = new LoSkeleton();
+	LoSkeleton &g_lo = *static_cast<LoSkeleton *>(ctx->lo_skeleton);
 	uint64_t key = fnv1a(off, sizeof(int32_t) * (size_t)(N + 1));
 	key = fnv1a(idx, sizeof(int32_t) * (size_t)off[N], key) ^ ((uint64_t)ctx->device << 56) ^ (uint64_t)N;
 	if (g_lo.key == key && g_lo.N == N && g_lo.buf.ptr) return PXB_OK;
@@ -453,6 +567,7 @@ int lo_labeling_device(pxb_ctx *ctx, const double *model_dev, double thr, double
                        const int32_t *csr_idx_host, uint8_t *seg_host) {
 	const int64_t N = ctx->pts.N;
 	PXB_TRY(lo_skeleton(ctx, N, csr_off_host, csr_idx_host));
+	const LoSkeleton &g_lo = *static_cast<LoSkeleton *>(ctx->lo_skeleton);
 	const int n = (int)N, m = std::max(2 * g_lo.pairs, 1);
 	const size_t bytes = sizeof(double) * ((size_t)m + 5 * (size_t)n) + sizeof(int32_t) * (2 * (size_t)n + 16) + (size_t)n + 256;
 	PXB_TRY(ctx->partials.reserve(bytes));
@@ -469,6 +584,8 @@ int lo_labeling_device(pxb_ctx *ctx, const double *model_dev, double thr, double
 	FlowGraphDev G;
 	G.n = n;
 	G.m = 2 * g_lo.pairs;
+	G.wide_begin = n;
+	G.wide_count = 0;
 	G.arc_off = g_lo.arc_off;
 	G.arc_head = g_lo.arc_head;
 	G.arc_rev = g_lo.arc_rev;
@@ -635,7 +752,7 @@ int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t
 						g.cap_rev[pidx] = std::min(g.cap_rev[pidx], bound);
 					}
 			}
-			PXB_TRY(solve_min_cut(ctx, g, seg));
+			PXB_TRY(solve_min_cut(ctx, g, seg, size));
 			// candidate labelling: SOURCE side (get_var == 0) takes alpha (:451-469)
 			bool any_switch = false;
 			std::vector<int32_t> cand = lab;

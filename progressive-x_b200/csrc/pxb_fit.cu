@@ -258,6 +258,7 @@ using namespace pxb;
 
 int pxb_knn_graph(pxb_ctx *ctx, double radius, int k, int32_t *nbr_out_host, int32_t *deg_out_host) {
 	PXB_CHECK_ARG(ctx && nbr_out_host && deg_out_host, "null argument");
+	PXB_CUDA(cudaSetDevice(ctx->device));
 	if (ctx->pts.N <= 0) {
 		set_error("no points uploaded");
 		return PXB_ERR_STATE;
@@ -276,6 +277,7 @@ int pxb_fit_nonminimal(pxb_ctx *ctx, int32_t P, const int32_t *off_host, const i
                        const double *weights_by_row_host, double *H_out_host, int32_t *ok_out_host) {
 	PXB_CHECK_ARG(ctx && off_host && idx_host && H_out_host && ok_out_host && P >= 0, "null argument");
 	if (P == 0) return PXB_OK;
+	PXB_CUDA(cudaSetDevice(ctx->device));
 	if (ctx->pts.N <= 0) {
 		set_error("no points uploaded");
 		return PXB_ERR_STATE;

@@ -89,10 +89,12 @@ struct pxb_ctx {
 	pxb::DevBuf models, pref, pref2, outA, outB, outC, outD, idx, mask, partials, staging, screen, stats;
 	void *pinned = nullptr;
 	size_t pinned_cap = 0;
+	void *lo_skeleton = nullptr; // pxb_expansion.cu: cached arc skeleton of the last neighbourhood graph
 	int reserve_pinned(size_t bytes);
 };
 
 namespace pxb {
+void lo_skeleton_free(void *p);
 // kernel launchers (device pointers, asynchronous on ctx->stream)
 int launch_residual_matrix(pxb_ctx *ctx, const double *models, int64_t K, double T2, double *r2, float *r2f,
                            uint32_t *mask);

@@ -551,6 +551,7 @@ __global__ void k_selftest_division(uint64_t seed, int iters, int mode, unsigned
 extern "C" int pxb_selftest_division(pxb_ctx *ctx, uint64_t seed, int64_t n_triples, int mode, int64_t *mismatches) {
 	using namespace pxb;
 	PXB_CHECK_ARG(ctx && mismatches && n_triples > 0, "null argument");
+	PXB_CUDA(cudaSetDevice(ctx->device));
 	PXB_TRY(ctx->outA.reserve(sizeof(unsigned long long)));
 	PXB_CUDA(cudaMemsetAsync(ctx->outA.ptr, 0, sizeof(unsigned long long), ctx->stream));
 	const int threads = 256, blocks = 148 * 8;

@@ -77,26 +77,90 @@ def findTwoViewMotions(corrs, w1, h1, w2, h2, threshold=4.0, conf=0.5, spatial_c
 findFundamentalMatrices = findTwoViewMotions
 
 
-def findHomographiesBatch(pairs, w1, h1, w2, h2, distributed=False, **kwargs):
+def findHomographiesBatch(pairs, w1, h1, w2, h2, distributed=False, workers=8, **kwargs):
     """BASELINE config C4: many independent image pairs. `pairs` is a list of [N_p, 4] correspondence arrays.
+
+    One fit is a chain of ~200 short kernels separated by host decisions, so a single problem leaves the GPU mostly
+    idle. Independent problems are therefore run CONCURRENTLY: `workers` host threads, each with its own context (own
+    CUDA stream and scratch), pull pairs from a queue; ctypes releases the GIL for the duration of every C call.
+    Results are identical to the sequential loop (every problem only depends on its own data and seed).
     With distributed=True (inside a torch.distributed job, one process per GPU) pair p is solved on rank p mod world
     and the surviving instances of every pair are all-gathered (sharding.gather_instances); every rank returns the
     full list [(models, labeling), ...]. Pairs must then share one N (padding is the caller's business)."""
+    dev = kwargs.get("device", 0)
+
+    def solve_many(indices):
+        if not indices:
+            return {}
+        n_workers = max(1, min(int(workers), len(indices)))
+        if n_workers == 1:
+            return {p: findHomographies(pairs[p], w1, h1, w2, h2, **kwargs) for p in indices}
+        import queue
+        import threading
+        todo = queue.SimpleQueue()
+        for p in indices:
+            todo.put(p)
+        out, errors = {}, []
+
+        def work():
+            ctx = Context(dev)  # one context per worker thread
+            try:
+                while True:
+                    try:
+                        p = todo.get_nowait()
+                    except queue.Empty:
+                        return
+                    out[p] = _find_with_context(ctx, pairs[p], w1, h1, w2, h2, **kwargs)
+            except Exception as e:  # surfaced after the join
+                errors.append(e)
+            finally:
+                ctx.close()
+
+        threads = [threading.Thread(target=work) for _ in range(n_workers)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        return out
+
     if not distributed:
-        return [findHomographies(c, w1, h1, w2, h2, **kwargs) for c in pairs]
+        res = solve_many(list(range(len(pairs))))
+        return [res[p] for p in range(len(pairs))]
     import torch
     import torch.distributed as dist
     from . import sharding
     rank, world = dist.get_rank(), dist.get_world_size()
     n_points = int(pairs[0].shape[0])
-    dev = kwargs.get("device", 0)
-    local = []
-    for p in sharding.pairs_of_rank(len(pairs), rank, world):
-        m, lab = findHomographies(pairs[p], w1, h1, w2, h2, **kwargs)
-        local.append((p, m.reshape(-1, 9), lab))
+    mine = list(sharding.pairs_of_rank(len(pairs), rank, world))
+    res = solve_many(mine)
+    local = [(p, res[p][0].reshape(-1, 9), res[p][1]) for p in mine]
     tdev = torch.device("cuda", dev) if dist.get_backend() == "nccl" else None
     gathered = sharding.gather_instances(local, len(pairs), n_points, 9, 10, tdev)
     return [(m.reshape(-1, 3), lab) for m, lab in gathered]
+
+
+def _find_with_context(ctx, corrs, w1, h1, w2, h2, threshold=4.0, conf=0.5, spatial_coherence_weight=0.0,
+                       neighborhood_ball_radius=200.0, maximum_tanimoto_similarity=0.4, max_iters=1000,
+                       minimum_point_number=10, maximum_model_number=-1, sampler_id=3, scoring_exponent=2,
+                       do_logging=False, seed=0, device=0):
+    """findHomographies on an explicit context (used by the concurrent batch)."""
+    corrs = _np.ascontiguousarray(corrs, dtype=_np.float64)
+    if corrs.ndim != 2 or corrs.shape[1] != 4 or corrs.shape[0] < 4:
+        raise ValueError("corrs should be an array with dims [n,4], n>=4")
+    N = corrs.shape[0]
+    labeling = _np.zeros(N, dtype=_np.int64)
+    cap = 16
+    models = _np.zeros((cap, 9), dtype=_np.float64)
+    rc = ctx.lib.pxb_find_homographies(ctx.handle, corrs.ctypes.data_as(_C.c_void_p), N, labeling.ctypes.data_as(_C.c_void_p),
+                                       models.ctypes.data_as(_C.c_void_p), cap, int(w1), int(h1), int(w2), int(h2),
+                                       float(spatial_coherence_weight), float(threshold), float(conf),
+                                       float(neighborhood_ball_radius), float(maximum_tanimoto_similarity), int(max_iters),
+                                       int(minimum_point_number), int(maximum_model_number), int(sampler_id),
+                                       float(scoring_exponent), int(bool(do_logging)), int(seed))
+    M = _native._check(rc)
+    return models[:M].reshape(M * 3, 3).copy(), labeling.astype(_np.int32)
 
 
 def find6DPoses(x1y1, x2y2z2, K, threshold=4.0, conf=0.90, spatial_coherence_weight=0.1,

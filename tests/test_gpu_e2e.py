@@ -77,9 +77,13 @@ def test_batched_pairs_config_c4():
         c, gt, _ = syn.multi_homography_scene(1500, n_planes=2 + p % 2, outlier_ratio=0.4, seed=300 + p)
         pairs.append(c)
         gts.append(gt)
-    out = pyprogressivex.findHomographiesBatch(pairs, 1024, 768, 1024, 768, threshold=2.0, conf=0.95, max_iters=1000,
-                                               minimum_point_number=60, sampler_id=0, seed=9)
+    kw = dict(threshold=2.0, conf=0.95, max_iters=1000, minimum_point_number=60, sampler_id=0, seed=9)
+    out = pyprogressivex.findHomographiesBatch(pairs, 1024, 768, 1024, 768, workers=4, **kw)
     assert len(out) == 6
+    # concurrent workers (own context / stream each) return exactly what the sequential loop returns
+    seq = pyprogressivex.findHomographiesBatch(pairs, 1024, 768, 1024, 768, workers=1, **kw)
+    for (ma, la), (mb, lb) in zip(out, seq):
+        assert np.array_equal(ma.view(np.uint64), mb.view(np.uint64)) and np.array_equal(la, lb)
     for (models, labels), gt, p in zip(out, gts, range(6)):
         M = models.shape[0] // 3
         assert M >= 2 + p % 2
