@@ -37,11 +37,18 @@ void DevBuf::release() {
 
 int launch_aos_to_soa(pxb_ctx *ctx);
 
+// drops whatever a previous, failed call may have left in the staging arena
+static void begin_call(pxb_ctx *ctx) {
+	ctx->pending.clear();
+	ctx->stage_used = 0;
+}
+
 static int require_points(pxb_ctx *ctx) {
 	if (!ctx) {
 		set_error("null context");
 		return PXB_ERR_ARGUMENT;
 	}
+	begin_call(ctx);
 	if (ctx->pts.N <= 0 || !ctx->pts.soa) {
 		set_error("no points uploaded: call pxb_upload_points first");
 		return PXB_ERR_STATE;
@@ -50,18 +57,42 @@ static int require_points(pxb_ctx *ctx) {
 	return PXB_OK;
 }
 
+constexpr size_t kStageBytes = size_t(4) << 20, kStageMaxItem = size_t(256) << 10; // larger payloads go direct
+
+static unsigned char *stage_take(pxb_ctx *ctx, size_t bytes) {
+	if (!ctx->stage || bytes > kStageMaxItem) return nullptr;
+	const size_t at = (ctx->stage_used + 255) & ~size_t(255);
+	if (at + bytes > ctx->stage_cap) return nullptr;
+	ctx->stage_used = at + bytes;
+	return ctx->stage + at;
+}
+
 static int h2d(pxb_ctx *ctx, void *dst, const void *src, size_t bytes) {
 	if (bytes == 0) return PXB_OK;
+	if (unsigned char *st = stage_take(ctx, bytes)) {
+		std::memcpy(st, src, bytes);
+		src = st;
+	}
 	PXB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
 	return PXB_OK;
 }
 static int d2h(pxb_ctx *ctx, void *dst, const void *src, size_t bytes) {
 	if (bytes == 0) return PXB_OK;
+	if (unsigned char *st = stage_take(ctx, bytes)) {
+		PXB_CUDA(cudaMemcpyAsync(st, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+		ctx->pending.push_back({dst, st, bytes}); // delivered by sync()
+		return PXB_OK;
+	}
 	PXB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
 	return PXB_OK;
 }
 static int sync(pxb_ctx *ctx) {
-	PXB_CUDA(cudaStreamSynchronize(ctx->stream));
+	const cudaError_t err = cudaStreamSynchronize(ctx->stream);
+	if (err == cudaSuccess)
+		for (const auto &c : ctx->pending) std::memcpy(c.dst, c.src, c.bytes);
+	ctx->pending.clear();
+	ctx->stage_used = 0;
+	PXB_CUDA(err);
 	return PXB_OK;
 }
 
@@ -114,6 +145,10 @@ int pxb_ctx_create(int device, pxb_ctx **out) {
 		delete ctx;
 		return PXB_ERR_CUDA;
 	}
+	if (cudaMallocHost(reinterpret_cast<void **>(&ctx->stage), kStageBytes) == cudaSuccess)
+		ctx->stage_cap = kStageBytes;
+	else
+		(void)cudaGetLastError(); // no staging arena: transfers fall back to direct copies
 	*out = ctx;
 	return PXB_OK;
 }
@@ -131,6 +166,7 @@ void pxb_ctx_destroy(pxb_ctx *ctx) {
 	                  &ctx->outD,   &ctx->idx,  &ctx->mask,  &ctx->partials, &ctx->staging, &ctx->screen, &ctx->stats};
 	for (DevBuf *b : bufs) b->release();
 	if (ctx->pinned) cudaFreeHost(ctx->pinned);
+	if (ctx->stage) cudaFreeHost(ctx->stage);
 	lo_skeleton_free(ctx->lo_skeleton);
 	cudaStreamDestroy(ctx->stream);
 	delete ctx;
@@ -160,12 +196,14 @@ int pxb_dev_free(pxb_ctx *ctx, void *dev_ptr) {
 int pxb_memcpy_h2d(pxb_ctx *ctx, void *dev_dst, const void *host_src, size_t bytes) {
 	PXB_CHECK_ARG(ctx && dev_dst && host_src, "null argument");
 	PXB_CUDA(cudaSetDevice(ctx->device));
+	begin_call(ctx);
 	PXB_TRY(h2d(ctx, dev_dst, host_src, bytes));
 	return sync(ctx);
 }
 int pxb_memcpy_d2h(pxb_ctx *ctx, void *host_dst, const void *dev_src, size_t bytes) {
 	PXB_CHECK_ARG(ctx && host_dst && dev_src, "null argument");
 	PXB_CUDA(cudaSetDevice(ctx->device));
+	begin_call(ctx);
 	PXB_TRY(d2h(ctx, host_dst, dev_src, bytes));
 	return sync(ctx);
 }
@@ -182,6 +220,7 @@ int pxb_host_free_pinned(void *host_ptr) {
 // ---- data ------------------------------------------------------------------------------------------------
 int pxb_upload_points(pxb_ctx *ctx, int model_type, const double *pts_host, int64_t N) {
 	PXB_CHECK_ARG(ctx != nullptr, "null context");
+	begin_call(ctx);
 	PXB_CHECK_ARG(model_type >= 0 && model_type <= PXB_MODEL_LINE2D, "unknown model type");
 	PXB_CHECK_ARG(pts_host != nullptr && N > 0, "points must be a non-empty [N, dim] array");
 	PXB_CUDA(cudaSetDevice(ctx->device));
@@ -333,6 +372,7 @@ int pxb_preference_vector(pxb_ctx *ctx, const double *model_host, double T, doub
 int pxb_tanimoto(pxb_ctx *ctx, const double *a_host, const double *b_host, int64_t N, double *similarity) {
 	PXB_CHECK_ARG(ctx && a_host && b_host && similarity && N > 0, "null argument");
 	PXB_CUDA(cudaSetDevice(ctx->device));
+	begin_call(ctx);
 	PXB_TRY(ctx->pref.reserve(sizeof(double) * (size_t)N));
 	PXB_TRY(ctx->pref2.reserve(sizeof(double) * (size_t)N));
 	PXB_TRY(ctx->outA.reserve(sizeof(double) * 3));
@@ -350,6 +390,7 @@ int pxb_tanimoto(pxb_ctx *ctx, const double *a_host, const double *b_host, int64
 int pxb_compound_max(pxb_ctx *ctx, const double *prefs_host, int64_t L, int64_t N, double *out_host) {
 	PXB_CHECK_ARG(ctx && prefs_host && out_host && L >= 0 && N > 0, "null argument");
 	PXB_CUDA(cudaSetDevice(ctx->device));
+	begin_call(ctx);
 	PXB_TRY(ctx->staging.reserve(sizeof(double) * (size_t)std::max<int64_t>(L, 1) * N));
 	PXB_TRY(ctx->pref.reserve(sizeof(double) * (size_t)N));
 	PXB_TRY(h2d(ctx, ctx->staging.ptr, prefs_host, sizeof(double) * (size_t)L * N));
@@ -408,6 +449,7 @@ int pxb_pearl_label(pxb_ctx *ctx, const double *D_host, int64_t N, int32_t L1, d
                     int32_t *labels_out_host, double *energy_out) {
 	PXB_CHECK_ARG(ctx && D_host && labels_out_host && energy_out && N > 0 && L1 >= 1, "null argument");
 	PXB_CUDA(cudaSetDevice(ctx->device));
+	begin_call(ctx);
 	// GCoptimization::setLabel range-checks labels (GCoptimization.cpp:929-934 throws GCException)
 	if (init_labels_host)
 		for (int64_t i = 0; i < N; ++i)

@@ -90,6 +90,18 @@ struct pxb_ctx {
 	void *pinned = nullptr;
 	size_t pinned_cap = 0;
 	void *lo_skeleton = nullptr; // pxb_expansion.cu: cached arc skeleton of the last neighbourhood graph
+	// Pinned staging arena of the host-pointer entry points: small H2D payloads are copied here first and small D2H
+	// results land here and are handed to the caller's (pageable) buffers after the stream synchronises. Pageable
+	// cudaMemcpyAsync calls are synchronous, take the driver's big lock and serialise concurrent contexts; pinned ones
+	// are queued DMA descriptors.
+	unsigned char *stage = nullptr;
+	size_t stage_cap = 0, stage_used = 0;
+	struct PendingCopy {
+		void *dst;
+		const void *src;
+		size_t bytes;
+	};
+	std::vector<PendingCopy> pending;
 	int reserve_pinned(size_t bytes);
 };
 

@@ -24,6 +24,16 @@ __all__ = ["findHomographies", "findTwoViewMotions", "findFundamentalMatrices", 
 _contexts = {}
 
 
+_worker_pool = {}
+
+
+def _worker_contexts(device: int, n: int):
+    pool = _worker_pool.setdefault(device, [])
+    while len(pool) < n:
+        pool.append(Context(device))
+    return pool
+
+
 def _ctx(device: int) -> Context:
     if device not in _contexts:
         _contexts[device] = Context(device)
@@ -102,8 +112,9 @@ def findHomographiesBatch(pairs, w1, h1, w2, h2, distributed=False, workers=8, *
             todo.put(p)
         out, errors = {}, []
 
-        def work():
-            ctx = Context(dev)  # one context per worker thread
+        pool = _worker_contexts(dev, n_workers)  # contexts (stream + scratch buffers) are kept across batch calls
+
+        def work(ctx):
             try:
                 while True:
                     try:
@@ -113,10 +124,8 @@ def findHomographiesBatch(pairs, w1, h1, w2, h2, distributed=False, workers=8, *
                     out[p] = _find_with_context(ctx, pairs[p], w1, h1, w2, h2, **kwargs)
             except Exception as e:  # surfaced after the join
                 errors.append(e)
-            finally:
-                ctx.close()
 
-        threads = [threading.Thread(target=work) for _ in range(n_workers)]
+        threads = [threading.Thread(target=work, args=(pool[i],)) for i in range(n_workers)]
         for t in threads:
             t.start()
         for t in threads:
