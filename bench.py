@@ -433,6 +433,17 @@ def main():
                       "planes + 40% outliers, findHomographies(max_iters=1000, conf=0.5, lambda=0), one problem per GPU "
                       "at a time", "models_found": n_models}
 
+    # same problem with the spatial coherence term (AdelaideH's lambda): GC-RANSAC LO cuts + alpha-expansion on the GPU max-flow
+    lam_kwargs = dict(fit_kwargs, spatial_coherence_weight=0.05)
+    pyprogressivex.findHomographies(c2_pts, 1024, 768, 1024, 768, seed=1, **lam_kwargs)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(2):
+        pyprogressivex.findHomographies(c2_pts, 1024, 768, 1024, 768, seed=2 + i, **lam_kwargs)
+    barrier()
+    extras["fits_lambda"] = {"fits_per_s": 2 * world / (time.perf_counter() - t0),
+                             "config": "C2 with spatial_coherence_weight=0.05 (kNN graph, LO st-cuts, alpha-expansion)"}
+
     # ---- config C4 in miniature: independent pairs solved concurrently (8 host threads, one context each) -----------
     n_pairs, n_pts = 32, 5_000
     c4 = [syn.multi_homography_scene(n_pts, n_planes=4, outlier_ratio=0.4, noise=0.5, seed=700 + 97 * rank + p)[0]

@@ -67,7 +67,7 @@ static unsigned char *stage_take(pxb_ctx *ctx, size_t bytes) {
 	return ctx->stage + at;
 }
 
-static int h2d(pxb_ctx *ctx, void *dst, const void *src, size_t bytes) {
+int api_h2d(pxb_ctx *ctx, void *dst, const void *src, size_t bytes) {
 	if (bytes == 0) return PXB_OK;
 	if (unsigned char *st = stage_take(ctx, bytes)) {
 		std::memcpy(st, src, bytes);
@@ -76,7 +76,7 @@ static int h2d(pxb_ctx *ctx, void *dst, const void *src, size_t bytes) {
 	PXB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
 	return PXB_OK;
 }
-static int d2h(pxb_ctx *ctx, void *dst, const void *src, size_t bytes) {
+int api_d2h(pxb_ctx *ctx, void *dst, const void *src, size_t bytes) {
 	if (bytes == 0) return PXB_OK;
 	if (unsigned char *st = stage_take(ctx, bytes)) {
 		PXB_CUDA(cudaMemcpyAsync(st, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -86,7 +86,7 @@ static int d2h(pxb_ctx *ctx, void *dst, const void *src, size_t bytes) {
 	PXB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
 	return PXB_OK;
 }
-static int sync(pxb_ctx *ctx) {
+int api_sync(pxb_ctx *ctx) {
 	const cudaError_t err = cudaStreamSynchronize(ctx->stream);
 	if (err == cudaSuccess)
 		for (const auto &c : ctx->pending) std::memcpy(c.dst, c.src, c.bytes);
@@ -95,6 +95,60 @@ static int sync(pxb_ctx *ctx) {
 	PXB_CUDA(err);
 	return PXB_OK;
 }
+
+// One PEARL::labeling call on a data-cost matrix that already sits on the device (D_dev, N x L1). Shared by
+// pxb_pearl_label and the host driver (which keeps the matrix on the device between pxb_pearl_datacost and the sweep).
+int pearl_label_device(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t L1, double lambda, double label_cost,
+                       const int32_t *csr_off_host, const int32_t *csr_idx_host, const int32_t *init_labels_host,
+                       int32_t *labels_out_host, double *energy_out) {
+	// GCoptimization::setLabel range-checks labels (GCoptimization.cpp:929-934 throws GCException)
+	if (init_labels_host)
+		for (int64_t i = 0; i < N; ++i)
+			if (init_labels_host[i] < 0 || init_labels_host[i] >= L1) {
+				set_error("init label %d of site %lld outside [0, %d)", init_labels_host[i], (long long)i, L1);
+				return PXB_ERR_ARGUMENT;
+			}
+	// Count the undirected edges setNeighbors would insert (self loops are skipped, PEARL.h:535).
+	int64_t n_dir = 0;
+	if (lambda > 0.0 && csr_off_host && csr_idx_host)
+		for (int64_t i = 0; i < N; ++i)
+			for (int32_t e = csr_off_host[i]; e < csr_off_host[i + 1]; ++e)
+				if (csr_idx_host[e] != i) ++n_dir;
+	PXB_TRY(ctx->outA.reserve(sizeof(int32_t) * (size_t)N * 2 + 64));
+	int32_t *lab_out = ctx->outA.as<int32_t>();
+	int32_t *lab_in = nullptr;
+	if (init_labels_host) {
+		lab_in = lab_out + N;
+		PXB_TRY(api_h2d(ctx, lab_in, init_labels_host, sizeof(int32_t) * (size_t)N));
+	}
+	if (n_dir == 0) {
+		// solveSpecialCases: data costs + per-label costs, no smooth term -> solveGreedy (GCoptimization.cpp:542-552).
+		// With label_cost == 0 the reference takes the per-site argmin branch (:499-517); the greedy solver with a
+		// zero label cost is not the same algorithm, so that case is handled explicitly.
+		if (!(label_cost > 0.0)) {
+			set_error("pxb_pearl_label: label_cost must be > 0 (PEARL always sets it to minimum_inlier_number)");
+			return PXB_ERR_UNSUPPORTED;
+		}
+		PXB_TRY(ctx->outB.reserve(sizeof(double)));
+		PXB_TRY(launch_greedy_label(ctx, D_dev, N, L1, label_cost, lab_in, lab_out, ctx->outB.as<double>()));
+		PXB_TRY(api_d2h(ctx, labels_out_host, lab_out, sizeof(int32_t) * (size_t)N));
+		PXB_TRY(api_d2h(ctx, energy_out, ctx->outB.ptr, sizeof(double)));
+		return api_sync(ctx);
+	}
+	// alpha-expansion
+	PXB_TRY(ctx->idx.reserve(sizeof(int32_t) * (size_t)(N + 1 + csr_off_host[N])));
+	int32_t *off = ctx->idx.as<int32_t>();
+	int32_t *idx = off + (N + 1);
+	PXB_TRY(api_h2d(ctx, off, csr_off_host, sizeof(int32_t) * (size_t)(N + 1)));
+	PXB_TRY(api_h2d(ctx, idx, csr_idx_host, sizeof(int32_t) * (size_t)csr_off_host[N]));
+	PXB_TRY(launch_alpha_expansion(ctx, D_dev, N, L1, lambda, label_cost, off, idx, csr_off_host[N], lab_in, lab_out, energy_out));
+	PXB_TRY(api_d2h(ctx, labels_out_host, lab_out, sizeof(int32_t) * (size_t)N));
+	return api_sync(ctx);
+}
+
+static int h2d(pxb_ctx *ctx, void *dst, const void *src, size_t bytes) { return api_h2d(ctx, dst, src, bytes); }
+static int d2h(pxb_ctx *ctx, void *dst, const void *src, size_t bytes) { return api_d2h(ctx, dst, src, bytes); }
+static int sync(pxb_ctx *ctx) { return api_sync(ctx); }
 
 } // namespace pxb
 
@@ -163,7 +217,7 @@ void pxb_ctx_destroy(pxb_ctx *ctx) {
 	if (ctx->pts.q) cudaFree(ctx->pts.q);
 	if (ctx->pts.norm) cudaFree(ctx->pts.norm);
 	DevBuf *bufs[] = {&ctx->models, &ctx->pref, &ctx->pref2, &ctx->outA, &ctx->outB, &ctx->outC,
-	                  &ctx->outD,   &ctx->idx,  &ctx->mask,  &ctx->partials, &ctx->staging, &ctx->screen, &ctx->stats};
+	                  &ctx->outD,   &ctx->idx,  &ctx->mask,  &ctx->partials, &ctx->staging, &ctx->screen, &ctx->stats, &ctx->cpref};
 	for (DevBuf *b : bufs) b->release();
 	if (ctx->pinned) cudaFreeHost(ctx->pinned);
 	if (ctx->stage) cudaFreeHost(ctx->stage);
@@ -450,53 +504,10 @@ int pxb_pearl_label(pxb_ctx *ctx, const double *D_host, int64_t N, int32_t L1, d
 	PXB_CHECK_ARG(ctx && D_host && labels_out_host && energy_out && N > 0 && L1 >= 1, "null argument");
 	PXB_CUDA(cudaSetDevice(ctx->device));
 	begin_call(ctx);
-	// GCoptimization::setLabel range-checks labels (GCoptimization.cpp:929-934 throws GCException)
-	if (init_labels_host)
-		for (int64_t i = 0; i < N; ++i)
-			if (init_labels_host[i] < 0 || init_labels_host[i] >= L1) {
-				set_error("init label %d of site %lld outside [0, %d)", init_labels_host[i], (long long)i, L1);
-				return PXB_ERR_ARGUMENT;
-			}
-	// Count the undirected edges setNeighbors would insert (self loops are skipped, PEARL.h:535).
-	int64_t n_dir = 0;
-	if (lambda > 0.0 && csr_off_host && csr_idx_host)
-		for (int64_t i = 0; i < N; ++i)
-			for (int32_t e = csr_off_host[i]; e < csr_off_host[i + 1]; ++e)
-				if (csr_idx_host[e] != i) ++n_dir;
 	PXB_TRY(ctx->staging.reserve(sizeof(double) * (size_t)N * L1));
 	PXB_TRY(h2d(ctx, ctx->staging.ptr, D_host, sizeof(double) * (size_t)N * L1));
-	PXB_TRY(ctx->outA.reserve(sizeof(int32_t) * (size_t)N * 2 + 64));
-	int32_t *lab_out = ctx->outA.as<int32_t>();
-	int32_t *lab_in = nullptr;
-	if (init_labels_host) {
-		lab_in = lab_out + N;
-		PXB_TRY(h2d(ctx, lab_in, init_labels_host, sizeof(int32_t) * (size_t)N));
-	}
-	if (n_dir == 0) {
-		// solveSpecialCases: data costs + per-label costs, no smooth term -> solveGreedy (GCoptimization.cpp:542-552).
-		// With label_cost == 0 the reference takes the per-site argmin branch (:499-517); the greedy solver with a
-		// zero label cost is not the same algorithm, so that case is handled explicitly.
-		if (!(label_cost > 0.0)) {
-			set_error("pxb_pearl_label: label_cost must be > 0 (PEARL always sets it to minimum_inlier_number)");
-			return PXB_ERR_UNSUPPORTED;
-		}
-		PXB_TRY(ctx->outB.reserve(sizeof(double)));
-		PXB_TRY(launch_greedy_label(ctx, ctx->staging.as<double>(), N, L1, label_cost, lab_in, lab_out,
-		                            ctx->outB.as<double>()));
-		PXB_TRY(d2h(ctx, labels_out_host, lab_out, sizeof(int32_t) * (size_t)N));
-		PXB_TRY(d2h(ctx, energy_out, ctx->outB.ptr, sizeof(double)));
-		return sync(ctx);
-	}
-	// alpha-expansion
-	PXB_TRY(ctx->idx.reserve(sizeof(int32_t) * (size_t)(N + 1 + csr_off_host[N])));
-	int32_t *off = ctx->idx.as<int32_t>();
-	int32_t *idx = off + (N + 1);
-	PXB_TRY(h2d(ctx, off, csr_off_host, sizeof(int32_t) * (size_t)(N + 1)));
-	PXB_TRY(h2d(ctx, idx, csr_idx_host, sizeof(int32_t) * (size_t)csr_off_host[N]));
-	PXB_TRY(launch_alpha_expansion(ctx, ctx->staging.as<double>(), N, L1, lambda, label_cost, off, idx, csr_off_host[N],
-	                               lab_in, lab_out, energy_out));
-	PXB_TRY(d2h(ctx, labels_out_host, lab_out, sizeof(int32_t) * (size_t)N));
-	return sync(ctx);
+	return pearl_label_device(ctx, ctx->staging.as<double>(), N, L1, lambda, label_cost, csr_off_host, csr_idx_host,
+	                          init_labels_host, labels_out_host, energy_out);
 }
 
 int pxb_segment_residual_sums(pxb_ctx *ctx, const double *models_host, int64_t L, const int32_t *labels_host,

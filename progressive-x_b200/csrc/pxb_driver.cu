@@ -238,6 +238,30 @@ class Driver {
 		if (!models_.empty()) sc.value -= std::pow(shared, s_.exponent); // :110-121
 		return sc;
 	}
+	// The compound preference vector lives on the device between updates (it changes once per accepted instance).
+	const double *compound_dev() const { return models_.empty() ? nullptr : ctx_->cpref.as<double>(); }
+	int upload_compound() {
+		PXB_TRY(ctx_->cpref.reserve(sizeof(double) * (size_t)N_));
+		PXB_CUDA(cudaMemcpyAsync(ctx_->cpref.ptr, compound_pref_.data(), sizeof(double) * (size_t)N_, cudaMemcpyHostToDevice,
+		                         ctx_->stream));
+		PXB_CUDA(cudaStreamSynchronize(ctx_->stream));
+		return PXB_OK;
+	}
+	// scores K models that already sit in ctx->models (device) and brings (count, value, shared) back: no sync here
+	int score_device_models(int64_t K, double T2, std::vector<int64_t> &cnt, std::vector<double> &val, std::vector<double> &shr) {
+		cnt.resize(K);
+		val.resize(K);
+		shr.resize(K);
+		if (K == 0) return PXB_OK;
+		PXB_TRY(ctx_->outB.reserve(sizeof(int64_t) * (size_t)K * 3));
+		int64_t *d_cnt = ctx_->outB.as<int64_t>();
+		double *d_val = reinterpret_cast<double *>(d_cnt + K), *d_shr = d_val + K;
+		PXB_TRY(launch_score_compound(ctx_, ctx_->models.as<double>(), K, T2, compound_dev(), d_cnt, d_val, d_shr));
+		PXB_TRY(api_d2h(ctx_, cnt.data(), d_cnt, sizeof(int64_t) * (size_t)K));
+		PXB_TRY(api_d2h(ctx_, val.data(), d_val, sizeof(double) * (size_t)K));
+		PXB_TRY(api_d2h(ctx_, shr.data(), d_shr, sizeof(double) * (size_t)K));
+		return PXB_OK;
+	}
 	int score_models(const double *models, int64_t K, double T2, std::vector<int64_t> &cnt, std::vector<double> &val,
 	                 std::vector<double> &shr) {
 		cnt.resize(K);
@@ -245,8 +269,31 @@ class Driver {
 		shr.resize(K);
 		if (K == 0) return PXB_OK;
 		Scoped t(prof_, "score_models");
-		return pxb_score_compound(ctx_, models, K, T2, models_.empty() ? nullptr : compound_pref_.data(), cnt.data(),
-		                          val.data(), shr.data());
+		PXB_TRY(ctx_->models.reserve(sizeof(double) * (size_t)K * ms_));
+		PXB_TRY(api_h2d(ctx_, ctx_->models.ptr, models, sizeof(double) * (size_t)K * ms_));
+		PXB_TRY(score_device_models(K, T2, cnt, val, shr));
+		return api_sync(ctx_);
+	}
+	// minimal solves of a block of samples + their scores in ONE round trip (GCRANSAC.h:296-447, block form)
+	int solve_and_score(const std::vector<int64_t> &samples, size_t want, double T2, std::vector<double> &models,
+	                    std::vector<int32_t> &n, std::vector<uint8_t> &sv, std::vector<uint8_t> &mv, std::vector<int64_t> &cnt,
+	                    std::vector<double> &val, std::vector<double> &shr) {
+		Scoped t(prof_, "refill(solve+score)");
+		const int64_t K = (int64_t)want, KS = K * maxsol_;
+		PXB_TRY(ctx_->idx.reserve(sizeof(int64_t) * (size_t)K * m_));
+		PXB_TRY(ctx_->models.reserve(sizeof(double) * (size_t)KS * ms_));
+		PXB_TRY(ctx_->outA.reserve(sizeof(int32_t) * (size_t)K + 2 * (size_t)K + 64));
+		int32_t *d_n = ctx_->outA.as<int32_t>();
+		uint8_t *d_sv = reinterpret_cast<uint8_t *>(d_n + K), *d_mv = d_sv + K;
+		PXB_TRY(api_h2d(ctx_, ctx_->idx.ptr, samples.data(), sizeof(int64_t) * (size_t)K * m_));
+		PXB_CUDA(cudaMemsetAsync(ctx_->models.ptr, 0, sizeof(double) * (size_t)KS * ms_, ctx_->stream));
+		PXB_TRY(launch_solve_minimal(ctx_, ctx_->idx.as<int64_t>(), K, ctx_->models.as<double>(), d_n, d_sv, d_mv));
+		PXB_TRY(api_d2h(ctx_, models.data(), ctx_->models.ptr, sizeof(double) * (size_t)KS * ms_));
+		PXB_TRY(api_d2h(ctx_, n.data(), d_n, sizeof(int32_t) * (size_t)K));
+		PXB_TRY(api_d2h(ctx_, sv.data(), d_sv, (size_t)K));
+		PXB_TRY(api_d2h(ctx_, mv.data(), d_mv, (size_t)K));
+		PXB_TRY(score_device_models(KS, T2, cnt, val, shr));
+		return api_sync(ctx_);
 	}
 	int inliers_of(const double *model, double T2, std::vector<int64_t> &out) {
 		out.resize(N_);
@@ -257,8 +304,11 @@ class Driver {
 		return PXB_OK;
 	}
 	// batched non-minimal fits over index lists; weights (may be null) follow the reference's row indexing
+	// with T2 >= 0 the fitted models are scored in the same round trip (they never leave the device in between)
 	int fit_nonminimal(const std::vector<std::vector<int64_t>> &sets, const double *weights_by_row,
-	                   std::vector<double> &models_out, std::vector<int32_t> &ok);
+	                   std::vector<double> &models_out, std::vector<int32_t> &ok, double T2 = -1.0,
+	                   std::vector<int64_t> *cnt = nullptr, std::vector<double> *val = nullptr,
+	                   std::vector<double> *shr = nullptr);
 	int lo_labeling(const double *model, std::vector<int64_t> &inliers);
 	// Estimator::nonMinimalSampleSize(): H four-point 4, F bundle-adjustment solver 7, PnP bundle adjustment 4,
 	// vanishing point / 2D line: the minimal solver doubles as the non-minimal one, 2
@@ -297,7 +347,8 @@ int Driver::build_graph(double radius, int k) {
 }
 
 int Driver::fit_nonminimal(const std::vector<std::vector<int64_t>> &sets, const double *weights_by_row,
-                           std::vector<double> &models_out, std::vector<int32_t> &ok) {
+                           std::vector<double> &models_out, std::vector<int32_t> &ok, double T2, std::vector<int64_t> *cnt,
+                           std::vector<double> *val, std::vector<double> *shr) {
 	const int P = (int)sets.size();
 	models_out.assign((size_t)P * ms_, 0.0);
 	ok.assign(P, 0);
@@ -319,10 +370,10 @@ int Driver::fit_nonminimal(const std::vector<std::vector<int64_t>> &sets, const 
 	if (weights_by_row) {
 		PXB_TRY(ctx_->pref2.reserve(sizeof(double) * wcount));
 		d_w = ctx_->pref2.as<double>();
-		PXB_CUDA(cudaMemcpyAsync(d_w, weights_by_row, sizeof(double) * wcount, cudaMemcpyHostToDevice, ctx_->stream));
+		PXB_TRY(api_h2d(ctx_, d_w, weights_by_row, sizeof(double) * wcount));
 	}
-	PXB_CUDA(cudaMemcpyAsync(d_off, off.data(), sizeof(int32_t) * off.size(), cudaMemcpyHostToDevice, ctx_->stream));
-	PXB_CUDA(cudaMemcpyAsync(d_idx, idx.data(), sizeof(int32_t) * idx.size(), cudaMemcpyHostToDevice, ctx_->stream));
+	PXB_TRY(api_h2d(ctx_, d_off, off.data(), sizeof(int32_t) * off.size()));
+	PXB_TRY(api_h2d(ctx_, d_idx, idx.data(), sizeof(int32_t) * idx.size()));
 	switch (s_.type) {
 	case PXB_MODEL_HOMOGRAPHY:
 		PXB_TRY(launch_fit_h(ctx_, P, d_off, d_idx, d_w, ctx_->models.as<double>(), ctx_->outA.as<int32_t>()));
@@ -340,11 +391,10 @@ int Driver::fit_nonminimal(const std::vector<std::vector<int64_t>> &sets, const 
 		PXB_TRY(launch_fit_line(ctx_, P, d_off, d_idx, ctx_->models.as<double>(), ctx_->outA.as<int32_t>()));
 		break;
 	}
-	PXB_CUDA(cudaMemcpyAsync(models_out.data(), ctx_->models.ptr, sizeof(double) * models_out.size(),
-	                         cudaMemcpyDeviceToHost, ctx_->stream));
-	PXB_CUDA(cudaMemcpyAsync(ok.data(), ctx_->outA.ptr, sizeof(int32_t) * ok.size(), cudaMemcpyDeviceToHost, ctx_->stream));
-	PXB_CUDA(cudaStreamSynchronize(ctx_->stream));
-	return PXB_OK;
+	PXB_TRY(api_d2h(ctx_, models_out.data(), ctx_->models.ptr, sizeof(double) * models_out.size()));
+	PXB_TRY(api_d2h(ctx_, ok.data(), ctx_->outA.ptr, sizeof(int32_t) * ok.size()));
+	if (cnt) PXB_TRY(score_device_models(P, T2, *cnt, *val, *shr));
+	return api_sync(ctx_);
 }
 
 // gcr/GCRANSAC.h:914-1022. Unary terms come from the device (k_lo_unary). Without a smoothness term the st-cut
@@ -423,10 +473,9 @@ int Driver::local_optimization(Sampler &lo_sampler, std::vector<double> &best_mo
 		}
 		std::vector<double> fitted;
 		std::vector<int32_t> ok;
-		PXB_TRY(fit_nonminimal(sets, nullptr, fitted, ok));
 		std::vector<int64_t> cnt;
 		std::vector<double> val, shr;
-		PXB_TRY(score_models(fitted.data(), (int64_t)sets.size(), T2, cnt, val, shr));
+		PXB_TRY(fit_nonminimal(sets, nullptr, fitted, ok, T2, &cnt, &val, &shr));
 		for (size_t t = 0; t < sets.size(); ++t) {
 			if (!ok[t]) continue; // estimateModelNonminimal failed -> `continue` (:851-855)
 			const Score sc = finish_score(cnt[t], val[t], shr[t], max_score.inliers);
@@ -462,11 +511,10 @@ int Driver::irls(std::vector<int64_t> &inliers, std::vector<double> &model, doub
 		std::vector<double> fitted;
 		std::vector<int32_t> ok;
 		const double *w_arg = !weighting_applicable() ? nullptr : (weights_by_point() ? w_point.data() : w_row.data());
-		PXB_TRY(fit_nonminimal(sets, w_arg, fitted, ok));
-		if (!ok[0]) break;
 		std::vector<int64_t> cnt;
 		std::vector<double> val, shr;
-		PXB_TRY(score_models(fitted.data(), 1, T2, cnt, val, shr));
+		PXB_TRY(fit_nonminimal(sets, w_arg, fitted, ok, T2, &cnt, &val, &shr));
+		if (!ok[0]) break;
 		const Score sc = finish_score(cnt[0], val[0], shr[0], 0);
 		if ((size_t)sc.inliers < (size_t)m_) break;
 		if ((size_t)sc.inliers <= inliers.size()) break;
@@ -527,10 +575,7 @@ int Driver::propose(uint64_t round_seed, std::vector<double> &model_out, bool &f
 		blk_n.assign(want, 0);
 		blk_sv.assign(want, 0);
 		blk_mv.assign(want, 0);
-		Scoped t(prof_, "refill(sample+solve)");
-		PXB_TRY(pxb_solve_minimal(ctx_, samples.data(), (int64_t)want, blk_models.data(), blk_n.data(), blk_sv.data(),
-		                          blk_mv.data()));
-		PXB_TRY(score_models(blk_models.data(), (int64_t)(want * maxsol_), T2, blk_cnt, blk_val, blk_shr));
+		PXB_TRY(solve_and_score(samples, want, T2, blk_models, blk_n, blk_sv, blk_mv, blk_cnt, blk_val, blk_shr));
 		cursor = 0;
 		filled = want;
 		return PXB_OK;
@@ -613,11 +658,10 @@ int Driver::propose(uint64_t round_seed, std::vector<double> &model_out, bool &f
 		std::vector<std::vector<int64_t>> sets(1, best_inliers);
 		std::vector<double> fitted;
 		std::vector<int32_t> ok;
-		PXB_TRY(fit_nonminimal(sets, nullptr, fitted, ok));
+		std::vector<int64_t> cnt;
+		std::vector<double> val, shr;
+		PXB_TRY(fit_nonminimal(sets, nullptr, fitted, ok, T2, &cnt, &val, &shr));
 		if (ok[0]) {
-			std::vector<int64_t> cnt;
-			std::vector<double> val, shr;
-			PXB_TRY(score_models(fitted.data(), 1, T2, cnt, val, shr));
 			const Score sc = finish_score(cnt[0], val[0], shr[0], 0);
 			if (best_score.value < sc.value) {
 				best_model = fitted;
@@ -662,18 +706,18 @@ int Driver::pearl() {
 		if (L == 0) break;
 		std::vector<double> flat((size_t)L * ms_);
 		for (int64_t l = 0; l < L; ++l) std::copy(models_[l].model.begin(), models_[l].model.end(), flat.begin() + l * ms_);
-		std::vector<double> D((size_t)N_ * (L + 1));
-		{
-			Scoped t(prof_, "pearl datacost");
-			PXB_TRY(pxb_pearl_datacost(ctx_, flat.data(), L, s_.threshold, s_.lambda, D.data()));
-		}
+		// data costs stay on the device between the cost kernel and the label sweep (PEARL.h:476-555 in two launches)
+		PXB_TRY(ctx_->models.reserve(sizeof(double) * (size_t)L * ms_));
+		PXB_TRY(api_h2d(ctx_, ctx_->models.ptr, flat.data(), sizeof(double) * (size_t)L * ms_));
+		PXB_TRY(ctx_->staging.reserve(sizeof(double) * (size_t)N_ * (L + 1)));
+		PXB_TRY(launch_pearl_datacost(ctx_, ctx_->models.as<double>(), L, s_.threshold, s_.lambda, ctx_->staging.as<double>()));
 		Scoped tl(prof_, "pearl label+refit");
 		const int32_t *init = (init_with_previous && have_labels) ? labels.data() : nullptr;
 		prev_labels = labels;
 		const bool smooth = s_.lambda > 0.0 && !graph_.idx.empty();
-		PXB_TRY(pxb_pearl_label(ctx_, D.data(), N_, (int32_t)(L + 1), s_.lambda, label_cost,
-		                        smooth ? graph_.off.data() : nullptr, smooth ? graph_.idx.data() : nullptr,
-		                        init ? prev_labels.data() : nullptr, labels.data(), &energy));
+		PXB_TRY(pearl_label_device(ctx_, ctx_->staging.as<double>(), N_, (int32_t)(L + 1), s_.lambda, label_cost,
+		                           smooth ? graph_.off.data() : nullptr, smooth ? graph_.idx.data() : nullptr,
+		                           init ? prev_labels.data() : nullptr, labels.data(), &energy));
 		have_labels = true;
 		// ---- parameterEstimation ----
 		bool model_parameters_changed = false;
@@ -782,6 +826,7 @@ int Driver::run() {
 			for (size_t k = 0; k < models_.size(); ++k)
 				std::copy(models_[k].pref.begin(), models_[k].pref.end(), prefs.begin() + k * N_);
 			PXB_TRY(pxb_compound_max(ctx_, prefs.data(), (int64_t)models_.size(), N_, compound_pref_.data()));
+			PXB_TRY(upload_compound());
 		}
 		size_t unseen;
 		if (models_.size() == 1 && first_model_inliers_stat)

@@ -86,7 +86,7 @@ struct pxb_ctx {
 	int64_t launches = 0;
 	pxb::Points pts;
 	// scratch
-	pxb::DevBuf models, pref, pref2, outA, outB, outC, outD, idx, mask, partials, staging, screen, stats;
+	pxb::DevBuf models, pref, pref2, outA, outB, outC, outD, idx, mask, partials, staging, screen, stats, cpref;
 	void *pinned = nullptr;
 	size_t pinned_cap = 0;
 	void *lo_skeleton = nullptr; // pxb_expansion.cu: cached arc skeleton of the last neighbourhood graph
@@ -107,6 +107,14 @@ struct pxb_ctx {
 
 namespace pxb {
 void lo_skeleton_free(void *p);
+// staged transfers of the host-pointer entry points (pxb_api.cu): small payloads go through the context's pinned arena;
+// api_sync synchronises the stream and delivers the staged D2H results
+int api_h2d(pxb_ctx *ctx, void *dst, const void *src, size_t bytes);
+int api_d2h(pxb_ctx *ctx, void *dst, const void *src, size_t bytes);
+int api_sync(pxb_ctx *ctx);
+int pearl_label_device(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t L1, double lambda, double label_cost,
+                       const int32_t *csr_off_host, const int32_t *csr_idx_host, const int32_t *init_labels_host,
+                       int32_t *labels_out_host, double *energy_out);
 // kernel launchers (device pointers, asynchronous on ctx->stream)
 int launch_residual_matrix(pxb_ctx *ctx, const double *models, int64_t K, double T2, double *r2, float *r2f,
                            uint32_t *mask);
