@@ -23,10 +23,11 @@
 // partially used capacities run-dependent, which cannot change the cut except on exact ties (saturating pushes and
 // emptied excesses are exact zeros in every order).
 //
-// Round-1 split of work: the host builds the binary-energy graph of each move (integer bookkeeping plus two or three
-// flops per edge, exactly the add_term1/add_term2 sequence of the reference) and evaluates labelling energies in the
-// reference's summation order; the device solves the cuts. Moving graph construction to the device is listed as the
-// next step in DESIGN.md.
+// Split of work: the binary-energy graph of every expansion move and of every LO cut is assembled ON THE DEVICE over a
+// fixed arc skeleton (k_exp_assemble / k_lo_assemble: the reference's add_term1 / add_term2 / add_tweights sequence, one
+// thread per node over the node's own neighbour list); the host keeps the move loop and evaluates the labelling energies
+// that decide whether a move is kept, in the reference's sequential summation order. pxb_lo_graph_cut (terms given by the
+// caller) still assembles on the host.
 #include <cooperative_groups.h>
 
 #include <algorithm>
@@ -56,8 +57,14 @@ struct FlowGraphDev {
 constexpr int kMfThreads = 256;
 constexpr int kWideDegree = 64;
 
+// Exact distance-to-sink labels by a level-synchronous BACKWARD breadth-first search in "push" form: the nodes of the
+// current frontier (height == level) mark every unlabelled in-neighbour v (residual arc v -> u, i.e. cap[rev(a)] > 0 for
+// the arc a = u -> v) with level + 1. Each node is expanded exactly once and all of its arcs are examined with
+// independent loads (the earlier "pull" form re-scanned every unlabelled node at every level with a serial, early-exit
+// arc loop: 16 us per level at N = 10^4; source-side nodes -- never labelled -- paid that at every level).
 __device__ void mf_global_relabel(const FlowGraphDev &G, int32_t *h, cg::grid_group &grid, int tid, int nthreads) {
 	const int n = G.n;
+	volatile int32_t *hv = h;
 	for (int u = tid; u < n; u += nthreads) h[u] = (G.sink_cap[u] > 0.0) ? 1 : n;
 	if (tid == 0) {
 		G.flags[0] = 0;
@@ -71,32 +78,31 @@ __device__ void mf_global_relabel(const FlowGraphDev &G, int32_t *h, cg::grid_gr
 		int32_t *changed = &G.flags[level % 3];
 		bool mine = false;
 		for (int u = tid; u < G.wide_begin; u += nthreads) {
-			if (h[u] != n) continue;
-			for (int a = G.arc_off[u]; a < G.arc_off[u + 1]; ++a)
-				if (G.cap[a] > 0.0 && h[G.arc_head[a]] == level) {
-					h[u] = level + 1;
+			if (hv[u] != level) continue;
+			for (int a = G.arc_off[u]; a < G.arc_off[u + 1]; ++a) {
+				const int v = G.arc_head[a];
+				if (G.cap[G.arc_rev[a]] > 0.0 && hv[v] == n) {
+					hv[v] = level + 1; // benign race: every writer stores the same value
 					mine = true;
-					break;
 				}
+			}
 		}
-		for (int w = blockIdx.x; w < G.wide_count; w += gridDim.x) { // block-cooperative scan of a wide node's arcs
+		for (int w = blockIdx.x; w < G.wide_count; w += gridDim.x) { // a wide node's arcs are expanded by its whole block
 			const int u = G.wide_begin + w;
-			__shared__ int s_hu;
-			if (threadIdx.x == 0) s_hu = h[u];
-			__syncthreads();
-			const bool open = s_hu == n;
-			int found = 0;
-			if (open)
-				for (int a = G.arc_off[u] + threadIdx.x; a < G.arc_off[u + 1] && !found; a += blockDim.x)
-					found = (G.cap[a] > 0.0 && h[G.arc_head[a]] == level);
-			found = __syncthreads_or(found);
-			if (found && threadIdx.x == 0) {
-				h[u] = level + 1;
-				mine = true;
+			if (hv[u] != level) continue; // block-uniform: h[u] was written before the previous barrier
+			for (int a = G.arc_off[u] + threadIdx.x; a < G.arc_off[u + 1]; a += blockDim.x) {
+				const int v = G.arc_head[a];
+				if (G.cap[G.arc_rev[a]] > 0.0 && hv[v] == n) {
+					hv[v] = level + 1;
+					mine = true;
+				}
 			}
 		}
 		if (mine) *changed = 1;
-		if (tid == 0) G.flags[(level + 1) % 3] = 0;
+		if (tid == 0) {
+			G.flags[(level + 1) % 3] = 0;
+			G.flags[8]++; // statistics: BFS levels
+		}
 		grid.sync();
 		if (*changed == 0) break;
 	}
@@ -266,7 +272,10 @@ __global__ void __launch_bounds__(kMfThreads) k_maxflow(FlowGraphDev G) {
 	int round = 0;
 	for (; round < kMaxRounds; ++round) {
 		// exact distance-to-sink labels; nodes that cannot reach the sink any more get height n and go quiet
+		const long long t0 = clock64();
 		mf_global_relabel(G, h, grid, tid, nthreads);
+		const long long t1 = clock64();
+		if (tid == 0) G.flags[10] += (int)((t1 - t0) >> 6);
 		bool active = false;
 		for (int u = tid; u < n; u += nthreads) active |= (G.excess[u] > 0.0 && h[u] < n);
 		if (tid == 0) G.flags[3 + ((round + 1) % 3)] = 0;
@@ -280,6 +289,7 @@ __global__ void __launch_bounds__(kMfThreads) k_maxflow(FlowGraphDev G) {
 		}
 		__threadfence();
 		grid.sync();
+		if (tid == 0) G.flags[12] += (int)((clock64() - t1) >> 6);
 	}
 	// heights now hold the final reachability: height < n  <=>  the node can reach the sink in the residual graph
 	if (tid == 0) {
@@ -421,8 +431,8 @@ static int solve_min_cut(pxb_ctx *ctx, const FlowGraphHost &g, std::vector<uint8
 		const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
 		total_ms += ms;
 		if (++calls % 20 == 0 || ms > 3 || getenv("PXB_MF_STATS")[0] == '2')
-			fprintf(stderr, "[pxb maxflow] call %d: n=%d arcs=%d rounds=%d grid=%d  %.2f ms (total %.1f ms)\n", calls, n, m,
-			        flags[6], grid, ms, total_ms);
+			fprintf(stderr, "[pxb maxflow] call %d: n=%d arcs=%d rounds=%d grid=%d  %.2f ms (total %.1f ms) bfs_levels=%d relabel=%.2f ms async+check=%.2f ms\n", calls, n, m,
+			        flags[6], grid, ms, total_ms, flags[8], (double)flags[10] * 64 / 1.965e6, (double)flags[12] * 64 / 1.965e6);
 	}
 	return PXB_OK;
 }
@@ -648,10 +658,104 @@ double compute_energy(const ExpansionProblem &P, const std::vector<int32_t> &lab
 }
 } // namespace
 
+// ---- device-side assembly of one expansion move ------------------------------------------------------------------
+// The binary energy of "expand alpha" lives on a FIXED arc skeleton: node s < N is site s, node N + l is the label-cost
+// auxiliary node of label l. Site s owns one arc per entry of its gco neighbour list (both directions of an undirected
+// pair are entries, so the reverse arc is simply the mirrored entry) plus one arc to the auxiliary node of its current
+// label; auxiliary node l owns one arc per site currently labelled l. Only capacities change from move to move, and the
+// site <-> auxiliary wiring changes when a move is accepted. Terminal capacities follow the reference's add_term1 /
+// add_term2 / add_tweights arithmetic (gcr/energy.h:204-256, gcr/graph.h): the terminal capacity of a site is a
+// sequential function of its OWN neighbour list (setupDataCostsExpansion :327-333, setupSmoothCostsExpansion :337-402
+// with Potts * lambda: a neighbour that keeps alpha adds add_tweights(lambda, 0); an active neighbour with a smaller
+// index adds add_tweights(e11, 0) and the arc pair (lambda, lambda - e11), e11 = lambda iff the two labels differ;
+// setupLabelCostsExpansion :1131-1195 adds the arc pair (0, label_cost) to the auxiliary node, whose own terminal
+// capacity is label_cost). Sites that already carry alpha are inert (all capacities zero).
+__global__ void k_exp_assemble(int64_t N, int L1, int alpha, double lambda, double label_cost, const double *__restrict__ D,
+                               const int32_t *__restrict__ lab, const int32_t *__restrict__ goff,
+                               const int32_t *__restrict__ gidx, const int32_t *__restrict__ label_count,
+                               const int32_t *__restrict__ arc_rev, double *__restrict__ cap, double *__restrict__ excess,
+                               double *__restrict__ sink_cap) {
+	const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= N + L1) return;
+	if (s >= N) { // auxiliary node of label l: add_term1(aux, 0, label_cost) = add_tweights(aux, label_cost, 0)
+		const int l = (int)(s - N);
+		const bool live = label_cost > 0 && l != alpha && label_count[l] > 0;
+		excess[s] = live ? label_cost : 0.0;
+		sink_cap[s] = 0.0;
+		return; // its arc capacities are written by the sites
+	}
+	const int ls = lab[s];
+	const bool active = ls != alpha;
+	const int64_t a0 = goff[s] + s; // arcs of site s: its list entries, then the auxiliary arc
+	const int e0 = goff[s], e1 = goff[s + 1];
+	double tr = 0.0;
+	auto add_tweights = [&](double cap_source, double cap_sink) {
+		const double delta = tr;
+		if (delta > 0) cap_source = __dadd_rn(cap_source, delta);
+		else cap_sink = __dsub_rn(cap_sink, delta);
+		tr = __dsub_rn(cap_source, cap_sink);
+	};
+	if (active) add_tweights(D[s * L1 + ls], D[s * L1 + alpha]); // add_term1(v, D(alpha), D(current))
+	double out_cap = 0.0;
+	for (int e = e0; e < e1; ++e) {
+		const int nb = gidx[e];
+		const int lnb = lab[nb];
+		double c = 0.0;
+		if (active && lambda > 0) {
+			if (lnb == alpha) {
+				add_tweights(lambda, 0.0); // add_term1(v, e0 = 0, e1 = lambda)
+			} else {
+				const double e11 = (ls != lnb) ? lambda : 0.0;
+				if (nb < s) {
+					add_tweights(e11, 0.0); // add_term2(v, w, 0, lambda, lambda, e11): add_tweights(v, D = e11, A = 0)
+					c = lambda;             // edge v -> w : B = e01 - e00
+				} else {
+					c = __dsub_rn(lambda, e11); // edge w -> v seen from w's side: C = e10 - e11
+				}
+			}
+		}
+		cap[a0 + (e - e0)] = c;
+		out_cap = __dadd_rn(out_cap, c);
+	}
+	const int64_t aux_arc = a0 + (e1 - e0);
+	double to_aux = 0.0, from_aux = 0.0;
+	if (active && label_cost > 0) {
+		// add_term2(v, aux, 0, 0, label_cost, 0): add_tweights(v, 0, 0) leaves tr as it is; arcs (v -> aux) = 0 and
+		// (aux -> v) = label_cost, clamped to what v can pass on (its sink link plus its outgoing n-links): every maximum
+		// flow and the set of nodes that reach the sink are unchanged, but the auxiliary node spreads its budget at once.
+		add_tweights(0.0, 0.0);
+		const double bound = __dadd_rn(tr < 0 ? -tr : 0.0, out_cap);
+		from_aux = fmin(label_cost, bound);
+	}
+	cap[aux_arc] = to_aux;
+	cap[arc_rev[aux_arc]] = from_aux;
+	excess[s] = (active && tr > 0) ? tr : 0.0;
+	sink_cap[s] = (active && tr < 0) ? -tr : 0.0;
+}
+
+// Rewires the site <-> auxiliary arcs after the labelling changed: site s points at node N + lab[s]; the auxiliary node
+// of label l lists the sites labelled l in index order (rank = number of earlier sites with the same label).
+__global__ void k_exp_wire_aux(int64_t N, int L1, int64_t E, const int32_t *__restrict__ lab, const int32_t *__restrict__ rank,
+                               const int32_t *__restrict__ label_off, const int32_t *__restrict__ goff,
+                               int32_t *__restrict__ arc_off, int32_t *__restrict__ arc_head, int32_t *__restrict__ arc_rev) {
+	const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (s < N) {
+		const int l = lab[s];
+		const int64_t site_arc = (int64_t)goff[s + 1] + s;                 // last arc of site s
+		const int64_t aux_arc = E + N + label_off[l] + rank[s];            // its mirror in the auxiliary node's list
+		arc_head[site_arc] = (int32_t)(N + l);
+		arc_rev[site_arc] = (int32_t)aux_arc;
+		arc_head[aux_arc] = (int32_t)s;
+		arc_rev[aux_arc] = (int32_t)site_arc;
+	}
+	if (s <= L1) arc_off[N + s] = (int32_t)(E + N + label_off[s]); // label_off[L1] = N: arc_off[N + L1] = E + 2N
+}
+
 int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t L1, double lambda, double label_cost,
                            const int32_t *csr_off_dev, const int32_t *csr_idx_dev, int64_t n_dir_edges,
                            const int32_t *init_labels_dev, int32_t *labels_out_dev, double *energy_out_host) {
-	// The problem description comes back to the host for graph assembly (see the header comment).
+	// The data costs and the labelling are mirrored on the host: the labelling energies that decide whether a move is
+	// kept are evaluated there in the reference's sequential summation order (compute_energy).
 	std::vector<double> D((size_t)N * L1);
 	std::vector<int32_t> off((size_t)N + 1), idx((size_t)std::max<int64_t>(n_dir_edges, 1)), lab((size_t)N, 0);
 	cudaStream_t st = ctx->stream;
@@ -669,6 +773,7 @@ int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t
 	P.L1 = L1;
 	P.lambda = lambda;
 	P.label_cost = label_cost;
+	std::vector<int32_t> grev; // mirrored entry of every neighbour-list entry
 	{ // gco adjacency: per site a list built with addFront, so the last inserted neighbour comes first
 		P.goff.assign((size_t)N + 1, 0);
 		for (int64_t i = 0; i < N; ++i)
@@ -680,88 +785,122 @@ int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t
 			}
 		for (int64_t i = 0; i < N; ++i) P.goff[i + 1] += P.goff[i];
 		P.gidx.resize((size_t)P.goff[N]);
+		grev.resize((size_t)P.goff[N]);
 		std::vector<int32_t> next(P.goff.begin() + 1, P.goff.end()); // fill every list from its back: reversed push order
 		for (int64_t i = 0; i < N; ++i)
 			for (int32_t e = off[i]; e < off[i + 1]; ++e) {
 				const int32_t j = idx[e];
 				if (j == i) continue;
-				P.gidx[--next[i]] = j;
-				P.gidx[--next[j]] = (int32_t)i;
+				const int32_t pi = --next[i], pj = --next[j];
+				P.gidx[pi] = j;
+				P.gidx[pj] = (int32_t)i;
+				grev[pi] = pj;
+				grev[pj] = pi;
 			}
 	}
+	const int64_t E = P.goff[N];
+	const int n = (int)(N + L1);
+	const int64_t m = E + 2 * N;
+
+	// ---- device arena: static skeleton + per-move state ----
+	const size_t n_int = (size_t)(n + 1) + 2 * (size_t)m + (size_t)(N + 1) + (size_t)E + 2 * (size_t)N + 2 * (size_t)(L1 + 1) +
+	                     2 * (size_t)n + 32;
+	const size_t bytes = sizeof(double) * ((size_t)m + 2 * (size_t)n) + sizeof(int32_t) * n_int + 256;
+	PXB_TRY(ctx->partials.reserve(bytes));
+	double *d_cap = ctx->partials.as<double>(), *d_excess = d_cap + m, *d_sink = d_excess + n;
+	int32_t *d_arc_off = reinterpret_cast<int32_t *>(d_sink + n), *d_head = d_arc_off + (n + 1), *d_rev = d_head + m;
+	int32_t *d_goff = d_rev + m, *d_gidx = d_goff + (N + 1), *d_lab = d_gidx + E, *d_rank = d_lab + N;
+	int32_t *d_label_off = d_rank + N, *d_label_count = d_label_off + (L1 + 1);
+	int32_t *d_h0 = d_label_count + (L1 + 1), *d_h1 = d_h0 + n, *d_flags = d_h1 + n;
+	{
+		std::vector<int32_t> arc_off((size_t)n + 1, 0), head((size_t)m, 0), rev((size_t)m, 0);
+		for (int64_t s2 = 0; s2 <= N; ++s2) arc_off[s2] = (int32_t)(P.goff[s2] + s2);
+		for (int64_t s2 = 0; s2 < N; ++s2)
+			for (int32_t e = P.goff[s2]; e < P.goff[s2 + 1]; ++e) {
+				const int32_t nb = P.gidx[e];
+				head[(size_t)e + s2] = nb;
+				rev[(size_t)e + s2] = grev[e] + nb; // the mirrored entry lives in nb's arc block, shifted by nb aux slots
+			}
+		PXB_CUDA(cudaMemcpyAsync(d_arc_off, arc_off.data(), sizeof(int32_t) * arc_off.size(), cudaMemcpyHostToDevice, st));
+		PXB_CUDA(cudaMemcpyAsync(d_head, head.data(), sizeof(int32_t) * head.size(), cudaMemcpyHostToDevice, st));
+		PXB_CUDA(cudaMemcpyAsync(d_rev, rev.data(), sizeof(int32_t) * rev.size(), cudaMemcpyHostToDevice, st));
+		PXB_CUDA(cudaMemcpyAsync(d_goff, P.goff.data(), sizeof(int32_t) * (size_t)(N + 1), cudaMemcpyHostToDevice, st));
+		if (E > 0) PXB_CUDA(cudaMemcpyAsync(d_gidx, P.gidx.data(), sizeof(int32_t) * (size_t)E, cudaMemcpyHostToDevice, st));
+		PXB_CUDA(cudaStreamSynchronize(st)); // the host vectors go out of scope
+	}
+	std::vector<int32_t> rank((size_t)N), label_off((size_t)L1 + 1), label_count((size_t)L1 + 1);
+	auto push_labelling = [&]() -> int { // labels, ranks and the auxiliary wiring follow the host labelling
+		std::fill(label_count.begin(), label_count.end(), 0);
+		for (int64_t i = 0; i < N; ++i) rank[i] = label_count[lab[i]]++;
+		label_off[0] = 0;
+		for (int l = 0; l < L1; ++l) label_off[l + 1] = label_off[l] + label_count[l];
+		PXB_CUDA(cudaMemcpyAsync(d_lab, lab.data(), sizeof(int32_t) * (size_t)N, cudaMemcpyHostToDevice, st));
+		PXB_CUDA(cudaMemcpyAsync(d_rank, rank.data(), sizeof(int32_t) * (size_t)N, cudaMemcpyHostToDevice, st));
+		PXB_CUDA(cudaMemcpyAsync(d_label_off, label_off.data(), sizeof(int32_t) * (size_t)(L1 + 1), cudaMemcpyHostToDevice, st));
+		PXB_CUDA(cudaMemcpyAsync(d_label_count, label_count.data(), sizeof(int32_t) * (size_t)(L1 + 1), cudaMemcpyHostToDevice, st));
+		k_exp_wire_aux<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(N, L1, E, d_lab, d_rank, d_label_off, d_goff, d_arc_off, d_head, d_rev);
+		ctx->launches++;
+		PXB_CUDA(cudaStreamSynchronize(st)); // rank / label_off are reused by the next change
+		return PXB_OK;
+	};
+	PXB_TRY(push_labelling());
+
+	FlowGraphDev G;
+	G.n = n;
+	G.m = (int)m;
+	G.wide_begin = (int)N;
+	G.wide_count = L1;
+	G.arc_off = d_arc_off;
+	G.arc_head = d_head;
+	G.arc_rev = d_rev;
+	G.cap = d_cap;
+	G.pushed = nullptr;
+	G.excess = d_excess;
+	G.sink_cap = d_sink;
+	G.height[0] = d_h0;
+	G.height[1] = d_h1;
+	G.flags = d_flags;
+	int blocks_per_sm = 0;
+	PXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_maxflow, kMfThreads, 0));
+	const int want = (n + kMfThreads - 1) / kMfThreads;
+	const int grid = std::max(std::min(L1, ctx->sm_count), std::min(want, ctx->sm_count * std::max(1, std::min(blocks_per_sm, 4))));
+	PXB_TRY(ctx->reserve_pinned(sizeof(int32_t) * ((size_t)n + 16)));
+	int32_t *h_host = static_cast<int32_t *>(ctx->pinned), *flags_host = h_host + n;
 
 	double new_energy = compute_energy(P, lab), old_energy; // always the energy of `lab` (compute_energy is a pure function)
-	std::vector<int32_t> active, lookup((size_t)N, -1);
-	std::vector<uint8_t> seg;
+	std::vector<int32_t> cand;
+	const bool stats = getenv("PXB_MF_STATS") != nullptr;
 	for (int cycle = 1; cycle <= 1000; ++cycle) { // GCoptimization.cpp:1062-1077
 		old_energy = new_energy;
 		for (int alpha = 0; alpha < L1; ++alpha) { // oneExpansionIteration, fixed label order 0..L
-			active.clear();
-			for (int64_t i = 0; i < N; ++i)
-				if (lab[i] != alpha) active.push_back((int32_t)i);
-			const int size = (int)active.size();
-			if (size == 0) continue;
-			for (int v = 0; v < size; ++v) lookup[active[v]] = v;
-			FlowGraphHost g(size);
-			// setupDataCostsExpansion (:327-333): add_term1(i, D(site, alpha), D(site, current))
-			for (int v = 0; v < size; ++v) {
-				const int64_t s = active[v];
-				g.add_term1(v, D[s * L1 + alpha], D[s * L1 + lab[s]]);
+			if (label_count[alpha] == (int32_t)N) continue; // no site to move (alpha_expansion returns at size == 0)
+			const auto t_move = std::chrono::steady_clock::now();
+			PXB_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int32_t) * 16, st));
+			k_exp_assemble<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(N, L1, alpha, lambda, label_cost, D_dev, d_lab, d_goff, d_gidx,
+			                                                          d_label_count, d_rev, d_cap, d_excess, d_sink);
+			void *args[] = {&G};
+			PXB_CUDA(cudaLaunchCooperativeKernel((void *)k_maxflow, dim3(grid), dim3(kMfThreads), args, 0, st));
+			ctx->launches += 2;
+			PXB_CUDA(cudaMemcpyAsync(h_host, d_h0, sizeof(int32_t) * (size_t)N, cudaMemcpyDeviceToHost, st));
+			PXB_CUDA(cudaMemcpyAsync(flags_host, d_flags, sizeof(int32_t) * 16, cudaMemcpyDeviceToHost, st));
+			PXB_CUDA(cudaStreamSynchronize(st));
+			if (flags_host[7] != 1 || flags_host[6] == 0) {
+				set_error("max-flow did not converge within %d relabel rounds", kMaxRounds);
+				return PXB_ERR_CUDA;
 			}
-			// setupSmoothCostsExpansion (:337-402), Potts * lambda, weight 1
-			if (lambda > 0)
-				for (int v = size - 1; v >= 0; --v) {
-					const int64_t s = active[v];
-					for (int32_t e = P.goff[s]; e < P.goff[s + 1]; ++e) {
-						const int32_t nb = P.gidx[e];
-						if (lookup[nb] == -1) { // neighbour keeps alpha
-							const double e0 = (alpha != lab[nb]) ? lambda : 0, e1 = (lab[s] != lab[nb]) ? lambda : 0;
-							g.add_term1(v, e0 * 1.0, e1 * 1.0);
-						} else if (nb < s) {
-							const double e00 = 0, e01 = (alpha != lab[nb]) ? lambda : 0, e10 = (lab[s] != alpha) ? lambda : 0,
-							             e11 = (lab[s] != lab[nb]) ? lambda : 0;
-							g.add_term2(v, lookup[nb], e00 * 1.0, e01 * 1.0, e10 * 1.0, e11 * 1.0);
-						}
-					}
-				}
-			// setupLabelCostsExpansion (:1131-1195): one auxiliary node per non-alpha label present among the active sites
-			if (label_cost > 0) {
-				std::vector<int> aux((size_t)L1, -1);
-				for (int v = 0; v < size; ++v) {
-					const int l = lab[active[v]];
-					if (aux[l] < 0) {
-						aux[l] = g.add_node();
-						g.add_term1(aux[l], 0, label_cost);
-					}
-					g.add_term2(v, aux[l], 0, 0, label_cost, 0);
-				}
-			}
-			// An auxiliary arc aux -> site can never carry more than the site can pass on (its own sink link plus its
-			// outgoing n-links). Clamping it to that bound leaves every maximum flow -- and the set of nodes that can
-			// reach the sink -- unchanged, but lets the auxiliary node spread its budget in one discharge.
-			if (label_cost > 0 && g.n > size) {
-				std::vector<double> out_cap((size_t)g.n, 0.0);
-				for (size_t pidx = 0; pidx < g.tail.size(); ++pidx) {
-					out_cap[g.tail[pidx]] += g.cap_fwd[pidx];
-					out_cap[g.head[pidx]] += g.cap_rev[pidx];
-				}
-				for (size_t pidx = 0; pidx < g.tail.size(); ++pidx)
-					if (g.head[pidx] >= size) { // site -> aux pair: cap_fwd = 0, cap_rev = label cost (aux -> site)
-						const int v = g.tail[pidx];
-						const double bound = (g.tr[v] < 0 ? -g.tr[v] : 0.0) + out_cap[v];
-						g.cap_rev[pidx] = std::min(g.cap_rev[pidx], bound);
-					}
-			}
-			PXB_TRY(solve_min_cut(ctx, g, seg, size));
-			// candidate labelling: SOURCE side (get_var == 0) takes alpha (:451-469)
+			if (stats)
+				fprintf(stderr, "[pxb expansion] alpha=%d active=%d rounds=%d bfs_levels=%d relabel=%.2f ms async=%.2f ms wall=%.2f ms\n",
+				        alpha, (int)(N - label_count[alpha]), flags_host[6], flags_host[8], (double)flags_host[10] * 64 / 1.965e6,
+				        (double)flags_host[12] * 64 / 1.965e6,
+				        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_move).count());
+			// candidate labelling: SOURCE side (cannot reach the sink) takes alpha (:451-469)
 			bool any_switch = false;
-			std::vector<int32_t> cand = lab;
-			for (int v = 0; v < size; ++v)
-				if (!seg[v]) {
-					cand[active[v]] = alpha;
+			cand = lab;
+			for (int64_t i = 0; i < N; ++i)
+				if (lab[i] != alpha && !(h_host[i] < n)) {
+					cand[i] = alpha;
 					any_switch = true;
 				}
-			for (int v = 0; v < size; ++v) lookup[active[v]] = -1;
 			if (!any_switch) continue;
 			// the reference applies the move iff afterExpansionEnergy < m_beforeExpansionEnergy (:1286); both are the
 			// energies of the two labellings, evaluated here directly
@@ -769,6 +908,7 @@ int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t
 			if (after < before) {
 				lab.swap(cand);
 				new_energy = after;
+				PXB_TRY(push_labelling());
 			}
 		}
 		if (new_energy == old_energy) break;
