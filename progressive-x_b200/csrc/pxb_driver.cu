@@ -56,6 +56,20 @@ int launch_fit_line(pxb_ctx *ctx, int P, const int32_t *off, const int32_t *idx,
 
 namespace {
 
+// Neighbours kept per point. The reference's FlannNeighborhoodGraph asks OpenCV's FLANN for radiusMatch with
+// SearchParams(checks = 6) (gcr/neighborhood/flann_neighborhood_graph.h:100-139): at most 6 approximate matches come back
+// whatever the radius, and the first one is dropped -- <= 5 neighbours per point (2-4.6 on average on the AdelaideRMF
+// scenes, probed with cv2 here). The deterministic stand-in keeps the 5 nearest points inside the radius; with more
+// neighbours the Potts term of PEARL (lambda per cut edge) outweighs the data term and every instance is swallowed by the
+// outlier label at the reference's own lambda = 0.5 (adelaideF.ipynb).
+inline int graph_degree() {
+	if (const char *e = getenv("PXB_GRAPH_K")) {
+		const int k = atoi(e);
+		if (k >= 1 && k <= 16) return k;
+	}
+	return 5;
+}
+
 // ---- RNG -----------------------------------------------------------------------------------------------------
 struct Rng {
 	uint64_t s;
@@ -874,7 +888,7 @@ int run_two_view(pxb_ctx *ctx, int type, const double *corr, int64_t N, int64_t 
 	Driver drv(ctx, s);
 	if (lambda > 0.0 || sampler_id == 3) {
 		Scoped t(drv.prof_, "build_graph");
-		PXB_TRY(drv.build_graph(radius, 8));
+		PXB_TRY(drv.build_graph(radius, graph_degree()));
 	}
 	{
 		Scoped t(drv.prof_, "run (inclusive)");
@@ -923,7 +937,7 @@ int run_points_family(pxb_ctx *ctx, int type, const double *rows, const double *
 	if (seed == 0) seed = (uint64_t)std::chrono::high_resolution_clock::now().time_since_epoch().count();
 	s.seed = seed;
 	Driver drv(ctx, s);
-	if (lambda > 0.0 || s.napsac) PXB_TRY(drv.build_graph(radius, 8));
+	if (lambda > 0.0 || s.napsac) PXB_TRY(drv.build_graph(radius, graph_degree()));
 	PXB_TRY(drv.run());
 	const auto &inst = drv.instances();
 	const int64_t M = (int64_t)inst.size();
@@ -1016,7 +1030,7 @@ int pxb_find_6d_poses(pxb_ctx *ctx, const double *image_points, const double *wo
 	s.seed = seed;
 	PXB_TRY(pxb_upload_points(ctx, PXB_MODEL_PNP, raw.data(), N));
 	Driver drv(ctx, s);
-	if (spatial_coherence_weight > 0.0) PXB_TRY(drv.build_graph(neighborhood_ball_radius, 8));
+	if (spatial_coherence_weight > 0.0) PXB_TRY(drv.build_graph(neighborhood_ball_radius, graph_degree()));
 	PXB_TRY(pxb_upload_points(ctx, PXB_MODEL_PNP, nrm.data(), N));
 	PXB_TRY(drv.run());
 	const auto &inst = drv.instances();
