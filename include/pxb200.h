@@ -191,8 +191,8 @@ int pxb_knn_graph(pxb_ctx *ctx, double radius, int k, int32_t *nbr_out_host, int
 int pxb_fit_homographies(pxb_ctx *ctx, int32_t P, const int32_t *off_host, const int32_t *idx_host,
                          const double *weights_by_row_host, double *H_out_host, int32_t *ok_out_host);
 /* Same for whatever estimator family the uploaded points belong to (Estimator::estimateModelNonminimal). H: as above.
- * F: normalised 8-point + rank-2 projection (gcr/estimators/fundamental_estimator.h:574-618 without the LM polish of
- * solver_fundamental_matrix_bundle_adjustment.h), n >= 8. PnP: normalised DLT + Levenberg-Marquardt on the reprojection
+ * F: normalised 8-point + rank-2 projection (gcr/estimators/fundamental_estimator.h:574-618) followed by a Levenberg-
+ * Marquardt polish of the Sampson error (the objective of solver_fundamental_matrix_bundle_adjustment.h:114-178), n >= 8. PnP: normalised DLT + Levenberg-Marquardt on the reprojection
  * error (stands in for solver_pnp_bundle_adjustment.h:108-225), n >= 6, weights ignored like the reference does.
  * Vanishing point: smallest eigenvector of the weighted 3x3 normal matrix (px/include/solver_vanishing_point_two_lines.h:
  * 187-233); here `weights_by_row_host` holds N entries and is read BY POINT, the reference's indexing for this solver (:203).

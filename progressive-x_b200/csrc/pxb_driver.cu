@@ -772,6 +772,12 @@ int Driver::pearl() {
 				}
 			}
 		}
+		if (s_.do_logging) {
+			fprintf(stdout, "[pxb]   PEARL it %zu: L=%lld energy %.4f (prev %.4f) init=%d points per instance:", iteration_number,
+			        (long long)L, energy, previous_energy, init ? 1 : 0);
+			for (int64_t l = 0; l < L; ++l) fprintf(stdout, " %zu", per_instance[l].size());
+			fprintf(stdout, " outliers %zu%s\n", outliers, model_parameters_changed ? " (refit accepted)" : "");
+		}
 		// ---- rejectInstances (back to front) ----
 		for (int64_t l = L - 1; l >= 0; --l)
 			if (per_instance[l].size() < s_.min_inliers) {
@@ -812,6 +818,9 @@ int Driver::run() {
 		std::vector<double> model;
 		bool found = false;
 		PXB_TRY(propose(s_.seed * 1000003ull + it, model, found));
+		if (s_.do_logging)
+			fprintf(stdout, "[pxb] proposal %zu: %s, %zu inliers, %zu iterations, %zu LO runs, %zu graph cuts\n", it + 1,
+			        found ? "found" : "none", proposal_inliers_.size(), iteration_number_, lo_number_, graph_cut_number_);
 		if (!found) continue; // :301-303
 		number_of_ransac_iterations += iteration_number_;
 		std::vector<double> pref;

@@ -111,6 +111,21 @@ __device__ void svd3(const double *M, double *U, double *s, double *V) {
 // ------------------------------------------------------------------------------------------------
 // fundamental matrix
 // ------------------------------------------------------------------------------------------------
+// closest rank-2 matrix (smallest singular value zeroed), scaled to unit Frobenius norm
+__device__ void fp_rank2_unit(double *F) {
+	double U[9], s[3], Vt[9];
+	svd3(F, U, s, Vt);
+	double nrm = 0.0;
+	for (int r = 0; r < 3; ++r)
+		for (int c = 0; c < 3; ++c) {
+			F[r * 3 + c] = U[r * 3 + 0] * s[0] * Vt[c * 3 + 0] + U[r * 3 + 1] * s[1] * Vt[c * 3 + 1];
+			nrm += F[r * 3 + c] * F[r * 3 + c];
+		}
+	nrm = sqrt(nrm);
+	if (nrm > 0.0)
+		for (int i = 0; i < 9; ++i) F[i] /= nrm;
+}
+
 __global__ void __launch_bounds__(kFitT)
     k_fit_f(const double *__restrict__ aos, const int32_t *__restrict__ off, const int32_t *__restrict__ idx,
             const double *__restrict__ weights, double *__restrict__ F_out, int32_t *__restrict__ ok_out) {
@@ -161,30 +176,152 @@ __global__ void __launch_bounds__(kFitT)
 		if (tid == 0) s_acc[a] = v;
 	}
 	__syncthreads();
-	if (tid != 0) return;
-	double A[81], V[81], w[9];
-	{
+	__shared__ double s_F[9], s_cand[9], s_vec[kFitT / 32][56], s_sys[56];
+	__shared__ int s_go;
+	if (tid == 0) {
+		double A[81], V[81], w[9];
 		int a = 0;
 		for (int r = 0; r < 9; ++r)
 			for (int c = r; c < 9; ++c, ++a) A[r * 9 + c] = A[c * 9 + r] = s_acc[a];
+		jacobi_eig<9>(A, V, w);
+		int best = 0;
+		for (int i = 1; i < 9; ++i)
+			if (w[i] < w[best]) best = i;
+		double Fn[9];
+		for (int i = 0; i < 9; ++i) Fn[i] = V[i * 9 + best];
+		fp_rank2_unit(Fn);
+		// the polish below works with ONE scale for both images (rs = sqrt(r1 r2)), so that its Sampson error is the pixel
+		// Sampson error times a constant: y_i = rs (x - m_i) = (rs / r_i) xn_i  =>  F_lm = K2 Fn K1, K_i = diag(r_i/rs, r_i/rs, 1)
+		const double rs = sqrt(r1 * r2), k1 = r1 / rs, k2 = r2 / rs;
+		for (int r = 0; r < 3; ++r)
+			for (int c = 0; c < 3; ++c) s_F[r * 3 + c] = Fn[r * 3 + c] * (r < 2 ? k2 : 1.0) * (c < 2 ? k1 : 1.0);
+		fp_rank2_unit(s_F);
 	}
-	jacobi_eig<9>(A, V, w);
-	int best = 0;
-	for (int i = 1; i < 9; ++i)
-		if (w[i] < w[best]) best = i;
-	double Fn[9];
-	for (int i = 0; i < 9; ++i) Fn[i] = V[i * 9 + best];
-	// rank 2
-	double U[9], s[3], Vt[9];
-	svd3(Fn, U, s, Vt);
-	for (int r = 0; r < 3; ++r)
-		for (int c = 0; c < 3; ++c) Fn[r * 3 + c] = U[r * 3 + 0] * s[0] * Vt[c * 3 + 0] + U[r * 3 + 1] * s[1] * Vt[c * 3 + 1];
-	// F = T2^T Fn T1, T = [r 0 -r m_x; 0 r -r m_y; 0 0 1]
-	const double T1[9] = {r1, 0, -r1 * mx1, 0, r1, -r1 * my1, 0, 0, 1};
-	const double T2[9] = {r2, 0, -r2 * mx2, 0, r2, -r2 * my2, 0, 0, 1};
+	__syncthreads();
+	// ---- Levenberg-Marquardt polish of the (weighted) Sampson error, the objective of the reference's bundle adjustment
+	// (solver_fundamental_matrix_bundle_adjustment.h:114-178 -> PoseLib refine_fundamental). 9 parameters with Marquardt
+	// scaling; the scale gauge is absorbed by the damping, the rank-2 constraint is re-imposed after every step, and a
+	// step is kept only if the error decreases.
+	const double rs = sqrt(r1 * r2);
+	auto accumulate = [&](const double *F, double *sys /*45 JtJ + 9 Jtr + cost*/) {
+		double acc2[55];
+#pragma unroll
+		for (int a = 0; a < 55; ++a) acc2[a] = 0.0;
+		for (int t = tid; t < n; t += kFitT) {
+			const double *q = aos + 4 * (int64_t)idx[beg + t];
+			const double x1[3] = {(q[0] - mx1) * rs, (q[1] - my1) * rs, 1.0}, x2[3] = {(q[2] - mx2) * rs, (q[3] - my2) * rs, 1.0};
+			const double wgt = weights ? weights[t] : 1.0;
+			double Fx[3], Ftx[3];
+			for (int r = 0; r < 3; ++r) Fx[r] = F[r * 3] * x1[0] + F[r * 3 + 1] * x1[1] + F[r * 3 + 2];
+			for (int c = 0; c < 3; ++c) Ftx[c] = F[c] * x2[0] + F[3 + c] * x2[1] + F[6 + c];
+			const double C = x2[0] * Fx[0] + x2[1] * Fx[1] + Fx[2];
+			const double S = Fx[0] * Fx[0] + Fx[1] * Fx[1] + Ftx[0] * Ftx[0] + Ftx[1] * Ftx[1];
+			if (!(S > 1e-300)) continue;
+			const double inv = 1.0 / sqrt(S), res = wgt * C * inv;
+			double J[9];
+			for (int r = 0; r < 3; ++r)
+				for (int c = 0; c < 3; ++c) {
+					const double dC = x2[r] * x1[c];
+					const double dS = 2.0 * ((r < 2 ? Fx[r] * x1[c] : 0.0) + (c < 2 ? Ftx[c] * x2[r] : 0.0));
+					J[r * 3 + c] = wgt * (dC * inv - 0.5 * C * inv * inv * inv * dS);
+				}
+			int a = 0;
+#pragma unroll
+			for (int r = 0; r < 9; ++r)
+#pragma unroll
+				for (int c = r; c < 9; ++c, ++a) acc2[a] += J[r] * J[c];
+#pragma unroll
+			for (int r = 0; r < 9; ++r) acc2[45 + r] += J[r] * res;
+			acc2[54] += res * res;
+		}
+		// vector block reduction: butterfly inside each warp, then 55 threads add the 8 warp rows in order
+#pragma unroll
+		for (int a = 0; a < 55; ++a)
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) acc2[a] += __shfl_xor_sync(0xffffffffu, acc2[a], o);
+		__syncthreads();
+		if ((tid & 31) == 0)
+			for (int a = 0; a < 55; ++a) s_vec[tid >> 5][a] = acc2[a];
+		__syncthreads();
+		if (tid < 55) {
+			double v = 0.0;
+			for (int wv = 0; wv < kFitT / 32; ++wv) v += s_vec[wv][tid];
+			sys[tid] = v;
+		}
+		__syncthreads();
+	};
+	accumulate(s_F, s_sys);
+	__shared__ double s_sys2[56];
+	double mu = 1e-3;
+	for (int it = 0; it < 8; ++it) {
+		if (tid == 0) { // solve (JtJ + mu diag(JtJ)) delta = -Jtr by Gaussian elimination with partial pivoting
+			double M[9][10];
+			int a = 0;
+			for (int r = 0; r < 9; ++r)
+				for (int c = r; c < 9; ++c, ++a) M[r][c] = M[c][r] = s_sys[a];
+			for (int r = 0; r < 9; ++r) {
+				M[r][r] += mu * fmax(M[r][r], 1e-12);
+				M[r][9] = -s_sys[45 + r];
+			}
+			bool okk = true;
+			for (int k = 0; k < 9 && okk; ++k) {
+				int piv = k;
+				for (int r = k + 1; r < 9; ++r)
+					if (fabs(M[r][k]) > fabs(M[piv][k])) piv = r;
+				if (!(fabs(M[piv][k]) > 1e-300)) {
+					okk = false;
+					break;
+				}
+				if (piv != k)
+					for (int c = 0; c < 10; ++c) {
+						const double t = M[k][c];
+						M[k][c] = M[piv][c];
+						M[piv][c] = t;
+					}
+				for (int r = k + 1; r < 9; ++r) {
+					const double f = M[r][k] / M[k][k];
+					for (int c = k; c < 10; ++c) M[r][c] -= f * M[k][c];
+				}
+			}
+			double delta[9];
+			if (okk)
+				for (int r = 8; r >= 0; --r) {
+					double v = M[r][9];
+					for (int c = r + 1; c < 9; ++c) v -= M[r][c] * delta[c];
+					delta[r] = v / M[r][r];
+					okk &= fabs(delta[r]) <= 1e300;
+				}
+			if (okk) {
+				for (int i = 0; i < 9; ++i) s_cand[i] = s_F[i] + delta[i];
+				fp_rank2_unit(s_cand);
+			}
+			s_go = okk ? 1 : 0;
+		}
+		__syncthreads();
+		if (!s_go) break; // block-uniform
+		accumulate(s_cand, s_sys2);
+		if (tid == 0) {
+			if (s_sys2[54] < s_sys[54]) {
+				const bool small = (s_sys[54] - s_sys2[54]) <= 1e-12 * s_sys[54];
+				for (int i = 0; i < 9; ++i) s_F[i] = s_cand[i];
+				for (int i = 0; i < 55; ++i) s_sys[i] = s_sys2[i];
+				s_go = small ? 0 : 1;
+			} else {
+				s_go = 2; // rejected: more damping
+			}
+		}
+		__syncthreads();
+		if (s_go == 0) break;
+		mu = (s_go == 2) ? mu * 10.0 : mu * 0.3;
+		if (mu > 1e6) break;
+	}
+	if (tid != 0) return;
+	// F = T2^T F_lm T1 with T_i = [rs 0 -rs m_x; 0 rs -rs m_y; 0 0 1]
+	const double T1[9] = {rs, 0, -rs * mx1, 0, rs, -rs * my1, 0, 0, 1};
+	const double T2[9] = {rs, 0, -rs * mx2, 0, rs, -rs * my2, 0, 0, 1};
 	double tmp[9], F[9];
 	for (int r = 0; r < 3; ++r)
-		for (int c = 0; c < 3; ++c) tmp[r * 3 + c] = T2[0 + r] * Fn[0 + c] + T2[3 + r] * Fn[3 + c] + T2[6 + r] * Fn[6 + c];
+		for (int c = 0; c < 3; ++c) tmp[r * 3 + c] = T2[0 + r] * s_F[0 + c] + T2[3 + r] * s_F[3 + c] + T2[6 + r] * s_F[6 + c];
 	for (int r = 0; r < 3; ++r)
 		for (int c = 0; c < 3; ++c) F[r * 3 + c] = tmp[r * 3 + 0] * T1[0 + c] + tmp[r * 3 + 1] * T1[3 + c] + tmp[r * 3 + 2] * T1[6 + c];
 	double nrm = 0;
