@@ -49,7 +49,7 @@ struct FlowGraphDev {
 	int wide_begin, wide_count; // nodes [wide_begin, wide_begin + wide_count) are label-cost auxiliary nodes: thousands
 	                            // of arcs each, handled by a whole thread block instead of one owner thread
 	const int32_t *arc_off, *arc_head, *arc_rev;
-	double *cap, *pushed, *excess, *sink_cap;
+	double *cap, *excess, *sink_cap;
 	int32_t *height[2];
 	int32_t *flags; // [0..2] BFS 'changed' (level mod 3), [3..5] 'active' (pulse mod 3), [6] pulses, [7] status
 };
@@ -393,7 +393,6 @@ static int solve_min_cut(pxb_ctx *ctx, const FlowGraphHost &g, std::vector<uint8
 	cudaStream_t st = ctx->stream;
 	PXB_CUDA(cudaMemcpyAsync(dp, hp, bytes_up, cudaMemcpyHostToDevice, st));
 	PXB_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int32_t) * 16, st));
-	double *d_pushed = nullptr;
 	FlowGraphDev G;
 	G.n = n;
 	G.m = m;
@@ -403,7 +402,6 @@ static int solve_min_cut(pxb_ctx *ctx, const FlowGraphHost &g, std::vector<uint8
 	G.arc_head = d_head;
 	G.arc_rev = d_rev;
 	G.cap = d_cap;
-	G.pushed = d_pushed;
 	G.excess = d_excess;
 	G.sink_cap = d_sink;
 	G.height[0] = d_h0;
@@ -600,7 +598,6 @@ int lo_labeling_device(pxb_ctx *ctx, const double *model_dev, double thr, double
 	G.arc_head = g_lo.arc_head;
 	G.arc_rev = g_lo.arc_rev;
 	G.cap = d_cap;
-	G.pushed = nullptr;
 	G.excess = d_excess;
 	G.sink_cap = d_sink;
 	G.height[0] = d_h0;
@@ -854,7 +851,6 @@ int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t
 	G.arc_head = d_head;
 	G.arc_rev = d_rev;
 	G.cap = d_cap;
-	G.pushed = nullptr;
 	G.excess = d_excess;
 	G.sink_cap = d_sink;
 	G.height[0] = d_h0;

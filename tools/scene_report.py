@@ -1,3 +1,5 @@
+"""Misclassification / pose errors of the drop-in on the reference's bundled scenes over several seeds (tuning aid; the
+asserting version is tests/test_gpu_reference_scenes.py)."""
 import sys, itertools
 from pathlib import Path
 import numpy as np
