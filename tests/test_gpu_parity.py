@@ -420,3 +420,18 @@ def test_vp_and_line_nonminimal_fits(ctx, oracle, t):
     cnt, _, _ = ctx.score_compound(got, T2)
     for k in range(planted.shape[0]):
         assert cnt[k] > 0.9 * len(sets[k])
+
+
+@pytest.mark.parametrize("t", ALL)
+@pytest.mark.parametrize("N", [1, 5, 33, 127, 129, 1023, 1025, 2049])
+def test_score_compound_ragged_sizes(ctx, oracle, t, N):
+    """Point counts around the warp (32), chunk (128) and block (1024) boundaries of the score kernel, K not a multiple
+    of the hypothesis tile, with and without a compound preference vector."""
+    pts, gt, planted, thr = scene(t, max(N, 300), seed=200 + N)
+    models = hypotheses(oracle, t, pts, gt, planted, 37, seed=7)
+    pts = np.ascontiguousarray(pts[:N])
+    T2 = (1.5 * thr) ** 2
+    cp = oracle.preference_vector(t, pts, planted[0], 9 / 4 * thr * thr)
+    for comp in (None, cp):
+        _assert_score_equals_oracle(ctx, oracle, t, pts, models, T2, comp)
+    _assert_score_equals_oracle(ctx, oracle, t, pts, models[:1], T2, cp)
