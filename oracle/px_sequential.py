@@ -1,0 +1,401 @@
+"""Sequential CPU restatement of the Progressive-X control flow (TEST INFRASTRUCTURE ONLY, see oracle/pxo_oracle.h).
+
+One hypothesis at a time, exactly as the reference runs it -- no blocks, no batching -- on top of the oracle's
+operators (pinned against the reference's own function bodies) and the reference's own gco / max-flow build:
+
+    ProgressiveX::run              src/pyprogressivex/include/progressive_x.h:251-489     -> ProgressiveXOracle.run
+    isPutativeModelValid           progressive_x.h:565-591                               -> putative_model_valid
+    updateCompoundModel            progressive_x.h:597-624                               -> (inside run)
+    getPredictedUnseenInliers      progressive_x.h:495-513                               -> predicted_unseen_inliers
+    GCRANSAC::run                  graph-cut-ransac/.../GCRANSAC.h:203-628               -> propose
+    graphCutLocalOptimization      GCRANSAC.h:781-911                                    -> local_optimization
+    labeling                       GCRANSAC.h:914-1022                                   -> lo_labeling (reference BK build)
+    iteratedLeastSquaresFitting    GCRANSAC.h:631-759                                    -> irls
+    PEARL::run / labeling / parameterEstimation / rejectInstances   PEARL.h:275-555      -> pearl (reference gco build)
+
+tests/test_gpu_sequential_oracle.py runs the GPU driver (blocks of 512 hypotheses per launch, device-resident
+chains) and this loop on the same inputs and seeds and compares instance counts, labels and models.
+
+What is shared with the GPU driver BY CONSTRUCTION, because the reference leaves it unspecified or non-reproducible
+(DESIGN.md section 8): the random streams (splitmix64, one stream per proposal for the main sampler and one for the
+local-optimisation sampler), the neighbourhood graph (handed in by the caller), and "the inlier list of the current
+best model" in place of the reference's accidental two-buffer ping-pong. Homographies only (the family whose
+non-minimal fit the oracle restates: column-pivoted Householder QR here, 8x8 normal equations on the GPU -- the two
+agree to ~1e-9, which is why models are compared with a tolerance and labels exactly)."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from . import oracle as O
+
+H = 0
+M64 = (1 << 64) - 1
+
+
+class Rng:
+    """splitmix64 as in progressive-x_b200/csrc/pxb_driver.cu (the reference seeds std::mt19937 from std::random_device)."""
+
+    def __init__(self, seed):
+        self.s = (seed & M64) or 0x9E3779B97F4A7C15
+
+    def next(self):
+        self.s = (self.s + 0x9E3779B97F4A7C15) & M64
+        z = self.s
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M64
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M64
+        return z ^ (z >> 31)
+
+    def uniform(self, mx):  # inclusive, rejection sampled like std::uniform_int_distribution(0, mx)
+        rng = mx + 1
+        limit = M64 - (M64 % rng)
+        while True:
+            r = self.next()
+            if r < limit:
+                return r % rng
+
+    def unique_set(self, n, mx, skip=None):  # gcr/uniform_random_generator.h:76-122
+        out = []
+        while len(out) < n:
+            v = self.uniform(mx)
+            if skip is not None and v == skip:
+                continue
+            if v in out:
+                continue
+            out.append(v)
+        return out
+
+
+class UniformSampler:  # gcr/samplers/uniform_sampler.h:118-134
+    def __init__(self, seed):
+        self.rng = Rng(seed)
+
+    def sample(self, pool, m):
+        if m > len(pool):
+            return None
+        return [pool[i] for i in self.rng.unique_set(m, len(pool) - 1)]
+
+
+class NapsacSampler:  # gcr/samplers/napsac_sampler.h:102-151 (incl. the point-index-as-list-index skip, :139-142)
+    def __init__(self, seed, off, idx):
+        self.rng, self.off, self.idx = Rng(seed), off, idx
+
+    def sample(self, pool, m):
+        if m > len(pool):
+            return None
+        attempts = 0
+        subset = None
+        while True:
+            attempts += 1
+            if not attempts - 1 < 100:
+                break
+            c = self.rng.unique_set(1, len(pool) - 1)[0]
+            nb = self.idx[self.off[c]:self.off[c + 1]]
+            if len(nb) < m:
+                continue
+            if len(nb) == m:
+                subset = [int(v) for v in nb[:m]]
+                break
+            rest = self.rng.unique_set(m - 1, len(nb) - 1, skip=c)
+            subset = [c] + [int(nb[j]) for j in rest]
+            break
+        return subset if attempts < 100 else None
+
+
+class Score:
+    __slots__ = ("inliers", "value")
+
+    def __init__(self, inliers=0, value=0.0):
+        self.inliers, self.value = inliers, value
+
+
+class ProgressiveXOracle:
+    def __init__(self, pts, *, threshold, confidence, lam, max_tanimoto, max_iters, min_inliers, max_models, napsac, exponent,
+                 seed, graph):
+        self.pts = np.ascontiguousarray(pts, dtype=np.float64)
+        self.N = self.pts.shape[0]
+        self.m = 4
+        self.thr, self.conf, self.lam, self.max_tanimoto = threshold, confidence, lam, max_tanimoto
+        self.max_iters, self.min_inliers = max_iters, min_inliers
+        self.max_models = max_models if max_models > 0 else 1 << 62
+        self.napsac, self.exponent, self.seed = napsac, int(exponent), seed
+        self.off, self.idx = graph if graph is not None else (np.zeros(self.N + 1, np.int32), np.zeros(0, np.int32))
+        # gcransac::utils::Settings as overridden by progressive_x.h:64-71
+        self.min_iteration_number = 20
+        self.min_iteration_number_before_lo = 20
+        self.max_local_optimization_number = 50
+        self.max_graph_cut_number = 10
+        self.max_least_squares_iterations = 10
+        self.max_unsuccessful_model_generations = 100
+        self.models, self.prefs = [], []
+        self.compound = np.zeros(self.N)
+        self.labeling = np.zeros(self.N, dtype=np.int64)
+        self.pearl_outliers = 0
+
+    # ---- operators: every N-point loop is an oracle call -----------------------------------------------------------
+    def _score(self, model, T2, best_inliers):
+        cp = self.compound if self.models else None
+        cnt, val, shr = O.score_batch(H, self.pts, model, T2, cp)
+        cnt, val, shr = int(cnt[0]), float(val[0]), float(shr[0])
+        if cnt + 1 < best_inliers:  # scoring_function_with_compound_model.h:105-106
+            return Score()
+        value = val - (math.pow(shr, self.exponent) if self.models else 0.0)  # :110-121
+        return Score(cnt, value)
+
+    def _inliers_of(self, model, T2):
+        r2, _ = O.residual_matrix(H, self.pts, model, T2, want_mask=False)
+        return [int(i) for i in np.flatnonzero(r2[0] < T2)]
+
+    def _fit(self, idx, weights_by_row=None):
+        return O.fit_h_nonminimal(self.pts, idx, weights_by_row)
+
+    def _lo_labeling(self, model):  # GCRANSAC.h:914-1022
+        d, e0, e1 = O.lo_unary_terms(H, self.pts, model, self.thr, self.lam)
+        if not (self.lam > 0) or self.idx.size == 0:
+            return [int(i) for i in np.flatnonzero(e1 - e0 < 0)]
+        seg, _ = O.gco_lo_labeling(e0, e1, d, self.lam, self.off, self.idx)
+        return [int(i) for i in np.flatnonzero(seg)]
+
+    def _iteration_number_for(self, inliers, log_probability):  # GCRANSAC.h:158-173
+        q = math.pow(inliers / self.N, self.m)
+        log2 = math.log(1 - q) if q < 1.0 else -math.inf
+        if abs(log2) < np.finfo(np.float64).eps:
+            return 1 << 62
+        return int(log_probability / log2) + 1
+
+    # ---- GCRANSAC.h:781-911 -----------------------------------------------------------------------------------------
+    def local_optimization(self, lo_sampler, best_model, best_score, T2):
+        inlier_limit = 7 * self.m
+        max_score, lo_model = Score(best_score.inliers, best_score.value), best_model
+        self.lo_number += 1
+        while True:
+            self.graph_cut_number += 1
+            if not self.graph_cut_number < self.max_graph_cut_number:
+                break
+            updated = False
+            inliers = self._lo_labeling(lo_model)
+            sample_size = min(inlier_limit, len(inliers))
+            if sample_size < len(inliers):
+                sets = [lo_sampler.sample(inliers, sample_size) for _ in range(self.max_local_optimization_number)]
+            elif self.m < len(inliers):
+                sets = [inliers]
+            else:
+                break
+            for st in sets:
+                model, ok = self._fit(st)
+                if not ok:
+                    continue
+                sc = self._score(model, T2, max_score.inliers)
+                if max_score.value < sc.value:
+                    updated, max_score, lo_model = True, sc, model
+            if not updated:
+                break
+        if best_score.value < max_score.value:
+            return lo_model, max_score
+        return best_model, best_score
+
+    # ---- GCRANSAC.h:631-759 -----------------------------------------------------------------------------------------
+    def irls(self, inliers, model, T2):
+        if len(inliers) <= self.m:
+            return inliers, model, False
+        iterations = 0
+        while True:
+            iterations += 1
+            if not iterations < self.max_least_squares_iterations:
+                break
+            weights = O.tukey_weights(H, self.pts, model, T2)
+            w_point = np.zeros(self.N)
+            w_point[inliers] = weights[inliers]
+            w_row = w_point[:len(inliers)].copy()  # the solver reads weights_[row] (reference quirk)
+            fitted, ok = self._fit(inliers, w_row)
+            if not ok:
+                break
+            sc = self._score(fitted, T2, 0)
+            if sc.inliers < self.m or sc.inliers <= len(inliers):
+                break
+            model = fitted
+            inliers = self._inliers_of(model, T2)
+        return inliers, model, iterations > 1
+
+    # ---- GCRANSAC.h:203-628 -----------------------------------------------------------------------------------------
+    def propose(self, round_seed):
+        self.iteration_number = self.graph_cut_number = self.lo_number = 0
+        self.proposal_inliers = []
+        log_probability = math.log(1.0 - self.conf)
+        max_iteration = self._iteration_number_for(1, log_probability)
+        tt = 3.0 / 2.0 * self.thr
+        T2 = tt * tt
+        if self.napsac and self.idx.size:
+            main = NapsacSampler((round_seed * 2 + 1) & M64, self.off, self.idx)
+        else:
+            main = UniformSampler((round_seed * 2 + 1) & M64)
+        lo_sampler = UniformSampler((round_seed * 2 + 2) & M64)
+        pool = list(range(self.N))
+        best_score, best_model = Score(), None
+        while self.min_iteration_number > self.iteration_number or self.iteration_number < min(max_iteration, self.max_iters):
+            do_lo = False
+            self.iteration_number += 1
+            unsuccessful, found = -1, None
+            while True:  # :296-339 select a sample that yields at least one model (<= 100 attempts)
+                unsuccessful += 1
+                if not unsuccessful < self.max_unsuccessful_model_generations:
+                    break
+                sample = main.sample(pool, self.m)
+                if sample is None:
+                    continue
+                models, n, sv, mv = O.solve_minimal(H, self.pts, np.asarray([sample], dtype=np.int64))
+                if not sv[0]:
+                    continue
+                if n[0] > 0:
+                    found = (models[0, 0].copy(), int(mv[0]))
+                    break
+            self.iteration_number += unsuccessful
+            if found is not None:
+                model, model_valid = found
+                sc = self._score(model, T2, best_score.inliers)
+                if best_score.value < sc.value and model_valid:  # :441-447
+                    best_model, best_score = model, sc
+                    do_lo = self.iteration_number > self.min_iteration_number_before_lo and best_score.inliers > self.m
+                    max_iteration = self._iteration_number_for(best_score.inliers, log_probability)
+            if do_lo:  # :482-503
+                self.lo_number += 1
+                best_model, best_score = self.local_optimization(lo_sampler, best_model, best_score, T2)
+                max_iteration = self._iteration_number_for(best_score.inliers, log_probability)
+        if best_score.inliers <= self.m:
+            return None
+        if self.lo_number == 0:  # :531-544
+            self.lo_number += 1
+            best_model, best_score = self.local_optimization(lo_sampler, best_model, best_score, T2)
+        best_inliers = self._inliers_of(best_model, T2)
+        best_score.inliers = len(best_inliers)
+        refit_applied = False
+        inl, model, success = self.irls(list(best_inliers), best_model, T2)  # :561-590
+        if success:
+            sc = self._score(model, T2, 0)
+            if best_score.value < sc.value:
+                refit_applied = True
+                best_model = model
+                best_inliers = self._inliers_of(best_model, T2)
+        if not refit_applied:  # :592-618
+            fitted, ok = self._fit(best_inliers)
+            if ok:
+                sc = self._score(fitted, T2, 0)
+                if best_score.value < sc.value:
+                    best_model = fitted
+                    best_inliers = self._inliers_of(best_model, T2)
+        self.proposal_inliers = best_inliers
+        return best_model
+
+    # ---- progressive_x.h:565-591 ------------------------------------------------------------------------------------
+    def putative_model_valid(self, model):
+        if len(self.proposal_inliers) < max(self.m, self.min_inliers):
+            return False, None
+        T = 9.0 / 4.0 * self.thr * self.thr
+        pref = O.preference_vector(H, self.pts, model, T)
+        tanimoto = O.tanimoto(pref, self.compound)
+        if self.max_tanimoto < tanimoto:  # NaN compares false -> accepted
+            return False, pref
+        return True, pref
+
+    # ---- PEARL.h:405-472 / 476-555 / 319-401 / 275-315 --------------------------------------------------------------
+    def pearl(self):
+        iteration_number, energy, previous_energy = 0, np.finfo(np.float64).max, -1.0
+        model_rejected, convergence, have_labels = False, False, False
+        labels = np.zeros(self.N, dtype=np.int32)
+        label_cost = float(self.min_inliers)
+        smooth = self.lam > 0.0 and self.idx.size > 0
+        while not convergence:
+            iteration_number += 1
+            if not iteration_number - 1 < 100:
+                break
+            init_with_previous = iteration_number > 1 and not model_rejected
+            L = len(self.models)
+            if L == 0:
+                break
+            flat = np.stack(self.models)
+            D = O.pearl_datacost(H, self.pts, flat, self.thr, self.lam)
+            init = labels.copy() if (init_with_previous and have_labels) else None
+            labels, energy, _ = O.gco_pearl_label(D, self.lam, label_cost, self.off if smooth else None,
+                                                  self.idx if smooth else None, init)
+            labels = np.asarray(labels, dtype=np.int32)
+            have_labels = True
+            changed, model_rejected = False, False
+            per_instance = [[int(i) for i in np.flatnonzero(labels == l)] for l in range(L)]
+            outliers = int(np.sum(labels >= L))
+            before, _ = O.segment_residual_sums(H, self.pts, flat, labels)
+            cand = flat.copy()
+            fitted_ok = [False] * L
+            for l in range(L):
+                if len(per_instance[l]) >= 4:  # nonMinimalSampleSize() (:363-365)
+                    model, ok = self._fit(per_instance[l])
+                    if ok:
+                        cand[l], fitted_ok[l] = model, True
+            after, _ = O.segment_residual_sums(H, self.pts, cand, labels)
+            for l in range(L):
+                if fitted_ok[l] and after[l] < before[l]:  # :393-399
+                    self.models[l] = cand[l].copy()
+                    changed = True
+            for l in range(L - 1, -1, -1):  # rejectInstances, back to front
+                if len(per_instance[l]) < self.min_inliers:
+                    outliers += len(per_instance[l])
+                    del self.models[l]
+                    del self.prefs[l]
+                    del per_instance[l]
+                    model_rejected = True
+            self.pearl_outliers = outliers
+            if not model_rejected and not changed and abs(energy - previous_energy) < 1e-5 and iteration_number > 1:
+                convergence = True
+            previous_energy = energy
+        self.labeling = labels.astype(np.int64)
+
+    def predicted_unseen_inliers(self, iterations, compound_inliers):  # progressive_x.h:495-513
+        unseen = self.N - compound_inliers
+        ratio = math.pow(1.0 - math.pow(1.0 - self.conf, 1.0 / iterations), 1.0 / self.m)
+        return int(round(unseen * ratio))
+
+    # ---- progressive_x.h:251-489 ------------------------------------------------------------------------------------
+    def run(self):
+        total_iterations, unaccepted = 0, 0
+        for it in range(10):  # :272 hard cap
+            model = self.propose((self.seed * 1000003 + it) & M64)
+            if model is None:
+                continue
+            total_iterations += self.iteration_number
+            valid, pref = self.putative_model_valid(model)
+            if not valid:  # :334-346 (the counter is never reset)
+                unaccepted += 1
+                if unaccepted == 10:
+                    break
+                continue
+            self.models.append(model.copy())
+            self.prefs.append(pref)
+            first_stat = 0
+            if len(self.models) == 1:  # :375-385
+                self.labeling[:] = 1
+                self.labeling[self.proposal_inliers] = 0
+                first_stat = 1
+            else:
+                self.pearl()
+            if self.models:  # updateCompoundModel: max over the stored (stale) preference vectors
+                self.compound = O.compound_max(np.stack(self.prefs))
+            if len(self.models) == 1 and first_stat:
+                unseen = self.predicted_unseen_inliers(total_iterations, first_stat)
+            else:
+                unseen = self.predicted_unseen_inliers(total_iterations, self.N - self.pearl_outliers)
+            if unseen < self.min_inliers:
+                break
+            if len(self.models) >= self.max_models:
+                break
+        models = np.stack(self.models) if self.models else np.zeros((0, 9))
+        return models, self.labeling.copy()
+
+
+def find_homographies(corrs, threshold, conf, spatial_coherence_weight, maximum_tanimoto_similarity, max_iters,
+                      minimum_point_number, maximum_model_number, sampler_id, scoring_exponent, seed, graph=None):
+    """findHomographies_ (src/pyprogressivex/src/progressivex_python.cpp:173-304) on the sequential loop above."""
+    px = ProgressiveXOracle(corrs, threshold=threshold, confidence=conf, lam=spatial_coherence_weight,
+                            max_tanimoto=maximum_tanimoto_similarity, max_iters=max_iters, min_inliers=minimum_point_number,
+                            max_models=maximum_model_number, napsac=(sampler_id == 3), exponent=scoring_exponent, seed=seed,
+                            graph=graph)
+    return px.run()

@@ -1,0 +1,68 @@
+"""The GPU driver against a SEQUENTIAL CPU restatement of the reference's control flow (oracle/px_sequential.py).
+
+The driver (progressive-x_b200/csrc/pxb_driver.cu) evaluates blocks of 512 hypotheses per launch, keeps operator chains
+on the device and replays the reference's bookkeeping over them. oracle/px_sequential.py is the reference's loop
+structure itself -- one sample, one solve, one getScore at a time (GCRANSAC.h:203-628), LO cuts and PEARL sweeps by the
+reference's own gco / max-flow build -- on the pinned oracle operators. Same seeds, same neighbourhood graph: the two must
+return the same number of instances and the same per-point labels; model parameters agree within the 1e-5 contract
+(the non-minimal fit is a QR factorisation in the oracle and normal equations on the GPU, ~1e-9 apart).
+"""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import pyprogressivex
+from pyprogressivex import _native
+from pyprogressivex import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+G = np.load(Path(__file__).resolve().parent / "golden" / "reference_scenes.npz")
+
+
+def _compare(corrs, radius, seeds, **kw):
+    from oracle import px_sequential as seq
+    graph = None
+    if kw["spatial_coherence_weight"] > 0 or kw["sampler_id"] == 3:
+        with _native.Context(0) as ctx:
+            ctx.upload_points(_native.MODEL_H, corrs)
+            graph = ctx.knn_graph(radius, 5)
+    agree = 0
+    for seed in seeds:
+        models, labels = pyprogressivex.findHomographies(corrs, 640, 480, 640, 480, neighborhood_ball_radius=radius, seed=seed, **kw)
+        m_o, l_o = seq.find_homographies(corrs, kw["threshold"], kw["conf"], kw["spatial_coherence_weight"],
+                                         kw["maximum_tanimoto_similarity"], kw["max_iters"], kw["minimum_point_number"],
+                                         kw["maximum_model_number"], kw["sampler_id"], kw["scoring_exponent"], seed, graph)
+        M = models.shape[0] // 3
+        same = M == m_o.shape[0] and np.array_equal(labels, l_o.astype(np.int32))
+        if same and M:
+            a, b = models.reshape(M, 9), m_o
+            same = bool(np.all(np.abs(a - b).max(1) <= 1e-5 * np.abs(b).max(1)))
+        agree += same
+    return agree
+
+
+def test_driver_equals_sequential_loop_lambda0():
+    corrs, gt, _ = syn.multi_homography_scene(900, n_planes=3, outlier_ratio=0.35, noise=0.5, seed=5)
+    kw = dict(threshold=2.0, conf=0.9, spatial_coherence_weight=0.0, maximum_tanimoto_similarity=0.4, max_iters=400,
+              minimum_point_number=40, maximum_model_number=-1, sampler_id=0, scoring_exponent=2)
+    assert _compare(corrs, 60.0, (1, 2, 3, 4), **kw) == 4
+
+
+def test_driver_equals_sequential_loop_with_spatial_coherence():
+    """lambda > 0: NAPSAC sampling, LO st-cuts (device assembly vs the reference's BK build), alpha-expansion (device
+    assembly + push-relabel vs the reference's gco build)."""
+    corrs, gt, _ = syn.multi_homography_scene(700, n_planes=2, outlier_ratio=0.35, noise=0.5, seed=8)
+    kw = dict(threshold=2.0, conf=0.9, spatial_coherence_weight=0.05, maximum_tanimoto_similarity=0.4, max_iters=300,
+              minimum_point_number=40, maximum_model_number=6, sampler_id=3, scoring_exponent=2)
+    assert _compare(corrs, 60.0, (1, 2, 3), **kw) == 3
+
+
+@pytest.mark.parametrize("scene", ["unionhouse", "oldclassicswing"])
+def test_driver_equals_sequential_loop_on_adelaide_h(scene):
+    """The reference's AdelaideH call (dataset_comparison/adelaideH.ipynb) on its bundled scenes."""
+    corrs = G[f"{scene}_corrs"]
+    kw = dict(threshold=4.0, conf=0.5, spatial_coherence_weight=0.05, maximum_tanimoto_similarity=0.4, max_iters=1000,
+              minimum_point_number=10, maximum_model_number=6, sampler_id=3, scoring_exponent=2)
+    assert _compare(corrs, 200.0, (1, 2, 3), **kw) >= 2  # an exact energy tie may split one seed
