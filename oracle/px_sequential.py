@@ -19,9 +19,11 @@ chains) and this loop on the same inputs and seeds and compares instance counts,
 What is shared with the GPU driver BY CONSTRUCTION, because the reference leaves it unspecified or non-reproducible
 (DESIGN.md section 8): the random streams (splitmix64, one stream per proposal for the main sampler and one for the
 local-optimisation sampler), the neighbourhood graph (handed in by the caller), and "the inlier list of the current
-best model" in place of the reference's accidental two-buffer ping-pong. Homographies only (the family whose
-non-minimal fit the oracle restates: column-pivoted Householder QR here, 8x8 normal equations on the GPU -- the two
-agree to ~1e-9, which is why models are compared with a tolerance and labels exactly)."""
+best model" in place of the reference's accidental two-buffer ping-pong. Families: homographies (non-minimal fit:
+column-pivoted Householder QR here, 8x8 normal equations on the GPU -- ~1e-9 apart, which is why models are compared with
+a tolerance and labels exactly), vanishing points and 2D lines (findVanishingPoints_ / findLines_,
+progressivex_python.cpp:306-535; weights of the vanishing-point solver are indexed by point). F and PnP are not covered:
+the oracle has no restatement of their non-minimal solvers."""
 from __future__ import annotations
 
 import math
@@ -30,7 +32,7 @@ import numpy as np
 
 from . import oracle as O
 
-H = 0
+H, VP, LINE = 0, 3, 4
 M64 = (1 << 64) - 1
 
 
@@ -112,10 +114,13 @@ class Score:
 
 class ProgressiveXOracle:
     def __init__(self, pts, *, threshold, confidence, lam, max_tanimoto, max_iters, min_inliers, max_models, napsac, exponent,
-                 seed, graph):
+                 seed, graph, family=H, point_weights=None):
         self.pts = np.ascontiguousarray(pts, dtype=np.float64)
         self.N = self.pts.shape[0]
-        self.m = 4
+        self.t = family
+        self.m = 4 if family == H else 2                       # Estimator::sampleSize()
+        self.nonminimal_size = 4 if family == H else 2         # Estimator::nonMinimalSampleSize()
+        self.point_weights = None if point_weights is None else np.ascontiguousarray(point_weights, dtype=np.float64)
         self.thr, self.conf, self.lam, self.max_tanimoto = threshold, confidence, lam, max_tanimoto
         self.max_iters, self.min_inliers = max_iters, min_inliers
         self.max_models = max_models if max_models > 0 else 1 << 62
@@ -136,7 +141,7 @@ class ProgressiveXOracle:
     # ---- operators: every N-point loop is an oracle call -----------------------------------------------------------
     def _score(self, model, T2, best_inliers):
         cp = self.compound if self.models else None
-        cnt, val, shr = O.score_batch(H, self.pts, model, T2, cp)
+        cnt, val, shr = O.score_batch(self.t, self.pts, model, T2, cp)
         cnt, val, shr = int(cnt[0]), float(val[0]), float(shr[0])
         if cnt + 1 < best_inliers:  # scoring_function_with_compound_model.h:105-106
             return Score()
@@ -144,14 +149,18 @@ class ProgressiveXOracle:
         return Score(cnt, value)
 
     def _inliers_of(self, model, T2):
-        r2, _ = O.residual_matrix(H, self.pts, model, T2, want_mask=False)
+        r2, _ = O.residual_matrix(self.t, self.pts, model, T2, want_mask=False)
         return [int(i) for i in np.flatnonzero(r2[0] < T2)]
 
-    def _fit(self, idx, weights_by_row=None):
-        return O.fit_h_nonminimal(self.pts, idx, weights_by_row)
+    def _fit(self, idx, weights=None):
+        """Estimator::estimateModelNonminimal. H reads weights_[row of the gathered sample]; the vanishing-point solver
+        reads weights_[point index] (solver_vanishing_point_two_lines.h:203); the line solver never reads them."""
+        if self.t == H:
+            return O.fit_h_nonminimal(self.pts, idx, weights)
+        return O.fit_nonminimal(self.t, self.pts, idx, weights if self.t == VP else None)
 
     def _lo_labeling(self, model):  # GCRANSAC.h:914-1022
-        d, e0, e1 = O.lo_unary_terms(H, self.pts, model, self.thr, self.lam)
+        d, e0, e1 = O.lo_unary_terms(self.t, self.pts, model, self.thr, self.lam)
         if not (self.lam > 0) or self.idx.size == 0:
             return [int(i) for i in np.flatnonzero(e1 - e0 < 0)]
         seg, _ = O.gco_lo_labeling(e0, e1, d, self.lam, self.off, self.idx)
@@ -204,11 +213,11 @@ class ProgressiveXOracle:
             iterations += 1
             if not iterations < self.max_least_squares_iterations:
                 break
-            weights = O.tukey_weights(H, self.pts, model, T2)
+            weights = O.tukey_weights(self.t, self.pts, model, T2)
             w_point = np.zeros(self.N)
             w_point[inliers] = weights[inliers]
-            w_row = w_point[:len(inliers)].copy()  # the solver reads weights_[row] (reference quirk)
-            fitted, ok = self._fit(inliers, w_row)
+            w_row = w_point[:len(inliers)].copy()  # the H solver reads weights_[row] (reference quirk)
+            fitted, ok = self._fit(inliers, w_point if self.t == VP else w_row)
             if not ok:
                 break
             sc = self._score(fitted, T2, 0)
@@ -244,7 +253,7 @@ class ProgressiveXOracle:
                 sample = main.sample(pool, self.m)
                 if sample is None:
                     continue
-                models, n, sv, mv = O.solve_minimal(H, self.pts, np.asarray([sample], dtype=np.int64))
+                models, n, sv, mv = O.solve_minimal(self.t, self.pts, np.asarray([sample], dtype=np.int64))
                 if not sv[0]:
                     continue
                 if n[0] > 0:
@@ -292,7 +301,7 @@ class ProgressiveXOracle:
         if len(self.proposal_inliers) < max(self.m, self.min_inliers):
             return False, None
         T = 9.0 / 4.0 * self.thr * self.thr
-        pref = O.preference_vector(H, self.pts, model, T)
+        pref = O.preference_vector(self.t, self.pts, model, T)
         tanimoto = O.tanimoto(pref, self.compound)
         if self.max_tanimoto < tanimoto:  # NaN compares false -> accepted
             return False, pref
@@ -314,7 +323,7 @@ class ProgressiveXOracle:
             if L == 0:
                 break
             flat = np.stack(self.models)
-            D = O.pearl_datacost(H, self.pts, flat, self.thr, self.lam)
+            D = O.pearl_datacost(self.t, self.pts, flat, self.thr, self.lam)
             init = labels.copy() if (init_with_previous and have_labels) else None
             labels, energy, _ = O.gco_pearl_label(D, self.lam, label_cost, self.off if smooth else None,
                                                   self.idx if smooth else None, init)
@@ -323,15 +332,15 @@ class ProgressiveXOracle:
             changed, model_rejected = False, False
             per_instance = [[int(i) for i in np.flatnonzero(labels == l)] for l in range(L)]
             outliers = int(np.sum(labels >= L))
-            before, _ = O.segment_residual_sums(H, self.pts, flat, labels)
+            before, _ = O.segment_residual_sums(self.t, self.pts, flat, labels)
             cand = flat.copy()
             fitted_ok = [False] * L
             for l in range(L):
-                if len(per_instance[l]) >= 4:  # nonMinimalSampleSize() (:363-365)
-                    model, ok = self._fit(per_instance[l])
+                if len(per_instance[l]) >= self.nonminimal_size:  # nonMinimalSampleSize() (:363-365)
+                    model, ok = self._fit(per_instance[l], self.point_weights if self.t == VP else None)  # :373-380
                     if ok:
                         cand[l], fitted_ok[l] = model, True
-            after, _ = O.segment_residual_sums(H, self.pts, cand, labels)
+            after, _ = O.segment_residual_sums(self.t, self.pts, cand, labels)
             for l in range(L):
                 if fitted_ok[l] and after[l] < before[l]:  # :393-399
                     self.models[l] = cand[l].copy()
@@ -387,7 +396,7 @@ class ProgressiveXOracle:
                 break
             if len(self.models) >= self.max_models:
                 break
-        models = np.stack(self.models) if self.models else np.zeros((0, 9))
+        models = np.stack(self.models) if self.models else np.zeros((0, O.MSIZE[self.t]))
         return models, self.labeling.copy()
 
 
@@ -398,4 +407,15 @@ def find_homographies(corrs, threshold, conf, spatial_coherence_weight, maximum_
                             max_tanimoto=maximum_tanimoto_similarity, max_iters=max_iters, min_inliers=minimum_point_number,
                             max_models=maximum_model_number, napsac=(sampler_id == 3), exponent=scoring_exponent, seed=seed,
                             graph=graph)
+    return px.run()
+
+
+def find_points_family(family, rows, weights, threshold, conf, spatial_coherence_weight, maximum_tanimoto_similarity, max_iters,
+                       minimum_point_number, maximum_model_number, sampler_id, scoring_exponent, seed, graph=None):
+    """findVanishingPoints_ / findLines_ (progressivex_python.cpp:306-535) on the sequential loop: family = VP or LINE."""
+    napsac = family == LINE and sampler_id == 2
+    px = ProgressiveXOracle(rows, threshold=threshold, confidence=conf, lam=spatial_coherence_weight,
+                            max_tanimoto=maximum_tanimoto_similarity, max_iters=max_iters, min_inliers=minimum_point_number,
+                            max_models=maximum_model_number, napsac=napsac, exponent=scoring_exponent, seed=seed, graph=graph,
+                            family=family, point_weights=weights if family == VP else None)
     return px.run()

@@ -66,3 +66,39 @@ def test_driver_equals_sequential_loop_on_adelaide_h(scene):
     kw = dict(threshold=4.0, conf=0.5, spatial_coherence_weight=0.05, maximum_tanimoto_similarity=0.4, max_iters=1000,
               minimum_point_number=10, maximum_model_number=6, sampler_id=3, scoring_exponent=2)
     assert _compare(corrs, 200.0, (1, 2, 3), **kw) >= 2  # an exact energy tie may split one seed
+
+
+def _models_match(a, b, tol):
+    """rows of a and b agree up to a global sign per row (vanishing points / lines are homogeneous)"""
+    if a.shape != b.shape:
+        return False
+    for x, y in zip(a, b):
+        s = 1.0 if np.dot(x, y) >= 0 else -1.0
+        if not np.all(np.abs(s * x - y) <= tol * max(1.0, np.abs(y).max())):
+            return False
+    return True
+
+
+def test_driver_equals_sequential_loop_vanishing_points():
+    from oracle import px_sequential as seq
+    seg, gt, vps = syn.multi_vanishing_point_scene(800, n_vps=3, outlier_ratio=0.3, noise=0.3, seed=23)
+    w = np.random.default_rng(1).uniform(0.5, 1.0, len(seg))
+    kw = dict(threshold=2.0, conf=0.9, spatial_coherence_weight=0.0, maximum_tanimoto_similarity=0.4, max_iters=400,
+              minimum_point_number=40, maximum_model_number=-1, sampler_id=0, scoring_exponent=2)
+    for seed in (1, 2, 3):
+        models, labels = pyprogressivex.findVanishingPoints(seg, w, 1024, 768, neighborhood_ball_radius=60.0, seed=seed, **kw)
+        m_o, l_o = seq.find_points_family(seq.VP, seg, w, kw["threshold"], kw["conf"], 0.0, 0.4, 400, 40, -1, 0, 2, seed)
+        assert np.array_equal(labels, l_o.astype(np.int32))
+        assert _models_match(models, m_o, 1e-7)
+
+
+def test_driver_equals_sequential_loop_lines():
+    from oracle import px_sequential as seq
+    pts, gt, lines = syn.multi_line_scene(700, n_lines=3, outlier_ratio=0.3, noise=0.5, seed=29)
+    kw = dict(threshold=2.0, conf=0.95, spatial_coherence_weight=0.0, maximum_tanimoto_similarity=0.4, max_iters=600,
+              minimum_point_number=40, maximum_model_number=-1, sampler_id=0, scoring_exponent=2)
+    for seed in (1, 2, 3):
+        models, labels = pyprogressivex.findLines(pts, None, 1024, 768, neighborhood_ball_radius=60.0, seed=seed, **kw)
+        m_o, l_o = seq.find_points_family(seq.LINE, pts, None, kw["threshold"], kw["conf"], 0.0, 0.4, 600, 40, -1, 0, 2, seed)
+        assert np.array_equal(labels, l_o.astype(np.int32))
+        assert _models_match(models, m_o, 1e-7)
