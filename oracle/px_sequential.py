@@ -105,6 +105,43 @@ class NapsacSampler:  # gcr/samplers/napsac_sampler.h:102-151 (incl. the point-i
         return subset if attempts < 100 else None
 
 
+class ProsacSampler:  # gcr/samplers/prosac_sampler.h (reset() state per proposal, progressive_x.h:290-291)
+    def __init__(self, seed, m, N):
+        self.rng, self.m, self.N = Rng(seed), m, N
+        self.convergence, self.kth, self.subset_size, self.gen_max = 100000, 1, m, m - 1
+        self.growth = [0] * N
+        T_n = float(self.convergence)
+        for i in range(m):
+            T_n *= (m - i) / (N - i)
+        T_n_prime = 1
+        for i in range(N):
+            if i + 1 <= m:
+                self.growth[i] = T_n_prime
+                continue
+            Tn_plus1 = (i + 1) * T_n / (i + 1 - m)
+            self.growth[i] = T_n_prime + (int(math.ceil(Tn_plus1 - T_n)) & 0xFFFFFFFF)
+            T_n = Tn_plus1
+            T_n_prime = self.growth[i]
+
+    def _increment(self):
+        self.kth += 1
+        if self.kth > self.convergence:
+            self.gen_max = self.N - 1
+        elif self.kth > self.growth[self.subset_size - 1]:
+            self.subset_size = min(self.subset_size + 1, self.N)
+            self.gen_max = self.subset_size - 2
+
+    def sample(self, pool, m):
+        if m != self.m:
+            self._increment()
+            return None
+        if self.kth > self.convergence:
+            return self.rng.unique_set(m, self.gen_max)
+        out = self.rng.unique_set(m - 1, self.gen_max) + [self.subset_size - 1]
+        self._increment()
+        return out
+
+
 class Score:
     __slots__ = ("inliers", "value")
 
@@ -114,7 +151,7 @@ class Score:
 
 class ProgressiveXOracle:
     def __init__(self, pts, *, threshold, confidence, lam, max_tanimoto, max_iters, min_inliers, max_models, napsac, exponent,
-                 seed, graph, family=H, point_weights=None):
+                 seed, graph, family=H, point_weights=None, prosac=False):
         self.pts = np.ascontiguousarray(pts, dtype=np.float64)
         self.N = self.pts.shape[0]
         self.t = family
@@ -125,6 +162,7 @@ class ProgressiveXOracle:
         self.max_iters, self.min_inliers = max_iters, min_inliers
         self.max_models = max_models if max_models > 0 else 1 << 62
         self.napsac, self.exponent, self.seed = napsac, int(exponent), seed
+        self.prosac = prosac
         self.off, self.idx = graph if graph is not None else (np.zeros(self.N + 1, np.int32), np.zeros(0, np.int32))
         # gcransac::utils::Settings as overridden by progressive_x.h:64-71
         self.min_iteration_number = 20
@@ -237,6 +275,8 @@ class ProgressiveXOracle:
         T2 = tt * tt
         if self.napsac and self.idx.size:
             main = NapsacSampler((round_seed * 2 + 1) & M64, self.off, self.idx)
+        elif self.prosac and self.N > self.m:
+            main = ProsacSampler((round_seed * 2 + 1) & M64, self.m, self.N)
         else:
             main = UniformSampler((round_seed * 2 + 1) & M64)
         lo_sampler = UniformSampler((round_seed * 2 + 2) & M64)
@@ -406,7 +446,7 @@ def find_homographies(corrs, threshold, conf, spatial_coherence_weight, maximum_
     px = ProgressiveXOracle(corrs, threshold=threshold, confidence=conf, lam=spatial_coherence_weight,
                             max_tanimoto=maximum_tanimoto_similarity, max_iters=max_iters, min_inliers=minimum_point_number,
                             max_models=maximum_model_number, napsac=(sampler_id == 3), exponent=scoring_exponent, seed=seed,
-                            graph=graph)
+                            graph=graph, prosac=(sampler_id == 1))
     return px.run()
 
 
@@ -417,5 +457,5 @@ def find_points_family(family, rows, weights, threshold, conf, spatial_coherence
     px = ProgressiveXOracle(rows, threshold=threshold, confidence=conf, lam=spatial_coherence_weight,
                             max_tanimoto=maximum_tanimoto_similarity, max_iters=max_iters, min_inliers=minimum_point_number,
                             max_models=maximum_model_number, napsac=napsac, exponent=scoring_exponent, seed=seed, graph=graph,
-                            family=family, point_weights=weights if family == VP else None)
+                            family=family, point_weights=weights if family == VP else None, prosac=(sampler_id == 1))
     return px.run()

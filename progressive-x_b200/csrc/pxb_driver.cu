@@ -25,7 +25,8 @@
 //   * neighbourhood graph: exact kNN-in-radius on the GPU instead of randomised FLANN;
 //   * the reference's two-buffer inlier ping-pong (GCRANSAC.h:244-252,:546-552) is replaced by "the inlier list of the
 //     current best model" -- the reference's version depends on list-size coincidences;
-//   * samplers 1 (PROSAC) and 2 (P-NAPSAC) fall back to uniform sampling (host-only RNG state machines, out of scope);
+//   * sampler 2 (P-NAPSAC) falls back to uniform sampling (multi-layer grid neighbourhoods are not built); PROSAC (1),
+//     NAPSAC (3; id 2 for lines) and uniform (0) follow the reference's state machines;
 //   * non-minimal fits ("next"): H through the 8x8 normal equations (same least-squares solution as
 //     the reference's QR); F as normalised 8-point + rank-2 projection and PnP as normalised DLT + 10 LM steps, i.e.
 //     without PoseLib's bundle adjustment / OpenCV's EPnP (pxb_fit_fp.cu); DEGENSAC is not applied to F.
@@ -150,6 +151,54 @@ struct NapsacSampler : Sampler { // gcr/samplers/napsac_sampler.h:102-151
 			break;
 		}
 		return attempts < maximum_iterations;
+	}
+};
+
+// gcr/samplers/prosac_sampler.h: samples are drawn from a pool that grows along the (quality-ordered) point list; the
+// newest point of the pool is always part of the sample. reset() state per proposal (progressive_x.h:290-291).
+struct ProsacSampler : Sampler {
+	Rng rng;
+	size_t sample_size, point_number, convergence = 100000, kth = 1, subset_size, gen_max;
+	std::vector<size_t> growth;
+	ProsacSampler(uint64_t seed, size_t m, size_t N) : rng(seed), sample_size(m), point_number(N), subset_size(m), gen_max(m - 1) {
+		growth.assign(N, 0); // :initialize
+		double T_n = (double)convergence;
+		for (size_t i = 0; i < m; i++) T_n *= static_cast<double>(m - i) / (double)(N - i);
+		size_t T_n_prime = 1;
+		for (size_t i = 0; i < N; ++i) {
+			if (i + 1 <= m) {
+				growth[i] = T_n_prime;
+				continue;
+			}
+			const double Tn_plus1 = static_cast<double>(i + 1) * T_n / (double)(i + 1 - m);
+			growth[i] = T_n_prime + (unsigned int)std::ceil(Tn_plus1 - T_n);
+			T_n = Tn_plus1;
+			T_n_prime = growth[i];
+		}
+	}
+	void increment() { // incrementIterationNumber
+		++kth;
+		if (kth > convergence) {
+			gen_max = point_number - 1;
+		} else if (kth > growth[subset_size - 1]) {
+			++subset_size;
+			if (subset_size > point_number) subset_size = point_number;
+			gen_max = subset_size - 2;
+		}
+	}
+	bool sample(const std::vector<size_t> &, size_t *subset, size_t m) override {
+		if (m != sample_size) { // "PROSAC is not yet implemented to change the sample size"
+			increment();
+			return false;
+		}
+		if (kth > convergence) {
+			rng.unique_set(subset, m, gen_max);
+			return true;
+		}
+		rng.unique_set(subset, m - 1, gen_max);
+		subset[m - 1] = subset_size - 1; // the last index is the point at the end of the current pool
+		increment();
+		return true;
 	}
 };
 
@@ -551,6 +600,8 @@ int Driver::propose(uint64_t round_seed, std::vector<double> &model_out, bool &f
 	std::unique_ptr<Sampler> main_sampler;
 	if (s_.napsac && !graph_.idx.empty())
 		main_sampler.reset(new NapsacSampler(round_seed * 2 + 1, &graph_));
+	else if (s_.sampler_id == 1 && (size_t)N_ > (size_t)m_)
+		main_sampler.reset(new ProsacSampler(round_seed * 2 + 1, (size_t)m_, (size_t)N_));
 	else
 		main_sampler.reset(new UniformSampler(round_seed * 2 + 1));
 	UniformSampler lo_sampler(round_seed * 2 + 2);

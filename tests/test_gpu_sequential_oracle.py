@@ -102,3 +102,13 @@ def test_driver_equals_sequential_loop_lines():
         m_o, l_o = seq.find_points_family(seq.LINE, pts, None, kw["threshold"], kw["conf"], 0.0, 0.4, 600, 40, -1, 0, 2, seed)
         assert np.array_equal(labels, l_o.astype(np.int32))
         assert _models_match(models, m_o, 1e-7)
+
+
+def test_driver_equals_sequential_loop_prosac():
+    """sampler_id = 1: the PROSAC state machine (growth function, pool growth, newest point always sampled)."""
+    corrs, gt, _ = syn.multi_homography_scene(800, n_planes=2, outlier_ratio=0.3, noise=0.5, seed=12)
+    order = np.argsort(np.where(gt >= 0, 0, 1), kind="stable")  # "quality" order: structure points first
+    corrs = np.ascontiguousarray(corrs[order])
+    kw = dict(threshold=2.0, conf=0.9, spatial_coherence_weight=0.0, maximum_tanimoto_similarity=0.4, max_iters=300,
+              minimum_point_number=40, maximum_model_number=-1, sampler_id=1, scoring_exponent=2)
+    assert _compare(corrs, 60.0, (1, 2, 3), **kw) == 3
