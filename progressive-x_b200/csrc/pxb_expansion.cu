@@ -112,17 +112,17 @@ __device__ void mf_global_relabel(const FlowGraphDev &G, int32_t *h, cg::grid_gr
 // One asynchronous push-relabel step of node u (Hong & He's lock-free rule: push to the LOWEST residual neighbour if it
 // is lower, else lift to one above it). Only the owner thread of u lowers excess[u] / cap[out-arcs of u] and writes
 // height[u]; everybody else only adds to them, so the atomics below can never drive a value negative.
-__device__ __forceinline__ void mf_process(const FlowGraphDev &G, volatile int32_t *h, int u) {
+__device__ __forceinline__ bool mf_process(const FlowGraphDev &G, volatile int32_t *h, int u) {
 	const int n = G.n;
 	volatile double *excess = G.excess, *cap = G.cap;
 	const double e = excess[u];
 	const int hu = h[u];
-	if (!(e > 0.0) || hu >= n) return;
+	if (!(e > 0.0) || hu >= n) return false;
 	if (G.sink_cap[u] > 0.0) { // the sink (height 0) is always the lowest neighbour
 		const double d = fmin(e, G.sink_cap[u]);
 		G.sink_cap[u] -= d;
 		atomicAdd(&G.excess[u], -d);
-		return;
+		return true;
 	}
 	const int a0 = G.arc_off[u], a1 = G.arc_off[u + 1];
 	if (a1 - a0 > kWideDegree) {
@@ -151,7 +151,7 @@ __device__ __forceinline__ void mf_process(const FlowGraphDev &G, volatile int32
 				if (cap[a] > 0.0) lowest = min(lowest, (int)h[G.arc_head[a]]);
 			h[u] = lowest == 0x7fffffff ? n : min(max(lowest + 1, hu), n);
 		}
-		return;
+		return true;
 	}
 	int best_h = 0x7fffffff, best_a = -1;
 	for (int a = a0; a < a1; ++a)
@@ -164,7 +164,7 @@ __device__ __forceinline__ void mf_process(const FlowGraphDev &G, volatile int32
 		}
 	if (best_a < 0) { // no residual arc at all: the excess is stranded on the source side
 		h[u] = n;
-		return;
+		return true;
 	}
 	if (hu > best_h) {
 		const double d = fmin(e, cap[best_a]);
@@ -175,13 +175,14 @@ __device__ __forceinline__ void mf_process(const FlowGraphDev &G, volatile int32
 	} else {
 		h[u] = min(best_h + 1, n);
 	}
+	return true;
 }
 
 // Block-cooperative discharge of one wide node: every thread looks at a strided share of the arcs, the node's excess is
 // handed out in arc order by a block-wide exclusive prefix sum of the eligible capacities (lower residual neighbours),
 // and the node is lifted when excess remains after every lower neighbour has been saturated. Same rule as the
 // single-thread wide branch of mf_process, ~100x fewer dependent memory round trips per visit.
-__device__ void mf_process_wide_block(const FlowGraphDev &G, volatile int32_t *h, int u) {
+__device__ bool mf_process_wide_block(const FlowGraphDev &G, volatile int32_t *h, int u) {
 	__shared__ double s_e, s_wsum[kMfThreads / 32], s_gsum[kMfThreads / 32];
 	__shared__ int s_hu, s_wlow[kMfThreads / 32];
 	const int n = G.n, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -193,47 +194,61 @@ __device__ void mf_process_wide_block(const FlowGraphDev &G, volatile int32_t *h
 	__syncthreads();
 	const double e = s_e;
 	const int hu = s_hu;
-	if (!(e > 0.0) || hu >= n) return; // block-uniform
+	if (!(e > 0.0) || hu >= n) return false; // block-uniform
 	const int a0 = G.arc_off[u], a1 = G.arc_off[u + 1];
 	double rem = e, given = 0.0;
 	int lowest = 0x7fffffff;
-	for (int base = a0; base < a1; base += kMfThreads) { // block-uniform trip count
-		const int a = base + threadIdx.x;
-		double want = 0.0;
-		int v = 0;
-		if (a < a1) {
-			const double c = cap[a];
-			if (c > 0.0) {
-				v = G.arc_head[a];
-				const int hv = h[v];
-				if (hv < hu) want = c;
-				else lowest = min(lowest, hv);
+	// Two passes over the arcs. Pass 0 hands every lower neighbour only what its own sink link can still absorb (those
+	// units leave the graph on the neighbour's next visit instead of trickling on through lambda-sized n-links); pass 1
+	// pushes whatever is left up to the arc capacities. Both are ordinary pushes to lower residual neighbours.
+	for (int pass = 0; pass < 2; ++pass) {
+		for (int base = a0; base < a1; base += kMfThreads) { // block-uniform trip count
+			const int a = base + threadIdx.x;
+			double want = 0.0;
+			int v = 0;
+			if (a < a1) {
+				const double c = cap[a];
+				if (c > 0.0) {
+					v = G.arc_head[a];
+					const int hv = h[v];
+					if (hv < hu) {
+						if (pass == 0) {
+							const volatile double *sc = G.sink_cap;
+							want = fmin(c, fmax(0.0, sc[v] - excess[v]));
+						} else {
+							want = c;
+						}
+					} else if (pass == 1) {
+						lowest = min(lowest, hv);
+					}
+				}
 			}
-		}
-		double incl = want;
+			double incl = want;
 #pragma unroll
-		for (int o = 1; o < 32; o <<= 1) {
-			const double t = __shfl_up_sync(0xffffffffu, incl, o);
-			if (lane >= o) incl += t;
-		}
-		if (lane == 31) s_wsum[warp] = incl;
-		__syncthreads();
-		double before = 0.0, total = 0.0;
+			for (int o = 1; o < 32; o <<= 1) {
+				const double t = __shfl_up_sync(0xffffffffu, incl, o);
+				if (lane >= o) incl += t;
+			}
+			if (lane == 31) s_wsum[warp] = incl;
+			__syncthreads();
+			double before = 0.0, total = 0.0;
 #pragma unroll
-		for (int w = 0; w < kMfThreads / 32; ++w) {
-			if (w < warp) before += s_wsum[w];
-			total += s_wsum[w];
+			for (int w = 0; w < kMfThreads / 32; ++w) {
+				if (w < warp) before += s_wsum[w];
+				total += s_wsum[w];
+			}
+			const double excl = before + incl - want;
+			const double give = fmin(want, fmax(0.0, rem - excl));
+			if (give > 0.0) {
+				atomicAdd(&G.cap[a], -give);
+				atomicAdd(&G.cap[G.arc_rev[a]], give);
+				atomicAdd(&G.excess[v], give);
+			}
+			given += give;
+			rem = fmax(0.0, rem - total);
+			__syncthreads(); // s_wsum is reused by the next chunk
+			if (!(rem > 0.0)) break; // block-uniform
 		}
-		const double excl = before + incl - want;
-		const double give = fmin(want, fmax(0.0, rem - excl));
-		if (give > 0.0) {
-			atomicAdd(&G.cap[a], -give);
-			atomicAdd(&G.cap[G.arc_rev[a]], give);
-			atomicAdd(&G.excess[v], give);
-		}
-		given += give;
-		rem = fmax(0.0, rem - total);
-		__syncthreads(); // s_wsum is reused by the next chunk
 		if (!(rem > 0.0)) break; // block-uniform
 	}
 	// what left the node, and the lowest neighbour that is still residual but not lower
@@ -258,6 +273,7 @@ __device__ void mf_process_wide_block(const FlowGraphDev &G, volatile int32_t *h
 		if (rem > 0.0) h[u] = low == 0x7fffffff ? n : min(max(low + 1, hu), n);
 	}
 	__syncthreads();
+	return true;
 }
 
 constexpr int kAsyncCycles = 192;
@@ -283,9 +299,18 @@ __global__ void __launch_bounds__(kMfThreads) k_maxflow(FlowGraphDev G) {
 		grid.sync();
 		if (G.flags[3 + (round % 3)] == 0) break;
 		// asynchronous phase: no barriers, every thread keeps discharging its own nodes
+		// A block whose nodes have been quiet for two checks in a row stops sweeping; flow that reaches it later from
+		// another block is picked up after the next relabel (the active test above decides termination, not this).
+		bool busy = false;
+		int idle_checks = 0;
 		for (int c = 0; c < kAsyncCycles; ++c) {
-			for (int w = blockIdx.x; w < G.wide_count; w += gridDim.x) mf_process_wide_block(G, h, G.wide_begin + w);
-			for (int u = tid; u < G.wide_begin; u += nthreads) mf_process(G, h, u);
+			for (int w = blockIdx.x; w < G.wide_count; w += gridDim.x) busy |= mf_process_wide_block(G, h, G.wide_begin + w);
+			for (int u = tid; u < G.wide_begin; u += nthreads) busy |= mf_process(G, h, u);
+			if ((c & 7) == 7) {
+				idle_checks = __syncthreads_or(busy) ? 0 : idle_checks + 1;
+				busy = false;
+				if (idle_checks >= 2) break; // block-uniform
+			}
 		}
 		__threadfence();
 		grid.sync();
@@ -653,6 +678,58 @@ double compute_energy(const ExpansionProblem &P, const std::vector<int32_t> &lab
 		if (used[l]) lc += P.label_cost;
 	return data + smooth + lc;
 }
+
+// The same value without walking every edge for every candidate labelling. The smooth term adds either lambda or 0 per
+// neighbour pair, so its sequentially accumulated value depends only on HOW MANY pairs disagree (adding 0.0 changes
+// nothing): smooth = lambda added k times, tabulated once. k is maintained incrementally from the sites that switch.
+// The data term is re-summed sequentially over all sites (N additions), the label term over the used labels.
+struct EnergyCache {
+	std::vector<double> lambda_times; // lambda_times[k] = ((lambda + lambda) + ...) k terms, sequentially rounded
+	int64_t pairs = 0;                // disagreeing neighbour pairs of the current labelling
+	static int64_t count_pairs(const ExpansionProblem &P, const std::vector<int32_t> &lab) {
+		int64_t k = 0;
+		for (int64_t i = 0; i < P.N; ++i)
+			for (int32_t e = P.goff[i]; e < P.goff[i + 1]; ++e) {
+				const int32_t nb = P.gidx[e];
+				if (nb < i && lab[i] != lab[nb]) ++k;
+			}
+		return k;
+	}
+	void init(const ExpansionProblem &P, const std::vector<int32_t> &lab) {
+		const size_t total = (size_t)P.goff[P.N] / 2 + 1;
+		lambda_times.resize(total + 1);
+		double acc = 0;
+		for (size_t k = 0; k <= total; ++k) {
+			lambda_times[k] = acc;
+			acc += 1.0 * P.lambda;
+		}
+		pairs = count_pairs(P, lab);
+	}
+	// pairs of `cand`, which differs from `lab` exactly on `switched` (all of which take the label alpha)
+	int64_t pairs_after(const ExpansionProblem &P, const std::vector<int32_t> &lab, const std::vector<int32_t> &cand,
+	                    const std::vector<int32_t> &switched) const {
+		int64_t k = pairs;
+		for (int32_t s2 : switched)
+			for (int32_t e = P.goff[s2]; e < P.goff[s2 + 1]; ++e) {
+				const int32_t nb = P.gidx[e];
+				// every entry of a site's list is one neighbour pair; a pair between two switched sites appears in both
+				// lists and is taken from the larger index only
+				if (cand[nb] != lab[nb] && nb > s2) continue;
+				k += (int64_t)(cand[s2] != cand[nb]) - (int64_t)(lab[s2] != lab[nb]);
+			}
+		return k;
+	}
+	double energy(const ExpansionProblem &P, const std::vector<int32_t> &lab, int64_t k) const {
+		double data = 0;
+		for (int64_t i = 0; i < P.N; ++i) data += P.D[i * P.L1 + lab[i]];
+		std::vector<char> used((size_t)P.L1, 0);
+		for (int64_t i = 0; i < P.N; ++i) used[lab[i]] = 1;
+		double lc = 0;
+		for (int l = P.L1 - 1; l >= 0; --l)
+			if (used[l]) lc += P.label_cost;
+		return data + lambda_times[(size_t)k] + lc;
+	}
+};
 } // namespace
 
 // ---- device-side assembly of one expansion move ------------------------------------------------------------------
@@ -753,6 +830,11 @@ int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t
                            const int32_t *init_labels_dev, int32_t *labels_out_dev, double *energy_out_host) {
 	// The data costs and the labelling are mirrored on the host: the labelling energies that decide whether a move is
 	// kept are evaluated there in the reference's sequential summation order (compute_energy).
+	const auto t_call = std::chrono::steady_clock::now();
+	double ms_setup = 0, ms_cut = 0, ms_energy = 0, ms_push = 0;
+	auto since = [](std::chrono::steady_clock::time_point t0) {
+		return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+	};
 	std::vector<double> D((size_t)N * L1);
 	std::vector<int32_t> off((size_t)N + 1), idx((size_t)std::max<int64_t>(n_dir_edges, 1)), lab((size_t)N, 0);
 	cudaStream_t st = ctx->stream;
@@ -841,6 +923,7 @@ int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t
 		return PXB_OK;
 	};
 	PXB_TRY(push_labelling());
+	ms_setup = since(t_call);
 
 	FlowGraphDev G;
 	G.n = n;
@@ -863,9 +946,11 @@ int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t
 	PXB_TRY(ctx->reserve_pinned(sizeof(int32_t) * ((size_t)n + 16)));
 	int32_t *h_host = static_cast<int32_t *>(ctx->pinned), *flags_host = h_host + n;
 
-	double new_energy = compute_energy(P, lab), old_energy; // always the energy of `lab` (compute_energy is a pure function)
-	std::vector<int32_t> cand;
-	const bool stats = getenv("PXB_MF_STATS") != nullptr;
+	EnergyCache ec;
+	ec.init(P, lab);
+	double new_energy = ec.energy(P, lab, ec.pairs), old_energy; // always the energy of `lab`
+	std::vector<int32_t> cand, switched;
+	const bool stats = getenv("PXB_MF_STATS") != nullptr, check_energy = getenv("PXB_CHECK_ENERGY") != nullptr;
 	for (int cycle = 1; cycle <= 1000; ++cycle) { // GCoptimization.cpp:1062-1077
 		old_energy = new_energy;
 		for (int alpha = 0; alpha < L1; ++alpha) { // oneExpansionIteration, fixed label order 0..L
@@ -884,27 +969,41 @@ int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t
 				set_error("max-flow did not converge within %d relabel rounds", kMaxRounds);
 				return PXB_ERR_CUDA;
 			}
-			if (stats)
+			ms_cut += since(t_move);
+			const auto t_en = std::chrono::steady_clock::now();
+			if (stats && getenv("PXB_MF_STATS")[0] == '2')
 				fprintf(stderr, "[pxb expansion] alpha=%d active=%d rounds=%d bfs_levels=%d relabel=%.2f ms async=%.2f ms wall=%.2f ms\n",
 				        alpha, (int)(N - label_count[alpha]), flags_host[6], flags_host[8], (double)flags_host[10] * 64 / 1.965e6,
 				        (double)flags_host[12] * 64 / 1.965e6,
 				        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_move).count());
 			// candidate labelling: SOURCE side (cannot reach the sink) takes alpha (:451-469)
-			bool any_switch = false;
 			cand = lab;
+			switched.clear();
 			for (int64_t i = 0; i < N; ++i)
 				if (lab[i] != alpha && !(h_host[i] < n)) {
 					cand[i] = alpha;
-					any_switch = true;
+					switched.push_back((int32_t)i);
 				}
-			if (!any_switch) continue;
+			if (switched.empty()) {
+				ms_energy += since(t_en);
+				continue;
+			}
 			// the reference applies the move iff afterExpansionEnergy < m_beforeExpansionEnergy (:1286); both are the
-			// energies of the two labellings, evaluated here directly
-			const double before = new_energy, after = compute_energy(P, cand);
+			// energies of the two labellings, evaluated here directly (in the reference's summation order)
+			const int64_t k_after = ec.pairs_after(P, lab, cand, switched);
+			const double before = new_energy, after = ec.energy(P, cand, k_after);
+			if (check_energy && after != compute_energy(P, cand)) { // PXB_CHECK_ENERGY=1: the full edge walk must agree bit for bit
+				set_error("incremental labelling energy %.17g differs from the full evaluation %.17g", after, compute_energy(P, cand));
+				return PXB_ERR_STATE;
+			}
+			ms_energy += since(t_en);
 			if (after < before) {
+				const auto t_p = std::chrono::steady_clock::now();
 				lab.swap(cand);
 				new_energy = after;
+				ec.pairs = k_after;
 				PXB_TRY(push_labelling());
+				ms_push += since(t_p);
 			}
 		}
 		if (new_energy == old_energy) break;
@@ -912,6 +1011,9 @@ int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t
 	*energy_out_host = new_energy;
 	PXB_CUDA(cudaMemcpyAsync(labels_out_dev, lab.data(), sizeof(int32_t) * (size_t)N, cudaMemcpyHostToDevice, st));
 	PXB_CUDA(cudaStreamSynchronize(st));
+	if (stats)
+		fprintf(stderr, "[pxb expansion] labelling: N=%lld L1=%d total %.2f ms = setup %.2f + cuts %.2f + energies %.2f + rewiring %.2f\n",
+		        (long long)N, L1, since(t_call), ms_setup, ms_cut, ms_energy, ms_push);
 	return PXB_OK;
 }
 

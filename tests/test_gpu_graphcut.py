@@ -31,8 +31,9 @@ def _assert_equal_up_to_exact_ties(oracle, D, lam, label_cost, off, idx, lab, la
 
 @pytest.mark.parametrize("seed", [0, 1, 2, 3])
 @pytest.mark.parametrize("lam", [0.05, 0.3])
-def test_alpha_expansion_labels_match_reference_gco(ctx, oracle, seed, lam):
+def test_alpha_expansion_labels_match_reference_gco(ctx, oracle, seed, lam, monkeypatch):
     _need_ref(oracle)
+    monkeypatch.setenv("PXB_CHECK_ENERGY", "1")  # the incremental energy bookkeeping must equal the full edge walk
     rng = np.random.default_rng(seed)
     N = [600, 1500, 4000, 9000][seed]
     pts, gt, Hs = syn.multi_homography_scene(N, n_planes=3 + seed % 2, outlier_ratio=0.35, seed=100 + seed)
