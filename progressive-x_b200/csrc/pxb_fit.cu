@@ -106,6 +106,30 @@ __device__ __forceinline__ double fit_block_sum(double x, double *s_tmp /*8*/) {
 	return t;
 }
 
+// NV block sums at once with the topology of fit_block_sum (butterfly inside the warp, then the warps in order): two
+// barriers for the whole vector instead of two per value. Every thread receives the sums in v[].
+template <int NV> __device__ __forceinline__ void fit_block_sum_vec(double (&v)[NV], double *s_vec /*[warps][NV]*/, double *s_out /*[NV]*/) {
+#pragma unroll
+	for (int a = 0; a < NV; ++a)
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) v[a] = add(v[a], __shfl_xor_sync(0xffffffffu, v[a], o));
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	__syncthreads();
+	if (lane == 0)
+#pragma unroll
+		for (int a = 0; a < NV; ++a) s_vec[warp * NV + a] = v[a];
+	__syncthreads();
+	if (threadIdx.x < NV) {
+		double t = 0.0;
+#pragma unroll
+		for (int w = 0; w < kFitThreads / 32; ++w) t = add(t, s_vec[w * NV + threadIdx.x]);
+		s_out[threadIdx.x] = t;
+	}
+	__syncthreads();
+#pragma unroll
+	for (int a = 0; a < NV; ++a) v[a] = s_out[a];
+}
+
 // problems: CSR (off[P+1], idx[]) of point indices; weights: NULL, or an array indexed BY ROW OF THE NORMALISED SAMPLE
 // (the reference passes weights_[i], i = 0..n-1, once the sample has been gathered into `normalized_points` with a null
 // sample pointer -- solver_homography_four_point.h:207-220 with sample_ == nullptr -- i.e. the first n entries of the
@@ -113,7 +137,6 @@ __device__ __forceinline__ double fit_block_sum(double x, double *s_tmp /*8*/) {
 __global__ void __launch_bounds__(kFitThreads)
     k_fit_h(const double *__restrict__ aos, const int32_t *__restrict__ off, const int32_t *__restrict__ idx,
             const double *__restrict__ weights, double *__restrict__ H_out, int32_t *__restrict__ ok_out) {
-	__shared__ double s_tmp[kFitThreads / 32];
 	__shared__ double s_acc[44];
 	const int pb = blockIdx.x;
 	const int beg = off[pb], n = off[pb + 1] - beg;
@@ -131,8 +154,11 @@ __global__ void __launch_bounds__(kFitThreads)
 		sx2 = add(sx2, q[2]);
 		sy2 = add(sy2, q[3]);
 	}
-	const double mx1 = divd(fit_block_sum(sx1, s_tmp), (double)n), my1 = divd(fit_block_sum(sy1, s_tmp), (double)n);
-	const double mx2 = divd(fit_block_sum(sx2, s_tmp), (double)n), my2 = divd(fit_block_sum(sy2, s_tmp), (double)n);
+	__shared__ double s_vec[(kFitThreads / 32) * 44];
+	double sums4[4] = {sx1, sy1, sx2, sy2};
+	fit_block_sum_vec<4>(sums4, s_vec, s_acc);
+	const double mx1 = divd(sums4[0], (double)n), my1 = divd(sums4[1], (double)n);
+	const double mx2 = divd(sums4[2], (double)n), my2 = divd(sums4[3], (double)n);
 	double d1 = 0, d2 = 0;
 	for (int t = tid; t < n; t += kFitThreads) {
 		const double *q = aos + 4 * (int64_t)idx[beg + t];
@@ -140,7 +166,9 @@ __global__ void __launch_bounds__(kFitThreads)
 		d1 = add(d1, __dsqrt_rn(add(mul(dx1, dx1), mul(dy1, dy1))));
 		d2 = add(d2, __dsqrt_rn(add(mul(dx2, dx2), mul(dy2, dy2))));
 	}
-	const double avg1 = divd(fit_block_sum(d1, s_tmp), (double)n), avg2 = divd(fit_block_sum(d2, s_tmp), (double)n);
+	double sums2[2] = {d1, d2};
+	fit_block_sum_vec<2>(sums2, s_vec, s_acc);
+	const double avg1 = divd(sums2[0], (double)n), avg2 = divd(sums2[1], (double)n);
 	const double r1 = divd(1.4142135623730951, avg1), r2 = divd(1.4142135623730951, avg2); // M_SQRT2 / mean distance
 	// ---- A^T A (upper triangle, 36) and A^T b (8) of the 2n x 8 system (solver_homography_four_point.h:207-252)
 	double acc[44];
@@ -163,11 +191,7 @@ __global__ void __launch_bounds__(kFitThreads)
 #pragma unroll
 		for (int r = 0; r < 8; ++r) acc[36 + r] = add(acc[36 + r], add(mul(ra[r], ba), mul(rb[r], bb)));
 	}
-	for (int a = 0; a < 44; ++a) {
-		const double v = fit_block_sum(acc[a], s_tmp);
-		if (tid == 0) s_acc[a] = v;
-	}
-	__syncthreads();
+	fit_block_sum_vec<44>(acc, s_vec, s_acc);
 	if (tid != 0) return;
 	// ---- solve the 8x8 SPD system: Gaussian elimination with partial pivoting (robust to semi-definite input)
 	double M[8][9];
