@@ -59,8 +59,19 @@ static int require_points(pxb_ctx *ctx) {
 
 constexpr size_t kStageBytes = size_t(4) << 20, kStageMaxItem = size_t(256) << 10; // larger payloads go direct
 
-static unsigned char *stage_take(pxb_ctx *ctx, size_t bytes) {
+// page-locked (cudaMallocHost / cudaHostRegister) caller memory is DMA-able as it is: no staging copy for it
+static bool caller_memory_is_pinned(const void *p) {
+	cudaPointerAttributes attr;
+	if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+		(void)cudaGetLastError();
+		return false;
+	}
+	return attr.type == cudaMemoryTypeHost;
+}
+
+static unsigned char *stage_take(pxb_ctx *ctx, size_t bytes, const void *caller_ptr) {
 	if (!ctx->stage || bytes > kStageMaxItem) return nullptr;
+	if (bytes >= (size_t(16) << 10) && caller_memory_is_pinned(caller_ptr)) return nullptr;
 	const size_t at = (ctx->stage_used + 255) & ~size_t(255);
 	if (at + bytes > ctx->stage_cap) return nullptr;
 	ctx->stage_used = at + bytes;
@@ -69,7 +80,7 @@ static unsigned char *stage_take(pxb_ctx *ctx, size_t bytes) {
 
 int api_h2d(pxb_ctx *ctx, void *dst, const void *src, size_t bytes) {
 	if (bytes == 0) return PXB_OK;
-	if (unsigned char *st = stage_take(ctx, bytes)) {
+	if (unsigned char *st = stage_take(ctx, bytes, src)) {
 		std::memcpy(st, src, bytes);
 		src = st;
 	}
@@ -78,7 +89,7 @@ int api_h2d(pxb_ctx *ctx, void *dst, const void *src, size_t bytes) {
 }
 int api_d2h(pxb_ctx *ctx, void *dst, const void *src, size_t bytes) {
 	if (bytes == 0) return PXB_OK;
-	if (unsigned char *st = stage_take(ctx, bytes)) {
+	if (unsigned char *st = stage_take(ctx, bytes, dst)) {
 		PXB_CUDA(cudaMemcpyAsync(st, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
 		ctx->pending.push_back({dst, st, bytes}); // delivered by sync()
 		return PXB_OK;
