@@ -10,7 +10,9 @@ inputs resident in HBM.  With --gpus N every rank owns a disjoint block of 10 00
 hypothesis-summary all-gather of the sharded RANSAC loop is timed separately and reported under "exchange").
 
 Printed JSON (one line, rank 0): the driver contract + "roofline", "cpu_baseline", "e2e", "clocks",
-"gpu_launches" and a few explanatory extras ("score_kernel", "screening_f32").
+"gpu_launches" and explanatory extras: "score_kernel" (the fused score path the RANSAC loop uses), "screening_f32" (the
+f32-output matrix), and the second half of the BASELINE metric -- "fits" (C2, one problem at a time), "fits_lambda" (C2
+with the spatial term), "fits_batch" (C4 in miniature: independent pairs on concurrent contexts).
 """
 from __future__ import annotations
 

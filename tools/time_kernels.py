@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Times the headline kernels (CUDA events on the context's stream) for a list of PXB_RM_VARIANT values.
-Each variant runs in a fresh subprocess because the knob is read once per process."""
+"""Times the headline kernels (CUDA events on the context's stream): the residual-and-inlier matrix and the fused score.
+Environment: PXB_TYPE (0 H, 1 F, 2 PnP), PXB_N, PXB_K, PXB_RM_HYPS (32 / 64 hypotheses per block of the matrix kernel; read
+once per process, hence the subprocess per run)."""
 import os
 import subprocess
 import sys
@@ -56,9 +57,9 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
     f_s = lambda: ctx.lib.pxb_score_compound_dev(ctx.handle, m.data_ptr(), K, T2, None, out[0].data_ptr(),
                                                  out[1].data_ptr(), out[2].data_ptr())
     tm, ts = run(f_m), run(f_s)
-    print(f"variant={os.environ.get('PXB_RM_VARIANT','0')} type={t} N={N} K={K} matrix {tm:.4f} ms "
+    print(f"hyps/block={os.environ.get('PXB_RM_HYPS','auto')} type={t} N={N} K={K} matrix {tm:.4f} ms "
           f"({N*K/tm/1e6:.1f} Gevals/s, {N*K*8.125/tm/1e6/6534.1*100:.1f}% of 6534 GB/s)  score {ts:.4f} ms ({N*K/ts/1e6:.1f} Gevals/s)")
 else:
     for v in sys.argv[1:] or ["0"]:
-        env = dict(os.environ, PXB_RM_VARIANT=v)
+        env = dict(os.environ) if v == "0" else dict(os.environ, PXB_RM_HYPS=v)
         subprocess.run([sys.executable, __file__, "--child"], env=env, check=False)
