@@ -106,9 +106,9 @@ class NapsacSampler:  # gcr/samplers/napsac_sampler.h:102-151 (incl. the point-i
 
 
 class ProsacSampler:  # gcr/samplers/prosac_sampler.h (reset() state per proposal, progressive_x.h:290-291)
-    def __init__(self, seed, m, N):
+    def __init__(self, seed, m, N, convergence=100000):
         self.rng, self.m, self.N = Rng(seed), m, N
-        self.convergence, self.kth, self.subset_size, self.gen_max = 100000, 1, m, m - 1
+        self.convergence, self.kth, self.subset_size, self.gen_max = convergence, 1, m, m - 1
         self.growth = [0] * N
         T_n = float(self.convergence)
         for i in range(m):
@@ -131,6 +131,15 @@ class ProsacSampler:  # gcr/samplers/prosac_sampler.h (reset() state per proposa
             self.subset_size = min(self.subset_size + 1, self.N)
             self.gen_max = self.subset_size - 2
 
+    def set_sample_number(self, k):  # setSampleNumber
+        self.kth = k
+        if self.kth > self.convergence:
+            self.gen_max = self.N - 1
+        else:
+            while self.kth > self.growth[self.subset_size - 1] and self.subset_size != self.N:
+                self.subset_size = min(self.subset_size + 1, self.N)
+                self.gen_max = self.subset_size - 2
+
     def sample(self, pool, m):
         if m != self.m:
             self._increment()
@@ -139,6 +148,88 @@ class ProsacSampler:  # gcr/samplers/prosac_sampler.h (reset() state per proposa
             return self.rng.unique_set(m, self.gen_max)
         out = self.rng.unique_set(m - 1, self.gen_max) + [self.subset_size - 1]
         self._increment()
+        return out
+
+
+class GridLayer:  # gcr/neighborhood/grid_neighborhood_graph.h (out-of-image coordinates clamped to the border cells)
+    def __init__(self, rows, sizes, cells):
+        idx = np.zeros(len(rows), dtype=np.int64)
+        offset = 1
+        for d in range(rows.shape[1]):
+            f = np.floor(rows[:, d] / (sizes[d] / cells))
+            f = np.where(f >= 0, f, 0)
+            f = np.minimum(f, cells - 1)
+            idx += offset * f.astype(np.int64)
+            offset *= cells
+        self.cell_of = idx
+        self.cells = {}
+        for i, c in enumerate(idx):
+            self.cells.setdefault(int(c), []).append(i)
+
+    def neighbors(self, i):
+        return self.cells[int(self.cell_of[i])]
+
+
+class ProgressiveNapsacSampler:  # gcr/samplers/progressive_napsac_sampler.h; layers {16, 8, 4, 2}, length 0.5
+    def __init__(self, seed, m, N, layers, sampler_length=0.5):
+        self.rng, self.layers, self.m, self.N, self.kth = Rng(seed), layers, m, N, 0
+        self.one_point = ProsacSampler(seed ^ 0x5851F42D4C957F2D, 1, N, N)
+        self.prosac = ProsacSampler(seed ^ 0x14057B7EF767814F, m, N, N)
+        self.max_local = int(sampler_length * N)
+        self.current_layer, self.hits, self.subset_size_of = [0] * N, [0] * N, [m] * N
+        self.growth = [0] * N
+        local = m - 1
+        T_n = float(self.max_local)
+        for i in range(local):
+            T_n *= (local - i) / (N - i)
+        T_n_prime = 1
+        for i in range(N):
+            if i + 1 <= local:
+                self.growth[i] = T_n_prime
+                continue
+            Tn_plus1 = (i + 1) * T_n / (i + 1 - local)
+            self.growth[i] = T_n_prime + int(math.ceil(Tn_plus1 - T_n))
+            T_n = Tn_plus1
+            T_n_prime = self.growth[i] & 0xFFFFFFFF
+
+    def sample(self, pool, m):
+        self.kth += 1
+        if m != self.m or m > len(pool):
+            return None
+        if self.kth > self.max_local:
+            self.prosac.set_sample_number(self.kth)
+            return self.prosac.sample(pool, m)
+        c = self.one_point.sample(pool, 1)
+        if c is None:
+            return None
+        centre = c[0]
+        self.hits[centre] += 1
+        h, ss = self.hits[centre], self.subset_size_of[centre]
+        while h > self.growth[ss - 1] and ss < self.N:
+            ss = min(ss + 1, self.N)
+        self.subset_size_of[centre] = ss
+        last = False
+        while True:
+            if self.current_layer[centre] >= len(self.layers):
+                last = True
+                break
+            if len(self.layers[self.current_layer[centre]].neighbors(centre)) < ss:
+                self.current_layer[centre] += 1
+                continue
+            break
+        if last:
+            self.prosac.set_sample_number(self.kth)
+            out = self.prosac.sample(pool, m)
+            if out is None:
+                return None
+            out[m - 1] = centre
+            return out
+        nb = self.layers[self.current_layer[centre]].neighbors(centre)
+        picks = self.rng.unique_set(m - 2, ss - 2, skip=centre)
+        out = [nb[j] for j in picks] + [nb[ss - 1], centre]
+        for v in out[:m - 2]:
+            self.hits[v] += 1
+        self.hits[out[m - 2]] += 1
         return out
 
 
@@ -151,7 +242,7 @@ class Score:
 
 class ProgressiveXOracle:
     def __init__(self, pts, *, threshold, confidence, lam, max_tanimoto, max_iters, min_inliers, max_models, napsac, exponent,
-                 seed, graph, family=H, point_weights=None, prosac=False):
+                 seed, graph, family=H, point_weights=None, prosac=False, pnapsac_sizes=None):
         self.pts = np.ascontiguousarray(pts, dtype=np.float64)
         self.N = self.pts.shape[0]
         self.t = family
@@ -163,6 +254,9 @@ class ProgressiveXOracle:
         self.max_models = max_models if max_models > 0 else 1 << 62
         self.napsac, self.exponent, self.seed = napsac, int(exponent), seed
         self.prosac = prosac
+        self.grid_layers = None
+        if pnapsac_sizes is not None:
+            self.grid_layers = [GridLayer(self.pts, pnapsac_sizes, c) for c in (16, 8, 4, 2)]
         self.off, self.idx = graph if graph is not None else (np.zeros(self.N + 1, np.int32), np.zeros(0, np.int32))
         # gcransac::utils::Settings as overridden by progressive_x.h:64-71
         self.min_iteration_number = 20
@@ -275,6 +369,8 @@ class ProgressiveXOracle:
         T2 = tt * tt
         if self.napsac and self.idx.size:
             main = NapsacSampler((round_seed * 2 + 1) & M64, self.off, self.idx)
+        elif self.grid_layers is not None and self.N > self.m:
+            main = ProgressiveNapsacSampler((round_seed * 2 + 1) & M64, self.m, self.N, self.grid_layers)
         elif self.prosac and self.N > self.m:
             main = ProsacSampler((round_seed * 2 + 1) & M64, self.m, self.N)
         else:
@@ -441,12 +537,14 @@ class ProgressiveXOracle:
 
 
 def find_homographies(corrs, threshold, conf, spatial_coherence_weight, maximum_tanimoto_similarity, max_iters,
-                      minimum_point_number, maximum_model_number, sampler_id, scoring_exponent, seed, graph=None):
+                      minimum_point_number, maximum_model_number, sampler_id, scoring_exponent, seed, graph=None,
+                      image_sizes=None):
     """findHomographies_ (src/pyprogressivex/src/progressivex_python.cpp:173-304) on the sequential loop above."""
     px = ProgressiveXOracle(corrs, threshold=threshold, confidence=conf, lam=spatial_coherence_weight,
                             max_tanimoto=maximum_tanimoto_similarity, max_iters=max_iters, min_inliers=minimum_point_number,
                             max_models=maximum_model_number, napsac=(sampler_id == 3), exponent=scoring_exponent, seed=seed,
-                            graph=graph, prosac=(sampler_id == 1))
+                            graph=graph, prosac=(sampler_id == 1),
+                            pnapsac_sizes=image_sizes if sampler_id == 2 else None)
     return px.run()
 
 

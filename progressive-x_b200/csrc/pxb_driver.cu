@@ -25,8 +25,8 @@
 //   * neighbourhood graph: exact kNN-in-radius on the GPU instead of randomised FLANN;
 //   * the reference's two-buffer inlier ping-pong (GCRANSAC.h:244-252,:546-552) is replaced by "the inlier list of the
 //     current best model" -- the reference's version depends on list-size coincidences;
-//   * sampler 2 (P-NAPSAC) falls back to uniform sampling (multi-layer grid neighbourhoods are not built); PROSAC (1),
-//     NAPSAC (3; id 2 for lines) and uniform (0) follow the reference's state machines;
+//   * samplers: uniform (0), PROSAC (1), Progressive NAPSAC (2, over four grid layers) and NAPSAC (3; id 2 for lines)
+//     follow the reference's state machines on the seedable generator;
 //   * non-minimal fits ("next"): H through the 8x8 normal equations (same least-squares solution as
 //     the reference's QR); F as normalised 8-point + rank-2 projection and PnP as normalised DLT + 10 LM steps, i.e.
 //     without PoseLib's bundle adjustment / OpenCV's EPnP (pxb_fit_fp.cu); DEGENSAC is not applied to F.
@@ -158,9 +158,10 @@ struct NapsacSampler : Sampler { // gcr/samplers/napsac_sampler.h:102-151
 // newest point of the pool is always part of the sample. reset() state per proposal (progressive_x.h:290-291).
 struct ProsacSampler : Sampler {
 	Rng rng;
-	size_t sample_size, point_number, convergence = 100000, kth = 1, subset_size, gen_max;
+	size_t sample_size, point_number, convergence, kth = 1, subset_size, gen_max;
 	std::vector<size_t> growth;
-	ProsacSampler(uint64_t seed, size_t m, size_t N) : rng(seed), sample_size(m), point_number(N), subset_size(m), gen_max(m - 1) {
+	ProsacSampler(uint64_t seed, size_t m, size_t N, size_t convergence_iterations = 100000)
+	    : rng(seed), sample_size(m), point_number(N), convergence(convergence_iterations), subset_size(m), gen_max(m - 1) {
 		growth.assign(N, 0); // :initialize
 		double T_n = (double)convergence;
 		for (size_t i = 0; i < m; i++) T_n *= static_cast<double>(m - i) / (double)(N - i);
@@ -186,6 +187,18 @@ struct ProsacSampler : Sampler {
 			gen_max = subset_size - 2;
 		}
 	}
+	void set_sample_number(size_t k) { // setSampleNumber
+		kth = k;
+		if (kth > convergence) {
+			gen_max = point_number - 1;
+		} else {
+			while (kth > growth[subset_size - 1] && subset_size != point_number) {
+				++subset_size;
+				if (subset_size > point_number) subset_size = point_number;
+				gen_max = subset_size - 2;
+			}
+		}
+	}
 	bool sample(const std::vector<size_t> &, size_t *subset, size_t m) override {
 		if (m != sample_size) { // "PROSAC is not yet implemented to change the sample size"
 			increment();
@@ -198,6 +211,113 @@ struct ProsacSampler : Sampler {
 		rng.unique_set(subset, m - 1, gen_max);
 		subset[m - 1] = subset_size - 1; // the last index is the point at the end of the current pool
 		increment();
+		return true;
+	}
+};
+
+// gcr/neighborhood/grid_neighborhood_graph.h: points hashed into a regular grid of `cells` cells per axis; the
+// neighbours of a point are the points of its cell (itself included) in row order. Coordinates outside [0, size) are
+// clamped to the border cells (the reference casts a negative floor() to size_t).
+struct GridLayer {
+	std::vector<std::vector<size_t>> cell_points;
+	std::vector<size_t> cell_of_point;
+	void build(const double *rows, size_t N, int dim, const double *sizes, size_t cells) {
+		std::vector<std::pair<size_t, size_t>> key((size_t)N);
+		for (size_t i = 0; i < N; ++i) {
+			size_t index = 0, offset = 1;
+			for (int d = 0; d < dim; ++d) {
+				const double cs = sizes[d] / (double)cells;
+				double f = std::floor(rows[i * dim + d] / cs);
+				if (!(f >= 0)) f = 0;
+				if (f > (double)(cells - 1)) f = (double)(cells - 1);
+				index += offset * (size_t)f;
+				offset *= cells;
+			}
+			key[i] = {index, i};
+		}
+		std::vector<std::pair<size_t, size_t>> sorted = key;
+		std::sort(sorted.begin(), sorted.end());
+		cell_of_point.assign(N, 0);
+		cell_points.clear();
+		for (size_t t = 0; t < N; ++t) {
+			if (t == 0 || sorted[t].first != sorted[t - 1].first) cell_points.emplace_back();
+			cell_points.back().push_back(sorted[t].second); // row order inside a cell (pairs sort by index, then row)
+			cell_of_point[sorted[t].second] = cell_points.size() - 1;
+		}
+	}
+	const std::vector<size_t> &neighbors(size_t i) const { return cell_points[cell_of_point[i]]; }
+};
+
+// gcr/samplers/progressive_napsac_sampler.h: local samples around a PROSAC-chosen centre from the finest grid layer that
+// holds enough points, blending into global PROSAC sampling. Layers {16, 8, 4, 2}, sampler length 0.5
+// (progressivex_python.cpp:227-235). The grid layers depend on the data only and are shared by all proposals.
+struct ProgressiveNapsacSampler : Sampler {
+	Rng rng;
+	const std::vector<GridLayer> *layers;
+	ProsacSampler one_point, prosac;
+	size_t sample_size, point_number, kth = 0, max_local_iterations;
+	std::vector<size_t> current_layer, hits, subset_size_of, growth;
+	ProgressiveNapsacSampler(uint64_t seed, size_t m, size_t N, const std::vector<GridLayer> *layers_, double sampler_length)
+	    : rng(seed), layers(layers_), one_point(seed ^ 0x5851F42D4C957F2Dull, 1, N, N), prosac(seed ^ 0x14057B7EF767814Full, m, N, N),
+	      sample_size(m), point_number(N), current_layer(N, 0), hits(N, 0), subset_size_of(N, m) {
+		max_local_iterations = static_cast<size_t>(sampler_length * (double)N);
+		growth.assign(N, 0);
+		const size_t local = m - 1;
+		double T_n = (double)max_local_iterations;
+		for (size_t i = 0; i < local; ++i) T_n *= static_cast<double>(local - i) / (double)(N - i);
+		unsigned int T_n_prime = 1;
+		for (size_t i = 0; i < N; ++i) {
+			if (i + 1 <= local) {
+				growth[i] = T_n_prime;
+				continue;
+			}
+			const double Tn_plus1 = static_cast<double>(i + 1) * T_n / (double)(i + 1 - local);
+			growth[i] = T_n_prime + static_cast<size_t>(std::ceil(Tn_plus1 - T_n));
+			T_n = Tn_plus1;
+			T_n_prime = (unsigned int)growth[i];
+		}
+	}
+	bool sample(const std::vector<size_t> &pool, size_t *subset, size_t m) override {
+		++kth;
+		if (m != sample_size) return false;
+		if (m > pool.size()) return false;
+		if (kth > max_local_iterations) { // fully blended into global sampling
+			prosac.set_sample_number(kth);
+			return prosac.sample(pool, subset, m);
+		}
+		if (!one_point.sample(pool, subset, 1)) return false;
+		const size_t centre = subset[0];
+		const size_t h = ++hits[centre];
+		size_t &ss = subset_size_of[centre];
+		while (h > growth[ss - 1] && ss < point_number) ss = std::min(ss + 1, point_number);
+		size_t &layer = current_layer[centre];
+		bool last = false;
+		while (true) { // the finest grid whose cell holds enough points
+			if (layer >= layers->size()) {
+				last = true;
+				break;
+			}
+			if ((*layers)[layer].neighbors(centre).size() < ss) {
+				++layer;
+				continue;
+			}
+			break;
+		}
+		if (last) {
+			prosac.set_sample_number(kth);
+			const bool ok = prosac.sample(pool, subset, m);
+			subset[m - 1] = centre;
+			return ok;
+		}
+		const std::vector<size_t> &nb = (*layers)[layer].neighbors(centre);
+		subset[m - 1] = centre;
+		subset[m - 2] = nb[ss - 1];
+		rng.unique_set(subset, m - 2, ss - 2, true, centre); // (:..., neighbour index compared with a point index: kept)
+		for (size_t i = 0; i + 2 < m; ++i) {
+			subset[i] = nb[subset[i]];
+			++hits[subset[i]];
+		}
+		++hits[subset[m - 2]];
 		return true;
 	}
 };
@@ -215,6 +335,8 @@ struct Settings {
 	int exponent = 2;                         // scoring_function_with_compound_model.h:20 (int!)
 	size_t sampler_id = 0;
 	bool napsac = false;                      // main sampler = NapsacSampler (H/F: id 3, lines: id 2)
+	bool progressive_napsac = false;          // main sampler = ProgressiveNapsacSampler (H/F: id 2)
+	double sizes[4] = {0, 0, 0, 0};           // image sizes: cell sizes of the P-NAPSAC grid layers
 	std::vector<double> point_weights;        // MultiModelSettings::point_weights (progressive_x.h:36), VP only
 	bool do_logging = false;
 	uint64_t seed = 1;
@@ -271,6 +393,11 @@ class Driver {
 		maxsol_ = max_solutions(s.type);
 	}
 	int build_graph(double radius, int k);
+	void build_grid_layers(const double *rows) { // ProgressiveNapsacSampler<4>(.., {16, 8, 4, 2}, .., sizes, 0.5)
+		const size_t cells[4] = {16, 8, 4, 2};
+		grid_layers_.resize(4);
+		for (int l = 0; l < 4; ++l) grid_layers_[l].build(rows, (size_t)N_, 4, s_.sizes, cells[l]);
+	}
 	int run();
 	const std::vector<Instance> &instances() const { return models_; }
 	const std::vector<int64_t> &labeling() const { return labeling_; }
@@ -283,6 +410,7 @@ class Driver {
 	int64_t N_;
 	int ms_, m_, maxsol_;
 	Graph graph_;
+	std::vector<GridLayer> grid_layers_;
 	std::vector<Instance> models_;
 	std::vector<double> compound_pref_;
 	std::vector<int64_t> labeling_;
@@ -600,6 +728,8 @@ int Driver::propose(uint64_t round_seed, std::vector<double> &model_out, bool &f
 	std::unique_ptr<Sampler> main_sampler;
 	if (s_.napsac && !graph_.idx.empty())
 		main_sampler.reset(new NapsacSampler(round_seed * 2 + 1, &graph_));
+	else if (s_.progressive_napsac && !grid_layers_.empty() && (size_t)N_ > (size_t)m_)
+		main_sampler.reset(new ProgressiveNapsacSampler(round_seed * 2 + 1, (size_t)m_, (size_t)N_, &grid_layers_, 0.5));
 	else if (s_.sampler_id == 1 && (size_t)N_ > (size_t)m_)
 		main_sampler.reset(new ProsacSampler(round_seed * 2 + 1, (size_t)m_, (size_t)N_));
 	else
@@ -917,7 +1047,7 @@ int Driver::run() {
 }
 
 int run_two_view(pxb_ctx *ctx, int type, const double *corr, int64_t N, int64_t *labeling_out, double *models_out,
-                 int64_t max_models_out, double lambda, double threshold, double confidence, double radius,
+                 int64_t max_models_out, const double (&sizes)[4], double lambda, double threshold, double confidence, double radius,
                  double max_tanimoto, size_t max_iters, size_t min_points, int max_models, size_t sampler_id,
                  double scoring_exponent, bool set_exponent, int do_logging, uint64_t seed) {
 	if (!ctx || !corr || !labeling_out || !models_out || N < 4) {
@@ -941,11 +1071,14 @@ int run_two_view(pxb_ctx *ctx, int type, const double *corr, int64_t N, int64_t 
 	if (max_models > 0) s.max_models = (size_t)max_models;
 	s.sampler_id = sampler_id;
 	s.napsac = sampler_id == 3;
+	s.progressive_napsac = sampler_id == 2 && sizes[0] > 0 && sizes[1] > 0 && sizes[2] > 0 && sizes[3] > 0;
+	for (int d = 0; d < 4; ++d) s.sizes[d] = sizes[d];
 	if (set_exponent) s.exponent = (int)scoring_exponent; // setExponent(const int) truncates (progressive_x.h:551)
 	s.do_logging = do_logging != 0;
 	if (seed == 0) seed = (uint64_t)std::chrono::high_resolution_clock::now().time_since_epoch().count();
 	s.seed = seed;
 	Driver drv(ctx, s);
+	if (s.progressive_napsac) drv.build_grid_layers(corr);
 	if (lambda > 0.0 || sampler_id == 3) {
 		Scoped t(drv.prof_, "build_graph");
 		PXB_TRY(drv.build_graph(radius, graph_degree()));
@@ -1014,25 +1147,27 @@ using namespace pxb;
 extern "C" {
 
 int pxb_find_homographies(pxb_ctx *ctx, const double *correspondences, int64_t N, int64_t *labeling_out,
-                          double *models_out, int64_t max_models_out, size_t, size_t, size_t, size_t,
+                          double *models_out, int64_t max_models_out, size_t w1, size_t h1, size_t w2, size_t h2,
                           double spatial_coherence_weight, double threshold, double confidence,
                           double neighborhood_ball_radius, double maximum_tanimoto_similarity, size_t max_iters,
                           size_t minimum_point_number, int maximum_model_number, size_t sampler_id,
                           double scoring_exponent, int do_logging, uint64_t seed) {
-	return run_two_view(ctx, PXB_MODEL_HOMOGRAPHY, correspondences, N, labeling_out, models_out, max_models_out,
+	const double sizes[4] = {(double)w1, (double)h1, (double)w2, (double)h2};
+	return run_two_view(ctx, PXB_MODEL_HOMOGRAPHY, correspondences, N, labeling_out, models_out, max_models_out, sizes,
 	                    spatial_coherence_weight, threshold, confidence, neighborhood_ball_radius,
 	                    maximum_tanimoto_similarity, max_iters, minimum_point_number, maximum_model_number, sampler_id,
 	                    scoring_exponent, true, do_logging, seed);
 }
 
 int pxb_find_two_view_motions(pxb_ctx *ctx, const double *correspondences, int64_t N, int64_t *labeling_out,
-                              double *models_out, int64_t max_models_out, size_t, size_t, size_t, size_t,
+                              double *models_out, int64_t max_models_out, size_t w1, size_t h1, size_t w2, size_t h2,
                               double spatial_coherence_weight, double threshold, double confidence,
                               double neighborhood_ball_radius, double maximum_tanimoto_similarity, size_t max_iters,
                               size_t minimum_point_number, int maximum_model_number, size_t sampler_id,
                               double scoring_exponent, int do_logging, uint64_t seed) {
 	// findTwoViewMotions_ never forwards scoring_exponent (progressivex_python.cpp:621-638): the exponent stays 2
-	return run_two_view(ctx, PXB_MODEL_FUNDAMENTAL, correspondences, N, labeling_out, models_out, max_models_out,
+	const double sizes[4] = {(double)w1, (double)h1, (double)w2, (double)h2};
+	return run_two_view(ctx, PXB_MODEL_FUNDAMENTAL, correspondences, N, labeling_out, models_out, max_models_out, sizes,
 	                    spatial_coherence_weight, threshold, confidence, neighborhood_ball_radius,
 	                    maximum_tanimoto_similarity, max_iters, minimum_point_number, maximum_model_number, sampler_id,
 	                    scoring_exponent, false, do_logging, seed);

@@ -33,7 +33,8 @@ def _compare(corrs, radius, seeds, **kw):
         models, labels = pyprogressivex.findHomographies(corrs, 640, 480, 640, 480, neighborhood_ball_radius=radius, seed=seed, **kw)
         m_o, l_o = seq.find_homographies(corrs, kw["threshold"], kw["conf"], kw["spatial_coherence_weight"],
                                          kw["maximum_tanimoto_similarity"], kw["max_iters"], kw["minimum_point_number"],
-                                         kw["maximum_model_number"], kw["sampler_id"], kw["scoring_exponent"], seed, graph)
+                                         kw["maximum_model_number"], kw["sampler_id"], kw["scoring_exponent"], seed, graph,
+                                         image_sizes=(640.0, 480.0, 640.0, 480.0))
         M = models.shape[0] // 3
         same = M == m_o.shape[0] and np.array_equal(labels, l_o.astype(np.int32))
         if same and M:
@@ -111,4 +112,13 @@ def test_driver_equals_sequential_loop_prosac():
     corrs = np.ascontiguousarray(corrs[order])
     kw = dict(threshold=2.0, conf=0.9, spatial_coherence_weight=0.0, maximum_tanimoto_similarity=0.4, max_iters=300,
               minimum_point_number=40, maximum_model_number=-1, sampler_id=1, scoring_exponent=2)
+    assert _compare(corrs, 60.0, (1, 2, 3), **kw) == 3
+
+
+def test_driver_equals_sequential_loop_progressive_napsac():
+    """sampler_id = 2: Progressive NAPSAC over the four grid layers {16, 8, 4, 2} of the image pair (centre by one-point
+    PROSAC, local samples from the finest cell that holds enough points, blending into global PROSAC)."""
+    corrs, gt, _ = syn.multi_homography_scene(800, n_planes=2, outlier_ratio=0.3, noise=0.5, w=640, h=480, seed=14)
+    kw = dict(threshold=2.0, conf=0.9, spatial_coherence_weight=0.0, maximum_tanimoto_similarity=0.4, max_iters=300,
+              minimum_point_number=40, maximum_model_number=-1, sampler_id=2, scoring_exponent=2)
     assert _compare(corrs, 60.0, (1, 2, 3), **kw) == 3
