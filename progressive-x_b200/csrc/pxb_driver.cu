@@ -993,8 +993,7 @@ int Driver::run() {
 	labeling_.assign((size_t)N_, 0);
 	compound_pref_.assign((size_t)N_, 0.0);
 	models_.clear();
-	size_t number_of_ransac_iterations = 0, unaccepted = 0, unseen_inliers = (size_t)N_;
-	(void)unseen_inliers;
+	size_t number_of_ransac_iterations = 0, unaccepted = 0;
 	for (size_t it = 0; it < 10; ++it) { // :272 hard cap
 		std::vector<double> model;
 		bool found = false;
