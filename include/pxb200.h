@@ -138,6 +138,22 @@ int pxb_compound_max(pxb_ctx *ctx, const double *prefs_host, int64_t L, int64_t 
 int pxb_solve_minimal(pxb_ctx *ctx, const int64_t *samples_host, int64_t K, double *models_out_host,
                       int32_t *n_models_host, uint8_t *sample_valid_host, uint8_t *model_valid_host);
 
+/* DEGENSAC's minimal solver (FundamentalMatrixPlaneParallaxSolver::estimateModel,
+ * gcr/estimators/solver_fundamental_matrix_plane_and_parallax.h:107-162): a fixed homography H (row-major 3x3) and
+ * two off-plane correspondences give F = [e]_x H with e = ((H x1_a) x x2_a) x ((H x1_b) x x2_b); no model when
+ * |e_z| < DBL_EPSILON. samples: [K, 2] indices; models_out: [K, 9]; n_models[k] in {0, 1}. Points must have been
+ * uploaded as PXB_MODEL_FUNDAMENTAL. */
+int pxb_solve_plane_parallax(pxb_ctx *ctx, const int64_t *samples_host, int64_t K, const double *H_host,
+                             double *models_out_host, int32_t *n_models_host);
+
+/* The H-degeneracy test of a seven-point sample (FundamentalMatrixEstimator::applyDegensac,
+ * gcr/estimators/fundamental_estimator.h:341-476): for the five point triplets {0,1,2},{3,4,5},{0,1,6},{3,4,6},{2,5,6}
+ * the homography compatible with F through the triplet is formed; the sample is degenerate when, for one of them, at
+ * least five of the seven correspondences have a transfer error below 2 px. Host arithmetic (seven points): no
+ * context needed. rows: [N, 4] correspondences, sample7: 7 indices, F: row-major 3x3. *degenerate receives 0/1 and,
+ * when 1, H_out (9 doubles) the homography of the first such triplet. */
+int pxb_h_degenerate_sample(const double *rows, const int64_t *sample7, const double *F, double *H_out, int32_t *degenerate);
+
 /* ---- a9/a10/a11/a12: PEARL ------------------------------------------------------------------------------- */
 /* dataEnergyFunctor + EnergyDataStructure (px/include/PEARL.h:17-56,82-128) evaluated densely:
  * D[i*(L+1) + l], l < L: 2(1-lambda) if r2 > T else (1-lambda) r2 / T, T = 9/4 thr^2; D[i*(L+1)+L] = 1-lambda. */

@@ -292,6 +292,75 @@ def solve_minimal(t, pts, samples):
     return models, n, sv, mv
 
 
+def _cross(a, b):
+    return np.array([a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]])
+
+
+def _matvec3(M, v):
+    """row-by-row (a*b + c*d) + e*f, the order Eigen's 3x3 product evaluates in (no FMA on the reference's x86-64 build)"""
+    return np.array([(M[r, 0] * v[0] + M[r, 1] * v[1]) + M[r, 2] * v[2] for r in range(3)])
+
+
+def solve_plane_parallax(pts, samples, H):
+    """FundamentalMatrixPlaneParallaxSolver::estimateModel
+    (gcr/estimators/solver_fundamental_matrix_plane_and_parallax.h:107-162), restated: not pinned against the reference's
+    body (its arithmetic is Eigen expression templates), anchored on the algebraic property F^T e = 0, x2^T F x1 = 0."""
+    pts = _f(pts)
+    H = _f(H).reshape(3, 3)
+    s = np.ascontiguousarray(samples, dtype=np.int64).reshape(-1, 2)
+    models = np.zeros((s.shape[0], 9))
+    n = np.zeros(s.shape[0], dtype=np.int32)
+    for k, (a, b) in enumerate(s):
+        lines = []
+        for i in (a, b):
+            src = np.array([pts[i, 0], pts[i, 1], 1.0])
+            dst = np.array([pts[i, 2], pts[i, 3], 1.0])
+            lines.append(_cross(_matvec3(H, src), dst))                      # :136-142
+        e = _cross(lines[0], lines[1])                                       # :145
+        if not abs(e[2]) >= np.finfo(np.float64).eps:                         # :148-149
+            continue
+        ex = np.array([[0.0, -e[2], e[1]], [e[2], 0.0, -e[0]], [-e[1], e[0], 0.0]])   # :152-155
+        F = np.array([[(ex[r, 0] * H[0, c] + ex[r, 1] * H[1, c]) + ex[r, 2] * H[2, c] for c in range(3)] for r in range(3)])
+        models[k] = F.reshape(9)                                             # :158-160
+        n[k] = 1
+    return models, n
+
+
+def h_degenerate_sample(rows, sample7, F, homography_threshold=2.0):
+    """The seven-point H-degeneracy test of FundamentalMatrixEstimator::applyDegensac
+    (gcr/estimators/fundamental_estimator.h:352-476), restated with numpy's SVD for the epipole.
+    Returns (degenerate, H, margins): margins = for every triplet the sorted transfer errors of the other four points
+    (so that tests can skip samples that sit on the 2 px decision boundary)."""
+    rows = _f(rows).reshape(-1, 4)
+    F = _f(F).reshape(3, 3)
+    U, _, _ = np.linalg.svd(F)
+    e = U[:, 2] / U[2, 2]                                                    # :370-372
+    ex = np.array([[0.0, -e[2], e[1]], [e[2], 0.0, -e[0]], [-e[1], e[0], 0.0]])
+    A = ex @ F                                                               # :380-381
+    triplets = [(0, 1, 2), (3, 4, 5), (0, 1, 6), (3, 4, 6), (2, 5, 6)]       # :352-357
+    margins = []
+    for trip in triplets:
+        ids = [int(sample7[j]) for j in trip]
+        x1 = np.array([[rows[i, 0], rows[i, 1], 1.0] for i in ids])
+        x2 = np.array([[rows[i, 2], rows[i, 3], 1.0] for i in ids])
+        b = np.empty(3)
+        for k in range(3):
+            c = np.cross(x2[k], e)
+            b[k] = np.dot(np.cross(x2[k], A @ x1[k]), c) / np.dot(c, c)      # :419-422
+        Hm = A - np.outer(e, np.linalg.solve(x1, b))                         # :424-430
+        errs = []
+        for j in range(7):
+            i = int(sample7[j])
+            if i in ids:
+                continue
+            t = Hm @ np.array([rows[i, 0], rows[i, 1], 1.0])
+            errs.append((rows[i, 2] - t[0] / t[2]) ** 2 + (rows[i, 3] - t[1] / t[2]) ** 2)   # :452-462
+        margins.append(sorted(errs))
+        if 3 + sum(x < homography_threshold ** 2 for x in errs) >= 5:        # :466-476
+            return True, Hm, margins
+    return False, None, margins
+
+
 def pearl_datacost(t, pts, models, thr, lam):
     pts, models = _f(pts), _f(models).reshape(-1, MSIZE[t])
     N, L = pts.shape[0], models.shape[0]

@@ -494,6 +494,32 @@ int pxb_solve_minimal(pxb_ctx *ctx, const int64_t *samples_host, int64_t K, doub
 	return sync(ctx);
 }
 
+int pxb_solve_plane_parallax(pxb_ctx *ctx, const int64_t *samples_host, int64_t K, const double *H_host,
+                             double *models_out_host, int32_t *n_models_host) {
+	PXB_TRY(require_points(ctx));
+	PXB_CHECK_ARG(samples_host && H_host && models_out_host && n_models_host && K >= 0, "null argument");
+	PXB_CHECK_ARG(ctx->pts.type == PXB_MODEL_FUNDAMENTAL, "plane-and-parallax needs two-view correspondences (PXB_MODEL_FUNDAMENTAL)");
+	if (K == 0) return PXB_OK;
+	const int64_t N = ctx->pts.N;
+	for (int64_t i = 0; i < K * 2; ++i)
+		if (samples_host[i] < 0 || samples_host[i] >= N) {
+			set_error("sample index %lld out of range [0, %lld)", (long long)samples_host[i], (long long)N);
+			return PXB_ERR_ARGUMENT;
+		}
+	PXB_TRY(ctx->idx.reserve(sizeof(int64_t) * (size_t)K * 2));
+	PXB_TRY(ctx->models.reserve(sizeof(double) * (size_t)K * 9));
+	PXB_TRY(ctx->outA.reserve(sizeof(int32_t) * (size_t)K));
+	PXB_TRY(ctx->outC.reserve(sizeof(double) * 9));
+	PXB_TRY(h2d(ctx, ctx->idx.ptr, samples_host, sizeof(int64_t) * (size_t)K * 2));
+	PXB_TRY(h2d(ctx, ctx->outC.ptr, H_host, sizeof(double) * 9));
+	PXB_CUDA(cudaMemsetAsync(ctx->models.ptr, 0, sizeof(double) * (size_t)K * 9, ctx->stream));
+	PXB_TRY(launch_solve_plane_parallax(ctx, ctx->idx.as<int64_t>(), K, ctx->outC.as<double>(), ctx->models.as<double>(),
+	                                    ctx->outA.as<int32_t>(), nullptr, nullptr));
+	PXB_TRY(d2h(ctx, models_out_host, ctx->models.ptr, sizeof(double) * (size_t)K * 9));
+	PXB_TRY(d2h(ctx, n_models_host, ctx->outA.ptr, sizeof(int32_t) * (size_t)K));
+	return sync(ctx);
+}
+
 // ---- a9/a10/a11/a12 ----------------------------------------------------------------------------------------
 int pxb_pearl_datacost(pxb_ctx *ctx, const double *models_host, int64_t L, double thr, double lambda,
                        double *D_host) {

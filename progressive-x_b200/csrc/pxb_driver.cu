@@ -338,6 +338,13 @@ struct Settings {
 	bool progressive_napsac = false;          // main sampler = ProgressiveNapsacSampler (H/F: id 2)
 	double sizes[4] = {0, 0, 0, 0};           // image sizes: cell sizes of the P-NAPSAC grid layers
 	std::vector<double> point_weights;        // MultiModelSettings::point_weights (progressive_x.h:36), VP only
+	// FundamentalMatrixEstimator(minimum_inlier_ratio_in_validity_check = 0.5, use_degensac = true)
+	double sym_epipolar_ratio = 0.5;
+	bool use_degensac = true;
+	// DEGENSAC's nested run: FundamentalMatrixPlaneParallaxSolver with a fixed homography as the minimal solver
+	bool plane_parallax = false;
+	double pp_H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+	const double *rows_host = nullptr; // the caller's [N, dim] rows (DEGENSAC's seven-point test runs on the host)
 	bool do_logging = false;
 	uint64_t seed = 1;
 	// gcransac::utils::Settings defaults (gcr/settings.h:66-86) as overridden by progressive_x.h:64-71
@@ -389,8 +396,8 @@ class Driver {
 	Driver(pxb_ctx *ctx, const Settings &s) : ctx_(ctx), s_(s) {
 		N_ = ctx->pts.N;
 		ms_ = model_size(s.type);
-		m_ = sample_size(s.type);
-		maxsol_ = max_solutions(s.type);
+		m_ = s.plane_parallax ? 2 : sample_size(s.type);
+		maxsol_ = s.plane_parallax ? 1 : max_solutions(s.type);
 	}
 	int build_graph(double radius, int k);
 	void build_grid_layers(const double *rows) { // ProgressiveNapsacSampler<4>(.., {16, 8, 4, 2}, .., sizes, 0.5)
@@ -417,6 +424,7 @@ class Driver {
 	size_t pearl_outliers_ = 0;
 	// GC-RANSAC statistics of the last proposal
 	size_t iteration_number_ = 0, graph_cut_number_ = 0, lo_number_ = 0;
+	size_t degensac_degenerate_ = 0, degensac_updates_ = 0; // H-degenerate samples seen / models replaced (logging)
 	std::vector<int64_t> proposal_inliers_;
 
 	// --- operators (thin wrappers; every N-point loop is a kernel) ---
@@ -478,7 +486,14 @@ class Driver {
 		uint8_t *d_sv = reinterpret_cast<uint8_t *>(d_n + K), *d_mv = d_sv + K;
 		PXB_TRY(api_h2d(ctx_, ctx_->idx.ptr, samples.data(), sizeof(int64_t) * (size_t)K * m_));
 		PXB_CUDA(cudaMemsetAsync(ctx_->models.ptr, 0, sizeof(double) * (size_t)KS * ms_, ctx_->stream));
-		PXB_TRY(launch_solve_minimal(ctx_, ctx_->idx.as<int64_t>(), K, ctx_->models.as<double>(), d_n, d_sv, d_mv));
+		if (s_.plane_parallax) {
+			PXB_TRY(ctx_->outC.reserve(sizeof(double) * 9));
+			PXB_TRY(api_h2d(ctx_, ctx_->outC.ptr, s_.pp_H, sizeof(double) * 9));
+			PXB_TRY(launch_solve_plane_parallax(ctx_, ctx_->idx.as<int64_t>(), K, ctx_->outC.as<double>(), ctx_->models.as<double>(),
+			                                    d_n, d_sv, d_mv));
+		} else {
+			PXB_TRY(launch_solve_minimal(ctx_, ctx_->idx.as<int64_t>(), K, ctx_->models.as<double>(), d_n, d_sv, d_mv));
+		}
 		PXB_TRY(api_d2h(ctx_, models.data(), ctx_->models.ptr, sizeof(double) * (size_t)KS * ms_));
 		PXB_TRY(api_d2h(ctx_, n.data(), d_n, sizeof(int32_t) * (size_t)K));
 		PXB_TRY(api_d2h(ctx_, sv.data(), d_sv, (size_t)K));
@@ -510,7 +525,9 @@ class Driver {
 	bool weighting_applicable() const { return s_.type != PXB_MODEL_PNP && s_.type != PXB_MODEL_LINE2D; }
 	// H/F solvers read weights_[row of the gathered sample]; the VP solver reads weights_[point index] (:203)
 	bool weights_by_point() const { return s_.type == PXB_MODEL_VANISHING_POINT; }
-	int model_is_valid(const double *model, size_t slot_valid, bool &valid);
+	int model_is_valid(std::vector<double> &model, size_t slot_valid, const int64_t *sample, uint64_t nested_seed, bool &valid,
+	                   bool &updated);
+	int apply_degensac(std::vector<double> &model, const int64_t *sample, uint64_t nested_seed, bool &valid, bool &updated);
 	size_t iteration_number_for(size_t inliers, double log_probability) const;
 	int propose(uint64_t round_seed, std::vector<double> &model_out, bool &found);
 	int local_optimization(Sampler &lo_sampler, std::vector<double> &best_model, Score &best_score, double T2);
@@ -610,21 +627,193 @@ int Driver::lo_labeling(const double *model, std::vector<int64_t> &inliers) {
 // Estimator::isValidModel as called from GCRANSAC::run (:441-447) with threshold_ = truncated_threshold.
 //   H   determinant test (already evaluated by the solver kernel)          homography_estimator.h:326-342
 //   F   at least max(7, half) of the Sampson inliers must also be inliers under the symmetric epipolar distance
-//       (fundamental_estimator.h:268-325); DEGENSAC (:341-572) is not applied (nested GC-RANSAC, out of scope)
+//       (fundamental_estimator.h:268-325), then DEGENSAC (:341-572, Driver::apply_degensac)
 //   PnP always true                                                         perspective_n_point_estimator.h:210-218
-int Driver::model_is_valid(const double *model, size_t slot_valid, bool &valid) {
+int Driver::model_is_valid(std::vector<double> &model, size_t slot_valid, const int64_t *sample, uint64_t nested_seed,
+                           bool &valid, bool &updated) {
 	valid = slot_valid != 0;
+	updated = false;
 	if (s_.type != PXB_MODEL_FUNDAMENTAL || !valid) return PXB_OK;
 	const double tt = 3.0 / 2.0 * s_.threshold, T2 = tt * tt;
 	PXB_TRY(ctx_->models.reserve(sizeof(double) * 9));
 	PXB_TRY(ctx_->outB.reserve(sizeof(long long) * 2));
-	PXB_CUDA(cudaMemcpyAsync(ctx_->models.ptr, model, sizeof(double) * 9, cudaMemcpyHostToDevice, ctx_->stream));
+	PXB_CUDA(cudaMemcpyAsync(ctx_->models.ptr, model.data(), sizeof(double) * 9, cudaMemcpyHostToDevice, ctx_->stream));
 	PXB_TRY(launch_f_sym_count(ctx_, ctx_->models.as<double>(), T2, tt * tt, ctx_->outB.as<long long>()));
 	long long c[2];
 	PXB_CUDA(cudaMemcpyAsync(c, ctx_->outB.ptr, sizeof(c), cudaMemcpyDeviceToHost, ctx_->stream));
 	PXB_CUDA(cudaStreamSynchronize(ctx_->stream));
-	const size_t minimum = std::max<size_t>(7, (size_t)((double)c[0] * 0.5));
+	const size_t minimum = std::max<size_t>(7, (size_t)((double)c[0] * s_.sym_epipolar_ratio)); // fundamental_estimator.h:303-304
 	valid = (size_t)c[1] >= minimum;
+	if (!valid) return PXB_OK;
+	// :326-334: seven-point models of the outer estimator go through DEGENSAC
+	if (s_.use_degensac && !s_.plane_parallax && s_.rows_host && sample) PXB_TRY(apply_degensac(model, sample, nested_seed, valid, updated));
+	return PXB_OK;
+}
+
+namespace {
+// eigenvector of the smallest eigenvalue of a symmetric 3x3 (cyclic Jacobi)
+void smallest_eigenvector3(double A[3][3], double v[3]) {
+	double V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+	for (int sweep = 0; sweep < 60; ++sweep) {
+		if (std::fabs(A[0][1]) + std::fabs(A[0][2]) + std::fabs(A[1][2]) == 0.0) break;
+		for (int p = 0; p < 2; ++p)
+			for (int q = p + 1; q < 3; ++q) {
+				if (A[p][q] == 0.0) continue;
+				const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+				const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+				const double c = 1.0 / std::sqrt(t * t + 1.0), sn = t * c;
+				for (int k = 0; k < 3; ++k) {
+					const double akp = A[k][p], akq = A[k][q];
+					A[k][p] = c * akp - sn * akq;
+					A[k][q] = sn * akp + c * akq;
+				}
+				for (int k = 0; k < 3; ++k) {
+					const double apk = A[p][k], aqk = A[q][k];
+					A[p][k] = c * apk - sn * aqk;
+					A[q][k] = sn * apk + c * aqk;
+				}
+				for (int k = 0; k < 3; ++k) {
+					const double vkp = V[k][p], vkq = V[k][q];
+					V[k][p] = c * vkp - sn * vkq;
+					V[k][q] = sn * vkp + c * vkq;
+				}
+			}
+	}
+	int b = 0;
+	for (int i = 1; i < 3; ++i)
+		if (A[i][i] < A[b][b]) b = i;
+	for (int i = 0; i < 3; ++i) v[i] = V[i][b];
+}
+inline void cross3(const double *a, const double *b, double *o) {
+	o[0] = a[1] * b[2] - a[2] * b[1];
+	o[1] = a[2] * b[0] - a[0] * b[2];
+	o[2] = a[0] * b[1] - a[1] * b[0];
+}
+inline double h_transfer_error2(const double *H, const double *q) { // homography_estimator.h:181-199
+	const double t1 = H[0] * q[0] + H[1] * q[1] + H[2], t2 = H[3] * q[0] + H[4] * q[1] + H[5], t3 = H[6] * q[0] + H[7] * q[1] + H[8];
+	const double d1 = q[2] - (t1 / t3), d2 = q[3] - (t2 / t3);
+	return d1 * d1 + d2 * d2;
+}
+// fundamental_estimator.h:341-476 (see pxb_h_degenerate_sample in include/pxb200.h)
+bool h_degenerate_sample(const double *rows, const int64_t *sample, const double *F, double *Hbest) {
+	static const int triplets[15] = {0, 1, 2, 3, 4, 5, 0, 1, 6, 3, 4, 6, 2, 5, 6};
+	// epipole = third left singular vector of F (null vector of F^T), scaled to z = 1
+	double FFt[3][3];
+	for (int i = 0; i < 3; ++i)
+		for (int j = 0; j < 3; ++j) FFt[i][j] = F[3 * i] * F[3 * j] + F[3 * i + 1] * F[3 * j + 1] + F[3 * i + 2] * F[3 * j + 2];
+	double e[3];
+	smallest_eigenvector3(FFt, e);
+	for (int i = 0; i < 3; ++i) e[i] /= e[2];
+	e[2] = 1.0;
+	const double ex[9] = {0, -e[2], e[1], e[2], 0, -e[0], -e[1], e[0], 0};
+	double A[9];
+	for (int r = 0; r < 3; ++r)
+		for (int c = 0; c < 3; ++c) A[3 * r + c] = ex[3 * r] * F[c] + ex[3 * r + 1] * F[3 + c] + ex[3 * r + 2] * F[6 + c];
+	const double sq_h_thr = 2.0 * 2.0; // homography_threshold_ = 2.0 (:93)
+	bool degenerate = false;
+	for (int t = 0; t < 5 && !degenerate; ++t) {
+		const int64_t pid[3] = {sample[triplets[3 * t]], sample[triplets[3 * t + 1]], sample[triplets[3 * t + 2]]};
+		double M[9], b[3];
+		for (int k = 0; k < 3; ++k) {
+			const double *q = rows + 4 * pid[k];
+			const double x1[3] = {q[0], q[1], 1.0}, x2[3] = {q[2], q[3], 1.0};
+			double Ax1[3], c1[3], c2[3];
+			for (int r = 0; r < 3; ++r) Ax1[r] = A[3 * r] * x1[0] + A[3 * r + 1] * x1[1] + A[3 * r + 2] * x1[2];
+			cross3(x2, Ax1, c1);
+			cross3(x2, e, c2);
+			b[k] = (c1[0] * c2[0] + c1[1] * c2[1] + c1[2] * c2[2]) / (c2[0] * c2[0] + c2[1] * c2[1] + c2[2] * c2[2]);
+			M[3 * k] = x1[0], M[3 * k + 1] = x1[1], M[3 * k + 2] = x1[2];
+		}
+		// M^-1 b by cofactors
+		const double c00 = M[4] * M[8] - M[5] * M[7], c01 = M[5] * M[6] - M[3] * M[8], c02 = M[3] * M[7] - M[4] * M[6];
+		const double det = M[0] * c00 + M[1] * c01 + M[2] * c02;
+		const double inv[9] = {c00 / det, (M[2] * M[7] - M[1] * M[8]) / det, (M[1] * M[5] - M[2] * M[4]) / det,
+		                       c01 / det, (M[0] * M[8] - M[2] * M[6]) / det, (M[2] * M[3] - M[0] * M[5]) / det,
+		                       c02 / det, (M[1] * M[6] - M[0] * M[7]) / det, (M[0] * M[4] - M[1] * M[3]) / det};
+		double mb[3];
+		for (int r = 0; r < 3; ++r) mb[r] = inv[3 * r] * b[0] + inv[3 * r + 1] * b[1] + inv[3 * r + 2] * b[2];
+		double Hm[9];
+		for (int r = 0; r < 3; ++r)
+			for (int c = 0; c < 3; ++c) Hm[3 * r + c] = A[3 * r + c] - e[r] * mb[c];
+		size_t inlier_number = 3;
+		for (int i = 0; i < 7; ++i) {
+			const int64_t idx = sample[i];
+			if (idx == pid[0] || idx == pid[1] || idx == pid[2]) continue;
+			if (h_transfer_error2(Hm, rows + 4 * idx) < sq_h_thr) ++inlier_number;
+		}
+		if (inlier_number >= 5) {
+			std::memcpy(Hbest, Hm, sizeof(Hm));
+			degenerate = true;
+		}
+	}
+	return degenerate;
+}
+} // namespace
+
+// FundamentalMatrixEstimator::applyDegensac (gcr/estimators/fundamental_estimator.h:341-572). The seven-point sample is
+// H-degenerate when one of five point triplets induces (together with F) a homography that at least five of the seven
+// points follow (2 px). Then: the homography is refitted to the F-inliers that follow it, a nested GC-RANSAC with the
+// plane-and-parallax solver (that homography + two off-plane correspondences) runs on all points, and its model replaces
+// F when it has more inliers. Differences from the reference: the nested run is capped at 5000 iterations (the
+// reference's cap is SIZE_MAX) and draws from the seedable generator.
+int Driver::apply_degensac(std::vector<double> &model, const int64_t *sample, uint64_t nested_seed, bool &valid, bool &updated) {
+	const double *rows = s_.rows_host;
+	const double sq_h_thr = 2.0 * 2.0; // homography_threshold_ = 2.0 (:93)
+	double Hbest[9];
+	const bool degenerate = h_degenerate_sample(rows, sample, model.data(), Hbest);
+	if (!degenerate) return PXB_OK;
+	++degensac_degenerate_;
+	// the F-inliers that follow the homography
+	const double tt = 3.0 / 2.0 * s_.threshold, T2 = tt * tt;
+	std::vector<int64_t> f_inliers, h_inliers;
+	PXB_TRY(inliers_of(model.data(), T2, f_inliers));
+	for (int64_t i : f_inliers)
+		if (h_transfer_error2(Hbest, rows + 4 * i) < sq_h_thr) h_inliers.push_back(i);
+	if (h_inliers.size() < 4) { // homography_estimator.nonMinimalSampleSize()
+		valid = false;
+		return PXB_OK;
+	}
+	// non-minimal homography on them (the H fit kernel reads the same [x1 y1 x2 y2] rows)
+	std::vector<int32_t> off = {0, (int32_t)h_inliers.size()}, idx(h_inliers.begin(), h_inliers.end());
+	PXB_TRY(ctx_->idx.reserve(sizeof(int32_t) * (off.size() + idx.size()) + 64));
+	int32_t *d_off = ctx_->idx.as<int32_t>(), *d_idx = d_off + off.size();
+	PXB_TRY(ctx_->models.reserve(sizeof(double) * 9));
+	PXB_TRY(ctx_->outA.reserve(sizeof(int32_t)));
+	PXB_TRY(api_h2d(ctx_, d_off, off.data(), sizeof(int32_t) * off.size()));
+	PXB_TRY(api_h2d(ctx_, d_idx, idx.data(), sizeof(int32_t) * idx.size()));
+	PXB_TRY(launch_fit_h(ctx_, 1, d_off, d_idx, nullptr, ctx_->models.as<double>(), ctx_->outA.as<int32_t>()));
+	double Hfit[9];
+	int32_t ok = 0;
+	PXB_TRY(api_d2h(ctx_, Hfit, ctx_->models.ptr, sizeof(Hfit)));
+	PXB_TRY(api_d2h(ctx_, &ok, ctx_->outA.ptr, sizeof(ok)));
+	PXB_TRY(api_sync(ctx_));
+	if (!ok) {
+		valid = false;
+		return PXB_OK;
+	}
+	// nested GC-RANSAC: plane-and-parallax minimal solver, eight-point non-minimal solver, plain MSAC scoring
+	Settings ns = s_;
+	ns.plane_parallax = true;
+	std::memcpy(ns.pp_H, Hfit, sizeof(Hfit));
+	ns.threshold = tt;          // gcransac.settings.threshold = threshold_ (the outer truncated threshold)
+	ns.lambda = 0.0;            // spatial_coherence_weight = 0
+	ns.confidence = 0.99;
+	ns.max_iters = 5000;
+	ns.max_local_optimization_number = 10; // gcr/settings.h:72
+	ns.sampler_id = 0;
+	ns.napsac = ns.progressive_napsac = false;
+	ns.use_degensac = false;    // FundamentalMatrixEstimator<PlaneParallax, EightPoint>(0.0, false)
+	ns.sym_epipolar_ratio = 0.0;
+	ns.do_logging = false;
+	Driver nested(ctx_, ns);
+	std::vector<double> model2;
+	bool found = false;
+	PXB_TRY(nested.propose(nested_seed, model2, found));
+	if (found && nested.proposal_inliers_.size() > f_inliers.size()) {
+		model = model2;
+		updated = true;
+		++degensac_updates_;
+	}
 	return PXB_OK;
 }
 
@@ -801,12 +990,21 @@ int Driver::propose(uint64_t round_seed, std::vector<double> &model_out, bool &f
 		if (slot != SIZE_MAX) {
 			for (int j = 0; j < blk_n[slot]; ++j) {
 				const size_t q = slot * maxsol_ + j;
-				const Score sc = finish_score(blk_cnt[q], blk_val[q], blk_shr[q], best_score.inliers);
-				// :441-447: better score AND Estimator::isValidModel
-				bool model_ok = false;
-				if (best_score.value < sc.value) PXB_TRY(model_is_valid(blk_models.data() + q * ms_, blk_mv[slot], model_ok));
+				Score sc = finish_score(blk_cnt[q], blk_val[q], blk_shr[q], best_score.inliers);
+				// :441-447: better score AND Estimator::isValidModel (which may replace the model: DEGENSAC)
+				bool model_ok = false, model_updated = false;
+				std::vector<double> candidate(blk_models.begin() + q * ms_, blk_models.begin() + (q + 1) * ms_);
+				if (best_score.value < sc.value)
+					PXB_TRY(model_is_valid(candidate, blk_mv[slot], samples.data() + slot * m_,
+					                       round_seed * 7919ull + iteration_number_ * 31ull + (uint64_t)j, model_ok, model_updated));
 				if (best_score.value < sc.value && model_ok) {
-					best_model.assign(blk_models.begin() + q * ms_, blk_models.begin() + (q + 1) * ms_);
+					if (model_updated) { // :450-457 re-score the replaced model
+						std::vector<int64_t> c1;
+						std::vector<double> v1, s1;
+						PXB_TRY(score_models(candidate.data(), 1, T2, c1, v1, s1));
+						sc = finish_score(c1[0], v1[0], s1[0], best_score.inliers);
+					}
+					best_model = candidate;
 					best_score = sc;
 					do_local_optimization = iteration_number_ > s_.min_iteration_number_before_lo &&
 					                        (size_t)best_score.inliers > (size_t)m_; // :464-465
@@ -999,8 +1197,9 @@ int Driver::run() {
 		bool found = false;
 		PXB_TRY(propose(s_.seed * 1000003ull + it, model, found));
 		if (s_.do_logging)
-			fprintf(stdout, "[pxb] proposal %zu: %s, %zu inliers, %zu iterations, %zu LO runs, %zu graph cuts\n", it + 1,
-			        found ? "found" : "none", proposal_inliers_.size(), iteration_number_, lo_number_, graph_cut_number_);
+			fprintf(stdout, "[pxb] proposal %zu: %s, %zu inliers, %zu iterations, %zu LO runs, %zu graph cuts, DEGENSAC %zu/%zu\n",
+			        it + 1, found ? "found" : "none", proposal_inliers_.size(), iteration_number_, lo_number_, graph_cut_number_,
+			        degensac_updates_, degensac_degenerate_);
 		if (!found) continue; // :301-303
 		number_of_ransac_iterations += iteration_number_;
 		std::vector<double> pref;
@@ -1074,6 +1273,8 @@ int run_two_view(pxb_ctx *ctx, int type, const double *corr, int64_t N, int64_t 
 	for (int d = 0; d < 4; ++d) s.sizes[d] = sizes[d];
 	if (set_exponent) s.exponent = (int)scoring_exponent; // setExponent(const int) truncates (progressive_x.h:551)
 	s.do_logging = do_logging != 0;
+	s.rows_host = corr;
+	if (const char *e = getenv("PXB_DEGENSAC")) s.use_degensac = atoi(e) != 0; // A/B switch (default on, as the reference)
 	if (seed == 0) seed = (uint64_t)std::chrono::high_resolution_clock::now().time_since_epoch().count();
 	s.seed = seed;
 	Driver drv(ctx, s);
@@ -1257,6 +1458,15 @@ int pxb_find_lines(pxb_ctx *ctx, const double *points, const double *weights, in
 	                         spatial_coherence_weight, threshold, confidence, neighborhood_ball_radius,
 	                         maximum_tanimoto_similarity, max_iters, minimum_point_number, maximum_model_number, sampler_id, 2,
 	                         2, scoring_exponent, do_logging, seed);
+}
+
+int pxb_h_degenerate_sample(const double *rows, const int64_t *sample7, const double *F, double *H_out, int32_t *degenerate) {
+	if (!rows || !sample7 || !F || !H_out || !degenerate) {
+		set_error("null argument");
+		return PXB_ERR_ARGUMENT;
+	}
+	*degenerate = h_degenerate_sample(rows, sample7, F, H_out) ? 1 : 0;
+	return PXB_OK;
 }
 
 } // extern "C"

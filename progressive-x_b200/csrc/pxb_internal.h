@@ -129,6 +129,8 @@ int launch_segment_sums(pxb_ctx *ctx, const double *models, int64_t L, const int
 int launch_lo_unary(pxb_ctx *ctx, const double *model, double thr, double lambda, double *d, double *e0, double *e1);
 int launch_tukey(pxb_ctx *ctx, const double *model, double T2, double *w);
 int launch_inlier_compact(pxb_ctx *ctx, const double *model, double T2, int64_t *inliers, int64_t *n_inliers_dev);
+int launch_solve_plane_parallax(pxb_ctx *ctx, const int64_t *samples, int64_t K, const double *H_dev, double *models_out,
+                                int32_t *n_models, uint8_t *sample_valid, uint8_t *model_valid);
 int launch_solve_minimal(pxb_ctx *ctx, const int64_t *samples, int64_t K, double *models_out, int32_t *n_models,
                          uint8_t *sample_valid, uint8_t *model_valid);
 int launch_greedy_label(pxb_ctx *ctx, const double *D, int64_t N, int32_t L1, double label_cost,

@@ -583,6 +583,55 @@ __global__ void __launch_bounds__(128)
 	n_models[k] = 1;
 }
 
+// ------------------------------------------------------------------------------------------------
+// DEGENSAC's plane-and-parallax solver: F from a fixed homography and two off-plane correspondences
+// ------------------------------------------------------------------------------------------------
+// FundamentalMatrixPlaneParallaxSolver::estimateModel (gcr/estimators/solver_fundamental_matrix_plane_and_parallax.h):
+// line_i = (H x1_i) x x2_i, epipole = line_1 x line_2, F = [epipole]_x H; no model when |epipole_z| < epsilon.
+__global__ void __launch_bounds__(128)
+    k_solve_fpp(const double *__restrict__ aos, const int64_t *__restrict__ samples, int64_t K, const double *__restrict__ Hm,
+                double *__restrict__ models, int32_t *__restrict__ n_models) {
+	const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= K) return;
+	double H[9];
+	for (int i = 0; i < 9; ++i) H[i] = Hm[i];
+	double line[2][3];
+	for (int j = 0; j < 2; ++j) {
+		const double *q = aos + 4 * samples[2 * k + j];
+		const double s[3] = {q[0], q[1], 1.0}, d[3] = {q[2], q[3], 1.0};
+		double pr[3];
+		for (int r = 0; r < 3; ++r) pr[r] = add(add(mul(H[3 * r], s[0]), mul(H[3 * r + 1], s[1])), mul(H[3 * r + 2], s[2]));
+		line[j][0] = sub(mul(pr[1], d[2]), mul(pr[2], d[1]));
+		line[j][1] = sub(mul(pr[2], d[0]), mul(pr[0], d[2]));
+		line[j][2] = sub(mul(pr[0], d[1]), mul(pr[1], d[0]));
+	}
+	double e[3];
+	e[0] = sub(mul(line[0][1], line[1][2]), mul(line[0][2], line[1][1]));
+	e[1] = sub(mul(line[0][2], line[1][0]), mul(line[0][0], line[1][2]));
+	e[2] = sub(mul(line[0][0], line[1][1]), mul(line[0][1], line[1][0]));
+	if (!(fabs(e[2]) >= 2.220446049250313e-16)) { // also rejects NaN
+		n_models[k] = 0;
+		return;
+	}
+	const double ex[9] = {0.0, -e[2], e[1], e[2], 0.0, -e[0], -e[1], e[0], 0.0};
+	double *F = models + 9 * k;
+	for (int r = 0; r < 3; ++r)
+		for (int c = 0; c < 3; ++c)
+			F[3 * r + c] = add(add(mul(ex[3 * r], H[c]), mul(ex[3 * r + 1], H[3 + c])), mul(ex[3 * r + 2], H[6 + c]));
+	n_models[k] = 1;
+}
+
+int launch_solve_plane_parallax(pxb_ctx *ctx, const int64_t *samples, int64_t K, const double *H_dev, double *models_out,
+                                int32_t *n_models, uint8_t *sample_valid, uint8_t *model_valid) {
+	if (K <= 0) return PXB_OK;
+	k_solve_fpp<<<(unsigned)((K + 127) / 128), 128, 0, ctx->stream>>>(ctx->pts.aos, samples, K, H_dev, models_out, n_models);
+	ctx->launches++;
+	if (sample_valid) PXB_CUDA(cudaMemsetAsync(sample_valid, 1, (size_t)K, ctx->stream));
+	if (model_valid) PXB_CUDA(cudaMemsetAsync(model_valid, 1, (size_t)K, ctx->stream));
+	PXB_CUDA(cudaGetLastError());
+	return PXB_OK;
+}
+
 int launch_solve_minimal(pxb_ctx *ctx, const int64_t *samples, int64_t K, double *models_out, int32_t *n_models,
                          uint8_t *sample_valid, uint8_t *model_valid) {
 	if (K <= 0) return PXB_OK;

@@ -74,6 +74,8 @@ def load_library() -> C.CDLL:
     lib.pxb_tanimoto.argtypes = [vp, vp, vp, i64, C.POINTER(f64)]
     lib.pxb_compound_max.argtypes = [vp, vp, i64, i64, vp]
     lib.pxb_solve_minimal.argtypes = [vp, vp, i64, vp, vp, vp, vp]
+    lib.pxb_solve_plane_parallax.argtypes = [vp, vp, i64, vp, vp, vp]
+    lib.pxb_h_degenerate_sample.argtypes = [vp, vp, vp, vp, vp]
     lib.pxb_pearl_datacost.argtypes = [vp, vp, i64, f64, f64, vp]
     lib.pxb_pearl_label.argtypes = [vp, vp, i64, i32, f64, f64, vp, vp, vp, vp, C.POINTER(f64)]
     lib.pxb_segment_residual_sums.argtypes = [vp, vp, i64, vp, vp, vp]
@@ -249,6 +251,16 @@ class Context:
         _check(self.lib.pxb_solve_minimal(self.handle, _ptr(s), K, _ptr(models), _ptr(n), _ptr(sv), _ptr(mv)))
         return models, n, sv, mv
 
+    def solve_plane_parallax(self, samples, H):
+        """DEGENSAC's two-point solver over a fixed homography: (models [K, 9], n [K])."""
+        s = np.ascontiguousarray(samples, dtype=np.int64).reshape(-1, 2)
+        Hm = np.ascontiguousarray(H, dtype=np.float64).reshape(9)
+        K = s.shape[0]
+        models = np.zeros((K, 9), dtype=np.float64)
+        n = np.zeros(K, dtype=np.int32)
+        _check(self.lib.pxb_solve_plane_parallax(self.handle, _ptr(s), K, _ptr(Hm), _ptr(models), _ptr(n)))
+        return models, n
+
     # -- a9..a12 -------------------------------------------------------------------------------------------
     def pearl_datacost(self, models, thr: float, lam: float) -> np.ndarray:
         m, L = self._models(models)
@@ -337,3 +349,14 @@ class Context:
         bad = C.c_int64()
         _check(self.lib.pxb_selftest_division(self.handle, seed, n, mode, C.byref(bad)))
         return bad.value
+
+
+def h_degenerate_sample(rows, sample7, F):
+    """DEGENSAC's seven-point test (host arithmetic, no context): (degenerate, H [3, 3] or None)."""
+    r = np.ascontiguousarray(rows, dtype=np.float64).reshape(-1, 4)
+    s = np.ascontiguousarray(sample7, dtype=np.int64).reshape(7)
+    Fm = np.ascontiguousarray(F, dtype=np.float64).reshape(9)
+    H = np.zeros(9, dtype=np.float64)
+    flag = np.zeros(1, dtype=np.int32)
+    _check(load_library().pxb_h_degenerate_sample(_ptr(r), _ptr(s), _ptr(Fm), _ptr(H), _ptr(flag)))
+    return bool(flag[0]), (H.reshape(3, 3) if flag[0] else None)

@@ -101,6 +101,26 @@ def multi_motion_scene(N, n_motions=3, ratios=(0.25, 0.25, 0.20), noise=0.3, f=8
     return np.ascontiguousarray(corrs[perm]), labels[perm], np.stack(Fs)
 
 
+def plane_dominated_pair(n_plane, n_off, noise, seed):
+    """Two views of a plane plus off-plane points: rows [n, 4], labels (0 = plane, 1 = off-plane), F."""
+    rng = np.random.default_rng(seed)
+    f, w, h = 800.0, 1024, 768
+    Kc = np.array([[f, 0, w / 2], [0, f, h / 2], [0, 0, 1.0]])
+    a = rng.normal(0, 0.15, 3)
+    R, _ = np.linalg.qr(np.eye(3) + np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]]))
+    R *= np.sign(np.linalg.det(R))
+    t = np.array([0.6, 0.1, 0.05])
+    xy = rng.uniform(-2, 2, (n_plane, 2))
+    Xp = np.column_stack([xy, 6.0 + 0.2 * xy[:, 0] - 0.1 * xy[:, 1]])
+    Xo = np.column_stack([rng.uniform(-2, 2, (n_off, 2)), rng.uniform(3.5, 9.0, n_off)])
+    X = np.concatenate([Xp, Xo])
+    p1, p2 = X @ Kc.T, (X @ R.T + t) @ Kc.T
+    rows = np.column_stack([p1[:, :2] / p1[:, 2:], p2[:, :2] / p2[:, 2:]]) + rng.normal(0, noise, (len(X), 4))
+    tx = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]])
+    Kinv = np.linalg.inv(Kc)
+    return np.ascontiguousarray(rows), np.r_[np.zeros(n_plane, int), np.ones(n_off, int)], Kinv.T @ tx @ R @ Kinv
+
+
 def multi_pose_scene(N, n_objects=10, inlier_ratio_each=0.06, noise_px=1.0, seed=0, Kc=TLESS_K):
     """2D-3D matches. Returns (image_points [N,2] px, world_points [N,3], K, gt_labels, poses [n,3,4])."""
     rng = np.random.default_rng(seed)

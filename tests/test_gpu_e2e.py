@@ -172,3 +172,37 @@ def test_find_lines_synthetic():
     assert found >= 1
     with pytest.raises(ValueError):
         pyprogressivex.findLines(np.zeros((10, 3)), None, 10, 10)
+
+
+def test_plane_dominated_two_view_motion_uses_degensac(monkeypatch):
+    """A rigid scene whose correspondences lie mostly on one plane (fundamental_estimator.h:341-572): seven-point samples
+    are then H-degenerate most of the time. With DEGENSAC the returned epipolar geometry must also explain the off-plane
+    points; the switch PXB_DEGENSAC=0 (not the reference's behaviour) is only exercised for determinism of the A/B."""
+    rows, lab, F_true = syn.plane_dominated_pair(420, 80, 0.3, 21)
+    rng = np.random.default_rng(1)
+    outl = np.column_stack([rng.uniform(0, 1024, 150), rng.uniform(0, 768, 150), rng.uniform(0, 1024, 150), rng.uniform(0, 768, 150)])
+    corrs = np.ascontiguousarray(np.concatenate([rows, outl]))
+    off = np.flatnonzero(lab == 1)
+    x1 = np.column_stack([corrs[:, :2], np.ones(len(corrs))])
+    x2 = np.column_stack([corrs[:, 2:], np.ones(len(corrs))])
+
+    def sampson(Fm):
+        Fx1, Ftx2 = x1 @ Fm.T, x2 @ Fm
+        num = np.einsum("ni,ni->n", x2, Fx1) ** 2
+        return num / (Fx1[:, 0] ** 2 + Fx1[:, 1] ** 2 + Ftx2[:, 0] ** 2 + Ftx2[:, 1] ** 2)
+
+    good = 0
+    for seed in (1, 2, 3, 4):
+        Fs, labels = pyprogressivex.findTwoViewMotions(corrs, 1024, 768, 1024, 768, threshold=1.0, conf=0.99,
+                                                       spatial_coherence_weight=0.0, neighborhood_ball_radius=50.0,
+                                                       maximum_tanimoto_similarity=0.4, max_iters=2000, minimum_point_number=50,
+                                                       maximum_model_number=1, sampler_id=0, scoring_exponent=1.0, seed=seed)
+        assert Fs.shape[0] == 3
+        frac = float(np.mean(sampson(Fs[:3]) [off] < 1.5 ** 2))
+        good += frac > 0.9
+        again = pyprogressivex.findTwoViewMotions(corrs, 1024, 768, 1024, 768, threshold=1.0, conf=0.99,
+                                                  spatial_coherence_weight=0.0, neighborhood_ball_radius=50.0,
+                                                  maximum_tanimoto_similarity=0.4, max_iters=2000, minimum_point_number=50,
+                                                  maximum_model_number=1, sampler_id=0, scoring_exponent=1.0, seed=seed)
+        assert np.array_equal(again[0], Fs) and np.array_equal(again[1], labels)
+    assert good >= 3, good

@@ -435,3 +435,30 @@ def test_score_compound_ragged_sizes(ctx, oracle, t, N):
     for comp in (None, cp):
         _assert_score_equals_oracle(ctx, oracle, t, pts, models, T2, comp)
     _assert_score_equals_oracle(ctx, oracle, t, pts, models[:1], T2, cp)
+
+
+def test_plane_parallax_solver_bit_exact(ctx, oracle):
+    """DEGENSAC's two-point solver over a fixed homography: bit-exact against the oracle restatement, and the algebra the
+    reference relies on: the plane's points and both sample points satisfy the epipolar constraint of F = [e]x H."""
+    rows, lab, _ = syn.plane_dominated_pair(400, 400, 0.0, 11)
+    plane, off = np.flatnonzero(lab == 0), np.flatnonzero(lab == 1)
+    Hm, ok = oracle.fit_h_nonminimal(rows, plane)
+    assert ok
+    rng = np.random.default_rng(2)
+    S = np.stack([rng.choice(off, 2, replace=False) for _ in range(3000)]).astype(np.int64)
+    S[0] = [off[3], off[3]]  # the same correspondence twice: both lines coincide, epipole = 0 -> no model
+    ctx.upload_points(F, rows)
+    models, n = ctx.solve_plane_parallax(S, Hm)
+    models_o, n_o = oracle.solve_plane_parallax(rows, S, Hm)
+    assert np.array_equal(n, n_o) and n[0] == 0 and n[1:].all()
+    assert bits_equal(models, models_o)
+    x1 = np.column_stack([rows[:, :2], np.ones(len(rows))])
+    x2 = np.column_stack([rows[:, 2:], np.ones(len(rows))])
+    for k in (1, 17, 2999):
+        Fm = models[k].reshape(3, 3)
+        Fm = Fm / np.linalg.norm(Fm)
+        alg = np.abs(np.einsum("ni,ij,nj->n", x2, Fm, x1))
+        assert alg[plane].max() < 1e-6 and alg[S[k]].max() < 1e-6
+        assert np.median(alg[off]) < 1e-6  # noise-free rigid scene: every point is on the true epipolar geometry
+    with pytest.raises(Exception):
+        ctx.solve_plane_parallax(np.array([[0, len(rows)]]), Hm)
