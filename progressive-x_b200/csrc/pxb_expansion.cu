@@ -52,10 +52,34 @@ struct FlowGraphDev {
 	double *cap, *excess, *sink_cap;
 	int32_t *height[2];
 	int32_t *flags; // [0..2] BFS 'changed' (level mod 3), [3..5] 'active' (pulse mod 3), [6] pulses, [7] status
+	int async_cycles, idle_checks; // tuning knobs of the asynchronous phase (PXB_MF_ASYNC, PXB_MF_IDLE)
+	int block_bfs;  // 1/2: the launch carries 2n (3n+1) ints of dynamic shared memory and block 0 runs the global relabel alone
 };
 
 constexpr int kMfThreads = 256;
 constexpr int kWideDegree = 64;
+
+// predicated loads: issued back to back, no branch; the destination keeps `otherwise` when the predicate is false
+__device__ __forceinline__ int ld_nc_s32_if(const int32_t *p, bool pred, int otherwise) {
+	int v = otherwise;
+	asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\t@q ld.global.nc.s32 %0, [%1];\n\t}" : "+r"(v) : "l"(p), "r"((int)pred));
+	return v;
+}
+__device__ __forceinline__ double ld_cg_f64_if(const double *p, bool pred) {
+	double v = 0.0;
+	asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\t@q ld.global.cg.f64 %0, [%1];\n\t}" : "+d"(v) : "l"(p), "r"((int)pred));
+	return v;
+}
+__device__ __forceinline__ double ld_volatile_f64_if(const double *p, bool pred) {
+	double v = 0.0;
+	asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\t@q ld.volatile.global.f64 %0, [%1];\n\t}" : "+d"(v) : "l"(p), "r"((int)pred) : "memory");
+	return v;
+}
+__device__ __forceinline__ int ld_volatile_s32_if(const int32_t *p, bool pred, int otherwise) {
+	int v = otherwise;
+	asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\t@q ld.volatile.global.s32 %0, [%1];\n\t}" : "+r"(v) : "l"(p), "r"((int)pred) : "memory");
+	return v;
+}
 
 // Exact distance-to-sink labels by a level-synchronous BACKWARD breadth-first search in "push" form: the nodes of the
 // current frontier (height == level) mark every unlabelled in-neighbour v (residual arc v -> u, i.e. cap[rev(a)] > 0 for
@@ -109,6 +133,132 @@ __device__ void mf_global_relabel(const FlowGraphDev &G, int32_t *h, cg::grid_gr
 	grid.sync();
 }
 
+// The same labels computed by ONE block with the heights and the BFS queue in shared memory (graphs up to ~28k nodes:
+// every PEARL / LO cut of the configurations this engine targets). A level of the grid-wide form costs a chain of
+// dependent L2 round trips plus a grid barrier (~10 us) whatever the size of the frontier, and the heavy expansion moves
+// need 20-30 relabels of ~35 levels each; here a level is a few block barriers around a frontier-sized loop (queue
+// form: every node is expanded exactly once), and the other blocks wait at one grid barrier per relabel.
+// Returns (block-uniformly) whether any node with excess can still reach the sink.
+constexpr int kBfsChunk = 16;
+__device__ bool mf_global_relabel_block(const FlowGraphDev &G, int32_t *h, bool first) {
+	extern __shared__ int32_t mf_smem[];
+	__shared__ int s_tail, s_nwide, s_wide[32];
+	const int n = G.n;
+	int32_t *hs = mf_smem, *queue = mf_smem + n;
+	// block_bfs == 2: the CSR offsets fit as well (filled once per launch) and save a round trip per expansion
+	const int32_t *offs = G.arc_off;
+	if (G.block_bfs == 2) {
+		int32_t *so = mf_smem + 2 * n;
+		if (first)
+			for (int u = threadIdx.x; u <= n; u += blockDim.x) so[u] = G.arc_off[u];
+		offs = so;
+	}
+	const double *capp = G.cap;
+	if (threadIdx.x == 0) {
+		s_tail = 0;
+		s_nwide = 0;
+	}
+	__syncthreads();
+	for (int base = threadIdx.x; base < n; base += 4 * blockDim.x) { // four independent loads in flight per thread
+		double sc[4];
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			const int u = base + j * blockDim.x;
+			sc[j] = u < n ? __ldcg(&G.sink_cap[u]) : 0.0;
+		}
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			const int u = base + j * blockDim.x;
+			if (u >= n) break;
+			const bool at_sink = sc[j] > 0.0;
+			hs[u] = at_sink ? 1 : n;
+			if (at_sink) queue[atomicAdd(&s_tail, 1)] = u;
+		}
+	}
+	__syncthreads();
+	int begin = 0, level = 1;
+	for (;;) {
+		const int end = s_tail;
+		if (begin == end) break; // block-uniform
+		__syncthreads();         // everybody has read s_tail before the level appends to the queue
+		for (int i = begin + threadIdx.x; i < end; i += blockDim.x) {
+			const int u = queue[i];
+			if (u >= G.wide_begin) { // expanded by the whole block below
+				s_wide[atomicAdd(&s_nwide, 1)] = u;
+				continue;
+			}
+			// Arcs in chunks of 16. One SM's load path handles about one divergent sector per cycle, so the loop is
+			// written for few loads AND no waiting: heads first (predicated on the range), then -- only for heads that
+			// are still unlabelled, typically 1-3 of 16 -- the reverse arc and its capacity. The loads are predicated
+			// instructions (inline PTX): under a branch each one would be waited for before the next is issued.
+			const int a0 = offs[u], a1 = offs[u + 1];
+			for (int base = a0; base < a1; base += kBfsChunk) {
+				int v[kBfsChunk], r[kBfsChunk];
+				double c[kBfsChunk];
+				bool want[kBfsChunk];
+#pragma unroll
+				for (int j = 0; j < kBfsChunk; ++j) v[j] = ld_nc_s32_if(G.arc_head + base + j, base + j < a1, -1);
+#pragma unroll
+				for (int j = 0; j < kBfsChunk; ++j) want[j] = v[j] >= 0 && hs[v[j]] == n;
+#pragma unroll
+				for (int j = 0; j < kBfsChunk; ++j) r[j] = ld_nc_s32_if(G.arc_rev + base + j, want[j], 0);
+#pragma unroll
+				for (int j = 0; j < kBfsChunk; ++j) c[j] = ld_cg_f64_if(capp + r[j], want[j]);
+#pragma unroll
+				for (int j = 0; j < kBfsChunk; ++j)
+					if (want[j] && c[j] > 0.0 && atomicCAS(&hs[v[j]], n, level + 1) == n) queue[atomicAdd(&s_tail, 1)] = v[j];
+			}
+		}
+		__syncthreads();
+		const int nwide = s_nwide;
+		for (int w = 0; w < nwide; ++w) {
+			const int u = s_wide[w];
+			const int a1 = G.arc_off[u + 1];
+			for (int base = G.arc_off[u] + threadIdx.x; base < a1; base += 4 * blockDim.x) {
+				int v[4], r[4];
+				double c[4];
+				bool want[4];
+#pragma unroll
+				for (int j = 0; j < 4; ++j) v[j] = ld_nc_s32_if(G.arc_head + base + j * blockDim.x, base + j * (int)blockDim.x < a1, -1);
+#pragma unroll
+				for (int j = 0; j < 4; ++j) want[j] = v[j] >= 0 && hs[v[j]] == n;
+#pragma unroll
+				for (int j = 0; j < 4; ++j) r[j] = ld_nc_s32_if(G.arc_rev + base + j * blockDim.x, want[j], 0);
+#pragma unroll
+				for (int j = 0; j < 4; ++j) c[j] = ld_cg_f64_if(capp + r[j], want[j]);
+#pragma unroll
+				for (int j = 0; j < 4; ++j)
+					if (want[j] && c[j] > 0.0 && atomicCAS(&hs[v[j]], n, level + 1) == n) queue[atomicAdd(&s_tail, 1)] = v[j];
+			}
+		}
+		__syncthreads();
+		if (threadIdx.x == 0) s_nwide = 0;
+		begin = end;
+		++level;
+	}
+	bool active = false;
+	for (int base = threadIdx.x; base < n; base += 4 * blockDim.x) {
+		double ex[4];
+		int hu[4];
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			const int u = base + j * blockDim.x;
+			hu[j] = u < n ? hs[u] : n;
+			ex[j] = hu[j] < n ? __ldcg(&G.excess[u]) : 0.0;
+		}
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			const int u = base + j * blockDim.x;
+			if (u < n) h[u] = hu[j];
+			active |= ex[j] > 0.0;
+		}
+	}
+	if (threadIdx.x == 0) {
+		G.flags[8] += level; // statistics: BFS levels
+	}
+	return __syncthreads_or(active) != 0;
+}
+
 // One asynchronous push-relabel step of node u (Hong & He's lock-free rule: push to the LOWEST residual neighbour if it
 // is lower, else lift to one above it). Only the owner thread of u lowers excess[u] / cap[out-arcs of u] and writes
 // height[u]; everybody else only adds to them, so the atomics below can never drive a value negative.
@@ -153,15 +303,27 @@ __device__ __forceinline__ bool mf_process(const FlowGraphDev &G, volatile int32
 		}
 		return true;
 	}
+	// lowest residual neighbour (the first one in arc order among equals). Chunks of 8 arcs with predicated loads: the
+	// capacities and heads of a chunk travel together, then the heights of the residual heads -- two dependent round
+	// trips per chunk instead of two per arc.
 	int best_h = 0x7fffffff, best_a = -1;
-	for (int a = a0; a < a1; ++a)
-		if (cap[a] > 0.0) {
-			const int hv = h[G.arc_head[a]];
-			if (hv < best_h) {
-				best_h = hv;
-				best_a = a;
-			}
+	for (int base = a0; base < a1; base += 8) {
+		double c[8];
+		int v[8], hv[8];
+#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			c[j] = ld_volatile_f64_if(G.cap + base + j, base + j < a1);
+			v[j] = ld_nc_s32_if(G.arc_head + base + j, base + j < a1, 0);
 		}
+#pragma unroll
+		for (int j = 0; j < 8; ++j) hv[j] = ld_volatile_s32_if(G.height[0] + v[j], c[j] > 0.0, 0x7fffffff);
+#pragma unroll
+		for (int j = 0; j < 8; ++j)
+			if (hv[j] < best_h) {
+				best_h = hv[j];
+				best_a = base + j;
+			}
+	}
 	if (best_a < 0) { // no residual arc at all: the excess is stranded on the source side
 		h[u] = n;
 		return true;
@@ -186,7 +348,7 @@ __device__ bool mf_process_wide_block(const FlowGraphDev &G, volatile int32_t *h
 	__shared__ double s_e, s_wsum[kMfThreads / 32], s_gsum[kMfThreads / 32];
 	__shared__ int s_hu, s_wlow[kMfThreads / 32];
 	const int n = G.n, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	volatile double *excess = G.excess, *cap = G.cap;
+	volatile double *excess = G.excess;
 	if (threadIdx.x == 0) {
 		s_e = excess[u];
 		s_hu = h[u];
@@ -204,24 +366,23 @@ __device__ bool mf_process_wide_block(const FlowGraphDev &G, volatile int32_t *h
 	for (int pass = 0; pass < 2; ++pass) {
 		for (int base = a0; base < a1; base += kMfThreads) { // block-uniform trip count
 			const int a = base + threadIdx.x;
+			// two dependent round trips per chunk (capacity + head, then what is needed of the head), predicated loads
 			double want = 0.0;
-			int v = 0;
-			if (a < a1) {
-				const double c = cap[a];
-				if (c > 0.0) {
-					v = G.arc_head[a];
-					const int hv = h[v];
-					if (hv < hu) {
-						if (pass == 0) {
-							const volatile double *sc = G.sink_cap;
-							want = fmin(c, fmax(0.0, sc[v] - excess[v]));
-						} else {
-							want = c;
-						}
-					} else if (pass == 1) {
-						lowest = min(lowest, hv);
-					}
-				}
+			const bool in = a < a1;
+			const double c = ld_volatile_f64_if(G.cap + a, in);
+			const int v = ld_nc_s32_if(G.arc_head + a, in, 0);
+			const bool residual = c > 0.0;
+			const int hv = ld_volatile_s32_if(G.height[0] + v, residual, 0x7fffffff);
+			double sink_v = 0.0, excess_v = 0.0;
+			if (pass == 0) {
+				sink_v = ld_volatile_f64_if(G.sink_cap + v, residual);
+				excess_v = ld_volatile_f64_if(G.excess + v, residual);
+			}
+			if (residual) {
+				if (hv < hu)
+					want = pass == 0 ? fmin(c, fmax(0.0, sink_v - excess_v)) : c;
+				else if (pass == 1)
+					lowest = min(lowest, hv);
 			}
 			double incl = want;
 #pragma unroll
@@ -276,7 +437,7 @@ __device__ bool mf_process_wide_block(const FlowGraphDev &G, volatile int32_t *h
 	return true;
 }
 
-constexpr int kAsyncCycles = 192;
+constexpr int kAsyncCycles = 128;
 constexpr int kMaxRounds = 100000;
 
 __global__ void __launch_bounds__(kMfThreads) k_maxflow(FlowGraphDev G) {
@@ -289,27 +450,38 @@ __global__ void __launch_bounds__(kMfThreads) k_maxflow(FlowGraphDev G) {
 	for (; round < kMaxRounds; ++round) {
 		// exact distance-to-sink labels; nodes that cannot reach the sink any more get height n and go quiet
 		const long long t0 = clock64();
-		mf_global_relabel(G, h, grid, tid, nthreads);
+		if (G.block_bfs) {
+			if (blockIdx.x == 0) {
+				const bool any = mf_global_relabel_block(G, h, round == 0);
+				if (threadIdx.x == 0) G.flags[3] = any ? 1 : 0; // re-written only after the barrier that ends this round
+			}
+			__threadfence();
+			grid.sync();
+			if (tid == 0) G.flags[10] += (int)((clock64() - t0) >> 6);
+			if (*(volatile int32_t *)&G.flags[3] == 0) break;
+		} else {
+			mf_global_relabel(G, h, grid, tid, nthreads);
+			if (tid == 0) G.flags[10] += (int)((clock64() - t0) >> 6);
+			bool active = false;
+			for (int u = tid; u < n; u += nthreads) active |= (G.excess[u] > 0.0 && h[u] < n);
+			if (tid == 0) G.flags[3 + ((round + 1) % 3)] = 0;
+			if (active) G.flags[3 + (round % 3)] = 1;
+			grid.sync();
+			if (G.flags[3 + (round % 3)] == 0) break;
+		}
 		const long long t1 = clock64();
-		if (tid == 0) G.flags[10] += (int)((t1 - t0) >> 6);
-		bool active = false;
-		for (int u = tid; u < n; u += nthreads) active |= (G.excess[u] > 0.0 && h[u] < n);
-		if (tid == 0) G.flags[3 + ((round + 1) % 3)] = 0;
-		if (active) G.flags[3 + (round % 3)] = 1;
-		grid.sync();
-		if (G.flags[3 + (round % 3)] == 0) break;
 		// asynchronous phase: no barriers, every thread keeps discharging its own nodes
 		// A block whose nodes have been quiet for two checks in a row stops sweeping; flow that reaches it later from
 		// another block is picked up after the next relabel (the active test above decides termination, not this).
 		bool busy = false;
 		int idle_checks = 0;
-		for (int c = 0; c < kAsyncCycles; ++c) {
+		for (int c = 0; c < G.async_cycles; ++c) {
 			for (int w = blockIdx.x; w < G.wide_count; w += gridDim.x) busy |= mf_process_wide_block(G, h, G.wide_begin + w);
 			for (int u = tid; u < G.wide_begin; u += nthreads) busy |= mf_process(G, h, u);
 			if ((c & 7) == 7) {
 				idle_checks = __syncthreads_or(busy) ? 0 : idle_checks + 1;
 				busy = false;
-				if (idle_checks >= 2) break; // block-uniform
+				if (idle_checks >= G.idle_checks) break; // block-uniform
 			}
 		}
 		__threadfence();
@@ -321,6 +493,39 @@ __global__ void __launch_bounds__(kMfThreads) k_maxflow(FlowGraphDev G) {
 		G.flags[6] = round + 1;
 		G.flags[7] = round < kMaxRounds ? 1 : 0;
 	}
+}
+
+// Launch geometry of k_maxflow: a cooperative grid of at most 4 blocks per SM (one node per thread is enough), and --
+// when heights + queue of the graph fit -- 2n ints of dynamic shared memory for the single-block global relabel.
+struct MfLaunch {
+	int grid = 1;
+	size_t smem = 0;
+};
+static int mf_launch_config(pxb_ctx *ctx, FlowGraphDev &G, int min_grid, MfLaunch &out) {
+	static const bool grid_bfs_only = getenv("PXB_MF_GRID_BFS") != nullptr; // A/B switch: the grid-wide relabel
+	static const int async_cycles = getenv("PXB_MF_ASYNC") ? atoi(getenv("PXB_MF_ASYNC")) : kAsyncCycles;
+	static const int idle_checks = getenv("PXB_MF_IDLE") ? atoi(getenv("PXB_MF_IDLE")) : 4;
+	G.async_cycles = std::max(8, async_cycles);
+	G.idle_checks = std::max(1, idle_checks);
+	static bool attribute_set[64] = {}; // per device (function attributes belong to the device's context)
+	constexpr size_t kMaxSmem = 200 * 1024;
+	if (ctx->device < 0 || ctx->device >= 64 || !attribute_set[ctx->device]) {
+		PXB_CUDA(cudaFuncSetAttribute(k_maxflow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+		if (ctx->device >= 0 && ctx->device < 64) attribute_set[ctx->device] = true;
+	}
+	const size_t need = sizeof(int32_t) * 2 * (size_t)G.n, need_offs = sizeof(int32_t) * (3 * (size_t)G.n + 1);
+	G.block_bfs = (grid_bfs_only || G.wide_count > 32) ? 0 : (need_offs <= kMaxSmem ? 2 : (need <= kMaxSmem ? 1 : 0));
+	out.smem = G.block_bfs == 2 ? need_offs : (G.block_bfs == 1 ? need : 0);
+	int blocks_per_sm = 0;
+	PXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_maxflow, kMfThreads, out.smem));
+	if (blocks_per_sm < 1) {
+		set_error("k_maxflow does not fit on an SM with %zu bytes of shared memory", out.smem);
+		return PXB_ERR_CUDA;
+	}
+	const int want = (G.n + kMfThreads - 1) / kMfThreads;
+	const int cap = ctx->sm_count * std::min(blocks_per_sm, 4);
+	out.grid = std::max(1, std::min(std::max(min_grid, want), cap));
+	return PXB_OK;
 }
 
 // ---- host-side graph assembly with the reference's Energy/Graph arithmetic -----------------------------------
@@ -432,12 +637,11 @@ static int solve_min_cut(pxb_ctx *ctx, const FlowGraphHost &g, std::vector<uint8
 	G.height[0] = d_h0;
 	G.height[1] = d_h1;
 	G.flags = d_flags;
-	int blocks_per_sm = 0;
-	PXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_maxflow, kMfThreads, 0));
-	const int want = (n + kMfThreads - 1) / kMfThreads;
-	const int grid = std::max(1, std::min(want, ctx->sm_count * std::max(1, std::min(blocks_per_sm, 4))));
+	MfLaunch lc;
+	PXB_TRY(mf_launch_config(ctx, G, 1, lc));
+	const int grid = lc.grid;
 	void *args[] = {&G};
-	PXB_CUDA(cudaLaunchCooperativeKernel((void *)k_maxflow, dim3(grid), dim3(kMfThreads), args, 0, st));
+	PXB_CUDA(cudaLaunchCooperativeKernel((void *)k_maxflow, dim3(grid), dim3(kMfThreads), args, lc.smem, st));
 	ctx->launches++;
 	const int32_t *h = h_h0, *flags = h_flags;
 	PXB_CUDA(cudaMemcpyAsync(h_h0, d_h0, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
@@ -636,12 +840,11 @@ int lo_labeling_device(pxb_ctx *ctx, const double *model_dev, double thr, double
 	G.height[0] = d_h0;
 	G.height[1] = d_h1;
 	G.flags = d_flags;
-	int blocks_per_sm = 0;
-	PXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_maxflow, kMfThreads, 0));
-	const int want = (n + kMfThreads - 1) / kMfThreads;
-	const int grid = std::max(1, std::min(want, ctx->sm_count * std::max(1, std::min(blocks_per_sm, 4))));
+	MfLaunch lc;
+	PXB_TRY(mf_launch_config(ctx, G, 1, lc));
+	const int grid = lc.grid;
 	void *args[] = {&G};
-	PXB_CUDA(cudaLaunchCooperativeKernel((void *)k_maxflow, dim3(grid), dim3(kMfThreads), args, 0, st));
+	PXB_CUDA(cudaLaunchCooperativeKernel((void *)k_maxflow, dim3(grid), dim3(kMfThreads), args, lc.smem, st));
 	ctx->launches++;
 	k_lo_collect<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(N, d_h0, n, d_seg);
 	ctx->launches++;
@@ -947,10 +1150,9 @@ int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t
 	G.height[0] = d_h0;
 	G.height[1] = d_h1;
 	G.flags = d_flags;
-	int blocks_per_sm = 0;
-	PXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_maxflow, kMfThreads, 0));
-	const int want = (n + kMfThreads - 1) / kMfThreads;
-	const int grid = std::max(std::min(L1, ctx->sm_count), std::min(want, ctx->sm_count * std::max(1, std::min(blocks_per_sm, 4))));
+	MfLaunch lc;
+	PXB_TRY(mf_launch_config(ctx, G, std::min(L1, ctx->sm_count), lc));
+	const int grid = lc.grid;
 	PXB_TRY(ctx->reserve_pinned(sizeof(int32_t) * ((size_t)n + 16)));
 	int32_t *h_host = static_cast<int32_t *>(ctx->pinned), *flags_host = h_host + n;
 
@@ -968,7 +1170,7 @@ int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t
 			k_exp_assemble<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(N, L1, alpha, lambda, label_cost, D_dev, d_lab, d_goff, d_gidx,
 			                                                          d_label_count, d_rev, d_cap, d_excess, d_sink);
 			void *args[] = {&G};
-			PXB_CUDA(cudaLaunchCooperativeKernel((void *)k_maxflow, dim3(grid), dim3(kMfThreads), args, 0, st));
+			PXB_CUDA(cudaLaunchCooperativeKernel((void *)k_maxflow, dim3(grid), dim3(kMfThreads), args, lc.smem, st));
 			ctx->launches += 2;
 			PXB_CUDA(cudaMemcpyAsync(h_host, d_h0, sizeof(int32_t) * (size_t)N, cudaMemcpyDeviceToHost, st));
 			PXB_CUDA(cudaMemcpyAsync(flags_host, d_flags, sizeof(int32_t) * 16, cudaMemcpyDeviceToHost, st));
