@@ -147,12 +147,7 @@ int pearl_label_device(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t L1,
 		return api_sync(ctx);
 	}
 	// alpha-expansion
-	PXB_TRY(ctx->idx.reserve(sizeof(int32_t) * (size_t)(N + 1 + csr_off_host[N])));
-	int32_t *off = ctx->idx.as<int32_t>();
-	int32_t *idx = off + (N + 1);
-	PXB_TRY(api_h2d(ctx, off, csr_off_host, sizeof(int32_t) * (size_t)(N + 1)));
-	PXB_TRY(api_h2d(ctx, idx, csr_idx_host, sizeof(int32_t) * (size_t)csr_off_host[N]));
-	PXB_TRY(launch_alpha_expansion(ctx, D_dev, N, L1, lambda, label_cost, off, idx, csr_off_host[N], lab_in, lab_out, energy_out));
+	PXB_TRY(launch_alpha_expansion(ctx, D_dev, N, L1, lambda, label_cost, csr_off_host, csr_idx_host, lab_in, lab_out, energy_out));
 	PXB_TRY(api_d2h(ctx, labels_out_host, lab_out, sizeof(int32_t) * (size_t)N));
 	return api_sync(ctx);
 }
@@ -233,6 +228,7 @@ void pxb_ctx_destroy(pxb_ctx *ctx) {
 	if (ctx->pinned) cudaFreeHost(ctx->pinned);
 	if (ctx->stage) cudaFreeHost(ctx->stage);
 	lo_skeleton_free(ctx->lo_skeleton);
+	exp_skeleton_free(ctx->exp_skeleton);
 	cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }

@@ -868,7 +868,7 @@ struct ExpansionProblem {
 	double lambda, label_cost;
 	// gco neighbour lists: setNeighbors(i, j) for every directed entry adds j to i's list AND i to j's list, each
 	// with addFront (GCoptimization.cpp:1683-1708); finalizeNeighbors walks each list from its front.
-	std::vector<int32_t> goff, gidx;
+	const int32_t *goff = nullptr, *gidx = nullptr;
 };
 
 // GCoptimization::compute_energy (GCoptimization.cpp:950-984) in the reference's summation order
@@ -1036,9 +1036,89 @@ __global__ void k_exp_wire_aux(int64_t N, int L1, int64_t E, const int32_t *__re
 	if (s <= L1) arc_off[N + s] = (int32_t)(E + N + label_off[s]); // label_off[L1] = N: arc_off[N + L1] = E + 2N
 }
 
+// The part of the expansion graph that depends on the neighbourhood graph only -- gco's adjacency lists and the
+// site-to-site arcs with their mirrors -- is built once per graph and kept in the context (host copy for the energy
+// bookkeeping, device copy for the assembly kernels); a fit calls PEARL::labeling a dozen times on the same graph.
+struct ExpSkeleton {
+	uint64_t key = 0;
+	int64_t N = 0, E = 0;
+	std::vector<int32_t> goff, gidx; // host: gco neighbour lists (also read by compute_energy / EnergyCache)
+	DevBuf buf;                      // arc_off[N+1] head[E+N] rev[E+N] goff[N+1] gidx[E]
+	int32_t *arc_off = nullptr, *head = nullptr, *rev = nullptr, *d_goff = nullptr, *d_gidx = nullptr;
+};
+
+void exp_skeleton_free(void *p) {
+	if (!p) return;
+	ExpSkeleton *sk = static_cast<ExpSkeleton *>(p);
+	sk->buf.release();
+	delete sk;
+}
+
+static int exp_skeleton(pxb_ctx *ctx, int64_t N, const int32_t *off, const int32_t *idx, ExpSkeleton *&out) {
+	if (!ctx->exp_skeleton) ctx->exp_skeleton = new ExpSkeleton();
+	ExpSkeleton &sk = *static_cast<ExpSkeleton *>(ctx->exp_skeleton);
+	out = &sk;
+	uint64_t key = fnv1a(off, sizeof(int32_t) * (size_t)(N + 1));
+	key = fnv1a(idx, sizeof(int32_t) * (size_t)off[N], key) ^ ((uint64_t)ctx->device << 56) ^ (uint64_t)N;
+	if (sk.key == key && sk.N == N && sk.buf.ptr) return PXB_OK;
+	std::vector<int32_t> grev; // mirrored entry of every neighbour-list entry
+	// gco adjacency: per site a list built with addFront, so the last inserted neighbour comes first
+	sk.goff.assign((size_t)N + 1, 0);
+	for (int64_t i = 0; i < N; ++i)
+		for (int32_t e = off[i]; e < off[i + 1]; ++e) {
+			const int32_t j = idx[e];
+			if (j == i) continue; // PEARL.h:535
+			sk.goff[i + 1]++;
+			sk.goff[j + 1]++;
+		}
+	for (int64_t i = 0; i < N; ++i) sk.goff[i + 1] += sk.goff[i];
+	const int64_t E = sk.goff[N];
+	sk.gidx.assign((size_t)std::max<int64_t>(E, 1), 0);
+	grev.resize((size_t)std::max<int64_t>(E, 1));
+	std::vector<int32_t> next(sk.goff.begin() + 1, sk.goff.end()); // fill every list from its back: reversed push order
+	for (int64_t i = 0; i < N; ++i)
+		for (int32_t e = off[i]; e < off[i + 1]; ++e) {
+			const int32_t j = idx[e];
+			if (j == i) continue;
+			const int32_t pi = --next[i], pj = --next[j];
+			sk.gidx[pi] = j;
+			sk.gidx[pj] = (int32_t)i;
+			grev[pi] = pj;
+			grev[pj] = pi;
+		}
+	// arcs of site s: its neighbour list shifted by s (one slot per earlier site for that site's auxiliary arc)
+	const size_t ms = (size_t)(E + N);
+	std::vector<int32_t> arc_off((size_t)N + 1, 0), head(ms, 0), rev(ms, 0);
+	for (int64_t s2 = 0; s2 <= N; ++s2) arc_off[s2] = (int32_t)(sk.goff[s2] + s2);
+	for (int64_t s2 = 0; s2 < N; ++s2)
+		for (int32_t e = sk.goff[s2]; e < sk.goff[s2 + 1]; ++e) {
+			const int32_t nb = sk.gidx[e];
+			head[(size_t)e + s2] = nb;
+			rev[(size_t)e + s2] = grev[e] + nb; // the mirrored entry lives in nb's arc block, shifted by nb aux slots
+		}
+	const size_t ints = 2 * ((size_t)N + 1) + 2 * ms + (size_t)std::max<int64_t>(E, 1);
+	PXB_TRY(sk.buf.reserve(sizeof(int32_t) * ints));
+	sk.arc_off = sk.buf.as<int32_t>();
+	sk.head = sk.arc_off + (N + 1);
+	sk.rev = sk.head + ms;
+	sk.d_goff = sk.rev + ms;
+	sk.d_gidx = sk.d_goff + (N + 1);
+	cudaStream_t st = ctx->stream;
+	PXB_CUDA(cudaMemcpyAsync(sk.arc_off, arc_off.data(), sizeof(int32_t) * arc_off.size(), cudaMemcpyHostToDevice, st));
+	PXB_CUDA(cudaMemcpyAsync(sk.head, head.data(), sizeof(int32_t) * ms, cudaMemcpyHostToDevice, st));
+	PXB_CUDA(cudaMemcpyAsync(sk.rev, rev.data(), sizeof(int32_t) * ms, cudaMemcpyHostToDevice, st));
+	PXB_CUDA(cudaMemcpyAsync(sk.d_goff, sk.goff.data(), sizeof(int32_t) * (size_t)(N + 1), cudaMemcpyHostToDevice, st));
+	if (E > 0) PXB_CUDA(cudaMemcpyAsync(sk.d_gidx, sk.gidx.data(), sizeof(int32_t) * (size_t)E, cudaMemcpyHostToDevice, st));
+	PXB_CUDA(cudaStreamSynchronize(st)); // the host vectors go out of scope
+	sk.key = key;
+	sk.N = N;
+	sk.E = E;
+	return PXB_OK;
+}
+
 int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t L1, double lambda, double label_cost,
-                           const int32_t *csr_off_dev, const int32_t *csr_idx_dev, int64_t n_dir_edges,
-                           const int32_t *init_labels_dev, int32_t *labels_out_dev, double *energy_out_host) {
+                           const int32_t *csr_off_host, const int32_t *csr_idx_host, const int32_t *init_labels_dev,
+                           int32_t *labels_out_dev, double *energy_out_host) {
 	// The data costs and the labelling are mirrored on the host: the labelling energies that decide whether a move is
 	// kept are evaluated there in the reference's sequential summation order (compute_energy).
 	const auto t_call = std::chrono::steady_clock::now();
@@ -1047,14 +1127,14 @@ int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t
 		return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 	};
 	std::vector<double> D((size_t)N * L1);
-	std::vector<int32_t> off((size_t)N + 1), idx((size_t)std::max<int64_t>(n_dir_edges, 1)), lab((size_t)N, 0);
+	std::vector<int32_t> lab((size_t)N, 0);
 	cudaStream_t st = ctx->stream;
 	PXB_CUDA(cudaMemcpyAsync(D.data(), D_dev, sizeof(double) * D.size(), cudaMemcpyDeviceToHost, st));
-	PXB_CUDA(cudaMemcpyAsync(off.data(), csr_off_dev, sizeof(int32_t) * off.size(), cudaMemcpyDeviceToHost, st));
-	if (n_dir_edges > 0)
-		PXB_CUDA(cudaMemcpyAsync(idx.data(), csr_idx_dev, sizeof(int32_t) * (size_t)n_dir_edges, cudaMemcpyDeviceToHost, st));
 	if (init_labels_dev)
 		PXB_CUDA(cudaMemcpyAsync(lab.data(), init_labels_dev, sizeof(int32_t) * (size_t)N, cudaMemcpyDeviceToHost, st));
+	ExpSkeleton *skp = nullptr;
+	PXB_TRY(exp_skeleton(ctx, N, csr_off_host, csr_idx_host, skp)); // overlaps the downloads on a cache hit
+	ExpSkeleton &sk = *skp;
 	PXB_CUDA(cudaStreamSynchronize(st));
 
 	ExpansionProblem P;
@@ -1063,61 +1143,25 @@ int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t
 	P.L1 = L1;
 	P.lambda = lambda;
 	P.label_cost = label_cost;
-	std::vector<int32_t> grev; // mirrored entry of every neighbour-list entry
-	{ // gco adjacency: per site a list built with addFront, so the last inserted neighbour comes first
-		P.goff.assign((size_t)N + 1, 0);
-		for (int64_t i = 0; i < N; ++i)
-			for (int32_t e = off[i]; e < off[i + 1]; ++e) {
-				const int32_t j = idx[e];
-				if (j == i) continue; // PEARL.h:535
-				P.goff[i + 1]++;
-				P.goff[j + 1]++;
-			}
-		for (int64_t i = 0; i < N; ++i) P.goff[i + 1] += P.goff[i];
-		P.gidx.resize((size_t)P.goff[N]);
-		grev.resize((size_t)P.goff[N]);
-		std::vector<int32_t> next(P.goff.begin() + 1, P.goff.end()); // fill every list from its back: reversed push order
-		for (int64_t i = 0; i < N; ++i)
-			for (int32_t e = off[i]; e < off[i + 1]; ++e) {
-				const int32_t j = idx[e];
-				if (j == i) continue;
-				const int32_t pi = --next[i], pj = --next[j];
-				P.gidx[pi] = j;
-				P.gidx[pj] = (int32_t)i;
-				grev[pi] = pj;
-				grev[pj] = pi;
-			}
-	}
-	const int64_t E = P.goff[N];
+	P.goff = sk.goff.data();
+	P.gidx = sk.gidx.data();
+	const int64_t E = sk.E;
 	const int n = (int)(N + L1);
 	const int64_t m = E + 2 * N;
 
-	// ---- device arena: static skeleton + per-move state ----
-	const size_t n_int = (size_t)(n + 1) + 2 * (size_t)m + (size_t)(N + 1) + (size_t)E + 2 * (size_t)N + 2 * (size_t)(L1 + 1) +
-	                     2 * (size_t)n + 32;
+	// ---- device arena: per-call copy of the arcs (the auxiliary part is rewired with the labelling) + per-move state ----
+	const size_t n_int = (size_t)(n + 1) + 2 * (size_t)m + 2 * (size_t)N + 2 * (size_t)(L1 + 1) + 2 * (size_t)n + 32;
 	const size_t bytes = sizeof(double) * ((size_t)m + 2 * (size_t)n) + sizeof(int32_t) * n_int + 256;
 	PXB_TRY(ctx->partials.reserve(bytes));
 	double *d_cap = ctx->partials.as<double>(), *d_excess = d_cap + m, *d_sink = d_excess + n;
 	int32_t *d_arc_off = reinterpret_cast<int32_t *>(d_sink + n), *d_head = d_arc_off + (n + 1), *d_rev = d_head + m;
-	int32_t *d_goff = d_rev + m, *d_gidx = d_goff + (N + 1), *d_lab = d_gidx + E, *d_rank = d_lab + N;
+	int32_t *d_lab = d_rev + m, *d_rank = d_lab + N;
 	int32_t *d_label_off = d_rank + N, *d_label_count = d_label_off + (L1 + 1);
 	int32_t *d_h0 = d_label_count + (L1 + 1), *d_h1 = d_h0 + n, *d_flags = d_h1 + n;
-	{
-		std::vector<int32_t> arc_off((size_t)n + 1, 0), head((size_t)m, 0), rev((size_t)m, 0);
-		for (int64_t s2 = 0; s2 <= N; ++s2) arc_off[s2] = (int32_t)(P.goff[s2] + s2);
-		for (int64_t s2 = 0; s2 < N; ++s2)
-			for (int32_t e = P.goff[s2]; e < P.goff[s2 + 1]; ++e) {
-				const int32_t nb = P.gidx[e];
-				head[(size_t)e + s2] = nb;
-				rev[(size_t)e + s2] = grev[e] + nb; // the mirrored entry lives in nb's arc block, shifted by nb aux slots
-			}
-		PXB_CUDA(cudaMemcpyAsync(d_arc_off, arc_off.data(), sizeof(int32_t) * arc_off.size(), cudaMemcpyHostToDevice, st));
-		PXB_CUDA(cudaMemcpyAsync(d_head, head.data(), sizeof(int32_t) * head.size(), cudaMemcpyHostToDevice, st));
-		PXB_CUDA(cudaMemcpyAsync(d_rev, rev.data(), sizeof(int32_t) * rev.size(), cudaMemcpyHostToDevice, st));
-		PXB_CUDA(cudaMemcpyAsync(d_goff, P.goff.data(), sizeof(int32_t) * (size_t)(N + 1), cudaMemcpyHostToDevice, st));
-		if (E > 0) PXB_CUDA(cudaMemcpyAsync(d_gidx, P.gidx.data(), sizeof(int32_t) * (size_t)E, cudaMemcpyHostToDevice, st));
-		PXB_CUDA(cudaStreamSynchronize(st)); // the host vectors go out of scope
-	}
+	const int32_t *d_goff = sk.d_goff, *d_gidx = sk.d_gidx;
+	PXB_CUDA(cudaMemcpyAsync(d_arc_off, sk.arc_off, sizeof(int32_t) * (size_t)(N + 1), cudaMemcpyDeviceToDevice, st));
+	PXB_CUDA(cudaMemcpyAsync(d_head, sk.head, sizeof(int32_t) * (size_t)(E + N), cudaMemcpyDeviceToDevice, st));
+	PXB_CUDA(cudaMemcpyAsync(d_rev, sk.rev, sizeof(int32_t) * (size_t)(E + N), cudaMemcpyDeviceToDevice, st));
 	std::vector<int32_t> rank((size_t)N), label_off((size_t)L1 + 1), label_count((size_t)L1 + 1);
 	auto push_labelling = [&]() -> int { // labels, ranks and the auxiliary wiring follow the host labelling
 		std::fill(label_count.begin(), label_count.end(), 0);

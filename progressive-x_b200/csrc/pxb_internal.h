@@ -90,6 +90,7 @@ struct pxb_ctx {
 	void *pinned = nullptr;
 	size_t pinned_cap = 0;
 	void *lo_skeleton = nullptr; // pxb_expansion.cu: cached arc skeleton of the last neighbourhood graph
+	void *exp_skeleton = nullptr; // pxb_expansion.cu: cached gco adjacency + static arcs of the alpha-expansion graph
 	// Pinned staging arena of the host-pointer entry points: small H2D payloads are copied here first and small D2H
 	// results land here and are handed to the caller's (pageable) buffers after the stream synchronises. Pageable
 	// cudaMemcpyAsync calls are synchronous, take the driver's big lock and serialise concurrent contexts; pinned ones
@@ -107,6 +108,7 @@ struct pxb_ctx {
 
 namespace pxb {
 void lo_skeleton_free(void *p);
+void exp_skeleton_free(void *p);
 // staged transfers of the host-pointer entry points (pxb_api.cu): small payloads go through the context's pinned arena;
 // api_sync synchronises the stream and delivers the staged D2H results
 int api_h2d(pxb_ctx *ctx, void *dst, const void *src, size_t bytes);
@@ -135,7 +137,7 @@ int launch_solve_minimal(pxb_ctx *ctx, const int64_t *samples, int64_t K, double
                          uint8_t *sample_valid, uint8_t *model_valid);
 int launch_greedy_label(pxb_ctx *ctx, const double *D, int64_t N, int32_t L1, double label_cost,
                         const int32_t *init_labels, int32_t *labels_out, double *energy_out_dev);
-int launch_alpha_expansion(pxb_ctx *ctx, const double *D, int64_t N, int32_t L1, double lambda, double label_cost,
-                           const int32_t *csr_off, const int32_t *csr_idx, int64_t n_dir_edges,
-                           const int32_t *init_labels, int32_t *labels_out, double *energy_out_host);
+int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t L1, double lambda, double label_cost,
+                           const int32_t *csr_off_host, const int32_t *csr_idx_host, const int32_t *init_labels_dev,
+                           int32_t *labels_out_dev, double *energy_out_host);
 } // namespace pxb
