@@ -103,12 +103,25 @@ __device__ void mf_global_relabel(const FlowGraphDev &G, int32_t *h, cg::grid_gr
 		bool mine = false;
 		for (int u = tid; u < G.wide_begin; u += nthreads) {
 			if (hv[u] != level) continue;
-			for (int a = G.arc_off[u]; a < G.arc_off[u + 1]; ++a) {
-				const int v = G.arc_head[a];
-				if (G.cap[G.arc_rev[a]] > 0.0 && hv[v] == n) {
-					hv[v] = level + 1; // benign race: every writer stores the same value
-					mine = true;
-				}
+			const int a0 = G.arc_off[u], a1 = G.arc_off[u + 1];
+			for (int base = a0; base < a1; base += 8) { // chunks of 8 arcs, predicated loads (see mf_process)
+				int v[8], r[8];
+				bool want[8];
+				double c[8];
+#pragma unroll
+				for (int j = 0; j < 8; ++j) v[j] = ld_nc_s32_if(G.arc_head + base + j, base + j < a1, -1);
+#pragma unroll
+				for (int j = 0; j < 8; ++j) want[j] = ld_volatile_s32_if(h + (v[j] >= 0 ? v[j] : 0), v[j] >= 0, 0) == n;
+#pragma unroll
+				for (int j = 0; j < 8; ++j) r[j] = ld_nc_s32_if(G.arc_rev + base + j, want[j], 0);
+#pragma unroll
+				for (int j = 0; j < 8; ++j) c[j] = ld_volatile_f64_if(G.cap + r[j], want[j]);
+#pragma unroll
+				for (int j = 0; j < 8; ++j)
+					if (want[j] && c[j] > 0.0) {
+						hv[v[j]] = level + 1; // benign race: every writer stores the same value
+						mine = true;
+					}
 			}
 		}
 		for (int w = blockIdx.x; w < G.wide_count; w += gridDim.x) { // a wide node's arcs are expanded by its whole block
