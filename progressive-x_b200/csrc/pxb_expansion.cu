@@ -515,19 +515,23 @@ struct MfLaunch {
 	size_t smem = 0;
 };
 static int mf_launch_config(pxb_ctx *ctx, FlowGraphDev &G, int min_grid, MfLaunch &out) {
-	static const bool grid_bfs_only = getenv("PXB_MF_GRID_BFS") != nullptr; // A/B switch: the grid-wide relabel
-	static const int async_cycles = getenv("PXB_MF_ASYNC") ? atoi(getenv("PXB_MF_ASYNC")) : kAsyncCycles;
-	static const int idle_checks = getenv("PXB_MF_IDLE") ? atoi(getenv("PXB_MF_IDLE")) : 4;
+	// tuning / A-B switches, read per call (tests flip them): PXB_MF_GRID_BFS=1 forces the grid-wide relabel,
+	// PXB_MF_SMEM_KB caps the shared memory the single-block relabel may use (selects its smaller layouts)
+	const bool grid_bfs_only = getenv("PXB_MF_GRID_BFS") != nullptr;
+	const int async_cycles = getenv("PXB_MF_ASYNC") ? atoi(getenv("PXB_MF_ASYNC")) : kAsyncCycles;
+	const int idle_checks = getenv("PXB_MF_IDLE") ? atoi(getenv("PXB_MF_IDLE")) : 4;
 	G.async_cycles = std::max(8, async_cycles);
 	G.idle_checks = std::max(1, idle_checks);
 	static bool attribute_set[64] = {}; // per device (function attributes belong to the device's context)
 	constexpr size_t kMaxSmem = 200 * 1024;
+	size_t smem_cap = kMaxSmem;
+	if (const char *e = getenv("PXB_MF_SMEM_KB")) smem_cap = std::min(kMaxSmem, (size_t)std::max(0, atoi(e)) * 1024);
 	if (ctx->device < 0 || ctx->device >= 64 || !attribute_set[ctx->device]) {
 		PXB_CUDA(cudaFuncSetAttribute(k_maxflow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
 		if (ctx->device >= 0 && ctx->device < 64) attribute_set[ctx->device] = true;
 	}
 	const size_t need = sizeof(int32_t) * 2 * (size_t)G.n, need_offs = sizeof(int32_t) * (3 * (size_t)G.n + 1);
-	G.block_bfs = (grid_bfs_only || G.wide_count > 32) ? 0 : (need_offs <= kMaxSmem ? 2 : (need <= kMaxSmem ? 1 : 0));
+	G.block_bfs = (grid_bfs_only || G.wide_count > 32) ? 0 : (need_offs <= smem_cap ? 2 : (need <= smem_cap ? 1 : 0));
 	out.smem = G.block_bfs == 2 ? need_offs : (G.block_bfs == 1 ? need : 0);
 	int blocks_per_sm = 0;
 	PXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_maxflow, kMfThreads, out.smem));

@@ -115,3 +115,28 @@ def test_nonminimal_homography_fit(ctx, oracle):
     # the fit explains its own inliers
     r2, _ = oracle.residual_matrix(H, pts[sets[0]], Hg[0], 9.0)
     assert np.median(r2) < 1.0
+
+
+@pytest.mark.parametrize("layout", ["offsets_in_smem", "heights_and_queue_only", "grid_wide"])
+def test_global_relabel_layouts_give_the_same_cut(ctx, oracle, layout, monkeypatch):
+    """k_maxflow's global relabel has three forms: block 0 alone with heights + queue + CSR offsets in
+    shared memory, the same without the offsets (larger graphs), and the grid-wide level-synchronous BFS (graphs that do
+    not fit). All three must reproduce the reference's cut and labels."""
+    _need_ref(oracle)
+    N = 4000  # 12 B/node -> 47 KB, 8 B/node -> 31 KB
+    if layout == "heights_and_queue_only":
+        monkeypatch.setenv("PXB_MF_SMEM_KB", "40")
+    elif layout == "grid_wide":
+        monkeypatch.setenv("PXB_MF_GRID_BFS", "1")
+    pts, gt, Hs = syn.multi_homography_scene(N, n_planes=3, outlier_ratio=0.4, seed=77)
+    lam = 0.1
+    D = oracle.pearl_datacost(H, pts, Hs.reshape(-1, 9), 2.0, lam)
+    off, idx = syn.knn_graph(pts, 80.0, 5)
+    lab_o, e_o, _ = oracle.gco_pearl_label(D, lam, 20.0, off, idx)
+    lab, e = ctx.pearl_label(D, lam, 20.0, off, idx)
+    assert e == e_o
+    _assert_equal_up_to_exact_ties(oracle, D, lam, 20.0, off, idx, lab, lab_o)
+    ctx.upload_points(H, pts)
+    model = Hs[0].reshape(-1)
+    d, e0, e1 = oracle.lo_unary_terms(H, pts, model, 2.0, 0.6)
+    assert np.array_equal(ctx.lo_labeling(model, 2.0, 0.6, off, idx), oracle.gco_lo_labeling(e0, e1, d, 0.6, off, idx)[0])
