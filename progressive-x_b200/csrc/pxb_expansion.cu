@@ -56,7 +56,10 @@ struct FlowGraphDev {
 	int block_bfs;  // 1/2: the launch carries 2n (3n+1) ints of dynamic shared memory and block 0 runs the global relabel alone
 };
 
-constexpr int kMfThreads = 256;
+#ifndef PXB_MF_THREADS
+#define PXB_MF_THREADS 1024
+#endif
+constexpr int kMfThreads = PXB_MF_THREADS;
 constexpr int kWideDegree = 64;
 
 // predicated loads: issued back to back, no branch; the destination keeps `otherwise` when the predicate is false
@@ -152,11 +155,24 @@ __device__ void mf_global_relabel(const FlowGraphDev &G, int32_t *h, cg::grid_gr
 // need 20-30 relabels of ~35 levels each; here a level is a few block barriers around a frontier-sized loop (queue
 // form: every node is expanded exactly once), and the other blocks wait at one grid barrier per relabel.
 // Returns (block-uniformly) whether any node with excess can still reach the sink.
-constexpr int kBfsChunk = 16;
+constexpr int kBfsBatch = 8;
+// Appends the items of the lanes with `take` set to the shared queue with ONE atomic per warp (a same-address shared
+// atomic per item serialises: at ~200 discoveries per level that alone was half of a level's time).
+__device__ __forceinline__ void bfs_enqueue(bool take, int item, int32_t *queue, int *tail) {
+	const unsigned mask = __ballot_sync(0xffffffffu, take);
+	if (mask == 0) return;
+	const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+	int base = 0;
+	if (lane == leader) base = atomicAdd(tail, __popc(mask));
+	base = __shfl_sync(0xffffffffu, base, leader);
+	if (take) queue[base + __popc(mask & ((1u << lane) - 1u))] = item;
+}
+
 __device__ bool mf_global_relabel_block(const FlowGraphDev &G, int32_t *h, bool first) {
 	extern __shared__ int32_t mf_smem[];
-	__shared__ int s_tail, s_nwide, s_wide[32];
+	__shared__ int s_tail, s_nwide, s_wide[32], s_end[2];
 	const int n = G.n;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 	int32_t *hs = mf_smem, *queue = mf_smem + n;
 	// block_bfs == 2: the CSR offsets fit as well (filled once per launch) and save a round trip per expansion
 	const int32_t *offs = G.arc_off;
@@ -172,80 +188,123 @@ __device__ bool mf_global_relabel_block(const FlowGraphDev &G, int32_t *h, bool 
 		s_nwide = 0;
 	}
 	__syncthreads();
-	for (int base = threadIdx.x; base < n; base += 4 * blockDim.x) { // four independent loads in flight per thread
+	// level 1: the nodes with residual capacity to the sink (warp-uniform trip count: bfs_enqueue is a warp collective)
+	for (int base = warp * 32; base < n; base += 4 * blockDim.x) {
 		double sc[4];
 #pragma unroll
 		for (int j = 0; j < 4; ++j) {
-			const int u = base + j * blockDim.x;
+			const int u = base + j * (int)blockDim.x + lane;
 			sc[j] = u < n ? __ldcg(&G.sink_cap[u]) : 0.0;
 		}
 #pragma unroll
 		for (int j = 0; j < 4; ++j) {
-			const int u = base + j * blockDim.x;
-			if (u >= n) break;
-			const bool at_sink = sc[j] > 0.0;
-			hs[u] = at_sink ? 1 : n;
-			if (at_sink) queue[atomicAdd(&s_tail, 1)] = u;
+			const int u = base + j * (int)blockDim.x + lane;
+			const bool at_sink = u < n && sc[j] > 0.0;
+			if (u < n) hs[u] = at_sink ? 1 : n;
+			bfs_enqueue(at_sink, u, queue, &s_tail);
 		}
 	}
 	__syncthreads();
+	if (threadIdx.x == 0) s_end[1] = s_tail;
 	int begin = 0, level = 1;
 	for (;;) {
-		const int end = s_tail;
+		__syncthreads(); // the previous level's appends and its end marker are visible
+		const int end = s_end[level & 1];
 		if (begin == end) break; // block-uniform
-		__syncthreads();         // everybody has read s_tail before the level appends to the queue
-		for (int i = begin + threadIdx.x; i < end; i += blockDim.x) {
-			const int u = queue[i];
-			if (u >= G.wide_begin) { // expanded by the whole block below
-				s_wide[atomicAdd(&s_nwide, 1)] = u;
-				continue;
+		// Warp-cooperative expansion: a warp takes kBfsBatch frontier nodes at a time, the lanes run over a node's
+		// arcs, so a node's heads and reverse arcs are one coalesced request each and only the capacities of the
+		// still-unlabelled heads (typically 1-3 per node) are scattered. All loads are predicated instructions
+		// (inline PTX): the batch's loads are in flight together, two dependent round trips per batch.
+		for (int i0 = begin + warp * kBfsBatch; i0 < end; i0 += nwarps * kBfsBatch) {
+			int a0[kBfsBatch], deg[kBfsBatch], v[kBfsBatch], r[kBfsBatch];
+			double c[kBfsBatch];
+			bool want[kBfsBatch];
+#pragma unroll
+			for (int b = 0; b < kBfsBatch; ++b) {
+				int u = i0 + b < end ? queue[i0 + b] : -1;
+				if (u >= G.wide_begin) { // expanded by the whole block below
+					if (lane == 0) s_wide[atomicAdd(&s_nwide, 1)] = u;
+					u = -1;
+				}
+				a0[b] = u >= 0 ? offs[u] : 0;
+				deg[b] = u >= 0 ? offs[u + 1] - a0[b] : 0;
 			}
-			// Arcs in chunks of 16. One SM's load path handles about one divergent sector per cycle, so the loop is
-			// written for few loads AND no waiting: heads first (predicated on the range), then -- only for heads that
-			// are still unlabelled, typically 1-3 of 16 -- the reverse arc and its capacity. The loads are predicated
-			// instructions (inline PTX): under a branch each one would be waited for before the next is issued.
-			const int a0 = offs[u], a1 = offs[u + 1];
-			for (int base = a0; base < a1; base += kBfsChunk) {
-				int v[kBfsChunk], r[kBfsChunk];
-				double c[kBfsChunk];
-				bool want[kBfsChunk];
 #pragma unroll
-				for (int j = 0; j < kBfsChunk; ++j) v[j] = ld_nc_s32_if(G.arc_head + base + j, base + j < a1, -1);
-#pragma unroll
-				for (int j = 0; j < kBfsChunk; ++j) want[j] = v[j] >= 0 && hs[v[j]] == n;
-#pragma unroll
-				for (int j = 0; j < kBfsChunk; ++j) r[j] = ld_nc_s32_if(G.arc_rev + base + j, want[j], 0);
-#pragma unroll
-				for (int j = 0; j < kBfsChunk; ++j) c[j] = ld_cg_f64_if(capp + r[j], want[j]);
-#pragma unroll
-				for (int j = 0; j < kBfsChunk; ++j)
-					if (want[j] && c[j] > 0.0 && atomicCAS(&hs[v[j]], n, level + 1) == n) queue[atomicAdd(&s_tail, 1)] = v[j];
+			for (int b = 0; b < kBfsBatch; ++b) {
+				v[b] = ld_nc_s32_if(G.arc_head + a0[b] + lane, lane < deg[b], -1);
+				r[b] = ld_nc_s32_if(G.arc_rev + a0[b] + lane, lane < deg[b], 0);
 			}
+#pragma unroll
+			for (int b = 0; b < kBfsBatch; ++b) want[b] = v[b] >= 0 && hs[v[b]] == n;
+#pragma unroll
+			for (int b = 0; b < kBfsBatch; ++b) c[b] = ld_cg_f64_if(capp + r[b], want[b]);
+			// claim the heads (independent shared-memory CAS operations), then append all winners of the batch with one
+			// atomic on the queue tail: a per-node append chain (CAS -> ballot -> atomic -> shuffle) cost 1.4 us per level
+			bool won[kBfsBatch];
+#pragma unroll
+			for (int b = 0; b < kBfsBatch; ++b) won[b] = want[b] && c[b] > 0.0 && atomicCAS(&hs[v[b]], n, level + 1) == n;
+			unsigned wmask[kBfsBatch];
+			int before[kBfsBatch], total = 0;
+#pragma unroll
+			for (int b = 0; b < kBfsBatch; ++b) {
+				wmask[b] = __ballot_sync(0xffffffffu, won[b]);
+				before[b] = total;
+				total += __popc(wmask[b]);
+			}
+			if (total > 0) { // warp-uniform
+				int base = 0;
+				if (lane == 0) base = atomicAdd(&s_tail, total);
+				base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+				for (int b = 0; b < kBfsBatch; ++b)
+					if (won[b]) queue[base + before[b] + __popc(wmask[b] & ((1u << lane) - 1u))] = v[b];
+			}
+			// the rare node with more than 32 arcs (warp-uniform trip count)
+#pragma unroll
+			for (int b = 0; b < kBfsBatch; ++b)
+				for (int k0 = 32; k0 < deg[b]; k0 += 32) {
+					const int k = k0 + lane;
+					const int vv = ld_nc_s32_if(G.arc_head + a0[b] + k, k < deg[b], -1);
+					const int rr = ld_nc_s32_if(G.arc_rev + a0[b] + k, k < deg[b], 0);
+					const bool w2 = vv >= 0 && hs[vv] == n;
+					const double cc = ld_cg_f64_if(capp + rr, w2);
+					const bool won = w2 && cc > 0.0 && atomicCAS(&hs[vv], n, level + 1) == n;
+					bfs_enqueue(won, vv, queue, &s_tail);
+				}
 		}
 		__syncthreads();
-		const int nwide = s_nwide;
-		for (int w = 0; w < nwide; ++w) {
-			const int u = s_wide[w];
-			const int a1 = G.arc_off[u + 1];
-			for (int base = G.arc_off[u] + threadIdx.x; base < a1; base += 4 * blockDim.x) {
-				int v[4], r[4];
-				double c[4];
-				bool want[4];
+		const int nwide = s_nwide; // block-uniform
+		if (nwide > 0) {
+			for (int w = 0; w < nwide; ++w) {
+				const int u = s_wide[w];
+				const int a1 = G.arc_off[u + 1];
+				for (int base = G.arc_off[u] + warp * 32; base < a1; base += 4 * blockDim.x) { // warp-uniform
+					int v[4], r[4];
+					double c[4];
+					bool want[4];
 #pragma unroll
-				for (int j = 0; j < 4; ++j) v[j] = ld_nc_s32_if(G.arc_head + base + j * blockDim.x, base + j * (int)blockDim.x < a1, -1);
+					for (int j = 0; j < 4; ++j) {
+						const int a = base + j * (int)blockDim.x + lane;
+						v[j] = ld_nc_s32_if(G.arc_head + a, a < a1, -1);
+						r[j] = ld_nc_s32_if(G.arc_rev + a, a < a1, 0);
+					}
 #pragma unroll
-				for (int j = 0; j < 4; ++j) want[j] = v[j] >= 0 && hs[v[j]] == n;
+					for (int j = 0; j < 4; ++j) want[j] = v[j] >= 0 && hs[v[j]] == n;
 #pragma unroll
-				for (int j = 0; j < 4; ++j) r[j] = ld_nc_s32_if(G.arc_rev + base + j * blockDim.x, want[j], 0);
+					for (int j = 0; j < 4; ++j) c[j] = ld_cg_f64_if(capp + r[j], want[j]);
 #pragma unroll
-				for (int j = 0; j < 4; ++j) c[j] = ld_cg_f64_if(capp + r[j], want[j]);
-#pragma unroll
-				for (int j = 0; j < 4; ++j)
-					if (want[j] && c[j] > 0.0 && atomicCAS(&hs[v[j]], n, level + 1) == n) queue[atomicAdd(&s_tail, 1)] = v[j];
+					for (int j = 0; j < 4; ++j) {
+						const bool won = want[j] && c[j] > 0.0 && atomicCAS(&hs[v[j]], n, level + 1) == n;
+						bfs_enqueue(won, v[j], queue, &s_tail);
+					}
+				}
 			}
+			__syncthreads();
+			if (threadIdx.x == 0) s_nwide = 0;
 		}
-		__syncthreads();
-		if (threadIdx.x == 0) s_nwide = 0;
+		// the end marker of the next level alternates between two slots: the other slot is still being read by
+		// stragglers of this level's loop test
+		if (threadIdx.x == 0) s_end[(level + 1) & 1] = s_tail;
 		begin = end;
 		++level;
 	}
