@@ -218,7 +218,9 @@ __global__ void __launch_bounds__(kThreads, MINB)
 
 template <int TYPE, typename OUT, bool HI_ONLY, int HYPS>
 static int launch_rm_v(pxb_ctx *ctx, const double *models, int64_t K, double T2, OUT *r2, uint32_t *mask) {
-	constexpr int P = 4, MINB = 2; // tuned on B200: (4,3), (2,3), (2,4) are within 3% but never faster
+	// points per lane, min blocks per SM. Tuned on B200 (1.023 ms): (5,2) 1.039, (6,2) 1.052 (spills), (8,1) 1.121,
+	// (4,3), (2,3), (2,4) within 3 % but never faster
+	constexpr int P = 4, MINB = 2;
 	const Points &p = ctx->pts;
 	const int64_t words = (p.N + 31) / 32;
 	const int64_t ppb = (int64_t)(kThreads / 32) * 32 * P;
