@@ -134,6 +134,7 @@ def refb() -> C.CDLL:
         B.pxr_f_orientation_valid.argtypes = [vp, vp, i64, vp, C.c_int]
         B.pxr_vp2_solve.argtypes = [vp, i64, vp, vp]
         B.pxr_line2_solve.argtypes = [vp, i64, vp, vp]
+        B.pxr_fpp_solve.argtypes = [vp, i64, vp, vp, vp]
         _refb = B
     return _refb
 
@@ -189,6 +190,15 @@ def ref_minimal_vp_or_line(t, pts, sample):
     out = np.zeros(3)
     fn = refb().pxr_vp2_solve if t == MODEL_VP else refb().pxr_line2_solve
     ok = fn(_p(pts), pts.shape[0], _p(s), _p(out))
+    return out, int(ok)
+
+
+def ref_plane_parallax(pts, sample, H):
+    """The reference's own FundamentalMatrixPlaneParallaxSolver::estimateModel body (matrix products through the shim)."""
+    pts, H = _f(pts), _f(H).reshape(9)
+    s = np.ascontiguousarray(sample, dtype=np.int64)
+    out = np.zeros(9)
+    ok = refb().pxr_fpp_solve(_p(pts), pts.shape[0], _p(s), _p(H), _p(out))
     return out, int(ok)
 
 
@@ -303,8 +313,8 @@ def _matvec3(M, v):
 
 def solve_plane_parallax(pts, samples, H):
     """FundamentalMatrixPlaneParallaxSolver::estimateModel
-    (gcr/estimators/solver_fundamental_matrix_plane_and_parallax.h:107-162), restated: not pinned against the reference's
-    body (its arithmetic is Eigen expression templates), anchored on the algebraic property F^T e = 0, x2^T F x1 = 0."""
+    (gcr/estimators/solver_fundamental_matrix_plane_and_parallax.h:105-163), restated; pinned bit for bit against the
+    reference's own body in tests/test_oracle_pinned.py (its two Eigen 3x3 products go through the shim's operator*)."""
     pts = _f(pts)
     H = _f(H).reshape(3, 3)
     s = np.ascontiguousarray(samples, dtype=np.int64).reshape(-1, 2)

@@ -2,7 +2,7 @@
 // compiles verbatim (TEST INFRASTRUCTURE ONLY; written from scratch, not Eigen code). Only element access, comma
 // initialisation, Zero(), hasNaN(), resize(), row().cross() and determinant() exist. All arithmetic of the pinned
 // functions is spelled out in scalar code in the reference sources themselves; the only arithmetic supplied HERE is
-// determinant() (partial-pivot LU, as Eigen does for dynamic matrices) and cross().
+// determinant() (partial-pivot LU, as Eigen does for dynamic matrices), cross() and the fixed-size product operator*.
 #pragma once
 #include <cmath>
 #include <cstddef>
@@ -107,6 +107,19 @@ template <class T, int R, int C> class Matrix {
 		return T(sign) * d;
 	}
 };
+
+// Coefficient-wise product as Eigen evaluates a fixed-size 3x3 lazy product: every entry is the inner product of a row
+// and a column accumulated left to right, (a0 b0 + a1 b1) + a2 b2. Used only by the DEGENSAC plane-and-parallax solver.
+template <class T, int R, int C, int C2> Matrix<T, R, C2> operator*(const Matrix<T, R, C> &a, const Matrix<T, C, C2> &b) {
+	Matrix<T, R, C2> r(a.rows_, b.cols_);
+	for (int i = 0; i < a.rows_; ++i)
+		for (int j = 0; j < b.cols_; ++j) {
+			T acc = a(i, 0) * b.data_[(size_t)0 * b.cols_ + j];
+			for (int k = 1; k < a.cols_; ++k) acc = acc + a(i, k) * b.data_[(size_t)k * b.cols_ + j];
+			r.data_[(size_t)i * b.cols_ + j] = acc;
+		}
+	return r;
+}
 
 typedef Matrix<double, Dynamic, Dynamic> MatrixXd;
 typedef Matrix<double, Dynamic, 1> VectorXd;

@@ -53,6 +53,7 @@ struct FlowGraphDev {
 	int32_t *height[2];
 	int32_t *flags; // [0..2] BFS 'changed' (level mod 3), [3..5] 'active' (pulse mod 3), [6] pulses, [7] status
 	int async_cycles, idle_checks; // tuning knobs of the asynchronous phase (PXB_MF_ASYNC, PXB_MF_IDLE)
+	int debug;      // PXB_MF_STATS=3: block 0 prints the number of active nodes after every relabel
 	int block_bfs;  // 1/2: the launch carries 2n (3n+1) ints of dynamic shared memory and block 0 runs the global relabel alone
 };
 
@@ -325,8 +326,10 @@ __device__ bool mf_global_relabel_block(const FlowGraphDev &G, int32_t *h, bool 
 			active |= ex[j] > 0.0;
 		}
 	}
-	if (threadIdx.x == 0) {
-		G.flags[8] += level; // statistics: BFS levels
+	if (threadIdx.x == 0) G.flags[8] += level; // statistics: BFS levels
+	if (G.debug) {
+		const int cnt = __syncthreads_count(active);
+		if (threadIdx.x == 0) printf("[mf] relabel: levels=%d reached=%d threads_with_active=%d\n", level, s_tail, cnt);
 	}
 	return __syncthreads_or(active) != 0;
 }
@@ -579,6 +582,7 @@ static int mf_launch_config(pxb_ctx *ctx, FlowGraphDev &G, int min_grid, MfLaunc
 	const bool grid_bfs_only = getenv("PXB_MF_GRID_BFS") != nullptr;
 	const int async_cycles = getenv("PXB_MF_ASYNC") ? atoi(getenv("PXB_MF_ASYNC")) : kAsyncCycles;
 	const int idle_checks = getenv("PXB_MF_IDLE") ? atoi(getenv("PXB_MF_IDLE")) : 4;
+	G.debug = (getenv("PXB_MF_STATS") && getenv("PXB_MF_STATS")[0] == '3') ? 1 : 0;
 	G.async_cycles = std::max(8, async_cycles);
 	G.idle_checks = std::max(1, idle_checks);
 	static bool attribute_set[64] = {}; // per device (function attributes belong to the device's context)

@@ -147,3 +147,22 @@ def test_vp_and_line_minimal_solvers_bit_exact(refb, t):
         assert np.array_equal(np.isnan(ref), np.isnan(models[k, 0]))
         fin = ~np.isnan(ref)
         assert np.array_equal(bits(models[k, 0][fin]), bits(ref[fin]))
+
+
+def test_plane_parallax_solver_bit_exact(refb):
+    """DEGENSAC's minimal solver (solver_fundamental_matrix_plane_and_parallax.h:105-163): the numpy restatement the GPU
+    kernel is compared with equals the reference's own body, including the `no intersection` rejection."""
+    rows, lab, _ = syn.plane_dominated_pair(300, 300, 0.3, 17)
+    plane, off = np.flatnonzero(lab == 0), np.flatnonzero(lab == 1)
+    Hm, ok = refb.fit_h_nonminimal(rows, plane)
+    assert ok
+    rng = np.random.default_rng(4)
+    S = np.stack([rng.choice(off, 2, replace=False) for _ in range(400)]).astype(np.int64)
+    S[0] = [off[7], off[7]]  # coincident lines: epipole = 0, no model
+    models, n = refb.solve_plane_parallax(rows, S, Hm)
+    assert n[0] == 0 and n[1:].all()
+    for k in range(400):
+        ref, ok = refb.ref_plane_parallax(rows, S[k], Hm)
+        assert ok == n[k]
+        if ok:
+            assert np.array_equal(bits(models[k]), bits(ref))
