@@ -53,6 +53,8 @@ struct FlowGraphDev {
 	int32_t *height[2];
 	int32_t *flags; // [0..2] BFS 'changed' (level mod 3), [3..5] 'active' (pulse mod 3), [6] pulses, [7] status
 	int async_cycles, idle_checks; // tuning knobs of the asynchronous phase (PXB_MF_ASYNC, PXB_MF_IDLE)
+	int local_exit;                // PXB_MF_LOCAL_EXIT=1: blocks leave the phase on their own (A/B)
+	long long quiet_cycles;        // PXB_MF_QUIET_US: grid-wide silence that ends the phase
 	int debug;      // PXB_MF_STATS=3: block 0 prints the number of active nodes after every relabel
 	int block_bfs;  // 1/2: the launch carries 2n (3n+1) ints of dynamic shared memory and block 0 runs the global relabel alone
 };
@@ -528,7 +530,10 @@ __global__ void __launch_bounds__(kMfThreads) k_maxflow(FlowGraphDev G) {
 		if (G.block_bfs) {
 			if (blockIdx.x == 0) {
 				const bool any = mf_global_relabel_block(G, h, round == 0);
-				if (threadIdx.x == 0) G.flags[3] = any ? 1 : 0; // re-written only after the barrier that ends this round
+				if (threadIdx.x == 0) {
+					G.flags[3] = any ? 1 : 0; // re-written only after the barrier that ends this round
+					G.flags[14] = 0;          // stop flag of the asynchronous phase
+				}
 			}
 			__threadfence();
 			grid.sync();
@@ -539,25 +544,60 @@ __global__ void __launch_bounds__(kMfThreads) k_maxflow(FlowGraphDev G) {
 			if (tid == 0) G.flags[10] += (int)((clock64() - t0) >> 6);
 			bool active = false;
 			for (int u = tid; u < n; u += nthreads) active |= (G.excess[u] > 0.0 && h[u] < n);
-			if (tid == 0) G.flags[3 + ((round + 1) % 3)] = 0;
+			if (tid == 0) {
+				G.flags[3 + ((round + 1) % 3)] = 0;
+				G.flags[14] = 0; // stop flag of the asynchronous phase
+			}
 			if (active) G.flags[3 + (round % 3)] = 1;
 			grid.sync();
 			if (G.flags[3 + (round % 3)] == 0) break;
 		}
 		const long long t1 = clock64();
-		// asynchronous phase: no barriers, every thread keeps discharging its own nodes
-		// A block whose nodes have been quiet for two checks in a row stops sweeping; flow that reaches it later from
-		// another block is picked up after the next relabel (the active test above decides termination, not this).
+		// Asynchronous phase: no grid barriers, every thread keeps discharging its own nodes. It ends for the whole grid
+		// at once: when one block has spent its budget of busy cycles (stop flag), or when no block has reported work
+		// for quiet_cycles clocks (blocks with work bump a heartbeat counter at every check). A block must not leave
+		// while others still push: nodes are spread over the blocks by index, so a unit of flow crossing the graph
+		// lands in a different block at almost every hop, and a block that had left stranded it until the next relabel
+		// (PXB_MF_LOCAL_EXIT=1 restores that rule for A/B: 9-12 relabel rounds per heavy move instead of 7-9).
+		__shared__ int s_ctl;
 		bool busy = false;
-		int idle_checks = 0;
-		for (int c = 0; c < G.async_cycles; ++c) {
+		int idle_checks = 0, busy_cycles = 0;
+		int last_hb = 0;
+		long long last_change = clock64();
+		if (threadIdx.x == 0) last_hb = *(volatile int32_t *)&G.flags[13];
+		const int hard_cap = 64 * G.async_cycles;
+		for (int c = 0; c < hard_cap; ++c) {
 			for (int w = blockIdx.x; w < G.wide_count; w += gridDim.x) busy |= mf_process_wide_block(G, h, G.wide_begin + w);
 			for (int u = tid; u < G.wide_begin; u += nthreads) busy |= mf_process(G, h, u);
-			if ((c & 7) == 7) {
-				idle_checks = __syncthreads_or(busy) ? 0 : idle_checks + 1;
-				busy = false;
-				if (idle_checks >= G.idle_checks) break; // block-uniform
+			if ((c & 3) != 3) continue;
+			const int block_busy = __syncthreads_or(busy);
+			busy = false;
+			if (G.local_exit) { // every block for itself: quiet for idle_checks x 8 cycles, or the cycle budget
+				idle_checks = block_busy ? 0 : idle_checks + 1;
+				if (idle_checks >= 2 * G.idle_checks || c + 1 >= G.async_cycles) break; // block-uniform
+				continue;
 			}
+			if (threadIdx.x == 0) {
+				int ctl = 0;
+				if (block_busy) {
+					atomicAdd(&G.flags[13], 1);
+					busy_cycles += 4;
+					if (busy_cycles >= G.async_cycles) *(volatile int32_t *)&G.flags[14] = 1;
+					last_change = clock64();
+				} else {
+					const int hb = *(volatile int32_t *)&G.flags[13];
+					if (hb != last_hb) {
+						last_hb = hb;
+						last_change = clock64();
+					} else if (clock64() - last_change > G.quiet_cycles) {
+						ctl = 1;
+					}
+				}
+				if (*(volatile int32_t *)&G.flags[14] != 0) ctl = 1;
+				s_ctl = ctl;
+			}
+			__syncthreads();
+			if (s_ctl) break; // block-uniform
 		}
 		__threadfence();
 		grid.sync();
@@ -583,6 +623,8 @@ static int mf_launch_config(pxb_ctx *ctx, FlowGraphDev &G, int min_grid, MfLaunc
 	const int async_cycles = getenv("PXB_MF_ASYNC") ? atoi(getenv("PXB_MF_ASYNC")) : kAsyncCycles;
 	const int idle_checks = getenv("PXB_MF_IDLE") ? atoi(getenv("PXB_MF_IDLE")) : 4;
 	G.debug = (getenv("PXB_MF_STATS") && getenv("PXB_MF_STATS")[0] == '3') ? 1 : 0;
+	G.local_exit = getenv("PXB_MF_LOCAL_EXIT") ? 1 : 0;
+	G.quiet_cycles = (long long)((getenv("PXB_MF_QUIET_US") ? atof(getenv("PXB_MF_QUIET_US")) : 20.0) * 1965.0);
 	G.async_cycles = std::max(8, async_cycles);
 	G.idle_checks = std::max(1, idle_checks);
 	static bool attribute_set[64] = {}; // per device (function attributes belong to the device's context)
