@@ -117,7 +117,7 @@ def test_nonminimal_homography_fit(ctx, oracle):
     assert np.median(r2) < 1.0
 
 
-@pytest.mark.parametrize("layout", ["offsets_in_smem", "heights_and_queue_only", "grid_wide"])
+@pytest.mark.parametrize("layout", ["offsets_in_smem", "heights_and_queue_only", "grid_wide", "blocks_leave_on_their_own"])
 def test_global_relabel_layouts_give_the_same_cut(ctx, oracle, layout, monkeypatch):
     """k_maxflow's global relabel has three forms: block 0 alone with heights + queue + CSR offsets in
     shared memory, the same without the offsets (larger graphs), and the grid-wide level-synchronous BFS (graphs that do
@@ -128,6 +128,8 @@ def test_global_relabel_layouts_give_the_same_cut(ctx, oracle, layout, monkeypat
         monkeypatch.setenv("PXB_MF_SMEM_KB", "40")
     elif layout == "grid_wide":
         monkeypatch.setenv("PXB_MF_GRID_BFS", "1")
+    elif layout == "blocks_leave_on_their_own":  # the other rule for ending the asynchronous phase
+        monkeypatch.setenv("PXB_MF_LOCAL_EXIT", "1")
     pts, gt, Hs = syn.multi_homography_scene(N, n_planes=3, outlier_ratio=0.4, seed=77)
     lam = 0.1
     D = oracle.pearl_datacost(H, pts, Hs.reshape(-1, 9), 2.0, lam)
