@@ -56,7 +56,8 @@ struct FlowGraphDev {
 	int local_exit;                // PXB_MF_LOCAL_EXIT=1: blocks leave the phase on their own (A/B)
 	long long quiet_cycles;        // PXB_MF_QUIET_US: grid-wide silence that ends the phase
 	int debug;      // PXB_MF_STATS=3: block 0 prints the number of active nodes after every relabel
-	int block_bfs;  // 1/2: the launch carries 2n (3n+1) ints of dynamic shared memory and block 0 runs the global relabel alone
+	int block_bfs;  // 1/2/3: the launch carries 2n / 3n+1 / 4n+1 ints of dynamic shared memory and block 0 runs the global
+	                // relabel alone (2: CSR offsets in shared memory, 3: and bottom-up levels)
 };
 
 #ifndef PXB_MF_THREADS
@@ -173,13 +174,15 @@ __device__ __forceinline__ void bfs_enqueue(bool take, int item, int32_t *queue,
 
 __device__ bool mf_global_relabel_block(const FlowGraphDev &G, int32_t *h, bool first) {
 	extern __shared__ int32_t mf_smem[];
-	__shared__ int s_tail, s_nwide, s_wide[32], s_end[2];
+	__shared__ int s_tail, s_nwide, s_wide[32], s_end[2], s_utail;
 	const int n = G.n;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 	int32_t *hs = mf_smem, *queue = mf_smem + n;
-	// block_bfs == 2: the CSR offsets fit as well (filled once per launch) and save a round trip per expansion
+	// block_bfs >= 2: the CSR offsets fit as well (filled once per launch) and save a round trip per expansion;
+	// block_bfs == 3: and the list of the nodes that level 1 left unlabelled, for the bottom-up levels (below)
 	const int32_t *offs = G.arc_off;
-	if (G.block_bfs == 2) {
+	int32_t *ulist = G.block_bfs == 3 ? mf_smem + 3 * n + 1 : nullptr;
+	if (G.block_bfs >= 2) {
 		int32_t *so = mf_smem + 2 * n;
 		if (first)
 			for (int u = threadIdx.x; u <= n; u += blockDim.x) so[u] = G.arc_off[u];
@@ -189,6 +192,7 @@ __device__ bool mf_global_relabel_block(const FlowGraphDev &G, int32_t *h, bool 
 	if (threadIdx.x == 0) {
 		s_tail = 0;
 		s_nwide = 0;
+		s_utail = 0;
 	}
 	__syncthreads();
 	// level 1: the nodes with residual capacity to the sink (warp-uniform trip count: bfs_enqueue is a warp collective)
@@ -205,15 +209,62 @@ __device__ bool mf_global_relabel_block(const FlowGraphDev &G, int32_t *h, bool 
 			const bool at_sink = u < n && sc[j] > 0.0;
 			if (u < n) hs[u] = at_sink ? 1 : n;
 			bfs_enqueue(at_sink, u, queue, &s_tail);
+			if (ulist) bfs_enqueue(u < n && !at_sink, u, ulist, &s_utail);
 		}
 	}
 	__syncthreads();
 	if (threadIdx.x == 0) s_end[1] = s_tail;
+	const int nulist = s_utail;
 	int begin = 0, level = 1;
 	for (;;) {
 		__syncthreads(); // the previous level's appends and its end marker are visible
 		const int end = s_end[level & 1];
 		if (begin == end) break; // block-uniform
+		// Direction-optimising step (Beamer et al.): when the frontier is larger than what is still unlabelled -- the
+		// first levels of every cut: thousands of nodes hang on the sink directly -- the level is computed BOTTOM-UP:
+		// every still-unlabelled node looks among its OWN out-arcs for a residual one into the frontier (capacity and
+		// head of an out-arc are addressed directly: one round trip, no reverse-arc indirection) and takes level + 1.
+		// Same labels as the top-down expansion (a node gets level + 1 iff it has a residual arc to a node of this
+		// level and none to a lower one); a light expansion move spent 60 of its 100 us per relabel expanding the
+		// ~8800 level-1 nodes to find the ~1200 others.
+		if (ulist != nullptr && 2 * (end - begin) > (n - end) + nulist / 8) {
+			for (int i0 = warp * kBfsBatch; i0 < nulist; i0 += nwarps * kBfsBatch) {
+				int vv[kBfsBatch], a0[kBfsBatch], deg[kBfsBatch], uu[kBfsBatch];
+				double c[kBfsBatch];
+#pragma unroll
+				for (int b = 0; b < kBfsBatch; ++b) {
+					int v = i0 + b < nulist ? ulist[i0 + b] : -1;
+					if (v >= 0 && hs[v] != n) v = -1; // labelled at an earlier level
+					vv[b] = v;
+					a0[b] = v >= 0 ? offs[v] : 0;
+					deg[b] = v >= 0 ? offs[v + 1] - a0[b] : 0;
+				}
+#pragma unroll
+				for (int b = 0; b < kBfsBatch; ++b) {
+					uu[b] = ld_nc_s32_if(G.arc_head + a0[b] + lane, lane < deg[b], -1);
+					c[b] = ld_cg_f64_if(capp + a0[b] + lane, lane < deg[b]);
+				}
+#pragma unroll
+				for (int b = 0; b < kBfsBatch; ++b) {
+					bool hit = uu[b] >= 0 && c[b] > 0.0 && hs[uu[b]] == level;
+					bool any = __any_sync(0xffffffffu, hit);
+					for (int k0 = 32; k0 < deg[b] && !any; k0 += 32) { // the rare node with more than 32 arcs (warp-uniform)
+						const int k = k0 + lane;
+						const int u2 = ld_nc_s32_if(G.arc_head + a0[b] + k, k < deg[b], -1);
+						const double c2 = ld_cg_f64_if(capp + a0[b] + k, k < deg[b]);
+						hit = u2 >= 0 && c2 > 0.0 && hs[u2] == level;
+						any = __any_sync(0xffffffffu, hit);
+					}
+					if (any && lane == 0) hs[vv[b]] = level + 1; // only this warp handles vv[b] in this pass
+					bfs_enqueue(any && lane == 0, vv[b], queue, &s_tail);
+				}
+			}
+			__syncthreads();
+			if (threadIdx.x == 0) s_end[(level + 1) & 1] = s_tail;
+			begin = end;
+			++level;
+			continue;
+		}
 		// Warp-cooperative expansion: a warp takes kBfsBatch frontier nodes at a time, the lanes run over a node's
 		// arcs, so a node's heads and reverse arcs are one coalesced request each and only the capacities of the
 		// still-unlabelled heads (typically 1-3 per node) are scattered. All loads are predicated instructions
@@ -636,8 +687,10 @@ static int mf_launch_config(pxb_ctx *ctx, FlowGraphDev &G, int min_grid, MfLaunc
 		if (ctx->device >= 0 && ctx->device < 64) attribute_set[ctx->device] = true;
 	}
 	const size_t need = sizeof(int32_t) * 2 * (size_t)G.n, need_offs = sizeof(int32_t) * (3 * (size_t)G.n + 1);
+	const size_t need_ulist = need_offs + sizeof(int32_t) * (size_t)G.n; // + the unlabelled list of the bottom-up levels
 	G.block_bfs = (grid_bfs_only || G.wide_count > 32) ? 0 : (need_offs <= smem_cap ? 2 : (need <= smem_cap ? 1 : 0));
-	out.smem = G.block_bfs == 2 ? need_offs : (G.block_bfs == 1 ? need : 0);
+	if (G.block_bfs == 2 && need_ulist <= smem_cap && !getenv("PXB_MF_TOP_DOWN")) G.block_bfs = 3;
+	out.smem = G.block_bfs == 3 ? need_ulist : (G.block_bfs == 2 ? need_offs : (G.block_bfs == 1 ? need : 0));
 	int blocks_per_sm = 0;
 	PXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_maxflow, kMfThreads, out.smem));
 	if (blocks_per_sm < 1) {
