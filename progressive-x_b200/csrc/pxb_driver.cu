@@ -399,6 +399,12 @@ class Driver {
 		m_ = s.plane_parallax ? 2 : sample_size(s.type);
 		maxsol_ = s.plane_parallax ? 1 : max_solutions(s.type);
 	}
+	~Driver() {
+		if (ctx_->trusted_csr_off == graph_.off.data()) { // the arrays die with this driver
+			ctx_->trusted_csr_key = 0;
+			ctx_->trusted_csr_off = ctx_->trusted_csr_idx = nullptr;
+		}
+	}
 	int build_graph(double radius, int k);
 	void build_grid_layers(const double *rows) { // ProgressiveNapsacSampler<4>(.., {16, 8, 4, 2}, .., sizes, 0.5)
 		const size_t cells[4] = {16, 8, 4, 2};
@@ -551,6 +557,11 @@ int Driver::build_graph(double radius, int k) {
 	graph_.idx.resize((size_t)graph_.off[N_]);
 	for (int64_t i = 0; i < N_; ++i)
 		for (int t = 0; t < deg[i]; ++t) graph_.idx[graph_.off[i] + t] = nbr[(size_t)i * k + t];
+	// the graph is fixed from here on: register its arrays so that the skeleton caches need not re-hash them per cut
+	ctx_->trusted_csr_key = 0;
+	ctx_->trusted_csr_key = csr_content_key(ctx_, N_, graph_.off.data(), graph_.idx.data()) | 1;
+	ctx_->trusted_csr_off = graph_.off.data();
+	ctx_->trusted_csr_idx = graph_.idx.data();
 	return PXB_OK;
 }
 

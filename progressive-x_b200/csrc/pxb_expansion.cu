@@ -868,6 +868,13 @@ static uint64_t fnv1a(const void *data, size_t bytes, uint64_t h = 1469598103934
 	return h;
 }
 
+// cache key of a neighbourhood graph: content hash, or the key the driver registered for exactly these arrays
+uint64_t csr_content_key(pxb_ctx *ctx, int64_t N, const int32_t *off, const int32_t *idx) {
+	if (ctx->trusted_csr_key != 0 && off == ctx->trusted_csr_off && idx == ctx->trusted_csr_idx) return ctx->trusted_csr_key;
+	uint64_t key = fnv1a(off, sizeof(int32_t) * (size_t)(N + 1));
+	return fnv1a(idx, sizeof(int32_t) * (size_t)off[N], key) ^ ((uint64_t)ctx->device << 56) ^ (uint64_t)N;
+}
+
 void lo_skeleton_free(void *p) {
 	if (!p) return;
 	LoSkeleton *sk = static_cast<LoSkeleton *>(p);
@@ -879,8 +886,7 @@ void lo_skeleton_free(void *p) {
 static int lo_skeleton(pxb_ctx *ctx, int64_t N, const int32_t *off, const int32_t *idx) {
 	if (!ctx->lo_skeleton) ctx->lo_skeleton = new LoSkeleton();
 	LoSkeleton &g_lo = *static_cast<LoSkeleton *>(ctx->lo_skeleton);
-	uint64_t key = fnv1a(off, sizeof(int32_t) * (size_t)(N + 1));
-	key = fnv1a(idx, sizeof(int32_t) * (size_t)off[N], key) ^ ((uint64_t)ctx->device << 56) ^ (uint64_t)N;
+	const uint64_t key = csr_content_key(ctx, N, off, idx);
 	if (g_lo.key == key && g_lo.N == N && g_lo.buf.ptr) return PXB_OK;
 	std::unordered_set<uint64_t> used;
 	used.reserve((size_t)off[N] * 2);
@@ -1233,8 +1239,7 @@ static int exp_skeleton(pxb_ctx *ctx, int64_t N, const int32_t *off, const int32
 	if (!ctx->exp_skeleton) ctx->exp_skeleton = new ExpSkeleton();
 	ExpSkeleton &sk = *static_cast<ExpSkeleton *>(ctx->exp_skeleton);
 	out = &sk;
-	uint64_t key = fnv1a(off, sizeof(int32_t) * (size_t)(N + 1));
-	key = fnv1a(idx, sizeof(int32_t) * (size_t)off[N], key) ^ ((uint64_t)ctx->device << 56) ^ (uint64_t)N;
+	const uint64_t key = csr_content_key(ctx, N, off, idx);
 	if (sk.key == key && sk.N == N && sk.buf.ptr) return PXB_OK;
 	std::vector<int32_t> grev; // mirrored entry of every neighbour-list entry
 	// gco adjacency: per site a list built with addFront, so the last inserted neighbour comes first

@@ -90,6 +90,10 @@ struct pxb_ctx {
 	void *pinned = nullptr;
 	size_t pinned_cap = 0;
 	void *lo_skeleton = nullptr; // pxb_expansion.cu: cached arc skeleton of the last neighbourhood graph
+	// set by the host driver for the lifetime of its neighbourhood graph: the CSR arrays at these addresses are not
+	// modified, so the skeleton caches may skip re-hashing them (external ABI callers always get the content hash)
+	const int32_t *trusted_csr_off = nullptr, *trusted_csr_idx = nullptr;
+	uint64_t trusted_csr_key = 0;
 	void *exp_skeleton = nullptr; // pxb_expansion.cu: cached gco adjacency + static arcs of the alpha-expansion graph
 	// Pinned staging arena of the host-pointer entry points: small H2D payloads are copied here first and small D2H
 	// results land here and are handed to the caller's (pageable) buffers after the stream synchronises. Pageable
@@ -109,6 +113,7 @@ struct pxb_ctx {
 namespace pxb {
 void lo_skeleton_free(void *p);
 void exp_skeleton_free(void *p);
+uint64_t csr_content_key(pxb_ctx *ctx, int64_t N, const int32_t *off, const int32_t *idx);
 // staged transfers of the host-pointer entry points (pxb_api.cu): small payloads go through the context's pinned arena;
 // api_sync synchronises the stream and delivers the staged D2H results
 int api_h2d(pxb_ctx *ctx, void *dst, const void *src, size_t bytes);
