@@ -432,6 +432,14 @@ class Driver {
 	size_t iteration_number_ = 0, graph_cut_number_ = 0, lo_number_ = 0;
 	size_t degensac_degenerate_ = 0, degensac_updates_ = 0; // H-degenerate samples seen / models replaced (logging)
 	std::vector<int64_t> proposal_inliers_;
+	// one packed device-to-host copy of (count, value, shared) per scoring call, unpacked after the sync
+	struct PendingScores {
+		std::vector<int64_t> *cnt;
+		std::vector<double> *val, *shr;
+		int64_t K;
+	} pending_scores_ = {nullptr, nullptr, nullptr, 0};
+	std::vector<int64_t> score_raw_;
+	std::vector<uint8_t> flags_raw_;
 
 	// --- operators (thin wrappers; every N-point loop is a kernel) ---
 	Score finish_score(int64_t count, double value_sum, double shared, int64_t best_inliers) const {
@@ -452,19 +460,32 @@ class Driver {
 		PXB_CUDA(cudaStreamSynchronize(ctx_->stream));
 		return PXB_OK;
 	}
-	// scores K models that already sit in ctx->models (device) and brings (count, value, shared) back: no sync here
+	// scores K models that already sit in ctx->models (device) and brings (count, value, shared) back in ONE copy (the
+	// three arrays are contiguous on the device): no sync here, sync_scores() waits and unpacks
 	int score_device_models(int64_t K, double T2, std::vector<int64_t> &cnt, std::vector<double> &val, std::vector<double> &shr) {
 		cnt.resize(K);
 		val.resize(K);
 		shr.resize(K);
+		pending_scores_ = {nullptr, nullptr, nullptr, 0};
 		if (K == 0) return PXB_OK;
 		PXB_TRY(ctx_->outB.reserve(sizeof(int64_t) * (size_t)K * 3));
 		int64_t *d_cnt = ctx_->outB.as<int64_t>();
 		double *d_val = reinterpret_cast<double *>(d_cnt + K), *d_shr = d_val + K;
 		PXB_TRY(launch_score_compound(ctx_, ctx_->models.as<double>(), K, T2, compound_dev(), d_cnt, d_val, d_shr));
-		PXB_TRY(api_d2h(ctx_, cnt.data(), d_cnt, sizeof(int64_t) * (size_t)K));
-		PXB_TRY(api_d2h(ctx_, val.data(), d_val, sizeof(double) * (size_t)K));
-		PXB_TRY(api_d2h(ctx_, shr.data(), d_shr, sizeof(double) * (size_t)K));
+		score_raw_.resize((size_t)K * 3);
+		PXB_TRY(api_d2h(ctx_, score_raw_.data(), d_cnt, sizeof(int64_t) * (size_t)K * 3));
+		pending_scores_ = {&cnt, &val, &shr, K};
+		return PXB_OK;
+	}
+	int sync_scores() {
+		PXB_TRY(api_sync(ctx_));
+		if (pending_scores_.K > 0) {
+			const int64_t K = pending_scores_.K;
+			std::memcpy(pending_scores_.cnt->data(), score_raw_.data(), sizeof(int64_t) * (size_t)K);
+			std::memcpy(pending_scores_.val->data(), score_raw_.data() + K, sizeof(double) * (size_t)K);
+			std::memcpy(pending_scores_.shr->data(), score_raw_.data() + 2 * K, sizeof(double) * (size_t)K);
+			pending_scores_.K = 0;
+		}
 		return PXB_OK;
 	}
 	int score_models(const double *models, int64_t K, double T2, std::vector<int64_t> &cnt, std::vector<double> &val,
@@ -477,7 +498,7 @@ class Driver {
 		PXB_TRY(ctx_->models.reserve(sizeof(double) * (size_t)K * ms_));
 		PXB_TRY(api_h2d(ctx_, ctx_->models.ptr, models, sizeof(double) * (size_t)K * ms_));
 		PXB_TRY(score_device_models(K, T2, cnt, val, shr));
-		return api_sync(ctx_);
+		return sync_scores();
 	}
 	// minimal solves of a block of samples + their scores in ONE round trip (GCRANSAC.h:296-447, block form)
 	int solve_and_score(const std::vector<int64_t> &samples, size_t want, double T2, std::vector<double> &models,
@@ -501,11 +522,14 @@ class Driver {
 			PXB_TRY(launch_solve_minimal(ctx_, ctx_->idx.as<int64_t>(), K, ctx_->models.as<double>(), d_n, d_sv, d_mv));
 		}
 		PXB_TRY(api_d2h(ctx_, models.data(), ctx_->models.ptr, sizeof(double) * (size_t)KS * ms_));
-		PXB_TRY(api_d2h(ctx_, n.data(), d_n, sizeof(int32_t) * (size_t)K));
-		PXB_TRY(api_d2h(ctx_, sv.data(), d_sv, (size_t)K));
-		PXB_TRY(api_d2h(ctx_, mv.data(), d_mv, (size_t)K));
+		flags_raw_.resize((size_t)K * 6); // n (4 B) + sample_valid (1 B) + model_valid (1 B) per sample, contiguous on the device
+		PXB_TRY(api_d2h(ctx_, flags_raw_.data(), d_n, (size_t)K * 6));
 		PXB_TRY(score_device_models(KS, T2, cnt, val, shr));
-		return api_sync(ctx_);
+		PXB_TRY(sync_scores());
+		std::memcpy(n.data(), flags_raw_.data(), sizeof(int32_t) * (size_t)K);
+		std::memcpy(sv.data(), flags_raw_.data() + 4 * (size_t)K, (size_t)K);
+		std::memcpy(mv.data(), flags_raw_.data() + 5 * (size_t)K, (size_t)K);
+		return PXB_OK;
 	}
 	int inliers_of(const double *model, double T2, std::vector<int64_t> &out) {
 		out.resize(N_);
@@ -573,14 +597,17 @@ int Driver::fit_nonminimal(const std::vector<std::vector<int64_t>> &sets, const 
 	ok.assign(P, 0);
 	if (P == 0) return PXB_OK;
 	Scoped t(prof_, "fit_nonminimal");
-	std::vector<int32_t> off(P + 1, 0), idx;
+	// offsets and indices in one array: they are adjacent on the device and go up in one copy
+	std::vector<int32_t> off(P + 1, 0);
 	for (int p = 0; p < P; ++p) off[p + 1] = off[p] + (int32_t)sets[p].size();
-	idx.reserve(off[P]);
+	std::vector<int32_t> packed(off);
+	packed.reserve(off.size() + (size_t)off[P]);
 	for (const auto &st : sets)
-		for (int64_t i : st) idx.push_back((int32_t)i);
+		for (int64_t i : st) packed.push_back((int32_t)i);
+	const size_t n_idx = packed.size() - off.size();
 	size_t wcount = 0;
 	if (weights_by_row) wcount = weights_by_point() ? (size_t)N_ : sets[0].size(); // row-indexed: one problem at a time (IRLS)
-	const size_t bytes = sizeof(int32_t) * (off.size() + idx.size()) + 64;
+	const size_t bytes = sizeof(int32_t) * packed.size() + 64;
 	PXB_TRY(ctx_->idx.reserve(bytes));
 	int32_t *d_off = ctx_->idx.as<int32_t>(), *d_idx = d_off + off.size();
 	PXB_TRY(ctx_->models.reserve(sizeof(double) * (size_t)P * ms_));
@@ -591,8 +618,8 @@ int Driver::fit_nonminimal(const std::vector<std::vector<int64_t>> &sets, const 
 		d_w = ctx_->pref2.as<double>();
 		PXB_TRY(api_h2d(ctx_, d_w, weights_by_row, sizeof(double) * wcount));
 	}
-	PXB_TRY(api_h2d(ctx_, d_off, off.data(), sizeof(int32_t) * off.size()));
-	PXB_TRY(api_h2d(ctx_, d_idx, idx.data(), sizeof(int32_t) * idx.size()));
+	(void)n_idx;
+	PXB_TRY(api_h2d(ctx_, d_off, packed.data(), sizeof(int32_t) * packed.size()));
 	switch (s_.type) {
 	case PXB_MODEL_HOMOGRAPHY:
 		PXB_TRY(launch_fit_h(ctx_, P, d_off, d_idx, d_w, ctx_->models.as<double>(), ctx_->outA.as<int32_t>()));
@@ -613,7 +640,7 @@ int Driver::fit_nonminimal(const std::vector<std::vector<int64_t>> &sets, const 
 	PXB_TRY(api_d2h(ctx_, models_out.data(), ctx_->models.ptr, sizeof(double) * models_out.size()));
 	PXB_TRY(api_d2h(ctx_, ok.data(), ctx_->outA.ptr, sizeof(int32_t) * ok.size()));
 	if (cnt) PXB_TRY(score_device_models(P, T2, *cnt, *val, *shr));
-	return api_sync(ctx_);
+	return cnt ? sync_scores() : api_sync(ctx_);
 }
 
 // gcr/GCRANSAC.h:914-1022. Unary terms come from the device (k_lo_unary). Without a smoothness term the st-cut
