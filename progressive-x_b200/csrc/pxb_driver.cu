@@ -648,14 +648,18 @@ int Driver::fit_nonminimal(const std::vector<std::vector<int64_t>> &sets, const 
 int Driver::lo_labeling(const double *model, std::vector<int64_t> &inliers) {
 	Scoped t(prof_, "lo_labeling");
 	inliers.clear();
-	if (!(s_.lambda > 0) || graph_.idx.empty()) {
-		std::vector<double> d(N_), e0(N_), e1(N_);
-		PXB_TRY(pxb_lo_unary_terms(ctx_, model, s_.threshold, s_.lambda, d.data(), e0.data(), e1.data()));
+	std::vector<uint8_t> seg(N_);
+	if (!(s_.lambda > 0) || graph_.idx.empty()) { // the per-node decision is taken on the device (k_lo_unary_cut)
+		PXB_TRY(ctx_->models.reserve(sizeof(double) * ms_));
+		PXB_TRY(ctx_->outA.reserve((size_t)N_));
+		PXB_TRY(api_h2d(ctx_, ctx_->models.ptr, model, sizeof(double) * ms_));
+		PXB_TRY(launch_lo_unary_cut(ctx_, ctx_->models.as<double>(), s_.threshold, s_.lambda, ctx_->outA.as<uint8_t>()));
+		PXB_TRY(api_d2h(ctx_, seg.data(), ctx_->outA.ptr, (size_t)N_));
+		PXB_TRY(api_sync(ctx_));
 		for (int64_t i = 0; i < N_; ++i)
-			if (e1[i] - e0[i] < 0) inliers.push_back(i); // tr_cap = cap_source - cap_sink = e1 - e0 (energy.h:204-208)
+			if (seg[i]) inliers.push_back(i);
 		return PXB_OK;
 	}
-	std::vector<uint8_t> seg(N_);
 	PXB_TRY(pxb_lo_labeling(ctx_, model, s_.threshold, s_.lambda, graph_.off.data(), graph_.idx.data(), seg.data()));
 	for (int64_t i = 0; i < N_; ++i)
 		if (seg[i]) inliers.push_back(i);

@@ -134,6 +134,7 @@ int launch_pearl_datacost(pxb_ctx *ctx, const double *models, int64_t L, double 
 int launch_segment_sums(pxb_ctx *ctx, const double *models, int64_t L, const int32_t *labels, double *sums,
                         int64_t *counts);
 int launch_lo_unary(pxb_ctx *ctx, const double *model, double thr, double lambda, double *d, double *e0, double *e1);
+int launch_lo_unary_cut(pxb_ctx *ctx, const double *model, double thr, double lambda, uint8_t *inlier);
 int launch_tukey(pxb_ctx *ctx, const double *model, double T2, double *w);
 int launch_inlier_compact(pxb_ctx *ctx, const double *model, double T2, int64_t *inliers, int64_t *n_inliers_dev);
 int launch_solve_plane_parallax(pxb_ctx *ctx, const int64_t *samples, int64_t K, const double *H_dev, double *models_out,

@@ -445,6 +445,23 @@ int launch_segment_sums(pxb_ctx *ctx, const double *models, int64_t L, const int
 // a13: GC-RANSAC local-optimisation unary terms and Tukey weights
 // ------------------------------------------------------------------------------------------------
 template <int TYPE>
+__device__ __forceinline__ void lo_unary_terms(const double (&p)[5], const double *m, double T, double one_minus, double &dist,
+                                               double &e0, double &e1) {
+	const double r2 = squared_residual<TYPE>(p, m);
+	// std::clamp(v, 0.0, 1.0): (v < lo) ? lo : (hi < v) ? hi : v   -- NaN passes through
+	const double q = divd(r2, T);
+	dist = (q < 0.0) ? 0.0 : ((1.0 < q) ? 1.0 : q);
+	const double tmp = sub(1.0, dist);
+	if (r2 <= T) { // GCRANSAC.h:958-961
+		e0 = mul(one_minus, tmp);
+		e1 = 0.0;
+	} else {
+		e0 = 0.0;
+		e1 = mul(one_minus, sub(1.0, tmp));
+	}
+}
+
+template <int TYPE>
 __global__ void k_lo_unary(const double *__restrict__ soa, int64_t stride, int64_t N, const double *__restrict__ model,
                            double T, double one_minus, double *__restrict__ d, double *__restrict__ e0,
                            double *__restrict__ e1) {
@@ -456,19 +473,40 @@ __global__ void k_lo_unary(const double *__restrict__ soa, int64_t stride, int64
 	if (i >= N) return;
 	double p[5];
 	load_point<DIM>(soa, stride, i, p);
-	const double r2 = squared_residual<TYPE>(p, m);
-	// std::clamp(v, 0.0, 1.0): (v < lo) ? lo : (hi < v) ? hi : v   -- NaN passes through
-	const double q = divd(r2, T);
-	const double dist = (q < 0.0) ? 0.0 : ((1.0 < q) ? 1.0 : q);
-	const double tmp = sub(1.0, dist);
+	double dist, a, b;
+	lo_unary_terms<TYPE>(p, m, T, one_minus, dist, a, b);
 	d[i] = dist;
-	if (r2 <= T) { // GCRANSAC.h:958-961
-		e0[i] = mul(one_minus, tmp);
-		e1[i] = 0.0;
-	} else {
-		e0[i] = 0.0;
-		e1[i] = mul(one_minus, sub(1.0, tmp));
-	}
+	e0[i] = a;
+	e1[i] = b;
+}
+
+// The cut of GCRANSAC::labeling without a smoothness term (lambda = 0 or no neighbourhood graph) decomposes per node:
+// SINK (= inlier) iff the t-link residual cap_source - cap_sink = e1 - e0 is negative (gcr/energy.h:204-208).
+template <int TYPE>
+__global__ void k_lo_unary_cut(const double *__restrict__ soa, int64_t stride, int64_t N, const double *__restrict__ model,
+                               double T, double one_minus, uint8_t *__restrict__ inlier) {
+	constexpr int DIM = ModelTraits<TYPE>::kDim, MS = ModelTraits<TYPE>::kSize;
+	__shared__ double m[MS];
+	if (threadIdx.x < MS) m[threadIdx.x] = model[threadIdx.x];
+	__syncthreads();
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= N) return;
+	double p[5];
+	load_point<DIM>(soa, stride, i, p);
+	double dist, a, b;
+	lo_unary_terms<TYPE>(p, m, T, one_minus, dist, a, b);
+	inlier[i] = sub(b, a) < 0.0 ? 1 : 0;
+}
+
+int launch_lo_unary_cut(pxb_ctx *ctx, const double *model, double thr, double lambda, uint8_t *inlier) {
+	const Points &p = ctx->pts;
+	const double T = thr * thr * 9 / 4; // GCRANSAC.h:942 spelling
+	const double one_minus = 1.0 - lambda;
+	const unsigned grid = (unsigned)((p.N + kThreads - 1) / kThreads);
+	PXB_DISPATCH_TYPE(p.type, (k_lo_unary_cut<TYPE><<<grid, kThreads, 0, ctx->stream>>>(p.soa, p.stride, p.N, model, T, one_minus, inlier)));
+	ctx->launches++;
+	PXB_CUDA(cudaGetLastError());
+	return PXB_OK;
 }
 
 int launch_lo_unary(pxb_ctx *ctx, const double *model, double thr, double lambda, double *d, double *e0, double *e1) {
