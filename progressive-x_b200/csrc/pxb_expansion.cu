@@ -159,7 +159,6 @@ __device__ void mf_global_relabel(const FlowGraphDev &G, int32_t *h, cg::grid_gr
 // need 20-30 relabels of ~35 levels each; here a level is a few block barriers around a frontier-sized loop (queue
 // form: every node is expanded exactly once), and the other blocks wait at one grid barrier per relabel.
 // Returns (block-uniformly) whether any node with excess can still reach the sink.
-constexpr int kBfsBatch = 8;
 // Appends the items of the lanes with `take` set to the shared queue with ONE atomic per warp (a same-address shared
 // atomic per item serialises: at ~200 discoveries per level that alone was half of a level's time).
 __device__ __forceinline__ void bfs_enqueue(bool take, int item, int32_t *queue, int *tail) {
@@ -227,37 +226,38 @@ __device__ bool mf_global_relabel_block(const FlowGraphDev &G, int32_t *h, bool 
 		// Same labels as the top-down expansion (a node gets level + 1 iff it has a residual arc to a node of this
 		// level and none to a lower one); a light expansion move spent 60 of its 100 us per relabel expanding the
 		// ~8800 level-1 nodes to find the ~1200 others.
+		// Work split of both forms: a warp takes 8 nodes at a time, FOUR LANES PER NODE, lane j of a group looks at arcs
+		// j, j + 4, j + 8, ... of its node, four of them per pass with predicated loads in flight together. The relabel
+		// runs on one SM and is bound by what that SM can issue: one node per thread makes every load instruction touch
+		// 32 different lines (load-path bound, ~3.8 us per level), one node per warp pass executes ~125 warp
+		// instructions per node with half of the lanes idle (issue bound, ~4 us per level); four lanes per node need
+		// ~25 instructions and 12 sectors per node.
+		const int grp = lane >> 2, sub = lane & 3;
+		const unsigned grp_mask = 0xFu << (grp * 4);
 		if (ulist != nullptr && 2 * (end - begin) > (n - end) + nulist / 8) {
-			for (int i0 = warp * kBfsBatch; i0 < nulist; i0 += nwarps * kBfsBatch) {
-				int vv[kBfsBatch], a0[kBfsBatch], deg[kBfsBatch], uu[kBfsBatch];
-				double c[kBfsBatch];
+			for (int i0 = warp * 8; i0 < nulist; i0 += nwarps * 8) {
+				int v = i0 + grp < nulist ? ulist[i0 + grp] : -1;
+				if (v >= 0 && hs[v] != n) v = -1; // labelled at an earlier level
+				const int a0 = v >= 0 ? offs[v] : 0, deg = v >= 0 ? offs[v + 1] - a0 : 0;
+				bool found = false; // group-uniform
+				for (int k0 = 0; __any_sync(0xffffffffu, k0 < deg && !found); k0 += 16) { // warp-uniform trip count
+					int uu[4];
+					double c[4];
 #pragma unroll
-				for (int b = 0; b < kBfsBatch; ++b) {
-					int v = i0 + b < nulist ? ulist[i0 + b] : -1;
-					if (v >= 0 && hs[v] != n) v = -1; // labelled at an earlier level
-					vv[b] = v;
-					a0[b] = v >= 0 ? offs[v] : 0;
-					deg[b] = v >= 0 ? offs[v + 1] - a0[b] : 0;
-				}
-#pragma unroll
-				for (int b = 0; b < kBfsBatch; ++b) {
-					uu[b] = ld_nc_s32_if(G.arc_head + a0[b] + lane, lane < deg[b], -1);
-					c[b] = ld_cg_f64_if(capp + a0[b] + lane, lane < deg[b]);
-				}
-#pragma unroll
-				for (int b = 0; b < kBfsBatch; ++b) {
-					bool hit = uu[b] >= 0 && c[b] > 0.0 && hs[uu[b]] == level;
-					bool any = __any_sync(0xffffffffu, hit);
-					for (int k0 = 32; k0 < deg[b] && !any; k0 += 32) { // the rare node with more than 32 arcs (warp-uniform)
-						const int k = k0 + lane;
-						const int u2 = ld_nc_s32_if(G.arc_head + a0[b] + k, k < deg[b], -1);
-						const double c2 = ld_cg_f64_if(capp + a0[b] + k, k < deg[b]);
-						hit = u2 >= 0 && c2 > 0.0 && hs[u2] == level;
-						any = __any_sync(0xffffffffu, hit);
+					for (int t = 0; t < 4; ++t) {
+						const int k = k0 + 4 * t + sub;
+						const bool in = k < deg && !found;
+						uu[t] = ld_nc_s32_if(G.arc_head + a0 + k, in, -1);
+						c[t] = ld_cg_f64_if(capp + a0 + k, in);
 					}
-					if (any && lane == 0) hs[vv[b]] = level + 1; // only this warp handles vv[b] in this pass
-					bfs_enqueue(any && lane == 0, vv[b], queue, &s_tail);
+					bool hit = false;
+#pragma unroll
+					for (int t = 0; t < 4; ++t) hit |= uu[t] >= 0 && c[t] > 0.0 && hs[uu[t]] == level;
+					found |= (__ballot_sync(0xffffffffu, hit) & grp_mask) != 0;
 				}
+				const bool take = found && sub == 0;
+				if (take) hs[v] = level + 1; // only this group handles v in this pass
+				bfs_enqueue(take, v, queue, &s_tail);
 			}
 			__syncthreads();
 			if (threadIdx.x == 0) s_end[(level + 1) & 1] = s_tail;
@@ -265,66 +265,49 @@ __device__ bool mf_global_relabel_block(const FlowGraphDev &G, int32_t *h, bool 
 			++level;
 			continue;
 		}
-		// Warp-cooperative expansion: a warp takes kBfsBatch frontier nodes at a time, the lanes run over a node's
-		// arcs, so a node's heads and reverse arcs are one coalesced request each and only the capacities of the
-		// still-unlabelled heads (typically 1-3 per node) are scattered. All loads are predicated instructions
-		// (inline PTX): the batch's loads are in flight together, two dependent round trips per batch.
-		for (int i0 = begin + warp * kBfsBatch; i0 < end; i0 += nwarps * kBfsBatch) {
-			int a0[kBfsBatch], deg[kBfsBatch], v[kBfsBatch], r[kBfsBatch];
-			double c[kBfsBatch];
-			bool want[kBfsBatch];
+		// Top-down expansion of the frontier: heads and reverse arcs of four arcs per lane in one round trip, then --
+		// only for heads that are still unlabelled -- the reverse capacities; atomicCAS claims a head; the winners of a
+		// pass are appended to the queue with one atomic per warp (a same-address shared atomic per item serialises).
+		for (int i0 = begin + warp * 8; i0 < end; i0 += nwarps * 8) {
+			int u = i0 + grp < end ? queue[i0 + grp] : -1;
+			if (u >= G.wide_begin) { // expanded by the whole block below
+				if (sub == 0) s_wide[atomicAdd(&s_nwide, 1)] = u;
+				u = -1;
+			}
+			const int a0 = u >= 0 ? offs[u] : 0, deg = u >= 0 ? offs[u + 1] - a0 : 0;
+			for (int k0 = 0; __any_sync(0xffffffffu, k0 < deg); k0 += 16) { // warp-uniform trip count
+				int v[4], r[4];
+				double c[4];
+				bool want[4], won[4];
 #pragma unroll
-			for (int b = 0; b < kBfsBatch; ++b) {
-				int u = i0 + b < end ? queue[i0 + b] : -1;
-				if (u >= G.wide_begin) { // expanded by the whole block below
-					if (lane == 0) s_wide[atomicAdd(&s_nwide, 1)] = u;
-					u = -1;
+				for (int t = 0; t < 4; ++t) {
+					const int k = k0 + 4 * t + sub;
+					v[t] = ld_nc_s32_if(G.arc_head + a0 + k, k < deg, -1);
+					r[t] = ld_nc_s32_if(G.arc_rev + a0 + k, k < deg, 0);
 				}
-				a0[b] = u >= 0 ? offs[u] : 0;
-				deg[b] = u >= 0 ? offs[u + 1] - a0[b] : 0;
-			}
 #pragma unroll
-			for (int b = 0; b < kBfsBatch; ++b) {
-				v[b] = ld_nc_s32_if(G.arc_head + a0[b] + lane, lane < deg[b], -1);
-				r[b] = ld_nc_s32_if(G.arc_rev + a0[b] + lane, lane < deg[b], 0);
-			}
+				for (int t = 0; t < 4; ++t) want[t] = v[t] >= 0 && hs[v[t]] == n;
 #pragma unroll
-			for (int b = 0; b < kBfsBatch; ++b) want[b] = v[b] >= 0 && hs[v[b]] == n;
+				for (int t = 0; t < 4; ++t) c[t] = ld_cg_f64_if(capp + r[t], want[t]);
 #pragma unroll
-			for (int b = 0; b < kBfsBatch; ++b) c[b] = ld_cg_f64_if(capp + r[b], want[b]);
-			// claim the heads (independent shared-memory CAS operations), then append all winners of the batch with one
-			// atomic on the queue tail: a per-node append chain (CAS -> ballot -> atomic -> shuffle) cost 1.4 us per level
-			bool won[kBfsBatch];
+				for (int t = 0; t < 4; ++t) won[t] = want[t] && c[t] > 0.0 && atomicCAS(&hs[v[t]], n, level + 1) == n;
+				unsigned wmask[4];
+				int before[4], total = 0;
 #pragma unroll
-			for (int b = 0; b < kBfsBatch; ++b) won[b] = want[b] && c[b] > 0.0 && atomicCAS(&hs[v[b]], n, level + 1) == n;
-			unsigned wmask[kBfsBatch];
-			int before[kBfsBatch], total = 0;
-#pragma unroll
-			for (int b = 0; b < kBfsBatch; ++b) {
-				wmask[b] = __ballot_sync(0xffffffffu, won[b]);
-				before[b] = total;
-				total += __popc(wmask[b]);
-			}
-			if (total > 0) { // warp-uniform
-				int base = 0;
-				if (lane == 0) base = atomicAdd(&s_tail, total);
-				base = __shfl_sync(0xffffffffu, base, 0);
-#pragma unroll
-				for (int b = 0; b < kBfsBatch; ++b)
-					if (won[b]) queue[base + before[b] + __popc(wmask[b] & ((1u << lane) - 1u))] = v[b];
-			}
-			// the rare node with more than 32 arcs (warp-uniform trip count)
-#pragma unroll
-			for (int b = 0; b < kBfsBatch; ++b)
-				for (int k0 = 32; k0 < deg[b]; k0 += 32) {
-					const int k = k0 + lane;
-					const int vv = ld_nc_s32_if(G.arc_head + a0[b] + k, k < deg[b], -1);
-					const int rr = ld_nc_s32_if(G.arc_rev + a0[b] + k, k < deg[b], 0);
-					const bool w2 = vv >= 0 && hs[vv] == n;
-					const double cc = ld_cg_f64_if(capp + rr, w2);
-					const bool won = w2 && cc > 0.0 && atomicCAS(&hs[vv], n, level + 1) == n;
-					bfs_enqueue(won, vv, queue, &s_tail);
+				for (int t = 0; t < 4; ++t) {
+					wmask[t] = __ballot_sync(0xffffffffu, won[t]);
+					before[t] = total;
+					total += __popc(wmask[t]);
 				}
+				if (total > 0) { // warp-uniform
+					int base = 0;
+					if (lane == 0) base = atomicAdd(&s_tail, total);
+					base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+					for (int t = 0; t < 4; ++t)
+						if (won[t]) queue[base + before[t] + __popc(wmask[t] & ((1u << lane) - 1u))] = v[t];
+				}
+			}
 		}
 		__syncthreads();
 		const int nwide = s_nwide; // block-uniform
