@@ -548,7 +548,7 @@ __device__ bool mf_process_wide_block(const FlowGraphDev &G, volatile int32_t *h
 	return true;
 }
 
-constexpr int kAsyncCycles = 128;
+constexpr int kAsyncCycles = 64;
 constexpr int kMaxRounds = 100000;
 
 __global__ void __launch_bounds__(kMfThreads) k_maxflow(FlowGraphDev G) {
@@ -658,7 +658,7 @@ static int mf_launch_config(pxb_ctx *ctx, FlowGraphDev &G, int min_grid, MfLaunc
 	const int idle_checks = getenv("PXB_MF_IDLE") ? atoi(getenv("PXB_MF_IDLE")) : 4;
 	G.debug = (getenv("PXB_MF_STATS") && getenv("PXB_MF_STATS")[0] == '3') ? 1 : 0;
 	G.local_exit = getenv("PXB_MF_LOCAL_EXIT") ? 1 : 0;
-	G.quiet_cycles = (long long)((getenv("PXB_MF_QUIET_US") ? atof(getenv("PXB_MF_QUIET_US")) : 20.0) * 1965.0);
+	G.quiet_cycles = (long long)((getenv("PXB_MF_QUIET_US") ? atof(getenv("PXB_MF_QUIET_US")) : 10.0) * 1965.0);
 	G.async_cycles = std::max(8, async_cycles);
 	G.idle_checks = std::max(1, idle_checks);
 	static bool attribute_set[64] = {}; // per device (function attributes belong to the device's context)
