@@ -376,16 +376,22 @@ __device__ bool mf_global_relabel_block(const FlowGraphDev &G, int32_t *h, bool 
 __device__ __forceinline__ bool mf_process(const FlowGraphDev &G, volatile int32_t *h, int u) {
 	const int n = G.n;
 	volatile double *excess = G.excess, *cap = G.cap;
-	const double e = excess[u];
+	// everything a visit needs about u itself travels in ONE round trip, also for the (many) nodes that turn out to be
+	// inactive: a visit of an active node is a chain of dependent round trips (~370 cycles each), and the length of
+	// that chain times the number of cycles is what an asynchronous phase costs
+	const double e0 = excess[u];
 	const int hu = h[u];
-	if (!(e > 0.0) || hu >= n) return false;
-	if (G.sink_cap[u] > 0.0) { // the sink (height 0) is always the lowest neighbour
-		const double d = fmin(e, G.sink_cap[u]);
-		G.sink_cap[u] -= d;
+	const double sc = ld_volatile_f64_if(G.sink_cap + u, true);
+	const int a0 = ld_nc_s32_if(G.arc_off + u, true, 0), a1 = ld_nc_s32_if(G.arc_off + u + 1, true, 0);
+	if (!(e0 > 0.0) || hu >= n) return false;
+	double e = e0;
+	if (sc > 0.0) { // the sink (height 0) is always the lowest neighbour; what it cannot absorb goes on below
+		const double d = fmin(e, sc);
+		G.sink_cap[u] = sc - d; // only u's owner writes its sink link
 		atomicAdd(&G.excess[u], -d);
-		return true;
+		e -= d;
+		if (!(e > 0.0)) return true;
 	}
-	const int a0 = G.arc_off[u], a1 = G.arc_off[u + 1];
 	if (a1 - a0 > kWideDegree) {
 		// high-degree node (a label-cost auxiliary node): one pass that pushes to EVERY lower residual neighbour, so
 		// that its budget is spread in one visit instead of one neighbour per visit
