@@ -283,8 +283,13 @@ static void launch_screened(pxb_ctx *ctx, int nchunks, const float *consts, cons
                             double T2, const double *cp, ScorePartial *pp) {
 	const Points &p = ctx->pts;
 	constexpr int kBytes = (int)ScoreSmem<TYPE, HAS_CP>::kBytes;
-	// opt in to > 48 KB of dynamic shared memory (per device and function; a host-side attribute write, ~1 us)
-	cudaFuncSetAttribute(k_score_screened<TYPE, HAS_CP, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBytes);
+	// opt in to > 48 KB of dynamic shared memory: once per device and instantiation (every API call counts when eight
+	// host threads drive one GPU)
+	static bool opted_in[64] = {};
+	if (ctx->device < 0 || ctx->device >= 64 || !opted_in[ctx->device]) {
+		cudaFuncSetAttribute(k_score_screened<TYPE, HAS_CP, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBytes);
+		if (ctx->device >= 0 && ctx->device < 64) opted_in[ctx->device] = true;
+	}
 	const int64_t tile = (int64_t)kScHyps * PASSES;
 	dim3 grid((unsigned)nchunks, (unsigned)((kk + tile - 1) / tile));
 	k_score_screened<TYPE, HAS_CP, PASSES><<<grid, kThreads, kBytes, ctx->stream>>>(p.soa, p.stride, p.N, p.f32n, p.q, consts, mf, m,
