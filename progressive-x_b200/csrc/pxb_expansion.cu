@@ -680,8 +680,18 @@ static int mf_launch_config(pxb_ctx *ctx, FlowGraphDev &G, int min_grid, MfLaunc
 	G.block_bfs = (grid_bfs_only || G.wide_count > 32) ? 0 : (need_offs <= smem_cap ? 2 : (need <= smem_cap ? 1 : 0));
 	if (G.block_bfs == 2 && need_ulist <= smem_cap && !getenv("PXB_MF_TOP_DOWN")) G.block_bfs = 3;
 	out.smem = G.block_bfs == 3 ? need_ulist : (G.block_bfs == 2 ? need_offs : (G.block_bfs == 1 ? need : 0));
-	int blocks_per_sm = 0;
-	PXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_maxflow, kMfThreads, out.smem));
+	// occupancy for this shared-memory size: asked once per (thread, device, size) -- a fit makes ~200 cuts
+	thread_local struct {
+		int device;
+		size_t smem;
+		int blocks;
+	} occ = {-1, 0, 0};
+	if (occ.device != ctx->device || occ.smem != out.smem) {
+		int b = 0;
+		PXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_maxflow, kMfThreads, out.smem));
+		occ = {ctx->device, out.smem, b};
+	}
+	const int blocks_per_sm = occ.blocks;
 	if (blocks_per_sm < 1) {
 		set_error("k_maxflow does not fit on an SM with %zu bytes of shared memory", out.smem);
 		return PXB_ERR_CUDA;
@@ -1129,8 +1139,9 @@ __global__ void k_exp_assemble(int64_t N, int L1, int alpha, double lambda, doub
                                const int32_t *__restrict__ lab, const int32_t *__restrict__ goff,
                                const int32_t *__restrict__ gidx, const int32_t *__restrict__ label_count,
                                const int32_t *__restrict__ arc_rev, double *__restrict__ cap, double *__restrict__ excess,
-                               double *__restrict__ sink_cap) {
+                               double *__restrict__ sink_cap, int32_t *__restrict__ flags) {
 	const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (s < 16) flags[s] = 0; // counters and status words of the max-flow kernel that follows
 	if (s >= N + L1) return;
 	if (s >= N) { // auxiliary node of label l: add_term1(aux, 0, label_cost) = add_tweights(aux, label_cost, 0)
 		const int l = (int)(s - N);
@@ -1326,7 +1337,8 @@ int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t
 	int32_t *d_arc_off = reinterpret_cast<int32_t *>(d_sink + n), *d_head = d_arc_off + (n + 1), *d_rev = d_head + m;
 	int32_t *d_lab = d_rev + m, *d_rank = d_lab + N;
 	int32_t *d_label_off = d_rank + N, *d_label_count = d_label_off + (L1 + 1);
-	int32_t *d_h0 = d_label_count + (L1 + 1), *d_h1 = d_h0 + n, *d_flags = d_h1 + n;
+	// heights and kernel flags are adjacent: they come back in one copy after every move
+	int32_t *d_h0 = d_label_count + (L1 + 1), *d_flags = d_h0 + n, *d_h1 = d_flags + 16;
 	const int32_t *d_goff = sk.d_goff, *d_gidx = sk.d_gidx;
 	PXB_CUDA(cudaMemcpyAsync(d_arc_off, sk.arc_off, sizeof(int32_t) * (size_t)(N + 1), cudaMemcpyDeviceToDevice, st));
 	PXB_CUDA(cudaMemcpyAsync(d_head, sk.head, sizeof(int32_t) * (size_t)(E + N), cudaMemcpyDeviceToDevice, st));
@@ -1379,14 +1391,12 @@ int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t
 		for (int alpha = 0; alpha < L1; ++alpha) { // oneExpansionIteration, fixed label order 0..L
 			if (label_count[alpha] == (int32_t)N) continue; // no site to move (alpha_expansion returns at size == 0)
 			const auto t_move = std::chrono::steady_clock::now();
-			PXB_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int32_t) * 16, st));
 			k_exp_assemble<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(N, L1, alpha, lambda, label_cost, D_dev, d_lab, d_goff, d_gidx,
-			                                                          d_label_count, d_rev, d_cap, d_excess, d_sink);
+			                                                          d_label_count, d_rev, d_cap, d_excess, d_sink, d_flags);
 			void *args[] = {&G};
 			PXB_CUDA(cudaLaunchCooperativeKernel((void *)k_maxflow, dim3(grid), dim3(kMfThreads), args, lc.smem, st));
 			ctx->launches += 2;
-			PXB_CUDA(cudaMemcpyAsync(h_host, d_h0, sizeof(int32_t) * (size_t)N, cudaMemcpyDeviceToHost, st));
-			PXB_CUDA(cudaMemcpyAsync(flags_host, d_flags, sizeof(int32_t) * 16, cudaMemcpyDeviceToHost, st));
+			PXB_CUDA(cudaMemcpyAsync(h_host, d_h0, sizeof(int32_t) * ((size_t)n + 16), cudaMemcpyDeviceToHost, st)); // + flags
 			PXB_CUDA(cudaStreamSynchronize(st));
 			if (flags_host[7] != 1 || flags_host[6] == 0) {
 				set_error("max-flow did not converge within %d relabel rounds", kMaxRounds);
