@@ -1,0 +1,69 @@
+"""The sequential control-flow oracle (oracle/px_sequential.py) on its own, without a GPU: run on the reference's bundled
+AdelaideH scenes with the notebook's parameters it must reach the misclassification errors the reference's notebook
+prints (adelaideH.ipynb: unionhouse 0.006, oldclassicswing 0.000), be deterministic for a seed, and recover planted
+vanishing points and lines. This is what makes it usable as the checker of the GPU driver's labels
+(tests/test_gpu_sequential_oracle.py)."""
+import itertools
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from pyprogressivex import synthetic as syn
+
+G = np.load(Path(__file__).resolve().parent / "golden" / "reference_scenes.npz")
+
+
+def misclassification(segmentation, ref):
+    n = int(ref.max()) + 1
+    return min(int(np.sum(np.asarray(p)[ref] != segmentation)) for p in itertools.permutations(range(n))) / len(ref)
+
+
+@pytest.mark.parametrize("scene,bar", [("unionhouse", 0.05), ("oldclassicswing", 0.05)])
+def test_sequential_oracle_on_adelaide_h(scene, bar):
+    from oracle import px_sequential as seq
+    corrs, ref = G[f"{scene}_corrs"], G[f"{scene}_labels"]
+    graph = syn.knn_graph(corrs, 200.0, 5)
+    errs = []
+    for seed in (1, 2, 3):
+        models, labels = seq.find_homographies(corrs, 4.0, 0.5, 0.05, 0.4, 1000, 10, 6, 3, 2, seed, graph,
+                                               image_sizes=(640.0, 480.0, 640.0, 480.0))
+        assert models.shape[1] == 9 and labels.shape == (len(corrs),)
+        errs.append(misclassification(labels.astype(int), ref))
+    assert np.median(errs) <= bar, errs
+    again = seq.find_homographies(corrs, 4.0, 0.5, 0.05, 0.4, 1000, 10, 6, 3, 2, 3, graph,
+                                  image_sizes=(640.0, 480.0, 640.0, 480.0))
+    assert np.array_equal(again[1], labels) and np.array_equal(again[0], models)
+
+
+@pytest.mark.parametrize("sampler_id", [0, 1, 2])
+def test_sequential_oracle_samplers_recover_planted_planes(sampler_id):
+    """uniform, PROSAC and Progressive NAPSAC on a synthetic three-plane scene (lambda = 0: greedy labelling)"""
+    from oracle import px_sequential as seq
+    pts, gt, _ = syn.multi_homography_scene(600, n_planes=3, outlier_ratio=0.3, noise=0.3, seed=5)
+    models, labels = seq.find_homographies(pts, 2.0, 0.9, 0.0, 0.4, 2000, 40, -1, sampler_id, 2, 7, None,
+                                           image_sizes=(1024.0, 768.0, 1024.0, 768.0))
+    assert models.shape[0] == 3
+    for k in range(3):
+        members = labels[gt == k]
+        assert np.bincount(members[members < 3], minlength=3).max() >= 0.9 * np.sum(gt == k)
+
+
+def test_sequential_oracle_vanishing_points_and_lines():
+    """same scenes and parameters as tests/test_gpu_sequential_oracle.py: every planted structure is among the instances"""
+    from oracle import px_sequential as seq
+    seg, gt, vps = syn.multi_vanishing_point_scene(800, n_vps=3, outlier_ratio=0.3, noise=0.3, seed=23)
+    w = np.random.default_rng(1).uniform(0.5, 1.0, len(seg))
+    models, labels = seq.find_points_family(seq.VP, seg, w, 2.0, 0.9, 0.0, 0.4, 400, 40, -1, 0, 2, 1)
+    assert models.shape[1] == 3 and labels.shape == (len(seg),)
+    for v in vps:
+        cosines = np.abs(models @ v) / (np.linalg.norm(models, axis=1) * np.linalg.norm(v))
+        assert cosines.max() > 0.999
+    pts, gt, lines = syn.multi_line_scene(700, n_lines=3, outlier_ratio=0.3, noise=0.5, seed=29)
+    models, labels = seq.find_points_family(seq.LINE, pts, None, 2.0, 0.95, 0.0, 0.4, 600, 40, -1, 0, 2, 1)
+    assert models.shape[1] == 3 and models.shape[0] >= 1
+    # the points of every recovered instance lie on its line
+    for k in range(models.shape[0]):
+        members = pts[labels == k]
+        d = np.abs(members @ models[k, :2] + models[k, 2]) / np.linalg.norm(models[k, :2])
+        assert len(members) >= 40 and np.median(d) < 2.0
