@@ -357,14 +357,19 @@ def h_degenerate_sample(rows, sample7, F, homography_threshold=2.0):
         for k in range(3):
             c = np.cross(x2[k], e)
             b[k] = np.dot(np.cross(x2[k], A @ x1[k]), c) / np.dot(c, c)      # :419-422
-        Hm = A - np.outer(e, np.linalg.solve(x1, b))                         # :424-430
+        try:
+            Hm = A - np.outer(e, np.linalg.solve(x1, b))                     # :424-430
+        except np.linalg.LinAlgError:  # collinear triplet: M.inverse() is inf/NaN in the reference, no point passes the test
+            margins.append([float("inf")] * 4)
+            continue
         errs = []
         for j in range(7):
             i = int(sample7[j])
             if i in ids:
                 continue
             t = Hm @ np.array([rows[i, 0], rows[i, 1], 1.0])
-            errs.append((rows[i, 2] - t[0] / t[2]) ** 2 + (rows[i, 3] - t[1] / t[2]) ** 2)   # :452-462
+            with np.errstate(divide="ignore", invalid="ignore"):
+                errs.append((rows[i, 2] - t[0] / t[2]) ** 2 + (rows[i, 3] - t[1] / t[2]) ** 2)   # :452-462
         margins.append(sorted(errs))
         if 3 + sum(x < homography_threshold ** 2 for x in errs) >= 5:        # :466-476
             return True, Hm, margins

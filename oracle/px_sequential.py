@@ -27,12 +27,13 @@ the oracle has no restatement of their non-minimal solvers."""
 from __future__ import annotations
 
 import math
+import os
 
 import numpy as np
 
 from . import oracle as O
 
-H, VP, LINE = 0, 3, 4
+H, F, VP, LINE = 0, 1, 3, 4
 M64 = (1 << 64) - 1
 
 
@@ -233,6 +234,109 @@ class ProgressiveNapsacSampler:  # gcr/samplers/progressive_napsac_sampler.h; la
         return out
 
 
+# ---- fundamental matrices ------------------------------------------------------------------------------------------
+def _rank2_unit(Fm):
+    """closest rank-2 matrix, unit Frobenius norm"""
+    U, sv, Vt = np.linalg.svd(Fm)
+    Fm = (U[:, :2] * sv[:2]) @ Vt[:2]
+    nrm = np.linalg.norm(Fm)
+    return Fm / nrm if nrm > 0 else Fm
+
+
+def _lm_system(Fm, x1, x2, w):
+    """J^T J, J^T r and the cost of the weighted Sampson residuals r_i = w_i C_i / sqrt(S_i) (9 parameters)"""
+    Fx = x1 @ Fm.T
+    Ftx = x2 @ Fm
+    C = np.einsum("ni,ni->n", x2, Fx)
+    S = Fx[:, 0] ** 2 + Fx[:, 1] ** 2 + Ftx[:, 0] ** 2 + Ftx[:, 1] ** 2
+    keep = S > 1e-300
+    x1, x2, Fx, Ftx, C, S, w = x1[keep], x2[keep], Fx[keep], Ftx[keep], C[keep], S[keep], w[keep]
+    inv = 1.0 / np.sqrt(S)
+    res = w * C * inv
+    J = np.empty((len(C), 9))
+    for r in range(3):
+        for c in range(3):
+            dC = x2[:, r] * x1[:, c]
+            dS = 2.0 * ((Fx[:, r] * x1[:, c] if r < 2 else 0.0) + (Ftx[:, c] * x2[:, r] if c < 2 else 0.0))
+            J[:, 3 * r + c] = w * (dC * inv - 0.5 * C * inv ** 3 * dS)
+    return J.T @ J, J.T @ res, float(res @ res)
+
+
+def fit_f_nonminimal(pts, idx, weights_by_row=None):
+    """The GPU engine's non-minimal F fit (progressive-x_b200/csrc/pxb_fit_fp.cu, k_fit_f) restated with numpy: normalised
+    eight-point (fundamental_estimator.h:574-618 / solver_fundamental_matrix_eight_point.h), rank-2 projection, then a
+    Levenberg-Marquardt polish of the weighted Sampson error -- the objective of the reference's bundle adjustment
+    (solver_fundamental_matrix_bundle_adjustment.h:114-178 -> PoseLib, not on disk). Same steps, damping schedule and
+    acceptance rule as the kernel; sums are numpy's, so results agree to ~1e-9, not bit for bit."""
+    q = pts[np.asarray(idx, dtype=np.int64)]
+    n = len(q)
+    if n < 8:
+        return None, False
+    w = np.ones(n) if weights_by_row is None else np.asarray(weights_by_row, dtype=np.float64)[:n]
+    m1, m2 = q[:, :2].mean(0), q[:, 2:].mean(0)
+    r1 = math.sqrt(2.0) / np.mean(np.sqrt(((m1 - q[:, :2]) ** 2).sum(1)))
+    r2 = math.sqrt(2.0) / np.mean(np.sqrt(((m2 - q[:, 2:]) ** 2).sum(1)))
+    a = (q[:, :2] - m1) * r1
+    b = (q[:, 2:] - m2) * r2
+    rows = np.column_stack([b[:, 0] * a[:, 0], b[:, 0] * a[:, 1], b[:, 0], b[:, 1] * a[:, 0], b[:, 1] * a[:, 1], b[:, 1],
+                            a[:, 0], a[:, 1], np.ones(n)]) * w[:, None]
+    evals, evecs = np.linalg.eigh(rows.T @ rows)
+    Fn = _rank2_unit(evecs[:, 0].reshape(3, 3))
+    rs = math.sqrt(r1 * r2)
+    k1, k2 = r1 / rs, r2 / rs
+    Fl = _rank2_unit(Fn * np.array([k2, k2, 1.0])[:, None] * np.array([k1, k1, 1.0])[None, :])
+    x1 = np.column_stack([(q[:, :2] - m1) * rs, np.ones(n)])
+    x2 = np.column_stack([(q[:, 2:] - m2) * rs, np.ones(n)])
+    JtJ, Jtr, cost = _lm_system(Fl, x1, x2, w)
+    mu = 1e-3
+    for _ in range(8):
+        M = JtJ.copy()
+        d = np.diag(M).copy()
+        M[np.diag_indices(9)] = d + mu * np.maximum(d, 1e-12)
+        try:
+            delta = np.linalg.solve(M, -Jtr)
+        except np.linalg.LinAlgError:
+            break
+        if not np.all(np.abs(delta) <= 1e300):
+            break
+        cand = _rank2_unit(Fl + delta.reshape(3, 3))
+        JtJ2, Jtr2, cost2 = _lm_system(cand, x1, x2, w)
+        if cost2 < cost:
+            small = (cost - cost2) <= 1e-12 * cost
+            Fl, JtJ, Jtr, cost = cand, JtJ2, Jtr2, cost2
+            if small:
+                break
+            mu *= 0.3
+        else:
+            mu *= 10.0
+        if mu > 1e6:
+            break
+    T1 = np.array([[rs, 0, -rs * m1[0]], [0, rs, -rs * m1[1]], [0, 0, 1.0]])
+    T2m = np.array([[rs, 0, -rs * m2[0]], [0, rs, -rs * m2[1]], [0, 0, 1.0]])
+    Fm = T2m.T @ Fl @ T1
+    nrm = np.linalg.norm(Fm)
+    if not (nrm > 0.0) or not np.isfinite(nrm):
+        return None, False
+    sgn = -1.0 if Fm[2, 2] < 0 else 1.0  # fundamental_estimator.h:611-613
+    return (sgn * Fm / nrm).reshape(9), True
+
+
+def sym_epipolar_sq(pts, Fm):
+    """squaredSymmetricEpipolarDistance (fundamental_estimator.h:224-252) for all points"""
+    e = np.asarray(Fm, dtype=np.float64).reshape(3, 3)
+    x1, y1, x2, y2 = pts[:, 0], pts[:, 1], pts[:, 2], pts[:, 3]
+    rxc = e[0, 0] * x2 + e[1, 0] * y2 + e[2, 0]
+    ryc = e[0, 1] * x2 + e[1, 1] * y2 + e[2, 1]
+    rwc = e[0, 2] * x2 + e[1, 2] * y2 + e[2, 2]
+    r = x1 * rxc + y1 * ryc + rwc
+    rx = e[0, 0] * x1 + e[0, 1] * y1 + e[0, 2]
+    ry = e[1, 0] * x1 + e[1, 1] * y1 + e[1, 2]
+    a, b = rxc * rxc + ryc * ryc, rx * rx + ry * ry
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return r * r * (a + b) / (a * b)
+
+
+
 class Score:
     __slots__ = ("inliers", "value")
 
@@ -246,8 +350,12 @@ class ProgressiveXOracle:
         self.pts = np.ascontiguousarray(pts, dtype=np.float64)
         self.N = self.pts.shape[0]
         self.t = family
-        self.m = 4 if family == H else 2                       # Estimator::sampleSize()
-        self.nonminimal_size = 4 if family == H else 2         # Estimator::nonMinimalSampleSize()
+        self.m = {H: 4, F: 7}.get(family, 2)                   # Estimator::sampleSize()
+        self.nonminimal_size = {H: 4, F: 7}.get(family, 2)     # Estimator::nonMinimalSampleSize()
+        # FundamentalMatrixEstimator(minimum_inlier_ratio_in_validity_check = 0.5, use_degensac = true); the nested
+        # estimator of DEGENSAC uses the plane-and-parallax solver over a fixed homography, ratio 0 and no DEGENSAC
+        self.sym_ratio, self.use_degensac, self.pp_H = 0.5, family == F, None
+        self.degensac_stats = [0, 0]                           # H-degenerate samples seen / models replaced
         self.point_weights = None if point_weights is None else np.ascontiguousarray(point_weights, dtype=np.float64)
         self.thr, self.conf, self.lam, self.max_tanimoto = threshold, confidence, lam, max_tanimoto
         self.max_iters, self.min_inliers = max_iters, min_inliers
@@ -289,7 +397,52 @@ class ProgressiveXOracle:
         reads weights_[point index] (solver_vanishing_point_two_lines.h:203); the line solver never reads them."""
         if self.t == H:
             return O.fit_h_nonminimal(self.pts, idx, weights)
+        if self.t == F:
+            return fit_f_nonminimal(self.pts, idx, weights)
         return O.fit_nonminimal(self.t, self.pts, idx, weights if self.t == VP else None)
+
+    # ---- FundamentalMatrixEstimator::isValidModel (fundamental_estimator.h:268-334) + applyDegensac (:341-572) --------
+    def _model_is_valid(self, model, solver_valid, sample, nested_seed):
+        """returns (valid, model): the model may have been replaced by DEGENSAC"""
+        if self.t != F or not solver_valid:
+            return bool(solver_valid), model
+        tt = 3.0 / 2.0 * self.thr
+        r2, _ = O.residual_matrix(self.t, self.pts, model, tt * tt, want_mask=False)
+        sampson_inliers = np.flatnonzero(r2[0] < tt * tt)
+        sym_count = int(np.sum(sym_epipolar_sq(self.pts[sampson_inliers], model) < tt * tt))
+        minimum = max(7, int(len(sampson_inliers) * self.sym_ratio))  # :303-304
+        if sym_count < minimum:
+            return False, model
+        if not (self.use_degensac and self.pp_H is None):
+            return True, model
+        degenerate, Hm, _ = O.h_degenerate_sample(self.pts, sample, model)
+        if not degenerate:
+            return True, model
+        self.degensac_stats[0] += 1
+        Hflat = Hm.reshape(9)
+        f_inliers = [int(i) for i in sampson_inliers]
+        q = self.pts[f_inliers]
+        t1 = Hflat[0] * q[:, 0] + Hflat[1] * q[:, 1] + Hflat[2]
+        t2 = Hflat[3] * q[:, 0] + Hflat[4] * q[:, 1] + Hflat[5]
+        t3 = Hflat[6] * q[:, 0] + Hflat[7] * q[:, 1] + Hflat[8]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            err = (q[:, 2] - t1 / t3) ** 2 + (q[:, 3] - t2 / t3) ** 2
+        h_inliers = [f_inliers[k] for k in np.flatnonzero(err < 4.0)]  # homography_threshold_ = 2 px (:93)
+        if len(h_inliers) < 4:
+            return False, model
+        Hfit, ok = O.fit_h_nonminimal(self.pts, h_inliers)
+        if not ok:
+            return False, model
+        nested = ProgressiveXOracle(self.pts, threshold=tt, confidence=0.99, lam=0.0, max_tanimoto=self.max_tanimoto,
+                                    max_iters=5000, min_inliers=self.min_inliers, max_models=1, napsac=False,
+                                    exponent=self.exponent, seed=0, graph=None, family=F)
+        nested.pp_H, nested.m, nested.sym_ratio, nested.use_degensac = Hfit, 2, 0.0, False
+        nested.max_local_optimization_number = 10  # gcr/settings.h:72 (progressive_x.h's 50 is not applied here)
+        model2 = nested.propose(nested_seed & M64)
+        if model2 is not None and len(nested.proposal_inliers) > len(f_inliers):
+            self.degensac_stats[1] += 1
+            return True, model2
+        return True, model
 
     def _lo_labeling(self, model):  # GCRANSAC.h:914-1022
         d, e0, e1 = O.lo_unary_terms(self.t, self.pts, model, self.thr, self.lam)
@@ -389,17 +542,32 @@ class ProgressiveXOracle:
                 sample = main.sample(pool, self.m)
                 if sample is None:
                     continue
+                if self.pp_H is not None:  # DEGENSAC's nested estimator: FundamentalMatrixPlaneParallaxSolver
+                    pm, pn = O.solve_plane_parallax(self.pts, np.asarray([sample], dtype=np.int64), self.pp_H)
+                    if pn[0] > 0:
+                        found = ([pm[0].copy()], 1, sample)
+                        break
+                    continue
                 models, n, sv, mv = O.solve_minimal(self.t, self.pts, np.asarray([sample], dtype=np.int64))
                 if not sv[0]:
                     continue
                 if n[0] > 0:
-                    found = (models[0, 0].copy(), int(mv[0]))
+                    found = ([models[0, j].copy() for j in range(int(n[0]))], int(mv[0]), sample)
                     break
             self.iteration_number += unsuccessful
             if found is not None:
-                model, model_valid = found
-                sc = self._score(model, T2, best_score.inliers)
-                if best_score.value < sc.value and model_valid:  # :441-447
+                candidates, solver_valid, sample = found
+                for j, model in enumerate(candidates):  # :373-470, every model the sample produced
+                    sc = self._score(model, T2, best_score.inliers)
+                    if not best_score.value < sc.value:
+                        continue
+                    nested_seed = round_seed * 7919 + self.iteration_number * 31 + j
+                    valid, replaced = self._model_is_valid(model, solver_valid, sample, nested_seed)
+                    if not valid:
+                        continue
+                    if replaced is not model:  # :450-457 re-score the model DEGENSAC put in its place
+                        model = replaced
+                        sc = self._score(model, T2, best_score.inliers)
                     best_model, best_score = model, sc
                     do_lo = self.iteration_number > self.min_iteration_number_before_lo and best_score.inliers > self.m
                     max_iteration = self._iteration_number_for(best_score.inliers, log_probability)
@@ -504,6 +672,10 @@ class ProgressiveXOracle:
         total_iterations, unaccepted = 0, 0
         for it in range(10):  # :272 hard cap
             model = self.propose((self.seed * 1000003 + it) & M64)
+            if os.environ.get("PXO_LOG"):  # same fields as the driver's do_logging line
+                print(f"[pxo] proposal {it + 1}: {'found' if model is not None else 'none'}, {len(self.proposal_inliers)} inliers, "
+                      f"{self.iteration_number} iterations, {self.lo_number} LO runs, {self.graph_cut_number} graph cuts, "
+                      f"DEGENSAC {self.degensac_stats[1]}/{self.degensac_stats[0]}")
             if model is None:
                 continue
             total_iterations += self.iteration_number
@@ -556,4 +728,19 @@ def find_points_family(family, rows, weights, threshold, conf, spatial_coherence
                             max_tanimoto=maximum_tanimoto_similarity, max_iters=max_iters, min_inliers=minimum_point_number,
                             max_models=maximum_model_number, napsac=napsac, exponent=scoring_exponent, seed=seed, graph=graph,
                             family=family, point_weights=weights if family == VP else None, prosac=(sampler_id == 1))
+    return px.run()
+
+
+def find_two_view_motions(corrs, threshold, conf, spatial_coherence_weight, maximum_tanimoto_similarity, max_iters,
+                          minimum_point_number, maximum_model_number, sampler_id, scoring_exponent, seed, graph=None,
+                          image_sizes=None):
+    """findTwoViewMotions_ (src/pyprogressivex/src/progressivex_python.cpp:535-666) on the sequential loop: seven-point
+    solver with the oriented-epipolar filter, symmetric-epipolar validity, DEGENSAC, eight-point + LM non-minimal fit.
+    The reference takes `scoring_exponent` (:554) and never applies it -- there is no setScoringExponent call in this entry,
+    unlike :276 / :399 / :513 -- so the scorer keeps its default exponent 2."""
+    px = ProgressiveXOracle(corrs, threshold=threshold, confidence=conf, lam=spatial_coherence_weight,
+                            max_tanimoto=maximum_tanimoto_similarity, max_iters=max_iters, min_inliers=minimum_point_number,
+                            max_models=maximum_model_number, napsac=(sampler_id == 3), exponent=2, seed=seed,
+                            graph=graph, family=F, prosac=(sampler_id == 1),
+                            pnapsac_sizes=image_sizes if sampler_id == 2 else None)
     return px.run()

@@ -122,3 +122,55 @@ def test_driver_equals_sequential_loop_progressive_napsac():
     kw = dict(threshold=2.0, conf=0.9, spatial_coherence_weight=0.0, maximum_tanimoto_similarity=0.4, max_iters=300,
               minimum_point_number=40, maximum_model_number=-1, sampler_id=2, scoring_exponent=2)
     assert _compare(corrs, 60.0, (1, 2, 3), **kw) == 3
+
+
+@pytest.mark.parametrize("scene", ["book", "breadcube", "cubetoy"])
+def test_driver_equals_sequential_loop_on_adelaide_f(scene):
+    """findTwoViewMotions with the reference's AdelaideF call (dataset_comparison/adelaideF.ipynb) against the sequential
+    loop: seven-point solver with up to three models per sample, oriented-epipolar and symmetric-epipolar validity,
+    DEGENSAC with its nested plane-and-parallax GC-RANSAC, eight-point + LM fits, Progressive NAPSAC, LO cuts and
+    alpha-expansion at lambda = 0.5 (the reference's own gco / BK build on the oracle side). Same instance count and
+    per-point labels; models within the 1e-5 contract."""
+    from oracle import px_sequential as seq
+    corrs = G[f"{scene}_corrs"]
+    with _native.Context(0) as ctx:
+        ctx.upload_points(_native.MODEL_F, corrs)
+        graph = ctx.knn_graph(50.0, 5)
+    kw = dict(threshold=0.75, conf=0.5, spatial_coherence_weight=0.5, neighborhood_ball_radius=50.0,
+              maximum_tanimoto_similarity=0.4, max_iters=10000, minimum_point_number=7, maximum_model_number=4,
+              sampler_id=2, scoring_exponent=1.0)
+    agree = 0
+    for seed in (2, 4):
+        models, labels = pyprogressivex.findTwoViewMotions(corrs, 640, 480, 640, 480, seed=seed, **kw)
+        m_o, l_o = seq.find_two_view_motions(corrs, 0.75, 0.5, 0.5, 0.4, 10000, 7, 4, 2, 1.0, seed, graph,
+                                             image_sizes=(640.0, 480.0, 640.0, 480.0))
+        M = models.shape[0] // 3
+        same = M == m_o.shape[0] and np.array_equal(labels, l_o.astype(np.int32))
+        if same and M:
+            a, b = models.reshape(M, 9), m_o
+            same = bool(np.all(np.abs(a - b).max(1) <= 1e-5 * np.abs(b).max(1)))
+        agree += same
+    assert agree == 2
+
+
+def test_fundamental_fit_equals_its_numpy_restatement():
+    """k_fit_f (normalised eight-point, rank 2, Levenberg-Marquardt on the weighted Sampson error) against
+    oracle/px_sequential.fit_f_nonminimal on ground-truth structures and small samples of a reference scene."""
+    from oracle import px_sequential as seq
+    corrs, ref = G["breadcube_corrs"], G["breadcube_labels"]
+    rng = np.random.default_rng(0)
+    sets = [np.flatnonzero(ref == k) for k in range(1, int(ref.max()) + 1)]
+    sets += [rng.choice(s, 14, replace=False) for s in sets for _ in range(3)]
+    sets += [rng.choice(len(corrs), 30, replace=False), np.arange(7)]
+    w = rng.uniform(0.2, 1.0, len(sets[0]))
+    with _native.Context(0) as ctx:
+        ctx.upload_points(_native.MODEL_F, corrs)
+        got, ok = ctx.fit_nonminimal(sets)
+        got_w, ok_w = ctx.fit_nonminimal([sets[0]], w)
+    for k, st in enumerate(sets):
+        want, ok_o = seq.fit_f_nonminimal(corrs, st)
+        assert bool(ok[k]) == ok_o
+        if ok_o:
+            np.testing.assert_allclose(got[k], want, rtol=0, atol=1e-9)
+    want, _ = seq.fit_f_nonminimal(corrs, sets[0], w)
+    np.testing.assert_allclose(got_w[0], want, rtol=0, atol=1e-9)

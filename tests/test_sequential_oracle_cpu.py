@@ -67,3 +67,19 @@ def test_sequential_oracle_vanishing_points_and_lines():
         members = pts[labels == k]
         d = np.abs(members @ models[k, :2] + models[k, 2]) / np.linalg.norm(models[k, :2])
         assert len(members) >= 40 and np.median(d) < 2.0
+
+
+@pytest.mark.parametrize("scene,bar", [("book", 0.08), ("breadcube", 0.08)])
+def test_sequential_oracle_on_adelaide_f(scene, bar):
+    """the F family of the sequential oracle (seven-point solver, validity tests, DEGENSAC, eight-point + LM fits) with
+    the notebook's call: adelaideF.ipynb prints book 0.032, breadcube 0.017"""
+    from oracle import px_sequential as seq
+    corrs, ref = G[f"{scene}_corrs"], G[f"{scene}_labels"]
+    graph = syn.knn_graph(corrs, 50.0, 5)
+    errs = []
+    for seed in (2, 3):
+        models, labels = seq.find_two_view_motions(corrs, 0.75, 0.5, 0.5, 0.4, 10000, 7, 4, 2, 1.0, seed, graph,
+                                                   image_sizes=(640.0, 480.0, 640.0, 480.0))
+        assert models.shape[1] == 9
+        errs.append(misclassification(labels.astype(int), ref))
+    assert max(errs) <= bar, errs
