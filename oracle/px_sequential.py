@@ -33,7 +33,7 @@ import numpy as np
 
 from . import oracle as O
 
-H, F, VP, LINE = 0, 1, 3, 4
+H, F, PNP, VP, LINE = 0, 1, 2, 3, 4
 M64 = (1 << 64) - 1
 
 
@@ -337,6 +337,91 @@ def sym_epipolar_sq(pts, Fm):
 
 
 
+# ---- 6D poses -------------------------------------------------------------------------------------------------------
+def _exp_left(w, R):
+    """R <- exp([w]x) R (Rodrigues), as k_fit_pnp's rodrigues_left"""
+    th2 = float(w @ w)
+    th = math.sqrt(th2)
+    a, b = (1.0, 0.5) if th < 1e-8 else (math.sin(th) / th, (1.0 - math.cos(th)) / th2)
+    Kx = np.array([[0.0, -w[2], w[1]], [w[2], 0.0, -w[0]], [-w[1], w[0], 0.0]])
+    return (np.eye(3) + a * Kx + b * (Kx @ Kx)) @ R
+
+
+def _pnp_system(R, t, q):
+    """J^T J (6x6), J^T r and the cost of the reprojection residuals for rows q = [u v X Y Z]"""
+    Xr = q[:, 2:] @ R.T
+    p = Xr + t
+    with np.errstate(divide="ignore", invalid="ignore"):
+        iz = 1.0 / p[:, 2]
+        ru, rv = p[:, 0] * iz - q[:, 0], p[:, 1] * iz - q[:, 1]
+        a0 = np.column_stack([iz, np.zeros(len(q)), -p[:, 0] * iz * iz])
+        a1 = np.column_stack([np.zeros(len(q)), iz, -p[:, 1] * iz * iz])
+        z = np.zeros(len(q))
+        Jw = np.stack([np.column_stack([z, Xr[:, 2], -Xr[:, 1]]), np.column_stack([-Xr[:, 2], z, Xr[:, 0]]),
+                       np.column_stack([Xr[:, 1], -Xr[:, 0], z])], axis=1)  # [n, 3 rows, 3 cols] = -[Xr]x
+        J0 = np.column_stack([np.einsum("nr,nrc->nc", a0, Jw), a0])
+        J1 = np.column_stack([np.einsum("nr,nrc->nc", a1, Jw), a1])
+        JtJ = J0.T @ J0 + J1.T @ J1
+        Jtr = J0.T @ ru + J1.T @ rv
+        cost = float(ru @ ru + rv @ rv)
+    return JtJ, Jtr, cost
+
+
+def fit_pnp_nonminimal(pts, idx):
+    """The GPU engine's non-minimal pose fit (pxb_fit_fp.cu, k_fit_pnp) restated with numpy: DLT on normalised 3D points,
+    projection of the left 3x3 onto SO(3), then Levenberg-Marquardt on the reprojection error with rollback -- the objective
+    of the reference's PnPBundleAdjustment (solver_pnp_bundle_adjustment.h:108-225 -> OpenCV EPnP + LM, not on disk)."""
+    q = pts[np.asarray(idx, dtype=np.int64)]
+    n = len(q)
+    if n < 6:
+        return None, False
+    c = q[:, 2:].mean(0)
+    md = float(np.mean(np.sqrt(((q[:, 2:] - c) ** 2).sum(1))))
+    sc = math.sqrt(3.0) / md if md > 0 else 1.0
+    X = (q[:, 2:] - c) * sc
+    u, v = q[:, 0], q[:, 1]
+    one, zero = np.ones(n), np.zeros((n, 4))
+    Xh = np.column_stack([X, one])
+    A = np.concatenate([np.column_stack([Xh, zero, -u[:, None] * Xh]), np.column_stack([zero, Xh, -v[:, None] * Xh])])
+    evals, evecs = np.linalg.eigh(A.T @ A)
+    Pn = evecs[:, 0].reshape(3, 4)
+    M = Pn[:, :3]
+    sg = -1.0 if np.linalg.det(M) < 0 else 1.0
+    U, S, Vt = np.linalg.svd(sg * M)
+    scale = float(S.mean())
+    if not scale > 0:
+        return None, False
+    R = U @ np.diag([1.0, 1.0, np.sign(np.linalg.det(U @ Vt)) or 1.0]) @ Vt
+    tn = sg * Pn[:, 3] / scale
+    t = tn / sc - R @ c
+    pose, best = (R, t), (R, t)
+    if not (np.all(np.isfinite(R)) and np.all(np.isfinite(t))):
+        return None, False
+    mu, best_cost = 1e-4, float("inf")
+    for _ in range(14):
+        R, t = pose
+        JtJ, Jtr, cost = _pnp_system(R, t, q)
+        if cost <= best_cost:
+            best_cost, best = cost, pose
+            mu *= 0.3
+        else:
+            pose = best
+            mu *= 10.0
+            continue
+        M6 = JtJ.copy()
+        M6[np.diag_indices(6)] *= (1.0 + mu)
+        try:
+            dlt = np.linalg.solve(M6, -Jtr)
+        except np.linalg.LinAlgError:
+            continue
+        if np.all(np.abs(dlt) <= 1e6):
+            pose = (_exp_left(dlt[:3], R), t + dlt[3:])
+    R, t = best
+    out = np.column_stack([R, t]).reshape(12)
+    return (out, True) if np.all(np.isfinite(out)) else (None, False)
+
+
+
 class Score:
     __slots__ = ("inliers", "value")
 
@@ -350,8 +435,8 @@ class ProgressiveXOracle:
         self.pts = np.ascontiguousarray(pts, dtype=np.float64)
         self.N = self.pts.shape[0]
         self.t = family
-        self.m = {H: 4, F: 7}.get(family, 2)                   # Estimator::sampleSize()
-        self.nonminimal_size = {H: 4, F: 7}.get(family, 2)     # Estimator::nonMinimalSampleSize()
+        self.m = {H: 4, F: 7, PNP: 3}.get(family, 2)           # Estimator::sampleSize()
+        self.nonminimal_size = {H: 4, F: 7, PNP: 4}.get(family, 2)  # Estimator::nonMinimalSampleSize()
         # FundamentalMatrixEstimator(minimum_inlier_ratio_in_validity_check = 0.5, use_degensac = true); the nested
         # estimator of DEGENSAC uses the plane-and-parallax solver over a fixed homography, ratio 0 and no DEGENSAC
         self.sym_ratio, self.use_degensac, self.pp_H = 0.5, family == F, None
@@ -399,6 +484,8 @@ class ProgressiveXOracle:
             return O.fit_h_nonminimal(self.pts, idx, weights)
         if self.t == F:
             return fit_f_nonminimal(self.pts, idx, weights)
+        if self.t == PNP:  # PerspectiveNPointEstimator::isWeightingApplicable() is false: weights never reach the solver
+            return fit_pnp_nonminimal(self.pts, idx)
         return O.fit_nonminimal(self.t, self.pts, idx, weights if self.t == VP else None)
 
     # ---- FundamentalMatrixEstimator::isValidModel (fundamental_estimator.h:268-334) + applyDegensac (:341-572) --------
@@ -743,4 +830,28 @@ def find_two_view_motions(corrs, threshold, conf, spatial_coherence_weight, maxi
                             max_models=maximum_model_number, napsac=(sampler_id == 3), exponent=2, seed=seed,
                             graph=graph, family=F, prosac=(sampler_id == 1),
                             pnapsac_sizes=image_sizes if sampler_id == 2 else None)
+    return px.run()
+
+
+def find_6d_poses(image_points, world_points, K, threshold, conf, spatial_coherence_weight, maximum_tanimoto_similarity,
+                  max_iters, minimum_point_number, maximum_model_number, seed, graph=None):
+    """find6DPoses_ (src/pyprogressivex/src/progressivex_python.cpp:41-171) on the sequential loop: image points are
+    normalised by K^-1, the threshold by the mean focal length (:96-98); P3P minimal solver (up to four poses per
+    sample), uniform sampler, default exponent. `graph` is the neighbourhood graph of the RAW [u v X Y Z] rows."""
+    Km = np.asarray(K, dtype=np.float64).reshape(3, 3)
+    m = Km.reshape(9)
+    c00, c01, c02 = m[4] * m[8] - m[5] * m[7], m[5] * m[6] - m[3] * m[8], m[3] * m[7] - m[4] * m[6]
+    idet = 1.0 / (m[0] * c00 + m[1] * c01 + m[2] * c02)  # Eigen Matrix3d::inverse(): cofactors / determinant
+    Kinv = np.array([c00, m[2] * m[7] - m[1] * m[8], m[1] * m[5] - m[2] * m[4],
+                     c01, m[0] * m[8] - m[2] * m[6], m[2] * m[3] - m[0] * m[5],
+                     c02, m[1] * m[6] - m[0] * m[7], m[0] * m[4] - m[1] * m[3]]) * idet
+    img = np.asarray(image_points, dtype=np.float64)
+    rows = np.empty((len(img), 5))
+    rows[:, 0] = Kinv[0] * img[:, 0] + Kinv[1] * img[:, 1] + Kinv[2] * 1
+    rows[:, 1] = Kinv[3] * img[:, 0] + Kinv[4] * img[:, 1] + Kinv[5] * 1
+    rows[:, 2:] = np.asarray(world_points, dtype=np.float64)
+    f = 0.5 * (Km[0, 0] + Km[1, 1])
+    px = ProgressiveXOracle(rows, threshold=threshold / f, confidence=conf, lam=spatial_coherence_weight,
+                            max_tanimoto=maximum_tanimoto_similarity, max_iters=max_iters, min_inliers=minimum_point_number,
+                            max_models=maximum_model_number, napsac=False, exponent=2, seed=seed, graph=graph, family=PNP)
     return px.run()

@@ -174,3 +174,51 @@ def test_fundamental_fit_equals_its_numpy_restatement():
             np.testing.assert_allclose(got[k], want, rtol=0, atol=1e-9)
     want, _ = seq.fit_f_nonminimal(corrs, sets[0], w)
     np.testing.assert_allclose(got_w[0], want, rtol=0, atol=1e-9)
+
+
+def test_driver_equals_sequential_loop_on_tless_poses():
+    """find6DPoses with the reference's example call (examples/example_multi_pose_6d.ipynb, T-LESS scene) against the
+    sequential loop: P3P with up to four poses per sample, uniform sampler, LO cuts and alpha-expansion at lambda = 0.1 on
+    the neighbourhood graph of the raw [u v X Y Z] rows, DLT + LM non-minimal fits. Same instance count and labels,
+    poses within the 1e-5 contract, on at least two of three seeds."""
+    from oracle import px_sequential as seq
+    pts, K = G["tless_points"], G["tless_K"]
+    raw = np.ascontiguousarray(np.column_stack([pts[:, :2], pts[:, 2:]]))
+    with _native.Context(0) as ctx:
+        ctx.upload_points(_native.MODEL_PNP, raw)
+        graph = ctx.knn_graph(20.0, 5)
+    agree = 0
+    for seed in (1, 2, 3):
+        poses, labels = pyprogressivex.find6DPoses(pts[:, :2], pts[:, 2:], K, 4.0, seed=seed)
+        m_o, l_o = seq.find_6d_poses(pts[:, :2], pts[:, 2:], K, 4.0, 0.9, 0.1, 0.9, 400, 6, -1, seed, graph)
+        M = poses.shape[0] // 3
+        same = M == m_o.shape[0] and np.array_equal(labels, l_o.astype(np.int32))
+        if same and M:
+            a, b = poses.reshape(M, 12), m_o
+            same = bool(np.all(np.abs(a - b).max(1) <= 1e-5 * np.abs(b).max(1)))
+        agree += same
+    # seeds 1, 3, 4, 5: eight or nine instances, all 1886 labels identical; seed 2: same instance count, 10 labels differ
+    # (a near-tie between two poses of the same object decided by 1e-9 differences of the LM fits)
+    assert agree >= 2
+
+
+def test_pose_fit_equals_its_numpy_restatement():
+    """k_fit_pnp (normalised DLT, projection onto SO(3), Levenberg-Marquardt with rollback) against
+    oracle/px_sequential.fit_pnp_nonminimal on the inliers of the two ground-truth poses of the T-LESS scene."""
+    from oracle import px_sequential as seq
+    pts, K, gt = G["tless_points"], G["tless_K"], G["tless_poses"]
+    rows = syn.normalize_pnp_points(pts[:, :2], pts[:, 2:], K)
+    sets = []
+    for g in gt:
+        p = rows[:, 2:] @ g[:, :3].T + g[:, 3]
+        err = np.hypot(p[:, 0] / p[:, 2] - rows[:, 0], p[:, 1] / p[:, 2] - rows[:, 1])
+        inl = np.flatnonzero(err < 6.0 / (0.5 * (K[0, 0] + K[1, 1])))
+        sets += [inl, inl[:12], inl[::3]]
+    with _native.Context(0) as ctx:
+        ctx.upload_points(_native.MODEL_PNP, rows)
+        got, ok = ctx.fit_nonminimal(sets)
+    for k, st in enumerate(sets):
+        want, ok_o = seq.fit_pnp_nonminimal(rows, st)
+        assert bool(ok[k]) == ok_o
+        if ok_o:
+            np.testing.assert_allclose(got[k], want, rtol=1e-7, atol=1e-7 * np.abs(want).max())
