@@ -22,8 +22,12 @@ local-optimisation sampler), the neighbourhood graph (handed in by the caller), 
 best model" in place of the reference's accidental two-buffer ping-pong. Families: homographies (non-minimal fit:
 column-pivoted Householder QR here, 8x8 normal equations on the GPU -- ~1e-9 apart, which is why models are compared with
 a tolerance and labels exactly), vanishing points and 2D lines (findVanishingPoints_ / findLines_,
-progressivex_python.cpp:306-535; weights of the vanishing-point solver are indexed by point). F and PnP are not covered:
-the oracle has no restatement of their non-minimal solvers."""
+progressivex_python.cpp:306-535; weights of the vanishing-point solver are indexed by point), fundamental matrices
+(findTwoViewMotions_, :535-666: every model of a seven-point sample is scored, isValidModel = symmetric-epipolar recount +
+DEGENSAC with its nested plane-and-parallax GC-RANSAC, fundamental_estimator.h:268-572) and 6D poses (find6DPoses_, :41-171:
+up to four P3P poses per sample). The reference's non-minimal F / pose solvers (PoseLib, OpenCV EPnP) are not on disk: for
+those two the fits restate the GPU engine's own algorithms (eight-point + LM on the Sampson error, DLT + LM on the
+reprojection error) in numpy, so the comparison checks the control flow around them, not the solvers against the reference."""
 from __future__ import annotations
 
 import math
