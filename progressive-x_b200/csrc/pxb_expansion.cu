@@ -2,8 +2,11 @@
 // optimisation, both on one GPU min-cut engine.
 //
 //   k_maxflow                 lock-free asynchronous push-relabel (Hong & He) on a CSR residual graph, alternating with
-//                             exact backward-BFS global relabelling, one persistent cooperative kernel per cut (grid
-//                             barriers only around the BFS levels, no host round trips).
+//                             exact backward-BFS global relabelling, one persistent cooperative kernel per cut (no host
+//                             round trips). Graphs that fit in shared memory are relabelled by block 0 alone (queue
+//                             BFS, four lanes per node, bottom-up levels while the frontier is the larger side, two
+//                             block barriers per level, one grid barrier per relabel); larger ones by a grid-wide
+//                             level-synchronous BFS. DESIGN.md section 4 has the measurements behind each choice.
 //   pxb_lo_graph_cut          GCRANSAC::labeling                       gcr/GCRANSAC.h:964-1018
 //   launch_alpha_expansion    GCoptimization::expansion / oneExpansionIteration / alpha_expansion
 //                                                                     gcr/GCoptimization.cpp:1003-1086,1239-1318
