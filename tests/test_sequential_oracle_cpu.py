@@ -104,3 +104,31 @@ def test_sequential_oracle_on_tless_poses():
         best = [min(pose_error(g, e) for e in est) for g in gt]
         good += all(ang < 15.0 and tr < 40.0 for ang, tr in best)
     assert good >= 1
+
+
+def test_restated_fits_recover_planted_models():
+    """known answers for the numpy restatements of the engine's F and pose fits (oracle/px_sequential.py)"""
+    from oracle import px_sequential as seq
+    rows, lab, F_true = syn.plane_dominated_pair(150, 150, 0.0, 3)
+    Fm, ok = seq.fit_f_nonminimal(rows, np.arange(len(rows)))
+    assert ok and abs(np.linalg.norm(Fm) - 1.0) < 1e-12 and Fm[8] >= 0
+    x1 = np.column_stack([rows[:, :2], np.ones(len(rows))])
+    x2 = np.column_stack([rows[:, 2:], np.ones(len(rows))])
+    assert np.abs(np.einsum("ni,ij,nj->n", x2, Fm.reshape(3, 3), x1)).max() < 1e-6  # noise-free: every point on its epipolar line
+    assert abs(np.linalg.det(Fm.reshape(3, 3))) < 1e-12                                # rank 2
+    Ft = F_true / np.linalg.norm(F_true) * np.sign(F_true[2, 2])
+    np.testing.assert_allclose(Fm.reshape(3, 3), Ft, atol=1e-6)
+    assert seq.fit_f_nonminimal(rows, np.arange(7)) == (None, False)
+    # pose: project random 3D points with a planted [R|t]
+    rng = np.random.default_rng(2)
+    a = rng.normal(0, 0.3, 3)
+    R, _ = np.linalg.qr(np.eye(3) + np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]]))
+    R *= np.sign(np.linalg.det(R))
+    t = np.array([0.1, -0.2, 5.0])
+    X = rng.uniform(-1, 1, (40, 3))
+    p = X @ R.T + t
+    pts = np.column_stack([p[:, 0] / p[:, 2], p[:, 1] / p[:, 2], X])
+    pose, ok = seq.fit_pnp_nonminimal(pts, np.arange(40))
+    assert ok
+    np.testing.assert_allclose(pose.reshape(3, 4), np.column_stack([R, t]), atol=1e-8)
+    assert seq.fit_pnp_nonminimal(pts, np.arange(5)) == (None, False)
