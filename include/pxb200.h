@@ -269,6 +269,38 @@ int pxb_find_lines(pxb_ctx *ctx, const double *points, const double *weights, in
                    double maximum_tanimoto_similarity, size_t max_iters, size_t minimum_point_number,
                    int maximum_model_number, size_t sampler_id, double scoring_exponent, int do_logging, uint64_t seed);
 
+/* ---- multi-GPU exchange steps ----------------------------------------------------------------- */
+/* One process per GPU; NCCL over NVLink / NVSwitch. The reference is single-process and has no counterpart: these are
+ * the two places where the sharded path has a real exchange step. NCCL is resolved at run time (dlopen of the libnccl.so.2
+ * the process already holds, else the system copy); without it every entry below returns PXB_ERR_UNSUPPORTED.
+ * `nccl_comm` is an ncclComm_t passed as void*: either one the caller already owns (all ranks must hold the same
+ * communicator with one rank per GPU) or one made by pxb_nccl_comm_init from an id that rank 0 obtained with
+ * pxb_nccl_unique_id and distributed by any means (torch.distributed object broadcast in pyprogressivex.sharding). */
+int pxb_nccl_version(int *version);
+int pxb_nccl_unique_id(void *id128 /* 128 bytes out */);
+int pxb_nccl_comm_init(pxb_ctx *ctx, const void *id128, int world, int rank, void **nccl_comm_out);
+int pxb_nccl_comm_destroy(void *nccl_comm);
+
+/* Hypothesis-block sharding of ONE problem (BASELINE configs C3 / C5). After pxb_ctx_set_shard(ctx, comm) the task-level
+ * entry points pxb_find_* on this context are COLLECTIVE: every rank of the communicator calls the same function with the
+ * same arguments (the points are replicated). Rank 0 runs GCRANSAC::run's control flow (gcr/GCRANSAC.h:283-518); for every
+ * block of minimal samples it broadcasts the sample indices, rank r solves and scores samples [r*S, (r+1)*S) of the block
+ * against all N points, and one ncclAllGather returns every slice's models, validity flags and (count, value, shared) in
+ * sample order. Scores do not depend on the batch or device that evaluated them, so models and labels are bit-identical
+ * to the single-GPU run with the same seed. Local optimisation, IRLS and PEARL (N x <= 50 work) stay on rank 0; the final
+ * (models, labeling) is broadcast, so every rank returns the same result. NULL detaches the communicator. */
+int pxb_ctx_set_shard(pxb_ctx *ctx, void *nccl_comm);
+int pxb_shard_info(pxb_ctx *ctx, int *world, int *rank);
+
+/* Independent problems sharded over ranks (BASELINE config C4): merges the surviving instances of every rank's pairs.
+ * Every rank passes `pairs_per_rank` records -- counts [P] int32 (-1 = empty slot), models [P, max_models, model_size]
+ * float64, labels [P, n_points] int32 -- and receives all ranks' records rank-major: counts_out [world * P], models_out
+ * [world * P, max_models, model_size], labels_out [world * P, n_points]. One ncclAllGather. */
+int pxb_allgather_instances(pxb_ctx *ctx, void *nccl_comm, int64_t pairs_per_rank, int64_t n_points, int32_t model_size,
+                            int32_t max_models, const int32_t *counts_host, const double *models_host,
+                            const int32_t *labels_host, int32_t *counts_out_host, double *models_out_host,
+                            int32_t *labels_out_host);
+
 #ifdef __cplusplus
 }
 #endif

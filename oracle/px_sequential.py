@@ -761,6 +761,7 @@ class ProgressiveXOracle:
     # ---- progressive_x.h:251-489 ------------------------------------------------------------------------------------
     def run(self):
         total_iterations, unaccepted = 0, 0
+        first_model_stat = 0  # statistics.inliers_of_each_model.size(): grows whenever an instance is added as the only one
         for it in range(10):  # :272 hard cap
             model = self.propose((self.seed * 1000003 + it) & M64)
             if os.environ.get("PXO_LOG"):  # same fields as the driver's do_logging line
@@ -778,17 +779,18 @@ class ProgressiveXOracle:
                 continue
             self.models.append(model.copy())
             self.prefs.append(pref)
-            first_stat = 0
             if len(self.models) == 1:  # :375-385
                 self.labeling[:] = 1
                 self.labeling[self.proposal_inliers] = 0
-                first_stat = 1
+                first_model_stat += 1
             else:
                 self.pearl()
             if self.models:  # updateCompoundModel: max over the stored (stale) preference vectors
                 self.compound = O.compound_max(np.stack(self.prefs))
-            if len(self.models) == 1 and first_stat:
-                unseen = self.predicted_unseen_inliers(total_iterations, first_stat)
+            # :447-457 branches on models.size() == 1 AFTER the optimisation (PEARL may have pruned the compound set back to
+            # one instance) and passes inliers_of_each_model.size() -- a model count -- as the inlier number (:451 quirk)
+            if len(self.models) == 1:
+                unseen = self.predicted_unseen_inliers(total_iterations, first_model_stat)
             else:
                 unseen = self.predicted_unseen_inliers(total_iterations, self.N - self.pearl_outliers)
             if unseen < self.min_inliers:

@@ -346,6 +346,7 @@ struct Settings {
 	double pp_H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 	const double *rows_host = nullptr; // the caller's [N, dim] rows (DEGENSAC's seven-point test runs on the host)
 	bool do_logging = false;
+	bool allow_shard = true; // nested (DEGENSAC) runs never shard
 	uint64_t seed = 1;
 	// gcransac::utils::Settings defaults (gcr/settings.h:66-86) as overridden by progressive_x.h:64-71
 	size_t min_iteration_number = 20, min_iteration_number_before_lo = 20, max_local_optimization_number = 50,
@@ -411,7 +412,10 @@ class Driver {
 		grid_layers_.resize(4);
 		for (int l = 0; l < 4; ++l) grid_layers_[l].build(rows, (size_t)N_, 4, s_.sizes, cells[l]);
 	}
-	int run();
+	int run(int setup_status = PXB_OK);
+	int run_local();
+	bool sharded() const { return ctx_->shard_comm != nullptr && s_.allow_shard && !s_.plane_parallax; }
+	bool is_worker() const { return sharded() && ctx_->shard_rank != 0; }
 	const std::vector<Instance> &instances() const { return models_; }
 	const std::vector<int64_t> &labeling() const { return labeling_; }
 
@@ -457,6 +461,12 @@ class Driver {
 		PXB_TRY(ctx_->cpref.reserve(sizeof(double) * (size_t)N_));
 		PXB_CUDA(cudaMemcpyAsync(ctx_->cpref.ptr, compound_pref_.data(), sizeof(double) * (size_t)N_, cudaMemcpyHostToDevice,
 		                         ctx_->stream));
+		if (sharded()) { // the other ranks score against the same compound preference vector
+			ShardMsg h{};
+			h.op = kShardCompound;
+			PXB_TRY(shard_send(h, nullptr, 0));
+			PXB_TRY(shard_broadcast(ctx_, ctx_->cpref.ptr, sizeof(double) * (size_t)N_, 0));
+		}
 		PXB_CUDA(cudaStreamSynchronize(ctx_->stream));
 		return PXB_OK;
 	}
@@ -488,6 +498,118 @@ class Driver {
 		}
 		return PXB_OK;
 	}
+	// ---- hypothesis-block sharding over NCCL (pxb_ctx_set_shard) ------------------------------------------
+	// Rank 0 (the coordinator) runs the whole control flow; the other ranks serve "solve and score your slice of this block"
+	// requests. A hypothesis' models / flags / (count, value, shared) do not depend on which GPU or batch evaluated them
+	// (fixed reduction topology, DESIGN.md "Summation order"), so the sharded run takes exactly the decisions of the
+	// single-GPU run for the same seed. Everything that is not a block refill (LO, IRLS, PEARL: N x <= 50 work) stays on
+	// the coordinator -- "replicas only" is not even needed for it.
+	enum ShardOp : int32_t { kShardBlock = 1, kShardCompound = 2, kShardDone = 3 };
+	struct ShardMsg { // 64-byte header in front of the sample indices of a block
+		int32_t op, has_compound;
+		int64_t want;
+		double T2;
+		int64_t result;
+		int64_t pad[4];
+	};
+	struct ShardRecord { // one rank's slice of a block inside the all-gather buffer (fields 16-byte aligned)
+		size_t models, cnt, val, shr, n, sv, mv, bytes;
+	};
+	ShardRecord shard_record(size_t S) const {
+		auto up16 = [](size_t v) { return (v + 15) & ~size_t(15); };
+		ShardRecord r;
+		size_t at = 0;
+		r.models = at, at += up16(sizeof(double) * S * maxsol_ * ms_);
+		r.cnt = at, at += up16(sizeof(int64_t) * S * maxsol_);
+		r.val = at, at += up16(sizeof(double) * S * maxsol_);
+		r.shr = at, at += up16(sizeof(double) * S * maxsol_);
+		r.n = at, at += up16(sizeof(int32_t) * S);
+		r.sv = at, at += up16(S);
+		r.mv = at, at += up16(S);
+		r.bytes = at;
+		return r;
+	}
+	size_t shard_block_cap() const { // largest block a refill may ask for: identical on every rank
+		size_t B = 512 * (size_t)ctx_->shard_world;
+		if (const char *e = getenv("PXB_BLOCK_SIZE")) {
+			const long v = atol(e);
+			if (v >= 1) B = (size_t)v;
+		}
+		return B;
+	}
+	size_t shard_msg_bytes() const { return sizeof(ShardMsg) + sizeof(int64_t) * shard_block_cap() * (size_t)m_; }
+	// solves and scores this rank's slice of the block whose samples sit behind the header in ctx->shard_msg, then gathers
+	int shard_compute_and_gather(size_t want, double T2, bool has_compound) {
+		const size_t G = (size_t)ctx_->shard_world, r = (size_t)ctx_->shard_rank;
+		const size_t S = (want + G - 1) / G, lo = std::min(want, r * S), ks = std::min(want, lo + S) - lo;
+		const ShardRecord rec = shard_record(S);
+		PXB_TRY(ctx_->shard_rec.reserve(rec.bytes * G));
+		char *mine = ctx_->shard_rec.as<char>() + rec.bytes * r;
+		PXB_CUDA(cudaMemsetAsync(mine, 0, rec.bytes, ctx_->stream));
+		if (ks > 0) {
+			const int64_t *smp = reinterpret_cast<const int64_t *>(ctx_->shard_msg.as<char>() + sizeof(ShardMsg)) + lo * m_;
+			double *models = reinterpret_cast<double *>(mine + rec.models);
+			PXB_TRY(launch_solve_minimal(ctx_, smp, (int64_t)ks, models, reinterpret_cast<int32_t *>(mine + rec.n),
+			                             reinterpret_cast<uint8_t *>(mine + rec.sv), reinterpret_cast<uint8_t *>(mine + rec.mv)));
+			PXB_TRY(launch_score_compound(ctx_, models, (int64_t)(ks * maxsol_), T2, has_compound ? ctx_->cpref.as<double>() : nullptr,
+			                              reinterpret_cast<int64_t *>(mine + rec.cnt), reinterpret_cast<double *>(mine + rec.val),
+			                              reinterpret_cast<double *>(mine + rec.shr)));
+		}
+		return shard_allgather(ctx_, ctx_->shard_rec.ptr, rec.bytes);
+	}
+	int shard_send(const ShardMsg &h, const int64_t *samples, size_t n_samples) { // coordinator: header (+ samples) to all ranks
+		const size_t bytes = shard_msg_bytes();
+		PXB_TRY(ctx_->shard_msg.reserve(bytes));
+		shard_host_.resize(bytes);
+		std::memcpy(shard_host_.data(), &h, sizeof(h));
+		if (n_samples) std::memcpy(shard_host_.data() + sizeof(h), samples, sizeof(int64_t) * n_samples);
+		PXB_TRY(api_h2d(ctx_, ctx_->shard_msg.ptr, shard_host_.data(), sizeof(h) + sizeof(int64_t) * n_samples));
+		return shard_broadcast(ctx_, ctx_->shard_msg.ptr, bytes, 0);
+	}
+	int solve_and_score_sharded(const std::vector<int64_t> &samples, size_t want, double T2, std::vector<double> &models,
+	                            std::vector<int32_t> &n, std::vector<uint8_t> &sv, std::vector<uint8_t> &mv,
+	                            std::vector<int64_t> &cnt, std::vector<double> &val, std::vector<double> &shr) {
+		Scoped t(prof_, "refill(sharded solve+score)");
+		if (want > shard_block_cap()) {
+			set_error("sharded block of %zu samples exceeds the agreed capacity %zu", want, shard_block_cap());
+			return PXB_ERR_STATE;
+		}
+		ShardMsg h{};
+		h.op = kShardBlock;
+		h.has_compound = models_.empty() ? 0 : 1;
+		h.want = (int64_t)want;
+		h.T2 = T2;
+		PXB_TRY(shard_send(h, samples.data(), want * (size_t)m_));
+		PXB_TRY(shard_compute_and_gather(want, T2, h.has_compound != 0));
+		const size_t G = (size_t)ctx_->shard_world, S = (want + G - 1) / G;
+		const ShardRecord rec = shard_record(S);
+		PXB_TRY(ctx_->reserve_pinned(rec.bytes * G));
+		PXB_CUDA(cudaMemcpyAsync(ctx_->pinned, ctx_->shard_rec.ptr, rec.bytes * G, cudaMemcpyDeviceToHost, ctx_->stream));
+		PXB_TRY(api_sync(ctx_));
+		const size_t KS = want * maxsol_;
+		cnt.resize(KS);
+		val.resize(KS);
+		shr.resize(KS);
+		for (size_t r = 0; r < G; ++r) { // slices are contiguous in sample order: rank r holds samples [r S, r S + ks)
+			const size_t lo = std::min(want, r * S), ks = std::min(want, lo + S) - lo;
+			if (!ks) continue;
+			const char *src = reinterpret_cast<const char *>(ctx_->pinned) + rec.bytes * r;
+			std::memcpy(models.data() + lo * maxsol_ * ms_, src + rec.models, sizeof(double) * ks * maxsol_ * ms_);
+			std::memcpy(cnt.data() + lo * maxsol_, src + rec.cnt, sizeof(int64_t) * ks * maxsol_);
+			std::memcpy(val.data() + lo * maxsol_, src + rec.val, sizeof(double) * ks * maxsol_);
+			std::memcpy(shr.data() + lo * maxsol_, src + rec.shr, sizeof(double) * ks * maxsol_);
+			std::memcpy(n.data() + lo, src + rec.n, sizeof(int32_t) * ks);
+			std::memcpy(sv.data() + lo, src + rec.sv, ks);
+			std::memcpy(mv.data() + lo, src + rec.mv, ks);
+		}
+		++shard_blocks_;
+		return PXB_OK;
+	}
+	int shard_worker(); // ranks > 0: serve requests until the coordinator sends the result
+	int shard_finish(int result); // coordinator: result (model count or a negative status) + payload to all ranks
+	std::vector<unsigned char> shard_host_;
+	size_t shard_blocks_ = 0;
+
 	int score_models(const double *models, int64_t K, double T2, std::vector<int64_t> &cnt, std::vector<double> &val,
 	                 std::vector<double> &shr) {
 		cnt.resize(K);
@@ -504,6 +626,7 @@ class Driver {
 	int solve_and_score(const std::vector<int64_t> &samples, size_t want, double T2, std::vector<double> &models,
 	                    std::vector<int32_t> &n, std::vector<uint8_t> &sv, std::vector<uint8_t> &mv, std::vector<int64_t> &cnt,
 	                    std::vector<double> &val, std::vector<double> &shr) {
+		if (sharded()) return solve_and_score_sharded(samples, want, T2, models, n, sv, mv, cnt, val, shr);
 		Scoped t(prof_, "refill(solve+score)");
 		const int64_t K = (int64_t)want, KS = K * maxsol_;
 		PXB_TRY(ctx_->idx.reserve(sizeof(int64_t) * (size_t)K * m_));
@@ -847,6 +970,7 @@ int Driver::apply_degensac(std::vector<double> &model, const int64_t *sample, ui
 	ns.use_degensac = false;    // FundamentalMatrixEstimator<PlaneParallax, EightPoint>(0.0, false)
 	ns.sym_epipolar_ratio = 0.0;
 	ns.do_logging = false;
+	ns.allow_shard = false;
 	Driver nested(ctx_, ns);
 	std::vector<double> model2;
 	bool found = false;
@@ -976,6 +1100,7 @@ int Driver::propose(uint64_t round_seed, std::vector<double> &model_out, bool &f
 	// Block size of the replay. Any value gives the same result for the same seed (the sample stream does not depend
 	// on it); PXB_BLOCK_SIZE=1 *is* the reference's sequential loop and is what tests/test_gpu_e2e.py compares against.
 	size_t B = 512, Bmin = 32;
+	if (sharded()) B *= (size_t)ctx_->shard_world; // every rank still sees up to 512 samples per refill
 	if (const char *e = getenv("PXB_BLOCK_SIZE")) {
 		const long v = atol(e);
 		if (v >= 1) B = Bmin = (size_t)v;
@@ -1227,13 +1352,91 @@ size_t Driver::predicted_unseen_inliers(size_t iterations, size_t compound_inlie
 	return static_cast<size_t>(std::round((double)unseen_point_number * inlier_ratio));
 }
 
-// px/include/progressive_x.h:251-489
-int Driver::run() {
+// ---- sharded runs: the request loop of ranks > 0 and the final broadcast ------------------------------------------------
+int Driver::shard_worker() {
+	bool has_compound = false;
+	const size_t bytes = shard_msg_bytes();
+	PXB_TRY(ctx_->shard_msg.reserve(bytes));
+	for (;;) {
+		PXB_TRY(shard_broadcast(ctx_, ctx_->shard_msg.ptr, bytes, 0));
+		ShardMsg h;
+		PXB_CUDA(cudaMemcpyAsync(&h, ctx_->shard_msg.ptr, sizeof(h), cudaMemcpyDeviceToHost, ctx_->stream));
+		PXB_CUDA(cudaStreamSynchronize(ctx_->stream));
+		if (h.op == kShardBlock) {
+			if (h.want < 0 || (size_t)h.want > shard_block_cap()) {
+				set_error("sharded block request of %lld samples exceeds the agreed capacity", (long long)h.want);
+				return PXB_ERR_STATE;
+			}
+			PXB_TRY(shard_compute_and_gather((size_t)h.want, h.T2, h.has_compound != 0 && has_compound));
+			++shard_blocks_;
+		} else if (h.op == kShardCompound) {
+			PXB_TRY(ctx_->cpref.reserve(sizeof(double) * (size_t)N_));
+			PXB_TRY(shard_broadcast(ctx_, ctx_->cpref.ptr, sizeof(double) * (size_t)N_, 0));
+			has_compound = true;
+		} else if (h.op == kShardDone) {
+			if (h.result < 0) {
+				set_error("the coordinator rank reported status %lld", (long long)h.result);
+				return (int)h.result;
+			}
+			const size_t M = (size_t)h.result, pay = sizeof(double) * M * ms_ + sizeof(int64_t) * (size_t)N_;
+			PXB_TRY(ctx_->staging.reserve(pay));
+			PXB_TRY(shard_broadcast(ctx_, ctx_->staging.ptr, pay, 0));
+			std::vector<unsigned char> host(pay);
+			PXB_CUDA(cudaMemcpyAsync(host.data(), ctx_->staging.ptr, pay, cudaMemcpyDeviceToHost, ctx_->stream));
+			PXB_CUDA(cudaStreamSynchronize(ctx_->stream));
+			models_.assign(M, Instance());
+			for (size_t k = 0; k < M; ++k) {
+				models_[k].model.resize(ms_);
+				std::memcpy(models_[k].model.data(), host.data() + sizeof(double) * k * ms_, sizeof(double) * ms_);
+			}
+			labeling_.resize((size_t)N_);
+			std::memcpy(labeling_.data(), host.data() + sizeof(double) * M * ms_, sizeof(int64_t) * (size_t)N_);
+			return PXB_OK;
+		} else {
+			set_error("unknown shard request %d", h.op);
+			return PXB_ERR_STATE;
+		}
+	}
+}
+
+int Driver::shard_finish(int result) {
+	ShardMsg h{};
+	h.op = kShardDone;
+	h.result = result < 0 ? result : (int64_t)models_.size();
+	PXB_TRY(shard_send(h, nullptr, 0));
+	if (result < 0) return api_sync(ctx_);
+	const size_t M = models_.size(), pay = sizeof(double) * M * ms_ + sizeof(int64_t) * (size_t)N_;
+	std::vector<unsigned char> host(pay);
+	for (size_t k = 0; k < M; ++k) std::memcpy(host.data() + sizeof(double) * k * ms_, models_[k].model.data(), sizeof(double) * ms_);
+	std::memcpy(host.data() + sizeof(double) * M * ms_, labeling_.data(), sizeof(int64_t) * (size_t)N_);
+	PXB_TRY(ctx_->staging.reserve(pay));
+	PXB_CUDA(cudaMemcpyAsync(ctx_->staging.ptr, host.data(), pay, cudaMemcpyHostToDevice, ctx_->stream));
+	PXB_TRY(shard_broadcast(ctx_, ctx_->staging.ptr, pay, 0));
+	return api_sync(ctx_);
+}
+
+int Driver::run(int setup_status) {
 	PXB_CUDA(cudaSetDevice(ctx_->device)); // the driver launches kernels directly as well: bind this host thread
+	if (setup_status != PXB_OK) { // the coordinator failed before the loop: release the other ranks
+		if (sharded() && !is_worker()) (void)shard_finish(setup_status);
+		return setup_status;
+	}
+	if (!sharded()) return run_local();
+	if (is_worker()) return shard_worker();
+	const int rc = run_local();
+	const int rc2 = shard_finish(rc);
+	return rc != PXB_OK ? rc : rc2;
+}
+
+// px/include/progressive_x.h:251-489
+int Driver::run_local() {
 	labeling_.assign((size_t)N_, 0);
 	compound_pref_.assign((size_t)N_, 0.0);
 	models_.clear();
 	size_t number_of_ransac_iterations = 0, unaccepted = 0;
+	// statistics.inliers_of_each_model.size(): one entry is appended whenever an instance is added while it is the only one
+	// (:375-381); the reference passes this COUNT as the compound inlier number whenever one instance remains (:447-451)
+	size_t inliers_of_each_model_size = 0;
 	for (size_t it = 0; it < 10; ++it) { // :272 hard cap
 		std::vector<double> model;
 		bool found = false;
@@ -1256,11 +1459,10 @@ int Driver::run() {
 		inst.model = model;
 		inst.pref = pref;
 		models_.push_back(std::move(inst));
-		size_t first_model_inliers_stat = 0;
 		if (models_.size() == 1) { // :375-385
 			std::fill(labeling_.begin(), labeling_.end(), 1);
 			for (int64_t i : proposal_inliers_) labeling_[(size_t)i] = 0;
-			first_model_inliers_stat = 1; // inliers_of_each_model.size(), a model count (:451 quirk)
+			++inliers_of_each_model_size;
 		} else {
 			PXB_TRY(pearl()); // :390-396
 		}
@@ -1273,8 +1475,8 @@ int Driver::run() {
 			PXB_TRY(upload_compound());
 		}
 		size_t unseen;
-		if (models_.size() == 1 && first_model_inliers_stat)
-			unseen = predicted_unseen_inliers(number_of_ransac_iterations, first_model_inliers_stat);
+		if (models_.size() == 1) // evaluated AFTER the optimisation: also when PEARL pruned the set back to one instance
+			unseen = predicted_unseen_inliers(number_of_ransac_iterations, inliers_of_each_model_size);
 		else
 			unseen = predicted_unseen_inliers(number_of_ransac_iterations, (size_t)N_ - pearl_outliers_);
 		if (s_.do_logging)
@@ -1284,6 +1486,13 @@ int Driver::run() {
 		if (models_.size() >= s_.max_models) break;      // :472
 	}
 	return PXB_OK;
+}
+
+// the caller's model buffer must hold every instance: the labeling refers to all of them
+int check_model_capacity(int64_t M, int64_t max_models_out) {
+	if (M <= max_models_out) return PXB_OK;
+	set_error("models_out holds %lld models but %lld instances were found", (long long)max_models_out, (long long)M);
+	return PXB_ERR_ARGUMENT;
 }
 
 int run_two_view(pxb_ctx *ctx, int type, const double *corr, int64_t N, int64_t *labeling_out, double *models_out,
@@ -1320,20 +1529,24 @@ int run_two_view(pxb_ctx *ctx, int type, const double *corr, int64_t N, int64_t 
 	if (seed == 0) seed = (uint64_t)std::chrono::high_resolution_clock::now().time_since_epoch().count();
 	s.seed = seed;
 	Driver drv(ctx, s);
-	if (s.progressive_napsac) drv.build_grid_layers(corr);
-	if (lambda > 0.0 || sampler_id == 3) {
-		Scoped t(drv.prof_, "build_graph");
-		PXB_TRY(drv.build_graph(radius, graph_degree()));
+	int setup = PXB_OK;
+	if (!drv.is_worker()) { // sampler state and the neighbourhood graph are only needed where the control flow runs
+		if (s.progressive_napsac) drv.build_grid_layers(corr);
+		if (lambda > 0.0 || sampler_id == 3) {
+			Scoped t(drv.prof_, "build_graph");
+			setup = drv.build_graph(radius, graph_degree());
+		}
 	}
 	{
 		Scoped t(drv.prof_, "run (inclusive)");
-		PXB_TRY(drv.run());
+		PXB_TRY(drv.run(setup));
 	}
 	drv.prof_.print();
 	const auto &inst = drv.instances();
 	const int ms = model_size(type);
 	const int64_t M = (int64_t)inst.size();
-	for (int64_t k = 0; k < std::min(M, max_models_out); ++k)
+	PXB_TRY(check_model_capacity(M, max_models_out));
+	for (int64_t k = 0; k < M; ++k)
 		std::memcpy(models_out + k * ms, inst[k].model.data(), sizeof(double) * ms);
 	std::memcpy(labeling_out, drv.labeling().data(), sizeof(int64_t) * (size_t)N);
 	return (int)M;
@@ -1372,11 +1585,13 @@ int run_points_family(pxb_ctx *ctx, int type, const double *rows, const double *
 	if (seed == 0) seed = (uint64_t)std::chrono::high_resolution_clock::now().time_since_epoch().count();
 	s.seed = seed;
 	Driver drv(ctx, s);
-	if (lambda > 0.0 || s.napsac) PXB_TRY(drv.build_graph(radius, graph_degree()));
-	PXB_TRY(drv.run());
+	int setup = PXB_OK;
+	if (!drv.is_worker() && (lambda > 0.0 || s.napsac)) setup = drv.build_graph(radius, graph_degree());
+	PXB_TRY(drv.run(setup));
 	const auto &inst = drv.instances();
 	const int64_t M = (int64_t)inst.size();
-	for (int64_t k = 0; k < std::min(M, max_models_out); ++k) std::memcpy(models_out + k * 3, inst[k].model.data(), sizeof(double) * 3);
+	PXB_TRY(check_model_capacity(M, max_models_out));
+	for (int64_t k = 0; k < M; ++k) std::memcpy(models_out + k * 3, inst[k].model.data(), sizeof(double) * 3);
 	std::memcpy(labeling_out, drv.labeling().data(), sizeof(int64_t) * (size_t)N);
 	return (int)M;
 }
@@ -1467,12 +1682,14 @@ int pxb_find_6d_poses(pxb_ctx *ctx, const double *image_points, const double *wo
 	s.seed = seed;
 	PXB_TRY(pxb_upload_points(ctx, PXB_MODEL_PNP, raw.data(), N));
 	Driver drv(ctx, s);
-	if (spatial_coherence_weight > 0.0) PXB_TRY(drv.build_graph(neighborhood_ball_radius, graph_degree()));
-	PXB_TRY(pxb_upload_points(ctx, PXB_MODEL_PNP, nrm.data(), N));
-	PXB_TRY(drv.run());
+	int setup = PXB_OK;
+	if (!drv.is_worker() && spatial_coherence_weight > 0.0) setup = drv.build_graph(neighborhood_ball_radius, graph_degree());
+	if (setup == PXB_OK) setup = pxb_upload_points(ctx, PXB_MODEL_PNP, nrm.data(), N);
+	PXB_TRY(drv.run(setup));
 	const auto &inst = drv.instances();
 	const int64_t M = (int64_t)inst.size();
-	for (int64_t k = 0; k < std::min(M, max_models_out); ++k) std::memcpy(poses_out + k * 12, inst[k].model.data(), sizeof(double) * 12);
+	PXB_TRY(check_model_capacity(M, max_models_out));
+	for (int64_t k = 0; k < M; ++k) std::memcpy(poses_out + k * 12, inst[k].model.data(), sizeof(double) * 12);
 	std::memcpy(labeling_out, drv.labeling().data(), sizeof(int64_t) * (size_t)N);
 	return (int)M;
 }

@@ -108,6 +108,11 @@ struct pxb_ctx {
 	};
 	std::vector<PendingCopy> pending;
 	int reserve_pinned(size_t bytes);
+	// hypothesis-block sharding (pxb_ctx_set_shard, pxb_nccl.cu): an ncclComm_t owned by the caller; when set, the task-level
+	// find* entry points are collective over its ranks
+	void *shard_comm = nullptr;
+	int shard_world = 1, shard_rank = 0;
+	pxb::DevBuf shard_msg, shard_rec;
 };
 
 namespace pxb {
@@ -119,6 +124,9 @@ uint64_t csr_content_key(pxb_ctx *ctx, int64_t N, const int32_t *off, const int3
 int api_h2d(pxb_ctx *ctx, void *dst, const void *src, size_t bytes);
 int api_d2h(pxb_ctx *ctx, void *dst, const void *src, size_t bytes);
 int api_sync(pxb_ctx *ctx);
+// NCCL exchange steps of the sharded driver (pxb_nccl.cu): device buffers, asynchronous on ctx->stream
+int shard_broadcast(pxb_ctx *ctx, void *buf_dev, size_t bytes, int root);
+int shard_allgather(pxb_ctx *ctx, void *recv_dev, size_t bytes_per_rank);
 int pearl_label_device(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t L1, double lambda, double label_cost,
                        const int32_t *csr_off_host, const int32_t *csr_idx_host, const int32_t *init_labels_host,
                        int32_t *labels_out_host, double *energy_out);

@@ -19,12 +19,18 @@ from . import _native
 from ._native import Context, PxbError  # noqa: F401
 
 __all__ = ["findHomographies", "findTwoViewMotions", "findFundamentalMatrices", "find6DPoses", "findVanishingPoints",
-           "findLines", "Context"]
+           "findLines", "findHomographiesBatch", "distributed", "Context"]
+
+import threading as _threading
 
 _contexts = {}
-
+_contexts_guard = _threading.Lock()
 
 _worker_pool = {}
+
+# every find* call may add at most this many instances (the outer loop of ProgressiveX::run is capped at 10 proposals,
+# progressive_x.h:272); the native side refuses to truncate if it ever found more
+_MODEL_CAP = 16
 
 
 def _worker_contexts(device: int, n: int):
@@ -35,9 +41,41 @@ def _worker_contexts(device: int, n: int):
 
 
 def _ctx(device: int) -> Context:
-    if device not in _contexts:
-        _contexts[device] = Context(device)
-    return _contexts[device]
+    """The cached per-device context. It is shared by every caller of the find* functions on that device; the calls
+    serialise on Context.lock (a pxb_ctx is not re-entrant). Use findHomographiesBatch for concurrent problems."""
+    with _contexts_guard:
+        if device not in _contexts:
+            _contexts[device] = Context(device)
+        return _contexts[device]
+
+
+_shards = {}
+
+
+def _nccl_shard(device: int):
+    """This rank's NCCL communicator inside libpxb200.so (created on first use; collective over the torch.distributed
+    job: every rank must reach this call)."""
+    from . import sharding
+    if device not in _shards:
+        _shards[device] = sharding.NcclShard(_ctx(device))
+    return _shards[device]
+
+
+class distributed:
+    """Context manager: inside `with pyprogressivex.distributed(device):` the find* calls of this process are
+    COLLECTIVE over the torch.distributed job -- every rank makes the same call with the same arguments, the hypothesis
+    blocks of the problem are split over the ranks' GPUs (pxb_ctx_set_shard) and every rank returns the same result, which
+    is bit-identical to the single-GPU result for the same seed."""
+
+    def __init__(self, device: int = 0):
+        self.shard = _nccl_shard(device)
+
+    def __enter__(self):
+        self.shard.attach()
+        return self.shard
+
+    def __exit__(self, *exc):
+        self.shard.detach()
 
 
 def _two_view(fn_name, corrs, w1, h1, w2, h2, threshold, conf, spatial_coherence_weight, neighborhood_ball_radius,
@@ -52,15 +90,17 @@ def _two_view(fn_name, corrs, w1, h1, w2, h2, threshold, conf, spatial_coherence
     ctx = _ctx(device)
     N = corrs.shape[0]
     labeling = _np.zeros(N, dtype=_np.int64)
-    cap = 16
+    cap = _MODEL_CAP
     models = _np.zeros((cap, 9), dtype=_np.float64)
     fn = getattr(ctx.lib, fn_name)
-    rc = fn(ctx.handle, corrs.ctypes.data_as(_C.c_void_p), N, labeling.ctypes.data_as(_C.c_void_p),
-            models.ctypes.data_as(_C.c_void_p), cap, int(w1), int(h1), int(w2), int(h2),
-            float(spatial_coherence_weight), float(threshold), float(conf), float(neighborhood_ball_radius),
-            float(maximum_tanimoto_similarity), int(max_iters), int(minimum_point_number), int(maximum_model_number),
-            int(sampler_id), float(scoring_exponent), int(bool(do_logging)), int(seed))
-    M = _native._check(rc)
+    with ctx.lock:
+        rc = fn(ctx.handle, corrs.ctypes.data_as(_C.c_void_p), N, labeling.ctypes.data_as(_C.c_void_p),
+                models.ctypes.data_as(_C.c_void_p), cap, int(w1), int(h1), int(w2), int(h2),
+                float(spatial_coherence_weight), float(threshold), float(conf), float(neighborhood_ball_radius),
+                float(maximum_tanimoto_similarity), int(max_iters), int(minimum_point_number), int(maximum_model_number),
+                int(sampler_id), float(scoring_exponent), int(bool(do_logging)), int(seed))
+        M = _native._check(rc)
+    assert M <= cap
     return models[:M].reshape(M * 3, 3).copy(), labeling.astype(_np.int32)
 
 
@@ -137,7 +177,6 @@ def findHomographiesBatch(pairs, w1, h1, w2, h2, distributed=False, workers=8, *
     if not distributed:
         res = solve_many(list(range(len(pairs))))
         return [res[p] for p in range(len(pairs))]
-    import torch
     import torch.distributed as dist
     from . import sharding
     rank, world = dist.get_rank(), dist.get_world_size()
@@ -145,8 +184,8 @@ def findHomographiesBatch(pairs, w1, h1, w2, h2, distributed=False, workers=8, *
     mine = list(sharding.pairs_of_rank(len(pairs), rank, world))
     res = solve_many(mine)
     local = [(p, res[p][0].reshape(-1, 9), res[p][1]) for p in mine]
-    tdev = torch.device("cuda", dev) if dist.get_backend() == "nccl" else None
-    gathered = sharding.gather_instances(local, len(pairs), n_points, 9, 10, tdev)
+    # the exchange step: one ncclAllGather inside libpxb200.so (pxb_allgather_instances) on this rank's context
+    gathered = _nccl_shard(dev).gather_instances(local, len(pairs), n_points, 9, 10)
     return [(m.reshape(-1, 3), lab) for m, lab in gathered]
 
 
@@ -160,15 +199,17 @@ def _find_with_context(ctx, corrs, w1, h1, w2, h2, threshold=4.0, conf=0.5, spat
         raise ValueError("corrs should be an array with dims [n,4], n>=4")
     N = corrs.shape[0]
     labeling = _np.zeros(N, dtype=_np.int64)
-    cap = 16
+    cap = _MODEL_CAP
     models = _np.zeros((cap, 9), dtype=_np.float64)
-    rc = ctx.lib.pxb_find_homographies(ctx.handle, corrs.ctypes.data_as(_C.c_void_p), N, labeling.ctypes.data_as(_C.c_void_p),
-                                       models.ctypes.data_as(_C.c_void_p), cap, int(w1), int(h1), int(w2), int(h2),
-                                       float(spatial_coherence_weight), float(threshold), float(conf),
-                                       float(neighborhood_ball_radius), float(maximum_tanimoto_similarity), int(max_iters),
-                                       int(minimum_point_number), int(maximum_model_number), int(sampler_id),
-                                       float(scoring_exponent), int(bool(do_logging)), int(seed))
-    M = _native._check(rc)
+    with ctx.lock:
+        rc = ctx.lib.pxb_find_homographies(ctx.handle, corrs.ctypes.data_as(_C.c_void_p), N, labeling.ctypes.data_as(_C.c_void_p),
+                                           models.ctypes.data_as(_C.c_void_p), cap, int(w1), int(h1), int(w2), int(h2),
+                                           float(spatial_coherence_weight), float(threshold), float(conf),
+                                           float(neighborhood_ball_radius), float(maximum_tanimoto_similarity), int(max_iters),
+                                           int(minimum_point_number), int(maximum_model_number), int(sampler_id),
+                                           float(scoring_exponent), int(bool(do_logging)), int(seed))
+        M = _native._check(rc)
+    assert M <= cap
     return models[:M].reshape(M * 3, 3).copy(), labeling.astype(_np.int32)
 
 
@@ -188,15 +229,17 @@ def find6DPoses(x1y1, x2y2z2, K, threshold=4.0, conf=0.90, spatial_coherence_wei
     ctx = _ctx(device)
     N = x1y1.shape[0]
     labeling = _np.zeros(N, dtype=_np.int64)
-    cap = 16
+    cap = _MODEL_CAP
     poses = _np.zeros((cap, 12), dtype=_np.float64)
-    rc = ctx.lib.pxb_find_6d_poses(ctx.handle, x1y1.ctypes.data_as(_C.c_void_p), xyz.ctypes.data_as(_C.c_void_p),
-                                   Km.ctypes.data_as(_C.c_void_p), N, labeling.ctypes.data_as(_C.c_void_p),
-                                   poses.ctypes.data_as(_C.c_void_p), cap, float(spatial_coherence_weight),
-                                   float(threshold), float(conf), float(neighborhood_ball_radius),
-                                   float(maximum_tanimoto_similarity), int(max_iters), int(minimum_point_number),
-                                   int(maximum_model_number), int(seed))
-    M = _native._check(rc)
+    with ctx.lock:
+        rc = ctx.lib.pxb_find_6d_poses(ctx.handle, x1y1.ctypes.data_as(_C.c_void_p), xyz.ctypes.data_as(_C.c_void_p),
+                                       Km.ctypes.data_as(_C.c_void_p), N, labeling.ctypes.data_as(_C.c_void_p),
+                                       poses.ctypes.data_as(_C.c_void_p), cap, float(spatial_coherence_weight),
+                                       float(threshold), float(conf), float(neighborhood_ball_radius),
+                                       float(maximum_tanimoto_similarity), int(max_iters), int(minimum_point_number),
+                                       int(maximum_model_number), int(seed))
+        M = _native._check(rc)
+    assert M <= cap
     return poses[:M].reshape(M * 3, 4).copy(), labeling.astype(_np.int32)
 
 
@@ -216,15 +259,17 @@ def _points_family(fn_name, rows, dim, what, weights, w, h, threshold, conf, spa
     ctx = _ctx(device)
     N = rows.shape[0]
     labeling = _np.zeros(N, dtype=_np.int64)
-    cap = 16
+    cap = _MODEL_CAP
     models = _np.zeros((cap, 3), dtype=_np.float64)
     fn = getattr(ctx.lib, fn_name)
-    rc = fn(ctx.handle, rows.ctypes.data_as(_C.c_void_p), None if wts is None else wts.ctypes.data_as(_C.c_void_p), N,
-            labeling.ctypes.data_as(_C.c_void_p), models.ctypes.data_as(_C.c_void_p), cap, int(w), int(h),
-            float(spatial_coherence_weight), float(threshold), float(conf), float(neighborhood_ball_radius),
-            float(maximum_tanimoto_similarity), int(max_iters), int(minimum_point_number), int(maximum_model_number),
-            int(sampler_id), float(scoring_exponent), int(bool(do_logging)), int(seed))
-    M = _native._check(rc)
+    with ctx.lock:
+        rc = fn(ctx.handle, rows.ctypes.data_as(_C.c_void_p), None if wts is None else wts.ctypes.data_as(_C.c_void_p), N,
+                labeling.ctypes.data_as(_C.c_void_p), models.ctypes.data_as(_C.c_void_p), cap, int(w), int(h),
+                float(spatial_coherence_weight), float(threshold), float(conf), float(neighborhood_ball_radius),
+                float(maximum_tanimoto_similarity), int(max_iters), int(minimum_point_number), int(maximum_model_number),
+                int(sampler_id), float(scoring_exponent), int(bool(do_logging)), int(seed))
+        M = _native._check(rc)
+    assert M <= cap
     return models[:M].copy(), labeling.astype(_np.int32)
 
 

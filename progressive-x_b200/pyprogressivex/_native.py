@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 from pathlib import Path
 
 import numpy as np
@@ -94,6 +95,13 @@ def load_library() -> C.CDLL:
     lib.pxb_find_vanishing_points.argtypes = [vp, vp, vp, i64, vp, vp, i64, sz, sz, f64, f64, f64, f64, f64, sz, sz,
                                               C.c_int, sz, f64, C.c_int, u64]
     lib.pxb_find_lines.argtypes = lib.pxb_find_vanishing_points.argtypes
+    lib.pxb_nccl_version.argtypes = [C.POINTER(C.c_int)]
+    lib.pxb_nccl_unique_id.argtypes = [vp]
+    lib.pxb_nccl_comm_init.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(vp)]
+    lib.pxb_nccl_comm_destroy.argtypes = [vp]
+    lib.pxb_ctx_set_shard.argtypes = [vp, vp]
+    lib.pxb_shard_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.pxb_allgather_instances.argtypes = [vp, vp, i64, i64, i32, i32, vp, vp, vp, vp, vp, vp]
     _lib = lib
     return lib
 
@@ -147,6 +155,10 @@ class Context:
         self.handle = h
         self.model_type = None
         self.N = 0
+        # A pxb_ctx is NOT re-entrant (one stream, one resident point set, shared scratch and staging buffers) and ctypes
+        # releases the GIL for the whole C call -- unlike the reference's pybind11 module, which holds it. The find* entry
+        # points take this lock around the native call so that Python threads sharing a context are serialised.
+        self.lock = threading.RLock()
 
     def close(self):
         if getattr(self, "handle", None):

@@ -14,6 +14,7 @@ block's solve.
 """
 from __future__ import annotations
 
+import ctypes as _C
 from typing import Callable, List, Sequence, Tuple
 
 import numpy as np
@@ -109,3 +110,84 @@ def gather_instances(local_results: Sequence[Tuple[int, np.ndarray, np.ndarray]]
         M = int(g_counts[r, slot])
         out.append((g_models[r, slot, :max(M, 0)].copy(), g_labels[r, slot].copy()))
     return out
+
+
+# ---- the native exchange steps (include/pxb200.h "multi-GPU exchange steps"): NCCL inside libpxb200.so --------------------
+class NcclShard:
+    """An ncclComm_t owned by libpxb200.so, one rank per GPU, created from a unique id that rank 0 draws and
+    torch.distributed hands to the other ranks (any backend: this is the only thing torch does on this path).
+
+        shard = NcclShard(ctx)              # inside a torch.distributed job, ctx = this rank's Context
+        shard.attach()                      # find* calls on ctx are now collective, hypothesis blocks split over ranks
+        models, labels = pyprogressivex.find6DPoses(..., seed=1)   # same call, same arguments on every rank
+        shard.detach(); shard.close()
+    """
+
+    def __init__(self, ctx, world: int | None = None, rank: int | None = None, unique_id: bytes | None = None):
+        from . import _native
+        self.ctx, self.lib = ctx, ctx.lib
+        if world is None:
+            dist = _dist()
+            world, rank = dist.get_world_size(), dist.get_rank()
+        self.world, self.rank = int(world), int(rank)
+        if unique_id is None:
+            buf = (_C.c_char * 128)()
+            if self.rank == 0:
+                _native._check(self.lib.pxb_nccl_unique_id(buf))
+            box = [bytes(buf)]
+            if self.world > 1:
+                _dist().broadcast_object_list(box, src=0)
+            unique_id = box[0]
+        comm = _C.c_void_p()
+        _native._check(self.lib.pxb_nccl_comm_init(ctx.handle, unique_id, self.world, self.rank, _C.byref(comm)))
+        self.comm = comm
+
+    def attach(self):
+        from . import _native
+        _native._check(self.lib.pxb_ctx_set_shard(self.ctx.handle, self.comm))
+
+    def detach(self):
+        self.lib.pxb_ctx_set_shard(self.ctx.handle, None)
+
+    def close(self):
+        if getattr(self, "comm", None):
+            self.detach()
+            self.lib.pxb_nccl_comm_destroy(self.comm)
+            self.comm = None
+
+    def __enter__(self):
+        self.attach()
+        return self
+
+    def __exit__(self, *exc):
+        self.detach()
+
+    def gather_instances(self, local_results, n_pairs: int, n_points: int, model_size: int = 9, max_models: int = 10):
+        """Same contract as gather_instances() above, through pxb_allgather_instances (one ncclAllGather of fixed-size
+        records on the context's stream)."""
+        from . import _native
+        world, rank = self.world, self.rank
+        per_rank = (n_pairs + world - 1) // world
+        counts = np.full(per_rank, -1, dtype=np.int32)
+        models = np.zeros((per_rank, max_models, model_size), dtype=np.float64)
+        labels = np.full((per_rank, n_points), -1, dtype=np.int32)
+        for pair, m, lab in local_results:
+            assert pair % world == rank, "pair does not belong to this rank"
+            slot = pair // world
+            M = min(int(m.shape[0]), max_models)
+            counts[slot] = M
+            if M:
+                models[slot, :M] = np.asarray(m[:M], dtype=np.float64).reshape(M, model_size)
+            labels[slot] = np.asarray(lab, dtype=np.int32)
+        g_counts = np.empty(world * per_rank, dtype=np.int32)
+        g_models = np.empty((world * per_rank, max_models, model_size), dtype=np.float64)
+        g_labels = np.empty((world * per_rank, n_points), dtype=np.int32)
+        p = lambda a: a.ctypes.data_as(_C.c_void_p)  # noqa: E731
+        _native._check(self.lib.pxb_allgather_instances(self.ctx.handle, self.comm, per_rank, n_points, model_size, max_models,
+                                                        p(counts), p(models), p(labels), p(g_counts), p(g_models), p(g_labels)))
+        out = []
+        for pair in range(n_pairs):
+            at = (pair % world) * per_rank + pair // world
+            M = int(g_counts[at])
+            out.append((g_models[at, :max(M, 0)].copy(), g_labels[at].copy()))
+        return out
