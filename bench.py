@@ -33,6 +33,9 @@ from pathlib import Path
 
 import numpy as np
 
+# NCCL prints its version banner to stdout when NCCL_DEBUG is VERSION/WARN/INFO: keep stdout for the one JSON line
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "progressive-x_b200"))
@@ -616,23 +619,25 @@ def main():
         n_pairs, n_pts = 256, 5_000
         c4 = [syn.multi_homography_scene(n_pts, n_planes=4, outlier_ratio=0.4, noise=0.5, seed=700 + p)[0] for p in range(n_pairs)]
         c4_kw = dict(C2_KW, spatial_coherence_weight=0.0, sampler_id=0, seed=11, device=local_rank)
-        workers = int(os.environ.get("PXB_BENCH_WORKERS", "4"))
+        workers = int(os.environ.get("PXB_BENCH_WORKERS", "2"))
+        in_flight = int(os.environ.get("PXB_BENCH_IN_FLIGHT", "8"))
         if world == 1:
             pyprogressivex._shards[local_rank] = sharding.NcclShard(ctx, world=1, rank=0)
-        pyprogressivex.findHomographiesBatch(c4[:2 * world * workers], 1024, 768, 1024, 768, workers=workers, distributed=True, **c4_kw)
+        pyprogressivex.findHomographiesBatch(c4[:world * workers * in_flight], 1024, 768, 1024, 768, workers=workers, in_flight=in_flight,
+                                             distributed=True, **c4_kw)
         barrier()
         t0 = time.perf_counter()
-        res = pyprogressivex.findHomographiesBatch(c4, 1024, 768, 1024, 768, workers=workers, distributed=True, **c4_kw)
+        res = pyprogressivex.findHomographiesBatch(c4, 1024, 768, 1024, 768, workers=workers, in_flight=in_flight, distributed=True, **c4_kw)
         barrier()
         c4_s = max_over_ranks(time.perf_counter() - t0)
         # gate: the gathered result of every pair equals the single-rank result (every rank re-solves a stripe locally)
         stripe = list(range(rank, n_pairs, max(world, 4)))
-        local = pyprogressivex.findHomographiesBatch([c4[p] for p in stripe], 1024, 768, 1024, 768, workers=workers, **c4_kw)
+        local = pyprogressivex.findHomographiesBatch([c4[p] for p in stripe], 1024, 768, 1024, 768, workers=workers, in_flight=in_flight, **c4_kw)
         bad = [p for p, r_ in zip(stripe, local) if not same_result(r_, res[p])]
         if bad:
             raise AssertionError(f"C4 parity gate: gathered result differs from the single-rank result for pairs {bad[:8]}")
         extras["batch_c4"] = {"fits_per_s": n_pairs / c4_s, "seconds": c4_s, "pairs": n_pairs, "points_per_pair": n_pts,
-                              "host_threads_per_gpu": workers, "models_found_mean": float(np.mean([m.shape[0] // 3 for m, _ in res])),
+                              "host_threads_per_gpu": workers, "problems_in_flight_per_thread": in_flight, "models_found_mean": float(np.mean([m.shape[0] // 3 for m, _ in res])),
                               "parity_gate": f"gathered == single-rank result on {len(stripe)} pairs per rank: ok",
                               "config": "C4: 256 independent pairs x 5 000 correspondences (4 planes + 40% outliers), pair p on rank "
                                         "p mod N, findHomographies(Python defaults, uniform sampler, lambda=0), instances merged by one "

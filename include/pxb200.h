@@ -269,6 +269,24 @@ int pxb_find_lines(pxb_ctx *ctx, const double *points, const double *weights, in
                    double maximum_tanimoto_similarity, size_t max_iters, size_t minimum_point_number,
                    int maximum_model_number, size_t sampler_id, double scoring_exponent, int do_logging, uint64_t seed);
 
+/* Many independent problems on ONE GPU (BASELINE config C4; with pxb_allgather_instances below: over several GPUs).
+ * Equivalent to calling pxb_find_homographies once per pair -- correspondences[p] is [n_points[p], 4], labeling_out[p]
+ * holds n_points[p] int64, models_out[p] max_models_out * 9 doubles, n_models_out[p] receives the instance count -- with
+ * seed (+ p when per_pair_seed != 0). The library runs the problems on `host_threads` threads with `in_flight` problems
+ * each: every problem is a fiber with its own stream and scratch that yields wherever the sequential driver would block
+ * on its stream, so a couple of host threads keep the GPU busy (pxb_batch.cu). Results are identical to the one-by-one
+ * calls. The reference has no counterpart (it is one problem, one thread: progressivex_python.cpp:173-304). */
+int pxb_find_homographies_batch(int device, int64_t n_pairs, const double *const *correspondences, const int64_t *n_points,
+                                int64_t *const *labeling_out, double *const *models_out, int64_t max_models_out,
+                                int32_t *n_models_out, size_t source_image_width, size_t source_image_height,
+                                size_t destination_image_width, size_t destination_image_height,
+                                double spatial_coherence_weight, double threshold, double confidence,
+                                double neighborhood_ball_radius, double maximum_tanimoto_similarity, size_t max_iters,
+                                size_t minimum_point_number, int maximum_model_number, size_t sampler_id,
+                                double scoring_exponent, uint64_t seed, int per_pair_seed, int host_threads, int in_flight);
+/* Destroys the contexts the batch driver keeps per device between calls. */
+void pxb_batch_release(void);
+
 /* ---- multi-GPU exchange steps ----------------------------------------------------------------- */
 /* One process per GPU; NCCL over NVLink / NVSwitch. The reference is single-process and has no counterpart: these are
  * the two places where the sharded path has a real exchange step. NCCL is resolved at run time (dlopen of the libnccl.so.2

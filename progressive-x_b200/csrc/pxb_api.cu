@@ -97,14 +97,30 @@ int api_d2h(pxb_ctx *ctx, void *dst, const void *src, size_t bytes) {
 	PXB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
 	return PXB_OK;
 }
+int ctx_wait(pxb_ctx *ctx) {
+	if (ctx->yield_fn) {
+		for (;;) {
+			const cudaError_t q = cudaStreamQuery(ctx->stream);
+			if (q == cudaSuccess) return PXB_OK;
+			if (q != cudaErrorNotReady) {
+				set_error("cudaStreamQuery failed: %s", cudaGetErrorString(q));
+				return PXB_ERR_CUDA;
+			}
+			ctx->yield_fn(ctx->yield_arg);
+		}
+	}
+	PXB_CUDA(cudaStreamSynchronize(ctx->stream));
+	return PXB_OK;
+}
+
 int api_sync(pxb_ctx *ctx) {
-	const cudaError_t err = cudaStreamSynchronize(ctx->stream);
+	cudaError_t err = cudaSuccess;
+	if (ctx_wait(ctx) != PXB_OK) err = cudaErrorUnknown;
 	if (err == cudaSuccess)
 		for (const auto &c : ctx->pending) std::memcpy(c.dst, c.src, c.bytes);
 	ctx->pending.clear();
 	ctx->stage_used = 0;
-	PXB_CUDA(err);
-	return PXB_OK;
+	return err == cudaSuccess ? PXB_OK : PXB_ERR_CUDA;
 }
 
 // One PEARL::labeling call on a data-cost matrix that already sits on the device (D_dev, N x L1). Shared by

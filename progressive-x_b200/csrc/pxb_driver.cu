@@ -467,7 +467,7 @@ class Driver {
 			PXB_TRY(shard_send(h, nullptr, 0));
 			PXB_TRY(shard_broadcast(ctx_, ctx_->cpref.ptr, sizeof(double) * (size_t)N_, 0));
 		}
-		PXB_CUDA(cudaStreamSynchronize(ctx_->stream));
+		PXB_TRY(ctx_wait(ctx_));
 		return PXB_OK;
 	}
 	// scores K models that already sit in ctx->models (device) and brings (count, value, shared) back in ONE copy (the
@@ -698,7 +698,7 @@ int Driver::build_graph(double radius, int k) {
 	PXB_TRY(launch_knn_graph(ctx_, radius, k, d_nbr, d_deg));
 	PXB_CUDA(cudaMemcpyAsync(nbr.data(), d_nbr, sizeof(int32_t) * nbr.size(), cudaMemcpyDeviceToHost, ctx_->stream));
 	PXB_CUDA(cudaMemcpyAsync(deg.data(), d_deg, sizeof(int32_t) * deg.size(), cudaMemcpyDeviceToHost, ctx_->stream));
-	PXB_CUDA(cudaStreamSynchronize(ctx_->stream));
+	PXB_TRY(ctx_wait(ctx_));
 	graph_.off.assign((size_t)N_ + 1, 0);
 	for (int64_t i = 0; i < N_; ++i) graph_.off[i + 1] = graph_.off[i] + deg[i];
 	graph_.idx.resize((size_t)graph_.off[N_]);
@@ -806,7 +806,7 @@ int Driver::model_is_valid(std::vector<double> &model, size_t slot_valid, const 
 	PXB_TRY(launch_f_sym_count(ctx_, ctx_->models.as<double>(), T2, tt * tt, ctx_->outB.as<long long>()));
 	long long c[2];
 	PXB_CUDA(cudaMemcpyAsync(c, ctx_->outB.ptr, sizeof(c), cudaMemcpyDeviceToHost, ctx_->stream));
-	PXB_CUDA(cudaStreamSynchronize(ctx_->stream));
+	PXB_TRY(ctx_wait(ctx_));
 	const size_t minimum = std::max<size_t>(7, (size_t)((double)c[0] * s_.sym_epipolar_ratio)); // fundamental_estimator.h:303-304
 	valid = (size_t)c[1] >= minimum;
 	if (!valid) return PXB_OK;
@@ -1361,7 +1361,7 @@ int Driver::shard_worker() {
 		PXB_TRY(shard_broadcast(ctx_, ctx_->shard_msg.ptr, bytes, 0));
 		ShardMsg h;
 		PXB_CUDA(cudaMemcpyAsync(&h, ctx_->shard_msg.ptr, sizeof(h), cudaMemcpyDeviceToHost, ctx_->stream));
-		PXB_CUDA(cudaStreamSynchronize(ctx_->stream));
+		PXB_TRY(ctx_wait(ctx_));
 		if (h.op == kShardBlock) {
 			if (h.want < 0 || (size_t)h.want > shard_block_cap()) {
 				set_error("sharded block request of %lld samples exceeds the agreed capacity", (long long)h.want);
@@ -1383,7 +1383,7 @@ int Driver::shard_worker() {
 			PXB_TRY(shard_broadcast(ctx_, ctx_->staging.ptr, pay, 0));
 			std::vector<unsigned char> host(pay);
 			PXB_CUDA(cudaMemcpyAsync(host.data(), ctx_->staging.ptr, pay, cudaMemcpyDeviceToHost, ctx_->stream));
-			PXB_CUDA(cudaStreamSynchronize(ctx_->stream));
+			PXB_TRY(ctx_wait(ctx_));
 			models_.assign(M, Instance());
 			for (size_t k = 0; k < M; ++k) {
 				models_[k].model.resize(ms_);

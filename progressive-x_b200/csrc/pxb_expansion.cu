@@ -823,7 +823,7 @@ static int solve_min_cut(pxb_ctx *ctx, const FlowGraphHost &g, std::vector<uint8
 	const int32_t *h = h_h0, *flags = h_flags;
 	PXB_CUDA(cudaMemcpyAsync(h_h0, d_h0, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
 	PXB_CUDA(cudaMemcpyAsync(h_flags, d_flags, sizeof(int32_t) * 16, cudaMemcpyDeviceToHost, st));
-	PXB_CUDA(cudaStreamSynchronize(st));
+	PXB_TRY(ctx_wait(ctx));
 	if (flags[7] != 1 || flags[6] == 0) {
 		set_error("max-flow did not converge within %d relabel rounds", kMaxRounds);
 		return PXB_ERR_CUDA;
@@ -940,7 +940,7 @@ static int lo_skeleton(pxb_ctx *ctx, int64_t N, const int32_t *off, const int32_
 	PXB_CUDA(cudaMemcpyAsync(g_lo.pair_fwd, pf.data(), sizeof(int32_t) * (size_t)pairs, cudaMemcpyHostToDevice, st));
 	PXB_CUDA(cudaMemcpyAsync(g_lo.pair_rev, pr.data(), sizeof(int32_t) * (size_t)pairs, cudaMemcpyHostToDevice, st));
 	PXB_CUDA(cudaMemcpyAsync(g_lo.first_off, first_off.data(), sizeof(int32_t) * first_off.size(), cudaMemcpyHostToDevice, st));
-	PXB_CUDA(cudaStreamSynchronize(st)); // the host vectors go out of scope
+	PXB_TRY(ctx_wait(ctx)); // the host vectors go out of scope
 	g_lo.key = key;
 	g_lo.N = N;
 	g_lo.pairs = pairs;
@@ -1034,7 +1034,7 @@ int lo_labeling_device(pxb_ctx *ctx, const double *model_dev, double thr, double
 	int32_t flags[16];
 	PXB_CUDA(cudaMemcpyAsync(seg_host, d_seg, (size_t)N, cudaMemcpyDeviceToHost, st));
 	PXB_CUDA(cudaMemcpyAsync(flags, d_flags, sizeof(flags), cudaMemcpyDeviceToHost, st));
-	PXB_CUDA(cudaStreamSynchronize(st));
+	PXB_TRY(ctx_wait(ctx));
 	if (flags[7] != 1 || flags[6] == 0) {
 		set_error("max-flow did not converge within %d relabel rounds", kMaxRounds);
 		return PXB_ERR_CUDA;
@@ -1292,7 +1292,7 @@ static int exp_skeleton(pxb_ctx *ctx, int64_t N, const int32_t *off, const int32
 	PXB_CUDA(cudaMemcpyAsync(sk.rev, rev.data(), sizeof(int32_t) * ms, cudaMemcpyHostToDevice, st));
 	PXB_CUDA(cudaMemcpyAsync(sk.d_goff, sk.goff.data(), sizeof(int32_t) * (size_t)(N + 1), cudaMemcpyHostToDevice, st));
 	if (E > 0) PXB_CUDA(cudaMemcpyAsync(sk.d_gidx, sk.gidx.data(), sizeof(int32_t) * (size_t)E, cudaMemcpyHostToDevice, st));
-	PXB_CUDA(cudaStreamSynchronize(st)); // the host vectors go out of scope
+	PXB_TRY(ctx_wait(ctx)); // the host vectors go out of scope
 	sk.key = key;
 	sk.N = N;
 	sk.E = E;
@@ -1318,7 +1318,7 @@ int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t
 	ExpSkeleton *skp = nullptr;
 	PXB_TRY(exp_skeleton(ctx, N, csr_off_host, csr_idx_host, skp)); // overlaps the downloads on a cache hit
 	ExpSkeleton &sk = *skp;
-	PXB_CUDA(cudaStreamSynchronize(st));
+	PXB_TRY(ctx_wait(ctx));
 
 	ExpansionProblem P;
 	P.D = D.data();
@@ -1358,7 +1358,7 @@ int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t
 		PXB_CUDA(cudaMemcpyAsync(d_label_count, label_count.data(), sizeof(int32_t) * (size_t)(L1 + 1), cudaMemcpyHostToDevice, st));
 		k_exp_wire_aux<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(N, L1, E, d_lab, d_rank, d_label_off, d_goff, d_arc_off, d_head, d_rev);
 		ctx->launches++;
-		PXB_CUDA(cudaStreamSynchronize(st)); // rank / label_off are reused by the next change
+		PXB_TRY(ctx_wait(ctx)); // rank / label_off are reused by the next change
 		return PXB_OK;
 	};
 	PXB_TRY(push_labelling());
@@ -1400,7 +1400,7 @@ int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t
 			PXB_CUDA(cudaLaunchCooperativeKernel((void *)k_maxflow, dim3(grid), dim3(kMfThreads), args, lc.smem, st));
 			ctx->launches += 2;
 			PXB_CUDA(cudaMemcpyAsync(h_host, d_h0, sizeof(int32_t) * ((size_t)n + 16), cudaMemcpyDeviceToHost, st)); // + flags
-			PXB_CUDA(cudaStreamSynchronize(st));
+			PXB_TRY(ctx_wait(ctx));
 			if (flags_host[7] != 1 || flags_host[6] == 0) {
 				set_error("max-flow did not converge within %d relabel rounds", kMaxRounds);
 				return PXB_ERR_CUDA;
@@ -1446,7 +1446,7 @@ int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t
 	}
 	*energy_out_host = new_energy;
 	PXB_CUDA(cudaMemcpyAsync(labels_out_dev, lab.data(), sizeof(int32_t) * (size_t)N, cudaMemcpyHostToDevice, st));
-	PXB_CUDA(cudaStreamSynchronize(st));
+	PXB_TRY(ctx_wait(ctx));
 	if (stats)
 		fprintf(stderr, "[pxb expansion] labelling: N=%lld L1=%d total %.2f ms = setup %.2f + cuts %.2f + energies %.2f + rewiring %.2f\n",
 		        (long long)N, L1, since(t_call), ms_setup, ms_cut, ms_energy, ms_push);

@@ -320,7 +320,7 @@ int pxb_knn_graph(pxb_ctx *ctx, double radius, int k, int32_t *nbr_out_host, int
 	PXB_TRY(launch_knn_graph(ctx, radius, k, d_nbr, d_deg));
 	PXB_CUDA(cudaMemcpyAsync(nbr_out_host, d_nbr, sizeof(int32_t) * (size_t)N * k, cudaMemcpyDeviceToHost, ctx->stream));
 	PXB_CUDA(cudaMemcpyAsync(deg_out_host, d_deg, sizeof(int32_t) * (size_t)N, cudaMemcpyDeviceToHost, ctx->stream));
-	PXB_CUDA(cudaStreamSynchronize(ctx->stream));
+	PXB_TRY(ctx_wait(ctx));
 	return PXB_OK;
 }
 
@@ -365,7 +365,7 @@ int pxb_fit_nonminimal(pxb_ctx *ctx, int32_t P, const int32_t *off_host, const i
 	}
 	PXB_CUDA(cudaMemcpyAsync(H_out_host, ctx->models.ptr, sizeof(double) * (size_t)P * ms, cudaMemcpyDeviceToHost, ctx->stream));
 	PXB_CUDA(cudaMemcpyAsync(ok_out_host, ctx->outA.ptr, sizeof(int32_t) * (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
-	PXB_CUDA(cudaStreamSynchronize(ctx->stream));
+	PXB_TRY(ctx_wait(ctx));
 	return PXB_OK;
 }
 

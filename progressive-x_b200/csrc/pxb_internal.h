@@ -110,6 +110,10 @@ struct pxb_ctx {
 	int reserve_pinned(size_t bytes);
 	// hypothesis-block sharding (pxb_ctx_set_shard, pxb_nccl.cu): an ncclComm_t owned by the caller; when set, the task-level
 	// find* entry points are collective over its ranks
+	// cooperative waiting (pxb_batch.cu): when set, every wait on this context's stream polls cudaStreamQuery and calls
+	// yield_fn between polls instead of blocking the host thread -- the batch driver runs several problems per host thread
+	void (*yield_fn)(void *) = nullptr;
+	void *yield_arg = nullptr;
 	void *shard_comm = nullptr;
 	int shard_world = 1, shard_rank = 0;
 	pxb::DevBuf shard_msg, shard_rec;
@@ -124,6 +128,8 @@ uint64_t csr_content_key(pxb_ctx *ctx, int64_t N, const int32_t *off, const int3
 int api_h2d(pxb_ctx *ctx, void *dst, const void *src, size_t bytes);
 int api_d2h(pxb_ctx *ctx, void *dst, const void *src, size_t bytes);
 int api_sync(pxb_ctx *ctx);
+// waits for everything queued on ctx->stream (blocking, or yielding to the batch scheduler when the context has one)
+int ctx_wait(pxb_ctx *ctx);
 // NCCL exchange steps of the sharded driver (pxb_nccl.cu): device buffers, asynchronous on ctx->stream
 int shard_broadcast(pxb_ctx *ctx, void *buf_dev, size_t bytes, int root);
 int shard_allgather(pxb_ctx *ctx, void *recv_dev, size_t bytes_per_rank);

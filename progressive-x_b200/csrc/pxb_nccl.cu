@@ -224,7 +224,7 @@ int pxb_allgather_instances(pxb_ctx *ctx, void *nccl_comm, int64_t pairs_per_ran
 		PXB_CUDA(cudaMemcpyAsync(reinterpret_cast<char *>(counts_out_host) + b_cnt * (size_t)r, src + up16(b_mod) + up16(b_lab),
 		                         b_cnt, cudaMemcpyDeviceToHost, ctx->stream));
 	}
-	PXB_CUDA(cudaStreamSynchronize(ctx->stream));
+	PXB_TRY(ctx_wait(ctx));
 	return PXB_OK;
 }
 

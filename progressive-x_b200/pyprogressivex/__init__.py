@@ -127,65 +127,60 @@ def findTwoViewMotions(corrs, w1, h1, w2, h2, threshold=4.0, conf=0.5, spatial_c
 findFundamentalMatrices = findTwoViewMotions
 
 
-def findHomographiesBatch(pairs, w1, h1, w2, h2, distributed=False, workers=8, **kwargs):
-    """BASELINE config C4: many independent image pairs. `pairs` is a list of [N_p, 4] correspondence arrays.
+def findHomographiesBatch(pairs, w1, h1, w2, h2, distributed=False, workers=2, in_flight=8, threshold=4.0, conf=0.5,
+                          spatial_coherence_weight=0.0, neighborhood_ball_radius=200.0, maximum_tanimoto_similarity=0.4,
+                          max_iters=1000, minimum_point_number=10, maximum_model_number=-1, sampler_id=3, scoring_exponent=2,
+                          do_logging=False, seed=0, per_pair_seed=False, device=0):
+    """BASELINE config C4: many independent image pairs. `pairs` is a list of [N_p, 4] correspondence arrays; the other
+    arguments are findHomographies'. Returns [(models, labeling), ...], identical to calling findHomographies per pair.
 
-    One fit is a chain of ~200 short kernels separated by host decisions, so a single problem leaves the GPU mostly
-    idle. Independent problems are therefore run CONCURRENTLY: `workers` host threads, each with its own context (own
-    CUDA stream and scratch), pull pairs from a queue; ctypes releases the GIL for the duration of every C call.
-    Results are identical to the sequential loop (every problem only depends on its own data and seed).
-    With distributed=True (inside a torch.distributed job, one process per GPU) pair p is solved on rank p mod world
-    and the surviving instances of every pair are all-gathered (sharding.gather_instances); every rank returns the
-    full list [(models, labeling), ...]. Pairs must then share one N (padding is the caller's business)."""
-    dev = kwargs.get("device", 0)
+    One fit is a chain of short kernel sequences separated by host decisions, so a single problem leaves the GPU mostly
+    idle. The native batch driver (pxb_find_homographies_batch) runs `workers` host threads with `in_flight` problems each
+    -- every problem is a fiber with its own stream that yields wherever the sequential driver would block -- entirely
+    inside libpxb200.so (no Python threads, no GIL).
+    With distributed=True (inside a torch.distributed job, one process per GPU) pair p is solved on rank p mod world and
+    the surviving instances of every pair are merged by one ncclAllGather (pxb_allgather_instances); every rank returns
+    the full list. Pairs must then share one N (padding is the caller's business)."""
+    import ctypes as C
 
     def solve_many(indices):
         if not indices:
             return {}
-        n_workers = max(1, min(int(workers), len(indices)))
-        if n_workers == 1:
-            return {p: findHomographies(pairs[p], w1, h1, w2, h2, **kwargs) for p in indices}
-        import queue
-        import threading
-        todo = queue.SimpleQueue()
-        for p in indices:
-            todo.put(p)
-        out, errors = {}, []
-
-        pool = _worker_contexts(dev, n_workers)  # contexts (stream + scratch buffers) are kept across batch calls
-
-        def work(ctx):
-            try:
-                while True:
-                    try:
-                        p = todo.get_nowait()
-                    except queue.Empty:
-                        return
-                    out[p] = _find_with_context(ctx, pairs[p], w1, h1, w2, h2, **kwargs)
-            except Exception as e:  # surfaced after the join
-                errors.append(e)
-
-        threads = [threading.Thread(target=work, args=(pool[i],)) for i in range(n_workers)]
-        for t in threads:
-            t.start()
-        for t in threads:
-            t.join()
-        if errors:
-            raise errors[0]
-        return out
+        lib = _native.load_library()
+        arrs = [_np.ascontiguousarray(pairs[p], dtype=_np.float64) for p in indices]
+        for a in arrs:
+            if a.ndim != 2 or a.shape[1] != 4 or a.shape[0] < 4:
+                raise ValueError("corrs should be an array with dims [n,4], n>=4")
+        n = len(arrs)
+        cap = _MODEL_CAP
+        labs = [_np.zeros(a.shape[0], dtype=_np.int64) for a in arrs]
+        mods = [_np.zeros((cap, 9), dtype=_np.float64) for _ in arrs]
+        counts = _np.zeros(n, dtype=_np.int32)
+        npts = _np.array([a.shape[0] for a in arrs], dtype=_np.int64)
+        ptrs = lambda xs: (C.c_void_p * n)(*[x.ctypes.data for x in xs])  # noqa: E731
+        rc = lib.pxb_find_homographies_batch(int(device), n, ptrs(arrs), npts.ctypes.data_as(C.c_void_p), ptrs(labs), ptrs(mods),
+                                             cap, counts.ctypes.data_as(C.c_void_p), int(w1), int(h1), int(w2), int(h2),
+                                             float(spatial_coherence_weight), float(threshold), float(conf),
+                                             float(neighborhood_ball_radius), float(maximum_tanimoto_similarity), int(max_iters),
+                                             int(minimum_point_number), int(maximum_model_number), int(sampler_id),
+                                             float(scoring_exponent), int(seed), int(bool(per_pair_seed)), int(workers),
+                                             int(in_flight))
+        _native._check(rc)
+        return {p: (mods[i][:counts[i]].reshape(int(counts[i]) * 3, 3).copy(), labs[i].astype(_np.int32))
+                for i, p in enumerate(indices)}
 
     if not distributed:
         res = solve_many(list(range(len(pairs))))
         return [res[p] for p in range(len(pairs))]
-    import torch.distributed as dist
     from . import sharding
-    rank, world = dist.get_rank(), dist.get_world_size()
+    shard = _nccl_shard(device)  # this rank's communicator (created on first use from the torch.distributed job)
+    rank, world = shard.rank, shard.world
     n_points = int(pairs[0].shape[0])
     mine = list(sharding.pairs_of_rank(len(pairs), rank, world))
     res = solve_many(mine)
     local = [(p, res[p][0].reshape(-1, 9), res[p][1]) for p in mine]
     # the exchange step: one ncclAllGather inside libpxb200.so (pxb_allgather_instances) on this rank's context
-    gathered = _nccl_shard(dev).gather_instances(local, len(pairs), n_points, 9, 10)
+    gathered = shard.gather_instances(local, len(pairs), n_points, 9, 10)
     return [(m.reshape(-1, 3), lab) for m, lab in gathered]
 
 

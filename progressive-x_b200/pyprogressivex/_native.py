@@ -95,6 +95,10 @@ def load_library() -> C.CDLL:
     lib.pxb_find_vanishing_points.argtypes = [vp, vp, vp, i64, vp, vp, i64, sz, sz, f64, f64, f64, f64, f64, sz, sz,
                                               C.c_int, sz, f64, C.c_int, u64]
     lib.pxb_find_lines.argtypes = lib.pxb_find_vanishing_points.argtypes
+    lib.pxb_find_homographies_batch.argtypes = [C.c_int, i64, vp, vp, vp, vp, i64, vp, sz, sz, sz, sz, f64, f64, f64, f64, f64,
+                                                sz, sz, C.c_int, sz, f64, u64, C.c_int, C.c_int, C.c_int]
+    lib.pxb_batch_release.argtypes = []
+    lib.pxb_batch_release.restype = None
     lib.pxb_nccl_version.argtypes = [C.POINTER(C.c_int)]
     lib.pxb_nccl_unique_id.argtypes = [vp]
     lib.pxb_nccl_comm_init.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(vp)]

@@ -78,12 +78,22 @@ def test_batched_pairs_config_c4():
         pairs.append(c)
         gts.append(gt)
     kw = dict(threshold=2.0, conf=0.95, max_iters=1000, minimum_point_number=60, sampler_id=0, seed=9)
-    out = pyprogressivex.findHomographiesBatch(pairs, 1024, 768, 1024, 768, workers=4, **kw)
+    out = pyprogressivex.findHomographiesBatch(pairs, 1024, 768, 1024, 768, workers=2, in_flight=3, **kw)
     assert len(out) == 6
-    # concurrent workers (own context / stream each) return exactly what the sequential loop returns
-    seq = pyprogressivex.findHomographiesBatch(pairs, 1024, 768, 1024, 768, workers=1, **kw)
-    for (ma, la), (mb, lb) in zip(out, seq):
+    # the native batch driver (fibers that yield at every stream wait, own context each) returns exactly what
+    # one-problem-at-a-time calls return, for any thread / in-flight split
+    seq = [pyprogressivex.findHomographies(c, 1024, 768, 1024, 768, **kw) for c in pairs]
+    one = pyprogressivex.findHomographiesBatch(pairs, 1024, 768, 1024, 768, workers=1, in_flight=6, **kw)
+    for (ma, la), (mb, lb), (mc, lc) in zip(out, seq, one):
         assert np.array_equal(ma.view(np.uint64), mb.view(np.uint64)) and np.array_equal(la, lb)
+        assert np.array_equal(mc.view(np.uint64), mb.view(np.uint64)) and np.array_equal(lc, lb)
+    # with the spatial term (kNN graph, LO cuts and alpha-expansion inside the fibers): instance counts must agree
+    # (the asynchronous max-flow may resolve exact energy ties differently between runs)
+    kl = dict(kw, spatial_coherence_weight=0.05)
+    bl = pyprogressivex.findHomographiesBatch(pairs[:3], 1024, 768, 1024, 768, workers=1, in_flight=3, **kl)
+    sl = [pyprogressivex.findHomographies(c, 1024, 768, 1024, 768, **kl) for c in pairs[:3]]
+    for (ma, la), (mb, lb) in zip(bl, sl):
+        assert ma.shape == mb.shape and np.mean(la != lb) < 0.01
     for (models, labels), gt, p in zip(out, gts, range(6)):
         M = models.shape[0] // 3
         assert M >= 2 + p % 2
