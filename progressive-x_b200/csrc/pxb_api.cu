@@ -123,30 +123,19 @@ int api_sync(pxb_ctx *ctx) {
 	return err == cudaSuccess ? PXB_OK : PXB_ERR_CUDA;
 }
 
-// One PEARL::labeling call on a data-cost matrix that already sits on the device (D_dev, N x L1). Shared by
-// pxb_pearl_label and the host driver (which keeps the matrix on the device between pxb_pearl_datacost and the sweep).
-int pearl_label_device(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t L1, double lambda, double label_cost,
-                       const int32_t *csr_off_host, const int32_t *csr_idx_host, const int32_t *init_labels_host,
-                       int32_t *labels_out_host, double *energy_out) {
-	// GCoptimization::setLabel range-checks labels (GCoptimization.cpp:929-934 throws GCException)
-	if (init_labels_host)
-		for (int64_t i = 0; i < N; ++i)
-			if (init_labels_host[i] < 0 || init_labels_host[i] >= L1) {
-				set_error("init label %d of site %lld outside [0, %d)", init_labels_host[i], (long long)i, L1);
-				return PXB_ERR_ARGUMENT;
-			}
+// One PEARL::labeling call on a data-cost matrix that already sits on the device (D_dev, N x L1), labels in and out on
+// the device. Shared by pxb_pearl_label and the host driver (which keeps matrix and labels on the device).
+int pearl_label_enqueue(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t L1, double lambda, double label_cost,
+                        const int32_t *csr_off_host, const int32_t *csr_idx_host, int64_t n_dir, const int32_t *init_labels_dev,
+                        int32_t *labels_out_dev, double *energy_host, double **energy_dev_out) {
+	*energy_dev_out = nullptr;
 	// Count the undirected edges setNeighbors would insert (self loops are skipped, PEARL.h:535).
-	int64_t n_dir = 0;
-	if (lambda > 0.0 && csr_off_host && csr_idx_host)
-		for (int64_t i = 0; i < N; ++i)
-			for (int32_t e = csr_off_host[i]; e < csr_off_host[i + 1]; ++e)
-				if (csr_idx_host[e] != i) ++n_dir;
-	PXB_TRY(ctx->outA.reserve(sizeof(int32_t) * (size_t)N * 2 + 64));
-	int32_t *lab_out = ctx->outA.as<int32_t>();
-	int32_t *lab_in = nullptr;
-	if (init_labels_host) {
-		lab_in = lab_out + N;
-		PXB_TRY(api_h2d(ctx, lab_in, init_labels_host, sizeof(int32_t) * (size_t)N));
+	if (n_dir < 0) {
+		n_dir = 0;
+		if (lambda > 0.0 && csr_off_host && csr_idx_host)
+			for (int64_t i = 0; i < N; ++i)
+				for (int32_t e = csr_off_host[i]; e < csr_off_host[i + 1]; ++e)
+					if (csr_idx_host[e] != i) ++n_dir;
 	}
 	if (n_dir == 0) {
 		// solveSpecialCases: data costs + per-label costs, no smooth term -> solveGreedy (GCoptimization.cpp:542-552).
@@ -157,14 +146,36 @@ int pearl_label_device(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t L1,
 			return PXB_ERR_UNSUPPORTED;
 		}
 		PXB_TRY(ctx->outB.reserve(sizeof(double)));
-		PXB_TRY(launch_greedy_label(ctx, D_dev, N, L1, label_cost, lab_in, lab_out, ctx->outB.as<double>()));
-		PXB_TRY(api_d2h(ctx, labels_out_host, lab_out, sizeof(int32_t) * (size_t)N));
-		PXB_TRY(api_d2h(ctx, energy_out, ctx->outB.ptr, sizeof(double)));
-		return api_sync(ctx);
+		PXB_TRY(launch_greedy_label(ctx, D_dev, N, L1, label_cost, init_labels_dev, labels_out_dev, ctx->outB.as<double>()));
+		*energy_dev_out = ctx->outB.as<double>();
+		return PXB_OK;
 	}
-	// alpha-expansion
-	PXB_TRY(launch_alpha_expansion(ctx, D_dev, N, L1, lambda, label_cost, csr_off_host, csr_idx_host, lab_in, lab_out, energy_out));
+	return launch_alpha_expansion(ctx, D_dev, N, L1, lambda, label_cost, csr_off_host, csr_idx_host, init_labels_dev,
+	                              labels_out_dev, energy_host);
+}
+
+int pearl_label_device(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t L1, double lambda, double label_cost,
+                       const int32_t *csr_off_host, const int32_t *csr_idx_host, const int32_t *init_labels_host,
+                       int32_t *labels_out_host, double *energy_out) {
+	// GCoptimization::setLabel range-checks labels (GCoptimization.cpp:929-934 throws GCException)
+	if (init_labels_host)
+		for (int64_t i = 0; i < N; ++i)
+			if (init_labels_host[i] < 0 || init_labels_host[i] >= L1) {
+				set_error("init label %d of site %lld outside [0, %d)", init_labels_host[i], (long long)i, L1);
+				return PXB_ERR_ARGUMENT;
+			}
+	PXB_TRY(ctx->labels.reserve(sizeof(int32_t) * (size_t)N * 2 + 64));
+	int32_t *lab_out = ctx->labels.as<int32_t>();
+	int32_t *lab_in = nullptr;
+	if (init_labels_host) {
+		lab_in = lab_out + N;
+		PXB_TRY(api_h2d(ctx, lab_in, init_labels_host, sizeof(int32_t) * (size_t)N));
+	}
+	double *energy_dev = nullptr;
+	PXB_TRY(pearl_label_enqueue(ctx, D_dev, N, L1, lambda, label_cost, csr_off_host, csr_idx_host, -1, lab_in, lab_out, energy_out,
+	                            &energy_dev));
 	PXB_TRY(api_d2h(ctx, labels_out_host, lab_out, sizeof(int32_t) * (size_t)N));
+	if (energy_dev) PXB_TRY(api_d2h(ctx, energy_out, energy_dev, sizeof(double)));
 	return api_sync(ctx);
 }
 
@@ -240,7 +251,7 @@ void pxb_ctx_destroy(pxb_ctx *ctx) {
 	if (ctx->pts.norm) cudaFree(ctx->pts.norm);
 	DevBuf *bufs[] = {&ctx->models, &ctx->pref, &ctx->pref2, &ctx->outA, &ctx->outB, &ctx->outC,
 	                  &ctx->outD,   &ctx->idx,  &ctx->mask,  &ctx->partials, &ctx->staging, &ctx->screen, &ctx->stats, &ctx->cpref,
-	                  &ctx->shard_msg, &ctx->shard_rec};
+	                  &ctx->shard_msg, &ctx->shard_rec, &ctx->labels, &ctx->pack};
 	for (DevBuf *b : bufs) b->release();
 	if (ctx->pinned) cudaFreeHost(ctx->pinned);
 	if (ctx->stage) cudaFreeHost(ctx->stage);

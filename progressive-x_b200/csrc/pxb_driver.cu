@@ -322,6 +322,10 @@ struct ProgressiveNapsacSampler : Sampler {
 	}
 };
 
+// Samples drawn ahead per refill of the block replay (GCRANSAC::run's main loop). 1024 covers the Python default
+// max_iters = 1000 in one solve + score round trip; the result does not depend on it.
+constexpr size_t kReplayBlock = 1024;
+
 struct Score { // gcr/scoring_function.h:48-73
 	int64_t inliers = 0;
 	double value = 0.0;
@@ -530,7 +534,7 @@ class Driver {
 		return r;
 	}
 	size_t shard_block_cap() const { // largest block a refill may ask for: identical on every rank
-		size_t B = 512 * (size_t)ctx_->shard_world;
+		size_t B = kReplayBlock * (size_t)ctx_->shard_world;
 		if (const char *e = getenv("PXB_BLOCK_SIZE")) {
 			const long v = atol(e);
 			if (v >= 1) B = (size_t)v;
@@ -628,30 +632,42 @@ class Driver {
 	                    std::vector<double> &val, std::vector<double> &shr) {
 		if (sharded()) return solve_and_score_sharded(samples, want, T2, models, n, sv, mv, cnt, val, shr);
 		Scoped t(prof_, "refill(solve+score)");
-		const int64_t K = (int64_t)want, KS = K * maxsol_;
-		PXB_TRY(ctx_->idx.reserve(sizeof(int64_t) * (size_t)K * m_));
-		PXB_TRY(ctx_->models.reserve(sizeof(double) * (size_t)KS * ms_));
-		PXB_TRY(ctx_->outA.reserve(sizeof(int32_t) * (size_t)K + 2 * (size_t)K + 64));
-		int32_t *d_n = ctx_->outA.as<int32_t>();
-		uint8_t *d_sv = reinterpret_cast<uint8_t *>(d_n + K), *d_mv = d_sv + K;
-		PXB_TRY(api_h2d(ctx_, ctx_->idx.ptr, samples.data(), sizeof(int64_t) * (size_t)K * m_));
-		PXB_CUDA(cudaMemsetAsync(ctx_->models.ptr, 0, sizeof(double) * (size_t)KS * ms_, ctx_->stream));
+		const size_t K = want;
+		// models, scores and flags of the block sit in one device record (same layout as a sharded slice): ONE copy back
+		const ShardRecord rec = shard_record(K);
+		PXB_TRY(ctx_->idx.reserve(sizeof(int64_t) * K * m_));
+		PXB_TRY(ctx_->shard_rec.reserve(rec.bytes));
+		char *rc_dev = ctx_->shard_rec.as<char>();
+		double *d_models = reinterpret_cast<double *>(rc_dev + rec.models);
+		int32_t *d_n = reinterpret_cast<int32_t *>(rc_dev + rec.n);
+		uint8_t *d_sv = reinterpret_cast<uint8_t *>(rc_dev + rec.sv), *d_mv = reinterpret_cast<uint8_t *>(rc_dev + rec.mv);
+		PXB_TRY(api_h2d(ctx_, ctx_->idx.ptr, samples.data(), sizeof(int64_t) * K * m_));
+		PXB_CUDA(cudaMemsetAsync(rc_dev, 0, rec.bytes, ctx_->stream));
 		if (s_.plane_parallax) {
 			PXB_TRY(ctx_->outC.reserve(sizeof(double) * 9));
 			PXB_TRY(api_h2d(ctx_, ctx_->outC.ptr, s_.pp_H, sizeof(double) * 9));
-			PXB_TRY(launch_solve_plane_parallax(ctx_, ctx_->idx.as<int64_t>(), K, ctx_->outC.as<double>(), ctx_->models.as<double>(),
-			                                    d_n, d_sv, d_mv));
+			PXB_TRY(launch_solve_plane_parallax(ctx_, ctx_->idx.as<int64_t>(), (int64_t)K, ctx_->outC.as<double>(), d_models, d_n, d_sv,
+			                                    d_mv));
 		} else {
-			PXB_TRY(launch_solve_minimal(ctx_, ctx_->idx.as<int64_t>(), K, ctx_->models.as<double>(), d_n, d_sv, d_mv));
+			PXB_TRY(launch_solve_minimal(ctx_, ctx_->idx.as<int64_t>(), (int64_t)K, d_models, d_n, d_sv, d_mv));
 		}
-		PXB_TRY(api_d2h(ctx_, models.data(), ctx_->models.ptr, sizeof(double) * (size_t)KS * ms_));
-		flags_raw_.resize((size_t)K * 6); // n (4 B) + sample_valid (1 B) + model_valid (1 B) per sample, contiguous on the device
-		PXB_TRY(api_d2h(ctx_, flags_raw_.data(), d_n, (size_t)K * 6));
-		PXB_TRY(score_device_models(KS, T2, cnt, val, shr));
-		PXB_TRY(sync_scores());
-		std::memcpy(n.data(), flags_raw_.data(), sizeof(int32_t) * (size_t)K);
-		std::memcpy(sv.data(), flags_raw_.data() + 4 * (size_t)K, (size_t)K);
-		std::memcpy(mv.data(), flags_raw_.data() + 5 * (size_t)K, (size_t)K);
+		PXB_TRY(launch_score_compound(ctx_, d_models, (int64_t)(K * maxsol_), T2, compound_dev(), reinterpret_cast<int64_t *>(rc_dev + rec.cnt),
+		                              reinterpret_cast<double *>(rc_dev + rec.val), reinterpret_cast<double *>(rc_dev + rec.shr)));
+		pack_host_.resize(rec.bytes);
+		PXB_TRY(api_d2h(ctx_, pack_host_.data(), rc_dev, rec.bytes));
+		PXB_TRY(api_sync(ctx_));
+		const unsigned char *h = pack_host_.data();
+		const size_t KS = K * maxsol_;
+		cnt.resize(KS);
+		val.resize(KS);
+		shr.resize(KS);
+		std::memcpy(models.data(), h + rec.models, sizeof(double) * KS * ms_);
+		std::memcpy(cnt.data(), h + rec.cnt, sizeof(int64_t) * KS);
+		std::memcpy(val.data(), h + rec.val, sizeof(double) * KS);
+		std::memcpy(shr.data(), h + rec.shr, sizeof(double) * KS);
+		std::memcpy(n.data(), h + rec.n, sizeof(int32_t) * K);
+		std::memcpy(sv.data(), h + rec.sv, K);
+		std::memcpy(mv.data(), h + rec.mv, K);
 		return PXB_OK;
 	}
 	int inliers_of(const double *model, double T2, std::vector<int64_t> &out) {
@@ -668,6 +684,9 @@ class Driver {
 	                   std::vector<double> &models_out, std::vector<int32_t> &ok, double T2 = -1.0,
 	                   std::vector<int64_t> *cnt = nullptr, std::vector<double> *val = nullptr,
 	                   std::vector<double> *shr = nullptr);
+	int launch_fit_family(int P, const int32_t *d_off, const int32_t *d_idx, const double *d_w, double *models_dev, int32_t *ok_dev);
+	std::vector<unsigned char> pack_host_;
+	int64_t smooth_edges_ = -1; // directed non-loop entries of the neighbour lists (counted once per graph)
 	int lo_labeling(const double *model, std::vector<int64_t> &inliers);
 	// Estimator::nonMinimalSampleSize(): H four-point 4, F bundle-adjustment solver 7, PnP bundle adjustment 4,
 	// vanishing point / 2D line: the minimal solver doubles as the non-minimal one, 2
@@ -712,6 +731,19 @@ int Driver::build_graph(double radius, int k) {
 	return PXB_OK;
 }
 
+// the non-minimal solver of the estimator family on device-resident CSR index lists (asynchronous)
+int Driver::launch_fit_family(int P, const int32_t *d_off, const int32_t *d_idx, const double *d_w, double *models_dev,
+                              int32_t *ok_dev) {
+	switch (s_.type) {
+	case PXB_MODEL_HOMOGRAPHY: return launch_fit_h(ctx_, P, d_off, d_idx, d_w, models_dev, ok_dev);
+	case PXB_MODEL_FUNDAMENTAL: return launch_fit_f(ctx_, P, d_off, d_idx, d_w, models_dev, ok_dev);
+	case PXB_MODEL_PNP: // PerspectiveNPointEstimator::isWeightingApplicable() is false: weights never reach the solver
+		return launch_fit_pnp(ctx_, P, d_off, d_idx, models_dev, ok_dev);
+	case PXB_MODEL_VANISHING_POINT: return launch_fit_vp(ctx_, P, d_off, d_idx, d_w, models_dev, ok_dev);
+	default: return launch_fit_line(ctx_, P, d_off, d_idx, models_dev, ok_dev);
+	}
+}
+
 int Driver::fit_nonminimal(const std::vector<std::vector<int64_t>> &sets, const double *weights_by_row,
                            std::vector<double> &models_out, std::vector<int32_t> &ok, double T2, std::vector<int64_t> *cnt,
                            std::vector<double> *val, std::vector<double> *shr) {
@@ -727,43 +759,44 @@ int Driver::fit_nonminimal(const std::vector<std::vector<int64_t>> &sets, const 
 	packed.reserve(off.size() + (size_t)off[P]);
 	for (const auto &st : sets)
 		for (int64_t i : st) packed.push_back((int32_t)i);
-	const size_t n_idx = packed.size() - off.size();
 	size_t wcount = 0;
 	if (weights_by_row) wcount = weights_by_point() ? (size_t)N_ : sets[0].size(); // row-indexed: one problem at a time (IRLS)
 	const size_t bytes = sizeof(int32_t) * packed.size() + 64;
 	PXB_TRY(ctx_->idx.reserve(bytes));
 	int32_t *d_off = ctx_->idx.as<int32_t>(), *d_idx = d_off + off.size();
-	PXB_TRY(ctx_->models.reserve(sizeof(double) * (size_t)P * ms_));
-	PXB_TRY(ctx_->outA.reserve(sizeof(int32_t) * (size_t)P));
+	// results packed on the device so that ONE copy brings them back: models | count | value | shared | ok
+	const size_t b_models = sizeof(double) * (size_t)P * ms_, b_sc = sizeof(int64_t) * (size_t)P;
+	const size_t pack_bytes = b_models + 3 * b_sc + sizeof(int32_t) * (size_t)P;
+	PXB_TRY(ctx_->pack.reserve(pack_bytes));
+	char *pk = ctx_->pack.as<char>();
+	double *d_models = reinterpret_cast<double *>(pk);
+	int64_t *d_cnt = reinterpret_cast<int64_t *>(pk + b_models);
+	double *d_val = reinterpret_cast<double *>(pk + b_models + b_sc), *d_shr = reinterpret_cast<double *>(pk + b_models + 2 * b_sc);
+	int32_t *d_ok = reinterpret_cast<int32_t *>(pk + b_models + 3 * b_sc);
 	double *d_w = nullptr;
 	if (weights_by_row) {
 		PXB_TRY(ctx_->pref2.reserve(sizeof(double) * wcount));
 		d_w = ctx_->pref2.as<double>();
 		PXB_TRY(api_h2d(ctx_, d_w, weights_by_row, sizeof(double) * wcount));
 	}
-	(void)n_idx;
 	PXB_TRY(api_h2d(ctx_, d_off, packed.data(), sizeof(int32_t) * packed.size()));
-	switch (s_.type) {
-	case PXB_MODEL_HOMOGRAPHY:
-		PXB_TRY(launch_fit_h(ctx_, P, d_off, d_idx, d_w, ctx_->models.as<double>(), ctx_->outA.as<int32_t>()));
-		break;
-	case PXB_MODEL_FUNDAMENTAL:
-		PXB_TRY(launch_fit_f(ctx_, P, d_off, d_idx, d_w, ctx_->models.as<double>(), ctx_->outA.as<int32_t>()));
-		break;
-	case PXB_MODEL_PNP: // PerspectiveNPointEstimator::isWeightingApplicable() is false: weights never reach the solver
-		PXB_TRY(launch_fit_pnp(ctx_, P, d_off, d_idx, ctx_->models.as<double>(), ctx_->outA.as<int32_t>()));
-		break;
-	case PXB_MODEL_VANISHING_POINT:
-		PXB_TRY(launch_fit_vp(ctx_, P, d_off, d_idx, d_w, ctx_->models.as<double>(), ctx_->outA.as<int32_t>()));
-		break;
-	default:
-		PXB_TRY(launch_fit_line(ctx_, P, d_off, d_idx, ctx_->models.as<double>(), ctx_->outA.as<int32_t>()));
-		break;
+	PXB_TRY(launch_fit_family(P, d_off, d_idx, d_w, d_models, d_ok));
+	if (cnt) PXB_TRY(launch_score_compound(ctx_, d_models, P, T2, compound_dev(), d_cnt, d_val, d_shr));
+	pack_host_.resize(pack_bytes);
+	PXB_TRY(api_d2h(ctx_, pack_host_.data(), pk, pack_bytes));
+	PXB_TRY(api_sync(ctx_));
+	const unsigned char *h = pack_host_.data();
+	std::memcpy(models_out.data(), h, b_models);
+	std::memcpy(ok.data(), h + b_models + 3 * b_sc, sizeof(int32_t) * (size_t)P);
+	if (cnt) {
+		cnt->resize(P);
+		val->resize(P);
+		shr->resize(P);
+		std::memcpy(cnt->data(), h + b_models, b_sc);
+		std::memcpy(val->data(), h + b_models + b_sc, b_sc);
+		std::memcpy(shr->data(), h + b_models + 2 * b_sc, b_sc);
 	}
-	PXB_TRY(api_d2h(ctx_, models_out.data(), ctx_->models.ptr, sizeof(double) * models_out.size()));
-	PXB_TRY(api_d2h(ctx_, ok.data(), ctx_->outA.ptr, sizeof(int32_t) * ok.size()));
-	if (cnt) PXB_TRY(score_device_models(P, T2, *cnt, *val, *shr));
-	return cnt ? sync_scores() : api_sync(ctx_);
+	return PXB_OK;
 }
 
 // gcr/GCRANSAC.h:914-1022. Unary terms come from the device (k_lo_unary). Without a smoothness term the st-cut
@@ -1099,8 +1132,8 @@ int Driver::propose(uint64_t round_seed, std::vector<double> &model_out, bool &f
 	// ---- block state ----
 	// Block size of the replay. Any value gives the same result for the same seed (the sample stream does not depend
 	// on it); PXB_BLOCK_SIZE=1 *is* the reference's sequential loop and is what tests/test_gpu_e2e.py compares against.
-	size_t B = 512, Bmin = 32;
-	if (sharded()) B *= (size_t)ctx_->shard_world; // every rank still sees up to 512 samples per refill
+	size_t B = kReplayBlock, Bmin = 32;
+	if (sharded()) B *= (size_t)ctx_->shard_world; // every rank still sees up to kReplayBlock samples per refill
 	if (const char *e = getenv("PXB_BLOCK_SIZE")) {
 		const long v = atol(e);
 		if (v >= 1) B = Bmin = (size_t)v;
@@ -1256,80 +1289,100 @@ int Driver::pearl() {
 	size_t iteration_number = 0;
 	double energy = std::numeric_limits<double>::max(), previous_energy = -1.0;
 	bool model_rejected = false, convergence = false;
-	std::vector<int32_t> labels(N_, 0), prev_labels;
 	bool have_labels = false;
 	const double label_cost = (double)s_.min_inliers; // model_complexity_weight(minimum_inlier_number_) (:147)
+	const bool smooth = s_.lambda > 0.0 && !graph_.idx.empty();
+	if (smooth && smooth_edges_ < 0) { // the undirected edges setNeighbors would insert (self loops skipped, PEARL.h:535)
+		smooth_edges_ = 0;
+		for (int64_t i = 0; i < N_; ++i)
+			for (int32_t e = graph_.off[i]; e < graph_.off[i + 1]; ++e)
+				if (graph_.idx[e] != i) ++smooth_edges_;
+	}
+	// The labels stay on the device for the whole run ([current | previous]); one iteration -- data costs, label sweep,
+	// per-instance point lists, residual sums, refits, residual sums of the refits -- is one stream-ordered chain with
+	// one packed copy back (PEARL.h:476-555 + :319-401).
+	PXB_TRY(ctx_->labels.reserve(sizeof(int32_t) * (size_t)N_ * 2 + 64));
+	int32_t *lab_cur = ctx_->labels.as<int32_t>(), *lab_prev = lab_cur + N_;
+	// PEARL.h:373-380 passes settings.point_weights (only findVanishingPoints_ sets them; read by point there)
+	double *d_w = nullptr;
+	if (weights_by_point() && s_.point_weights.size() == (size_t)N_) {
+		PXB_TRY(ctx_->pref2.reserve(sizeof(double) * (size_t)N_));
+		d_w = ctx_->pref2.as<double>();
+		PXB_TRY(api_h2d(ctx_, d_w, s_.point_weights.data(), sizeof(double) * (size_t)N_));
+	}
+	std::vector<int64_t> counts;
 	while (!convergence && iteration_number++ < 100) {
 		const bool init_with_previous = iteration_number > 1 && !model_rejected;
 		// ---- labeling ----
 		const int64_t L = (int64_t)models_.size();
 		if (L == 0) break;
+		Scoped tl(prof_, "pearl iteration");
 		std::vector<double> flat((size_t)L * ms_);
 		for (int64_t l = 0; l < L; ++l) std::copy(models_[l].model.begin(), models_[l].model.end(), flat.begin() + l * ms_);
-		// data costs stay on the device between the cost kernel and the label sweep (PEARL.h:476-555 in two launches)
 		PXB_TRY(ctx_->models.reserve(sizeof(double) * (size_t)L * ms_));
 		PXB_TRY(api_h2d(ctx_, ctx_->models.ptr, flat.data(), sizeof(double) * (size_t)L * ms_));
 		PXB_TRY(ctx_->staging.reserve(sizeof(double) * (size_t)N_ * (L + 1)));
 		PXB_TRY(launch_pearl_datacost(ctx_, ctx_->models.as<double>(), L, s_.threshold, s_.lambda, ctx_->staging.as<double>()));
-		Scoped tl(prof_, "pearl label+refit");
-		const int32_t *init = (init_with_previous && have_labels) ? labels.data() : nullptr;
-		prev_labels = labels;
-		const bool smooth = s_.lambda > 0.0 && !graph_.idx.empty();
-		PXB_TRY(pearl_label_device(ctx_, ctx_->staging.as<double>(), N_, (int32_t)(L + 1), s_.lambda, label_cost,
-		                           smooth ? graph_.off.data() : nullptr, smooth ? graph_.idx.data() : nullptr,
-		                           init ? prev_labels.data() : nullptr, labels.data(), &energy));
+		const int32_t *init = nullptr;
+		if (init_with_previous && have_labels) { // no instance was rejected: the previous labels are valid for L + 1 labels
+			PXB_CUDA(cudaMemcpyAsync(lab_prev, lab_cur, sizeof(int32_t) * (size_t)N_, cudaMemcpyDeviceToDevice, ctx_->stream));
+			init = lab_prev;
+		}
+		// packed results: energy | before[L] | after[L] | counts[L] | counts2[L] | fitted[L ms] | cand[L ms] | ok[L]
+		const size_t bL = sizeof(double) * (size_t)L, bM = sizeof(double) * (size_t)L * ms_;
+		const size_t o_before = 8, o_after = o_before + bL, o_cnt = o_after + bL, o_cnt2 = o_cnt + bL, o_fit = o_cnt2 + bL,
+		             o_cand = o_fit + bM, o_ok = o_cand + bM, pack_bytes = o_ok + sizeof(int32_t) * (size_t)L;
+		PXB_TRY(ctx_->pack.reserve(pack_bytes));
+		char *pk = ctx_->pack.as<char>();
+		double *energy_dev = nullptr;
+		PXB_TRY(pearl_label_enqueue(ctx_, ctx_->staging.as<double>(), N_, (int32_t)(L + 1), s_.lambda, label_cost,
+		                            smooth ? graph_.off.data() : nullptr, smooth ? graph_.idx.data() : nullptr, smooth ? smooth_edges_ : 0,
+		                            init, lab_cur, &energy, &energy_dev));
 		have_labels = true;
+		if (energy_dev) PXB_CUDA(cudaMemcpyAsync(pk, energy_dev, sizeof(double), cudaMemcpyDeviceToDevice, ctx_->stream));
 		// ---- parameterEstimation ----
+		PXB_TRY(ctx_->idx.reserve(sizeof(int32_t) * ((size_t)N_ + (size_t)L + 1) + 64));
+		int32_t *d_off = ctx_->idx.as<int32_t>(), *d_idx = d_off + (L + 1);
+		PXB_TRY(launch_label_lists(ctx_, lab_cur, N_, (int)L, d_off, d_idx));
+		PXB_TRY(launch_segment_sums(ctx_, ctx_->models.as<double>(), L, lab_cur, reinterpret_cast<double *>(pk + o_before),
+		                            reinterpret_cast<int64_t *>(pk + o_cnt)));
+		// instances with fewer points than nonMinimalSampleSize() are not refitted (:363-365): the solvers report !ok for them
+		PXB_TRY(launch_fit_family((int)L, d_off, d_idx, d_w, reinterpret_cast<double *>(pk + o_fit), reinterpret_cast<int32_t *>(pk + o_ok)));
+		PXB_TRY(launch_select_models(ctx_, ctx_->models.as<double>(), reinterpret_cast<double *>(pk + o_fit),
+		                             reinterpret_cast<int32_t *>(pk + o_ok), (int)L, ms_, reinterpret_cast<double *>(pk + o_cand)));
+		PXB_TRY(launch_segment_sums(ctx_, reinterpret_cast<double *>(pk + o_cand), L, lab_cur, reinterpret_cast<double *>(pk + o_after),
+		                            reinterpret_cast<int64_t *>(pk + o_cnt2)));
+		pack_host_.resize(pack_bytes);
+		PXB_TRY(api_d2h(ctx_, pack_host_.data(), pk, pack_bytes));
+		PXB_TRY(api_sync(ctx_));
+		const unsigned char *h = pack_host_.data();
+		if (energy_dev) std::memcpy(&energy, h, sizeof(double));
+		const double *before = reinterpret_cast<const double *>(h + o_before), *after = reinterpret_cast<const double *>(h + o_after);
+		const double *fitted = reinterpret_cast<const double *>(h + o_fit);
+		const int32_t *ok = reinterpret_cast<const int32_t *>(h + o_ok);
+		counts.assign(reinterpret_cast<const int64_t *>(h + o_cnt), reinterpret_cast<const int64_t *>(h + o_cnt) + L);
 		bool model_parameters_changed = false;
 		model_rejected = false;
-		std::vector<std::vector<int64_t>> per_instance((size_t)L);
-		size_t outliers = 0;
-		for (int64_t i = 0; i < N_; ++i) {
-			if (labels[i] < L)
-				per_instance[(size_t)labels[i]].push_back(i);
-			else
-				++outliers;
-		}
-		{
-			std::vector<double> before(L), after(L);
-			std::vector<int64_t> counts(L);
-			PXB_TRY(pxb_segment_residual_sums(ctx_, flat.data(), L, labels.data(), before.data(), counts.data()));
-			std::vector<std::vector<int64_t>> sets;
-			std::vector<int64_t> which;
-			for (int64_t l = 0; l < L; ++l)
-				if (per_instance[l].size() >= non_minimal_sample_size()) { // :363-365
-					sets.push_back(per_instance[l]);
-					which.push_back(l);
-				}
-			std::vector<double> fitted;
-			std::vector<int32_t> ok;
-			// PEARL.h:373-380 passes settings.point_weights (only findVanishingPoints_ sets them; read by point there)
-			const double *pw = (weights_by_point() && s_.point_weights.size() == (size_t)N_) ? s_.point_weights.data() : nullptr;
-			PXB_TRY(fit_nonminimal(sets, pw, fitted, ok));
-			std::vector<double> cand = flat;
-			for (size_t t = 0; t < which.size(); ++t)
-				if (ok[t]) std::copy(fitted.begin() + t * ms_, fitted.begin() + (t + 1) * ms_, cand.begin() + which[t] * ms_);
-			PXB_TRY(pxb_segment_residual_sums(ctx_, cand.data(), L, labels.data(), after.data(), counts.data()));
-			for (size_t t = 0; t < which.size(); ++t) {
-				const int64_t l = which[t];
-				if (ok[t] && after[l] < before[l]) { // :393-399
-					models_[l].model.assign(cand.begin() + l * ms_, cand.begin() + (l + 1) * ms_);
-					model_parameters_changed = true;
-				}
+		size_t outliers = (size_t)N_;
+		for (int64_t l = 0; l < L; ++l) outliers -= (size_t)counts[l];
+		for (int64_t l = 0; l < L; ++l) {
+			if ((size_t)counts[l] < non_minimal_sample_size()) continue; // :363-365
+			if (ok[l] && after[l] < before[l]) { // :393-399
+				models_[l].model.assign(fitted + l * ms_, fitted + (l + 1) * ms_);
+				model_parameters_changed = true;
 			}
 		}
 		if (s_.do_logging) {
 			fprintf(stdout, "[pxb]   PEARL it %zu: L=%lld energy %.4f (prev %.4f) init=%d points per instance:", iteration_number,
 			        (long long)L, energy, previous_energy, init ? 1 : 0);
-			for (int64_t l = 0; l < L; ++l) fprintf(stdout, " %zu", per_instance[l].size());
+			for (int64_t l = 0; l < L; ++l) fprintf(stdout, " %lld", (long long)counts[l]);
 			fprintf(stdout, " outliers %zu%s\n", outliers, model_parameters_changed ? " (refit accepted)" : "");
 		}
 		// ---- rejectInstances (back to front) ----
 		for (int64_t l = L - 1; l >= 0; --l)
-			if (per_instance[l].size() < s_.min_inliers) {
-				outliers += per_instance[l].size();
+			if ((size_t)counts[l] < s_.min_inliers) {
+				outliers += (size_t)counts[l];
 				models_.erase(models_.begin() + l);
-				per_instance.erase(per_instance.begin() + l);
 				model_rejected = true;
 			}
 		pearl_outliers_ = outliers;
@@ -1338,7 +1391,13 @@ int Driver::pearl() {
 			convergence = true;
 		previous_energy = energy;
 	}
-	labeling_.assign(labels.begin(), labels.end()); // getLabeling (:218-249): raw gco labels of the last labeling
+	// getLabeling (:218-249): raw gco labels of the last labeling
+	std::vector<int32_t> labels((size_t)N_, 0);
+	if (have_labels) {
+		PXB_TRY(api_d2h(ctx_, labels.data(), lab_cur, sizeof(int32_t) * (size_t)N_));
+		PXB_TRY(api_sync(ctx_));
+	}
+	labeling_.assign(labels.begin(), labels.end());
 	return PXB_OK;
 }
 

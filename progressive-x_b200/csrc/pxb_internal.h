@@ -117,6 +117,7 @@ struct pxb_ctx {
 	void *shard_comm = nullptr;
 	int shard_world = 1, shard_rank = 0;
 	pxb::DevBuf shard_msg, shard_rec;
+	pxb::DevBuf labels, pack; // PEARL labels (kept on the device between iterations) and the packed per-call results
 };
 
 namespace pxb {
@@ -136,6 +137,15 @@ int shard_allgather(pxb_ctx *ctx, void *recv_dev, size_t bytes_per_rank);
 int pearl_label_device(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t L1, double lambda, double label_cost,
                        const int32_t *csr_off_host, const int32_t *csr_idx_host, const int32_t *init_labels_host,
                        int32_t *labels_out_host, double *energy_out);
+// the same labelling with the labels staying on the device: init_labels_dev (may be null) and labels_out_dev are device
+// arrays of N int32; the energy arrives either on the device (*energy_dev_out != null: greedy path, asynchronous) or in
+// *energy_host (alpha-expansion: its host move loop has synchronised). n_dir < 0: count the smooth edges here.
+int pearl_label_enqueue(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t L1, double lambda, double label_cost,
+                        const int32_t *csr_off_host, const int32_t *csr_idx_host, int64_t n_dir, const int32_t *init_labels_dev,
+                        int32_t *labels_out_dev, double *energy_host, double **energy_dev_out);
+int launch_label_lists(pxb_ctx *ctx, const int32_t *labels_dev, int64_t N, int L, int32_t *off_dev, int32_t *idx_dev);
+int launch_select_models(pxb_ctx *ctx, const double *current, const double *fitted, const int32_t *ok, int L, int ms,
+                         double *cand);
 // kernel launchers (device pointers, asynchronous on ctx->stream)
 int launch_residual_matrix(pxb_ctx *ctx, const double *models, int64_t K, double T2, double *r2, float *r2f,
                            uint32_t *mask);

@@ -110,6 +110,34 @@ def load_library() -> C.CDLL:
     return lib
 
 
+_nccl_preloaded = False
+
+
+def preload_nccl() -> None:
+    """libpxb200.so resolves NCCL at run time and takes the copy of libnccl.so.2 the process already holds. A Python
+    process that has not imported torch yet holds none -- and mapping the SYSTEM libnccl first would later break
+    `import torch` (torch's libtorch_cuda.so needs the newer copy it ships with: the loader reuses whatever already
+    carries the soname). So map the wheel-bundled copy (nvidia/nccl/lib) first when there is one."""
+    global _nccl_preloaded
+    if _nccl_preloaded:
+        return
+    _nccl_preloaded = True
+    import sys
+    if "torch" in sys.modules:
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        if spec is not None and spec.submodule_search_locations:
+            for base in spec.submodule_search_locations:
+                cand = Path(base) / "lib" / "libnccl.so.2"
+                if cand.exists():
+                    C.CDLL(str(cand), mode=C.RTLD_GLOBAL)
+                    return
+    except Exception:
+        pass
+
+
 def _check(rc: int):
     if rc < 0:
         raise PxbError(rc, load_library().pxb_last_error().decode("utf-8", "replace"))

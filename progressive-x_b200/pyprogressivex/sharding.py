@@ -125,6 +125,7 @@ class NcclShard:
 
     def __init__(self, ctx, world: int | None = None, rank: int | None = None, unique_id: bytes | None = None):
         from . import _native
+        _native.preload_nccl()
         self.ctx, self.lib = ctx, ctx.lib
         if world is None:
             dist = _dist()
