@@ -74,6 +74,15 @@ class Rng:
         return out
 
 
+def lo_substream(seed, event, trial):
+    """Generator seed of trial `trial` of the `event`-th LO labelling of a proposal (pxb_driver.cu lo_substream: the GPU
+    driver draws all inner-RANSAC samples of one LO step at once, one generator per trial)."""
+    z = (seed + 0x9E3779B97F4A7C15 * (event * 64 + trial + 1)) & M64
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M64
+    return z ^ (z >> 31)
+
+
 class UniformSampler:  # gcr/samplers/uniform_sampler.h:118-134
     def __init__(self, seed):
         self.rng = Rng(seed)
@@ -550,7 +559,7 @@ class ProgressiveXOracle:
         return int(log_probability / log2) + 1
 
     # ---- GCRANSAC.h:781-911 -----------------------------------------------------------------------------------------
-    def local_optimization(self, lo_sampler, best_model, best_score, T2):
+    def local_optimization(self, lo_seed, best_model, best_score, T2):
         inlier_limit = 7 * self.m
         max_score, lo_model = Score(best_score.inliers, best_score.value), best_model
         self.lo_number += 1
@@ -560,9 +569,12 @@ class ProgressiveXOracle:
                 break
             updated = False
             inliers = self._lo_labeling(lo_model)
+            event = self.lo_events
+            self.lo_events += 1
             sample_size = min(inlier_limit, len(inliers))
             if sample_size < len(inliers):
-                sets = [lo_sampler.sample(inliers, sample_size) for _ in range(self.max_local_optimization_number)]
+                sets = [UniformSampler(lo_substream(lo_seed, event, t)).sample(inliers, sample_size)
+                        for t in range(self.max_local_optimization_number)]
             elif self.m < len(inliers):
                 sets = [inliers]
             else:
@@ -619,7 +631,8 @@ class ProgressiveXOracle:
             main = ProsacSampler((round_seed * 2 + 1) & M64, self.m, self.N)
         else:
             main = UniformSampler((round_seed * 2 + 1) & M64)
-        lo_sampler = UniformSampler((round_seed * 2 + 2) & M64)
+        lo_seed = (round_seed * 2 + 2) & M64
+        self.lo_events = 0
         pool = list(range(self.N))
         best_score, best_model = Score(), None
         while self.min_iteration_number > self.iteration_number or self.iteration_number < min(max_iteration, self.max_iters):
@@ -664,13 +677,13 @@ class ProgressiveXOracle:
                     max_iteration = self._iteration_number_for(best_score.inliers, log_probability)
             if do_lo:  # :482-503
                 self.lo_number += 1
-                best_model, best_score = self.local_optimization(lo_sampler, best_model, best_score, T2)
+                best_model, best_score = self.local_optimization(lo_seed, best_model, best_score, T2)
                 max_iteration = self._iteration_number_for(best_score.inliers, log_probability)
         if best_score.inliers <= self.m:
             return None
         if self.lo_number == 0:  # :531-544
             self.lo_number += 1
-            best_model, best_score = self.local_optimization(lo_sampler, best_model, best_score, T2)
+            best_model, best_score = self.local_optimization(lo_seed, best_model, best_score, T2)
         best_inliers = self._inliers_of(best_model, T2)
         best_score.inliers = len(best_inliers)
         refit_applied = False

@@ -1,0 +1,247 @@
+// pxb_chain.cu -- device-side glue that keeps the host driver's loops to ONE round trip per iteration: index lists are
+// built, sampled and consumed on the device instead of travelling to the host and back.
+//
+// PEARL iteration (px/include/PEARL.h:319-401, parameterEstimation): labeling -> per-instance point lists -> residual
+// sums -> non-minimal refits -> residual sums of the refits is one stream-ordered chain with a single small copy at its
+// end (it used to take four round trips: labels down, sums, index lists up + fits, sums again).
+// GC-RANSAC local optimisation (gcr/GCRANSAC.h:781-911): labelling -> inlier list -> the <= 50 inner-RANSAC samples ->
+// fits -> scores, one copy back (two round trips and an N-byte copy before).
+// Least-squares tail (gcr/GCRANSAC.h:561-618, 631-759): inlier list of the current model -> Tukey weights -> weighted
+// fit -> score, one copy back (three round trips per iteration before).
+//
+//   k_label_lists     per-instance point lists from the label array: block l writes the indices of the points with
+//                     label l in ascending order to idx[off[l] ...] (the order in which PEARL.h:342-352 collects them),
+//                     off[l] = number of points with a label below l
+//   k_select_models   cand[l] = ok[l] ? fitted[l] : current[l]   (PEARL.h:381-391 evaluates the refit only where it succeeded)
+#include "pxb_internal.h"
+
+namespace pxb {
+
+constexpr int kListThreads = 1024;
+
+__global__ void __launch_bounds__(kListThreads)
+    k_label_lists(const int32_t *__restrict__ labels, int64_t N, int L, int32_t *__restrict__ off /*L+1*/,
+                  int32_t *__restrict__ idx) {
+	__shared__ int s_warp[32];
+	__shared__ int s_a, s_b;
+	const int l = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	// pass 1: how many points carry a label below l / equal to l
+	int below = 0, mine = 0;
+	for (int64_t i = tid; i < N; i += kListThreads) {
+		const int v = labels[i];
+		below += (v >= 0 && v < l);
+		mine += (v == l);
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		below += __shfl_xor_sync(0xffffffffu, below, o);
+		mine += __shfl_xor_sync(0xffffffffu, mine, o);
+	}
+	if (tid == 0) s_a = 0, s_b = 0;
+	__syncthreads();
+	if (lane == 0) {
+		atomicAdd(&s_a, below);
+		atomicAdd(&s_b, mine);
+	}
+	__syncthreads();
+	const int base = s_a;
+	if (tid == 0) {
+		off[l] = base;
+		if (l == L - 1) off[L] = base + s_b;
+	}
+	// pass 2: ordered compaction, one chunk of 1024 points per step
+	int running = base;
+	for (int64_t c0 = 0; c0 < N; c0 += kListThreads) {
+		const int64_t i = c0 + tid;
+		const bool pred = i < N && labels[i] == l;
+		const unsigned b = __ballot_sync(0xffffffffu, pred);
+		if (lane == 0) s_warp[warp] = __popc(b);
+		__syncthreads();
+		if (warp == 0) {
+			const int v = s_warp[lane];
+			int inc = v;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) {
+				const int t = __shfl_up_sync(0xffffffffu, inc, o);
+				if (lane >= o) inc += t;
+			}
+			s_warp[lane] = inc - v; // exclusive prefix of the warp counts
+			if (lane == 31) s_a = inc; // chunk total
+		}
+		__syncthreads();
+		if (pred) idx[running + s_warp[warp] + __popc(b & ((1u << lane) - 1u))] = (int32_t)i;
+		running += s_a;
+		__syncthreads();
+	}
+}
+
+__global__ void k_select_models(const double *__restrict__ current, const double *__restrict__ fitted,
+                                const int32_t *__restrict__ ok, int L, int ms, double *__restrict__ cand) {
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= L * ms) return;
+	cand[t] = ok[t / ms] ? fitted[t] : current[t];
+}
+
+// ---- ordered compaction of a 0/1 byte array (the LO labelling: SINK = inlier) or of an inlier bit mask -------------------
+// One block; indices ascending, the order in which the reference walks the points (GCRANSAC.h:1006-1016,
+// scoring_function_with_compound_model.h:85-95). count_out[0] receives the number of entries.
+template <bool BITS>
+__global__ void __launch_bounds__(kListThreads)
+    k_flag_compact(const void *__restrict__ flags, int64_t N, int32_t *__restrict__ idx, int64_t *__restrict__ count_out,
+                   int32_t *__restrict__ off2 /* optional: off2[0] = 0, off2[1] = count (a one-problem CSR) */) {
+	__shared__ int s_warp[32];
+	__shared__ int s_total;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	int running = 0;
+	const int64_t items = BITS ? (N + 31) / 32 : N; // bit mask: one 32-bit word per thread and step
+	for (int64_t c0 = 0; c0 < items; c0 += kListThreads) {
+		const int64_t i = c0 + tid;
+		int mine;
+		unsigned word = 0;
+		if (BITS) {
+			word = i < items ? reinterpret_cast<const uint32_t *>(flags)[i] : 0u;
+			mine = __popc(word);
+		} else {
+			mine = (i < N && reinterpret_cast<const uint8_t *>(flags)[i]) ? 1 : 0;
+		}
+		int inc = mine; // inclusive scan over the warp, then over the warp totals
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const int t = __shfl_up_sync(0xffffffffu, inc, o);
+			if (lane >= o) inc += t;
+		}
+		if (lane == 31) s_warp[warp] = inc;
+		__syncthreads();
+		if (warp == 0) {
+			const int v = s_warp[lane];
+			int w = v;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) {
+				const int t = __shfl_up_sync(0xffffffffu, w, o);
+				if (lane >= o) w += t;
+			}
+			s_warp[lane] = w - v;
+			if (lane == 31) s_total = w;
+		}
+		__syncthreads();
+		int at = running + s_warp[warp] + inc - mine;
+		if (BITS) {
+			while (word) {
+				const int b = __ffs(word) - 1;
+				idx[at++] = (int32_t)(i * 32 + b);
+				word &= word - 1;
+			}
+		} else if (mine) {
+			idx[at] = (int32_t)i;
+		}
+		running += s_total;
+		__syncthreads();
+	}
+	if (tid == 0) {
+		count_out[0] = running;
+		if (off2) off2[0] = 0, off2[1] = running;
+	}
+}
+
+// ---- the inner-RANSAC samples of one local-optimisation step (GCRANSAC.h:823-851) --------------------------------------
+// count > limit : `trials` samples of `limit` distinct inliers each; trial t draws from its own generator (splitmix64
+//                 seeded by lo_substream(seed, event, t)), exactly as the host sampler would: unique_set by rejection
+//                 (gcr/uniform_random_generator.h:76-122) over positions of the inlier list;
+// m < count     : one problem holding every inlier (all trials would refit the same set);
+// otherwise     : nothing (the host loop breaks).
+__device__ __forceinline__ uint64_t lo_rng_next(uint64_t &s) {
+	uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+	z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+	z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+	return z ^ (z >> 31);
+}
+__device__ __forceinline__ uint64_t lo_substream(uint64_t seed, uint64_t event, uint64_t trial) {
+	uint64_t z = seed + 0x9E3779B97F4A7C15ull * (event * 64 + trial + 1);
+	z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+	z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+	return z ^ (z >> 31);
+}
+constexpr int kLoMaxSample = 64;
+
+__global__ void __launch_bounds__(kListThreads)
+    k_lo_sample(const int32_t *__restrict__ inl, const int64_t *__restrict__ count_in, int m, int limit, int trials,
+                uint64_t seed, uint64_t event, int32_t *__restrict__ off /*trials + 1*/, int32_t *__restrict__ idx) {
+	const int64_t count = count_in[0];
+	const int tid = threadIdx.x;
+	if (count > (int64_t)limit) {
+		if (tid <= trials) off[tid] = tid * limit;
+		if (tid >= trials) return;
+		uint64_t s = lo_substream(seed, event, (uint64_t)tid);
+		if (s == 0) s = 0x9E3779B97F4A7C15ull;
+		const uint64_t range = (uint64_t)count; // uniform(max = count - 1)
+		const uint64_t lim = UINT64_MAX - (UINT64_MAX % range);
+		int32_t pos[kLoMaxSample];
+		for (int i = 0; i < limit; ++i) {
+			for (;;) {
+				uint64_t r;
+				do r = lo_rng_next(s); while (r >= lim);
+				const int32_t v = (int32_t)(r % range);
+				bool dup = false;
+				for (int j = i - 1; j >= 0; --j)
+					if (pos[j] == v) {
+						dup = true;
+						break;
+					}
+				if (!dup) {
+					pos[i] = v;
+					break;
+				}
+			}
+		}
+		for (int i = 0; i < limit; ++i) idx[tid * limit + i] = inl[pos[i]];
+	} else if (count > (int64_t)m) {
+		if (tid <= trials) off[tid] = tid == 0 ? 0 : (int32_t)count;
+		for (int64_t i = tid; i < count; i += kListThreads) idx[i] = inl[i];
+	} else {
+		if (tid <= trials) off[tid] = 0;
+	}
+}
+
+int launch_flag_compact(pxb_ctx *ctx, const uint8_t *flags_dev, int64_t N, int32_t *idx_dev, int64_t *count_dev, int32_t *off2_dev) {
+	k_flag_compact<false><<<1, kListThreads, 0, ctx->stream>>>(flags_dev, N, idx_dev, count_dev, off2_dev);
+	ctx->launches++;
+	PXB_CUDA(cudaGetLastError());
+	return PXB_OK;
+}
+int launch_mask_compact(pxb_ctx *ctx, const uint32_t *mask_dev, int64_t N, int32_t *idx_dev, int64_t *count_dev, int32_t *off2_dev) {
+	k_flag_compact<true><<<1, kListThreads, 0, ctx->stream>>>(mask_dev, N, idx_dev, count_dev, off2_dev);
+	ctx->launches++;
+	PXB_CUDA(cudaGetLastError());
+	return PXB_OK;
+}
+int launch_lo_sample(pxb_ctx *ctx, const int32_t *inl_dev, const int64_t *count_dev, int m, int limit, int trials, uint64_t seed,
+                     uint64_t event, int32_t *off_dev, int32_t *idx_dev) {
+	if (limit > kLoMaxSample || trials + 1 > kListThreads) {
+		set_error("local optimisation sample of %d points / %d trials exceeds the kernel limits", limit, trials);
+		return PXB_ERR_UNSUPPORTED;
+	}
+	k_lo_sample<<<1, kListThreads, 0, ctx->stream>>>(inl_dev, count_dev, m, limit, trials, seed, event, off_dev, idx_dev);
+	ctx->launches++;
+	PXB_CUDA(cudaGetLastError());
+	return PXB_OK;
+}
+
+int launch_label_lists(pxb_ctx *ctx, const int32_t *labels_dev, int64_t N, int L, int32_t *off_dev, int32_t *idx_dev) {
+	if (L <= 0) return PXB_OK;
+	k_label_lists<<<(unsigned)L, kListThreads, 0, ctx->stream>>>(labels_dev, N, L, off_dev, idx_dev);
+	ctx->launches++;
+	PXB_CUDA(cudaGetLastError());
+	return PXB_OK;
+}
+
+int launch_select_models(pxb_ctx *ctx, const double *current, const double *fitted, const int32_t *ok, int L, int ms,
+                         double *cand) {
+	if (L <= 0) return PXB_OK;
+	const int n = L * ms;
+	k_select_models<<<(n + 127) / 128, 128, 0, ctx->stream>>>(current, fitted, ok, L, ms, cand);
+	ctx->launches++;
+	PXB_CUDA(cudaGetLastError());
+	return PXB_OK;
+}
+
+} // namespace pxb

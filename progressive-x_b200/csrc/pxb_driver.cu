@@ -678,16 +678,9 @@ class Driver {
 		out.resize(n);
 		return PXB_OK;
 	}
-	// batched non-minimal fits over index lists; weights (may be null) follow the reference's row indexing
-	// with T2 >= 0 the fitted models are scored in the same round trip (they never leave the device in between)
-	int fit_nonminimal(const std::vector<std::vector<int64_t>> &sets, const double *weights_by_row,
-	                   std::vector<double> &models_out, std::vector<int32_t> &ok, double T2 = -1.0,
-	                   std::vector<int64_t> *cnt = nullptr, std::vector<double> *val = nullptr,
-	                   std::vector<double> *shr = nullptr);
 	int launch_fit_family(int P, const int32_t *d_off, const int32_t *d_idx, const double *d_w, double *models_dev, int32_t *ok_dev);
 	std::vector<unsigned char> pack_host_;
 	int64_t smooth_edges_ = -1; // directed non-loop entries of the neighbour lists (counted once per graph)
-	int lo_labeling(const double *model, std::vector<int64_t> &inliers);
 	// Estimator::nonMinimalSampleSize(): H four-point 4, F bundle-adjustment solver 7, PnP bundle adjustment 4,
 	// vanishing point / 2D line: the minimal solver doubles as the non-minimal one, 2
 	size_t non_minimal_sample_size() const {
@@ -702,8 +695,22 @@ class Driver {
 	int apply_degensac(std::vector<double> &model, const int64_t *sample, uint64_t nested_seed, bool &valid, bool &updated);
 	size_t iteration_number_for(size_t inliers, double log_probability) const;
 	int propose(uint64_t round_seed, std::vector<double> &model_out, bool &found);
-	int local_optimization(Sampler &lo_sampler, std::vector<double> &best_model, Score &best_score, double T2);
-	int irls(std::vector<int64_t> &inliers, std::vector<double> &model, double T2, bool &success);
+	struct LoStep { // results of one local-optimisation step
+		int64_t inliers = 0;
+		std::vector<double> fitted, val, shr;
+		std::vector<int64_t> cnt;
+		std::vector<int32_t> ok;
+	};
+	int lo_step(const double *model, uint64_t lo_seed, uint64_t event, double T2, LoStep &out);
+	uint64_t lo_events_ = 0; // LO labellings of the current proposal (selects the sampling substreams)
+	int local_optimization(uint64_t lo_seed, std::vector<double> &best_model, Score &best_score, double T2);
+	struct TailStep { // results of one least-squares step
+		int64_t inliers = 0, cnt = 0;
+		std::vector<double> fitted;
+		double val = 0, shr = 0;
+		int32_t ok = 0;
+	};
+	int tail_step(const double *model, bool weighted, double T2, TailStep &out);
 	int putative_model_valid(const std::vector<double> &model, std::vector<double> &pref, bool &valid);
 	int pearl();
 	size_t predicted_unseen_inliers(size_t iterations, size_t compound_inliers) const;
@@ -742,84 +749,6 @@ int Driver::launch_fit_family(int P, const int32_t *d_off, const int32_t *d_idx,
 	case PXB_MODEL_VANISHING_POINT: return launch_fit_vp(ctx_, P, d_off, d_idx, d_w, models_dev, ok_dev);
 	default: return launch_fit_line(ctx_, P, d_off, d_idx, models_dev, ok_dev);
 	}
-}
-
-int Driver::fit_nonminimal(const std::vector<std::vector<int64_t>> &sets, const double *weights_by_row,
-                           std::vector<double> &models_out, std::vector<int32_t> &ok, double T2, std::vector<int64_t> *cnt,
-                           std::vector<double> *val, std::vector<double> *shr) {
-	const int P = (int)sets.size();
-	models_out.assign((size_t)P * ms_, 0.0);
-	ok.assign(P, 0);
-	if (P == 0) return PXB_OK;
-	Scoped t(prof_, "fit_nonminimal");
-	// offsets and indices in one array: they are adjacent on the device and go up in one copy
-	std::vector<int32_t> off(P + 1, 0);
-	for (int p = 0; p < P; ++p) off[p + 1] = off[p] + (int32_t)sets[p].size();
-	std::vector<int32_t> packed(off);
-	packed.reserve(off.size() + (size_t)off[P]);
-	for (const auto &st : sets)
-		for (int64_t i : st) packed.push_back((int32_t)i);
-	size_t wcount = 0;
-	if (weights_by_row) wcount = weights_by_point() ? (size_t)N_ : sets[0].size(); // row-indexed: one problem at a time (IRLS)
-	const size_t bytes = sizeof(int32_t) * packed.size() + 64;
-	PXB_TRY(ctx_->idx.reserve(bytes));
-	int32_t *d_off = ctx_->idx.as<int32_t>(), *d_idx = d_off + off.size();
-	// results packed on the device so that ONE copy brings them back: models | count | value | shared | ok
-	const size_t b_models = sizeof(double) * (size_t)P * ms_, b_sc = sizeof(int64_t) * (size_t)P;
-	const size_t pack_bytes = b_models + 3 * b_sc + sizeof(int32_t) * (size_t)P;
-	PXB_TRY(ctx_->pack.reserve(pack_bytes));
-	char *pk = ctx_->pack.as<char>();
-	double *d_models = reinterpret_cast<double *>(pk);
-	int64_t *d_cnt = reinterpret_cast<int64_t *>(pk + b_models);
-	double *d_val = reinterpret_cast<double *>(pk + b_models + b_sc), *d_shr = reinterpret_cast<double *>(pk + b_models + 2 * b_sc);
-	int32_t *d_ok = reinterpret_cast<int32_t *>(pk + b_models + 3 * b_sc);
-	double *d_w = nullptr;
-	if (weights_by_row) {
-		PXB_TRY(ctx_->pref2.reserve(sizeof(double) * wcount));
-		d_w = ctx_->pref2.as<double>();
-		PXB_TRY(api_h2d(ctx_, d_w, weights_by_row, sizeof(double) * wcount));
-	}
-	PXB_TRY(api_h2d(ctx_, d_off, packed.data(), sizeof(int32_t) * packed.size()));
-	PXB_TRY(launch_fit_family(P, d_off, d_idx, d_w, d_models, d_ok));
-	if (cnt) PXB_TRY(launch_score_compound(ctx_, d_models, P, T2, compound_dev(), d_cnt, d_val, d_shr));
-	pack_host_.resize(pack_bytes);
-	PXB_TRY(api_d2h(ctx_, pack_host_.data(), pk, pack_bytes));
-	PXB_TRY(api_sync(ctx_));
-	const unsigned char *h = pack_host_.data();
-	std::memcpy(models_out.data(), h, b_models);
-	std::memcpy(ok.data(), h + b_models + 3 * b_sc, sizeof(int32_t) * (size_t)P);
-	if (cnt) {
-		cnt->resize(P);
-		val->resize(P);
-		shr->resize(P);
-		std::memcpy(cnt->data(), h + b_models, b_sc);
-		std::memcpy(val->data(), h + b_models + b_sc, b_sc);
-		std::memcpy(shr->data(), h + b_models + 2 * b_sc, b_sc);
-	}
-	return PXB_OK;
-}
-
-// gcr/GCRANSAC.h:914-1022. Unary terms come from the device (k_lo_unary). Without a smoothness term the st-cut
-// decomposes per node: SINK (= inlier) iff the t-link residual source-sink is negative, i.e. e0 > e1.
-int Driver::lo_labeling(const double *model, std::vector<int64_t> &inliers) {
-	Scoped t(prof_, "lo_labeling");
-	inliers.clear();
-	std::vector<uint8_t> seg(N_);
-	if (!(s_.lambda > 0) || graph_.idx.empty()) { // the per-node decision is taken on the device (k_lo_unary_cut)
-		PXB_TRY(ctx_->models.reserve(sizeof(double) * ms_));
-		PXB_TRY(ctx_->outA.reserve((size_t)N_));
-		PXB_TRY(api_h2d(ctx_, ctx_->models.ptr, model, sizeof(double) * ms_));
-		PXB_TRY(launch_lo_unary_cut(ctx_, ctx_->models.as<double>(), s_.threshold, s_.lambda, ctx_->outA.as<uint8_t>()));
-		PXB_TRY(api_d2h(ctx_, seg.data(), ctx_->outA.ptr, (size_t)N_));
-		PXB_TRY(api_sync(ctx_));
-		for (int64_t i = 0; i < N_; ++i)
-			if (seg[i]) inliers.push_back(i);
-		return PXB_OK;
-	}
-	PXB_TRY(pxb_lo_labeling(ctx_, model, s_.threshold, s_.lambda, graph_.off.data(), graph_.idx.data(), seg.data()));
-	for (int64_t i = 0; i < N_; ++i)
-		if (seg[i]) inliers.push_back(i);
-	return PXB_OK;
 }
 
 // Estimator::isValidModel as called from GCRANSAC::run (:441-447) with threshold_ = truncated_threshold.
@@ -1025,43 +954,88 @@ size_t Driver::iteration_number_for(size_t inliers, double log_probability) cons
 	return static_cast<size_t>(iter) + 1;
 }
 
-// gcr/GCRANSAC.h:781-911. The <= 50 inner-RANSAC trials of one graph cut are independent given the cut: their samples
-// are drawn up front (same LO-sampler stream as the sequential loop), fitted in one launch, scored in one launch, and
-// the max_score bookkeeping is replayed in trial order.
-int Driver::local_optimization(Sampler &lo_sampler, std::vector<double> &best_model, Score &best_score, double T2) {
+// One step of graphCutLocalOptimization (gcr/GCRANSAC.h:806-905) as ONE stream-ordered chain: GCRANSAC::labeling of
+// `model` (unary decision for lambda = 0, st-cut otherwise) -> ordered inlier list -> the inner-RANSAC samples (drawn on
+// the device, one splitmix64 generator per trial seeded by lo_substream(lo_seed, event, trial) -- k_lo_sample in
+// pxb_chain.cu; oracle/px_sequential.py derives the same substreams) -> non-minimal fits -> scores; one packed copy back.
+int Driver::lo_step(const double *model, uint64_t lo_seed, uint64_t event, double T2, LoStep &out) {
+	Scoped t(prof_, "lo_step");
+	const int trials = (int)s_.max_local_optimization_number, limit = 7 * m_; // estimator.inlierLimit()
+	PXB_TRY(ctx_->models.reserve(sizeof(double) * ms_));
+	PXB_TRY(api_h2d(ctx_, ctx_->models.ptr, model, sizeof(double) * ms_));
+	uint8_t *d_seg = nullptr;
+	int32_t *d_mf_flags = nullptr;
+	if (!(s_.lambda > 0) || graph_.idx.empty()) { // no smoothness term: the st-cut decomposes per node (k_lo_unary_cut)
+		PXB_TRY(ctx_->outA.reserve((size_t)N_));
+		d_seg = ctx_->outA.as<uint8_t>();
+		PXB_TRY(launch_lo_unary_cut(ctx_, ctx_->models.as<double>(), s_.threshold, s_.lambda, d_seg));
+	} else {
+		PXB_TRY(lo_labeling_enqueue(ctx_, ctx_->models.as<double>(), s_.threshold, s_.lambda, graph_.off.data(), graph_.idx.data(),
+		                            &d_seg, &d_mf_flags));
+	}
+	// lists: inliers [N] | off [trials + 1] | idx [max(N, trials * limit)]
+	const size_t n_idx = std::max((size_t)N_, (size_t)trials * limit);
+	PXB_TRY(ctx_->idx.reserve(sizeof(int32_t) * ((size_t)N_ + trials + 1 + n_idx) + 64));
+	int32_t *d_inl = ctx_->idx.as<int32_t>(), *d_off = d_inl + N_, *d_idx = d_off + trials + 1;
+	// packed results: count | max-flow flags [16] | fitted [trials ms] | count / value / shared [trials] | ok [trials]
+	const size_t bM = sizeof(double) * (size_t)trials * ms_, bT = sizeof(double) * (size_t)trials;
+	const size_t o_flags = 8, o_fit = o_flags + 64, o_cnt = o_fit + bM, o_val = o_cnt + bT, o_shr = o_val + bT, o_ok = o_shr + bT,
+	             pack_bytes = o_ok + sizeof(int32_t) * (size_t)trials;
+	PXB_TRY(ctx_->pack.reserve(pack_bytes));
+	char *pk = ctx_->pack.as<char>();
+	PXB_CUDA(cudaMemsetAsync(pk, 0, pack_bytes, ctx_->stream));
+	PXB_TRY(launch_flag_compact(ctx_, d_seg, N_, d_inl, reinterpret_cast<int64_t *>(pk), nullptr));
+	PXB_TRY(launch_lo_sample(ctx_, d_inl, reinterpret_cast<int64_t *>(pk), m_, limit, trials, lo_seed, event, d_off, d_idx));
+	PXB_TRY(launch_fit_family(trials, d_off, d_idx, nullptr, reinterpret_cast<double *>(pk + o_fit), reinterpret_cast<int32_t *>(pk + o_ok)));
+	PXB_TRY(launch_score_compound(ctx_, reinterpret_cast<double *>(pk + o_fit), trials, T2, compound_dev(),
+	                              reinterpret_cast<int64_t *>(pk + o_cnt), reinterpret_cast<double *>(pk + o_val),
+	                              reinterpret_cast<double *>(pk + o_shr)));
+	if (d_mf_flags) PXB_CUDA(cudaMemcpyAsync(pk + o_flags, d_mf_flags, 64, cudaMemcpyDeviceToDevice, ctx_->stream));
+	pack_host_.resize(pack_bytes);
+	PXB_TRY(api_d2h(ctx_, pack_host_.data(), pk, pack_bytes));
+	PXB_TRY(api_sync(ctx_));
+	const unsigned char *h = pack_host_.data();
+	if (d_mf_flags) {
+		const int32_t *f = reinterpret_cast<const int32_t *>(h + o_flags);
+		if (f[7] != 1 || f[6] == 0) {
+			set_error("max-flow of the local optimisation did not converge");
+			return PXB_ERR_CUDA;
+		}
+	}
+	std::memcpy(&out.inliers, h, sizeof(int64_t));
+	out.fitted.assign(reinterpret_cast<const double *>(h + o_fit), reinterpret_cast<const double *>(h + o_fit) + (size_t)trials * ms_);
+	out.cnt.assign(reinterpret_cast<const int64_t *>(h + o_cnt), reinterpret_cast<const int64_t *>(h + o_cnt) + trials);
+	out.val.assign(reinterpret_cast<const double *>(h + o_val), reinterpret_cast<const double *>(h + o_val) + trials);
+	out.shr.assign(reinterpret_cast<const double *>(h + o_shr), reinterpret_cast<const double *>(h + o_shr) + trials);
+	out.ok.assign(reinterpret_cast<const int32_t *>(h + o_ok), reinterpret_cast<const int32_t *>(h + o_ok) + trials);
+	return PXB_OK;
+}
+
+// gcr/GCRANSAC.h:781-911. The <= 50 inner-RANSAC trials of one graph cut are independent given the cut: they are drawn,
+// fitted and scored in one device chain (lo_step) and the max_score bookkeeping is replayed in trial order.
+int Driver::local_optimization(uint64_t lo_seed, std::vector<double> &best_model, Score &best_score, double T2) {
 	const size_t inlier_limit = 7 * (size_t)m_; // estimator.inlierLimit()
 	Score max_score = best_score;
 	std::vector<double> lo_model = best_model;
-	std::vector<int64_t> inliers;
+	LoStep st;
 	++lo_number_;
 	while (++graph_cut_number_ < s_.max_graph_cut_number) {
 		bool updated = false;
-		PXB_TRY(lo_labeling(lo_model.data(), inliers));
-		const size_t sample_size = std::min(inlier_limit, inliers.size());
-		std::vector<std::vector<int64_t>> sets;
-		if (sample_size < inliers.size()) {
-			std::vector<size_t> pool(inliers.begin(), inliers.end()), sub(sample_size);
-			for (size_t trial = 0; trial < s_.max_local_optimization_number; ++trial) {
-				lo_sampler.sample(pool, sub.data(), sample_size);
-				sets.emplace_back(sub.begin(), sub.end());
-			}
-		} else if ((size_t)m_ < inliers.size()) {
-			sets.emplace_back(inliers); // every trial refits the same set: one evaluation is equivalent
-		} else {
+		PXB_TRY(lo_step(lo_model.data(), lo_seed, lo_events_++, T2, st));
+		size_t n_trials;
+		if (inlier_limit < (size_t)st.inliers)
+			n_trials = s_.max_local_optimization_number; // samples of inlier_limit points (:823-851)
+		else if ((size_t)m_ < (size_t)st.inliers)
+			n_trials = 1; // every trial refits the same set: one evaluation is equivalent
+		else
 			break;
-		}
-		std::vector<double> fitted;
-		std::vector<int32_t> ok;
-		std::vector<int64_t> cnt;
-		std::vector<double> val, shr;
-		PXB_TRY(fit_nonminimal(sets, nullptr, fitted, ok, T2, &cnt, &val, &shr));
-		for (size_t t = 0; t < sets.size(); ++t) {
-			if (!ok[t]) continue; // estimateModelNonminimal failed -> `continue` (:851-855)
-			const Score sc = finish_score(cnt[t], val[t], shr[t], max_score.inliers);
+		for (size_t t = 0; t < n_trials; ++t) {
+			if (!st.ok[t]) continue; // estimateModelNonminimal failed -> `continue` (:851-855)
+			const Score sc = finish_score(st.cnt[t], st.val[t], st.shr[t], max_score.inliers);
 			if (max_score.value < sc.value) {
 				updated = true;
 				max_score = sc;
-				lo_model.assign(fitted.begin() + t * ms_, fitted.begin() + (t + 1) * ms_);
+				lo_model.assign(st.fitted.begin() + t * ms_, st.fitted.begin() + (t + 1) * ms_);
 			}
 		}
 		if (!updated) break;
@@ -1073,34 +1047,47 @@ int Driver::local_optimization(Sampler &lo_sampler, std::vector<double> &best_mo
 	return PXB_OK;
 }
 
-// gcr/GCRANSAC.h:631-759 (single-model estimators: the models.size()==1 branch)
-int Driver::irls(std::vector<int64_t> &inliers, std::vector<double> &model, double T2, bool &success) {
-	success = false;
-	if (inliers.size() <= (size_t)m_) return PXB_OK;
-	size_t iterations = 0;
-	std::vector<double> weights(N_);
-	while (++iterations < s_.max_least_squares_iterations) {
-		// Tukey bisquare weights of the inliers (:658-669); all other entries are zero (:686-688 resets them)
-		PXB_TRY(pxb_tukey_weights(ctx_, model.data(), T2, weights.data()));
-		std::vector<double> w_point(N_, 0.0);
-		for (int64_t i : inliers) w_point[i] = weights[i];
-		// the solver reads weights_[row], row = 0..n-1 of the gathered sample (see k_fit_h)
-		std::vector<double> w_row(w_point.begin(), w_point.begin() + inliers.size());
-		std::vector<std::vector<int64_t>> sets(1, inliers);
-		std::vector<double> fitted;
-		std::vector<int32_t> ok;
-		const double *w_arg = !weighting_applicable() ? nullptr : (weights_by_point() ? w_point.data() : w_row.data());
-		std::vector<int64_t> cnt;
-		std::vector<double> val, shr;
-		PXB_TRY(fit_nonminimal(sets, w_arg, fitted, ok, T2, &cnt, &val, &shr));
-		if (!ok[0]) break;
-		const Score sc = finish_score(cnt[0], val[0], shr[0], 0);
-		if ((size_t)sc.inliers < (size_t)m_) break;
-		if ((size_t)sc.inliers <= inliers.size()) break;
-		model = fitted;
-		PXB_TRY(inliers_of(model.data(), T2, inliers));
+// One least-squares step of the tail of GCRANSAC::run as ONE stream-ordered chain: ordered inlier list of `model`
+// (r2 < T2, the list getScore would return) -> [Tukey bisquare weights of `model`, GCRANSAC.h:658-669] -> one non-minimal
+// fit on all of them -> score of the fit; one packed copy back. The Tukey weight of a point is zero exactly when the
+// point is not an inlier, so the per-point weight array of the reference (:686-688: zero for non-inliers) is the kernel's
+// output as it is; H / F solvers read it by ROW of the gathered sample, the vanishing-point solver by point (k_fit_*).
+int Driver::tail_step(const double *model, bool weighted, double T2, TailStep &out) {
+	Scoped t(prof_, "tail_step");
+	const int64_t words = (N_ + 31) / 32;
+	PXB_TRY(ctx_->models.reserve(sizeof(double) * ms_));
+	PXB_TRY(api_h2d(ctx_, ctx_->models.ptr, model, sizeof(double) * ms_));
+	PXB_TRY(ctx_->mask.reserve(sizeof(uint32_t) * (size_t)words));
+	PXB_TRY(launch_residual_matrix(ctx_, ctx_->models.as<double>(), 1, T2, nullptr, nullptr, ctx_->mask.as<uint32_t>()));
+	PXB_TRY(ctx_->idx.reserve(sizeof(int32_t) * ((size_t)N_ + 2) + 64));
+	int32_t *d_off = ctx_->idx.as<int32_t>(), *d_inl = d_off + 2;
+	// packed results: count | fitted [ms] | count / value / shared of the fit | ok
+	const size_t o_fit = 8, o_cnt = o_fit + sizeof(double) * ms_, o_val = o_cnt + 8, o_shr = o_val + 8, o_ok = o_shr + 8,
+	             pack_bytes = o_ok + 8;
+	PXB_TRY(ctx_->pack.reserve(pack_bytes));
+	char *pk = ctx_->pack.as<char>();
+	PXB_CUDA(cudaMemsetAsync(pk, 0, pack_bytes, ctx_->stream));
+	PXB_TRY(launch_mask_compact(ctx_, ctx_->mask.as<uint32_t>(), N_, d_inl, reinterpret_cast<int64_t *>(pk), d_off));
+	double *d_w = nullptr;
+	if (weighted) {
+		PXB_TRY(ctx_->pref2.reserve(sizeof(double) * (size_t)N_));
+		d_w = ctx_->pref2.as<double>();
+		PXB_TRY(launch_tukey(ctx_, ctx_->models.as<double>(), T2, d_w));
 	}
-	success = iterations > 1;
+	PXB_TRY(launch_fit_family(1, d_off, d_inl, d_w, reinterpret_cast<double *>(pk + o_fit), reinterpret_cast<int32_t *>(pk + o_ok)));
+	PXB_TRY(launch_score_compound(ctx_, reinterpret_cast<double *>(pk + o_fit), 1, T2, compound_dev(),
+	                              reinterpret_cast<int64_t *>(pk + o_cnt), reinterpret_cast<double *>(pk + o_val),
+	                              reinterpret_cast<double *>(pk + o_shr)));
+	pack_host_.resize(pack_bytes);
+	PXB_TRY(api_d2h(ctx_, pack_host_.data(), pk, pack_bytes));
+	PXB_TRY(api_sync(ctx_));
+	const unsigned char *h = pack_host_.data();
+	std::memcpy(&out.inliers, h, 8);
+	out.fitted.assign(reinterpret_cast<const double *>(h + o_fit), reinterpret_cast<const double *>(h + o_fit) + ms_);
+	std::memcpy(&out.cnt, h + o_cnt, 8);
+	std::memcpy(&out.val, h + o_val, 8);
+	std::memcpy(&out.shr, h + o_shr, 8);
+	std::memcpy(&out.ok, h + o_ok, 4);
 	return PXB_OK;
 }
 
@@ -1122,7 +1109,8 @@ int Driver::propose(uint64_t round_seed, std::vector<double> &model_out, bool &f
 		main_sampler.reset(new ProsacSampler(round_seed * 2 + 1, (size_t)m_, (size_t)N_));
 	else
 		main_sampler.reset(new UniformSampler(round_seed * 2 + 1));
-	UniformSampler lo_sampler(round_seed * 2 + 2);
+	const uint64_t lo_seed = round_seed * 2 + 2;
+	lo_events_ = 0;
 	std::vector<size_t> pool(N_);
 	std::iota(pool.begin(), pool.end(), 0);
 
@@ -1214,7 +1202,7 @@ int Driver::propose(uint64_t round_seed, std::vector<double> &model_out, bool &f
 		}
 		if (do_local_optimization) { // :482-503
 			++lo_number_;
-			PXB_TRY(local_optimization(lo_sampler, best_model, best_score, T2));
+			PXB_TRY(local_optimization(lo_seed, best_model, best_score, T2));
 			max_iteration = iteration_number_for((size_t)best_score.inliers, log_probability);
 		}
 	}
@@ -1222,46 +1210,54 @@ int Driver::propose(uint64_t round_seed, std::vector<double> &model_out, bool &f
 
 	if (lo_number_ == 0) { // :531-544 final LO if it never ran
 		++lo_number_;
-		PXB_TRY(local_optimization(lo_sampler, best_model, best_score, T2));
+		PXB_TRY(local_optimization(lo_seed, best_model, best_score, T2));
 	}
-	std::vector<int64_t> best_inliers;
-	PXB_TRY(inliers_of(best_model.data(), T2, best_inliers));
-	best_score.inliers = (int64_t)best_inliers.size();
-
-	// :561-590 iterated least squares polishing
+	// :546-559 the inliers of the best model; :561-590 iterated least squares (GCRANSAC.h:631-759, the single-model branch);
+	// :592-618 else one least-squares fit on all inliers. Every step is one device chain (tail_step): the inlier LIST of
+	// a model is only needed on the host once, at the very end.
+	const bool weighted = weighting_applicable();
+	TailStep first, ts;
+	PXB_TRY(tail_step(best_model.data(), weighted, T2, first));
+	best_score.inliers = first.inliers;
 	bool refit_applied = false;
 	{
 		std::vector<double> model = best_model;
-		std::vector<int64_t> inl = best_inliers;
+		size_t current = (size_t)first.inliers, iterations = 0;
 		bool success = false;
-		PXB_TRY(irls(inl, model, T2, success));
-		if (success) {
-			std::vector<int64_t> cnt;
-			std::vector<double> val, shr;
-			PXB_TRY(score_models(model.data(), 1, T2, cnt, val, shr));
-			const Score sc = finish_score(cnt[0], val[0], shr[0], 0);
-			if (best_score.value < sc.value) {
-				refit_applied = true;
-				best_model = model;
-				PXB_TRY(inliers_of(best_model.data(), T2, best_inliers));
+		Score irls_score;
+		if (current > (size_t)m_) {
+			ts = first;
+			bool have_step = true; // `ts` holds the step of `model`
+			while (++iterations < s_.max_least_squares_iterations) {
+				if (!have_step) PXB_TRY(tail_step(model.data(), weighted, T2, ts));
+				have_step = false;
+				if (!ts.ok) break;
+				const Score sc = finish_score(ts.cnt, ts.val, ts.shr, 0);
+				if ((size_t)sc.inliers < (size_t)m_) break;
+				if ((size_t)sc.inliers <= current) break;
+				model = ts.fitted;
+				irls_score = sc;               // = the score getScore gives the polished model (:575-583)
+				current = (size_t)sc.inliers;  // = |inliers of the new model| (same r2 < T2 predicate)
 			}
+			success = iterations > 1;
+		}
+		if (success && best_score.value < irls_score.value) {
+			refit_applied = true;
+			best_model = model;
 		}
 	}
-	if (!refit_applied) { // :592-618 one least-squares fit on all inliers
-		std::vector<std::vector<int64_t>> sets(1, best_inliers);
-		std::vector<double> fitted;
-		std::vector<int32_t> ok;
-		std::vector<int64_t> cnt;
-		std::vector<double> val, shr;
-		PXB_TRY(fit_nonminimal(sets, nullptr, fitted, ok, T2, &cnt, &val, &shr));
-		if (ok[0]) {
-			const Score sc = finish_score(cnt[0], val[0], shr[0], 0);
-			if (best_score.value < sc.value) {
-				best_model = fitted;
-				PXB_TRY(inliers_of(best_model.data(), T2, best_inliers));
-			}
+	if (!refit_applied) { // :592-618 one (unweighted) least-squares fit on all inliers of the best model
+		if (weighted)
+			PXB_TRY(tail_step(best_model.data(), false, T2, ts));
+		else
+			ts = first; // the first step already was that fit
+		if (ts.ok) {
+			const Score sc = finish_score(ts.cnt, ts.val, ts.shr, 0);
+			if (best_score.value < sc.value) best_model = ts.fitted;
 		}
 	}
+	std::vector<int64_t> best_inliers;
+	PXB_TRY(inliers_of(best_model.data(), T2, best_inliers));
 	proposal_inliers_ = best_inliers; // statistics.inliers (:621)
 	model_out = best_model;
 	found = true;

@@ -991,8 +991,8 @@ __global__ void k_lo_collect(int64_t N, const int32_t *__restrict__ h, int n_nod
 int launch_lo_unary(pxb_ctx *ctx, const double *model, double thr, double lambda, double *d, double *e0, double *e1);
 
 // model_dev: device pointer to the model; seg_host: N bytes, 1 = inlier (SINK side)
-int lo_labeling_device(pxb_ctx *ctx, const double *model_dev, double thr, double lambda, const int32_t *csr_off_host,
-                       const int32_t *csr_idx_host, uint8_t *seg_host) {
+int lo_labeling_enqueue(pxb_ctx *ctx, const double *model_dev, double thr, double lambda, const int32_t *csr_off_host,
+                        const int32_t *csr_idx_host, uint8_t **seg_dev_out, int32_t **flags_dev_out) {
 	const int64_t N = ctx->pts.N;
 	PXB_TRY(lo_skeleton(ctx, N, csr_off_host, csr_idx_host));
 	const LoSkeleton &g_lo = *static_cast<LoSkeleton *>(ctx->lo_skeleton);
@@ -1031,9 +1031,19 @@ int lo_labeling_device(pxb_ctx *ctx, const double *model_dev, double thr, double
 	ctx->launches++;
 	k_lo_collect<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(N, d_h0, n, d_seg);
 	ctx->launches++;
+	*seg_dev_out = d_seg;
+	*flags_dev_out = d_flags;
+	return PXB_OK;
+}
+
+int lo_labeling_device(pxb_ctx *ctx, const double *model_dev, double thr, double lambda, const int32_t *csr_off_host,
+                       const int32_t *csr_idx_host, uint8_t *seg_host) {
+	uint8_t *d_seg = nullptr;
+	int32_t *d_flags = nullptr;
+	PXB_TRY(lo_labeling_enqueue(ctx, model_dev, thr, lambda, csr_off_host, csr_idx_host, &d_seg, &d_flags));
 	int32_t flags[16];
-	PXB_CUDA(cudaMemcpyAsync(seg_host, d_seg, (size_t)N, cudaMemcpyDeviceToHost, st));
-	PXB_CUDA(cudaMemcpyAsync(flags, d_flags, sizeof(flags), cudaMemcpyDeviceToHost, st));
+	PXB_CUDA(cudaMemcpyAsync(seg_host, d_seg, (size_t)ctx->pts.N, cudaMemcpyDeviceToHost, ctx->stream));
+	PXB_CUDA(cudaMemcpyAsync(flags, d_flags, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
 	PXB_TRY(ctx_wait(ctx));
 	if (flags[7] != 1 || flags[6] == 0) {
 		set_error("max-flow did not converge within %d relabel rounds", kMaxRounds);

@@ -143,6 +143,14 @@ int pearl_label_device(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t L1,
 int pearl_label_enqueue(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t L1, double lambda, double label_cost,
                         const int32_t *csr_off_host, const int32_t *csr_idx_host, int64_t n_dir, const int32_t *init_labels_dev,
                         int32_t *labels_out_dev, double *energy_host, double **energy_dev_out);
+int launch_flag_compact(pxb_ctx *ctx, const uint8_t *flags_dev, int64_t N, int32_t *idx_dev, int64_t *count_dev, int32_t *off2_dev);
+int launch_mask_compact(pxb_ctx *ctx, const uint32_t *mask_dev, int64_t N, int32_t *idx_dev, int64_t *count_dev, int32_t *off2_dev);
+int launch_lo_sample(pxb_ctx *ctx, const int32_t *inl_dev, const int64_t *count_dev, int m, int limit, int trials, uint64_t seed,
+                     uint64_t event, int32_t *off_dev, int32_t *idx_dev);
+// GCRANSAC::labeling with the 0/1 result left on the device (*seg_dev_out, N bytes) and the max-flow status words in
+// *flags_dev_out (16 int32; converged iff flags[7] == 1 && flags[6] != 0): asynchronous
+int lo_labeling_enqueue(pxb_ctx *ctx, const double *model_dev, double thr, double lambda, const int32_t *csr_off_host,
+                        const int32_t *csr_idx_host, uint8_t **seg_dev_out, int32_t **flags_dev_out);
 int launch_label_lists(pxb_ctx *ctx, const int32_t *labels_dev, int64_t N, int L, int32_t *off_dev, int32_t *idx_dev);
 int launch_select_models(pxb_ctx *ctx, const double *current, const double *fitted, const int32_t *ok, int L, int ms,
                          double *cand);
@@ -160,7 +168,6 @@ int launch_segment_sums(pxb_ctx *ctx, const double *models, int64_t L, const int
 int launch_lo_unary(pxb_ctx *ctx, const double *model, double thr, double lambda, double *d, double *e0, double *e1);
 int launch_lo_unary_cut(pxb_ctx *ctx, const double *model, double thr, double lambda, uint8_t *inlier);
 int launch_tukey(pxb_ctx *ctx, const double *model, double T2, double *w);
-int launch_inlier_compact(pxb_ctx *ctx, const double *model, double T2, int64_t *inliers, int64_t *n_inliers_dev);
 int launch_solve_plane_parallax(pxb_ctx *ctx, const int64_t *samples, int64_t K, const double *H_dev, double *models_out,
                                 int32_t *n_models, uint8_t *sample_valid, uint8_t *model_valid);
 int launch_solve_minimal(pxb_ctx *ctx, const int64_t *samples, int64_t K, double *models_out, int32_t *n_models,
