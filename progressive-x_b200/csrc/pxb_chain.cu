@@ -163,42 +163,58 @@ __device__ __forceinline__ uint64_t lo_substream(uint64_t seed, uint64_t event, 
 }
 constexpr int kLoMaxSample = 64;
 
-__global__ void __launch_bounds__(kListThreads)
+// One warp per trial. splitmix64 is counter based (output k = mix(s0 + k * golden)), so a warp computes 32 generator
+// outputs at once; they are then CONSUMED in order exactly like the sequential sampler does: an output r >= lim is
+// rejected (uniform_int_distribution), a value already in the set is rejected (unique_set redraws that position).
+__global__ void __launch_bounds__(32)
     k_lo_sample(const int32_t *__restrict__ inl, const int64_t *__restrict__ count_in, int m, int limit, int trials,
                 uint64_t seed, uint64_t event, int32_t *__restrict__ off /*trials + 1*/, int32_t *__restrict__ idx) {
 	const int64_t count = count_in[0];
-	const int tid = threadIdx.x;
+	const int t = blockIdx.x, lane = threadIdx.x;
 	if (count > (int64_t)limit) {
-		if (tid <= trials) off[tid] = tid * limit;
-		if (tid >= trials) return;
-		uint64_t s = lo_substream(seed, event, (uint64_t)tid);
-		if (s == 0) s = 0x9E3779B97F4A7C15ull;
+		if (lane == 0) {
+			off[t] = t * limit;
+			if (t == trials - 1) off[trials] = trials * limit;
+		}
+		uint64_t s0 = lo_substream(seed, event, (uint64_t)t);
+		if (s0 == 0) s0 = 0x9E3779B97F4A7C15ull;
 		const uint64_t range = (uint64_t)count; // uniform(max = count - 1)
 		const uint64_t lim = UINT64_MAX - (UINT64_MAX % range);
-		int32_t pos[kLoMaxSample];
-		for (int i = 0; i < limit; ++i) {
-			for (;;) {
-				uint64_t r;
-				do r = lo_rng_next(s); while (r >= lim);
-				const int32_t v = (int32_t)(r % range);
-				bool dup = false;
-				for (int j = i - 1; j >= 0; --j)
-					if (pos[j] == v) {
-						dup = true;
-						break;
+		int32_t acc_lo = -1, acc_hi = -1; // lane l holds accepted[l] and accepted[l + 32]
+		int a = 0;
+		for (uint64_t k_base = 0; a < limit; k_base += 32) {
+			uint64_t z = s0 + (k_base + (uint64_t)lane + 1) * 0x9E3779B97F4A7C15ull;
+			z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+			z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+			const uint64_t r = z ^ (z >> 31);
+			const int valid = r < lim;
+			const int32_t v = (int32_t)(r % range);
+			for (int j = 0; j < 32 && a < limit; ++j) {
+				const int32_t vj = __shfl_sync(0xffffffffu, v, j);
+				const int okj = __shfl_sync(0xffffffffu, valid, j);
+				const bool hit = (lane < a && acc_lo == vj) || (lane + 32 < a && acc_hi == vj);
+				const bool dup = __any_sync(0xffffffffu, hit);
+				if (okj && !dup) {
+					if (a < 32) {
+						if (lane == a) acc_lo = vj;
+					} else if (lane == a - 32) {
+						acc_hi = vj;
 					}
-				if (!dup) {
-					pos[i] = v;
-					break;
+					++a;
 				}
 			}
 		}
-		for (int i = 0; i < limit; ++i) idx[tid * limit + i] = inl[pos[i]];
+		if (lane < limit) idx[t * limit + lane] = inl[acc_lo];
+		if (lane + 32 < limit) idx[t * limit + lane + 32] = inl[acc_hi];
 	} else if (count > (int64_t)m) {
-		if (tid <= trials) off[tid] = tid == 0 ? 0 : (int32_t)count;
-		for (int64_t i = tid; i < count; i += kListThreads) idx[i] = inl[i];
-	} else {
-		if (tid <= trials) off[tid] = 0;
+		if (lane == 0) {
+			off[t] = t == 0 ? 0 : (int32_t)count;
+			if (t == trials - 1) off[trials] = (int32_t)count;
+		}
+		for (int64_t i = (int64_t)t * 32 + lane; i < count; i += (int64_t)trials * 32) idx[i] = inl[i];
+	} else if (lane == 0) {
+		off[t] = 0;
+		if (t == trials - 1) off[trials] = 0;
 	}
 }
 
@@ -216,11 +232,11 @@ int launch_mask_compact(pxb_ctx *ctx, const uint32_t *mask_dev, int64_t N, int32
 }
 int launch_lo_sample(pxb_ctx *ctx, const int32_t *inl_dev, const int64_t *count_dev, int m, int limit, int trials, uint64_t seed,
                      uint64_t event, int32_t *off_dev, int32_t *idx_dev) {
-	if (limit > kLoMaxSample || trials + 1 > kListThreads) {
+	if (limit > kLoMaxSample || trials < 1) {
 		set_error("local optimisation sample of %d points / %d trials exceeds the kernel limits", limit, trials);
 		return PXB_ERR_UNSUPPORTED;
 	}
-	k_lo_sample<<<1, kListThreads, 0, ctx->stream>>>(inl_dev, count_dev, m, limit, trials, seed, event, off_dev, idx_dev);
+	k_lo_sample<<<(unsigned)trials, 32, 0, ctx->stream>>>(inl_dev, count_dev, m, limit, trials, seed, event, off_dev, idx_dev);
 	ctx->launches++;
 	PXB_CUDA(cudaGetLastError());
 	return PXB_OK;

@@ -985,12 +985,13 @@ int Driver::lo_step(const double *model, uint64_t lo_seed, uint64_t event, doubl
 	char *pk = ctx_->pack.as<char>();
 	PXB_CUDA(cudaMemsetAsync(pk, 0, pack_bytes, ctx_->stream));
 	PXB_TRY(launch_flag_compact(ctx_, d_seg, N_, d_inl, reinterpret_cast<int64_t *>(pk), nullptr));
+	// (the labelling's scratch is shared with the score kernel's partial sums: take its status words now)
+	if (d_mf_flags) PXB_CUDA(cudaMemcpyAsync(pk + o_flags, d_mf_flags, 64, cudaMemcpyDeviceToDevice, ctx_->stream));
 	PXB_TRY(launch_lo_sample(ctx_, d_inl, reinterpret_cast<int64_t *>(pk), m_, limit, trials, lo_seed, event, d_off, d_idx));
 	PXB_TRY(launch_fit_family(trials, d_off, d_idx, nullptr, reinterpret_cast<double *>(pk + o_fit), reinterpret_cast<int32_t *>(pk + o_ok)));
 	PXB_TRY(launch_score_compound(ctx_, reinterpret_cast<double *>(pk + o_fit), trials, T2, compound_dev(),
 	                              reinterpret_cast<int64_t *>(pk + o_cnt), reinterpret_cast<double *>(pk + o_val),
 	                              reinterpret_cast<double *>(pk + o_shr)));
-	if (d_mf_flags) PXB_CUDA(cudaMemcpyAsync(pk + o_flags, d_mf_flags, 64, cudaMemcpyDeviceToDevice, ctx_->stream));
 	pack_host_.resize(pack_bytes);
 	PXB_TRY(api_d2h(ctx_, pack_host_.data(), pk, pack_bytes));
 	PXB_TRY(api_sync(ctx_));

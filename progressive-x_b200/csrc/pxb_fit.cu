@@ -219,49 +219,65 @@ __global__ void __launch_bounds__(kFitThreads)
 		for (int r = 0; r < 8; ++r) acc[36 + r] = add(acc[36 + r], add(mul(ra[r], ba), mul(rb[r], bb)));
 	}
 	fit_block_sum_vec<44>(acc, s_vec, s_acc);
-	if (tid != 0) return;
-	// ---- solve the 8x8 SPD system: Gaussian elimination with partial pivoting (robust to semi-definite input)
-	double M[8][9];
-	{
-		int a = 0;
-		for (int r = 0; r < 8; ++r)
-			for (int c = r; c < 8; ++c, ++a) {
-				M[r][c] = s_acc[a];
-				M[c][r] = s_acc[a];
-			}
-		for (int r = 0; r < 8; ++r) M[r][8] = s_acc[36 + r];
-	}
-	bool singular = false;
+	if (tid >= 32) return;
+	// ---- solve the 8x8 SPD system: Gaussian elimination with partial pivoting (robust to semi-definite input).
+	// Lane r < 8 holds row r of [A^T A | A^T b] in registers; pivot rows travel by shuffle. Every element sees exactly the
+	// operations of the sequential elimination (same pivot choice: the first row holding the largest |entry|), so the
+	// result is bit-identical to it -- only the rows are processed side by side.
+	const int lane = tid;
+	double row[9];
+#pragma unroll
 	for (int c = 0; c < 8; ++c) {
+		const int r0 = lane < c ? lane : c, c0 = lane < c ? c : lane; // upper-triangle index of (lane, c)
+		row[c] = lane < 8 ? s_acc[r0 * 8 - r0 * (r0 - 1) / 2 + (c0 - r0)] : 0.0;
+	}
+	row[8] = lane < 8 ? s_acc[36 + lane] : 0.0;
+	bool singular = false;
+#pragma unroll
+	for (int c = 0; c < 8; ++c) {
+		if (singular) break; // warp-uniform
+		const double mine = fabs(row[c]);
+		double best = __shfl_sync(0xffffffffu, mine, c);
 		int piv = c;
-		double best = fabs(M[c][c]);
-		for (int r = c + 1; r < 8; ++r)
-			if (fabs(M[r][c]) > best) {
-				best = fabs(M[r][c]);
+#pragma unroll
+		for (int r = c + 1; r < 8; ++r) {
+			const double v = __shfl_sync(0xffffffffu, mine, r);
+			if (v > best) {
+				best = v;
 				piv = r;
 			}
+		}
 		if (!(best > 0.0)) {
 			singular = true;
 			break;
 		}
-		if (piv != c)
-			for (int j = 0; j < 9; ++j) {
-				const double t = M[c][j];
-				M[c][j] = M[piv][j];
-				M[piv][j] = t;
-			}
-		for (int r = c + 1; r < 8; ++r) {
-			const double f = divd(M[r][c], M[c][c]);
-			for (int j = c; j < 9; ++j) M[r][j] = sub(M[r][j], mul(f, M[c][j]));
+		const int src = lane == c ? piv : (lane == piv ? c : lane); // swap rows c and piv
+		double pc[9];
+#pragma unroll
+		for (int j = 0; j < 9; ++j) {
+			row[j] = __shfl_sync(0xffffffffu, row[j], src);
+			pc[j] = __shfl_sync(0xffffffffu, row[j], c);
+		}
+		if (lane > c && lane < 8) {
+			const double f = divd(row[c], pc[c]);
+#pragma unroll
+			for (int j = 0; j < 9; ++j)
+				if (j >= c) row[j] = sub(row[j], mul(f, pc[j]));
 		}
 	}
 	double h[9];
-	if (!singular)
+#pragma unroll
+	for (int r = 0; r < 9; ++r) h[r] = 0.0;
+	if (!singular) {
+#pragma unroll
 		for (int r = 7; r >= 0; --r) {
-			double v = M[r][8];
-			for (int j = r + 1; j < 8; ++j) v = sub(v, mul(M[r][j], h[j]));
-			h[r] = divd(v, M[r][r]);
+			double v = row[8];
+#pragma unroll
+			for (int j = r + 1; j < 8; ++j) v = sub(v, mul(row[j], h[j]));
+			h[r] = __shfl_sync(0xffffffffu, divd(v, row[r]), r);
 		}
+	}
+	if (lane != 0) return;
 	h[8] = 1.0;
 	bool bad = singular;
 	for (int r = 0; r < 8 && !bad; ++r) bad = !(fabs(h[r]) <= DBL_MAX);

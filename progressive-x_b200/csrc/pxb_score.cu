@@ -18,6 +18,8 @@
 //   inliers of a 128-point chunk in ascending point order, sequentially (exactly the reference's loop order)
 //   -> the 8 chunks of a block in order -> blocks (1024 points) in order (k_score_finalize).
 // Counts are exact integers. Skipped pairs contribute exactly nothing in the reference as well (r2 >= T2).
+#include <algorithm>
+
 #include "pxb_internal.h"
 #include "pxb_screen.cuh"
 
@@ -193,7 +195,7 @@ __global__ void __launch_bounds__(kThreads, 3)
     k_score_screened(const double *__restrict__ soa, int64_t stride, int64_t N, const float *__restrict__ pf,
                      const float *__restrict__ pq, const float *__restrict__ consts, const float *__restrict__ mfg,
                      const double *__restrict__ models, int64_t K, double T2, const double *__restrict__ compound_pref,
-                     ScorePartial *__restrict__ partials, int nchunks) {
+                     ScorePartial *__restrict__ partials, int nchunks, int tile /* hypotheses per pass, <= kScHyps */) {
 	using L = ScoreSmem<TYPE, HAS_CP>;
 	constexpr int DIM = L::DIM, MS = ModelTraits<TYPE>::kSize, MP = L::MP, MF = L::MF;
 	extern __shared__ __align__(16) unsigned char smem[];
@@ -232,9 +234,9 @@ __global__ void __launch_bounds__(kThreads, 3)
 	const bool full = warp_base + 32 * kScP <= N; // interior warps run without validity predicates (warp-uniform)
 
 	for (int pass = 0; pass < PASSES; ++pass) {
-		const int64_t k0 = ((int64_t)blockIdx.y * PASSES + pass) * kScHyps;
+		const int64_t k0 = ((int64_t)blockIdx.y * PASSES + pass) * tile;
 		if (k0 >= K) break; // block-uniform
-		const int nk = (int)min((int64_t)kScHyps, K - k0);
+		const int nk = (int)min((int64_t)tile, K - k0);
 		for (int t = threadIdx.x; t < nk * MS; t += kThreads) s_models[(t / MS) * MP + (t % MS)] = models[k0 * MS + t];
 		for (int t = threadIdx.x; t < nk * MF; t += kThreads) s_mf[t] = __ldg(mfg + k0 * MF + t);
 		__syncthreads();
@@ -280,7 +282,7 @@ __global__ void k_score_finalize(const ScorePartial *__restrict__ partials, int6
 
 template <int TYPE, bool HAS_CP, int PASSES>
 static void launch_screened(pxb_ctx *ctx, int nchunks, const float *consts, const float *mf, const double *m, int64_t kk,
-                            double T2, const double *cp, ScorePartial *pp) {
+                            double T2, const double *cp, ScorePartial *pp, int tile_hyps) {
 	const Points &p = ctx->pts;
 	constexpr int kBytes = (int)ScoreSmem<TYPE, HAS_CP>::kBytes;
 	// opt in to > 48 KB of dynamic shared memory: once per device and instantiation (every API call counts when eight
@@ -290,10 +292,10 @@ static void launch_screened(pxb_ctx *ctx, int nchunks, const float *consts, cons
 		cudaFuncSetAttribute(k_score_screened<TYPE, HAS_CP, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBytes);
 		if (ctx->device >= 0 && ctx->device < 64) opted_in[ctx->device] = true;
 	}
-	const int64_t tile = (int64_t)kScHyps * PASSES;
+	const int64_t tile = (int64_t)tile_hyps * PASSES;
 	dim3 grid((unsigned)nchunks, (unsigned)((kk + tile - 1) / tile));
 	k_score_screened<TYPE, HAS_CP, PASSES><<<grid, kThreads, kBytes, ctx->stream>>>(p.soa, p.stride, p.N, p.f32n, p.q, consts, mf, m,
-	                                                                             kk, T2, cp, pp, nchunks);
+	                                                                             kk, T2, cp, pp, nchunks, tile_hyps);
 }
 
 template <int TYPE>
@@ -306,12 +308,20 @@ static int launch_partial(pxb_ctx *ctx, int nchunks, const double *m, int64_t kk
 	// big batches walk 4 tiles of 32 hypotheses per block (the per-block prologue -- staging 1024 points -- is paid once);
 	// RANSAC-sized batches keep one tile per block so that the grid still fills the GPU
 	const bool big = kk * nchunks >= (int64_t)4 * 32 * 3 * ctx->sm_count * 2;
+	// small batches (the <= 50 refits of a local-optimisation step, the single model of a least-squares step): fewer
+	// hypotheses per block so that the grid still covers the SMs -- the hypothesis loop of a warp is sequential, and these
+	// models are inlier rich (every inlier takes the exact float64 path). The sums do not depend on the tile.
+	int tile = kScHyps;
+	if (!big) {
+		const int64_t want_blocks = 2 * (int64_t)ctx->sm_count;
+		tile = (int)std::min<int64_t>(kScHyps, std::max<int64_t>(1, kk * nchunks / want_blocks));
+	}
 	if (cp) {
-		if (big) launch_screened<TYPE, true, 4>(ctx, nchunks, consts, mf, m, kk, T2, cp, pp);
-		else launch_screened<TYPE, true, 1>(ctx, nchunks, consts, mf, m, kk, T2, cp, pp);
+		if (big) launch_screened<TYPE, true, 4>(ctx, nchunks, consts, mf, m, kk, T2, cp, pp, kScHyps);
+		else launch_screened<TYPE, true, 1>(ctx, nchunks, consts, mf, m, kk, T2, cp, pp, tile);
 	} else {
-		if (big) launch_screened<TYPE, false, 4>(ctx, nchunks, consts, mf, m, kk, T2, cp, pp);
-		else launch_screened<TYPE, false, 1>(ctx, nchunks, consts, mf, m, kk, T2, cp, pp);
+		if (big) launch_screened<TYPE, false, 4>(ctx, nchunks, consts, mf, m, kk, T2, cp, pp, kScHyps);
+		else launch_screened<TYPE, false, 1>(ctx, nchunks, consts, mf, m, kk, T2, cp, pp, tile);
 	}
 	ctx->launches++;
 	return PXB_OK;
