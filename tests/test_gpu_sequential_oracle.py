@@ -21,6 +21,35 @@ pytestmark = pytest.mark.gpu
 G = np.load(Path(__file__).resolve().parent / "golden" / "reference_scenes.npz")
 
 
+def _same_up_to_exact_energy_ties(model_type, rows, models, m_o, labels, l_o, ms, thr, lam, label_cost, graph, what):
+    """True when the GPU driver and the sequential oracle agree: same instance count, models within the 1e-5 contract,
+    and per-point labels identical -- or, where a few labels differ, the two labellings are an EXACT TIE of the PEARL
+    energy (data + Potts + label costs, evaluated by the reference's own GCoptimization::compute_energy build): the
+    reference decides such ties by the rounding noise of BK's augmentation order (GCoptimization.cpp:1286), which no
+    other max-flow can reproduce. Raises with the details otherwise."""
+    from oracle import oracle as O
+    l_o = l_o.astype(np.int32)
+    M = models.shape[0] * models.shape[1] // ms
+    assert M == m_o.shape[0], f"{what}: {M} instances on the GPU, {m_o.shape[0]} in the sequential loop"
+    if M:
+        a, b = models.reshape(M, ms), m_o
+        rel = np.abs(a - b).max(1) / np.abs(b).max(1)
+        assert np.all(rel <= 1e-5), f"{what}: model parameters differ by {rel.max():.2e} relative"
+    if np.array_equal(labels, l_o):
+        return True
+    differing = int(np.sum(labels != l_o))
+    assert lam > 0 and graph is not None and M > 1, f"{what}: {differing} labels differ without a smoothness term"
+    assert differing <= max(2, len(labels) // 100), f"{what}: {differing} labels differ"
+    with _native.Context(0) as ctx:
+        ctx.upload_points(model_type, rows)
+        D = ctx.pearl_datacost(m_o.reshape(M, ms), thr, lam)
+    e_gpu = O.gco_energy(D, lam, label_cost, graph[0], graph[1], labels)
+    e_seq = O.gco_energy(D, lam, label_cost, graph[0], graph[1], l_o)
+    assert abs(e_gpu - e_seq) <= 1e-9 * max(1.0, abs(e_seq)), \
+        f"{what}: {differing} labels differ and the energies are not tied ({e_gpu!r} vs {e_seq!r})"
+    return True
+
+
 def _compare(corrs, radius, seeds, **kw):
     from oracle import px_sequential as seq
     graph = None
@@ -35,12 +64,9 @@ def _compare(corrs, radius, seeds, **kw):
                                          kw["maximum_tanimoto_similarity"], kw["max_iters"], kw["minimum_point_number"],
                                          kw["maximum_model_number"], kw["sampler_id"], kw["scoring_exponent"], seed, graph,
                                          image_sizes=(640.0, 480.0, 640.0, 480.0))
-        M = models.shape[0] // 3
-        same = M == m_o.shape[0] and np.array_equal(labels, l_o.astype(np.int32))
-        if same and M:
-            a, b = models.reshape(M, 9), m_o
-            same = bool(np.all(np.abs(a - b).max(1) <= 1e-5 * np.abs(b).max(1)))
-        agree += same
+        agree += _same_up_to_exact_energy_ties(_native.MODEL_H, corrs, models, m_o, labels, l_o, 9, kw["threshold"],
+                                               kw["spatial_coherence_weight"], float(kw["minimum_point_number"]), graph,
+                                               f"seed {seed}")
     return agree
 
 
@@ -66,7 +92,7 @@ def test_driver_equals_sequential_loop_on_adelaide_h(scene):
     corrs = G[f"{scene}_corrs"]
     kw = dict(threshold=4.0, conf=0.5, spatial_coherence_weight=0.05, maximum_tanimoto_similarity=0.4, max_iters=1000,
               minimum_point_number=10, maximum_model_number=6, sampler_id=3, scoring_exponent=2)
-    assert _compare(corrs, 200.0, (1, 2, 3), **kw) >= 2  # an exact energy tie may split one seed
+    assert _compare(corrs, 200.0, (1, 2, 3, 4, 5), **kw) == 5
 
 
 def _models_match(a, b, tol):
@@ -129,8 +155,8 @@ def test_driver_equals_sequential_loop_on_adelaide_f(scene):
     """findTwoViewMotions with the reference's AdelaideF call (dataset_comparison/adelaideF.ipynb) against the sequential
     loop: seven-point solver with up to three models per sample, oriented-epipolar and symmetric-epipolar validity,
     DEGENSAC with its nested plane-and-parallax GC-RANSAC, eight-point + LM fits, Progressive NAPSAC, LO cuts and
-    alpha-expansion at lambda = 0.5 (the reference's own gco / BK build on the oracle side). Same instance count and
-    per-point labels; models within the 1e-5 contract."""
+    alpha-expansion at lambda = 0.5 (the reference's own gco / BK build on the oracle side). Seeds 1-5: same instance count,
+    models within the 1e-5 contract, per-point labels identical or exact energy ties (_same_up_to_exact_energy_ties)."""
     from oracle import px_sequential as seq
     corrs = G[f"{scene}_corrs"]
     with _native.Context(0) as ctx:
@@ -139,18 +165,12 @@ def test_driver_equals_sequential_loop_on_adelaide_f(scene):
     kw = dict(threshold=0.75, conf=0.5, spatial_coherence_weight=0.5, neighborhood_ball_radius=50.0,
               maximum_tanimoto_similarity=0.4, max_iters=10000, minimum_point_number=7, maximum_model_number=4,
               sampler_id=2, scoring_exponent=1.0)
-    agree = 0
-    for seed in (2, 4):
+    for seed in (1, 2, 3, 4, 5):
         models, labels = pyprogressivex.findTwoViewMotions(corrs, 640, 480, 640, 480, seed=seed, **kw)
         m_o, l_o = seq.find_two_view_motions(corrs, 0.75, 0.5, 0.5, 0.4, 10000, 7, 4, 2, 1.0, seed, graph,
                                              image_sizes=(640.0, 480.0, 640.0, 480.0))
-        M = models.shape[0] // 3
-        same = M == m_o.shape[0] and np.array_equal(labels, l_o.astype(np.int32))
-        if same and M:
-            a, b = models.reshape(M, 9), m_o
-            same = bool(np.all(np.abs(a - b).max(1) <= 1e-5 * np.abs(b).max(1)))
-        agree += same
-    assert agree == 2
+        assert _same_up_to_exact_energy_ties(_native.MODEL_F, corrs, models, m_o, labels, l_o, 9, 0.75, 0.5, 7.0, graph,
+                                             f"{scene} seed {seed}")
 
 
 def test_fundamental_fit_equals_its_numpy_restatement():
@@ -179,27 +199,21 @@ def test_fundamental_fit_equals_its_numpy_restatement():
 def test_driver_equals_sequential_loop_on_tless_poses():
     """find6DPoses with the reference's example call (examples/example_multi_pose_6d.ipynb, T-LESS scene) against the
     sequential loop: P3P with up to four poses per sample, uniform sampler, LO cuts and alpha-expansion at lambda = 0.1 on
-    the neighbourhood graph of the raw [u v X Y Z] rows, DLT + LM non-minimal fits. Same instance count and labels,
-    poses within the 1e-5 contract, on at least two of three seeds."""
+    the neighbourhood graph of the raw [u v X Y Z] rows, DLT + LM non-minimal fits. Seeds 1-5: same instance count, poses
+    within the 1e-5 contract, labels identical or exact energy ties."""
     from oracle import px_sequential as seq
     pts, K = G["tless_points"], G["tless_K"]
     raw = np.ascontiguousarray(np.column_stack([pts[:, :2], pts[:, 2:]]))
     with _native.Context(0) as ctx:
         ctx.upload_points(_native.MODEL_PNP, raw)
         graph = ctx.knn_graph(20.0, 5)
-    agree = 0
-    for seed in (1, 2, 3):
+    rows = syn.normalize_pnp_points(pts[:, :2], pts[:, 2:], K)
+    thr = 4.0 / (0.5 * (K[0, 0] + K[1, 1]))
+    for seed in (1, 2, 3, 4, 5):
         poses, labels = pyprogressivex.find6DPoses(pts[:, :2], pts[:, 2:], K, 4.0, seed=seed)
         m_o, l_o = seq.find_6d_poses(pts[:, :2], pts[:, 2:], K, 4.0, 0.9, 0.1, 0.9, 400, 6, -1, seed, graph)
-        M = poses.shape[0] // 3
-        same = M == m_o.shape[0] and np.array_equal(labels, l_o.astype(np.int32))
-        if same and M:
-            a, b = poses.reshape(M, 12), m_o
-            same = bool(np.all(np.abs(a - b).max(1) <= 1e-5 * np.abs(b).max(1)))
-        agree += same
-    # seeds 1, 3, 4, 5: eight or nine instances, all 1886 labels identical; seed 2: same instance count, 10 labels differ
-    # (a near-tie between two poses of the same object decided by 1e-9 differences of the LM fits)
-    assert agree >= 2
+        assert _same_up_to_exact_energy_ties(_native.MODEL_PNP, rows, poses, m_o, labels, l_o, 12, thr, 0.1, 6.0, graph,
+                                             f"T-LESS seed {seed}")
 
 
 def test_pose_fit_equals_its_numpy_restatement():

@@ -15,7 +15,12 @@ H, F, PNP, VP, LINE = 0, 1, 2, 3, 4
 @pytest.fixture(scope="module")
 def refb(oracle):
     if not oracle.have_ref_bodies():
-        pytest.skip("oracle/_ref/libpx_refbodies.so not built (needs /root/reference; it travels prebuilt to the GPU box)")
+        from pathlib import Path
+        # where the reference is present the pinning build must exist (build() makes it): a missing file is a FAILURE,
+        # not a skip -- otherwise the oracle would silently become "parity unpinned"
+        assert not Path("/root/reference").is_dir(), \
+            "oracle/_ref/libpx_refbodies.so not built although /root/reference exists: run __graft_entry__.build()"
+        pytest.skip("no /root/reference and no prebuilt oracle/_ref (the GPU-side pinning runs in tests/test_gpu_pinning.py)")
     oracle.refb()
     return oracle
 
