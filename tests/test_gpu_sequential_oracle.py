@@ -38,7 +38,7 @@ def _same_up_to_exact_energy_ties(model_type, rows, models, m_o, labels, l_o, ms
     if np.array_equal(labels, l_o):
         return True
     differing = int(np.sum(labels != l_o))
-    assert lam > 0 and graph is not None and M > 1, f"{what}: {differing} labels differ without a smoothness term"
+    assert lam > 0 and graph is not None and M >= 1, f"{what}: {differing} labels differ without a smoothness term"
     assert differing <= max(2, len(labels) // 100), f"{what}: {differing} labels differ"
     with _native.Context(0) as ctx:
         ctx.upload_points(model_type, rows)
