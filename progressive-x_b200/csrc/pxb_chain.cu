@@ -93,17 +93,25 @@ __global__ void __launch_bounds__(kListThreads)
 	__shared__ int s_total;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	int running = 0;
-	const int64_t items = BITS ? (N + 31) / 32 : N; // bit mask: one 32-bit word per thread and step
+	// per thread and step: one 32-bit word of the bit mask, or eight consecutive flag bytes (one 64-bit load)
+	const int64_t items = BITS ? (N + 31) / 32 : (N + 7) / 8;
 	for (int64_t c0 = 0; c0 < items; c0 += kListThreads) {
 		const int64_t i = c0 + tid;
 		int mine;
-		unsigned word = 0;
+		unsigned word = 0; // bit j set: entry base + j is flagged
 		if (BITS) {
 			word = i < items ? reinterpret_cast<const uint32_t *>(flags)[i] : 0u;
-			mine = __popc(word);
-		} else {
-			mine = (i < N && reinterpret_cast<const uint8_t *>(flags)[i]) ? 1 : 0;
+		} else if (i < items) {
+			const uint8_t *f = reinterpret_cast<const uint8_t *>(flags) + i * 8;
+			if (i * 8 + 8 <= N && (reinterpret_cast<uintptr_t>(f) & 7u) == 0) {
+				const unsigned long long v = *reinterpret_cast<const unsigned long long *>(f);
+#pragma unroll
+				for (int j = 0; j < 8; ++j) word |= ((v >> (8 * j)) & 0xffull) ? (1u << j) : 0u;
+			} else {
+				for (int j = 0; j < 8 && i * 8 + j < N; ++j) word |= f[j] ? (1u << j) : 0u;
+			}
 		}
+		mine = __popc(word);
 		int inc = mine; // inclusive scan over the warp, then over the warp totals
 #pragma unroll
 		for (int o = 1; o < 32; o <<= 1) {
@@ -125,14 +133,11 @@ __global__ void __launch_bounds__(kListThreads)
 		}
 		__syncthreads();
 		int at = running + s_warp[warp] + inc - mine;
-		if (BITS) {
-			while (word) {
-				const int b = __ffs(word) - 1;
-				idx[at++] = (int32_t)(i * 32 + b);
-				word &= word - 1;
-			}
-		} else if (mine) {
-			idx[at] = (int32_t)i;
+		const int64_t base = i * (BITS ? 32 : 8);
+		while (word) {
+			const int bpos = __ffs(word) - 1;
+			idx[at++] = (int32_t)(base + bpos);
+			word &= word - 1;
 		}
 		running += s_total;
 		__syncthreads();

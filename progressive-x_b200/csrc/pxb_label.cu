@@ -6,9 +6,16 @@
 //                             default) -- a handful of column reductions, no graph cut at all.
 //   alpha-expansion      a11  see pxb_expansion.cu
 //
-// The whole greedy solve is one persistent single-block kernel: L+1 <= 11 labels and at most L+1 rounds of
-// column sums over N <= 1e5 sites is a few hundred microseconds of work; a multi-kernel version would be launch
-// bound. Column sums use the fixed block topology of pxb_kernels.cu (thread-strided, butterfly, warps in order).
+// The whole greedy solve is one persistent kernel (a multi-kernel version would be launch bound). k_greedy_ufl_fused
+// reads every row of D once per round and accumulates ALL column sums of the round in registers (the first version made
+// one pass over N per column: ~L^2/2 passes); for N > 16k it runs on several blocks of a cooperative launch, block
+// partials combined in block order after a grid barrier, every block taking the (identical) decision redundantly.
+// Column sums use the fixed topology of pxb_kernels.cu (grid-strided thread partials in index order, butterfly, warps in
+// order, blocks in order): a function of N only. k_greedy_ufl (one block, one column per pass) remains for L + 1 > 16.
+#include <cooperative_groups.h>
+
+#include <algorithm>
+
 #include "pxb_internal.h"
 #include "pxb_residuals.cuh"
 
@@ -147,16 +154,207 @@ __global__ void __launch_bounds__(kBlock)
 	if (tid == 0) *energy_out = better ? efinal : s_estart;
 }
 
+constexpr int kUflMaxL = 16;
+
+// sums of NV per-thread values over the block: butterfly inside the warp, then the warps in order (thread a < NV adds them)
+template <int NV> __device__ __forceinline__ void ufl_block_sums(double (&v)[NV], double *s_vec /*[32][NV]*/, double *s_out /*[NV]*/) {
+#pragma unroll
+	for (int a = 0; a < NV; ++a)
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) v[a] = add(v[a], __shfl_xor_sync(0xffffffffu, v[a], o));
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	__syncthreads();
+	if (lane == 0)
+#pragma unroll
+		for (int a = 0; a < NV; ++a) s_vec[warp * NV + a] = v[a];
+	__syncthreads();
+	if (threadIdx.x < NV) {
+		double t = 0.0;
+		for (int w = 0; w < kBlock / 32; ++w) t = add(t, s_vec[w * NV + threadIdx.x]);
+		s_out[threadIdx.x] = t;
+	}
+	__syncthreads();
+}
+
+__global__ void __launch_bounds__(kBlock)
+    k_greedy_ufl_fused(const double *__restrict__ D, int64_t N, int L1, double label_cost, const int32_t *__restrict__ init_labels,
+                       int32_t *__restrict__ labels_out, double *__restrict__ cur, int32_t *__restrict__ lab,
+                       double *__restrict__ energy_out, double *__restrict__ partials /*[2][G][kUflMaxL + 1]*/,
+                       unsigned *__restrict__ used_bits /*[G]*/) {
+	constexpr int NV = kUflMaxL + 1;
+	__shared__ double s_vec[(kBlock / 32) * NV];
+	__shared__ double s_col[NV];
+	__shared__ double e[kUflMaxL];
+	__shared__ int order[kUflMaxL];
+	__shared__ unsigned char active[kUflMaxL];
+	__shared__ unsigned s_used;
+	__shared__ int s_alpha, s_alpha_prev, s_stop;
+	__shared__ double s_estart;
+	const int tid = threadIdx.x, G = gridDim.x, b = blockIdx.x;
+	const int64_t first = (int64_t)b * kBlock + tid, step = (int64_t)G * kBlock;
+	int round = 0; // selects the partials buffer: a block can be at most one round ahead of another
+	// combines the block sums of all blocks (in block order) into s_col; one grid barrier per round
+	auto combine = [&]() {
+		if (G > 1) {
+			double *buf = partials + (size_t)(round & 1) * G * NV;
+			if (tid < NV) buf[b * NV + tid] = s_col[tid];
+			__threadfence();
+			cooperative_groups::this_grid().sync();
+			if (tid < NV) {
+				double t = 0.0;
+				for (int g = 0; g < G; ++g) t = add(t, buf[g * NV + tid]);
+				s_col[tid] = t;
+			}
+			__syncthreads();
+			++round;
+		}
+	};
+	// ---- estart = compute_energy() of the initial labelling (:614) and all column sums (:634-650), one pass
+	if (tid == 0) s_used = 0;
+	__syncthreads();
+	double acc[NV];
+#pragma unroll
+	for (int a = 0; a < NV; ++a) acc[a] = 0.0;
+	unsigned used = 0;
+	for (int64_t i = first; i < N; i += step) {
+		const double *row = D + i * L1;
+		const int l0 = init_labels ? init_labels[i] : 0;
+		used |= 1u << l0;
+#pragma unroll
+		for (int l = 0; l < kUflMaxL; ++l)
+			if (l < L1) {
+				const double d = row[l];
+				acc[l] = add(acc[l], d);
+				if (l == l0) acc[kUflMaxL] = add(acc[kUflMaxL], d);
+			}
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) used |= __shfl_xor_sync(0xffffffffu, used, o);
+	if ((tid & 31) == 0 && used) atomicOr(&s_used, used);
+	ufl_block_sums<NV>(acc, s_vec, s_col);
+	if (G > 1 && tid == 0) used_bits[b] = s_used;
+	combine();
+	if (tid == 0) {
+		unsigned u = s_used;
+		if (G > 1) {
+			u = 0;
+			for (int g = 0; g < G; ++g) u |= used_bits[g];
+		}
+		double le = 0.0;
+		for (int l = L1 - 1; l >= 0; --l)
+			if (u >> l & 1u) le = add(le, label_cost);
+		s_estart = add(add(s_col[kUflMaxL], 0.0), le);
+		for (int l = 0; l < L1; ++l) e[l] = add(label_cost, s_col[l]);
+		int alpha = 0;
+		for (int l = 0; l < L1; ++l)
+			if (e[l] < e[alpha]) alpha = l;
+		for (int l = 0; l < L1; ++l) {
+			order[l] = l;
+			active[l] = 0;
+		}
+		order[alpha] = 0;
+		order[0] = alpha;
+		active[alpha] = 1;
+		s_alpha = alpha;
+		s_stop = 0;
+	}
+	__syncthreads();
+	{
+		const int alpha = s_alpha;
+		for (int64_t i = first; i < N; i += step) {
+			lab[i] = alpha;
+			cur[i] = D[i * L1 + alpha];
+		}
+	}
+	// ---- greedy expansion rounds (:667-722): every candidate's drop in one pass
+	for (int alpha_count = 1; alpha_count <= L1; ++alpha_count) {
+		if (tid == 0) s_alpha_prev = s_alpha;
+		__syncthreads();
+		unsigned cand = 0; // labels still outside the solution
+		for (int li = alpha_count; li < L1; ++li) cand |= 1u << order[li];
+#pragma unroll
+		for (int a = 0; a < NV; ++a) acc[a] = 0.0;
+		if (cand)
+			for (int64_t i = first; i < N; i += step) {
+				const double *row = D + i * L1;
+				const double c = cur[i];
+#pragma unroll
+				for (int l = 0; l < kUflMaxL; ++l)
+					if (cand >> l & 1u) {
+						const double delta = sub(row[l], c);
+						if (delta < 0) acc[l] = add(acc[l], delta);
+					}
+			}
+		ufl_block_sums<NV>(acc, s_vec, s_col);
+		combine();
+		if (tid == 0) {
+			for (int li = alpha_count; li < L1; ++li) {
+				const int l = order[li];
+				double v = e[s_alpha_prev];
+				if (!active[l]) v = add(v, label_cost);
+				e[l] = add(v, s_col[l]);
+			}
+			int alpha = s_alpha;
+			int alpha_index = alpha_count - 1;
+			for (int li = alpha_count; li < L1; ++li) {
+				const int l = order[li];
+				if (e[l] < e[alpha]) {
+					alpha = l;
+					alpha_index = li;
+				}
+			}
+			if (alpha == s_alpha_prev) {
+				s_stop = 1;
+			} else {
+				const int t = order[alpha_count];
+				order[alpha_count] = order[alpha_index];
+				order[alpha_index] = t;
+				active[alpha] = 1;
+				s_alpha = alpha;
+			}
+		}
+		__syncthreads();
+		if (s_stop) break; // identical in every block: all of them decided on the same sums
+		const int alpha = s_alpha;
+		for (int64_t i = first; i < N; i += step) {
+			const double dc_l = D[i * L1 + alpha];
+			if (sub(dc_l, cur[i]) < 0) {
+				lab[i] = alpha;
+				cur[i] = dc_l;
+			}
+		}
+	}
+	// ---- accept only if strictly better than the start labelling (:724-741)
+	const double efinal = e[s_alpha];
+	const bool better = efinal < s_estart;
+	for (int64_t i = first; i < N; i += step) labels_out[i] = better ? lab[i] : (init_labels ? init_labels[i] : 0);
+	if (b == 0 && tid == 0) *energy_out = better ? efinal : s_estart;
+}
+
 int launch_greedy_label(pxb_ctx *ctx, const double *D, int64_t N, int32_t L1, double label_cost,
                         const int32_t *init_labels, int32_t *labels_out, double *energy_out_dev) {
 	if (L1 > kMaxL || L1 < 1) {
 		set_error("label count %d outside [1, %d]", L1, kMaxL);
 		return PXB_ERR_ARGUMENT;
 	}
-	PXB_TRY(ctx->outC.reserve(sizeof(double) * (size_t)N));
-	PXB_TRY(ctx->outD.reserve(sizeof(int32_t) * (size_t)N));
-	k_greedy_ufl<<<1, kBlock, 0, ctx->stream>>>(D, N, L1, label_cost, init_labels, labels_out, ctx->outC.as<double>(),
-	                                           ctx->outD.as<int32_t>(), energy_out_dev);
+	int G = 1;
+	if (N > 16384) G = (int)std::min<int64_t>((N + 8191) / 8192, ctx->sm_count); // a function of N (and the part) only
+	PXB_TRY(ctx->outC.reserve(sizeof(double) * ((size_t)N + 2 * (size_t)G * (kUflMaxL + 1))));
+	PXB_TRY(ctx->outD.reserve(sizeof(int32_t) * ((size_t)N + (size_t)G)));
+	double *cur = ctx->outC.as<double>(), *partials = cur + N;
+	int32_t *lab = ctx->outD.as<int32_t>();
+	unsigned *used_bits = reinterpret_cast<unsigned *>(lab + N);
+	if (L1 > kUflMaxL) {
+		k_greedy_ufl<<<1, kBlock, 0, ctx->stream>>>(D, N, L1, label_cost, init_labels, labels_out, cur, lab, energy_out_dev);
+	} else if (G == 1) {
+		k_greedy_ufl_fused<<<1, kBlock, 0, ctx->stream>>>(D, N, (int)L1, label_cost, init_labels, labels_out, cur, lab, energy_out_dev,
+		                                                 partials, used_bits);
+	} else {
+		int l1 = (int)L1;
+		void *args[] = {(void *)&D, (void *)&N, (void *)&l1, (void *)&label_cost, (void *)&init_labels, (void *)&labels_out,
+		                (void *)&cur, (void *)&lab, (void *)&energy_out_dev, (void *)&partials, (void *)&used_bits};
+		PXB_CUDA(cudaLaunchCooperativeKernel((void *)k_greedy_ufl_fused, dim3((unsigned)G), dim3(kBlock), args, 0, ctx->stream));
+	}
 	ctx->launches++;
 	PXB_CUDA(cudaGetLastError());
 	return PXB_OK;

@@ -54,7 +54,8 @@ template <int TYPE, bool HAS_CP> struct ScoreSmem {
 	static constexpr size_t kAcc = kQueue + sizeof(unsigned short) * kScWarps * kScQueue;
 	static constexpr size_t kRes = kAcc + sizeof(ScoreAcc) * kScWarps * kScHyps; // per warp: 32 values (+32 shared) + 32 segments
 	static constexpr size_t kSeg = kRes + sizeof(double) * kScWarps * 32 * (HAS_CP ? 2 : 1);
-	static constexpr size_t kBytes = kSeg + sizeof(unsigned short) * kScWarps * 32;
+	static constexpr size_t kEmpty = kSeg + sizeof(unsigned short) * kScWarps * 32; // per hypothesis of the tile: empty slot
+	static constexpr size_t kBytes = kEmpty + kScHyps;
 };
 
 // Drains up to 32 queued candidates of one warp: one candidate per lane, the reference's exact float64 residual, the
@@ -123,9 +124,10 @@ __device__ __noinline__ ScoreAcc score_drain(const double *s_pts, const double *
 // The hypothesis loop of one warp: screening, queueing, draining.
 template <int TYPE, bool HAS_CP, bool FULL>
 __device__ __forceinline__ ScoreAcc score_tile(const float (&p)[kScP][5], const float (&zq)[kScP], const bool (&valid)[kScP],
-                                               const float *s_mf, int nk, float cT, const double *s_pts, const double *s_cp,
-                                               const double *s_models, int pbase, double T2, unsigned short *queue,
-                                               double *res_v, double *res_s, unsigned short *seg) {
+                                               const float *s_mf, const unsigned char *s_empty, int nk, float cT,
+                                               const double *s_pts, const double *s_cp, const double *s_models, int pbase,
+                                               double T2, unsigned short *queue, double *res_v, double *res_s,
+                                               unsigned short *seg) {
 	constexpr int MF = ScreenTraits<TYPE>::kFloats;
 	const int lane = threadIdx.x & 31;
 	const unsigned lt = (1u << lane) - 1u;
@@ -133,6 +135,9 @@ __device__ __forceinline__ ScoreAcc score_tile(const float (&p)[kScP][5], const 
 	ScoreAcc acc = {0.0, 0.0, 0};
 #pragma unroll 2
 	for (int h = 0; h < nk; ++h) {
+		// an unfilled solution slot of a minimal solver (all-zero model): every residual is NaN, nothing is an inlier --
+		// count, score and shared support are exactly zero, as the reference's loop would find (block-uniform skip)
+		if (s_empty[h]) continue;
 		float m[MF];
 		const float4 *s4 = reinterpret_cast<const float4 *>(s_mf + h * MF);
 #pragma unroll
@@ -172,7 +177,7 @@ __device__ __forceinline__ ScoreAcc score_tile(const float (&p)[kScP][5], const 
 // launch constants of the test. One thread per hypothesis; keeps all float64 conjugation out of the hot kernel.
 template <int TYPE>
 __global__ void k_screen_prepare(const double *__restrict__ models, int64_t K, double T2, const NormDev *__restrict__ norm,
-                                 float *__restrict__ consts, float *__restrict__ mf) {
+                                 float *__restrict__ consts, float *__restrict__ mf, unsigned char *__restrict__ empty) {
 	constexpr int MS = ModelTraits<TYPE>::kSize, MF = ScreenTraits<TYPE>::kFloats;
 	const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	const NormDev nd = *norm;
@@ -188,13 +193,19 @@ __global__ void k_screen_prepare(const double *__restrict__ models, int64_t K, d
 	screen_model<TYPE>(models + k * MS, nd, out);
 #pragma unroll
 	for (int i = 0; i < MF; ++i) mf[k * MF + i] = out[i];
+	bool zero = true;
+#pragma unroll
+	for (int i = 0; i < MS; ++i) zero &= models[k * MS + i] == 0.0;
+	// H, F, PnP: an all-zero model gives 0/0 residuals everywhere. (A zero LINE has residual 0 -- all inliers -- and is scored.)
+	empty[k] = (zero && TYPE <= PXB_MODEL_PNP) ? 1 : 0;
 }
 
 template <int TYPE, bool HAS_CP, int PASSES>
 __global__ void __launch_bounds__(kThreads, 3)
     k_score_screened(const double *__restrict__ soa, int64_t stride, int64_t N, const float *__restrict__ pf,
                      const float *__restrict__ pq, const float *__restrict__ consts, const float *__restrict__ mfg,
-                     const double *__restrict__ models, int64_t K, double T2, const double *__restrict__ compound_pref,
+                     const unsigned char *__restrict__ emptyg, const double *__restrict__ models, int64_t K, double T2,
+                     const double *__restrict__ compound_pref,
                      ScorePartial *__restrict__ partials, int nchunks, int tile /* hypotheses per pass, <= kScHyps */) {
 	using L = ScoreSmem<TYPE, HAS_CP>;
 	constexpr int DIM = L::DIM, MS = ModelTraits<TYPE>::kSize, MP = L::MP, MF = L::MF;
@@ -207,6 +218,7 @@ __global__ void __launch_bounds__(kThreads, 3)
 	ScoreAcc *s_acc = reinterpret_cast<ScoreAcc *>(smem + L::kAcc);
 	double *s_res = reinterpret_cast<double *>(smem + L::kRes);
 	unsigned short *s_seg = reinterpret_cast<unsigned short *>(smem + L::kSeg);
+	unsigned char *s_empty = smem + L::kEmpty;
 
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int chunk = blockIdx.x;
@@ -239,13 +251,14 @@ __global__ void __launch_bounds__(kThreads, 3)
 		const int nk = (int)min((int64_t)tile, K - k0);
 		for (int t = threadIdx.x; t < nk * MS; t += kThreads) s_models[(t / MS) * MP + (t % MS)] = models[k0 * MS + t];
 		for (int t = threadIdx.x; t < nk * MF; t += kThreads) s_mf[t] = __ldg(mfg + k0 * MF + t);
+		if (threadIdx.x < nk) s_empty[threadIdx.x] = __ldg(emptyg + k0 + threadIdx.x);
 		__syncthreads();
 		ScoreAcc acc;
 		if (full)
-			acc = score_tile<TYPE, HAS_CP, true>(p, zq, valid, s_mf, nk, cT, s_pts, s_cp, s_models, warp * (32 * kScP), T2,
+			acc = score_tile<TYPE, HAS_CP, true>(p, zq, valid, s_mf, s_empty, nk, cT, s_pts, s_cp, s_models, warp * (32 * kScP), T2,
 			                                     s_queue + warp * kScQueue, res_v, res_s, s_seg + warp * 32);
 		else
-			acc = score_tile<TYPE, HAS_CP, false>(p, zq, valid, s_mf, nk, cT, s_pts, s_cp, s_models, warp * (32 * kScP), T2,
+			acc = score_tile<TYPE, HAS_CP, false>(p, zq, valid, s_mf, s_empty, nk, cT, s_pts, s_cp, s_models, warp * (32 * kScP), T2,
 			                                      s_queue + warp * kScQueue, res_v, res_s, s_seg + warp * 32);
 		s_acc[warp * kScHyps + lane] = acc;
 		__syncthreads();
@@ -281,8 +294,8 @@ __global__ void k_score_finalize(const ScorePartial *__restrict__ partials, int6
 }
 
 template <int TYPE, bool HAS_CP, int PASSES>
-static void launch_screened(pxb_ctx *ctx, int nchunks, const float *consts, const float *mf, const double *m, int64_t kk,
-                            double T2, const double *cp, ScorePartial *pp, int tile_hyps) {
+static void launch_screened(pxb_ctx *ctx, int nchunks, const float *consts, const float *mf, const unsigned char *empty,
+                            const double *m, int64_t kk, double T2, const double *cp, ScorePartial *pp, int tile_hyps) {
 	const Points &p = ctx->pts;
 	constexpr int kBytes = (int)ScoreSmem<TYPE, HAS_CP>::kBytes;
 	// opt in to > 48 KB of dynamic shared memory: once per device and instantiation (every API call counts when eight
@@ -294,16 +307,17 @@ static void launch_screened(pxb_ctx *ctx, int nchunks, const float *consts, cons
 	}
 	const int64_t tile = (int64_t)tile_hyps * PASSES;
 	dim3 grid((unsigned)nchunks, (unsigned)((kk + tile - 1) / tile));
-	k_score_screened<TYPE, HAS_CP, PASSES><<<grid, kThreads, kBytes, ctx->stream>>>(p.soa, p.stride, p.N, p.f32n, p.q, consts, mf, m,
-	                                                                             kk, T2, cp, pp, nchunks, tile_hyps);
+	k_score_screened<TYPE, HAS_CP, PASSES><<<grid, kThreads, kBytes, ctx->stream>>>(p.soa, p.stride, p.N, p.f32n, p.q, consts, mf,
+	                                                                             empty, m, kk, T2, cp, pp, nchunks, tile_hyps);
 }
 
 template <int TYPE>
 static int launch_partial(pxb_ctx *ctx, int nchunks, const double *m, int64_t kk, double T2, const double *cp, ScorePartial *pp) {
 	constexpr int MF = ScreenTraits<TYPE>::kFloats;
-	PXB_TRY(ctx->screen.reserve(sizeof(float) * (4 + (size_t)kk * MF)));
+	PXB_TRY(ctx->screen.reserve(sizeof(float) * (4 + (size_t)kk * MF) + (size_t)kk + 64));
 	float *consts = ctx->screen.as<float>(), *mf = consts + 4;
-	k_screen_prepare<TYPE><<<(unsigned)((kk + 127) / 128), 128, 0, ctx->stream>>>(m, kk, T2, ctx->pts.norm, consts, mf);
+	unsigned char *empty = reinterpret_cast<unsigned char *>(mf + (size_t)kk * MF);
+	k_screen_prepare<TYPE><<<(unsigned)((kk + 127) / 128), 128, 0, ctx->stream>>>(m, kk, T2, ctx->pts.norm, consts, mf, empty);
 	ctx->launches++;
 	// big batches walk 4 tiles of 32 hypotheses per block (the per-block prologue -- staging 1024 points -- is paid once);
 	// RANSAC-sized batches keep one tile per block so that the grid still fills the GPU
@@ -317,11 +331,11 @@ static int launch_partial(pxb_ctx *ctx, int nchunks, const double *m, int64_t kk
 		tile = (int)std::min<int64_t>(kScHyps, std::max<int64_t>(1, kk * nchunks / want_blocks));
 	}
 	if (cp) {
-		if (big) launch_screened<TYPE, true, 4>(ctx, nchunks, consts, mf, m, kk, T2, cp, pp, kScHyps);
-		else launch_screened<TYPE, true, 1>(ctx, nchunks, consts, mf, m, kk, T2, cp, pp, tile);
+		if (big) launch_screened<TYPE, true, 4>(ctx, nchunks, consts, mf, empty, m, kk, T2, cp, pp, kScHyps);
+		else launch_screened<TYPE, true, 1>(ctx, nchunks, consts, mf, empty, m, kk, T2, cp, pp, tile);
 	} else {
-		if (big) launch_screened<TYPE, false, 4>(ctx, nchunks, consts, mf, m, kk, T2, cp, pp, kScHyps);
-		else launch_screened<TYPE, false, 1>(ctx, nchunks, consts, mf, m, kk, T2, cp, pp, tile);
+		if (big) launch_screened<TYPE, false, 4>(ctx, nchunks, consts, mf, empty, m, kk, T2, cp, pp, kScHyps);
+		else launch_screened<TYPE, false, 1>(ctx, nchunks, consts, mf, empty, m, kk, T2, cp, pp, tile);
 	}
 	ctx->launches++;
 	return PXB_OK;
