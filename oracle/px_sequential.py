@@ -248,44 +248,62 @@ class ProgressiveNapsacSampler:  # gcr/samplers/progressive_napsac_sampler.h; la
 
 
 # ---- fundamental matrices ------------------------------------------------------------------------------------------
-def _rank2_unit(Fm):
-    """closest rank-2 matrix, unit Frobenius norm"""
-    U, sv, Vt = np.linalg.svd(Fm)
-    Fm = (U[:, :2] * sv[:2]) @ Vt[:2]
-    nrm = np.linalg.norm(Fm)
-    return Fm / nrm if nrm > 0 else Fm
+def _skew(w):
+    return np.array([[0.0, -w[2], w[1]], [w[2], 0.0, -w[0]], [-w[1], w[0], 0.0]])
 
 
-def _lm_system(Fm, x1, x2, w):
-    """J^T J, J^T r and the cost of the weighted Sampson residuals r_i = w_i C_i / sqrt(S_i) (9 parameters)"""
-    Fx = x1 @ Fm.T
-    Ftx = x2 @ Fm
-    C = np.einsum("ni,ni->n", x2, Fx)
-    S = Fx[:, 0] ** 2 + Fx[:, 1] ** 2 + Ftx[:, 0] ** 2 + Ftx[:, 1] ** 2
-    keep = S > 1e-300
-    x1, x2, Fx, Ftx, C, S, w = x1[keep], x2[keep], Fx[keep], Ftx[keep], C[keep], S[keep], w[keep]
-    inv = 1.0 / np.sqrt(S)
-    res = w * C * inv
-    J = np.empty((len(C), 9))
+def _factorized_F(U, V, sigma):  # FactorizedFundamentalMatrix::F (relative_pose/jacobian_impl.h:484-486)
+    return np.outer(U[:, 0], V[:, 0]) + sigma * np.outer(U[:, 1], V[:, 1])
+
+
+def _lm_f_cost(Fm, p1, p2, w, sq_thr=1.0):  # FundamentalJacobianAccumulator::residual (jacobian_impl.h:504-532)
+    Fx = p1 @ Fm.T
+    Ft = p2 @ Fm
+    C = np.einsum("ni,ni->n", p2, Fx)
+    nJ = Fx[:, 0] ** 2 + Fx[:, 1] ** 2 + Ft[:, 0] ** 2 + Ft[:, 1] ** 2
+    with np.errstate(all="ignore"):
+        r2 = C * C / nJ
+    return float(np.sum(w * np.fmin(r2, sq_thr)))
+
+
+def _lm_f_system(Fm, U, V, p1, p2, w, sq_thr=1.0):  # ...::accumulate (jacobian_impl.h:534-606): J^T J, J^T r
+    n = len(p1)
+    E = np.eye(3)
+    dP = [(_skew(E[k]) @ Fm) for k in range(3)] + [(-Fm @ _skew(E[k])) for k in range(3)] + [np.outer(U[:, 1], V[:, 1])]
+    Fx = p1 @ Fm.T
+    Ft = p2 @ Fm
+    C = np.einsum("ni,ni->n", p2, Fx)
+    nJ = np.sqrt(Ft[:, 0] ** 2 + Ft[:, 1] ** 2 + Fx[:, 0] ** 2 + Fx[:, 1] ** 2)
+    with np.errstate(all="ignore"):
+        inv = 1.0 / nJ
+    res = C * inv
+    wgt = np.where(res * res < sq_thr, 1.0, 0.0) / n * w
+    sC = C * inv * inv
+    G = np.empty((n, 3, 3))
     for r in range(3):
         for c in range(3):
-            dC = x2[:, r] * x1[:, c]
-            dS = 2.0 * ((Fx[:, r] * x1[:, c] if r < 2 else 0.0) + (Ftx[:, c] * x2[:, r] if c < 2 else 0.0))
-            J[:, 3 * r + c] = w * (dC * inv - 0.5 * C * inv ** 3 * dS)
-    return J.T @ J, J.T @ res, float(res @ res)
+            G[:, r, c] = (p2[:, r] * p1[:, c] - sC * ((Ft[:, c] * p2[:, r] if c < 2 else 0.0) + (Fx[:, r] * p1[:, c] if r < 2 else 0.0))) * inv
+    J = np.stack([np.einsum("nrc,rc->n", G, d) for d in dP], 1)
+    keep = wgt != 0.0
+    J, wgt, res = J[keep], wgt[keep], res[keep]
+    return (J * wgt[:, None]).T @ J, J.T @ (wgt * res)
 
 
 def fit_f_nonminimal(pts, idx, weights_by_row=None):
-    """The GPU engine's non-minimal F fit (progressive-x_b200/csrc/pxb_fit_fp.cu, k_fit_f) restated with numpy: normalised
-    eight-point (fundamental_estimator.h:574-618 / solver_fundamental_matrix_eight_point.h), rank-2 projection, then a
-    Levenberg-Marquardt polish of the weighted Sampson error -- the objective of the reference's bundle adjustment
-    (solver_fundamental_matrix_bundle_adjustment.h:114-178 -> PoseLib, not on disk). Same steps, damping schedule and
-    acceptance rule as the kernel; sums are numpy's, so results agree to ~1e-9, not bit for bit."""
+    """FundamentalMatrixEstimator::estimateModelNonminimal (fundamental_estimator.h:574-618) with the reference's
+    FundamentalMatrixBundleAdjustmentSolver (solver_fundamental_matrix_bundle_adjustment.h:114-178) restated with numpy:
+    Hartley normalisation, eight-point estimate on the normalised points, then PoseLib's refine_fundamental = lm_F_impl
+    (relative_pose/bundle.cpp:253-340,454-500; 7-parameter factorised F, truncated loss with loss_scale 1, LLT steps, at most
+    25 iterations, tolerances 1e-8), denormalisation, unit norm, f33 >= 0. The same restatement as k_fit_f
+    (progressive-x_b200/csrc/pxb_fit_fp.cu); sums are numpy's, so results agree to ~1e-9, not bit for bit. As there, the
+    eight-point null vector is the smallest eigenvector of A^T A (the reference: last column of a FullPivHouseholderQR) and
+    n == 7 (seven-point initialisation) is not covered."""
     q = pts[np.asarray(idx, dtype=np.int64)]
     n = len(q)
     if n < 8:
         return None, False
-    w = np.ones(n) if weights_by_row is None else np.asarray(weights_by_row, dtype=np.float64)[:n]
+    have_w = weights_by_row is not None
+    w = np.ones(n) if not have_w else np.asarray(weights_by_row, dtype=np.float64)[:n]
     m1, m2 = q[:, :2].mean(0), q[:, 2:].mean(0)
     r1 = math.sqrt(2.0) / np.mean(np.sqrt(((m1 - q[:, :2]) ** 2).sum(1)))
     r2 = math.sqrt(2.0) / np.mean(np.sqrt(((m2 - q[:, 2:]) ** 2).sum(1)))
@@ -294,39 +312,46 @@ def fit_f_nonminimal(pts, idx, weights_by_row=None):
     rows = np.column_stack([b[:, 0] * a[:, 0], b[:, 0] * a[:, 1], b[:, 0], b[:, 1] * a[:, 0], b[:, 1] * a[:, 1], b[:, 1],
                             a[:, 0], a[:, 1], np.ones(n)]) * w[:, None]
     evals, evecs = np.linalg.eigh(rows.T @ rows)
-    Fn = _rank2_unit(evecs[:, 0].reshape(3, 3))
-    rs = math.sqrt(r1 * r2)
-    k1, k2 = r1 / rs, r2 / rs
-    Fl = _rank2_unit(Fn * np.array([k2, k2, 1.0])[:, None] * np.array([k1, k1, 1.0])[None, :])
-    x1 = np.column_stack([(q[:, :2] - m1) * rs, np.ones(n)])
-    x2 = np.column_stack([(q[:, 2:] - m2) * rs, np.ones(n)])
-    JtJ, Jtr, cost = _lm_system(Fl, x1, x2, w)
-    mu = 1e-3
-    for _ in range(8):
-        M = JtJ.copy()
-        d = np.diag(M).copy()
-        M[np.diag_indices(9)] = d + mu * np.maximum(d, 1e-12)
+    U, sv, Vt = np.linalg.svd(evecs[:, 0].reshape(3, 3))
+    V = Vt.T
+    sigma = sv[1] / sv[0] if sv[0] > 0 else 0.0
+    p1 = np.column_stack([a, np.ones(n)])
+    p2 = np.column_stack([b, np.ones(n)])
+    Fc = _factorized_F(U, V, sigma)
+    cost = _lm_f_cost(Fc, p1, p2, w)
+    lam, recompute = 1e-3, True
+    JtJ = Jtr = None
+    for _ in range(25):
+        if recompute:
+            JtJ, Jtr = _lm_f_system(Fc, U, V, p1, p2, w)
+            if np.linalg.norm(Jtr) < 1e-8:
+                break
         try:
-            delta = np.linalg.solve(M, -Jtr)
+            L = np.linalg.cholesky(JtJ + lam * np.eye(7))
         except np.linalg.LinAlgError:
             break
-        if not np.all(np.abs(delta) <= 1e300):
+        sol = -np.linalg.solve(L.T, np.linalg.solve(L, Jtr))
+        if np.linalg.norm(sol) < 1e-8:
             break
-        cand = _rank2_unit(Fl + delta.reshape(3, 3))
-        JtJ2, Jtr2, cost2 = _lm_system(cand, x1, x2, w)
-        if cost2 < cost:
-            small = (cost - cost2) <= 1e-12 * cost
-            Fl, JtJ, Jtr, cost = cand, JtJ2, Jtr2, cost2
-            if small:
-                break
-            mu *= 0.3
+        with np.errstate(all="ignore"):
+            new = []
+            for M, wv in ((U, sol[:3]), (V, sol[3:6])):
+                theta = np.linalg.norm(wv)
+                sw = _skew(wv / theta)
+                new.append(M + (math.sin(theta) * sw + (1 - math.cos(theta)) * sw @ sw) @ M)
+        Un, Vn, sn = new[0], new[1], sigma + sol[6]
+        Fn = _factorized_F(Un, Vn, sn)
+        cost_new = _lm_f_cost(Fn, p1, p2, w)
+        if cost_new < cost:
+            U, V, sigma, Fc, cost = Un, Vn, sn, Fn, cost_new
+            lam /= 10
+            recompute = True
         else:
-            mu *= 10.0
-        if mu > 1e6:
-            break
-    T1 = np.array([[rs, 0, -rs * m1[0]], [0, rs, -rs * m1[1]], [0, 0, 1.0]])
-    T2m = np.array([[rs, 0, -rs * m2[0]], [0, rs, -rs * m2[1]], [0, 0, 1.0]])
-    Fm = T2m.T @ Fl @ T1
+            lam *= 10
+            recompute = False
+    T1 = np.array([[r1, 0, -r1 * m1[0]], [0, r1, -r1 * m1[1]], [0, 0, 1.0]])
+    T2m = np.array([[r2, 0, -r2 * m2[0]], [0, r2, -r2 * m2[1]], [0, 0, 1.0]])
+    Fm = T2m.T @ Fc @ T1
     nrm = np.linalg.norm(Fm)
     if not (nrm > 0.0) or not np.isfinite(nrm):
         return None, False
@@ -351,39 +376,41 @@ def sym_epipolar_sq(pts, Fm):
 
 
 # ---- 6D poses -------------------------------------------------------------------------------------------------------
-def _exp_left(w, R):
-    """R <- exp([w]x) R (Rodrigues), as k_fit_pnp's rodrigues_left"""
-    th2 = float(w @ w)
-    th = math.sqrt(th2)
-    a, b = (1.0, 0.5) if th < 1e-8 else (math.sin(th) / th, (1.0 - math.cos(th)) / th2)
-    Kx = np.array([[0.0, -w[2], w[1]], [w[2], 0.0, -w[0]], [-w[1], w[0], 0.0]])
-    return (np.eye(3) + a * Kx + b * (Kx @ Kx)) @ R
+def _pnp_cost(R, t, q, sq_thr=1.0):  # CameraJacobianAccumulator::residual (jacobian_impl.h:26-59), calibrated camera
+    Z = q[:, 2:] @ R.T + t
+    front = Z[:, 2] >= 0
+    z = Z[front, :2] / Z[front, 2:3]
+    r = z - q[front, :2]
+    return float(np.sum(np.fmin((r * r).sum(1), sq_thr)))
 
 
-def _pnp_system(R, t, q):
-    """J^T J (6x6), J^T r and the cost of the reprojection residuals for rows q = [u v X Y Z]"""
-    Xr = q[:, 2:] @ R.T
-    p = Xr + t
-    with np.errstate(divide="ignore", invalid="ignore"):
-        iz = 1.0 / p[:, 2]
-        ru, rv = p[:, 0] * iz - q[:, 0], p[:, 1] * iz - q[:, 1]
-        a0 = np.column_stack([iz, np.zeros(len(q)), -p[:, 0] * iz * iz])
-        a1 = np.column_stack([np.zeros(len(q)), iz, -p[:, 1] * iz * iz])
-        z = np.zeros(len(q))
-        Jw = np.stack([np.column_stack([z, Xr[:, 2], -Xr[:, 1]]), np.column_stack([-Xr[:, 2], z, Xr[:, 0]]),
-                       np.column_stack([Xr[:, 1], -Xr[:, 0], z])], axis=1)  # [n, 3 rows, 3 cols] = -[Xr]x
-        J0 = np.column_stack([np.einsum("nr,nrc->nc", a0, Jw), a0])
-        J1 = np.column_stack([np.einsum("nr,nrc->nc", a1, Jw), a1])
-        JtJ = J0.T @ J0 + J1.T @ J1
-        Jtr = J0.T @ ru + J1.T @ rv
-        cost = float(ru @ ru + rv @ rv)
-    return JtJ, Jtr, cost
+def _pnp_system(R, t, q, sq_thr=1.0):  # ...::accumulate (jacobian_impl.h:63-155): J^T J and J^T r, truncated-loss weights
+    X = q[:, 2:]
+    Z = X @ R.T + t
+    keep = Z[:, 2] >= 0
+    X, Z, x = X[keep], Z[keep], q[keep, :2]
+    z = Z[:, :2] / Z[:, 2:3]
+    r = z - x
+    on = (r * r).sum(1) < sq_thr
+    X, Z, z, r = X[on], Z[on], z[on], r[on]
+    iz = 1.0 / Z[:, 2]
+    d0 = (R[0][None, :] - z[:, 0:1] * R[2][None, :]) * iz[:, None]  # rows of dZ = [I | -z] R / Z_z
+    d1 = (R[1][None, :] - z[:, 1:2] * R[2][None, :]) * iz[:, None]
+
+    def rot(d):  # columns of -dZ [X]x
+        return np.column_stack([X[:, 1] * d[:, 2] - X[:, 2] * d[:, 1], X[:, 2] * d[:, 0] - X[:, 0] * d[:, 2],
+                                X[:, 0] * d[:, 1] - X[:, 1] * d[:, 0]])
+    J0 = np.column_stack([rot(d0), d0])
+    J1 = np.column_stack([rot(d1), d1])
+    return J0.T @ J0 + J1.T @ J1, J0.T @ r[:, 0] + J1.T @ r[:, 1]
 
 
 def fit_pnp_nonminimal(pts, idx):
-    """The GPU engine's non-minimal pose fit (pxb_fit_fp.cu, k_fit_pnp) restated with numpy: DLT on normalised 3D points,
-    projection of the left 3x3 onto SO(3), then Levenberg-Marquardt on the reprojection error with rollback -- the objective
-    of the reference's PnPBundleAdjustment (solver_pnp_bundle_adjustment.h:108-225 -> OpenCV EPnP + LM, not on disk)."""
+    """PerspectiveNPointEstimator::estimateModelNonminimal -> PnPBundleAdjustment (solver_pnp_bundle_adjustment.h:108-225)
+    restated with numpy, as k_fit_pnp (pxb_fit_fp.cu) does: the initial pose is a DLT on normalised 3D points projected onto
+    SO(3) (the reference: cv::solvePnP(EPNP), OpenCV -- not on disk), the refinement is PoseLib's refine_pnp = lm_pnp_impl
+    (relative_pose/bundle.cpp:24-100: truncated loss with loss_scale 1, lambda0 = 1e-3, LLT steps, R <- R exp([w]x),
+    t <- t + R dt, tolerances 1e-8, at most 25 iterations) over the sample with unit weights."""
     q = pts[np.asarray(idx, dtype=np.int64)]
     n = len(q)
     if n < 6:
@@ -407,32 +434,38 @@ def fit_pnp_nonminimal(pts, idx):
     R = U @ np.diag([1.0, 1.0, np.sign(np.linalg.det(U @ Vt)) or 1.0]) @ Vt
     tn = sg * Pn[:, 3] / scale
     t = tn / sc - R @ c
-    pose, best = (R, t), (R, t)
     if not (np.all(np.isfinite(R)) and np.all(np.isfinite(t))):
         return None, False
-    mu, best_cost = 1e-4, float("inf")
-    for _ in range(14):
-        R, t = pose
-        JtJ, Jtr, cost = _pnp_system(R, t, q)
-        if cost <= best_cost:
-            best_cost, best = cost, pose
-            mu *= 0.3
-        else:
-            pose = best
-            mu *= 10.0
-            continue
-        M6 = JtJ.copy()
-        M6[np.diag_indices(6)] *= (1.0 + mu)
+    cost = _pnp_cost(R, t, q)
+    lam, recompute = 1e-3, True
+    JtJ = Jtr = None
+    for _ in range(25):
+        if recompute:
+            JtJ, Jtr = _pnp_system(R, t, q)
+            if np.linalg.norm(Jtr) < 1e-8:
+                break
         try:
-            dlt = np.linalg.solve(M6, -Jtr)
+            L = np.linalg.cholesky(JtJ + lam * np.eye(6))
         except np.linalg.LinAlgError:
-            continue
-        if np.all(np.abs(dlt) <= 1e6):
-            pose = (_exp_left(dlt[:3], R), t + dlt[3:])
-    R, t = best
+            break
+        sol = -np.linalg.solve(L.T, np.linalg.solve(L, Jtr))
+        if np.linalg.norm(sol) < 1e-8:
+            break
+        with np.errstate(all="ignore"):
+            theta = np.linalg.norm(sol[:3])
+            sw = _skew(sol[:3] / theta)
+            Rn = R + R @ (math.sin(theta) * sw + (1 - math.cos(theta)) * sw @ sw)
+        tn2 = t + R @ sol[3:]
+        cost_new = _pnp_cost(Rn, tn2, q)
+        if cost_new < cost:
+            R, t, cost = Rn, tn2, cost_new
+            lam /= 10
+            recompute = True
+        else:
+            lam *= 10
+            recompute = False
     out = np.column_stack([R, t]).reshape(12)
     return (out, True) if np.all(np.isfinite(out)) else (None, False)
-
 
 
 class Score:

@@ -6,18 +6,21 @@
 //   k_fit_f    FundamentalMatrixEstimator::estimateModelNonminimal (gcr/estimators/fundamental_estimator.h:574-618):
 //              Hartley normalisation (:636-735), the n x 9 system of FundamentalMatrixEightPointSolver
 //              (solver_fundamental_matrix_eight_point.h:93-182) through A^T A, denormalisation F = T2^T Fn T1, unit
-//              Frobenius norm, f33 >= 0. DIFFERENCES: the reference takes the last column of a FullPivHouseholderQR of
-//              A^T A and then polishes with PoseLib's Levenberg-Marquardt (solver_fundamental_matrix_bundle_adjustment.h:
-//              114-178, relative_pose/bundle.cpp); here the null vector is the smallest eigenvector (cyclic Jacobi) and
-//              the rank-2 constraint is imposed by a 3x3 SVD instead of the LM parametrisation. n >= 8 required.
+//              Frobenius norm, f33 >= 0, and in between PoseLib's Levenberg-Marquardt refinement restated (lm_F_impl,
+//              relative_pose/bundle.cpp:253-340: 7-parameter factorised F, truncated loss, LLT steps -- see the kernel).
+//              DIFFERENCES: the reference's eight-point step takes the last column of a FullPivHouseholderQR of A^T A,
+//              here the null vector is the smallest eigenvector (cyclic Jacobi) -- both only seed the LM; n >= 8 required
+//              (for n == 7 the reference refines the up-to-three seven-point solutions).
 //   k_fit_pnp  PerspectiveNPointEstimator::estimateModelNonminimal -> PnPBundleAdjustment (solver_pnp_bundle_adjustment.h:
-//              108-225): the reference initialises with cv::solvePnP(EPNP) and refines with PoseLib LM; here the
-//              initialisation is a normalised DLT (n >= 6) projected onto SO(3), followed by 10 Levenberg-Marquardt
-//              steps on the squared reprojection error (6 parameters, left-multiplicative rotation update).
+//              108-225): the reference initialises with cv::solvePnP(EPNP) (OpenCV, not on disk) and refines with PoseLib's
+//              refine_pnp; here the initialisation is a normalised DLT (n >= 6) projected onto SO(3) and the refinement is
+//              lm_pnp_impl restated (relative_pose/bundle.cpp:24-100: truncated loss, LLT steps, right-multiplicative
+//              rotation update -- see the kernel).
 //   k_f_sym_count  the symmetric-epipolar recount of FundamentalMatrixEstimator::isValidModel (:268-325, :224-252).
 //
-// These two solvers have no bit-level parity claim (the reference's own versions depend on Eigen/OpenCV internals);
-// they are validated by what they must achieve: residuals of the fit on its own inliers (tests/test_gpu_fits.py).
+// These two solvers have no bit-level parity claim (the reference's own versions depend on Eigen/OpenCV internals); they
+// are compared with numpy restatements of the same algorithms (oracle/px_sequential.py, 1e-9 / 1e-7) and validated by what
+// they must achieve: residuals of the fit on its own inliers (tests/test_gpu_fits.py).
 #include <cfloat>
 
 #include "pxb_internal.h"
@@ -78,6 +81,80 @@ template <int NN> __device__ void jacobi_eig(double *A, double *V, double *w) {
 	for (int i = 0; i < NN; ++i) w[i] = A[i * NN + i];
 }
 
+// The same cyclic Jacobi executed by ONE WARP on matrices in shared memory: lane k applies a rotation to row / column k,
+// so a rotation costs three short phases instead of ~6 NN dependent local-memory updates in one thread (the 12 x 12
+// eigenproblem of the pose DLT took several hundred microseconds in the serial form). Rotation arithmetic per element is
+// unchanged.
+template <int NN> __device__ void jacobi_eig_warp(double *A, double *V, double *w) {
+	const int lane = threadIdx.x & 31;
+	for (int e = lane; e < NN * NN; e += 32) V[e] = (e / NN == e % NN) ? 1.0 : 0.0;
+	__syncwarp();
+	for (int sweep = 0; sweep < 60; ++sweep) {
+		double off = 0.0, diag = 0.0;
+		for (int e = lane; e < NN * NN; e += 32) {
+			const int i = e / NN, j = e % NN;
+			const double a = A[e];
+			if (i == j) diag += a * a;
+			else if (j > i) off += a * a;
+		}
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) {
+			off += __shfl_xor_sync(0xffffffffu, off, o);
+			diag += __shfl_xor_sync(0xffffffffu, diag, o);
+		}
+		if (!(off > 1e-30 * diag) || !(off == off)) break;
+		for (int p = 0; p < NN - 1; ++p)
+			for (int q = p + 1; q < NN; ++q) {
+				const double apq = A[p * NN + q];
+				if (apq == 0.0) continue; // warp-uniform
+				const double theta = (A[q * NN + q] - A[p * NN + p]) / (2.0 * apq);
+				const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+				const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+				__syncwarp();
+				if (lane < NN) {
+					const double akp = A[lane * NN + p], akq = A[lane * NN + q];
+					A[lane * NN + p] = c * akp - sn * akq;
+					A[lane * NN + q] = sn * akp + c * akq;
+				}
+				__syncwarp();
+				if (lane < NN) {
+					const double apk = A[p * NN + lane], aqk = A[q * NN + lane];
+					A[p * NN + lane] = c * apk - sn * aqk;
+					A[q * NN + lane] = sn * apk + c * aqk;
+					const double vkp = V[lane * NN + p], vkq = V[lane * NN + q];
+					V[lane * NN + p] = c * vkp - sn * vkq;
+					V[lane * NN + q] = sn * vkp + c * vkq;
+				}
+				__syncwarp();
+			}
+	}
+	__syncwarp();
+	if (lane < NN) w[lane] = A[lane * NN + lane];
+	__syncwarp();
+}
+
+// sums of NV per-thread values over the block (butterfly inside the warp, then the warps in order): two barriers for
+// the whole vector. s_vec: [kFitT / 32][NV] shared, out: [NV] shared.
+template <int NV> __device__ __forceinline__ void fp_block_sums(double (&v)[NV], double *s_vec, double *out) {
+#pragma unroll
+	for (int a = 0; a < NV; ++a)
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) v[a] = add(v[a], __shfl_xor_sync(0xffffffffu, v[a], o));
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	__syncthreads();
+	if (lane == 0)
+#pragma unroll
+		for (int a = 0; a < NV; ++a) s_vec[warp * NV + a] = v[a];
+	__syncthreads();
+	if (threadIdx.x < NV) {
+		double t = 0.0;
+#pragma unroll
+		for (int wv = 0; wv < kFitT / 32; ++wv) t = add(t, s_vec[wv * NV + threadIdx.x]);
+		out[threadIdx.x] = t;
+	}
+	__syncthreads();
+}
+
 // M = U diag(s) V^T for a 3x3 (via the eigen-decomposition of M^T M); singular values descending
 __device__ void svd3(const double *M, double *U, double *s, double *V) {
 	double MtM[9], w[3];
@@ -111,21 +188,6 @@ __device__ void svd3(const double *M, double *U, double *s, double *V) {
 // ------------------------------------------------------------------------------------------------
 // fundamental matrix
 // ------------------------------------------------------------------------------------------------
-// closest rank-2 matrix (smallest singular value zeroed), scaled to unit Frobenius norm
-__device__ void fp_rank2_unit(double *F) {
-	double U[9], s[3], Vt[9];
-	svd3(F, U, s, Vt);
-	double nrm = 0.0;
-	for (int r = 0; r < 3; ++r)
-		for (int c = 0; c < 3; ++c) {
-			F[r * 3 + c] = U[r * 3 + 0] * s[0] * Vt[c * 3 + 0] + U[r * 3 + 1] * s[1] * Vt[c * 3 + 1];
-			nrm += F[r * 3 + c] * F[r * 3 + c];
-		}
-	nrm = sqrt(nrm);
-	if (nrm > 0.0)
-		for (int i = 0; i < 9; ++i) F[i] /= nrm;
-}
-
 __global__ void __launch_bounds__(kFitT)
     k_fit_f(const double *__restrict__ aos, const int32_t *__restrict__ off, const int32_t *__restrict__ idx,
             const double *__restrict__ weights, double *__restrict__ F_out, int32_t *__restrict__ ok_out) {
@@ -171,157 +233,224 @@ __global__ void __launch_bounds__(kFitT)
 #pragma unroll
 			for (int c = r; c < 9; ++c, ++a) acc[a] = add(acc[a], mul(row[r], row[c]));
 	}
-	for (int a = 0; a < 45; ++a) {
-		const double v = fp_block_sum(acc[a], s_tmp);
-		if (tid == 0) s_acc[a] = v;
+	__shared__ double s_big[(kFitT / 32) * 45];
+	fp_block_sums<45>(acc, s_big, s_acc);
+	// ---- FundamentalMatrixBundleAdjustmentSolver (solver_fundamental_matrix_bundle_adjustment.h:114-178): the eight-point
+	// estimate is refined by PoseLib's refine_fundamental = lm_F_impl (relative_pose/bundle.cpp:253-340,454-500) ON THE
+	// NORMALISED points (fundamental_estimator.h:586-603 hands the solver `normalized_points`), restated here:
+	//   * F = U diag(1, sigma, 0) V^T (FactorizedFundamentalMatrix, jacobian_impl.h:472-488), 7 parameters: U <- exp([w1]x) U,
+	//     V <- exp([w2]x) V, sigma <- sigma + d;
+	//   * residual r = C / |J_C| (Sampson), cost = sum w_k min(r^2, loss_scale^2) with the TRUNCATED loss, loss_scale = 1
+	//     (normalised units), IRLS weight (r^2 < 1) / n (jacobian_impl.h:504-606);
+	//   * Levenberg-Marquardt: lambda0 = 1e-3, +lambda on the diagonal, LLT solve, step accepted iff the cost decreases
+	//     (lambda /= 10, Jacobian recomputed) else lambda *= 10; stops at |J^T r| < 1e-8, |step| < 1e-8 or 25 iterations.
+	// Column sums use the library's fixed block topology. Not restated: the 7-point initialisation for n == 7 (n >= 8 here).
+	__shared__ double s_U[9], s_V[9], s_Fc[9], s_Un[9], s_Vn[9], s_Fn[9], s_vec[kFitT / 32][36], s_sys[36];
+	__shared__ double s_sigma, s_sigma_n;
+	__shared__ int s_go;
+	auto compose = [](const double *U, const double *V, double sigma, double *F) { // U.col(0) V.col(0)^T + sigma U.col(1) V.col(1)^T
+		for (int r = 0; r < 3; ++r)
+			for (int c = 0; c < 3; ++c) F[r * 3 + c] = U[r * 3 + 0] * V[c * 3 + 0] + sigma * U[r * 3 + 1] * V[c * 3 + 1];
+	};
+	__shared__ double s_A[81], s_Vv[81], s_w[9];
+	if (tid < 32) {
+		int a = 0;
+		if (tid == 0)
+			for (int r = 0; r < 9; ++r)
+				for (int c = r; c < 9; ++c, ++a) s_A[r * 9 + c] = s_A[c * 9 + r] = s_acc[a];
+		__syncwarp();
+		jacobi_eig_warp<9>(s_A, s_Vv, s_w);
 	}
 	__syncthreads();
-	__shared__ double s_F[9], s_cand[9], s_vec[kFitT / 32][56], s_sys[56];
-	__shared__ int s_go;
 	if (tid == 0) {
-		double A[81], V[81], w[9];
-		int a = 0;
-		for (int r = 0; r < 9; ++r)
-			for (int c = r; c < 9; ++c, ++a) A[r * 9 + c] = A[c * 9 + r] = s_acc[a];
-		jacobi_eig<9>(A, V, w);
 		int best = 0;
 		for (int i = 1; i < 9; ++i)
-			if (w[i] < w[best]) best = i;
-		double Fn[9];
-		for (int i = 0; i < 9; ++i) Fn[i] = V[i * 9 + best];
-		fp_rank2_unit(Fn);
-		// the polish below works with ONE scale for both images (rs = sqrt(r1 r2)), so that its Sampson error is the pixel
-		// Sampson error times a constant: y_i = rs (x - m_i) = (rs / r_i) xn_i  =>  F_lm = K2 Fn K1, K_i = diag(r_i/rs, r_i/rs, 1)
-		const double rs = sqrt(r1 * r2), k1 = r1 / rs, k2 = r2 / rs;
-		for (int r = 0; r < 3; ++r)
-			for (int c = 0; c < 3; ++c) s_F[r * 3 + c] = Fn[r * 3 + c] * (r < 2 ? k2 : 1.0) * (c < 2 ? k1 : 1.0);
-		fp_rank2_unit(s_F);
+			if (s_w[i] < s_w[best]) best = i;
+		double Fn[9], sv[3];
+		for (int i = 0; i < 9; ++i) Fn[i] = s_Vv[i * 9 + best];
+		svd3(Fn, s_U, sv, s_V); // FactorizedFundamentalMatrix(F): U, V of the SVD, sigma = s1 / s0
+		s_sigma = sv[0] > 0.0 ? sv[1] / sv[0] : 0.0;
+		compose(s_U, s_V, s_sigma, s_Fc);
 	}
 	__syncthreads();
-	// ---- Levenberg-Marquardt polish of the (weighted) Sampson error, the objective of the reference's bundle adjustment
-	// (solver_fundamental_matrix_bundle_adjustment.h:114-178 -> PoseLib refine_fundamental). 9 parameters with Marquardt
-	// scaling; the scale gauge is absorbed by the damping, the rank-2 constraint is re-imposed after every step, and a
-	// step is kept only if the error decreases.
-	const double rs = sqrt(r1 * r2);
-	auto accumulate = [&](const double *F, double *sys /*45 JtJ + 9 Jtr + cost*/) {
-		double acc2[55];
-#pragma unroll
-		for (int a = 0; a < 55; ++a) acc2[a] = 0.0;
+	const double sq_thr = 1.0; // TruncatedLoss(loss_scale = 1.0)
+	// cost of F: sum_k w_k min(r_k^2, thr^2)  (FundamentalJacobianAccumulator::residual)
+	auto lm_cost = [&](const double *F) -> double {
+		double c = 0.0;
 		for (int t = tid; t < n; t += kFitT) {
 			const double *q = aos + 4 * (int64_t)idx[beg + t];
-			const double x1[3] = {(q[0] - mx1) * rs, (q[1] - my1) * rs, 1.0}, x2[3] = {(q[2] - mx2) * rs, (q[3] - my2) * rs, 1.0};
-			const double wgt = weights ? weights[t] : 1.0;
-			double Fx[3], Ftx[3];
-			for (int r = 0; r < 3; ++r) Fx[r] = F[r * 3] * x1[0] + F[r * 3 + 1] * x1[1] + F[r * 3 + 2];
-			for (int c = 0; c < 3; ++c) Ftx[c] = F[c] * x2[0] + F[3 + c] * x2[1] + F[6 + c];
-			const double C = x2[0] * Fx[0] + x2[1] * Fx[1] + Fx[2];
-			const double S = Fx[0] * Fx[0] + Fx[1] * Fx[1] + Ftx[0] * Ftx[0] + Ftx[1] * Ftx[1];
-			if (!(S > 1e-300)) continue;
-			const double inv = 1.0 / sqrt(S), res = wgt * C * inv;
-			double J[9];
+			const double x1 = (q[0] - mx1) * r1, y1 = (q[1] - my1) * r1, x2 = (q[2] - mx2) * r2, y2 = (q[3] - my2) * r2;
+			const double Fx0 = F[0] * x1 + F[1] * y1 + F[2], Fx1 = F[3] * x1 + F[4] * y1 + F[5], Fx2 = F[6] * x1 + F[7] * y1 + F[8];
+			const double Ft0 = F[0] * x2 + F[3] * y2 + F[6], Ft1 = F[1] * x2 + F[4] * y2 + F[7];
+			const double C = x2 * Fx0 + y2 * Fx1 + Fx2;
+			const double nJ = Fx0 * Fx0 + Fx1 * Fx1 + Ft0 * Ft0 + Ft1 * Ft1;
+			const double rr = (C * C) / nJ;
+			const double l = fmin(rr, sq_thr); // std::min(r2, squared_thr): NaN r2 gives squared_thr
+			c += weights ? weights[t] * l : l;
+		}
+		return fp_block_sum(c, s_tmp);
+	};
+	// J^T J (lower, 28) and J^T r (7) of F = compose(U, V, sigma)  (FundamentalJacobianAccumulator::accumulate)
+	auto lm_accumulate = [&](const double *F, const double *U, const double *V, double *sys /*35*/) {
+		double acc2[35];
+#pragma unroll
+		for (int a = 0; a < 35; ++a) acc2[a] = 0.0;
+		// dF/dparams: d/dw1_k = [e_k]x F, d/dw2_k = -F [e_k]x, d/dsigma = U.col(1) V.col(1)^T
+		double dP[7][9];
+		for (int c = 0; c < 3; ++c) {
+			dP[0][0 + c] = 0.0, dP[0][3 + c] = -F[6 + c], dP[0][6 + c] = F[3 + c];
+			dP[1][0 + c] = F[6 + c], dP[1][3 + c] = 0.0, dP[1][6 + c] = -F[0 + c];
+			dP[2][0 + c] = -F[3 + c], dP[2][3 + c] = F[0 + c], dP[2][6 + c] = 0.0;
+		}
+		for (int r = 0; r < 3; ++r) {
+			dP[3][r * 3 + 0] = 0.0, dP[3][r * 3 + 1] = F[r * 3 + 2], dP[3][r * 3 + 2] = -F[r * 3 + 1];
+			dP[4][r * 3 + 0] = -F[r * 3 + 2], dP[4][r * 3 + 1] = 0.0, dP[4][r * 3 + 2] = F[r * 3 + 0];
+			dP[5][r * 3 + 0] = F[r * 3 + 1], dP[5][r * 3 + 1] = -F[r * 3 + 0], dP[5][r * 3 + 2] = 0.0;
+			for (int c = 0; c < 3; ++c) dP[6][r * 3 + c] = U[r * 3 + 1] * V[c * 3 + 1];
+		}
+		for (int t = tid; t < n; t += kFitT) {
+			const double *q = aos + 4 * (int64_t)idx[beg + t];
+			const double p1[3] = {(q[0] - mx1) * r1, (q[1] - my1) * r1, 1.0}, p2[3] = {(q[2] - mx2) * r2, (q[3] - my2) * r2, 1.0};
+			double Fx[3], Ft[3];
+			for (int r = 0; r < 3; ++r) Fx[r] = F[r * 3] * p1[0] + F[r * 3 + 1] * p1[1] + F[r * 3 + 2];
+			for (int c = 0; c < 3; ++c) Ft[c] = F[c] * p2[0] + F[3 + c] * p2[1] + F[6 + c];
+			const double C = p2[0] * Fx[0] + p2[1] * Fx[1] + Fx[2];
+			const double nJ = sqrt(Ft[0] * Ft[0] + Ft[1] * Ft[1] + Fx[0] * Fx[0] + Fx[1] * Fx[1]);
+			const double inv = 1.0 / nJ, res = C * inv;
+			double wgt = ((res * res < sq_thr) ? 1.0 : 0.0) / (double)n; // loss_fn.weight(r^2) / sample_size
+			if (weights) wgt = weights[t] * wgt;
+			if (wgt == 0.0) continue;
+			const double sC = C * inv * inv;
+			double G[9]; // d r / d F(r, c)
 			for (int r = 0; r < 3; ++r)
-				for (int c = 0; c < 3; ++c) {
-					const double dC = x2[r] * x1[c];
-					const double dS = 2.0 * ((r < 2 ? Fx[r] * x1[c] : 0.0) + (c < 2 ? Ftx[c] * x2[r] : 0.0));
-					J[r * 3 + c] = wgt * (dC * inv - 0.5 * C * inv * inv * inv * dS);
-				}
+				for (int c = 0; c < 3; ++c)
+					G[r * 3 + c] = (p2[r] * p1[c] - sC * ((c < 2 ? Ft[c] * p2[r] : 0.0) + (r < 2 ? Fx[r] * p1[c] : 0.0))) * inv;
+			double J[7];
+#pragma unroll
+			for (int k = 0; k < 7; ++k) {
+				double v = 0.0;
+#pragma unroll
+				for (int e = 0; e < 9; ++e) v += G[e] * dP[k][e];
+				J[k] = v;
+			}
 			int a = 0;
 #pragma unroll
-			for (int r = 0; r < 9; ++r)
+			for (int i = 0; i < 7; ++i)
 #pragma unroll
-				for (int c = r; c < 9; ++c, ++a) acc2[a] += J[r] * J[c];
+				for (int j = 0; j <= i; ++j, ++a) acc2[a] += wgt * (J[i] * J[j]);
 #pragma unroll
-			for (int r = 0; r < 9; ++r) acc2[45 + r] += J[r] * res;
-			acc2[54] += res * res;
+			for (int i = 0; i < 7; ++i) acc2[28 + i] += wgt * res * J[i];
 		}
-		// vector block reduction: butterfly inside each warp, then 55 threads add the 8 warp rows in order
 #pragma unroll
-		for (int a = 0; a < 55; ++a)
+		for (int a = 0; a < 35; ++a)
 #pragma unroll
 			for (int o = 16; o > 0; o >>= 1) acc2[a] += __shfl_xor_sync(0xffffffffu, acc2[a], o);
 		__syncthreads();
 		if ((tid & 31) == 0)
-			for (int a = 0; a < 55; ++a) s_vec[tid >> 5][a] = acc2[a];
+			for (int a = 0; a < 35; ++a) s_vec[tid >> 5][a] = acc2[a];
 		__syncthreads();
-		if (tid < 55) {
+		if (tid < 35) {
 			double v = 0.0;
 			for (int wv = 0; wv < kFitT / 32; ++wv) v += s_vec[wv][tid];
 			sys[tid] = v;
 		}
 		__syncthreads();
 	};
-	accumulate(s_F, s_sys);
-	__shared__ double s_sys2[56];
-	double mu = 1e-3;
-	for (int it = 0; it < 8; ++it) {
-		if (tid == 0) { // solve (JtJ + mu diag(JtJ)) delta = -Jtr by Gaussian elimination with partial pivoting
-			double M[9][10];
-			int a = 0;
-			for (int r = 0; r < 9; ++r)
-				for (int c = r; c < 9; ++c, ++a) M[r][c] = M[c][r] = s_sys[a];
-			for (int r = 0; r < 9; ++r) {
-				M[r][r] += mu * fmax(M[r][r], 1e-12);
-				M[r][9] = -s_sys[45 + r];
-			}
-			bool okk = true;
-			for (int k = 0; k < 9 && okk; ++k) {
-				int piv = k;
-				for (int r = k + 1; r < 9; ++r)
-					if (fabs(M[r][k]) > fabs(M[piv][k])) piv = r;
-				if (!(fabs(M[piv][k]) > 1e-300)) {
-					okk = false;
-					break;
-				}
-				if (piv != k)
-					for (int c = 0; c < 10; ++c) {
-						const double t = M[k][c];
-						M[k][c] = M[piv][c];
-						M[piv][c] = t;
+	double cost = lm_cost(s_Fc);
+	double lambda = 1e-3;
+	bool recompute = true;
+	for (int iter = 0; iter < 25; ++iter) {
+		if (recompute) lm_accumulate(s_Fc, s_U, s_V, s_sys);
+		if (tid == 0) {
+			int go = 1;
+			double g2 = 0.0;
+			for (int i = 0; i < 7; ++i) g2 += s_sys[28 + i] * s_sys[28 + i];
+			if (recompute && sqrt(g2) < 1e-8) go = 0; // gradient_tol
+			double sol[7];
+			if (go) { // (J^T J + lambda I) sol = -J^T r by LLT (lower triangle)
+				double Lm[7][7];
+				int a = 0;
+				for (int i = 0; i < 7; ++i)
+					for (int j = 0; j <= i; ++j, ++a) Lm[i][j] = s_sys[a] + (i == j ? lambda : 0.0);
+				for (int j = 0; j < 7 && go; ++j) {
+					double d = Lm[j][j];
+					for (int k = 0; k < j; ++k) d -= Lm[j][k] * Lm[j][k];
+					if (!(d > 0.0)) {
+						go = 0; // not positive definite: Eigen's LLT would return garbage; stop with the current estimate
+						break;
 					}
-				for (int r = k + 1; r < 9; ++r) {
-					const double f = M[r][k] / M[k][k];
-					for (int c = k; c < 10; ++c) M[r][c] -= f * M[k][c];
+					Lm[j][j] = sqrt(d);
+					for (int i = j + 1; i < 7; ++i) {
+						double v = Lm[i][j];
+						for (int k = 0; k < j; ++k) v -= Lm[i][k] * Lm[j][k];
+						Lm[i][j] = v / Lm[j][j];
+					}
+				}
+				if (go) {
+					double y[7];
+					for (int i = 0; i < 7; ++i) {
+						double v = s_sys[28 + i];
+						for (int k = 0; k < i; ++k) v -= Lm[i][k] * y[k];
+						y[i] = v / Lm[i][i];
+					}
+					for (int i = 6; i >= 0; --i) {
+						double v = y[i];
+						for (int k = i + 1; k < 7; ++k) v -= Lm[k][i] * sol[k];
+						sol[i] = -(v / Lm[i][i]);
+					}
+					// sol = -(A^-1 g): the loop above solved A x = g and negated
+					double s2 = 0.0;
+					for (int i = 0; i < 7; ++i) s2 += sol[i] * sol[i];
+					if (sqrt(s2) < 1e-8) go = 0; // step_tol
 				}
 			}
-			double delta[9];
-			if (okk)
-				for (int r = 8; r >= 0; --r) {
-					double v = M[r][9];
-					for (int c = r + 1; c < 9; ++c) v -= M[r][c] * delta[c];
-					delta[r] = v / M[r][r];
-					okk &= fabs(delta[r]) <= 1e300;
+			if (go) { // U <- U + (a sw + (1 - b) sw^2) U, same for V; sigma += sol(6)
+				for (int side = 0; side < 2; ++side) {
+					double wv[3] = {sol[3 * side], sol[3 * side + 1], sol[3 * side + 2]};
+					const double theta = sqrt(wv[0] * wv[0] + wv[1] * wv[1] + wv[2] * wv[2]);
+					for (int i = 0; i < 3; ++i) wv[i] /= theta;
+					const double a1 = sin(theta), b1 = cos(theta);
+					const double sw[9] = {0, -wv[2], wv[1], wv[2], 0, -wv[0], -wv[1], wv[0], 0};
+					double sw2[9], R[9];
+					for (int i = 0; i < 3; ++i)
+						for (int j = 0; j < 3; ++j) sw2[i * 3 + j] = sw[i * 3] * sw[j] + sw[i * 3 + 1] * sw[3 + j] + sw[i * 3 + 2] * sw[6 + j];
+					for (int i = 0; i < 9; ++i) R[i] = a1 * sw[i] + (1 - b1) * sw2[i];
+					const double *M = side == 0 ? s_U : s_V;
+					double *Mn = side == 0 ? s_Un : s_Vn;
+					for (int i = 0; i < 3; ++i)
+						for (int j = 0; j < 3; ++j)
+							Mn[i * 3 + j] = M[i * 3 + j] + (R[i * 3] * M[j] + R[i * 3 + 1] * M[3 + j] + R[i * 3 + 2] * M[6 + j]);
 				}
-			if (okk) {
-				for (int i = 0; i < 9; ++i) s_cand[i] = s_F[i] + delta[i];
-				fp_rank2_unit(s_cand);
+				s_sigma_n = s_sigma + sol[6];
+				compose(s_Un, s_Vn, s_sigma_n, s_Fn);
 			}
-			s_go = okk ? 1 : 0;
+			s_go = go;
 		}
 		__syncthreads();
 		if (!s_go) break; // block-uniform
-		accumulate(s_cand, s_sys2);
-		if (tid == 0) {
-			if (s_sys2[54] < s_sys[54]) {
-				const bool small = (s_sys[54] - s_sys2[54]) <= 1e-12 * s_sys[54];
-				for (int i = 0; i < 9; ++i) s_F[i] = s_cand[i];
-				for (int i = 0; i < 55; ++i) s_sys[i] = s_sys2[i];
-				s_go = small ? 0 : 1;
-			} else {
-				s_go = 2; // rejected: more damping
+		const double cost_new = lm_cost(s_Fn);
+		__syncthreads();
+		if (cost_new < cost) {
+			if (tid == 0) {
+				for (int i = 0; i < 9; ++i) s_U[i] = s_Un[i], s_V[i] = s_Vn[i], s_Fc[i] = s_Fn[i];
+				s_sigma = s_sigma_n;
 			}
+			lambda /= 10;
+			cost = cost_new;
+			recompute = true;
+		} else {
+			lambda *= 10;
+			recompute = false;
 		}
 		__syncthreads();
-		if (s_go == 0) break;
-		mu = (s_go == 2) ? mu * 10.0 : mu * 0.3;
-		if (mu > 1e6) break;
 	}
 	if (tid != 0) return;
-	// F = T2^T F_lm T1 with T_i = [rs 0 -rs m_x; 0 rs -rs m_y; 0 0 1]
-	const double T1[9] = {rs, 0, -rs * mx1, 0, rs, -rs * my1, 0, 0, 1};
-	const double T2[9] = {rs, 0, -rs * mx2, 0, rs, -rs * my2, 0, 0, 1};
+	// F = T2^T F_lm T1 with T_i = [r_i 0 -r_i m_x; 0 r_i -r_i m_y; 0 0 1] (fundamental_estimator.h:604-613)
+	const double T1[9] = {r1, 0, -r1 * mx1, 0, r1, -r1 * my1, 0, 0, 1};
+	const double T2[9] = {r2, 0, -r2 * mx2, 0, r2, -r2 * my2, 0, 0, 1};
 	double tmp[9], F[9];
 	for (int r = 0; r < 3; ++r)
-		for (int c = 0; c < 3; ++c) tmp[r * 3 + c] = T2[0 + r] * s_F[0 + c] + T2[3 + r] * s_F[3 + c] + T2[6 + r] * s_F[6 + c];
+		for (int c = 0; c < 3; ++c) tmp[r * 3 + c] = T2[0 + r] * s_Fc[0 + c] + T2[3 + r] * s_Fc[3 + c] + T2[6 + r] * s_Fc[6 + c];
 	for (int r = 0; r < 3; ++r)
 		for (int c = 0; c < 3; ++c) F[r * 3 + c] = tmp[r * 3 + 0] * T1[0 + c] + tmp[r * 3 + 1] * T1[3 + c] + tmp[r * 3 + 2] * T1[6 + c];
 	double nrm = 0;
@@ -408,9 +537,9 @@ __global__ void __launch_bounds__(kFitT)
               double *__restrict__ P_out, int32_t *__restrict__ ok_out) {
 	__shared__ double s_tmp[kFitT / 32];
 	__shared__ double s_acc[78];
-	__shared__ double s_pose[12], s_best[12];
-	__shared__ double s_best_cost;
-	__shared__ int s_ok, s_skip;
+	__shared__ double s_big[(kFitT / 32) * 78], s_A[144], s_Vv[144], s_w[12];
+	__shared__ double s_pose[12], s_new[12], s_sys[28];
+	__shared__ int s_ok, s_go;
 	const int pb = blockIdx.x, tid = threadIdx.x;
 	const int beg = off[pb], n = off[pb + 1] - beg;
 	if (n < 6) {
@@ -452,18 +581,20 @@ __global__ void __launch_bounds__(kFitT)
 #pragma unroll
 				for (int c = r; c < 12; ++c, ++a) acc[a] = add(acc[a], add(mul(ra[r], ra[c]), mul(rb[r], rb[c])));
 		}
-		for (int a = 0; a < 78; ++a) {
-			const double v = fp_block_sum(acc[a], s_tmp);
-			if (tid == 0) s_acc[a] = v;
+		fp_block_sums<78>(acc, s_big, s_acc);
+	}
+	if (tid < 32) {
+		if (tid == 0) {
+			int a = 0;
+			for (int r = 0; r < 12; ++r)
+				for (int c = r; c < 12; ++c, ++a) s_A[r * 12 + c] = s_A[c * 12 + r] = s_acc[a];
 		}
+		__syncwarp();
+		jacobi_eig_warp<12>(s_A, s_Vv, s_w);
 	}
 	__syncthreads();
 	if (tid == 0) {
-		double A[144], V[144], w[12];
-		int a = 0;
-		for (int r = 0; r < 12; ++r)
-			for (int c = r; c < 12; ++c, ++a) A[r * 12 + c] = A[c * 12 + r] = s_acc[a];
-		jacobi_eig<12>(A, V, w);
+		const double *V = s_Vv, *w = s_w;
 		int best = 0;
 		for (int i = 1; i < 12; ++i)
 			if (w[i] < w[best]) best = i;
@@ -506,135 +637,144 @@ __global__ void __launch_bounds__(kFitT)
 		if (tid == 0) ok_out[pb] = 0;
 		return;
 	}
-	// ---- Levenberg-Marquardt on sum ||proj(R X + t) - (u, v)||^2 (steps that raise the cost are rolled back) ----
-	double mu = 1e-4;
-	if (tid == 0) {
-		s_best_cost = DBL_MAX;
-		for (int i = 0; i < 12; ++i) s_best[i] = s_pose[i];
-	}
-	__syncthreads();
-	for (int it = 0; it < 14; ++it) {
-		double R[9], tt[3];
-		for (int r = 0; r < 3; ++r) {
-			R[r * 3 + 0] = s_pose[4 * r + 0];
-			R[r * 3 + 1] = s_pose[4 * r + 1];
-			R[r * 3 + 2] = s_pose[4 * r + 2];
-			tt[r] = s_pose[4 * r + 3];
-		}
-		double acc[28]; // 21 JtJ + 6 Jtr + cost
-#pragma unroll
-		for (int a = 0; a < 28; ++a) acc[a] = 0.0;
+	// ---- PoseLib's refine_pnp = lm_pnp_impl (relative_pose/bundle.cpp:24-100,558-597) with the calibrated camera model,
+	// restated: residual r = (R X + t).hnormalized() - x over the points in front of the camera (Z_z >= 0), TRUNCATED loss
+	// with loss_scale = 1 (normalised image units) -- cost = sum min(|r|^2, 1), IRLS weight (|r|^2 < 1) --, J = [dZ (-[X]x) | dZ]
+	// with dZ = [I | -z] R / Z_z (rotation by right multiplication R <- R exp([w]x), t <- t + R dt; jacobian_impl.h:61-155),
+	// LM exactly as for F above: lambda0 = 1e-3 added to the diagonal, LLT, accept iff the cost decreases, tolerances 1e-8,
+	// at most 25 iterations. The reference's accumulator iterates over correspondences->rows with sample[i] and reads
+	// weights[i] unconditionally (jacobian_impl.h:32-56,76-104) -- out-of-bounds / null reads for a sample shorter than the
+	// data; restated as intended: over the sample, unit weights.
+	const double sq_thr = 1.0;
+	auto pnp_cost = [&](const double *P) -> double {
+		double c = 0.0;
 		for (int t = tid; t < n; t += kFitT) {
 			const double *q = aos + 5 * (int64_t)idx[beg + t];
-			const double Xr[3] = {R[0] * q[2] + R[1] * q[3] + R[2] * q[4], R[3] * q[2] + R[4] * q[3] + R[5] * q[4],
-			                      R[6] * q[2] + R[7] * q[3] + R[8] * q[4]};
-			const double x = Xr[0] + tt[0], y = Xr[1] + tt[1], z = Xr[2] + tt[2];
-			const double iz = 1.0 / z;
-			const double ru = x * iz - q[0], rv = y * iz - q[1];
-			// d(res)/dp
-			const double a0[3] = {iz, 0, -x * iz * iz}, a1[3] = {0, iz, -y * iz * iz};
-			// dp/dw = -[Xr]x, dp/dt = I
-			const double Jw[9] = {0, Xr[2], -Xr[1], -Xr[2], 0, Xr[0], Xr[1], -Xr[0], 0};
-			double J0[6], J1[6];
+			const double Zx = P[0] * q[2] + P[1] * q[3] + P[2] * q[4] + P[3], Zy = P[4] * q[2] + P[5] * q[3] + P[6] * q[4] + P[7],
+			             Zz = P[8] * q[2] + P[9] * q[3] + P[10] * q[4] + P[11];
+			if (Zz < 0) continue;
+			const double iz = 1.0 / Zz, r0 = Zx * iz - q[0], r1 = Zy * iz - q[1];
+			c += fmin(r0 * r0 + r1 * r1, sq_thr);
+		}
+		return fp_block_sum(c, s_tmp);
+	};
+	auto pnp_accumulate = [&](const double *P, double *sys /*21 lower + 6*/) {
+		double acc[27];
+#pragma unroll
+		for (int a = 0; a < 27; ++a) acc[a] = 0.0;
+		for (int t = tid; t < n; t += kFitT) {
+			const double *q = aos + 5 * (int64_t)idx[beg + t];
+			const double X[3] = {q[2], q[3], q[4]};
+			const double Zx = P[0] * X[0] + P[1] * X[1] + P[2] * X[2] + P[3], Zy = P[4] * X[0] + P[5] * X[1] + P[6] * X[2] + P[7],
+			             Zz = P[8] * X[0] + P[9] * X[1] + P[10] * X[2] + P[11];
+			if (Zz < 0) continue;
+			const double iz = 1.0 / Zz, zx = Zx * iz, zy = Zy * iz;
+			const double r0 = zx - q[0], r1 = zy - q[1];
+			if (!(r0 * r0 + r1 * r1 < sq_thr)) continue; // loss_fn.weight == 0
+			// dZ = [1 0 -zx; 0 1 -zy] / Zz * R
+			double d0[3], d1[3];
 			for (int c = 0; c < 3; ++c) {
-				J0[c] = a0[0] * Jw[0 + c] + a0[1] * Jw[3 + c] + a0[2] * Jw[6 + c];
-				J1[c] = a1[0] * Jw[0 + c] + a1[1] * Jw[3 + c] + a1[2] * Jw[6 + c];
-				J0[3 + c] = a0[c];
-				J1[3 + c] = a1[c];
+				d0[c] = (P[c] - zx * P[8 + c]) * iz;
+				d1[c] = (P[4 + c] - zy * P[8 + c]) * iz;
 			}
+			// columns of -dZ [X]x: X1 dZ(:,2) - X2 dZ(:,1), X2 dZ(:,0) - X0 dZ(:,2), X0 dZ(:,1) - X1 dZ(:,0)
+			const double J0[6] = {X[1] * d0[2] - X[2] * d0[1], X[2] * d0[0] - X[0] * d0[2], X[0] * d0[1] - X[1] * d0[0], d0[0], d0[1], d0[2]};
+			const double J1[6] = {X[1] * d1[2] - X[2] * d1[1], X[2] * d1[0] - X[0] * d1[2], X[0] * d1[1] - X[1] * d1[0], d1[0], d1[1], d1[2]};
 			int a = 0;
 #pragma unroll
-			for (int r = 0; r < 6; ++r)
+			for (int i = 0; i < 6; ++i)
 #pragma unroll
-				for (int c = r; c < 6; ++c, ++a) acc[a] += J0[r] * J0[c] + J1[r] * J1[c];
+				for (int j = 0; j <= i; ++j, ++a) acc[a] += J0[i] * J0[j] + J1[i] * J1[j];
 #pragma unroll
-			for (int r = 0; r < 6; ++r) acc[21 + r] += J0[r] * ru + J1[r] * rv;
-			acc[27] += ru * ru + rv * rv;
+			for (int i = 0; i < 6; ++i) acc[21 + i] += J0[i] * r0 + J1[i] * r1;
 		}
-		__syncthreads();
-		for (int a = 0; a < 28; ++a) {
-			const double v = fp_block_sum(acc[a], s_tmp);
-			if (tid == 0) s_acc[a] = v;
-		}
-		__syncthreads();
+		fp_block_sums<27>(acc, s_big, sys);
+	};
+	double cost = pnp_cost(s_pose);
+	double lambda = 1e-3;
+	bool recompute = true;
+	for (int iter = 0; iter < 25; ++iter) {
+		if (recompute) pnp_accumulate(s_pose, s_sys);
 		if (tid == 0) {
-			const double cost = s_acc[27];
-			s_skip = 0;
-			if (cost <= s_best_cost) { // accept the pose the step led to
-				s_best_cost = cost;
-				for (int i = 0; i < 12; ++i) s_best[i] = s_pose[i];
-				mu *= 0.3;
-			} else { // roll back and damp harder; the normal equations are rebuilt at the kept pose next round
-				for (int i = 0; i < 12; ++i) s_pose[i] = s_best[i];
-				mu *= 10.0;
-				s_skip = 1;
+			int go = 1;
+			double g2 = 0.0;
+			for (int i = 0; i < 6; ++i) g2 += s_sys[21 + i] * s_sys[21 + i];
+			if (recompute && sqrt(g2) < 1e-8) go = 0; // gradient_tol
+			double sol[6];
+			if (go) {
+				double Lm[6][6];
+				int a = 0;
+				for (int i = 0; i < 6; ++i)
+					for (int j = 0; j <= i; ++j, ++a) Lm[i][j] = s_sys[a] + (i == j ? lambda : 0.0);
+				for (int j = 0; j < 6 && go; ++j) {
+					double d = Lm[j][j];
+					for (int k = 0; k < j; ++k) d -= Lm[j][k] * Lm[j][k];
+					if (!(d > 0.0)) {
+						go = 0;
+						break;
+					}
+					Lm[j][j] = sqrt(d);
+					for (int i = j + 1; i < 6; ++i) {
+						double v = Lm[i][j];
+						for (int k = 0; k < j; ++k) v -= Lm[i][k] * Lm[j][k];
+						Lm[i][j] = v / Lm[j][j];
+					}
+				}
+				if (go) {
+					double y[6];
+					for (int i = 0; i < 6; ++i) {
+						double v = s_sys[21 + i];
+						for (int k = 0; k < i; ++k) v -= Lm[i][k] * y[k];
+						y[i] = v / Lm[i][i];
+					}
+					for (int i = 5; i >= 0; --i) {
+						double v = y[i];
+						for (int k = i + 1; k < 6; ++k) v -= Lm[k][i] * sol[k];
+						sol[i] = -(v / Lm[i][i]);
+					}
+					double s2 = 0.0;
+					for (int i = 0; i < 6; ++i) s2 += sol[i] * sol[i];
+					if (sqrt(s2) < 1e-8) go = 0; // step_tol
+				}
 			}
+			if (go) { // R <- R + R (a sw + (1 - b) sw^2), t <- t + R sol(3:6)
+				double wv[3] = {sol[0], sol[1], sol[2]};
+				const double theta = sqrt(wv[0] * wv[0] + wv[1] * wv[1] + wv[2] * wv[2]);
+				for (int i = 0; i < 3; ++i) wv[i] /= theta;
+				const double a1 = sin(theta), b1 = cos(theta);
+				const double sw[9] = {0, -wv[2], wv[1], wv[2], 0, -wv[0], -wv[1], wv[0], 0};
+				double E[9];
+				for (int i = 0; i < 3; ++i)
+					for (int j = 0; j < 3; ++j)
+						E[i * 3 + j] = a1 * sw[i * 3 + j] + (1 - b1) * (sw[i * 3] * sw[j] + sw[i * 3 + 1] * sw[3 + j] + sw[i * 3 + 2] * sw[6 + j]);
+				for (int r = 0; r < 3; ++r) {
+					const double R0 = s_pose[4 * r], R1 = s_pose[4 * r + 1], R2 = s_pose[4 * r + 2];
+					for (int c = 0; c < 3; ++c) s_new[4 * r + c] = s_pose[4 * r + c] + (R0 * E[c] + R1 * E[3 + c] + R2 * E[6 + c]);
+					s_new[4 * r + 3] = s_pose[4 * r + 3] + (R0 * sol[3] + R1 * sol[4] + R2 * sol[5]);
+				}
+			}
+			s_go = go;
 		}
 		__syncthreads();
-		if (s_skip) continue;
-		if (tid == 0) {
-			double M[6][7];
-			int a = 0;
-			for (int r = 0; r < 6; ++r)
-				for (int c = r; c < 6; ++c, ++a) M[r][c] = M[c][r] = s_acc[a];
-			for (int r = 0; r < 6; ++r) {
-				M[r][r] *= (1.0 + mu);
-				M[r][6] = -s_acc[21 + r];
-			}
-			bool sing = false;
-			for (int c = 0; c < 6 && !sing; ++c) {
-				int piv = c;
-				for (int r = c + 1; r < 6; ++r)
-					if (fabs(M[r][c]) > fabs(M[piv][c])) piv = r;
-				if (!(fabs(M[piv][c]) > 0)) {
-					sing = true;
-					break;
-				}
-				if (piv != c)
-					for (int j = 0; j < 7; ++j) {
-						const double tsw = M[c][j];
-						M[c][j] = M[piv][j];
-						M[piv][j] = tsw;
-					}
-				for (int r = c + 1; r < 6; ++r) {
-					const double f = M[r][c] / M[c][c];
-					for (int j = c; j < 7; ++j) M[r][j] -= f * M[c][j];
-				}
-			}
-			if (!sing) {
-				double dlt[6];
-				for (int r = 5; r >= 0; --r) {
-					double v = M[r][6];
-					for (int j = r + 1; j < 6; ++j) v -= M[r][j] * dlt[j];
-					dlt[r] = v / M[r][r];
-				}
-				bool fin = true;
-				for (int r = 0; r < 6; ++r) fin = fin && (fabs(dlt[r]) <= 1e6);
-				if (fin) {
-					double Rn[9];
-					for (int r = 0; r < 3; ++r) {
-						Rn[r * 3 + 0] = s_pose[4 * r + 0];
-						Rn[r * 3 + 1] = s_pose[4 * r + 1];
-						Rn[r * 3 + 2] = s_pose[4 * r + 2];
-					}
-					// left update rotates R X; the translation stays additive
-					rodrigues_left(dlt, Rn);
-					for (int r = 0; r < 3; ++r) {
-						s_pose[4 * r + 0] = Rn[r * 3 + 0];
-						s_pose[4 * r + 1] = Rn[r * 3 + 1];
-						s_pose[4 * r + 2] = Rn[r * 3 + 2];
-						s_pose[4 * r + 3] += dlt[3 + r];
-					}
-				}
-			}
+		if (!s_go) break; // block-uniform
+		const double cost_new = pnp_cost(s_new);
+		__syncthreads();
+		if (cost_new < cost) {
+			if (tid < 12) s_pose[tid] = s_new[tid];
+			lambda /= 10;
+			cost = cost_new;
+			recompute = true;
+		} else {
+			lambda *= 10;
+			recompute = false;
 		}
 		__syncthreads();
 	}
 	if (tid == 0) {
 		bool ok = true;
 		for (int i = 0; i < 12; ++i) {
-			ok = ok && (fabs(s_best[i]) <= DBL_MAX);
-			P_out[12 * (int64_t)pb + i] = s_best[i];
+			ok = ok && (fabs(s_pose[i]) <= DBL_MAX);
+			P_out[12 * (int64_t)pb + i] = s_pose[i];
 		}
 		ok_out[pb] = ok ? 1 : 0;
 	}
