@@ -396,9 +396,9 @@ __global__ void __launch_bounds__(kFitT)
 					for (int i = 6; i >= 0; --i) {
 						double v = y[i];
 						for (int k = i + 1; k < 7; ++k) v -= Lm[k][i] * sol[k];
-						sol[i] = -(v / Lm[i][i]);
+						sol[i] = v / Lm[i][i];
 					}
-					// sol = -(A^-1 g): the loop above solved A x = g and negated
+					for (int i = 0; i < 7; ++i) sol[i] = -sol[i]; // sol = -(J^T J + lambda I)^-1 J^T r
 					double s2 = 0.0;
 					for (int i = 0; i < 7; ++i) s2 += sol[i] * sol[i];
 					if (sqrt(s2) < 1e-8) go = 0; // step_tol
@@ -730,8 +730,9 @@ __global__ void __launch_bounds__(kFitT)
 					for (int i = 5; i >= 0; --i) {
 						double v = y[i];
 						for (int k = i + 1; k < 6; ++k) v -= Lm[k][i] * sol[k];
-						sol[i] = -(v / Lm[i][i]);
+						sol[i] = v / Lm[i][i];
 					}
+					for (int i = 0; i < 6; ++i) sol[i] = -sol[i]; // sol = -(J^T J + lambda I)^-1 J^T r
 					double s2 = 0.0;
 					for (int i = 0; i < 6; ++i) s2 += sol[i] * sol[i];
 					if (sqrt(s2) < 1e-8) go = 0; // step_tol
