@@ -303,9 +303,9 @@ __global__ void __launch_bounds__(kFitT)
 			dP[2][0 + c] = -F[3 + c], dP[2][3 + c] = F[0 + c], dP[2][6 + c] = 0.0;
 		}
 		for (int r = 0; r < 3; ++r) {
-			dP[3][r * 3 + 0] = 0.0, dP[3][r * 3 + 1] = F[r * 3 + 2], dP[3][r * 3 + 2] = -F[r * 3 + 1];
-			dP[4][r * 3 + 0] = -F[r * 3 + 2], dP[4][r * 3 + 1] = 0.0, dP[4][r * 3 + 2] = F[r * 3 + 0];
-			dP[5][r * 3 + 0] = F[r * 3 + 1], dP[5][r * 3 + 1] = -F[r * 3 + 0], dP[5][r * 3 + 2] = 0.0;
+			dP[3][r * 3 + 0] = 0.0, dP[3][r * 3 + 1] = -F[r * 3 + 2], dP[3][r * 3 + 2] = F[r * 3 + 1];
+			dP[4][r * 3 + 0] = F[r * 3 + 2], dP[4][r * 3 + 1] = 0.0, dP[4][r * 3 + 2] = -F[r * 3 + 0];
+			dP[5][r * 3 + 0] = -F[r * 3 + 1], dP[5][r * 3 + 1] = F[r * 3 + 0], dP[5][r * 3 + 2] = 0.0;
 			for (int c = 0; c < 3; ++c) dP[6][r * 3 + c] = U[r * 3 + 1] * V[c * 3 + 1];
 		}
 		for (int t = tid; t < n; t += kFitT) {
