@@ -12,6 +12,7 @@
 //                      2n x 8 system: same least-squares solution, agreement ~1e-9 relative after normalisation).
 //                      One block per problem; A^T A / A^T b are block reductions with the library's fixed topology.
 #include <cfloat>
+#include <cstdlib>
 
 #include "pxb_internal.h"
 #include "pxb_residuals.cuh"
@@ -161,6 +162,18 @@ template <int NV> __device__ __forceinline__ void fit_block_sum_vec(double (&v)[
 // (the reference passes weights_[i], i = 0..n-1, once the sample has been gathered into `normalized_points` with a null
 // sample pointer -- solver_homography_four_point.h:207-220 with sample_ == nullptr -- i.e. the first n entries of the
 // caller's per-point weight array; replicated as is).
+// FP64 tensor-core form of the normal equations (MMA = true): the 2n x 8 design matrix is walked in chunks of 4 rows (two
+// points); for a chunk Mc (4 x 8) one DMMA m8n8k4 adds Mc^T Mc to the 8 x 8 accumulator -- the A operand (8 x 4, row
+// major) and the B operand (4 x 8, column major) of that shape are THE SAME register per lane (lane l holds Mc[l % 4][l / 4])
+// -- and a second one adds Mc^T [b | 0] (column 0 = A^T b). Warps take chunks round robin; their accumulators are added
+// in warp order. Same sums as the scalar form up to the order of additions (1e-12 relative on the fitted H).
+__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b) {
+	asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+	             : "+d"(d0), "+d"(d1)
+	             : "d"(a), "d"(b));
+}
+
+template <bool MMA>
 __global__ void __launch_bounds__(kFitThreads)
     k_fit_h(const double *__restrict__ aos, const int32_t *__restrict__ off, const int32_t *__restrict__ idx,
             const double *__restrict__ weights, double *__restrict__ H_out, int32_t *__restrict__ ok_out) {
@@ -181,7 +194,7 @@ __global__ void __launch_bounds__(kFitThreads)
 		sx2 = add(sx2, q[2]);
 		sy2 = add(sy2, q[3]);
 	}
-	__shared__ double s_vec[(kFitThreads / 32) * 44];
+	__shared__ double s_vec[(kFitThreads / 32) * 72]; // 44 sums per warp (scalar form) or a warp's 8 x 8 + 8 accumulators (MMA form)
 	double sums4[4] = {sx1, sy1, sx2, sy2};
 	fit_block_sum_vec<4>(sums4, s_vec, s_acc);
 	const double mx1 = divd(sums4[0], (double)n), my1 = divd(sums4[1], (double)n);
@@ -198,6 +211,63 @@ __global__ void __launch_bounds__(kFitThreads)
 	const double avg1 = divd(sums2[0], (double)n), avg2 = divd(sums2[1], (double)n);
 	const double r1 = divd(1.4142135623730951, avg1), r2 = divd(1.4142135623730951, avg2); // M_SQRT2 / mean distance
 	// ---- A^T A (upper triangle, 36) and A^T b (8) of the 2n x 8 system (solver_homography_four_point.h:207-252)
+	if (MMA) {
+		const int lane = tid & 31, warp = tid >> 5;
+		const int krow = lane & 3, jcol = lane >> 2; // this lane's entry of a chunk: design row krow, coefficient jcol
+		double g0 = 0.0, g1 = 0.0, b0 = 0.0, b1 = 0.0;
+		const int chunks = (n + 1) / 2;
+		for (int c = warp; c < chunks; c += kFitThreads / 32) {
+			const int t = 2 * c + (krow >> 1);
+			double a = 0.0, bv = 0.0; // rows past the end are zero rows
+			if (t < n) {
+				const double *q = aos + 4 * (int64_t)idx[beg + t];
+				const double x1 = mul(sub(q[0], mx1), r1), y1 = mul(sub(q[1], my1), r1);
+				const double x2 = mul(sub(q[2], mx2), r2), y2 = mul(sub(q[3], my2), r2);
+				const double w = weights ? weights[t] : 1.0;
+				const bool second = krow & 1; // equation of y2 (else x2)
+				const double tgt = second ? y2 : x2;
+				switch (jcol) {
+				case 0: a = second ? 0.0 : mul(-w, x1); break;
+				case 1: a = second ? 0.0 : mul(-w, y1); break;
+				case 2: a = second ? 0.0 : -w; break;
+				case 3: a = second ? mul(-w, x1) : 0.0; break;
+				case 4: a = second ? mul(-w, y1) : 0.0; break;
+				case 5: a = second ? -w : 0.0; break;
+				case 6: a = mul(mul(w, tgt), x1); break;
+				default: a = mul(mul(w, tgt), y1); break;
+				}
+				bv = jcol == 0 ? -mul(w, tgt) : 0.0; // B' = [b | 0]: only column 0 carries the right-hand side
+			}
+			dmma_m8n8k4(g0, g1, a, a);
+			dmma_m8n8k4(b0, b1, a, bv);
+		}
+		// accumulators of the 8 warps, added in warp order: lane holds G[lane / 4][2 (lane % 4) + {0, 1}] and, for lane % 4 == 0,
+		// (A^T b)[lane / 4] in b0
+		double *s_g = s_vec; // [warps][72]: 64 entries of G + 8 of A^T b
+		s_g[warp * 72 + (lane >> 2) * 8 + 2 * (lane & 3)] = g0;
+		s_g[warp * 72 + (lane >> 2) * 8 + 2 * (lane & 3) + 1] = g1;
+		if ((lane & 3) == 0) s_g[warp * 72 + 64 + (lane >> 2)] = b0;
+		__syncthreads();
+		if (tid < 44) {
+			int r = 0, c = 0, a = 0; // entry tid of the packed layout: upper triangle row by row, then A^T b
+			bool found = false;
+			if (tid >= 36) {
+				r = tid - 36;
+			} else {
+				for (r = 0; r < 8 && !found; ++r)
+					for (c = r; c < 8; ++c, ++a)
+						if (a == tid) {
+							found = true;
+							break;
+						}
+				--r;
+			}
+			double v = 0.0;
+			for (int w = 0; w < kFitThreads / 32; ++w) v = add(v, tid >= 36 ? s_g[w * 72 + 64 + r] : s_g[w * 72 + r * 8 + c]);
+			s_acc[tid] = v;
+		}
+		__syncthreads();
+	} else {
 	double acc[44];
 #pragma unroll
 	for (int a = 0; a < 44; ++a) acc[a] = 0.0;
@@ -219,6 +289,7 @@ __global__ void __launch_bounds__(kFitThreads)
 		for (int r = 0; r < 8; ++r) acc[36 + r] = add(acc[36 + r], add(mul(ra[r], ba), mul(rb[r], bb)));
 	}
 	fit_block_sum_vec<44>(acc, s_vec, s_acc);
+	}
 	if (tid >= 32) return;
 	// ---- solve the 8x8 SPD system: Gaussian elimination with partial pivoting (robust to semi-definite input).
 	// Lane r < 8 holds row r of [A^T A | A^T b] in registers; pivot rows travel by shuffle. Every element sees exactly the
@@ -303,7 +374,13 @@ __global__ void __launch_bounds__(kFitThreads)
 int launch_fit_h(pxb_ctx *ctx, int P, const int32_t *off, const int32_t *idx, const double *weights, double *H_out,
                  int32_t *ok_out) {
 	if (P <= 0) return PXB_OK;
-	k_fit_h<<<(unsigned)P, kFitThreads, 0, ctx->stream>>>(ctx->pts.aos, off, idx, weights, H_out, ok_out);
+	// PXB_FIT_H_MMA=1 selects the FP64 tensor-core accumulation (measured in profiles/: it does not beat the scalar
+	// block reduction on these 8 x 8 problems, so the scalar form stays the default)
+	static const bool use_mma = getenv("PXB_FIT_H_MMA") && atoi(getenv("PXB_FIT_H_MMA")) != 0;
+	if (use_mma)
+		k_fit_h<true><<<(unsigned)P, kFitThreads, 0, ctx->stream>>>(ctx->pts.aos, off, idx, weights, H_out, ok_out);
+	else
+		k_fit_h<false><<<(unsigned)P, kFitThreads, 0, ctx->stream>>>(ctx->pts.aos, off, idx, weights, H_out, ok_out);
 	ctx->launches++;
 	PXB_CUDA(cudaGetLastError());
 	return PXB_OK;

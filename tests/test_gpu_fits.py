@@ -86,3 +86,24 @@ def test_find_6d_poses_with_spatial_coherence():
     M = models.shape[0] // 3
     assert M >= 2
     assert misclassification(gt, labels, M) < 0.15
+
+
+def test_fit_h_tensor_core_variant_agrees():
+    """k_fit_h<MMA>: the normal equations accumulated with FP64 DMMA m8n8k4 (PXB_FIT_H_MMA=1, read once per process) give
+    the same homographies as the scalar block reduction to 1e-9 (the sums differ only in the order of additions)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+    tool = Path(__file__).resolve().parent.parent / "tools" / "fit_h_bench.py"
+    runs = {}
+    for mma in ("0", "1"):
+        r = subprocess.run([sys.executable, str(tool)], capture_output=True, text=True, timeout=300,
+                           env=dict(os.environ, PXB_FIT_H_MMA=mma))
+        assert r.returncode == 0, r.stderr[-2000:]
+        runs[mma] = json.loads(r.stdout.strip().splitlines()[-1])
+    for shape in ("lo_50x28", "pearl_5x1200"):
+        a, b = np.array(runs["0"][shape]["H"]), np.array(runs["1"][shape]["H"])
+        assert runs["0"][shape]["ok"] == runs["1"][shape]["ok"] and a.shape == b.shape
+        assert np.abs(a - b).max() <= 1e-9 * np.abs(a).max()
