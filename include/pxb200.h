@@ -269,6 +269,60 @@ int pxb_find_lines(pxb_ctx *ctx, const double *points, const double *weights, in
                    double maximum_tanimoto_similarity, size_t max_iters, size_t minimum_point_number,
                    int maximum_model_number, size_t sampler_id, double scoring_exponent, int do_logging, uint64_t seed);
 
+/* ---- settings and statistics (px/include/progressive_x.h:32-104,210-217) ------------------------------------------------ */
+/* progx::MultiModelSettings with the gcransac::utils::Settings of the proposal engine it carries (gcr/settings.h:66-86 as
+ * overridden by progressive_x.h:64-71). pxb_settings_default fills in the constructor's values. The task-level entry
+ * points overwrite the fields their argument lists carry (threshold, confidence, spatial_coherence_weight,
+ * maximum_tanimoto_similarity, minimum_number_of_inliers, maximum_model_number, max_iteration_number, scoring_exponent) --
+ * exactly as findHomographies_ does (progressivex_python.cpp:262-276); the remaining fields are what
+ * ProgressiveX::getMutableSettings() (progressive_x.h:214-217) lets a C++ caller change: pxb_ctx_set_settings installs them
+ * for all later find* calls on the context (NULL restores the defaults). */
+typedef struct pxb_multi_model_settings {
+	size_t minimum_number_of_inliers;          /* 20 */
+	size_t max_proposal_number_without_change; /* 10 */
+	size_t cell_number_in_neighborhood_graph;  /* 8 (unused by the Python entry points: they build a radius graph) */
+	size_t maximum_model_number;               /* SIZE_MAX */
+	double maximum_tanimoto_similarity;        /* 0.5 */
+	double confidence;                         /* 0.95 */
+	double inlier_outlier_threshold;           /* 2.0 */
+	double spatial_coherence_weight;           /* 0.14 */
+	/* proposal_engine_settings */
+	size_t max_iteration_number;               /* 5000 */
+	size_t min_iteration_number;               /* 20 */
+	size_t min_iteration_number_before_lo;     /* 20 */
+	size_t max_local_optimization_number;      /* 50 */
+	size_t max_graph_cut_number;               /* 10 */
+	size_t max_least_squares_iterations;       /* 10 */
+	size_t max_unsuccessful_model_generations; /* 100 */
+	int scoring_exponent;                      /* 2 (scoring_function_with_compound_model.h:20) */
+} pxb_multi_model_settings;
+int pxb_settings_default(pxb_multi_model_settings *out);
+int pxb_ctx_set_settings(pxb_ctx *ctx, const pxb_multi_model_settings *settings_or_null);
+
+/* progx::IterationStatistics / MultiModelStatistics (progressive_x.h:78-104) of the LAST find* call on the context
+ * (ProgressiveX::getStatistics, progressive_x.h:210-213). The four per-round times are measured on the context's CUDA
+ * stream with events recorded where the reference reads its chrono clock (progressive_x.h:299-437); every round ends in a
+ * synchronisation, so they are wall times of the round's phases as the device saw them, in seconds. Rounds whose proposal
+ * was rejected add no entry, like the reference (:334-346 `continue` before addIterationStatistics). The labeling is
+ * what the find* call returned; the reference's inliers_of_each_model only ever receives the first instance's inliers
+ * (:375-381) -- its size is reported. */
+#define PXB_MAX_ROUNDS 10 /* the outer loop is capped at 10 proposals (progressive_x.h:272) */
+typedef struct pxb_iteration_statistics {
+	double time_of_proposal_engine, time_of_model_validation, time_of_optimization, time_of_compound_model_update;
+	size_t number_of_instances;
+	/* RANSACStatistics of the round's proposal (gcr/statistics.h): */
+	size_t ransac_iteration_number, local_optimization_number, graph_cut_number, proposal_inlier_number;
+} pxb_iteration_statistics;
+typedef struct pxb_multi_model_statistics {
+	double processing_time, total_time_of_proposal_engine, total_time_of_model_validation, total_time_of_optimization,
+	    total_time_of_compound_model_calculation;
+	size_t iteration_statistics_size;
+	pxb_iteration_statistics iteration_statistics[PXB_MAX_ROUNDS];
+	size_t model_number, inliers_of_each_model_size;
+	size_t kernel_launches; /* kernels this call launched (no counterpart in the reference) */
+} pxb_multi_model_statistics;
+int pxb_ctx_get_statistics(pxb_ctx *ctx, pxb_multi_model_statistics *out);
+
 /* Many independent problems on ONE GPU (BASELINE config C4; with pxb_allgather_instances below: over several GPUs).
  * Equivalent to calling pxb_find_homographies once per pair -- correspondences[p] is [n_points[p], 4], labeling_out[p]
  * holds n_points[p] int64, models_out[p] max_models_out * 9 doubles, n_models_out[p] receives the instance count -- with

@@ -255,6 +255,8 @@ void pxb_ctx_destroy(pxb_ctx *ctx) {
 	for (DevBuf *b : bufs) b->release();
 	if (ctx->pinned) cudaFreeHost(ctx->pinned);
 	if (ctx->stage) cudaFreeHost(ctx->stage);
+	if (ctx->timing_events_ready)
+		for (cudaEvent_t e : ctx->timing_events) cudaEventDestroy(e);
 	lo_skeleton_free(ctx->lo_skeleton);
 	exp_skeleton_free(ctx->exp_skeleton);
 	cudaStreamDestroy(ctx->stream);
@@ -262,6 +264,44 @@ void pxb_ctx_destroy(pxb_ctx *ctx) {
 }
 
 void *pxb_ctx_stream(pxb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int pxb_settings_default(pxb_multi_model_settings *out) { // MultiModelSettings() (progressive_x.h:60-75), gcr/settings.h:66-86
+	PXB_CHECK_ARG(out != nullptr, "null argument");
+	out->minimum_number_of_inliers = 20;
+	out->max_proposal_number_without_change = 10;
+	out->cell_number_in_neighborhood_graph = 8;
+	out->maximum_model_number = SIZE_MAX;
+	out->maximum_tanimoto_similarity = 0.5;
+	out->confidence = 0.95;
+	out->inlier_outlier_threshold = 2.0;
+	out->spatial_coherence_weight = 0.14;
+	out->max_iteration_number = 5000;
+	out->min_iteration_number = 20;
+	out->min_iteration_number_before_lo = 20;
+	out->max_local_optimization_number = 50;
+	out->max_graph_cut_number = 10;
+	out->max_least_squares_iterations = 10;
+	out->max_unsuccessful_model_generations = 100;
+	out->scoring_exponent = 2;
+	return PXB_OK;
+}
+
+int pxb_ctx_set_settings(pxb_ctx *ctx, const pxb_multi_model_settings *settings) {
+	PXB_CHECK_ARG(ctx != nullptr, "null context");
+	ctx->has_engine_settings = settings != nullptr;
+	if (settings) {
+		PXB_CHECK_ARG(settings->max_local_optimization_number >= 1 && settings->max_local_optimization_number <= 512,
+		              "max_local_optimization_number in [1, 512]");
+		ctx->engine_settings = *settings;
+	}
+	return PXB_OK;
+}
+
+int pxb_ctx_get_statistics(pxb_ctx *ctx, pxb_multi_model_statistics *out) {
+	PXB_CHECK_ARG(ctx && out, "null argument");
+	*out = ctx->last_statistics;
+	return PXB_OK;
+}
 
 int pxb_sync(pxb_ctx *ctx) {
 	PXB_CHECK_ARG(ctx != nullptr, "null context");

@@ -399,6 +399,16 @@ struct Instance {
 class Driver {
   public:
 	Driver(pxb_ctx *ctx, const Settings &s) : ctx_(ctx), s_(s) {
+		if (ctx->has_engine_settings && s.allow_shard) { // getMutableSettings(): the knobs no argument list carries
+			const pxb_multi_model_settings &e = ctx->engine_settings;
+			s_.max_proposals_without_change = e.max_proposal_number_without_change;
+			s_.min_iteration_number = e.min_iteration_number;
+			s_.min_iteration_number_before_lo = e.min_iteration_number_before_lo;
+			s_.max_local_optimization_number = e.max_local_optimization_number;
+			s_.max_graph_cut_number = e.max_graph_cut_number;
+			s_.max_least_squares_iterations = e.max_least_squares_iterations;
+			s_.max_unsuccessful_model_generations = e.max_unsuccessful_model_generations;
+		}
 		N_ = ctx->pts.N;
 		ms_ = model_size(s.type);
 		m_ = s.plane_parallax ? 2 : sample_size(s.type);
@@ -1493,9 +1503,33 @@ int Driver::run_local() {
 	// statistics.inliers_of_each_model.size(): one entry is appended whenever an instance is added while it is the only one
 	// (:375-381); the reference passes this COUNT as the compound inlier number whenever one instance remains (:447-451)
 	size_t inliers_of_each_model_size = 0;
-	for (size_t it = 0; it < 10; ++it) { // :272 hard cap
+	// ---- statistics (progressive_x.h:78-104): CUDA events on the stream where the reference reads its clock ----
+	pxb_multi_model_statistics &st = ctx_->last_statistics;
+	const bool timed = s_.allow_shard; // nested (DEGENSAC) runs do not touch the context's statistics
+	const int64_t launches0 = ctx_->launches;
+	if (timed) {
+		st = pxb_multi_model_statistics{};
+		if (!ctx_->timing_events_ready) {
+			for (cudaEvent_t &e : ctx_->timing_events) PXB_CUDA(cudaEventCreate(&e));
+			ctx_->timing_events_ready = true;
+		}
+		PXB_CUDA(cudaEventRecord(ctx_->timing_events[4 * PXB_MAX_ROUNDS], ctx_->stream));
+	}
+	struct RoundMarks {
+		int first_event;
+		pxb_iteration_statistics stat;
+	};
+	std::vector<RoundMarks> rounds;
+	int next_event = 0;
+	auto mark = [&]() -> int { // records the next event of the current round
+		if (timed) cudaEventRecord(ctx_->timing_events[next_event], ctx_->stream);
+		return next_event++;
+	};
+	for (size_t it = 0; it < PXB_MAX_ROUNDS; ++it) { // :272 hard cap
 		std::vector<double> model;
 		bool found = false;
+		next_event = 4 * (int)rounds.size();
+		const int e_start = mark();
 		PXB_TRY(propose(s_.seed * 1000003ull + it, model, found));
 		if (s_.do_logging)
 			fprintf(stdout, "[pxb] proposal %zu: %s, %zu inliers, %zu iterations, %zu LO runs, %zu graph cuts, DEGENSAC %zu/%zu\n",
@@ -1503,6 +1537,13 @@ int Driver::run_local() {
 			        degensac_updates_, degensac_degenerate_);
 		if (!found) continue; // :301-303
 		number_of_ransac_iterations += iteration_number_;
+		RoundMarks rm{};
+		rm.first_event = e_start;
+		rm.stat.ransac_iteration_number = iteration_number_;
+		rm.stat.local_optimization_number = lo_number_;
+		rm.stat.graph_cut_number = graph_cut_number_;
+		rm.stat.proposal_inlier_number = proposal_inliers_.size();
+		mark(); // end of the proposal engine / start of the validation
 		std::vector<double> pref;
 		bool valid = false;
 		PXB_TRY(putative_model_valid(model, pref, valid));
@@ -1511,6 +1552,7 @@ int Driver::run_local() {
 			if (unaccepted == s_.max_proposals_without_change) break;
 			continue;
 		}
+		mark(); // end of the validation / start of the optimisation
 		Instance inst;
 		inst.model = model;
 		inst.pref = pref;
@@ -1522,6 +1564,7 @@ int Driver::run_local() {
 		} else {
 			PXB_TRY(pearl()); // :390-396
 		}
+		mark(); // end of the optimisation / start of the compound update
 		// updateCompoundModel (:597-624): max over the *stored* preference vectors
 		if (!models_.empty()) {
 			std::vector<double> prefs((size_t)models_.size() * N_);
@@ -1529,6 +1572,23 @@ int Driver::run_local() {
 				std::copy(models_[k].pref.begin(), models_[k].pref.end(), prefs.begin() + k * N_);
 			PXB_TRY(pxb_compound_max(ctx_, prefs.data(), (int64_t)models_.size(), N_, compound_pref_.data()));
 			PXB_TRY(upload_compound());
+		}
+		if (timed) cudaEventRecord(ctx_->timing_events[4 * PXB_MAX_ROUNDS + 1], ctx_->stream); // end of this round's compound update
+		rm.stat.number_of_instances = models_.size();
+		if (timed && rounds.size() < PXB_MAX_ROUNDS) {
+			// the closing event is shared: read this round's times now (the stream is idle: upload_compound synchronised)
+			PXB_TRY(ctx_wait(ctx_));
+			float ms[4] = {0, 0, 0, 0};
+			cudaEvent_t *ev = ctx_->timing_events;
+			cudaEventElapsedTime(&ms[0], ev[rm.first_event], ev[rm.first_event + 1]);
+			cudaEventElapsedTime(&ms[1], ev[rm.first_event + 1], ev[rm.first_event + 2]);
+			cudaEventElapsedTime(&ms[2], ev[rm.first_event + 2], ev[rm.first_event + 3]);
+			cudaEventElapsedTime(&ms[3], ev[rm.first_event + 3], ev[4 * PXB_MAX_ROUNDS + 1]);
+			rm.stat.time_of_proposal_engine = ms[0] * 1e-3;
+			rm.stat.time_of_model_validation = ms[1] * 1e-3;
+			rm.stat.time_of_optimization = ms[2] * 1e-3;
+			rm.stat.time_of_compound_model_update = ms[3] * 1e-3;
+			rounds.push_back(rm);
 		}
 		size_t unseen;
 		if (models_.size() == 1) // evaluated AFTER the optimisation: also when PEARL pruned the set back to one instance
@@ -1540,6 +1600,24 @@ int Driver::run_local() {
 			        models_.size(), number_of_ransac_iterations, unseen);
 		if (unseen < s_.min_inliers) break;              // :468
 		if (models_.size() >= s_.max_models) break;      // :472
+	}
+	if (timed) { // addIterationStatistics (:91-100) + processing_time (:483-488)
+		for (const RoundMarks &rm : rounds) {
+			st.iteration_statistics[st.iteration_statistics_size++] = rm.stat;
+			st.total_time_of_proposal_engine += rm.stat.time_of_proposal_engine;
+			st.total_time_of_model_validation += rm.stat.time_of_model_validation;
+			st.total_time_of_optimization += rm.stat.time_of_optimization;
+			st.total_time_of_compound_model_calculation += rm.stat.time_of_compound_model_update;
+		}
+		cudaEvent_t *ev = ctx_->timing_events;
+		PXB_CUDA(cudaEventRecord(ev[4 * PXB_MAX_ROUNDS + 1], ctx_->stream));
+		PXB_CUDA(cudaEventSynchronize(ev[4 * PXB_MAX_ROUNDS + 1]));
+		float total_ms = 0;
+		cudaEventElapsedTime(&total_ms, ev[4 * PXB_MAX_ROUNDS], ev[4 * PXB_MAX_ROUNDS + 1]);
+		st.processing_time = total_ms * 1e-3;
+		st.model_number = models_.size();
+		st.inliers_of_each_model_size = inliers_of_each_model_size;
+		st.kernel_launches = (size_t)(ctx_->launches - launches0);
 	}
 	return PXB_OK;
 }

@@ -117,6 +117,12 @@ struct pxb_ctx {
 	void *shard_comm = nullptr;
 	int shard_world = 1, shard_rank = 0;
 	pxb::DevBuf shard_msg, shard_rec;
+	// ProgressiveX::getMutableSettings / getStatistics (pxb_ctx_set_settings, pxb_ctx_get_statistics)
+	pxb_multi_model_settings engine_settings;
+	bool has_engine_settings = false;
+	pxb_multi_model_statistics last_statistics = {};
+	cudaEvent_t timing_events[4 * PXB_MAX_ROUNDS + 2] = {};
+	bool timing_events_ready = false;
 	pxb::DevBuf labels, pack; // PEARL labels (kept on the device between iterations) and the packed per-call results
 };
 

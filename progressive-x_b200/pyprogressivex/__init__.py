@@ -19,7 +19,7 @@ from . import _native
 from ._native import Context, PxbError  # noqa: F401
 
 __all__ = ["findHomographies", "findTwoViewMotions", "findFundamentalMatrices", "find6DPoses", "findVanishingPoints",
-           "findLines", "findHomographiesBatch", "distributed", "Context"]
+           "findLines", "findHomographiesBatch", "distributed", "getStatistics", "getMutableSettings", "setSettings", "Context"]
 
 import threading as _threading
 
@@ -47,6 +47,22 @@ def _ctx(device: int) -> Context:
         if device not in _contexts:
             _contexts[device] = Context(device)
         return _contexts[device]
+
+
+def getStatistics(device: int = 0) -> dict:
+    """ProgressiveX::getStatistics (progressive_x.h:210-213) of the last find* call on `device`: processing_time, the four
+    total_time_of_* sums and one entry per accepted round (times from CUDA events on the context's stream, seconds)."""
+    return _ctx(device).statistics()
+
+
+def getMutableSettings(device: int = 0):
+    """A MultiModelSettings structure holding the reference's defaults (progressive_x.h:60-75); change fields and hand it
+    to setSettings. Fields that the find* argument lists carry are overwritten by those arguments, as in the reference."""
+    return _ctx(device).default_settings()
+
+
+def setSettings(settings, device: int = 0) -> None:
+    _ctx(device).set_settings(settings)
 
 
 _shards = {}

@@ -22,6 +22,41 @@ SAMPLE_SIZE = {MODEL_H: 4, MODEL_F: 7, MODEL_PNP: 3, MODEL_VP: 2, MODEL_LINE: 2}
 MAX_SOLUTIONS = {MODEL_H: 1, MODEL_F: 3, MODEL_PNP: 4, MODEL_VP: 1, MODEL_LINE: 1}
 
 
+class MultiModelSettings(C.Structure):
+    """pxb_multi_model_settings (include/pxb200.h) = progx::MultiModelSettings + the proposal engine's settings."""
+    _fields_ = [("minimum_number_of_inliers", C.c_size_t), ("max_proposal_number_without_change", C.c_size_t),
+                ("cell_number_in_neighborhood_graph", C.c_size_t), ("maximum_model_number", C.c_size_t),
+                ("maximum_tanimoto_similarity", C.c_double), ("confidence", C.c_double),
+                ("inlier_outlier_threshold", C.c_double), ("spatial_coherence_weight", C.c_double),
+                ("max_iteration_number", C.c_size_t), ("min_iteration_number", C.c_size_t),
+                ("min_iteration_number_before_lo", C.c_size_t), ("max_local_optimization_number", C.c_size_t),
+                ("max_graph_cut_number", C.c_size_t), ("max_least_squares_iterations", C.c_size_t),
+                ("max_unsuccessful_model_generations", C.c_size_t), ("scoring_exponent", C.c_int)]
+
+
+class IterationStatistics(C.Structure):
+    _fields_ = [("time_of_proposal_engine", C.c_double), ("time_of_model_validation", C.c_double),
+                ("time_of_optimization", C.c_double), ("time_of_compound_model_update", C.c_double),
+                ("number_of_instances", C.c_size_t), ("ransac_iteration_number", C.c_size_t),
+                ("local_optimization_number", C.c_size_t), ("graph_cut_number", C.c_size_t),
+                ("proposal_inlier_number", C.c_size_t)]
+
+
+class MultiModelStatistics(C.Structure):
+    """pxb_multi_model_statistics = progx::MultiModelStatistics of the last find* call on a context."""
+    _fields_ = [("processing_time", C.c_double), ("total_time_of_proposal_engine", C.c_double),
+                ("total_time_of_model_validation", C.c_double), ("total_time_of_optimization", C.c_double),
+                ("total_time_of_compound_model_calculation", C.c_double), ("iteration_statistics_size", C.c_size_t),
+                ("iteration_statistics", IterationStatistics * 10), ("model_number", C.c_size_t),
+                ("inliers_of_each_model_size", C.c_size_t), ("kernel_launches", C.c_size_t)]
+
+    def as_dict(self):
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k != "iteration_statistics"}
+        d["iteration_statistics"] = [{k: getattr(it, k) for k, _ in IterationStatistics._fields_}
+                                     for it in self.iteration_statistics[: self.iteration_statistics_size]]
+        return d
+
+
 class PxbError(RuntimeError):
     def __init__(self, status: int, message: str):
         super().__init__(f"libpxb200 error {status}: {message}")
@@ -99,6 +134,9 @@ def load_library() -> C.CDLL:
                                                 sz, sz, C.c_int, sz, f64, u64, C.c_int, C.c_int, C.c_int]
     lib.pxb_batch_release.argtypes = []
     lib.pxb_batch_release.restype = None
+    lib.pxb_settings_default.argtypes = [C.POINTER(MultiModelSettings)]
+    lib.pxb_ctx_set_settings.argtypes = [vp, C.POINTER(MultiModelSettings)]
+    lib.pxb_ctx_get_statistics.argtypes = [vp, C.POINTER(MultiModelStatistics)]
     lib.pxb_nccl_version.argtypes = [C.POINTER(C.c_int)]
     lib.pxb_nccl_unique_id.argtypes = [vp]
     lib.pxb_nccl_comm_init.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(vp)]
@@ -219,6 +257,22 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self.lib.pxb_launch_count(self.handle))
+
+    # -- ProgressiveX::getMutableSettings / getStatistics (progressive_x.h:210-217) -----------------------
+    def default_settings(self) -> MultiModelSettings:
+        s = MultiModelSettings()
+        _check(self.lib.pxb_settings_default(C.byref(s)))
+        return s
+
+    def set_settings(self, settings) -> None:
+        """Installs the engine settings no find* argument carries (None restores the defaults)."""
+        _check(self.lib.pxb_ctx_set_settings(self.handle, None if settings is None else C.byref(settings)))
+
+    def statistics(self) -> dict:
+        """Statistics of the last find* call on this context (per-round times from CUDA events, in seconds)."""
+        st = MultiModelStatistics()
+        _check(self.lib.pxb_ctx_get_statistics(self.handle, C.byref(st)))
+        return st.as_dict()
 
     def alloc(self, nbytes: int) -> DeviceBuffer:
         return DeviceBuffer(self, nbytes)

@@ -216,3 +216,37 @@ def test_plane_dominated_two_view_motion_uses_degensac(monkeypatch):
                                                   maximum_model_number=1, sampler_id=0, scoring_exponent=1.0, seed=seed)
         assert np.array_equal(again[0], Fs) and np.array_equal(again[1], labels)
     assert good >= 3, good
+
+
+def test_statistics_and_mutable_settings():
+    """ProgressiveX::getStatistics / getMutableSettings (progressive_x.h:210-217) through the ABI: one entry per accepted
+    round with the four phase times (CUDA events), totals that add up, and engine settings that take effect."""
+    corrs, gt, Hs = syn.multi_homography_scene(3000, n_planes=3, outlier_ratio=0.3, seed=21)
+    kw = dict(threshold=2.0, conf=0.9, max_iters=600, minimum_point_number=100, sampler_id=0, seed=5)
+    models, labels = pyprogressivex.findHomographies(corrs, 1024, 768, 1024, 768, **kw)
+    st = pyprogressivex.getStatistics()
+    its = st["iteration_statistics"]
+    assert st["model_number"] == models.shape[0] // 3 >= 3 and len(its) >= 3
+    assert its[-1]["number_of_instances"] == st["model_number"] and its[0]["number_of_instances"] == 1
+    for it in its:
+        assert it["time_of_proposal_engine"] > 0 and it["time_of_model_validation"] > 0 and it["time_of_compound_model_update"] > 0
+        assert 20 <= it["ransac_iteration_number"] <= 600 and it["local_optimization_number"] >= 1
+        assert it["proposal_inlier_number"] >= 100
+    assert abs(st["total_time_of_proposal_engine"] - sum(i["time_of_proposal_engine"] for i in its)) < 1e-12
+    phases = (st["total_time_of_proposal_engine"] + st["total_time_of_model_validation"] + st["total_time_of_optimization"]
+              + st["total_time_of_compound_model_calculation"])
+    assert 0 < phases <= st["processing_time"] * 1.001 and st["kernel_launches"] > 50
+    # one graph cut per local optimisation instead of up to ten: fewer cuts, still a valid result
+    s = pyprogressivex.getMutableSettings()
+    assert (s.max_graph_cut_number, s.max_local_optimization_number, s.min_iteration_number) == (10, 50, 20)
+    s.max_graph_cut_number = 2
+    pyprogressivex.setSettings(s)
+    try:
+        m2, l2 = pyprogressivex.findHomographies(corrs, 1024, 768, 1024, 768, **kw)
+        st2 = pyprogressivex.getStatistics()
+        assert all(i["graph_cut_number"] <= 2 * i["local_optimization_number"] for i in st2["iteration_statistics"])
+        assert max(i["graph_cut_number"] for i in its) > 2
+    finally:
+        pyprogressivex.setSettings(None)
+    again = pyprogressivex.findHomographies(corrs, 1024, 768, 1024, 768, **kw)
+    assert np.array_equal(again[0], models) and np.array_equal(again[1], labels)
