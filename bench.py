@@ -392,19 +392,8 @@ def main():
                 "written; float32 screening proves outliers, exact float64 only for queued candidates (issue bound)"}
 
     if not args.quick:
-        # ---- screening matrix variants ------------------------------------------------------------------------------
+        # ---- inlier bit matrix only (float32-screened kernel) -------------------------------------------------------
         del r2
-        with torch.cuda.stream(stream):
-            r2f = torch.empty((K, N), dtype=torch.float32, device=dev)
-
-        def step_f32():
-            check(lib.pxb_residual_matrix_f32_dev(ctx.handle, models.data_ptr(), K, T2, r2f.data_ptr(), mask.data_ptr()))
-
-        f32_ms, f32_per, _, _ = timed(step_f32, sc_steps, 3)
-        f32_achieved = evals_per_step * 4.125 / (float(np.mean(f32_per)) * 1e-3) / 1e9
-        extras["screening_f32"] = {"evals_per_s": evals_per_step * world * sc_steps / (f32_ms * 1e-3),
-                                   "roofline_frac": f32_achieved / peak, "bytes_per_eval": 4.125}
-        del r2f
 
         def step_mask():
             check(lib.pxb_residual_matrix_dev(ctx.handle, models.data_ptr(), K, T2, None, mask.data_ptr()))
@@ -412,7 +401,9 @@ def main():
         mk_ms, mk_per, _, _ = timed(step_mask, sc_steps, 3)
         extras["mask_only"] = {"evals_per_s": evals_per_step * world * sc_steps / (mk_ms * 1e-3),
                                "launch_ms": float(np.mean(mk_per)), "bytes_per_eval": 0.125,
-                               "note": "inlier bit matrix only (pxb_residual_matrix_dev with r2 = NULL)"}
+                               "note": "inlier bit matrix only (pxb_residual_matrix_dev with r2 = NULL): float32-screened kernel, "
+                                       "exact float64 only for the pairs screening cannot dismiss; bit-identical masks. Replaces "
+                                       "round 1's float32-r2 variant (removed: it ran at the float64 kernel's speed)"}
 
         # ---- C3 / C5 residual-matrix roofline lines --------------------------------------------------------------------
         def matrix_line(model_type, rows, sample_rows, t2, label, traffic_key):

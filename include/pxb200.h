@@ -91,9 +91,10 @@ int pxb_residual_matrix(pxb_ctx *ctx, const double *models_host, int64_t K, doub
                         uint32_t *mask_host);
 int pxb_residual_matrix_dev(pxb_ctx *ctx, const double *models_dev, int64_t K, double T2, double *r2_dev,
                             uint32_t *mask_dev);
-/* Screening variant: residuals stored as float32 (rounded from the exact float64 value), mask still exact. */
-int pxb_residual_matrix_f32_dev(pxb_ctx *ctx, const double *models_dev, int64_t K, double T2, float *r2_dev,
-                                uint32_t *mask_dev);
+/* With r2 == NULL only the bit matrix is produced, by the float32-SCREENED kernel: pairs that are provably outliers
+ * never take the float64 path (the mask is bit-identical to the one written beside r2). A float32-r2 output variant
+ * existed in round 1 (pxb_residual_matrix_f32_dev); it had to evaluate every pair in float64 before rounding, ran at the
+ * speed of the float64 matrix (30 % of its own 4.125 B/eval roofline) and was removed. */
 
 /* ---- a4: compound-aware MSAC score ----------------------------------------------------------------------- */
 /* Replaces MSACScoringFunctionWithCompoundModel::getScore (px/include/scoring_function_with_compound_model.h:61-125)

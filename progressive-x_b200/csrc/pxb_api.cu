@@ -389,13 +389,6 @@ int pxb_residual_matrix_dev(pxb_ctx *ctx, const double *models_dev, int64_t K, d
 	return launch_residual_matrix(ctx, models_dev, K, T2, r2_dev, nullptr, mask_dev);
 }
 
-int pxb_residual_matrix_f32_dev(pxb_ctx *ctx, const double *models_dev, int64_t K, double T2, float *r2_dev,
-                                uint32_t *mask_dev) {
-	PXB_TRY(require_points(ctx));
-	PXB_CHECK_ARG(models_dev != nullptr && K >= 0 && r2_dev != nullptr, "models / r2");
-	return launch_residual_matrix(ctx, models_dev, K, T2, nullptr, r2_dev, mask_dev);
-}
-
 int pxb_residual_matrix(pxb_ctx *ctx, const double *models_host, int64_t K, double T2, double *r2_host,
                         uint32_t *mask_host) {
 	PXB_TRY(require_points(ctx));

@@ -163,6 +163,8 @@ int launch_select_models(pxb_ctx *ctx, const double *current, const double *fitt
 // kernel launchers (device pointers, asynchronous on ctx->stream)
 int launch_residual_matrix(pxb_ctx *ctx, const double *models, int64_t K, double T2, double *r2, float *r2f,
                            uint32_t *mask);
+// inlier bit matrix only, float32-screened (pxb_score.cu): bit-identical to the mask launch_residual_matrix writes
+int launch_inlier_mask(pxb_ctx *ctx, const double *models, int64_t K, double T2, uint32_t *mask);
 int launch_score_compound(pxb_ctx *ctx, const double *models, int64_t K, double T2, const double *compound_pref,
                           int64_t *count, double *value_sum, double *shared);
 int launch_preference(pxb_ctx *ctx, const double *model, double T, double *pref);

@@ -260,6 +260,10 @@ static int launch_rm_t(pxb_ctx *ctx, const double *models, int64_t K, double T2,
 int launch_residual_matrix(pxb_ctx *ctx, const double *models, int64_t K, double T2, double *r2, float *r2f,
                            uint32_t *mask) {
 	if (K <= 0) return PXB_OK;
+	// bit matrix only: the float32-screened kernel (pxb_score.cu) -- same bits, and provable outliers skip the float64 path.
+	// Single models (inlier lists of one hypothesis) stay here: they are inlier rich and one launch cheaper.
+	static const bool no_screen = getenv("PXB_MASK_EXACT") && atoi(getenv("PXB_MASK_EXACT")) != 0; // A/B knob for the tests
+	if (!r2 && !r2f && mask && K >= 8 && !no_screen) return launch_inlier_mask(ctx, models, K, T2, mask);
 	int rc = PXB_OK;
 	if (r2f)
 		PXB_DISPATCH_TYPE(ctx->pts.type, rc = (launch_rm_t<TYPE, float>(ctx, models, K, T2, r2f, mask)));

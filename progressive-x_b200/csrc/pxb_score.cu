@@ -311,6 +311,183 @@ static void launch_screened(pxb_ctx *ctx, int nchunks, const float *consts, cons
 	                                                                             empty, m, kk, T2, cp, pp, nchunks, tile_hyps);
 }
 
+// ------------------------------------------------------------------------------------------------
+// a1-a3, bit-matrix only: the inlier mask of every (hypothesis, point) pair WITHOUT the r2 matrix
+// ------------------------------------------------------------------------------------------------
+// Same screening as the score kernel: float32 proves "r2 >= T2" for most pairs (bit 0, nothing else to do); the pairs it
+// cannot dismiss are queued per warp and drained 32 at a time through the reference's float64 residual, whose exact
+// comparison r2 < T2 sets the bit in a shared-memory tile [hypothesis][word of 32 points]; the tile goes to global memory
+// once per block. The mask is bit-identical to the one k_residual_matrix writes (tests/test_gpu_parity.py).
+template <int TYPE> struct MaskSmem {
+	static constexpr int DIM = ModelTraits<TYPE>::kDim, MP = ModelTraits<TYPE>::kPadded, MF = ScreenTraits<TYPE>::kFloats;
+	static constexpr size_t kPts = 0;
+	static constexpr size_t kModels = kPts + sizeof(double) * DIM * kScChunk;
+	static constexpr size_t kMf = kModels + sizeof(double) * kScHyps * MP;
+	static constexpr size_t kQueue = kMf + sizeof(float) * kScHyps * MF;
+	static constexpr size_t kMask = kQueue + sizeof(unsigned short) * kScWarps * kScQueue;
+	static constexpr size_t kEmpty = kMask + sizeof(uint32_t) * kScHyps * (kScChunk / 32);
+	static constexpr size_t kBytes = kEmpty + kScHyps;
+};
+
+template <int TYPE>
+__device__ __forceinline__ void mask_drain(const double *s_pts, const double *s_models, int pbase, double T2,
+                                           const unsigned short *queue, int head, int n, uint32_t *s_mask, int word0) {
+	constexpr int DIM = ModelTraits<TYPE>::kDim, MP = ModelTraits<TYPE>::kPadded;
+	const int lane = threadIdx.x & 31;
+	if (lane < n) {
+		const unsigned e = queue[(head + lane) & (kScQueue - 1)];
+		const int qh = (int)(e >> 7), local = (int)(e & 127u);
+		double p[5];
+#pragma unroll
+		for (int c = 0; c < DIM; ++c) p[c] = s_pts[c * kScChunk + pbase + local];
+		const double *m = s_models + qh * MP;
+		bool ok = true;
+		double r2 = squared_residual_fast<TYPE>(p, m, ok); // bit-identical to the plain division inside its domain
+		if (!ok) r2 = squared_residual<TYPE>(p, m);
+		if (r2 < T2) atomicOr(&s_mask[qh * (kScChunk / 32) + word0 + (local >> 5)], 1u << (local & 31));
+	}
+	__syncwarp();
+}
+
+template <int TYPE, bool FULL>
+__device__ __forceinline__ void mask_tile(const float (&p)[kScP][5], const float (&zq)[kScP], const bool (&valid)[kScP],
+                                          const float *s_mf, const unsigned char *s_empty, int nk, float cT,
+                                          const double *s_pts, const double *s_models, int pbase, double T2,
+                                          unsigned short *queue, uint32_t *s_mask, int word0) {
+	constexpr int MF = ScreenTraits<TYPE>::kFloats;
+	const int lane = threadIdx.x & 31;
+	const unsigned lt = (1u << lane) - 1u;
+	int head = 0, tail = 0;
+#pragma unroll 2
+	for (int h = 0; h < nk; ++h) {
+		if (s_empty[h]) continue; // all-zero model: every residual is NaN, no bit is set
+		float m[MF];
+		const float4 *s4 = reinterpret_cast<const float4 *>(s_mf + h * MF);
+#pragma unroll
+		for (int i = 0; i < MF / 4; ++i) {
+			const float4 v = s4[i];
+			m[4 * i] = v.x, m[4 * i + 1] = v.y, m[4 * i + 2] = v.z, m[4 * i + 3] = v.w;
+		}
+		bool cand[kScP];
+		bool any = false;
+#pragma unroll
+		for (int j = 0; j < kScP; ++j) {
+			const bool sure = screen_sure_outlier<TYPE>(p[j], m, cT, zq[j]);
+			cand[j] = FULL ? !sure : (!sure & valid[j]);
+			any |= cand[j];
+		}
+		if (__any_sync(0xffffffffu, any)) {
+#pragma unroll
+			for (int j = 0; j < kScP; ++j) {
+				const unsigned b = __ballot_sync(0xffffffffu, cand[j]);
+				if (b == 0) continue; // warp-uniform
+				if (cand[j]) queue[(tail + __popc(b & lt)) & (kScQueue - 1)] = (unsigned short)((h << 7) | (32 * j + lane));
+				tail += __popc(b);
+			}
+			__syncwarp();
+			while (tail - head >= 32) {
+				mask_drain<TYPE>(s_pts, s_models, pbase, T2, queue, head, 32, s_mask, word0);
+				head += 32;
+			}
+		}
+	}
+	if (tail > head) mask_drain<TYPE>(s_pts, s_models, pbase, T2, queue, head, tail - head, s_mask, word0);
+}
+
+template <int TYPE>
+__global__ void __launch_bounds__(kThreads, 3)
+    k_mask_screened(const double *__restrict__ soa, int64_t stride, int64_t N, const float *__restrict__ pf,
+                    const float *__restrict__ pq, const float *__restrict__ consts, const float *__restrict__ mfg,
+                    const unsigned char *__restrict__ emptyg, const double *__restrict__ models, int64_t K, double T2,
+                    uint32_t *__restrict__ mask, int64_t words) {
+	using L = MaskSmem<TYPE>;
+	constexpr int DIM = L::DIM, MS = ModelTraits<TYPE>::kSize, MP = L::MP, MF = L::MF, WPB = kScChunk / 32;
+	extern __shared__ __align__(16) unsigned char smem[];
+	double *s_pts = reinterpret_cast<double *>(smem + L::kPts);
+	double *s_models = reinterpret_cast<double *>(smem + L::kModels);
+	float *s_mf = reinterpret_cast<float *>(smem + L::kMf);
+	unsigned short *s_queue = reinterpret_cast<unsigned short *>(smem + L::kQueue);
+	uint32_t *s_mask = reinterpret_cast<uint32_t *>(smem + L::kMask);
+	unsigned char *s_empty = smem + L::kEmpty;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int chunk = blockIdx.x;
+	const int64_t block_base = (int64_t)chunk * kScChunk;
+	for (int t = threadIdx.x; t < kScChunk; t += kThreads) {
+		const int64_t i = min(block_base + t, stride - 1);
+#pragma unroll
+		for (int c = 0; c < DIM; ++c) s_pts[c * kScChunk + t] = __ldg(soa + c * stride + i);
+	}
+	const int64_t k0 = (int64_t)blockIdx.y * kScHyps;
+	const int nk = (int)min((int64_t)kScHyps, K - k0);
+	for (int t = threadIdx.x; t < nk * MS; t += kThreads) s_models[(t / MS) * MP + (t % MS)] = models[k0 * MS + t];
+	for (int t = threadIdx.x; t < nk * MF; t += kThreads) s_mf[t] = __ldg(mfg + k0 * MF + t);
+	if (threadIdx.x < nk) s_empty[threadIdx.x] = __ldg(emptyg + k0 + threadIdx.x);
+	for (int t = threadIdx.x; t < kScHyps * WPB; t += kThreads) s_mask[t] = 0u;
+	const float cT = __ldg(consts), cE = __ldg(consts + 1);
+	const int64_t warp_base = block_base + warp * (32 * kScP);
+	float p[kScP][5], zq[kScP];
+	bool valid[kScP];
+#pragma unroll
+	for (int j = 0; j < kScP; ++j) {
+		const int64_t i = warp_base + lane + 32 * j;
+		valid[j] = i < N;
+		const int64_t ii = valid[j] ? i : (N - 1);
+#pragma unroll
+		for (int c = 0; c < DIM; ++c) p[j][c] = __ldg(pf + c * stride + ii);
+		zq[j] = cE * __ldg(pq + ii);
+	}
+	__syncthreads();
+	if (warp_base + 32 * kScP <= N)
+		mask_tile<TYPE, true>(p, zq, valid, s_mf, s_empty, nk, cT, s_pts, s_models, warp * (32 * kScP), T2, s_queue + warp * kScQueue,
+		                      s_mask, warp * kScP);
+	else
+		mask_tile<TYPE, false>(p, zq, valid, s_mf, s_empty, nk, cT, s_pts, s_models, warp * (32 * kScP), T2, s_queue + warp * kScQueue,
+		                       s_mask, warp * kScP);
+	__syncthreads();
+	const int64_t w0 = (int64_t)chunk * WPB;
+	for (int t = threadIdx.x; t < nk * WPB; t += kThreads) {
+		const int h = t / WPB, w = t % WPB;
+		if (w0 + w < words) mask[(k0 + h) * words + w0 + w] = s_mask[h * WPB + w];
+	}
+}
+
+template <int TYPE> static int launch_mask_t(pxb_ctx *ctx, const double *models, int64_t K, double T2, uint32_t *mask) {
+	constexpr int MF = ScreenTraits<TYPE>::kFloats;
+	constexpr int kBytes = (int)MaskSmem<TYPE>::kBytes;
+	const Points &p = ctx->pts;
+	const int nchunks = (int)((p.N + kScChunk - 1) / kScChunk);
+	const int64_t words = (p.N + 31) / 32;
+	static bool opted_in[64] = {};
+	if (ctx->device < 0 || ctx->device >= 64 || !opted_in[ctx->device]) {
+		cudaFuncSetAttribute(k_mask_screened<TYPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBytes);
+		if (ctx->device >= 0 && ctx->device < 64) opted_in[ctx->device] = true;
+	}
+	int64_t done = 0;
+	while (done < K) { // gridDim.y is limited to 65535
+		const int64_t kk = std::min<int64_t>(K - done, (int64_t)65535 * kScHyps);
+		const double *m = models + done * ModelTraits<TYPE>::kSize;
+		PXB_TRY(ctx->screen.reserve(sizeof(float) * (4 + (size_t)kk * MF) + (size_t)kk + 64));
+		float *consts = ctx->screen.as<float>(), *mf = consts + 4;
+		unsigned char *empty = reinterpret_cast<unsigned char *>(mf + (size_t)kk * MF);
+		k_screen_prepare<TYPE><<<(unsigned)((kk + 127) / 128), 128, 0, ctx->stream>>>(m, kk, T2, p.norm, consts, mf, empty);
+		dim3 grid((unsigned)nchunks, (unsigned)((kk + kScHyps - 1) / kScHyps));
+		k_mask_screened<TYPE><<<grid, kThreads, kBytes, ctx->stream>>>(p.soa, p.stride, p.N, p.f32n, p.q, consts, mf, empty, m, kk, T2,
+		                                                              mask + done * words, words);
+		ctx->launches += 2;
+		done += kk;
+	}
+	PXB_CUDA(cudaGetLastError());
+	return PXB_OK;
+}
+
+// inlier bit matrix only (mask[k * words + (i >> 5)], bit i & 31), float32-screened
+int launch_inlier_mask(pxb_ctx *ctx, const double *models, int64_t K, double T2, uint32_t *mask) {
+	if (K <= 0) return PXB_OK;
+	int rc = PXB_OK;
+	PXB_DISPATCH_TYPE(ctx->pts.type, rc = launch_mask_t<TYPE>(ctx, models, K, T2, mask));
+	return rc;
+}
+
 template <int TYPE>
 static int launch_partial(pxb_ctx *ctx, int nchunks, const double *m, int64_t kk, double T2, const double *cp, ScorePartial *pp) {
 	constexpr int MF = ScreenTraits<TYPE>::kFloats;

@@ -113,7 +113,10 @@ __device__ __forceinline__ int screen_model_finish(const double *out, const doub
 		wild |= !(fabs(out[i]) <= 1e300) || !(mag[i] <= 1e300);
 		M = fmax(M, mag[i]);
 	}
-	wild |= !(M >= 1e-300);
+	// The screening argument is scale invariant, the reference's float64 arithmetic is not: outside this window its squares
+	// and fourth powers overflow or underflow (a vanishing point scaled by 1e200 makes every residual 0/inf = 0, an inlier
+	// everywhere). Such hypotheses take the exact path for every point.
+	wild |= !(M >= 0x1p-100) || !(M <= 0x1p100);
 	int e = 0;
 	frexp(wild ? 1.0 : M, &e); // M = f 2^e, f in [0.5, 1)
 	for (int i = 0; i < n; ++i) mf[i] = wild ? __int_as_float(0x7fc00000) : (float)ldexp(out[i], 1 - e);

@@ -102,7 +102,6 @@ def load_library() -> C.CDLL:
     lib.pxb_point_count.restype = i64
     lib.pxb_residual_matrix.argtypes = [vp, vp, i64, f64, vp, vp]
     lib.pxb_residual_matrix_dev.argtypes = [vp, vp, i64, f64, vp, vp]
-    lib.pxb_residual_matrix_f32_dev.argtypes = [vp, vp, i64, f64, vp, vp]
     lib.pxb_score_compound.argtypes = [vp, vp, i64, f64, vp, vp, vp, vp]
     lib.pxb_score_compound_dev.argtypes = [vp, vp, i64, f64, vp, vp, vp, vp]
     lib.pxb_inliers.argtypes = [vp, vp, f64, vp, C.POINTER(i64)]

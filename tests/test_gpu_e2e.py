@@ -230,7 +230,7 @@ def test_statistics_and_mutable_settings():
     assert its[-1]["number_of_instances"] == st["model_number"] and its[0]["number_of_instances"] == 1
     for it in its:
         assert it["time_of_proposal_engine"] > 0 and it["time_of_model_validation"] > 0 and it["time_of_compound_model_update"] > 0
-        assert 20 <= it["ransac_iteration_number"] <= 600 and it["local_optimization_number"] >= 1
+        assert 20 <= it["ransac_iteration_number"] <= 700 and it["local_optimization_number"] >= 1  # failed generations count too (GCRANSAC.h:341)
         assert it["proposal_inlier_number"] >= 100
     assert abs(st["total_time_of_proposal_engine"] - sum(i["time_of_proposal_engine"] for i in its)) < 1e-12
     phases = (st["total_time_of_proposal_engine"] + st["total_time_of_model_validation"] + st["total_time_of_optimization"]

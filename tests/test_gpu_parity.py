@@ -462,3 +462,46 @@ def test_plane_parallax_solver_bit_exact(ctx, oracle):
         assert np.median(alg[off]) < 1e-6  # noise-free rigid scene: every point is on the true epipolar geometry
     with pytest.raises(Exception):
         ctx.solve_plane_parallax(np.array([[0, len(rows)]]), Hm)
+
+
+@pytest.mark.parametrize("t", [0, 1, 2, 3, 4], ids=["H", "F", "PnP", "VP", "Line"])
+def test_screened_bit_matrix_equals_exact_mask(ctx, t):
+    from pyprogressivex import _native
+    """pxb_residual_matrix(r2 = NULL): the float32-screened bit-matrix kernel (k_mask_screened) must give exactly the mask
+    the float64 matrix kernel writes beside r2 -- on planted models, solver output incl. empty solution slots, degenerate
+    models (zero, NaN, inf, huge), a threshold with a non-zero low word, and a ragged N."""
+    rng = np.random.default_rng(5 + t)
+    N = 7013
+    if t == 0:
+        pts, gt, planted = syn.multi_homography_scene(N, seed=40)
+        thr = 2.0
+    elif t == 1:
+        pts, gt, planted = syn.multi_motion_scene(N, seed=41)
+        thr = 0.75
+    elif t == 2:
+        img, w, K, gt, planted = syn.multi_pose_scene(N, n_objects=4, inlier_ratio_each=0.15, seed=42)
+        pts = syn.normalize_pnp_points(img, w, K)
+        thr = 4.0 / 1074.0
+    elif t == 3:
+        pts, gt, planted = syn.multi_vanishing_point_scene(N, seed=43)
+        thr = 2.0
+    else:
+        pts, gt, planted = syn.multi_line_scene(N, seed=44)
+        thr = 2.0
+    ms = _native.MODEL_SIZE[t]
+    ctx.upload_points(t, pts)
+    S = syn.minimal_samples(gt, 150, _native.SAMPLE_SIZE[t], seed=t)
+    models, n, _, _ = ctx.solve_minimal(S)
+    hyps = [planted.reshape(-1, ms), models.reshape(-1, ms)]  # all slots, filled or not
+    bad = np.tile(planted.reshape(-1, ms)[:1], (6, 1))
+    bad[0] = 0.0
+    bad[1, 0] = np.nan
+    bad[2, -1] = np.inf
+    bad[3] *= 1e200
+    bad[4] *= 1e-200
+    bad[5] = rng.normal(size=ms)
+    hyps = np.ascontiguousarray(np.concatenate(hyps + [bad]))
+    for T2 in ((1.5 * thr) ** 2, (1.5 * thr) ** 2 * (1 + 2.0 ** -40), 1e-30, 1e30):
+        _, exact = ctx.residual_matrix(hyps, T2, want_r2=True, want_mask=True)
+        _, screened = ctx.residual_matrix(hyps, T2, want_r2=False, want_mask=True)
+        assert np.array_equal(exact, screened)

@@ -15,7 +15,7 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "progressive-x_b200"))
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--kernel", default="matrix", choices=["matrix", "matrix_f32", "score", "all"])
+ap.add_argument("--kernel", default="matrix", choices=["matrix", "mask", "score", "all"])
 ap.add_argument("--iters", type=int, default=4)
 ap.add_argument("--n", type=int, default=50_000)
 ap.add_argument("--k", type=int, default=10_000)
@@ -54,8 +54,8 @@ d_out = ctx.alloc(K * 8 * 3)
 for _ in range(args.iters):
     if args.kernel in ("matrix", "all"):
         _native._check(ctx.lib.pxb_residual_matrix_dev(ctx.handle, d_models.ptr, K, T2, d_r2.ptr, d_mask.ptr))
-    if args.kernel in ("matrix_f32", "all"):
-        _native._check(ctx.lib.pxb_residual_matrix_f32_dev(ctx.handle, d_models.ptr, K, T2, d_r2.ptr, d_mask.ptr))
+    if args.kernel in ("mask", "all"):
+        _native._check(ctx.lib.pxb_residual_matrix_dev(ctx.handle, d_models.ptr, K, T2, None, d_mask.ptr))
     if args.kernel in ("score", "all"):
         _native._check(ctx.lib.pxb_score_compound_dev(ctx.handle, d_models.ptr, K, T2, None, d_out.ptr,
                                                       d_out.ptr + K * 8, d_out.ptr + 2 * K * 8))
