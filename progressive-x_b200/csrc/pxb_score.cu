@@ -133,11 +133,13 @@ __device__ __forceinline__ ScoreAcc score_tile(const float (&p)[kScP][5], const 
 	const unsigned lt = (1u << lane) - 1u;
 	int head = 0, tail = 0;
 	ScoreAcc acc = {0.0, 0.0, 0};
+	// an unfilled solution slot of a minimal solver (all-zero model): every residual is NaN, nothing is an inlier -- count,
+	// score and shared support are exactly zero, as the reference's loop would find. One flag bit per hypothesis of the
+	// tile, held in a register (warp-uniform skip).
+	const unsigned empty_bits = __ballot_sync(0xffffffffu, lane < nk && s_empty[lane] != 0);
 #pragma unroll 2
 	for (int h = 0; h < nk; ++h) {
-		// an unfilled solution slot of a minimal solver (all-zero model): every residual is NaN, nothing is an inlier --
-		// count, score and shared support are exactly zero, as the reference's loop would find (block-uniform skip)
-		if (s_empty[h]) continue;
+		if (empty_bits >> h & 1u) continue;
 		float m[MF];
 		const float4 *s4 = reinterpret_cast<const float4 *>(s_mf + h * MF);
 #pragma unroll
@@ -358,9 +360,10 @@ __device__ __forceinline__ void mask_tile(const float (&p)[kScP][5], const float
 	const int lane = threadIdx.x & 31;
 	const unsigned lt = (1u << lane) - 1u;
 	int head = 0, tail = 0;
+	const unsigned empty_bits = __ballot_sync(0xffffffffu, lane < nk && s_empty[lane] != 0);
 #pragma unroll 2
 	for (int h = 0; h < nk; ++h) {
-		if (s_empty[h]) continue; // all-zero model: every residual is NaN, no bit is set
+		if (empty_bits >> h & 1u) continue; // all-zero model: every residual is NaN, no bit is set
 		float m[MF];
 		const float4 *s4 = reinterpret_cast<const float4 *>(s_mf + h * MF);
 #pragma unroll
