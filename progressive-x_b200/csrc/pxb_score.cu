@@ -55,7 +55,7 @@ template <int TYPE, bool HAS_CP> struct ScoreSmem {
 	static constexpr size_t kRes = kAcc + sizeof(ScoreAcc) * kScWarps * kScHyps; // per warp: 32 values (+32 shared) + 32 segments
 	static constexpr size_t kSeg = kRes + sizeof(double) * kScWarps * 32 * (HAS_CP ? 2 : 1);
 	static constexpr size_t kEmpty = kSeg + sizeof(unsigned short) * kScWarps * 32; // per hypothesis of the tile: empty slot
-	static constexpr size_t kBytes = kEmpty + kScHyps;
+	static constexpr size_t kBytes = kEmpty + kScHyps + 16; // slot map of the compacted tile + its size
 };
 
 // Drains up to 32 queued candidates of one warp: one candidate per lane, the reference's exact float64 residual, the
@@ -124,22 +124,16 @@ __device__ __noinline__ ScoreAcc score_drain(const double *s_pts, const double *
 // The hypothesis loop of one warp: screening, queueing, draining.
 template <int TYPE, bool HAS_CP, bool FULL>
 __device__ __forceinline__ ScoreAcc score_tile(const float (&p)[kScP][5], const float (&zq)[kScP], const bool (&valid)[kScP],
-                                               const float *s_mf, const unsigned char *s_empty, int nk, float cT,
-                                               const double *s_pts, const double *s_cp, const double *s_models, int pbase,
-                                               double T2, unsigned short *queue, double *res_v, double *res_s,
-                                               unsigned short *seg) {
+                                               const float *s_mf, int nk, float cT, const double *s_pts, const double *s_cp,
+                                               const double *s_models, int pbase, double T2, unsigned short *queue,
+                                               double *res_v, double *res_s, unsigned short *seg) {
 	constexpr int MF = ScreenTraits<TYPE>::kFloats;
 	const int lane = threadIdx.x & 31;
 	const unsigned lt = (1u << lane) - 1u;
 	int head = 0, tail = 0;
 	ScoreAcc acc = {0.0, 0.0, 0};
-	// an unfilled solution slot of a minimal solver (all-zero model): every residual is NaN, nothing is an inlier -- count,
-	// score and shared support are exactly zero, as the reference's loop would find. One flag bit per hypothesis of the
-	// tile, held in a register (warp-uniform skip).
-	const unsigned empty_bits = __ballot_sync(0xffffffffu, lane < nk && s_empty[lane] != 0);
 #pragma unroll 2
 	for (int h = 0; h < nk; ++h) {
-		if (empty_bits >> h & 1u) continue;
 		float m[MF];
 		const float4 *s4 = reinterpret_cast<const float4 *>(s_mf + h * MF);
 #pragma unroll
@@ -251,20 +245,32 @@ __global__ void __launch_bounds__(kThreads, 3)
 		const int64_t k0 = ((int64_t)blockIdx.y * PASSES + pass) * tile;
 		if (k0 >= K) break; // block-uniform
 		const int nk = (int)min((int64_t)tile, K - k0);
-		for (int t = threadIdx.x; t < nk * MS; t += kThreads) s_models[(t / MS) * MP + (t % MS)] = models[k0 * MS + t];
-		for (int t = threadIdx.x; t < nk * MF; t += kThreads) s_mf[t] = __ldg(mfg + k0 * MF + t);
-		if (threadIdx.x < nk) s_empty[threadIdx.x] = __ldg(emptyg + k0 + threadIdx.x);
+		// Unfilled solution slots of a minimal solver (all-zero models: every residual is NaN, nothing is an inlier; count,
+		// score and shared support are exactly zero, as the reference's loop would find) never enter the hypothesis loop:
+		// the tile is compacted while it is staged, s_empty[j] = original slot of compacted hypothesis j.
+		__syncthreads(); // the previous pass has read s_empty / s_acc
+		if (warp == 0) {
+			const bool filled = lane < nk && __ldg(emptyg + k0 + lane) == 0;
+			const unsigned bits = __ballot_sync(0xffffffffu, filled);
+			if (filled) s_empty[__popc(bits & ((1u << lane) - 1u))] = (unsigned char)lane;
+			if (lane == 0) s_empty[kScHyps] = (unsigned char)__popc(bits);
+			if (lane < nk && !filled) partials[(k0 + lane) * nchunks + chunk] = ScorePartial{0.0, 0.0, 0};
+		}
+		__syncthreads();
+		const int nc = s_empty[kScHyps];
+		for (int t = threadIdx.x; t < nc * MS; t += kThreads) s_models[(t / MS) * MP + (t % MS)] = models[(k0 + s_empty[t / MS]) * MS + (t % MS)];
+		for (int t = threadIdx.x; t < nc * MF; t += kThreads) s_mf[t] = __ldg(mfg + (k0 + s_empty[t / MF]) * MF + (t % MF));
 		__syncthreads();
 		ScoreAcc acc;
 		if (full)
-			acc = score_tile<TYPE, HAS_CP, true>(p, zq, valid, s_mf, s_empty, nk, cT, s_pts, s_cp, s_models, warp * (32 * kScP), T2,
+			acc = score_tile<TYPE, HAS_CP, true>(p, zq, valid, s_mf, nc, cT, s_pts, s_cp, s_models, warp * (32 * kScP), T2,
 			                                     s_queue + warp * kScQueue, res_v, res_s, s_seg + warp * 32);
 		else
-			acc = score_tile<TYPE, HAS_CP, false>(p, zq, valid, s_mf, s_empty, nk, cT, s_pts, s_cp, s_models, warp * (32 * kScP), T2,
+			acc = score_tile<TYPE, HAS_CP, false>(p, zq, valid, s_mf, nc, cT, s_pts, s_cp, s_models, warp * (32 * kScP), T2,
 			                                      s_queue + warp * kScQueue, res_v, res_s, s_seg + warp * 32);
 		s_acc[warp * kScHyps + lane] = acc;
 		__syncthreads();
-		if (threadIdx.x < nk) { // the 8 chunks of the block, in order
+		if (threadIdx.x < nc) { // the 8 chunks of the block, in order
 			ScorePartial out = {0.0, 0.0, 0};
 #pragma unroll
 			for (int w = 0; w < kScWarps; ++w) {
@@ -273,7 +279,7 @@ __global__ void __launch_bounds__(kThreads, 3)
 				out.shared = add(out.shared, a.s);
 				out.count += a.c;
 			}
-			partials[(k0 + threadIdx.x) * nchunks + chunk] = out;
+			partials[(k0 + s_empty[threadIdx.x]) * nchunks + chunk] = out;
 		}
 	}
 }
@@ -328,7 +334,7 @@ template <int TYPE> struct MaskSmem {
 	static constexpr size_t kQueue = kMf + sizeof(float) * kScHyps * MF;
 	static constexpr size_t kMask = kQueue + sizeof(unsigned short) * kScWarps * kScQueue;
 	static constexpr size_t kEmpty = kMask + sizeof(uint32_t) * kScHyps * (kScChunk / 32);
-	static constexpr size_t kBytes = kEmpty + kScHyps;
+	static constexpr size_t kBytes = kEmpty + kScHyps + 16; // slot map of the compacted tile + its size
 };
 
 template <int TYPE>
@@ -353,17 +359,14 @@ __device__ __forceinline__ void mask_drain(const double *s_pts, const double *s_
 
 template <int TYPE, bool FULL>
 __device__ __forceinline__ void mask_tile(const float (&p)[kScP][5], const float (&zq)[kScP], const bool (&valid)[kScP],
-                                          const float *s_mf, const unsigned char *s_empty, int nk, float cT,
-                                          const double *s_pts, const double *s_models, int pbase, double T2,
-                                          unsigned short *queue, uint32_t *s_mask, int word0) {
+                                          const float *s_mf, int nk, float cT, const double *s_pts, const double *s_models,
+                                          int pbase, double T2, unsigned short *queue, uint32_t *s_mask, int word0) {
 	constexpr int MF = ScreenTraits<TYPE>::kFloats;
 	const int lane = threadIdx.x & 31;
 	const unsigned lt = (1u << lane) - 1u;
 	int head = 0, tail = 0;
-	const unsigned empty_bits = __ballot_sync(0xffffffffu, lane < nk && s_empty[lane] != 0);
 #pragma unroll 2
 	for (int h = 0; h < nk; ++h) {
-		if (empty_bits >> h & 1u) continue; // all-zero model: every residual is NaN, no bit is set
 		float m[MF];
 		const float4 *s4 = reinterpret_cast<const float4 *>(s_mf + h * MF);
 #pragma unroll
@@ -422,10 +425,17 @@ __global__ void __launch_bounds__(kThreads, 3)
 	}
 	const int64_t k0 = (int64_t)blockIdx.y * kScHyps;
 	const int nk = (int)min((int64_t)kScHyps, K - k0);
-	for (int t = threadIdx.x; t < nk * MS; t += kThreads) s_models[(t / MS) * MP + (t % MS)] = models[k0 * MS + t];
-	for (int t = threadIdx.x; t < nk * MF; t += kThreads) s_mf[t] = __ldg(mfg + k0 * MF + t);
-	if (threadIdx.x < nk) s_empty[threadIdx.x] = __ldg(emptyg + k0 + threadIdx.x);
+	if (warp == 0) { // compact the tile: all-zero models set no bit (every residual is NaN) and never enter the loop
+		const bool filled = lane < nk && __ldg(emptyg + k0 + lane) == 0;
+		const unsigned bits = __ballot_sync(0xffffffffu, filled);
+		if (filled) s_empty[__popc(bits & ((1u << lane) - 1u))] = (unsigned char)lane;
+		if (lane == 0) s_empty[kScHyps] = (unsigned char)__popc(bits);
+	}
 	for (int t = threadIdx.x; t < kScHyps * WPB; t += kThreads) s_mask[t] = 0u;
+	__syncthreads();
+	const int nc = s_empty[kScHyps];
+	for (int t = threadIdx.x; t < nc * MS; t += kThreads) s_models[(t / MS) * MP + (t % MS)] = models[(k0 + s_empty[t / MS]) * MS + (t % MS)];
+	for (int t = threadIdx.x; t < nc * MF; t += kThreads) s_mf[t] = __ldg(mfg + (k0 + s_empty[t / MF]) * MF + (t % MF));
 	const float cT = __ldg(consts), cE = __ldg(consts + 1);
 	const int64_t warp_base = block_base + warp * (32 * kScP);
 	float p[kScP][5], zq[kScP];
@@ -441,16 +451,22 @@ __global__ void __launch_bounds__(kThreads, 3)
 	}
 	__syncthreads();
 	if (warp_base + 32 * kScP <= N)
-		mask_tile<TYPE, true>(p, zq, valid, s_mf, s_empty, nk, cT, s_pts, s_models, warp * (32 * kScP), T2, s_queue + warp * kScQueue,
-		                      s_mask, warp * kScP);
+		mask_tile<TYPE, true>(p, zq, valid, s_mf, nc, cT, s_pts, s_models, warp * (32 * kScP), T2, s_queue + warp * kScQueue, s_mask,
+		                      warp * kScP);
 	else
-		mask_tile<TYPE, false>(p, zq, valid, s_mf, s_empty, nk, cT, s_pts, s_models, warp * (32 * kScP), T2, s_queue + warp * kScQueue,
-		                       s_mask, warp * kScP);
+		mask_tile<TYPE, false>(p, zq, valid, s_mf, nc, cT, s_pts, s_models, warp * (32 * kScP), T2, s_queue + warp * kScQueue, s_mask,
+		                       warp * kScP);
 	__syncthreads();
 	const int64_t w0 = (int64_t)chunk * WPB;
+	// rows of the compacted hypotheses go to their original slots; the rows of empty slots are zero
 	for (int t = threadIdx.x; t < nk * WPB; t += kThreads) {
 		const int h = t / WPB, w = t % WPB;
-		if (w0 + w < words) mask[(k0 + h) * words + w0 + w] = s_mask[h * WPB + w];
+		if (w0 + w < words) mask[(k0 + h) * words + w0 + w] = 0u;
+	}
+	__syncthreads();
+	for (int t = threadIdx.x; t < nc * WPB; t += kThreads) {
+		const int h = t / WPB, w = t % WPB;
+		if (w0 + w < words) mask[(k0 + s_empty[h]) * words + w0 + w] = s_mask[h * WPB + w];
 	}
 }
 
