@@ -30,6 +30,7 @@ constexpr int kScWarps = kThreads / 32;   // 8
 constexpr int kScChunk = kThreads * kScP; // 1024 points per block
 constexpr int kScHyps = 32;               // hypotheses per tile = lanes (lane h accumulates hypothesis h)
 constexpr int kScQueue = 256;             // circular candidate queue per warp (>= 31 + 128)
+constexpr unsigned kEmptySlotTag = 0x7fc0e000u; // first float of an unfilled solver slot's screening model
 
 struct ScorePartial {
 	double value, shared;
@@ -173,7 +174,7 @@ __device__ __forceinline__ ScoreAcc score_tile(const float (&p)[kScP][5], const 
 // launch constants of the test. One thread per hypothesis; keeps all float64 conjugation out of the hot kernel.
 template <int TYPE>
 __global__ void k_screen_prepare(const double *__restrict__ models, int64_t K, double T2, const NormDev *__restrict__ norm,
-                                 float *__restrict__ consts, float *__restrict__ mf, unsigned char *__restrict__ empty) {
+                                 float *__restrict__ consts, float *__restrict__ mf) {
 	constexpr int MS = ModelTraits<TYPE>::kSize, MF = ScreenTraits<TYPE>::kFloats;
 	const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	const NormDev nd = *norm;
@@ -192,17 +193,17 @@ __global__ void k_screen_prepare(const double *__restrict__ models, int64_t K, d
 	bool zero = true;
 #pragma unroll
 	for (int i = 0; i < MS; ++i) zero &= models[k * MS + i] == 0.0;
-	// H, F, PnP: an all-zero model gives 0/0 residuals everywhere. (A zero LINE has residual 0 -- all inliers -- and is scored.)
-	empty[k] = (zero && TYPE <= PXB_MODEL_PNP) ? 1 : 0;
+	// H, F, PnP: an all-zero model gives 0/0 residuals everywhere: the slot is tagged (a NaN payload in its first float) and
+	// the kernels leave it out of their tiles. (A zero LINE has residual 0 -- all inliers -- and is scored.)
+	if (zero && TYPE <= PXB_MODEL_PNP) mf[k * MF] = __uint_as_float(kEmptySlotTag);
 }
 
 template <int TYPE, bool HAS_CP, int PASSES>
 __global__ void __launch_bounds__(kThreads, 3)
     k_score_screened(const double *__restrict__ soa, int64_t stride, int64_t N, const float *__restrict__ pf,
                      const float *__restrict__ pq, const float *__restrict__ consts, const float *__restrict__ mfg,
-                     const unsigned char *__restrict__ emptyg, const double *__restrict__ models, int64_t K, double T2,
-                     const double *__restrict__ compound_pref,
-                     ScorePartial *__restrict__ partials, int nchunks, int tile /* hypotheses per pass, <= kScHyps */) {
+                     const double *__restrict__ models, int64_t K, double T2, const double *__restrict__ compound_pref,
+                     ScorePartial *__restrict__ partials, int nchunks, int tile_arg /* hypotheses per pass (PASSES == 1 only) */) {
 	using L = ScoreSmem<TYPE, HAS_CP>;
 	constexpr int DIM = L::DIM, MS = ModelTraits<TYPE>::kSize, MP = L::MP, MF = L::MF;
 	extern __shared__ __align__(16) unsigned char smem[];
@@ -241,25 +242,36 @@ __global__ void __launch_bounds__(kThreads, 3)
 	double *res_v = s_res + warp * 32 * (HAS_CP ? 2 : 1), *res_s = res_v + (HAS_CP ? 32 : 0);
 	const bool full = warp_base + 32 * kScP <= N; // interior warps run without validity predicates (warp-uniform)
 
+	const int tile = PASSES == 1 ? tile_arg : kScHyps; // big batches always walk full tiles
 	for (int pass = 0; pass < PASSES; ++pass) {
 		const int64_t k0 = ((int64_t)blockIdx.y * PASSES + pass) * tile;
 		if (k0 >= K) break; // block-uniform
 		const int nk = (int)min((int64_t)tile, K - k0);
 		// Unfilled solution slots of a minimal solver (all-zero models: every residual is NaN, nothing is an inlier; count,
 		// score and shared support are exactly zero, as the reference's loop would find) never enter the hypothesis loop:
-		// the tile is compacted while it is staged, s_empty[j] = original slot of compacted hypothesis j.
-		__syncthreads(); // the previous pass has read s_empty / s_acc
-		if (warp == 0) {
-			const bool filled = lane < nk && __ldg(emptyg + k0 + lane) == 0;
-			const unsigned bits = __ballot_sync(0xffffffffu, filled);
-			if (filled) s_empty[__popc(bits & ((1u << lane) - 1u))] = (unsigned char)lane;
-			if (lane == 0) s_empty[kScHyps] = (unsigned char)__popc(bits);
-			if (lane < nk && !filled) partials[(k0 + lane) * nchunks + chunk] = ScorePartial{0.0, 0.0, 0};
+		// for the families whose solvers return several solutions per sample (F: up to 3, PnP: up to 4) the tile is
+		// compacted while it is staged, s_empty[j] = original slot of compacted hypothesis j. The one-solution families
+		// keep the straight staging (the extra bookkeeping costs registers in the hot loop: measured -9 % on the H grid).
+		constexpr bool COMPACT = TYPE == PXB_MODEL_FUNDAMENTAL || TYPE == PXB_MODEL_PNP;
+		int nc = nk;
+		if (COMPACT) {
+			__syncthreads(); // the previous pass has read s_empty / s_acc
+			if (warp == 0) {
+				const bool filled = lane < nk && __float_as_uint(__ldg(mfg + (k0 + lane) * MF)) != kEmptySlotTag;
+				const unsigned bits = __ballot_sync(0xffffffffu, filled);
+				if (filled) s_empty[__popc(bits & ((1u << lane) - 1u))] = (unsigned char)lane;
+				if (lane == 0) s_empty[kScHyps] = (unsigned char)__popc(bits);
+				if (lane < nk && !filled) partials[(k0 + lane) * nchunks + chunk] = ScorePartial{0.0, 0.0, 0};
+			}
+			__syncthreads();
+			nc = s_empty[kScHyps];
+			for (int t = threadIdx.x; t < nc * MS; t += kThreads)
+				s_models[(t / MS) * MP + (t % MS)] = models[(k0 + s_empty[t / MS]) * MS + (t % MS)];
+			for (int t = threadIdx.x; t < nc * MF; t += kThreads) s_mf[t] = __ldg(mfg + (k0 + s_empty[t / MF]) * MF + (t % MF));
+		} else {
+			for (int t = threadIdx.x; t < nk * MS; t += kThreads) s_models[(t / MS) * MP + (t % MS)] = models[k0 * MS + t];
+			for (int t = threadIdx.x; t < nk * MF; t += kThreads) s_mf[t] = __ldg(mfg + k0 * MF + t);
 		}
-		__syncthreads();
-		const int nc = s_empty[kScHyps];
-		for (int t = threadIdx.x; t < nc * MS; t += kThreads) s_models[(t / MS) * MP + (t % MS)] = models[(k0 + s_empty[t / MS]) * MS + (t % MS)];
-		for (int t = threadIdx.x; t < nc * MF; t += kThreads) s_mf[t] = __ldg(mfg + (k0 + s_empty[t / MF]) * MF + (t % MF));
 		__syncthreads();
 		ScoreAcc acc;
 		if (full)
@@ -279,7 +291,7 @@ __global__ void __launch_bounds__(kThreads, 3)
 				out.shared = add(out.shared, a.s);
 				out.count += a.c;
 			}
-			partials[(k0 + s_empty[threadIdx.x]) * nchunks + chunk] = out;
+			partials[(k0 + (COMPACT ? (int)s_empty[threadIdx.x] : (int)threadIdx.x)) * nchunks + chunk] = out;
 		}
 	}
 }
@@ -302,8 +314,8 @@ __global__ void k_score_finalize(const ScorePartial *__restrict__ partials, int6
 }
 
 template <int TYPE, bool HAS_CP, int PASSES>
-static void launch_screened(pxb_ctx *ctx, int nchunks, const float *consts, const float *mf, const unsigned char *empty,
-                            const double *m, int64_t kk, double T2, const double *cp, ScorePartial *pp, int tile_hyps) {
+static void launch_screened(pxb_ctx *ctx, int nchunks, const float *consts, const float *mf, const double *m, int64_t kk,
+                            double T2, const double *cp, ScorePartial *pp, int tile_hyps) {
 	const Points &p = ctx->pts;
 	constexpr int kBytes = (int)ScoreSmem<TYPE, HAS_CP>::kBytes;
 	// opt in to > 48 KB of dynamic shared memory: once per device and instantiation (every API call counts when eight
@@ -315,8 +327,8 @@ static void launch_screened(pxb_ctx *ctx, int nchunks, const float *consts, cons
 	}
 	const int64_t tile = (int64_t)tile_hyps * PASSES;
 	dim3 grid((unsigned)nchunks, (unsigned)((kk + tile - 1) / tile));
-	k_score_screened<TYPE, HAS_CP, PASSES><<<grid, kThreads, kBytes, ctx->stream>>>(p.soa, p.stride, p.N, p.f32n, p.q, consts, mf,
-	                                                                             empty, m, kk, T2, cp, pp, nchunks, tile_hyps);
+	k_score_screened<TYPE, HAS_CP, PASSES><<<grid, kThreads, kBytes, ctx->stream>>>(p.soa, p.stride, p.N, p.f32n, p.q, consts, mf, m,
+	                                                                             kk, T2, cp, pp, nchunks, tile_hyps);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -404,8 +416,7 @@ template <int TYPE>
 __global__ void __launch_bounds__(kThreads, 3)
     k_mask_screened(const double *__restrict__ soa, int64_t stride, int64_t N, const float *__restrict__ pf,
                     const float *__restrict__ pq, const float *__restrict__ consts, const float *__restrict__ mfg,
-                    const unsigned char *__restrict__ emptyg, const double *__restrict__ models, int64_t K, double T2,
-                    uint32_t *__restrict__ mask, int64_t words) {
+                    const double *__restrict__ models, int64_t K, double T2, uint32_t *__restrict__ mask, int64_t words) {
 	using L = MaskSmem<TYPE>;
 	constexpr int DIM = L::DIM, MS = ModelTraits<TYPE>::kSize, MP = L::MP, MF = L::MF, WPB = kScChunk / 32;
 	extern __shared__ __align__(16) unsigned char smem[];
@@ -426,7 +437,7 @@ __global__ void __launch_bounds__(kThreads, 3)
 	const int64_t k0 = (int64_t)blockIdx.y * kScHyps;
 	const int nk = (int)min((int64_t)kScHyps, K - k0);
 	if (warp == 0) { // compact the tile: all-zero models set no bit (every residual is NaN) and never enter the loop
-		const bool filled = lane < nk && __ldg(emptyg + k0 + lane) == 0;
+		const bool filled = lane < nk && __float_as_uint(__ldg(mfg + (k0 + lane) * MF)) != kEmptySlotTag;
 		const unsigned bits = __ballot_sync(0xffffffffu, filled);
 		if (filled) s_empty[__popc(bits & ((1u << lane) - 1u))] = (unsigned char)lane;
 		if (lane == 0) s_empty[kScHyps] = (unsigned char)__popc(bits);
@@ -485,12 +496,11 @@ template <int TYPE> static int launch_mask_t(pxb_ctx *ctx, const double *models,
 	while (done < K) { // gridDim.y is limited to 65535
 		const int64_t kk = std::min<int64_t>(K - done, (int64_t)65535 * kScHyps);
 		const double *m = models + done * ModelTraits<TYPE>::kSize;
-		PXB_TRY(ctx->screen.reserve(sizeof(float) * (4 + (size_t)kk * MF) + (size_t)kk + 64));
+		PXB_TRY(ctx->screen.reserve(sizeof(float) * (4 + (size_t)kk * MF)));
 		float *consts = ctx->screen.as<float>(), *mf = consts + 4;
-		unsigned char *empty = reinterpret_cast<unsigned char *>(mf + (size_t)kk * MF);
-		k_screen_prepare<TYPE><<<(unsigned)((kk + 127) / 128), 128, 0, ctx->stream>>>(m, kk, T2, p.norm, consts, mf, empty);
+		k_screen_prepare<TYPE><<<(unsigned)((kk + 127) / 128), 128, 0, ctx->stream>>>(m, kk, T2, p.norm, consts, mf);
 		dim3 grid((unsigned)nchunks, (unsigned)((kk + kScHyps - 1) / kScHyps));
-		k_mask_screened<TYPE><<<grid, kThreads, kBytes, ctx->stream>>>(p.soa, p.stride, p.N, p.f32n, p.q, consts, mf, empty, m, kk, T2,
+		k_mask_screened<TYPE><<<grid, kThreads, kBytes, ctx->stream>>>(p.soa, p.stride, p.N, p.f32n, p.q, consts, mf, m, kk, T2,
 		                                                              mask + done * words, words);
 		ctx->launches += 2;
 		done += kk;
@@ -510,10 +520,9 @@ int launch_inlier_mask(pxb_ctx *ctx, const double *models, int64_t K, double T2,
 template <int TYPE>
 static int launch_partial(pxb_ctx *ctx, int nchunks, const double *m, int64_t kk, double T2, const double *cp, ScorePartial *pp) {
 	constexpr int MF = ScreenTraits<TYPE>::kFloats;
-	PXB_TRY(ctx->screen.reserve(sizeof(float) * (4 + (size_t)kk * MF) + (size_t)kk + 64));
+	PXB_TRY(ctx->screen.reserve(sizeof(float) * (4 + (size_t)kk * MF)));
 	float *consts = ctx->screen.as<float>(), *mf = consts + 4;
-	unsigned char *empty = reinterpret_cast<unsigned char *>(mf + (size_t)kk * MF);
-	k_screen_prepare<TYPE><<<(unsigned)((kk + 127) / 128), 128, 0, ctx->stream>>>(m, kk, T2, ctx->pts.norm, consts, mf, empty);
+	k_screen_prepare<TYPE><<<(unsigned)((kk + 127) / 128), 128, 0, ctx->stream>>>(m, kk, T2, ctx->pts.norm, consts, mf);
 	ctx->launches++;
 	// big batches walk 4 tiles of 32 hypotheses per block (the per-block prologue -- staging 1024 points -- is paid once);
 	// RANSAC-sized batches keep one tile per block so that the grid still fills the GPU
@@ -527,11 +536,11 @@ static int launch_partial(pxb_ctx *ctx, int nchunks, const double *m, int64_t kk
 		tile = (int)std::min<int64_t>(kScHyps, std::max<int64_t>(1, kk * nchunks / want_blocks));
 	}
 	if (cp) {
-		if (big) launch_screened<TYPE, true, 4>(ctx, nchunks, consts, mf, empty, m, kk, T2, cp, pp, kScHyps);
-		else launch_screened<TYPE, true, 1>(ctx, nchunks, consts, mf, empty, m, kk, T2, cp, pp, tile);
+		if (big) launch_screened<TYPE, true, 4>(ctx, nchunks, consts, mf, m, kk, T2, cp, pp, kScHyps);
+		else launch_screened<TYPE, true, 1>(ctx, nchunks, consts, mf, m, kk, T2, cp, pp, tile);
 	} else {
-		if (big) launch_screened<TYPE, false, 4>(ctx, nchunks, consts, mf, empty, m, kk, T2, cp, pp, kScHyps);
-		else launch_screened<TYPE, false, 1>(ctx, nchunks, consts, mf, empty, m, kk, T2, cp, pp, tile);
+		if (big) launch_screened<TYPE, false, 4>(ctx, nchunks, consts, mf, m, kk, T2, cp, pp, kScHyps);
+		else launch_screened<TYPE, false, 1>(ctx, nchunks, consts, mf, m, kk, T2, cp, pp, tile);
 	}
 	ctx->launches++;
 	return PXB_OK;
