@@ -634,6 +634,20 @@ def main():
                                         "p mod N, findHomographies(Python defaults, uniform sampler, lambda=0), instances merged by one "
                                         "ncclAllGather (pxb_allgather_instances); strong scaling over N"}
 
+        # weak-scaling companion: 64 pairs PER GPU (different scenes per rank), same call, no exchange step
+        weak = [syn.multi_homography_scene(n_pts, n_planes=4, outlier_ratio=0.4, noise=0.5, seed=5000 + 64 * rank + p)[0]
+                for p in range(64)]
+        pyprogressivex.findHomographiesBatch(weak[:workers * in_flight], 1024, 768, 1024, 768, workers=workers, in_flight=in_flight, **c4_kw)
+        barrier()
+        t0 = time.perf_counter()
+        pyprogressivex.findHomographiesBatch(weak, 1024, 768, 1024, 768, workers=workers, in_flight=in_flight, **c4_kw)
+        barrier()
+        weak_s = max_over_ranks(time.perf_counter() - t0)
+        extras["batch_c4_weak"] = {"fits_per_s": 64 * world / weak_s, "pairs_per_gpu": 64, "points_per_pair": n_pts,
+                                   "host_threads_per_gpu": workers, "problems_in_flight_per_thread": in_flight,
+                                   "note": "same call as batch_c4 with a fixed load per GPU (weak scaling, no exchange): "
+                                           "efficiency at N GPUs = fits_per_s(N) / (N x fits_per_s(1))"}
+
         # ---- C5 as specified: one 100k-match 6D-pose problem, hypothesis blocks sharded over the ranks -------------------
         c5_kw = dict(threshold=4.0, conf=0.9, spatial_coherence_weight=0.0, neighborhood_ball_radius=20.0,
                      maximum_tanimoto_similarity=0.9, max_iters=5000, minimum_point_number=1000, maximum_model_number=-1,
