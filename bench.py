@@ -441,7 +441,8 @@ def main():
                 del out, mk, md
                 return {"workload": label, "N": Nx, "K": Kx, "launch_ms": ms, "evals_per_s": Nx * Kx * world * reps / (tot * 1e-3),
                         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                                     "traffic": committed(traffic_key), "algorithmic_bytes_per_launch": Nx * Kx * BYTES_PER_EVAL},
+                                     "traffic": (committed(traffic_key) * Nx * Kx) if committed(traffic_key) else None,
+                                     "algorithmic_bytes_per_launch": Nx * Kx * BYTES_PER_EVAL},
                         "inliers_in_first_64_hypotheses": inl}
             finally:
                 c.close()
@@ -452,7 +453,7 @@ def main():
         extras["matrix_F"] = matrix_line(_native.MODEL_F, f_pts, f_s, (1.5 * 0.75) ** 2,
                                          "C3: synthetic multi-F, N=50 000 correspondences (3 motions 25/25/20% + 30% outliers), "
                                          "hypotheses = all solutions of 10 000 seven-point samples, thr=0.75 px; Sampson r2 f64 + bit",
-                                         "k_residual_matrix_F_bytes_per_launch")
+                                         "k_residual_matrix_F_traffic_bytes_per_eval")
         p_img, p_w, p_K, p_gt, _ = syn.multi_pose_scene(100_000, n_objects=10, inlier_ratio_each=0.06, noise_px=1.0, seed=0)
         p_rows = syn.normalize_pnp_points(p_img, p_w, p_K)
         p_s = syn.minimal_samples(p_gt, 10_000, 3, within_ratio=0.5, seed=3000 + rank)
@@ -460,7 +461,7 @@ def main():
         extras["matrix_PnP"] = matrix_line(_native.MODEL_PNP, p_rows, p_s, (1.5 * p_thr) ** 2,
                                            "C5: synthetic multi-pose, N=100 000 2D-3D matches (10 objects x 6% + 40% outliers), "
                                            "hypotheses = all poses of 10 000 P3P samples, thr=4 px / f; reprojection r2 f64 + bit",
-                                           "k_residual_matrix_PnP_bytes_per_launch")
+                                           "k_residual_matrix_PnP_traffic_bytes_per_eval")
         ctx.upload_points(_native.MODEL_H, pts)
 
     # ---- hypothesis-summary exchange of the sharded RANSAC loop (N > 1 only) ---------------------------------
