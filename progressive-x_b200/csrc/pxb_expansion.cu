@@ -99,55 +99,127 @@ __device__ __forceinline__ int ld_volatile_s32_if(const int32_t *p, bool pred, i
 __device__ void mf_global_relabel(const FlowGraphDev &G, int32_t *h, cg::grid_group &grid, int tid, int nthreads) {
 	const int n = G.n;
 	volatile int32_t *hv = h;
-	for (int u = tid; u < n; u += nthreads) h[u] = (G.sink_cap[u] > 0.0) ? 1 : n;
+	const int lane = threadIdx.x & 31;
+	// flags[9], [11], [15]: size of the frontier of level L in slot L % 3 -- they choose the direction of every level
+	// (below). Like the 'changed' flags they rotate over three slots: during level L the slot of L + 1 is accumulated and
+	// the slot of L + 2 (= L - 1, read by everyone before the previous barrier) is cleared.
+	const int cnt_slot[3] = {9, 11, 15};
 	if (tid == 0) {
 		G.flags[0] = 0;
 		G.flags[1] = 0;
 		G.flags[2] = 0;
+		G.flags[9] = 0;
+		G.flags[11] = 0;
+		G.flags[15] = 0;
 	}
 	grid.sync();
+	int first = 0;
+	for (int u = tid; u < n; u += nthreads) {
+		const bool at_sink = G.sink_cap[u] > 0.0;
+		h[u] = at_sink ? 1 : n;
+		first += at_sink;
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) first += __shfl_xor_sync(0xffffffffu, first, o);
+	if (lane == 0 && first) atomicAdd(&G.flags[cnt_slot[1]], first);
+	grid.sync();
+	int labelled = 0;
 	// flags rotate over three slots: the slot of level L+1 is cleared during level L, while stragglers may still be
 	// reading the slot of level L-1 (they are past that level's barrier but not yet past its test)
 	for (int level = 1; level < n; ++level) {
 		int32_t *changed = &G.flags[level % 3];
+		int32_t *count_next = &G.flags[cnt_slot[(level + 1) % 3]];
+		const int frontier = *(volatile int32_t *)&G.flags[cnt_slot[level % 3]]; // stable: written before the last barrier
+		labelled += frontier;
 		bool mine = false;
-		for (int u = tid; u < G.wide_begin; u += nthreads) {
-			if (hv[u] != level) continue;
-			const int a0 = G.arc_off[u], a1 = G.arc_off[u + 1];
-			for (int base = a0; base < a1; base += 8) { // chunks of 8 arcs, predicated loads (see mf_process)
-				int v[8], r[8];
-				bool want[8];
-				double c[8];
+		int found_here = 0;
+		// Direction-optimising step (Beamer et al.), as in the single-block form: when the frontier is larger than what
+		// is still unlabelled -- level 1 of every cut: most nodes hang on the sink directly -- every still-unlabelled
+		// node looks among its OWN out-arcs for a residual one into the frontier instead of the frontier expanding all of
+		// its arcs (the top-down level 1 of a 10^5-node light move cost 0.4 ms: 9.4 10^4 nodes x ~10 arcs x 4 dependent
+		// loads to find the ~6000 others). Same labels: a node gets level + 1 iff it has a residual arc into this level
+		// and was not labelled before.
+		const bool bottom_up = 2 * (long long)frontier > (long long)(n - labelled);
+		if (bottom_up) {
+			for (int u = tid; u < G.wide_begin; u += nthreads) {
+				if (hv[u] != n) continue;
+				const int a0 = G.arc_off[u], a1 = G.arc_off[u + 1];
+				bool hit = false;
+				for (int base = a0; base < a1 && !hit; base += 8) {
+					int v[8];
+					double c[8];
 #pragma unroll
-				for (int j = 0; j < 8; ++j) v[j] = ld_nc_s32_if(G.arc_head + base + j, base + j < a1, -1);
-#pragma unroll
-				for (int j = 0; j < 8; ++j) want[j] = ld_volatile_s32_if(h + (v[j] >= 0 ? v[j] : 0), v[j] >= 0, 0) == n;
-#pragma unroll
-				for (int j = 0; j < 8; ++j) r[j] = ld_nc_s32_if(G.arc_rev + base + j, want[j], 0);
-#pragma unroll
-				for (int j = 0; j < 8; ++j) c[j] = ld_volatile_f64_if(G.cap + r[j], want[j]);
-#pragma unroll
-				for (int j = 0; j < 8; ++j)
-					if (want[j] && c[j] > 0.0) {
-						hv[v[j]] = level + 1; // benign race: every writer stores the same value
-						mine = true;
+					for (int j = 0; j < 8; ++j) {
+						v[j] = ld_nc_s32_if(G.arc_head + base + j, base + j < a1, -1);
+						c[j] = ld_volatile_f64_if(G.cap + base + j, base + j < a1);
 					}
+#pragma unroll
+					for (int j = 0; j < 8; ++j)
+						hit |= v[j] >= 0 && c[j] > 0.0 && ld_volatile_s32_if(h + (v[j] >= 0 ? v[j] : 0), v[j] >= 0 && c[j] > 0.0, 0) == level;
+				}
+				if (hit) {
+					hv[u] = level + 1;
+					mine = true;
+					++found_here;
+				}
 			}
-		}
-		for (int w = blockIdx.x; w < G.wide_count; w += gridDim.x) { // a wide node's arcs are expanded by its whole block
-			const int u = G.wide_begin + w;
-			if (hv[u] != level) continue; // block-uniform: h[u] was written before the previous barrier
-			for (int a = G.arc_off[u] + threadIdx.x; a < G.arc_off[u + 1]; a += blockDim.x) {
-				const int v = G.arc_head[a];
-				if (G.cap[G.arc_rev[a]] > 0.0 && hv[v] == n) {
-					hv[v] = level + 1;
+			for (int w = blockIdx.x; w < G.wide_count; w += gridDim.x) { // an unlabelled wide node: its block scans its arcs
+				const int u = G.wide_begin + w;
+				if (hv[u] != n) continue; // block-uniform
+				bool hit = false;
+				for (int a = G.arc_off[u] + threadIdx.x; a < G.arc_off[u + 1] && !hit; a += blockDim.x)
+					hit = G.cap[a] > 0.0 && hv[G.arc_head[a]] == level;
+				if (__syncthreads_or(hit)) {
+					if (threadIdx.x == 0) {
+						hv[u] = level + 1;
+						++found_here;
+					}
 					mine = true;
 				}
 			}
+		} else {
+			for (int u = tid; u < G.wide_begin; u += nthreads) {
+				if (hv[u] != level) continue;
+				const int a0 = G.arc_off[u], a1 = G.arc_off[u + 1];
+				for (int base = a0; base < a1; base += 8) { // chunks of 8 arcs, predicated loads (see mf_process)
+					int v[8], r[8];
+					bool want[8];
+					double c[8];
+#pragma unroll
+					for (int j = 0; j < 8; ++j) v[j] = ld_nc_s32_if(G.arc_head + base + j, base + j < a1, -1);
+#pragma unroll
+					for (int j = 0; j < 8; ++j) want[j] = ld_volatile_s32_if(h + (v[j] >= 0 ? v[j] : 0), v[j] >= 0, 0) == n;
+#pragma unroll
+					for (int j = 0; j < 8; ++j) r[j] = ld_nc_s32_if(G.arc_rev + base + j, want[j], 0);
+#pragma unroll
+					for (int j = 0; j < 8; ++j) c[j] = ld_volatile_f64_if(G.cap + r[j], want[j]);
+#pragma unroll
+					for (int j = 0; j < 8; ++j)
+						if (want[j] && c[j] > 0.0 && atomicCAS(&h[v[j]], n, level + 1) == n) { // claimed once: exact frontier counts
+							mine = true;
+							++found_here;
+						}
+				}
+			}
+			for (int w = blockIdx.x; w < G.wide_count; w += gridDim.x) { // a wide node's arcs are expanded by its whole block
+				const int u = G.wide_begin + w;
+				if (hv[u] != level) continue; // block-uniform: h[u] was written before the previous barrier
+				for (int a = G.arc_off[u] + threadIdx.x; a < G.arc_off[u + 1]; a += blockDim.x) {
+					const int v = G.arc_head[a];
+					if (G.cap[G.arc_rev[a]] > 0.0 && hv[v] == n && atomicCAS(&h[v], n, level + 1) == n) {
+						mine = true;
+						++found_here;
+					}
+				}
+			}
 		}
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) found_here += __shfl_xor_sync(0xffffffffu, found_here, o);
+		if (lane == 0 && found_here) atomicAdd(count_next, found_here);
 		if (mine) *changed = 1;
 		if (tid == 0) {
 			G.flags[(level + 1) % 3] = 0;
+			G.flags[cnt_slot[(level + 2) % 3]] = 0;
 			G.flags[8]++; // statistics: BFS levels
 		}
 		grid.sync();
@@ -669,6 +741,7 @@ static int mf_launch_config(pxb_ctx *ctx, FlowGraphDev &G, int min_grid, MfLaunc
 	G.local_exit = getenv("PXB_MF_LOCAL_EXIT") ? 1 : 0;
 	G.quiet_cycles = (long long)((getenv("PXB_MF_QUIET_US") ? atof(getenv("PXB_MF_QUIET_US")) : 10.0) * 1965.0);
 	G.async_cycles = std::max(8, async_cycles);
+	const bool async_given = getenv("PXB_MF_ASYNC") != nullptr;
 	G.idle_checks = std::max(1, idle_checks);
 	static bool attribute_set[64] = {}; // per device (function attributes belong to the device's context)
 	constexpr size_t kMaxSmem = 200 * 1024;
@@ -683,6 +756,10 @@ static int mf_launch_config(pxb_ctx *ctx, FlowGraphDev &G, int min_grid, MfLaunc
 	G.block_bfs = (grid_bfs_only || G.wide_count > 32) ? 0 : (need_offs <= smem_cap ? 2 : (need <= smem_cap ? 1 : 0));
 	if (G.block_bfs == 2 && need_ulist <= smem_cap && !getenv("PXB_MF_TOP_DOWN")) G.block_bfs = 3;
 	out.smem = G.block_bfs == 3 ? need_ulist : (G.block_bfs == 2 ? need_offs : (G.block_bfs == 1 ? need : 0));
+	// Graphs too large for the single-block relabel pay a grid-wide BFS per round (hundreds of levels of ~6 us on a
+	// 10^5-node neighbourhood graph): longer push phases trade rounds for cycles there (C5 at lambda = 0.1: 2.0 s with 64
+	// busy cycles per phase, 1.36 s with 256, 1.20 s with 1024, 1.86 s with 4096)
+	if (G.block_bfs == 0 && !async_given) G.async_cycles = 1024;
 	// occupancy for this shared-memory size: asked once per (thread, device, size) -- a fit makes ~200 cuts
 	thread_local struct {
 		int device;
