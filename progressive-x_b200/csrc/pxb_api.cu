@@ -236,6 +236,15 @@ int pxb_ctx_create(int device, pxb_ctx **out) {
 		ctx->stage_cap = kStageBytes;
 	else
 		(void)cudaGetLastError(); // no staging arena: transfers fall back to direct copies
+	// fixed pinned slots of the replayable device chains (without them the driver simply never captures a graph)
+	if (cudaMallocHost(reinterpret_cast<void **>(&ctx->chain_in), kChainInBytes) != cudaSuccess ||
+	    cudaMallocHost(reinterpret_cast<void **>(&ctx->chain_out), kChainOutBytes) != cudaSuccess ||
+	    ctx->chain_par.reserve(kChainInBytes) != PXB_OK) {
+		(void)cudaGetLastError();
+		if (ctx->chain_in) cudaFreeHost(ctx->chain_in);
+		if (ctx->chain_out) cudaFreeHost(ctx->chain_out);
+		ctx->chain_in = ctx->chain_out = nullptr;
+	}
 	*out = ctx;
 	return PXB_OK;
 }
@@ -251,10 +260,14 @@ void pxb_ctx_destroy(pxb_ctx *ctx) {
 	if (ctx->pts.norm) cudaFree(ctx->pts.norm);
 	DevBuf *bufs[] = {&ctx->models, &ctx->pref, &ctx->pref2, &ctx->outA, &ctx->outB, &ctx->outC,
 	                  &ctx->outD,   &ctx->idx,  &ctx->mask,  &ctx->partials, &ctx->staging, &ctx->screen, &ctx->stats, &ctx->cpref,
-	                  &ctx->shard_msg, &ctx->shard_rec, &ctx->labels, &ctx->pack};
+	                  &ctx->shard_msg, &ctx->shard_rec, &ctx->labels, &ctx->pack, &ctx->chain_par};
 	for (DevBuf *b : bufs) b->release();
 	if (ctx->pinned) cudaFreeHost(ctx->pinned);
 	if (ctx->stage) cudaFreeHost(ctx->stage);
+	for (auto &g : ctx->chain_graphs)
+		if (g.exec) cudaGraphExecDestroy(g.exec);
+	if (ctx->chain_in) cudaFreeHost(ctx->chain_in);
+	if (ctx->chain_out) cudaFreeHost(ctx->chain_out);
 	if (ctx->timing_events_ready)
 		for (cudaEvent_t e : ctx->timing_events) cudaEventDestroy(e);
 	lo_skeleton_free(ctx->lo_skeleton);

@@ -173,7 +173,8 @@ constexpr int kLoMaxSample = 64;
 // rejected (uniform_int_distribution), a value already in the set is rejected (unique_set redraws that position).
 __global__ void __launch_bounds__(32)
     k_lo_sample(const int32_t *__restrict__ inl, const int64_t *__restrict__ count_in, int m, int limit, int trials,
-                uint64_t seed, uint64_t event, int32_t *__restrict__ off /*trials + 1*/, int32_t *__restrict__ idx) {
+                const uint64_t *__restrict__ seed_event, int32_t *__restrict__ off /*trials + 1*/, int32_t *__restrict__ idx) {
+	const uint64_t seed = seed_event[0], event = seed_event[1]; // on the device: the launch is part of a replayed graph
 	const int64_t count = count_in[0];
 	const int t = blockIdx.x, lane = threadIdx.x;
 	if (count > (int64_t)limit) {
@@ -235,13 +236,13 @@ int launch_mask_compact(pxb_ctx *ctx, const uint32_t *mask_dev, int64_t N, int32
 	PXB_CUDA(cudaGetLastError());
 	return PXB_OK;
 }
-int launch_lo_sample(pxb_ctx *ctx, const int32_t *inl_dev, const int64_t *count_dev, int m, int limit, int trials, uint64_t seed,
-                     uint64_t event, int32_t *off_dev, int32_t *idx_dev) {
+int launch_lo_sample(pxb_ctx *ctx, const int32_t *inl_dev, const int64_t *count_dev, int m, int limit, int trials,
+                     const uint64_t *seed_event_dev, int32_t *off_dev, int32_t *idx_dev) {
 	if (limit > kLoMaxSample || trials < 1) {
 		set_error("local optimisation sample of %d points / %d trials exceeds the kernel limits", limit, trials);
 		return PXB_ERR_UNSUPPORTED;
 	}
-	k_lo_sample<<<(unsigned)trials, 32, 0, ctx->stream>>>(inl_dev, count_dev, m, limit, trials, seed, event, off_dev, idx_dev);
+	k_lo_sample<<<(unsigned)trials, 32, 0, ctx->stream>>>(inl_dev, count_dev, m, limit, trials, seed_event_dev, off_dev, idx_dev);
 	ctx->launches++;
 	PXB_CUDA(cudaGetLastError());
 	return PXB_OK;

@@ -643,30 +643,51 @@ class Driver {
 		if (sharded()) return solve_and_score_sharded(samples, want, T2, models, n, sv, mv, cnt, val, shr);
 		Scoped t(prof_, "refill(solve+score)");
 		const size_t K = want;
-		// models, scores and flags of the block sit in one device record (same layout as a sharded slice): ONE copy back
+		// models, scores and flags of the block sit in one device record (same layout as a sharded slice): ONE copy back.
+		// inputs: sample indices [K m] | plane-and-parallax homography [9]
 		const ShardRecord rec = shard_record(K);
-		PXB_TRY(ctx_->idx.reserve(sizeof(int64_t) * K * m_));
+		const size_t b_smp = sizeof(int64_t) * K * m_, in_bytes = b_smp + sizeof(double) * 9;
+		PXB_TRY(ctx_->chain_par.reserve(in_bytes));
 		PXB_TRY(ctx_->shard_rec.reserve(rec.bytes));
-		char *rc_dev = ctx_->shard_rec.as<char>();
-		double *d_models = reinterpret_cast<double *>(rc_dev + rec.models);
-		int32_t *d_n = reinterpret_cast<int32_t *>(rc_dev + rec.n);
-		uint8_t *d_sv = reinterpret_cast<uint8_t *>(rc_dev + rec.sv), *d_mv = reinterpret_cast<uint8_t *>(rc_dev + rec.mv);
-		PXB_TRY(api_h2d(ctx_, ctx_->idx.ptr, samples.data(), sizeof(int64_t) * K * m_));
-		PXB_CUDA(cudaMemsetAsync(rc_dev, 0, rec.bytes, ctx_->stream));
-		if (s_.plane_parallax) {
-			PXB_TRY(ctx_->outC.reserve(sizeof(double) * 9));
-			PXB_TRY(api_h2d(ctx_, ctx_->outC.ptr, s_.pp_H, sizeof(double) * 9));
-			PXB_TRY(launch_solve_plane_parallax(ctx_, ctx_->idx.as<int64_t>(), (int64_t)K, ctx_->outC.as<double>(), d_models, d_n, d_sv,
-			                                    d_mv));
-		} else {
-			PXB_TRY(launch_solve_minimal(ctx_, ctx_->idx.as<int64_t>(), (int64_t)K, d_models, d_n, d_sv, d_mv));
-		}
-		PXB_TRY(launch_score_compound(ctx_, d_models, (int64_t)(K * maxsol_), T2, compound_dev(), reinterpret_cast<int64_t *>(rc_dev + rec.cnt),
-		                              reinterpret_cast<double *>(rc_dev + rec.val), reinterpret_cast<double *>(rc_dev + rec.shr)));
+		const bool slots = chain_slots(in_bytes, rec.bytes);
+		chain_tmp_in_.resize(in_bytes);
+		unsigned char *hin = slots ? ctx_->chain_in : chain_tmp_in_.data();
+		std::memcpy(hin, samples.data(), b_smp);
+		std::memcpy(hin + b_smp, s_.pp_H, sizeof(double) * 9);
 		pack_host_.resize(rec.bytes);
-		PXB_TRY(api_d2h(ctx_, pack_host_.data(), rc_dev, rec.bytes));
+		unsigned char *hout = slots ? ctx_->chain_out : pack_host_.data();
+		auto enqueue = [&]() -> int {
+			char *par = ctx_->chain_par.as<char>();
+			const int64_t *d_smp = reinterpret_cast<const int64_t *>(par);
+			const double *d_ppH = reinterpret_cast<const double *>(par + b_smp);
+			char *rc_dev = ctx_->shard_rec.as<char>();
+			double *d_models = reinterpret_cast<double *>(rc_dev + rec.models);
+			int32_t *d_n = reinterpret_cast<int32_t *>(rc_dev + rec.n);
+			uint8_t *d_sv = reinterpret_cast<uint8_t *>(rc_dev + rec.sv), *d_mv = reinterpret_cast<uint8_t *>(rc_dev + rec.mv);
+			if (slots)
+				PXB_CUDA(cudaMemcpyAsync(par, hin, in_bytes, cudaMemcpyHostToDevice, ctx_->stream));
+			else
+				PXB_TRY(api_h2d(ctx_, par, hin, in_bytes));
+			PXB_CUDA(cudaMemsetAsync(rc_dev, 0, rec.bytes, ctx_->stream));
+			if (s_.plane_parallax)
+				PXB_TRY(launch_solve_plane_parallax(ctx_, d_smp, (int64_t)K, d_ppH, d_models, d_n, d_sv, d_mv));
+			else
+				PXB_TRY(launch_solve_minimal(ctx_, d_smp, (int64_t)K, d_models, d_n, d_sv, d_mv));
+			PXB_TRY(launch_score_compound(ctx_, d_models, (int64_t)(K * maxsol_), T2, compound_dev(),
+			                              reinterpret_cast<int64_t *>(rc_dev + rec.cnt), reinterpret_cast<double *>(rc_dev + rec.val),
+			                              reinterpret_cast<double *>(rc_dev + rec.shr)));
+			if (slots)
+				PXB_CUDA(cudaMemcpyAsync(hout, rc_dev, rec.bytes, cudaMemcpyDeviceToHost, ctx_->stream));
+			else
+				PXB_TRY(api_d2h(ctx_, hout, rc_dev, rec.bytes));
+			return PXB_OK;
+		};
+		if (slots)
+			PXB_TRY(run_chain(mix_key({kChainRefill, buffers_key(), (uint64_t)K, (uint64_t)s_.plane_parallax, bits(T2)}), enqueue));
+		else
+			PXB_TRY(enqueue());
 		PXB_TRY(api_sync(ctx_));
-		const unsigned char *h = pack_host_.data();
+		const unsigned char *h = hout;
 		const size_t KS = K * maxsol_;
 		cnt.resize(KS);
 		val.resize(KS);
@@ -689,7 +710,101 @@ class Driver {
 		return PXB_OK;
 	}
 	int launch_fit_family(int P, const int32_t *d_off, const int32_t *d_idx, const double *d_w, double *models_dev, int32_t *ok_dev);
-	std::vector<unsigned char> pack_host_;
+	std::vector<unsigned char> pack_host_, chain_tmp_in_;
+	// ---- replayable device chains (CUDA graphs; see pxb_ctx::ChainGraph) ---------------------------------------------
+	enum ChainKind : uint64_t { kChainRefill = 1, kChainLo = 2, kChainTail = 3, kChainPearl = 4 };
+	static uint64_t mix_key(std::initializer_list<uint64_t> parts) {
+		uint64_t h = 0x9E3779B97F4A7C15ull;
+		for (uint64_t v : parts) {
+			h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+			h *= 0xBF58476D1CE4E5B9ull;
+			h ^= h >> 29;
+		}
+		return h | 1;
+	}
+	static uint64_t bits(double v) {
+		uint64_t u;
+		std::memcpy(&u, &v, sizeof(u));
+		return u;
+	}
+	static uint64_t bits(const void *p) { return (uint64_t)reinterpret_cast<uintptr_t>(p); }
+	// the buffers every chain touches: a reallocation of any of them changes the signature (and forces a new capture)
+	uint64_t buffers_key() const {
+		const pxb::Points &p = ctx_->pts;
+		return mix_key({bits(p.soa), bits(p.aos), bits(p.f32n), bits(p.q), bits(p.norm), (uint64_t)p.N, (uint64_t)p.type,
+		                bits(ctx_->idx.ptr), bits(ctx_->pack.ptr), bits(ctx_->screen.ptr), bits(ctx_->partials.ptr),
+		                bits(ctx_->outA.ptr), bits(ctx_->mask.ptr), bits(ctx_->pref2.ptr), bits(ctx_->shard_rec.ptr),
+		                bits(ctx_->staging.ptr), bits(ctx_->labels.ptr), bits(ctx_->outB.ptr), bits(ctx_->outC.ptr),
+		                bits(ctx_->outD.ptr), bits(ctx_->cpref.ptr), bits(ctx_->chain_par.ptr), bits(compound_dev())});
+	}
+	bool chain_slots(size_t in_bytes, size_t out_bytes) const {
+		return ctx_->chain_in && in_bytes <= kChainInBytes && out_bytes <= kChainOutBytes;
+	}
+	// Runs `enqueue` (a fixed sequence of asynchronous copies and launches on the context's stream that only depends on
+	// `key`): plainly the first time a key is seen (buffers get allocated), captured into a CUDA graph the second time,
+	// replayed with one cudaGraphLaunch from then on. PXB_GRAPHS=0 disables capturing.
+	template <class Enqueue> int run_chain(uint64_t key, Enqueue &&enqueue) {
+		static const bool enabled = !(getenv("PXB_GRAPHS") && atoi(getenv("PXB_GRAPHS")) == 0);
+		if (!enabled) return enqueue();
+		auto &cache = ctx_->chain_graphs;
+		pxb_ctx::ChainGraph *e = nullptr;
+		for (auto &g : cache)
+			if (g.key == key) e = &g;
+		const uint64_t now = ++ctx_->chain_tick;
+		if (e && e->state == 1) {
+			e->last_use = now;
+			ctx_->launches += e->launches;
+			PXB_CUDA(cudaGraphLaunch(e->exec, ctx_->stream));
+			return PXB_OK;
+		}
+		if (e && e->state == 2) return enqueue();
+		if (!e) { // first sight: run it plainly (this is also where scratch buffers grow), remember the signature
+			if (cache.size() >= 48) { // evict the least recently used entry
+				size_t victim = 0;
+				for (size_t i = 1; i < cache.size(); ++i)
+					if (cache[i].last_use < cache[victim].last_use) victim = i;
+				if (cache[victim].exec) cudaGraphExecDestroy(cache[victim].exec);
+				cache.erase(cache.begin() + victim);
+			}
+			pxb_ctx::ChainGraph g;
+			g.key = key;
+			g.last_use = now;
+			cache.push_back(g);
+			return enqueue();
+		}
+		// second sight: capture
+		e->last_use = now;
+		const int64_t launches0 = ctx_->launches;
+		if (cudaStreamBeginCapture(ctx_->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+			(void)cudaGetLastError();
+			e->state = 2;
+			return enqueue();
+		}
+		const int rc = enqueue();
+		cudaGraph_t graph = nullptr;
+		const cudaError_t ce = cudaStreamEndCapture(ctx_->stream, &graph);
+		if (rc != PXB_OK || ce != cudaSuccess || !graph) {
+			(void)cudaGetLastError();
+			if (graph) cudaGraphDestroy(graph);
+			e->state = 2;
+			ctx_->launches = launches0;
+			return enqueue(); // nothing was executed during the failed capture
+		}
+		cudaGraphExec_t exec = nullptr;
+		const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+		cudaGraphDestroy(graph);
+		if (ie != cudaSuccess || !exec) {
+			(void)cudaGetLastError();
+			e->state = 2;
+			ctx_->launches = launches0;
+			return enqueue();
+		}
+		e->exec = exec;
+		e->state = 1;
+		e->launches = (int)(ctx_->launches - launches0);
+		PXB_CUDA(cudaGraphLaunch(e->exec, ctx_->stream));
+		return PXB_OK;
+	}
 	int64_t smooth_edges_ = -1; // directed non-loop entries of the neighbour lists (counted once per graph)
 	// Estimator::nonMinimalSampleSize(): H four-point 4, F bundle-adjustment solver 7, PnP bundle adjustment 4,
 	// vanishing point / 2D line: the minimal solver doubles as the non-minimal one, 2
@@ -971,42 +1086,66 @@ size_t Driver::iteration_number_for(size_t inliers, double log_probability) cons
 int Driver::lo_step(const double *model, uint64_t lo_seed, uint64_t event, double T2, LoStep &out) {
 	Scoped t(prof_, "lo_step");
 	const int trials = (int)s_.max_local_optimization_number, limit = 7 * m_; // estimator.inlierLimit()
-	PXB_TRY(ctx_->models.reserve(sizeof(double) * ms_));
-	PXB_TRY(api_h2d(ctx_, ctx_->models.ptr, model, sizeof(double) * ms_));
-	uint8_t *d_seg = nullptr;
-	int32_t *d_mf_flags = nullptr;
-	if (!(s_.lambda > 0) || graph_.idx.empty()) { // no smoothness term: the st-cut decomposes per node (k_lo_unary_cut)
-		PXB_TRY(ctx_->outA.reserve((size_t)N_));
-		d_seg = ctx_->outA.as<uint8_t>();
-		PXB_TRY(launch_lo_unary_cut(ctx_, ctx_->models.as<double>(), s_.threshold, s_.lambda, d_seg));
-	} else {
-		PXB_TRY(lo_labeling_enqueue(ctx_, ctx_->models.as<double>(), s_.threshold, s_.lambda, graph_.off.data(), graph_.idx.data(),
-		                            &d_seg, &d_mf_flags));
-	}
-	// lists: inliers [N] | off [trials + 1] | idx [max(N, trials * limit)]
+	const bool cut = s_.lambda > 0 && !graph_.idx.empty(); // st-cut (else the cut decomposes per node: k_lo_unary_cut)
+	// inputs: model | seed, event; lists: inliers [N] | off [trials + 1] | idx [max(N, trials * limit)]
+	const size_t in_bytes = sizeof(double) * ms_ + 2 * sizeof(uint64_t);
 	const size_t n_idx = std::max((size_t)N_, (size_t)trials * limit);
-	PXB_TRY(ctx_->idx.reserve(sizeof(int32_t) * ((size_t)N_ + trials + 1 + n_idx) + 64));
-	int32_t *d_inl = ctx_->idx.as<int32_t>(), *d_off = d_inl + N_, *d_idx = d_off + trials + 1;
 	// packed results: count | max-flow flags [16] | fitted [trials ms] | count / value / shared [trials] | ok [trials]
 	const size_t bM = sizeof(double) * (size_t)trials * ms_, bT = sizeof(double) * (size_t)trials;
 	const size_t o_flags = 8, o_fit = o_flags + 64, o_cnt = o_fit + bM, o_val = o_cnt + bT, o_shr = o_val + bT, o_ok = o_shr + bT,
 	             pack_bytes = o_ok + sizeof(int32_t) * (size_t)trials;
+	PXB_TRY(ctx_->chain_par.reserve(in_bytes));
+	PXB_TRY(ctx_->outA.reserve((size_t)N_));
+	PXB_TRY(ctx_->idx.reserve(sizeof(int32_t) * ((size_t)N_ + trials + 1 + n_idx) + 64));
 	PXB_TRY(ctx_->pack.reserve(pack_bytes));
-	char *pk = ctx_->pack.as<char>();
-	PXB_CUDA(cudaMemsetAsync(pk, 0, pack_bytes, ctx_->stream));
-	PXB_TRY(launch_flag_compact(ctx_, d_seg, N_, d_inl, reinterpret_cast<int64_t *>(pk), nullptr));
-	// (the labelling's scratch is shared with the score kernel's partial sums: take its status words now)
-	if (d_mf_flags) PXB_CUDA(cudaMemcpyAsync(pk + o_flags, d_mf_flags, 64, cudaMemcpyDeviceToDevice, ctx_->stream));
-	PXB_TRY(launch_lo_sample(ctx_, d_inl, reinterpret_cast<int64_t *>(pk), m_, limit, trials, lo_seed, event, d_off, d_idx));
-	PXB_TRY(launch_fit_family(trials, d_off, d_idx, nullptr, reinterpret_cast<double *>(pk + o_fit), reinterpret_cast<int32_t *>(pk + o_ok)));
-	PXB_TRY(launch_score_compound(ctx_, reinterpret_cast<double *>(pk + o_fit), trials, T2, compound_dev(),
-	                              reinterpret_cast<int64_t *>(pk + o_cnt), reinterpret_cast<double *>(pk + o_val),
-	                              reinterpret_cast<double *>(pk + o_shr)));
+	const bool slots = chain_slots(in_bytes, pack_bytes);
+	chain_tmp_in_.resize(in_bytes);
+	unsigned char *hin = slots ? ctx_->chain_in : chain_tmp_in_.data();
+	std::memcpy(hin, model, sizeof(double) * ms_);
+	const uint64_t se[2] = {lo_seed, event};
+	std::memcpy(hin + sizeof(double) * ms_, se, sizeof(se));
 	pack_host_.resize(pack_bytes);
-	PXB_TRY(api_d2h(ctx_, pack_host_.data(), pk, pack_bytes));
+	unsigned char *hout = slots ? ctx_->chain_out : pack_host_.data();
+	auto enqueue = [&]() -> int {
+		char *par = ctx_->chain_par.as<char>();
+		const double *d_model = reinterpret_cast<const double *>(par);
+		const uint64_t *d_se = reinterpret_cast<const uint64_t *>(par + sizeof(double) * ms_);
+		int32_t *d_inl = ctx_->idx.as<int32_t>(), *d_off = d_inl + N_, *d_idx = d_off + trials + 1;
+		char *pk = ctx_->pack.as<char>();
+		if (slots)
+			PXB_CUDA(cudaMemcpyAsync(par, hin, in_bytes, cudaMemcpyHostToDevice, ctx_->stream));
+		else
+			PXB_TRY(api_h2d(ctx_, par, hin, in_bytes));
+		uint8_t *d_seg = nullptr;
+		int32_t *d_mf_flags = nullptr;
+		if (!cut) {
+			d_seg = ctx_->outA.as<uint8_t>();
+			PXB_TRY(launch_lo_unary_cut(ctx_, d_model, s_.threshold, s_.lambda, d_seg));
+		} else {
+			PXB_TRY(lo_labeling_enqueue(ctx_, d_model, s_.threshold, s_.lambda, graph_.off.data(), graph_.idx.data(), &d_seg, &d_mf_flags));
+		}
+		PXB_CUDA(cudaMemsetAsync(pk, 0, pack_bytes, ctx_->stream));
+		PXB_TRY(launch_flag_compact(ctx_, d_seg, N_, d_inl, reinterpret_cast<int64_t *>(pk), nullptr));
+		// (the labelling's scratch is shared with the score kernel's partial sums: take its status words now)
+		if (d_mf_flags) PXB_CUDA(cudaMemcpyAsync(pk + o_flags, d_mf_flags, 64, cudaMemcpyDeviceToDevice, ctx_->stream));
+		PXB_TRY(launch_lo_sample(ctx_, d_inl, reinterpret_cast<int64_t *>(pk), m_, limit, trials, d_se, d_off, d_idx));
+		PXB_TRY(launch_fit_family(trials, d_off, d_idx, nullptr, reinterpret_cast<double *>(pk + o_fit), reinterpret_cast<int32_t *>(pk + o_ok)));
+		PXB_TRY(launch_score_compound(ctx_, reinterpret_cast<double *>(pk + o_fit), trials, T2, compound_dev(),
+		                              reinterpret_cast<int64_t *>(pk + o_cnt), reinterpret_cast<double *>(pk + o_val),
+		                              reinterpret_cast<double *>(pk + o_shr)));
+		if (slots)
+			PXB_CUDA(cudaMemcpyAsync(hout, pk, pack_bytes, cudaMemcpyDeviceToHost, ctx_->stream));
+		else
+			PXB_TRY(api_d2h(ctx_, hout, pk, pack_bytes));
+		return PXB_OK;
+	};
+	if (slots && !cut) // the st-cut runs a cooperative kernel over a cached skeleton: left out of the graphs
+		PXB_TRY(run_chain(mix_key({kChainLo, buffers_key(), (uint64_t)trials, (uint64_t)limit, bits(T2), bits(s_.threshold), bits(s_.lambda)}), enqueue));
+	else
+		PXB_TRY(enqueue());
 	PXB_TRY(api_sync(ctx_));
-	const unsigned char *h = pack_host_.data();
-	if (d_mf_flags) {
+	const unsigned char *h = hout;
+	if (cut) {
 		const int32_t *f = reinterpret_cast<const int32_t *>(h + o_flags);
 		if (f[7] != 1 || f[6] == 0) {
 			set_error("max-flow of the local optimisation did not converge");
@@ -1066,33 +1205,53 @@ int Driver::local_optimization(uint64_t lo_seed, std::vector<double> &best_model
 int Driver::tail_step(const double *model, bool weighted, double T2, TailStep &out) {
 	Scoped t(prof_, "tail_step");
 	const int64_t words = (N_ + 31) / 32;
-	PXB_TRY(ctx_->models.reserve(sizeof(double) * ms_));
-	PXB_TRY(api_h2d(ctx_, ctx_->models.ptr, model, sizeof(double) * ms_));
-	PXB_TRY(ctx_->mask.reserve(sizeof(uint32_t) * (size_t)words));
-	PXB_TRY(launch_residual_matrix(ctx_, ctx_->models.as<double>(), 1, T2, nullptr, nullptr, ctx_->mask.as<uint32_t>()));
-	PXB_TRY(ctx_->idx.reserve(sizeof(int32_t) * ((size_t)N_ + 2) + 64));
-	int32_t *d_off = ctx_->idx.as<int32_t>(), *d_inl = d_off + 2;
+	const size_t in_bytes = sizeof(double) * ms_;
 	// packed results: count | fitted [ms] | count / value / shared of the fit | ok
 	const size_t o_fit = 8, o_cnt = o_fit + sizeof(double) * ms_, o_val = o_cnt + 8, o_shr = o_val + 8, o_ok = o_shr + 8,
 	             pack_bytes = o_ok + 8;
+	PXB_TRY(ctx_->chain_par.reserve(in_bytes));
+	PXB_TRY(ctx_->mask.reserve(sizeof(uint32_t) * (size_t)words));
+	PXB_TRY(ctx_->idx.reserve(sizeof(int32_t) * ((size_t)N_ + 2) + 64));
 	PXB_TRY(ctx_->pack.reserve(pack_bytes));
-	char *pk = ctx_->pack.as<char>();
-	PXB_CUDA(cudaMemsetAsync(pk, 0, pack_bytes, ctx_->stream));
-	PXB_TRY(launch_mask_compact(ctx_, ctx_->mask.as<uint32_t>(), N_, d_inl, reinterpret_cast<int64_t *>(pk), d_off));
-	double *d_w = nullptr;
-	if (weighted) {
-		PXB_TRY(ctx_->pref2.reserve(sizeof(double) * (size_t)N_));
-		d_w = ctx_->pref2.as<double>();
-		PXB_TRY(launch_tukey(ctx_, ctx_->models.as<double>(), T2, d_w));
-	}
-	PXB_TRY(launch_fit_family(1, d_off, d_inl, d_w, reinterpret_cast<double *>(pk + o_fit), reinterpret_cast<int32_t *>(pk + o_ok)));
-	PXB_TRY(launch_score_compound(ctx_, reinterpret_cast<double *>(pk + o_fit), 1, T2, compound_dev(),
-	                              reinterpret_cast<int64_t *>(pk + o_cnt), reinterpret_cast<double *>(pk + o_val),
-	                              reinterpret_cast<double *>(pk + o_shr)));
+	if (weighted) PXB_TRY(ctx_->pref2.reserve(sizeof(double) * (size_t)N_));
+	const bool slots = chain_slots(in_bytes, pack_bytes);
+	chain_tmp_in_.resize(in_bytes);
+	unsigned char *hin = slots ? ctx_->chain_in : chain_tmp_in_.data();
+	std::memcpy(hin, model, in_bytes);
 	pack_host_.resize(pack_bytes);
-	PXB_TRY(api_d2h(ctx_, pack_host_.data(), pk, pack_bytes));
+	unsigned char *hout = slots ? ctx_->chain_out : pack_host_.data();
+	auto enqueue = [&]() -> int {
+		double *d_model = ctx_->chain_par.as<double>();
+		int32_t *d_off = ctx_->idx.as<int32_t>(), *d_inl = d_off + 2;
+		char *pk = ctx_->pack.as<char>();
+		if (slots)
+			PXB_CUDA(cudaMemcpyAsync(d_model, hin, in_bytes, cudaMemcpyHostToDevice, ctx_->stream));
+		else
+			PXB_TRY(api_h2d(ctx_, d_model, hin, in_bytes));
+		PXB_TRY(launch_residual_matrix(ctx_, d_model, 1, T2, nullptr, nullptr, ctx_->mask.as<uint32_t>()));
+		PXB_CUDA(cudaMemsetAsync(pk, 0, pack_bytes, ctx_->stream));
+		PXB_TRY(launch_mask_compact(ctx_, ctx_->mask.as<uint32_t>(), N_, d_inl, reinterpret_cast<int64_t *>(pk), d_off));
+		double *d_w = nullptr;
+		if (weighted) {
+			d_w = ctx_->pref2.as<double>();
+			PXB_TRY(launch_tukey(ctx_, d_model, T2, d_w));
+		}
+		PXB_TRY(launch_fit_family(1, d_off, d_inl, d_w, reinterpret_cast<double *>(pk + o_fit), reinterpret_cast<int32_t *>(pk + o_ok)));
+		PXB_TRY(launch_score_compound(ctx_, reinterpret_cast<double *>(pk + o_fit), 1, T2, compound_dev(),
+		                              reinterpret_cast<int64_t *>(pk + o_cnt), reinterpret_cast<double *>(pk + o_val),
+		                              reinterpret_cast<double *>(pk + o_shr)));
+		if (slots)
+			PXB_CUDA(cudaMemcpyAsync(hout, pk, pack_bytes, cudaMemcpyDeviceToHost, ctx_->stream));
+		else
+			PXB_TRY(api_d2h(ctx_, hout, pk, pack_bytes));
+		return PXB_OK;
+	};
+	if (slots)
+		PXB_TRY(run_chain(mix_key({kChainTail, buffers_key(), (uint64_t)weighted, bits(T2)}), enqueue));
+	else
+		PXB_TRY(enqueue());
 	PXB_TRY(api_sync(ctx_));
-	const unsigned char *h = pack_host_.data();
+	const unsigned char *h = hout;
 	std::memcpy(&out.inliers, h, 8);
 	out.fitted.assign(reinterpret_cast<const double *>(h + o_fit), reinterpret_cast<const double *>(h + o_fit) + ms_);
 	std::memcpy(&out.cnt, h + o_cnt, 8);
@@ -1326,43 +1485,68 @@ int Driver::pearl() {
 		Scoped tl(prof_, "pearl iteration");
 		std::vector<double> flat((size_t)L * ms_);
 		for (int64_t l = 0; l < L; ++l) std::copy(models_[l].model.begin(), models_[l].model.end(), flat.begin() + l * ms_);
-		PXB_TRY(ctx_->models.reserve(sizeof(double) * (size_t)L * ms_));
-		PXB_TRY(api_h2d(ctx_, ctx_->models.ptr, flat.data(), sizeof(double) * (size_t)L * ms_));
-		PXB_TRY(ctx_->staging.reserve(sizeof(double) * (size_t)N_ * (L + 1)));
-		PXB_TRY(launch_pearl_datacost(ctx_, ctx_->models.as<double>(), L, s_.threshold, s_.lambda, ctx_->staging.as<double>()));
-		const int32_t *init = nullptr;
-		if (init_with_previous && have_labels) { // no instance was rejected: the previous labels are valid for L + 1 labels
-			PXB_CUDA(cudaMemcpyAsync(lab_prev, lab_cur, sizeof(int32_t) * (size_t)N_, cudaMemcpyDeviceToDevice, ctx_->stream));
-			init = lab_prev;
-		}
+		const bool init_prev = init_with_previous && have_labels; // no instance was rejected: the previous labels are valid
 		// packed results: energy | before[L] | after[L] | counts[L] | counts2[L] | fitted[L ms] | cand[L ms] | ok[L]
 		const size_t bL = sizeof(double) * (size_t)L, bM = sizeof(double) * (size_t)L * ms_;
 		const size_t o_before = 8, o_after = o_before + bL, o_cnt = o_after + bL, o_cnt2 = o_cnt + bL, o_fit = o_cnt2 + bL,
 		             o_cand = o_fit + bM, o_ok = o_cand + bM, pack_bytes = o_ok + sizeof(int32_t) * (size_t)L;
+		PXB_TRY(ctx_->chain_par.reserve(bM));
+		PXB_TRY(ctx_->staging.reserve(sizeof(double) * (size_t)N_ * (L + 1)));
 		PXB_TRY(ctx_->pack.reserve(pack_bytes));
-		char *pk = ctx_->pack.as<char>();
-		double *energy_dev = nullptr;
-		PXB_TRY(pearl_label_enqueue(ctx_, ctx_->staging.as<double>(), N_, (int32_t)(L + 1), s_.lambda, label_cost,
-		                            smooth ? graph_.off.data() : nullptr, smooth ? graph_.idx.data() : nullptr, smooth ? smooth_edges_ : 0,
-		                            init, lab_cur, &energy, &energy_dev));
-		have_labels = true;
-		if (energy_dev) PXB_CUDA(cudaMemcpyAsync(pk, energy_dev, sizeof(double), cudaMemcpyDeviceToDevice, ctx_->stream));
-		// ---- parameterEstimation ----
 		PXB_TRY(ctx_->idx.reserve(sizeof(int32_t) * ((size_t)N_ + (size_t)L + 1) + 64));
-		int32_t *d_off = ctx_->idx.as<int32_t>(), *d_idx = d_off + (L + 1);
-		PXB_TRY(launch_label_lists(ctx_, lab_cur, N_, (int)L, d_off, d_idx));
-		PXB_TRY(launch_segment_sums(ctx_, ctx_->models.as<double>(), L, lab_cur, reinterpret_cast<double *>(pk + o_before),
-		                            reinterpret_cast<int64_t *>(pk + o_cnt)));
-		// instances with fewer points than nonMinimalSampleSize() are not refitted (:363-365): the solvers report !ok for them
-		PXB_TRY(launch_fit_family((int)L, d_off, d_idx, d_w, reinterpret_cast<double *>(pk + o_fit), reinterpret_cast<int32_t *>(pk + o_ok)));
-		PXB_TRY(launch_select_models(ctx_, ctx_->models.as<double>(), reinterpret_cast<double *>(pk + o_fit),
-		                             reinterpret_cast<int32_t *>(pk + o_ok), (int)L, ms_, reinterpret_cast<double *>(pk + o_cand)));
-		PXB_TRY(launch_segment_sums(ctx_, reinterpret_cast<double *>(pk + o_cand), L, lab_cur, reinterpret_cast<double *>(pk + o_after),
-		                            reinterpret_cast<int64_t *>(pk + o_cnt2)));
+		const bool slots = chain_slots(bM, pack_bytes);
+		chain_tmp_in_.resize(bM);
+		unsigned char *hin = slots ? ctx_->chain_in : chain_tmp_in_.data();
+		std::memcpy(hin, flat.data(), bM);
 		pack_host_.resize(pack_bytes);
-		PXB_TRY(api_d2h(ctx_, pack_host_.data(), pk, pack_bytes));
+		unsigned char *hout = slots ? ctx_->chain_out : pack_host_.data();
+		double *energy_dev = nullptr;
+		auto enqueue = [&]() -> int {
+			double *d_models = ctx_->chain_par.as<double>();
+			char *pk = ctx_->pack.as<char>();
+			if (slots)
+				PXB_CUDA(cudaMemcpyAsync(d_models, hin, bM, cudaMemcpyHostToDevice, ctx_->stream));
+			else
+				PXB_TRY(api_h2d(ctx_, d_models, hin, bM));
+			PXB_TRY(launch_pearl_datacost(ctx_, d_models, L, s_.threshold, s_.lambda, ctx_->staging.as<double>()));
+			const int32_t *init = nullptr;
+			if (init_prev) {
+				PXB_CUDA(cudaMemcpyAsync(lab_prev, lab_cur, sizeof(int32_t) * (size_t)N_, cudaMemcpyDeviceToDevice, ctx_->stream));
+				init = lab_prev;
+			}
+			PXB_TRY(pearl_label_enqueue(ctx_, ctx_->staging.as<double>(), N_, (int32_t)(L + 1), s_.lambda, label_cost,
+			                            smooth ? graph_.off.data() : nullptr, smooth ? graph_.idx.data() : nullptr, smooth ? smooth_edges_ : 0,
+			                            init, lab_cur, &energy, &energy_dev));
+			if (energy_dev) PXB_CUDA(cudaMemcpyAsync(pk, energy_dev, sizeof(double), cudaMemcpyDeviceToDevice, ctx_->stream));
+			// ---- parameterEstimation ----
+			int32_t *d_off = ctx_->idx.as<int32_t>(), *d_idx = d_off + (L + 1);
+			PXB_TRY(launch_label_lists(ctx_, lab_cur, N_, (int)L, d_off, d_idx));
+			PXB_TRY(launch_segment_sums(ctx_, d_models, L, lab_cur, reinterpret_cast<double *>(pk + o_before),
+			                            reinterpret_cast<int64_t *>(pk + o_cnt)));
+			// instances with fewer points than nonMinimalSampleSize() are not refitted (:363-365): the solvers report !ok for them
+			PXB_TRY(launch_fit_family((int)L, d_off, d_idx, d_w, reinterpret_cast<double *>(pk + o_fit), reinterpret_cast<int32_t *>(pk + o_ok)));
+			PXB_TRY(launch_select_models(ctx_, d_models, reinterpret_cast<double *>(pk + o_fit), reinterpret_cast<int32_t *>(pk + o_ok),
+			                             (int)L, ms_, reinterpret_cast<double *>(pk + o_cand)));
+			PXB_TRY(launch_segment_sums(ctx_, reinterpret_cast<double *>(pk + o_cand), L, lab_cur, reinterpret_cast<double *>(pk + o_after),
+			                            reinterpret_cast<int64_t *>(pk + o_cnt2)));
+			if (slots)
+				PXB_CUDA(cudaMemcpyAsync(hout, pk, pack_bytes, cudaMemcpyDeviceToHost, ctx_->stream));
+			else
+				PXB_TRY(api_d2h(ctx_, hout, pk, pack_bytes));
+			return PXB_OK;
+		};
+		// replayable when the sweep is the single-block greedy kernel (no smoothness term, N <= 16384: the alpha-expansion has
+		// a host move loop, the multi-block greedy sweep is a cooperative launch)
+		if (slots && !smooth && N_ <= 16384) {
+			PXB_TRY(run_chain(mix_key({kChainPearl, buffers_key(), (uint64_t)L, (uint64_t)init_prev, bits(s_.threshold), bits(s_.lambda),
+			                           bits(label_cost), bits(d_w)}), enqueue));
+			energy_dev = ctx_->outB.as<double>(); // the greedy sweep's energy sits in the pack (replays do not run the lambda)
+		} else {
+			PXB_TRY(enqueue());
+		}
+		have_labels = true;
 		PXB_TRY(api_sync(ctx_));
-		const unsigned char *h = pack_host_.data();
+		const unsigned char *h = hout;
 		if (energy_dev) std::memcpy(&energy, h, sizeof(double));
 		const double *before = reinterpret_cast<const double *>(h + o_before), *after = reinterpret_cast<const double *>(h + o_after);
 		const double *fitted = reinterpret_cast<const double *>(h + o_fit);
@@ -1381,7 +1565,7 @@ int Driver::pearl() {
 		}
 		if (s_.do_logging) {
 			fprintf(stdout, "[pxb]   PEARL it %zu: L=%lld energy %.4f (prev %.4f) init=%d points per instance:", iteration_number,
-			        (long long)L, energy, previous_energy, init ? 1 : 0);
+			        (long long)L, energy, previous_energy, init_prev ? 1 : 0);
 			for (int64_t l = 0; l < L; ++l) fprintf(stdout, " %lld", (long long)counts[l]);
 			fprintf(stdout, " outliers %zu%s\n", outliers, model_parameters_changed ? " (refit accepted)" : "");
 		}

@@ -123,10 +123,26 @@ struct pxb_ctx {
 	pxb_multi_model_statistics last_statistics = {};
 	cudaEvent_t timing_events[4 * PXB_MAX_ROUNDS + 2] = {};
 	bool timing_events_ready = false;
+	// Replayable device chains (pxb_driver.cu run_chain): the loops of the driver issue the same fixed sequence of copies
+	// and kernels again and again; the second time a sequence with the same signature is seen it is captured into a CUDA
+	// graph and from then on replayed with ONE launch. Inputs travel through a fixed pinned slot (chain_in -> chain_par on
+	// the device), results come back into another (chain_out).
+	struct ChainGraph {
+		uint64_t key = 0;
+		cudaGraphExec_t exec = nullptr;
+		int state = 0; // 0: seen once (not captured yet), 1: captured, 2: cannot be captured
+		int launches = 0;
+		uint64_t last_use = 0;
+	};
+	std::vector<ChainGraph> chain_graphs;
+	uint64_t chain_tick = 0;
+	unsigned char *chain_in = nullptr, *chain_out = nullptr; // pinned, kChainInBytes / kChainOutBytes
+	pxb::DevBuf chain_par;
 	pxb::DevBuf labels, pack; // PEARL labels (kept on the device between iterations) and the packed per-call results
 };
 
 namespace pxb {
+constexpr size_t kChainInBytes = size_t(256) << 10, kChainOutBytes = size_t(1) << 20;
 void lo_skeleton_free(void *p);
 void exp_skeleton_free(void *p);
 uint64_t csr_content_key(pxb_ctx *ctx, int64_t N, const int32_t *off, const int32_t *idx);
@@ -151,8 +167,9 @@ int pearl_label_enqueue(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t L1
                         int32_t *labels_out_dev, double *energy_host, double **energy_dev_out);
 int launch_flag_compact(pxb_ctx *ctx, const uint8_t *flags_dev, int64_t N, int32_t *idx_dev, int64_t *count_dev, int32_t *off2_dev);
 int launch_mask_compact(pxb_ctx *ctx, const uint32_t *mask_dev, int64_t N, int32_t *idx_dev, int64_t *count_dev, int32_t *off2_dev);
-int launch_lo_sample(pxb_ctx *ctx, const int32_t *inl_dev, const int64_t *count_dev, int m, int limit, int trials, uint64_t seed,
-                     uint64_t event, int32_t *off_dev, int32_t *idx_dev);
+// seed_event_dev: two uint64 on the device (generator seed of the proposal's LO sampler, index of this LO labelling)
+int launch_lo_sample(pxb_ctx *ctx, const int32_t *inl_dev, const int64_t *count_dev, int m, int limit, int trials,
+                     const uint64_t *seed_event_dev, int32_t *off_dev, int32_t *idx_dev);
 // GCRANSAC::labeling with the 0/1 result left on the device (*seg_dev_out, N bytes) and the max-flow status words in
 // *flags_dev_out (16 int32; converged iff flags[7] == 1 && flags[6] != 0): asynchronous
 int lo_labeling_enqueue(pxb_ctx *ctx, const double *model_dev, double thr, double lambda, const int32_t *csr_off_host,
