@@ -35,6 +35,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -42,26 +43,12 @@
 #include <vector>
 
 #include "pxb_internal.h"
+#include "pxb_maxflow.h"
 
 namespace cg = cooperative_groups;
 
 namespace pxb {
 
-struct FlowGraphDev {
-	int n, m;
-	int wide_begin, wide_count; // nodes [wide_begin, wide_begin + wide_count) are label-cost auxiliary nodes: thousands
-	                            // of arcs each, handled by a whole thread block instead of one owner thread
-	const int32_t *arc_off, *arc_head, *arc_rev;
-	double *cap, *excess, *sink_cap;
-	int32_t *height[2];
-	int32_t *flags; // [0..2] BFS 'changed' (level mod 3), [3..5] 'active' (pulse mod 3), [6] pulses, [7] status
-	int async_cycles, idle_checks; // tuning knobs of the asynchronous phase (PXB_MF_ASYNC, PXB_MF_IDLE)
-	int local_exit;                // PXB_MF_LOCAL_EXIT=1: blocks leave the phase on their own (A/B)
-	long long quiet_cycles;        // PXB_MF_QUIET_US: grid-wide silence that ends the phase
-	int debug;      // PXB_MF_STATS=3: block 0 prints the number of active nodes after every relabel
-	int block_bfs;  // 1/2/3: the launch carries 2n / 3n+1 / 4n+1 ints of dynamic shared memory and block 0 runs the global
-	                // relabel alone (2: CSR offsets in shared memory, 3: and bottom-up levels)
-};
 
 #ifndef PXB_MF_THREADS
 #define PXB_MF_THREADS 1024
@@ -931,7 +918,17 @@ struct LoSkeleton {
 	DevBuf buf; // arc_off[N+1] arc_head[m] arc_rev[m] pair_j[p] pair_fwd[p] pair_rev[p] first_off[N+1]
 	int32_t *arc_off = nullptr, *arc_head = nullptr, *arc_rev = nullptr, *pair_j = nullptr, *pair_fwd = nullptr,
 	        *pair_rev = nullptr, *first_off = nullptr;
+	std::vector<int32_t> arc_off_host; // for the launch plan of the cluster-resident engine
+	McPlan plan;
+	uint64_t plan_key = ~0ull;
 };
+
+// The launch plan of k_maxflow_cluster depends on the arc skeleton and on three tuning switches only: cached with the
+// skeleton, recomputed when a switch changes (tests flip them).
+static uint64_t mc_env_key() {
+	auto val = [](const char *name) { const char *e = getenv(name); return e ? (uint64_t)(atoi(e) + 1) : 0ull; };
+	return val("PXB_MF_CLUSTER") * 1000003ull + val("PXB_MC_CSIZE") * 10007ull + val("PXB_MC_SMEM_KB");
+}
 
 // 64-bit-word multiply-xor hash of the CSR arrays (the cache key of the skeleton; ~10 GB/s on the host)
 static uint64_t fnv1a(const void *data, size_t bytes, uint64_t h = 1469598103934665603ull) {
@@ -1021,6 +1018,8 @@ static int lo_skeleton(pxb_ctx *ctx, int64_t N, const int32_t *off, const int32_
 	g_lo.key = key;
 	g_lo.N = N;
 	g_lo.pairs = pairs;
+	g_lo.arc_off_host = aoff;
+	g_lo.plan_key = ~0ull;
 	return PXB_OK;
 }
 
@@ -1072,7 +1071,11 @@ int lo_labeling_enqueue(pxb_ctx *ctx, const double *model_dev, double thr, doubl
                         const int32_t *csr_idx_host, uint8_t **seg_dev_out, int32_t **flags_dev_out) {
 	const int64_t N = ctx->pts.N;
 	PXB_TRY(lo_skeleton(ctx, N, csr_off_host, csr_idx_host));
-	const LoSkeleton &g_lo = *static_cast<LoSkeleton *>(ctx->lo_skeleton);
+	LoSkeleton &g_lo = *static_cast<LoSkeleton *>(ctx->lo_skeleton);
+	if (g_lo.plan_key != mc_env_key()) {
+		PXB_TRY(mf_cluster_plan(ctx, (int)N, 0, g_lo.arc_off_host.data(), g_lo.plan));
+		g_lo.plan_key = mc_env_key();
+	}
 	const int n = (int)N, m = std::max(2 * g_lo.pairs, 1);
 	const size_t bytes = sizeof(double) * ((size_t)m + 5 * (size_t)n) + sizeof(int32_t) * (2 * (size_t)n + 16) + (size_t)n + 256;
 	PXB_TRY(ctx->partials.reserve(bytes));
@@ -1100,12 +1103,16 @@ int lo_labeling_enqueue(pxb_ctx *ctx, const double *model_dev, double thr, doubl
 	G.height[0] = d_h0;
 	G.height[1] = d_h1;
 	G.flags = d_flags;
-	MfLaunch lc;
-	PXB_TRY(mf_launch_config(ctx, G, 1, lc));
-	const int grid = lc.grid;
-	void *args[] = {&G};
-	PXB_CUDA(cudaLaunchCooperativeKernel((void *)k_maxflow, dim3(grid), dim3(kMfThreads), args, lc.smem, st));
-	ctx->launches++;
+	if (g_lo.plan.ok) { // the graph fits into one thread-block cluster (pxb_maxflow_cluster.cu)
+		PXB_TRY(mf_cluster_launch(ctx, G, g_lo.plan));
+	} else {
+		MfLaunch lc;
+		PXB_TRY(mf_launch_config(ctx, G, 1, lc));
+		const int grid = lc.grid;
+		void *args[] = {&G};
+		PXB_CUDA(cudaLaunchCooperativeKernel((void *)k_maxflow, dim3(grid), dim3(kMfThreads), args, lc.smem, st));
+		ctx->launches++;
+	}
 	k_lo_collect<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(N, d_h0, n, d_seg);
 	ctx->launches++;
 	*seg_dev_out = d_seg;
@@ -1314,6 +1321,9 @@ struct ExpSkeleton {
 	uint64_t key = 0;
 	int64_t N = 0, E = 0;
 	std::vector<int32_t> goff, gidx; // host: gco neighbour lists (also read by compute_energy / EnergyCache)
+	std::vector<int32_t> arc_off_host; // site arc offsets (list entries + one auxiliary arc per site)
+	McPlan plan;                       // launch plan of the cluster-resident engine (per label count: n_aux <= 16 only)
+	uint64_t plan_key = ~0ull;
 	DevBuf buf;                      // arc_off[N+1] head[E+N] rev[E+N] goff[N+1] gidx[E]
 	int32_t *arc_off = nullptr, *head = nullptr, *rev = nullptr, *d_goff = nullptr, *d_gidx = nullptr;
 };
@@ -1383,6 +1393,8 @@ static int exp_skeleton(pxb_ctx *ctx, int64_t N, const int32_t *off, const int32
 	sk.key = key;
 	sk.N = N;
 	sk.E = E;
+	sk.arc_off_host = arc_off;
+	sk.plan_key = ~0ull;
 	return PXB_OK;
 }
 
@@ -1468,6 +1480,12 @@ int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t
 	MfLaunch lc;
 	PXB_TRY(mf_launch_config(ctx, G, std::min(L1, ctx->sm_count), lc));
 	const int grid = lc.grid;
+	// graphs that fit run on the cluster-resident engine (pxb_maxflow_cluster.cu)
+	if (sk.plan_key != mc_env_key() + (uint64_t)L1 * 0x9E3779B97F4A7C15ull) {
+		PXB_TRY(mf_cluster_plan(ctx, (int)N, L1, sk.arc_off_host.data(), sk.plan));
+		sk.plan_key = mc_env_key() + (uint64_t)L1 * 0x9E3779B97F4A7C15ull;
+	}
+	const bool use_cluster = sk.plan.ok;
 	PXB_TRY(ctx->reserve_pinned(sizeof(int32_t) * ((size_t)n + 16)));
 	int32_t *h_host = static_cast<int32_t *>(ctx->pinned), *flags_host = h_host + n;
 
@@ -1483,9 +1501,14 @@ int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t
 			const auto t_move = std::chrono::steady_clock::now();
 			k_exp_assemble<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(N, L1, alpha, lambda, label_cost, D_dev, d_lab, d_goff, d_gidx,
 			                                                          d_label_count, d_rev, d_cap, d_excess, d_sink, d_flags);
-			void *args[] = {&G};
-			PXB_CUDA(cudaLaunchCooperativeKernel((void *)k_maxflow, dim3(grid), dim3(kMfThreads), args, lc.smem, st));
-			ctx->launches += 2;
+			ctx->launches++;
+			if (use_cluster) {
+				PXB_TRY(mf_cluster_launch(ctx, G, sk.plan));
+			} else {
+				void *args[] = {&G};
+				PXB_CUDA(cudaLaunchCooperativeKernel((void *)k_maxflow, dim3(grid), dim3(kMfThreads), args, lc.smem, st));
+				ctx->launches++;
+			}
 			PXB_CUDA(cudaMemcpyAsync(h_host, d_h0, sizeof(int32_t) * ((size_t)n + 16), cudaMemcpyDeviceToHost, st)); // + flags
 			PXB_TRY(ctx_wait(ctx));
 			if (flags_host[7] != 1 || flags_host[6] == 0) {
