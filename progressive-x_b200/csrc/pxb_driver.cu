@@ -1139,8 +1139,11 @@ int Driver::lo_step(const double *model, uint64_t lo_seed, uint64_t event, doubl
 			PXB_TRY(api_d2h(ctx_, hout, pk, pack_bytes));
 		return PXB_OK;
 	};
-	if (slots && !cut) // the st-cut runs a cooperative kernel over a cached skeleton: left out of the graphs
-		PXB_TRY(run_chain(mix_key({kChainLo, buffers_key(), (uint64_t)trials, (uint64_t)limit, bits(T2), bits(s_.threshold), bits(s_.lambda)}), enqueue));
+	// (the cooperative k_maxflow over a lazily built skeleton is left out of the graphs; the cluster-resident engine over a
+	// cached skeleton is a plain launch)
+	uint64_t cut_signature = 0;
+	if (slots && (!cut || lo_labeling_capturable(ctx_, graph_.off.data(), graph_.idx.data(), &cut_signature)))
+		PXB_TRY(run_chain(mix_key({kChainLo, buffers_key(), (uint64_t)trials, (uint64_t)limit, bits(T2), bits(s_.threshold), bits(s_.lambda), cut_signature}), enqueue));
 	else
 		PXB_TRY(enqueue());
 	PXB_TRY(api_sync(ctx_));

@@ -1120,6 +1120,22 @@ int lo_labeling_enqueue(pxb_ctx *ctx, const double *model_dev, double thr, doubl
 	return PXB_OK;
 }
 
+// True when lo_labeling_enqueue for this neighbourhood graph is a fixed sequence of plain launches (skeleton cached, cut on
+// the cluster-resident engine): the driver may then capture its local-optimisation chain into a CUDA graph.
+// *signature identifies what such a graph bakes in (the skeleton's content and buffers, the launch plan).
+bool lo_labeling_capturable(pxb_ctx *ctx, const int32_t *csr_off_host, const int32_t *csr_idx_host, uint64_t *signature) {
+	if (!ctx->lo_skeleton) return false;
+	const LoSkeleton &g_lo = *static_cast<LoSkeleton *>(ctx->lo_skeleton);
+	const int64_t N = ctx->pts.N;
+	if (!(g_lo.buf.ptr && g_lo.N == N && g_lo.key == csr_content_key(ctx, N, csr_off_host, csr_idx_host) && g_lo.plan.ok &&
+	      g_lo.plan_key == mc_env_key()))
+		return false;
+	const uint64_t parts[8] = {g_lo.key, (uint64_t)reinterpret_cast<uintptr_t>(g_lo.buf.ptr), (uint64_t)g_lo.pairs, (uint64_t)g_lo.plan.csize,
+	                           (uint64_t)g_lo.plan.sites_per_cta, (uint64_t)g_lo.plan.arcs_per_cta, (uint64_t)g_lo.plan.smem, g_lo.plan_key};
+	*signature = fnv1a(parts, sizeof(parts));
+	return true;
+}
+
 int lo_labeling_device(pxb_ctx *ctx, const double *model_dev, double thr, double lambda, const int32_t *csr_off_host,
                        const int32_t *csr_idx_host, uint8_t *seg_host) {
 	uint8_t *d_seg = nullptr;
@@ -1324,6 +1340,12 @@ struct ExpSkeleton {
 	std::vector<int32_t> arc_off_host; // site arc offsets (list entries + one auxiliary arc per site)
 	McPlan plan;                       // launch plan of the cluster-resident engine (per label count: n_aux <= 16 only)
 	uint64_t plan_key = ~0ull;
+	// The last labelling solved on this graph. PEARL's final iteration re-labels with models refitted on an unchanged
+	// labelling: data costs and initial labels are bit-identical to the previous call, and so is the result of this
+	// deterministic-up-to-exact-ties function; it is handed back instead of re-running L + 1 expansion moves.
+	uint64_t memo_key = 0;
+	std::vector<int32_t> memo_labels;
+	double memo_energy = 0;
 	DevBuf buf;                      // arc_off[N+1] head[E+N] rev[E+N] goff[N+1] gidx[E]
 	int32_t *arc_off = nullptr, *head = nullptr, *rev = nullptr, *d_goff = nullptr, *d_gidx = nullptr;
 };
@@ -1418,6 +1440,22 @@ int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t
 	PXB_TRY(exp_skeleton(ctx, N, csr_off_host, csr_idx_host, skp)); // overlaps the downloads on a cache hit
 	ExpSkeleton &sk = *skp;
 	PXB_TRY(ctx_wait(ctx));
+	uint64_t memo_key = 0;
+	if (!getenv("PXB_NO_LABEL_MEMO")) {
+		memo_key = fnv1a(D.data(), sizeof(double) * D.size(), sk.key ^ 0x5851F42D4C957F2Dull);
+		memo_key = fnv1a(lab.data(), sizeof(int32_t) * lab.size(), memo_key);
+		const double par[2] = {lambda, label_cost};
+		const int64_t dims[2] = {N, L1};
+		memo_key = fnv1a(par, sizeof(par), memo_key);
+		memo_key = fnv1a(dims, sizeof(dims), memo_key) | 1;
+		if (memo_key == sk.memo_key && (int64_t)sk.memo_labels.size() == N) {
+			*energy_out_host = sk.memo_energy;
+			PXB_CUDA(cudaMemcpyAsync(labels_out_dev, sk.memo_labels.data(), sizeof(int32_t) * (size_t)N, cudaMemcpyHostToDevice, st));
+			PXB_TRY(ctx_wait(ctx));
+			if (getenv("PXB_MF_STATS")) fprintf(stderr, "[pxb expansion] labelling: identical to the previous call (memo)\n");
+			return PXB_OK;
+		}
+	}
 
 	ExpansionProblem P;
 	P.D = D.data();
@@ -1557,6 +1595,11 @@ int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t
 	*energy_out_host = new_energy;
 	PXB_CUDA(cudaMemcpyAsync(labels_out_dev, lab.data(), sizeof(int32_t) * (size_t)N, cudaMemcpyHostToDevice, st));
 	PXB_TRY(ctx_wait(ctx));
+	if (memo_key) {
+		sk.memo_key = memo_key;
+		sk.memo_labels = lab;
+		sk.memo_energy = new_energy;
+	}
 	if (stats)
 		fprintf(stderr, "[pxb expansion] labelling: N=%lld L1=%d total %.2f ms = setup %.2f + cuts %.2f + energies %.2f + rewiring %.2f\n",
 		        (long long)N, L1, since(t_call), ms_setup, ms_cut, ms_energy, ms_push);

@@ -174,6 +174,7 @@ int launch_lo_sample(pxb_ctx *ctx, const int32_t *inl_dev, const int64_t *count_
 // *flags_dev_out (16 int32; converged iff flags[7] == 1 && flags[6] != 0): asynchronous
 int lo_labeling_enqueue(pxb_ctx *ctx, const double *model_dev, double thr, double lambda, const int32_t *csr_off_host,
                         const int32_t *csr_idx_host, uint8_t **seg_dev_out, int32_t **flags_dev_out);
+bool lo_labeling_capturable(pxb_ctx *ctx, const int32_t *csr_off_host, const int32_t *csr_idx_host, uint64_t *signature);
 int launch_label_lists(pxb_ctx *ctx, const int32_t *labels_dev, int64_t N, int L, int32_t *off_dev, int32_t *idx_dev);
 int launch_select_models(pxb_ctx *ctx, const double *current, const double *fitted, const int32_t *ok, int L, int ms,
                          double *cand);
