@@ -1521,9 +1521,12 @@ int Driver::pearl() {
 				PXB_CUDA(cudaMemcpyAsync(lab_prev, lab_cur, sizeof(int32_t) * (size_t)N_, cudaMemcpyDeviceToDevice, ctx_->stream));
 				init = lab_prev;
 			}
-			PXB_TRY(pearl_label_enqueue(ctx_, ctx_->staging.as<double>(), N_, (int32_t)(L + 1), s_.lambda, label_cost,
-			                            smooth ? graph_.off.data() : nullptr, smooth ? graph_.idx.data() : nullptr, smooth ? smooth_edges_ : 0,
-			                            init, lab_cur, &energy, &energy_dev));
+			ctx_->label_memo = true;
+			const int rc_label = pearl_label_enqueue(ctx_, ctx_->staging.as<double>(), N_, (int32_t)(L + 1), s_.lambda, label_cost,
+			                                         smooth ? graph_.off.data() : nullptr, smooth ? graph_.idx.data() : nullptr,
+			                                         smooth ? smooth_edges_ : 0, init, lab_cur, &energy, &energy_dev);
+			ctx_->label_memo = false;
+			PXB_TRY(rc_label);
 			if (energy_dev) PXB_CUDA(cudaMemcpyAsync(pk, energy_dev, sizeof(double), cudaMemcpyDeviceToDevice, ctx_->stream));
 			// ---- parameterEstimation ----
 			int32_t *d_off = ctx_->idx.as<int32_t>(), *d_idx = d_off + (L + 1);

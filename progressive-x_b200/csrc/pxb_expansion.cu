@@ -1441,7 +1441,7 @@ int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t
 	ExpSkeleton &sk = *skp;
 	PXB_TRY(ctx_wait(ctx));
 	uint64_t memo_key = 0;
-	if (!getenv("PXB_NO_LABEL_MEMO")) {
+	if (ctx->label_memo && !getenv("PXB_NO_LABEL_MEMO")) {
 		memo_key = fnv1a(D.data(), sizeof(double) * D.size(), sk.key ^ 0x5851F42D4C957F2Dull);
 		memo_key = fnv1a(lab.data(), sizeof(int32_t) * lab.size(), memo_key);
 		const double par[2] = {lambda, label_cost};

@@ -95,6 +95,10 @@ struct pxb_ctx {
 	const int32_t *trusted_csr_off = nullptr, *trusted_csr_idx = nullptr;
 	uint64_t trusted_csr_key = 0;
 	void *exp_skeleton = nullptr; // pxb_expansion.cu: cached gco adjacency + static arcs of the alpha-expansion graph
+	// set by the host driver around PEARL's labelling calls: an alpha-expansion whose data costs and initial labels are
+	// bit-identical to the previous call of the same run hands back that call's result (the standalone operator
+	// pxb_pearl_label always computes)
+	bool label_memo = false;
 	// Pinned staging arena of the host-pointer entry points: small H2D payloads are copied here first and small D2H
 	// results land here and are handed to the caller's (pageable) buffers after the stream synchronises. Pageable
 	// cudaMemcpyAsync calls are synchronous, take the driver's big lock and serialise concurrent contexts; pinned ones
