@@ -1156,8 +1156,8 @@ int Driver::lo_step(const double *model, uint64_t lo_seed, uint64_t event, doubl
 		}
 		if (const char *e = getenv("PXB_MF_STATS"))
 			if (e[0] == '2')
-				fprintf(stderr, "[pxb lo cut] rounds=%d bfs_levels=%d relabel=%.3f ms push=%.3f ms\n", f[6], f[8],
-				        (double)f[10] * 64 / 1.965e6, (double)f[12] * 64 / 1.965e6);
+				fprintf(stderr, "[pxb lo cut] rounds=%d bfs_levels=%d relabel=%.3f ms push=%.3f ms (level scans %.3f ms, votes %.3f ms)\n", f[6], f[8],
+				        (double)f[10] * 64 / 1.965e6, (double)f[12] * 64 / 1.965e6, (double)f[13] * 64 / 1.965e6, (double)f[14] * 64 / 1.965e6);
 	}
 	std::memcpy(&out.inliers, h, sizeof(int64_t));
 	out.fitted.assign(reinterpret_cast<const double *>(h + o_fit), reinterpret_cast<const double *>(h + o_fit) + (size_t)trials * ms_);

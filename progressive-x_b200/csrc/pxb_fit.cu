@@ -23,67 +23,116 @@ namespace pxb {
 // neighbourhood graph
 // ------------------------------------------------------------------------------------------------
 constexpr int kKnnMax = 16;
-constexpr int kKnnTile = 64; // N = 10^4 gives 157 blocks: one per SM (with 256 the grid had 40 blocks and the build took 1.6 ms)
+constexpr int kKnnQuery = 64; // query points per block: N = 10^4 gives 157 blocks, one per SM
 
-// The k best candidates live in registers: arrays of a compile-time size with statically indexed, fully unrolled
-// compare-and-swap insertion (dynamically indexed arrays go to local memory; with ~16 % of all points inside a 200 px
-// ball the insertion path is hot: 1.6 ms at N = 10^4 before, the whole build is a brute-force N^2 scan).
-template <int DIM, int KMAX>
-__global__ void __launch_bounds__(kKnnTile)
+// Brute force over all pairs, float64 like the reference's distances. A block serves 64 query points; the candidates of
+// a query are split into SLICES contiguous index ranges scanned by SLICES threads (64 x SLICES threads per block: a thread
+// per query left every SM with two warps of dependent FP64 chains -- 0.92 ms at N = 10^4). A warp is 32 consecutive
+// queries of ONE slice, so every candidate is a uniform (broadcast) load. The k best candidates of a thread live in
+// registers: arrays of a compile-time size with statically indexed, fully unrolled compare-and-swap insertion
+// (dynamically indexed arrays go to local memory; with ~16 % of all points inside a 200 px ball the insertion path is
+// hot). Candidates are visited in ascending index order and inserted with strict comparisons, and the slices' lists are
+// merged in slice order the same way: the result is the k smallest (distance, index) pairs -- ties go to the lower
+// index -- exactly what one sequential scan over all candidates returns.
+template <int KMAX>
+__device__ __forceinline__ void knn_insert(double (&bd)[KMAX], int (&bi)[KMAX], double &worst, double cd, int ci, int k) {
+	// the candidate goes in front of the first strictly larger entry; everything behind it moves down one slot (an entry
+	// that has been displaced is never compared again: it would leapfrog an equal neighbour and break the tie rule)
+	bool placed = false;
+#pragma unroll
+	for (int q = 0; q < KMAX; ++q) {
+		if (q < k && (placed || cd < bd[q])) {
+			const double td = bd[q];
+			const int ti = bi[q];
+			bd[q] = cd;
+			bi[q] = ci;
+			cd = td;
+			ci = ti;
+			placed = true;
+		}
+		if (q == k - 1) worst = bd[q];
+	}
+}
+
+template <int DIM> __device__ __forceinline__ double knn_dist2(const double (&me)[DIM], const double *__restrict__ pj) {
+	double c[DIM];
+	if (DIM == 4) {
+		const double2 a = __ldg(reinterpret_cast<const double2 *>(pj)), b = __ldg(reinterpret_cast<const double2 *>(pj) + 1);
+		c[0] = a.x, c[1] = a.y, c[2 % DIM] = b.x, c[3 % DIM] = b.y;
+	} else if (DIM == 2) {
+		const double2 a = __ldg(reinterpret_cast<const double2 *>(pj));
+		c[0] = a.x, c[1] = a.y;
+	} else {
+#pragma unroll
+		for (int q = 0; q < DIM; ++q) c[q] = __ldg(pj + q);
+	}
+	double d2 = 0.0;
+#pragma unroll
+	for (int q = 0; q < DIM; ++q) {
+		const double d = me[q] - c[q];
+		d2 += d * d;
+	}
+	return d2;
+}
+
+template <int DIM, int KMAX, int SLICES>
+__global__ void __launch_bounds__(kKnnQuery *SLICES)
     k_knn_graph(const double *__restrict__ aos, int64_t N, double radius2, int k, int32_t *__restrict__ nbr /*N*k*/,
                 int32_t *__restrict__ deg) {
-	__shared__ double s_pts[kKnnTile * DIM];
-	const int64_t i = (int64_t)blockIdx.x * kKnnTile + threadIdx.x;
+	__shared__ double s_d[SLICES - 1][KMAX][kKnnQuery];
+	__shared__ int s_i[SLICES - 1][KMAX][kKnnQuery];
+	const int q = threadIdx.x % kKnnQuery, slice = threadIdx.x / kKnnQuery;
+	const int64_t i = (int64_t)blockIdx.x * kKnnQuery + q;
 	double me[DIM];
 #pragma unroll
 	for (int c = 0; c < DIM; ++c) me[c] = (i < N) ? aos[i * DIM + c] : 0.0;
 	double bd[KMAX];
 	int bi[KMAX];
 #pragma unroll
-	for (int q = 0; q < KMAX; ++q) {
-		bd[q] = DBL_MAX;
-		bi[q] = -1;
+	for (int r = 0; r < KMAX; ++r) {
+		bd[r] = DBL_MAX;
+		bi[r] = -1;
 	}
 	double worst = DBL_MAX; // bd[k - 1]
-	for (int64_t j0 = 0; j0 < N; j0 += kKnnTile) {
-		const int nt = (int)min((int64_t)kKnnTile, N - j0);
-		__syncthreads();
-		for (int t = threadIdx.x; t < nt * DIM; t += kKnnTile) s_pts[t] = aos[j0 * DIM + t];
-		__syncthreads();
-		if (i >= N) continue;
-		for (int t = 0; t < nt; ++t) {
-			double d2 = 0.0;
+	const int64_t chunk = (N + SLICES - 1) / SLICES;
+	const int64_t j_begin = min(N, slice * chunk), j_end = min(N, j_begin + chunk);
+	if (i < N) {
+		int64_t j = j_begin;
+		for (; j + 4 <= j_end; j += 4) { // four independent distance chains, then the (rare) insertions in index order
+			double d2[4];
 #pragma unroll
-			for (int c = 0; c < DIM; ++c) {
-				const double d = me[c] - s_pts[t * DIM + c];
-				d2 += d * d;
-			}
-			const int64_t j = j0 + t;
-			// j ascending: on equal distance the lower index stays (strict comparisons below)
-			if (j == i || !(d2 <= radius2) || !(d2 < worst)) continue;
-			double cd = d2;
-			int ci = (int)j;
+			for (int u = 0; u < 4; ++u) d2[u] = knn_dist2<DIM>(me, aos + (j + u) * DIM);
 #pragma unroll
-			for (int q = 0; q < KMAX; ++q) { // bubble the candidate through the ascending list
-				if (q < k && cd < bd[q]) {
-					const double td = bd[q];
-					const int ti = bi[q];
-					bd[q] = cd;
-					bi[q] = ci;
-					cd = td;
-					ci = ti;
-				}
-				if (q == k - 1) worst = bd[q];
-			}
+			for (int u = 0; u < 4; ++u)
+				if (j + u != i && d2[u] <= radius2 && d2[u] < worst) knn_insert<KMAX>(bd, bi, worst, d2[u], (int)(j + u), k);
+		}
+		for (; j < j_end; ++j) {
+			const double d2 = knn_dist2<DIM>(me, aos + j * DIM);
+			if (j != i && d2 <= radius2 && d2 < worst) knn_insert<KMAX>(bd, bi, worst, d2, (int)j, k);
 		}
 	}
-	if (i < N) {
+	if (slice > 0) {
+#pragma unroll
+		for (int r = 0; r < KMAX; ++r) {
+			s_d[slice - 1][r][q] = bd[r];
+			s_i[slice - 1][r][q] = bi[r];
+		}
+	}
+	__syncthreads();
+	if (slice == 0 && i < N) {
+		for (int s2 = 0; s2 < SLICES - 1; ++s2)
+			for (int r = 0; r < k; ++r) { // a slice's list is ascending: once an entry fails, the rest of the list fails too
+				const double cd = s_d[s2][r][q];
+				const int ci = s_i[s2][r][q];
+				if (ci < 0 || !(cd < worst)) break;
+				knn_insert<KMAX>(bd, bi, worst, cd, ci, k);
+			}
 		int cnt = 0;
 #pragma unroll
-		for (int q = 0; q < KMAX; ++q)
-			if (q < k) {
-				nbr[i * k + q] = bi[q];
-				cnt += bi[q] >= 0;
+		for (int r = 0; r < KMAX; ++r)
+			if (r < k) {
+				nbr[i * k + r] = bi[r];
+				cnt += bi[r] >= 0;
 			}
 		deg[i] = cnt;
 	}
@@ -93,9 +142,9 @@ template <int DIM>
 static void launch_knn_dim(pxb_ctx *ctx, unsigned grid, double radius, int k, int32_t *nbr, int32_t *deg) {
 	const Points &p = ctx->pts;
 	if (k <= 8)
-		k_knn_graph<DIM, 8><<<grid, kKnnTile, 0, ctx->stream>>>(p.aos, p.N, radius * radius, k, nbr, deg);
+		k_knn_graph<DIM, 8, 8><<<grid, kKnnQuery * 8, 0, ctx->stream>>>(p.aos, p.N, radius * radius, k, nbr, deg);
 	else
-		k_knn_graph<DIM, kKnnMax><<<grid, kKnnTile, 0, ctx->stream>>>(p.aos, p.N, radius * radius, k, nbr, deg);
+		k_knn_graph<DIM, kKnnMax, 4><<<grid, kKnnQuery * 4, 0, ctx->stream>>>(p.aos, p.N, radius * radius, k, nbr, deg);
 }
 
 int launch_knn_graph(pxb_ctx *ctx, double radius, int k, int32_t *nbr, int32_t *deg) {
@@ -104,7 +153,7 @@ int launch_knn_graph(pxb_ctx *ctx, double radius, int k, int32_t *nbr, int32_t *
 		set_error("k must be in [1, %d]", kKnnMax);
 		return PXB_ERR_ARGUMENT;
 	}
-	const unsigned grid = (unsigned)((p.N + kKnnTile - 1) / kKnnTile);
+	const unsigned grid = (unsigned)((p.N + kKnnQuery - 1) / kKnnQuery);
 	if (p.dim == 4)
 		launch_knn_dim<4>(ctx, grid, radius, k, nbr, deg);
 	else if (p.dim == 2)

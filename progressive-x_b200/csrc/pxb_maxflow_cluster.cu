@@ -269,7 +269,9 @@ __global__ void __launch_bounds__(kMcThreads, 1) k_maxflow_cluster(McParams P) {
 	}
 	unsigned hmine = kInf;
 	int epoch = 0, rounds = 0, levels_total = 0;
-	long long clk_relabel = 0, clk_push = 0;
+	long long clk_relabel = 0, clk_push = 0, acc_scan = 0, acc_or = 0;
+	__shared__ unsigned long long s_scan_max, s_or_min;
+	if (tid == 0) s_scan_max = 0ull, s_or_min = ~0ull;
 	cluster_sync_all();
 
 	for (; rounds < kMcMaxRounds; ++rounds) {
@@ -294,6 +296,7 @@ __global__ void __launch_bounds__(kMcThreads, 1) k_maxflow_cluster(McParams P) {
 		unsigned level = 1;
 		for (;; ++level) {
 			bool found = false;
+			const long long lv0 = clock64();
 			if (t < nb) {
 				if (hmine == kInf) {
 					found = reaches_level(vcap, head, vh, a0, a1, level);
@@ -312,7 +315,11 @@ __global__ void __launch_bounds__(kMcThreads, 1) k_maxflow_cluster(McParams P) {
 					found = true;
 				}
 			}
-			if (!cluster_or(found, epoch, s_slots, nranks)) break;
+			const long long lv1 = clock64();
+			const bool more = cluster_or(found, epoch, s_slots, nranks);
+			acc_scan += lv1 - lv0;
+			acc_or += clock64() - lv1;
+			if (!more) break;
 		}
 		levels_total += (int)level;
 		bool active = t < nb && hmine != kInf && vexc[t] > 0.0;
@@ -416,7 +423,12 @@ __global__ void __launch_bounds__(kMcThreads, 1) k_maxflow_cluster(McParams P) {
 	// heights now hold the final reachability: height < n  <=>  the node can reach the sink in the residual graph
 	if (t < nb) P.height[s0 + t] = hmine == kInf ? n : (int)hmine;
 	if (rank == 0 && tid < naux) P.height[N + tid] = vh[auxbase + tid] == kInf ? n : (int)vh[auxbase + tid];
+	atomicMax(&s_scan_max, (unsigned long long)acc_scan);
+	atomicMin(&s_or_min, (unsigned long long)acc_or);
+	__syncthreads();
 	if (rank == 0 && tid == 0) {
+		P.flags[13] = (int)(s_scan_max >> 6); // slowest thread's time in the level scans / fastest thread's time in the votes
+		P.flags[14] = (int)(s_or_min >> 6);
 		P.flags[6] = rounds + 1;
 		P.flags[7] = rounds < kMcMaxRounds ? 1 : 0;
 		P.flags[8] = levels_total;

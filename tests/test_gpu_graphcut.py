@@ -93,6 +93,44 @@ def test_knn_graph_matches_kdtree(ctx):
         assert set(idx[off[i]:off[i + 1]]) == set(idx_o[off_o[i]:off_o[i + 1]])
 
 
+def _knn_bruteforce(rows, radius, k):
+    """the rule k_knn_graph implements: the k smallest (squared distance, index) pairs within the radius, self excluded;
+    squared distances summed coordinate by coordinate in float64 (no fused multiply-add), ties to the lower index"""
+    N = rows.shape[0]
+    out = []
+    for i in range(N):
+        d2 = np.zeros(N)
+        for c in range(rows.shape[1]):
+            d = rows[i, c] - rows[:, c]
+            d2 = d2 + d * d
+        d2[i] = np.inf
+        order = np.argsort(d2, kind="stable")[:k]
+        out.append([int(j) for j in order if d2[j] <= radius * radius])
+    return out
+
+
+@pytest.mark.parametrize("t,N,radius,k", [(0, 3001, 60.0, 5), (0, 1237, 400.0, 12), (4, 2050, 40.0, 8), (2, 1500, 0.35, 5), (0, 7, 1e9, 8)])
+def test_knn_graph_exact_order(ctx, t, N, radius, k):
+    """every neighbour list is exactly the sequential scan's (order included): 64 x SLICES threads per block split the
+    candidates of a query into index ranges and merge their lists; N not a multiple of anything, k <= 8 and k > 8
+    instantiations, 2 / 4 / 5 coordinates, duplicated points (exact distance ties)"""
+    rng = np.random.default_rng(N)
+    if t == 0:
+        rows, _, _ = syn.multi_homography_scene(N, seed=5)
+    elif t == 4:
+        rows = np.round(rng.uniform(0, 500, size=(N, 2)))  # integer coordinates: many exactly equal distances
+    else:
+        rows = np.concatenate([rng.normal(size=(N, 2)), rng.uniform(-1, 1, size=(N, 3))], axis=1)
+    rows = np.ascontiguousarray(rows, dtype=np.float64)
+    rows[N // 2] = rows[N // 3]  # a duplicated point
+    ctx.upload_points(t, rows)
+    off, idx = ctx.knn_graph(radius, k)
+    want = _knn_bruteforce(rows, radius, k)
+    assert off[-1] == sum(len(w) for w in want)
+    for i in range(N):
+        assert idx[off[i]:off[i + 1]].tolist() == want[i], i
+
+
 def test_nonminimal_homography_fit(ctx, oracle):
     """normal equations on the device vs column-pivoted Householder QR in the oracle: same least-squares solution"""
     pts, gt, Hs = syn.multi_homography_scene(6000, n_planes=3, noise=0.5, seed=13)
