@@ -393,7 +393,7 @@ struct Scoped {
 
 struct Instance {
 	std::vector<double> model;
-	std::vector<double> pref; // preference vector as of acceptance (never refreshed: progressive_x.h:597-624)
+	// (the preference vector as of acceptance -- never refreshed: progressive_x.h:597-624 -- is row k of ctx->pref_rows)
 };
 
 class Driver {
@@ -443,7 +443,6 @@ class Driver {
 	Graph graph_;
 	std::vector<GridLayer> grid_layers_;
 	std::vector<Instance> models_;
-	std::vector<double> compound_pref_;
 	std::vector<int64_t> labeling_;
 	size_t pearl_outliers_ = 0;
 	// GC-RANSAC statistics of the last proposal
@@ -469,19 +468,31 @@ class Driver {
 		if (!models_.empty()) sc.value -= std::pow(shared, s_.exponent); // :110-121
 		return sc;
 	}
-	// The compound preference vector lives on the device between updates (it changes once per accepted instance).
+	// The compound preference vector and the instances' preference vectors never leave the device: ctx->cpref [N] is the
+	// element-wise maximum of rows 0 .. |models_|-1 of ctx->pref_rows (updateCompoundModel, progressive_x.h:597-624).
 	const double *compound_dev() const { return models_.empty() ? nullptr : ctx_->cpref.as<double>(); }
-	int upload_compound() {
+	double *pref_row(size_t k) const { return ctx_->pref_rows.as<double>() + k * (size_t)N_; }
+	int reserve_round_buffers() { // once per run: all-zero compound vector (progressive_x.h:262), the preference table
 		PXB_TRY(ctx_->cpref.reserve(sizeof(double) * (size_t)N_));
-		PXB_CUDA(cudaMemcpyAsync(ctx_->cpref.ptr, compound_pref_.data(), sizeof(double) * (size_t)N_, cudaMemcpyHostToDevice,
-		                         ctx_->stream));
+		PXB_TRY(ctx_->pref2.reserve(sizeof(double) * (size_t)N_));
+		PXB_TRY(ctx_->pref_rows.reserve(sizeof(double) * (size_t)N_ * (PXB_MAX_ROUNDS + 1)));
+		PXB_CUDA(cudaMemsetAsync(ctx_->cpref.ptr, 0, sizeof(double) * (size_t)N_, ctx_->stream));
+		return PXB_OK;
+	}
+	int publish_compound() { // stream ordered, no wait: the next chain that scores against the vector comes after it
+		PXB_TRY(launch_compound_max(ctx_, ctx_->pref_rows.as<double>(), (int64_t)models_.size(), N_, ctx_->cpref.as<double>()));
 		if (sharded()) { // the other ranks score against the same compound preference vector
 			ShardMsg h{};
 			h.op = kShardCompound;
 			PXB_TRY(shard_send(h, nullptr, 0));
 			PXB_TRY(shard_broadcast(ctx_, ctx_->cpref.ptr, sizeof(double) * (size_t)N_, 0));
 		}
-		PXB_TRY(ctx_wait(ctx_));
+		return PXB_OK;
+	}
+	// PEARL rejected instance l of S: the rows behind it move down (rare; rows do not overlap)
+	int erase_pref_row(size_t l, size_t S) {
+		for (size_t k = l + 1; k < S; ++k)
+			PXB_CUDA(cudaMemcpyAsync(pref_row(k - 1), pref_row(k), sizeof(double) * (size_t)N_, cudaMemcpyDeviceToDevice, ctx_->stream));
 		return PXB_OK;
 	}
 	// scores K models that already sit in ctx->models (device) and brings (count, value, shared) back in ONE copy (the
@@ -712,7 +723,7 @@ class Driver {
 	int launch_fit_family(int P, const int32_t *d_off, const int32_t *d_idx, const double *d_w, double *models_dev, int32_t *ok_dev);
 	std::vector<unsigned char> pack_host_, chain_tmp_in_;
 	// ---- replayable device chains (CUDA graphs; see pxb_ctx::ChainGraph) ---------------------------------------------
-	enum ChainKind : uint64_t { kChainRefill = 1, kChainLo = 2, kChainTail = 3, kChainPearl = 4 };
+	enum ChainKind : uint64_t { kChainRefill = 1, kChainLo = 2, kChainTail = 3, kChainPearl = 4, kChainFinish = 5 };
 	static uint64_t mix_key(std::initializer_list<uint64_t> parts) {
 		uint64_t h = 0x9E3779B97F4A7C15ull;
 		for (uint64_t v : parts) {
@@ -836,7 +847,8 @@ class Driver {
 		int32_t ok = 0;
 	};
 	int tail_step(const double *model, bool weighted, double T2, TailStep &out);
-	int putative_model_valid(const std::vector<double> &model, std::vector<double> &pref, bool &valid);
+	int proposal_finish(const double *model, std::vector<int64_t> &inliers, double &tanimoto);
+	bool defer_inliers_ = false; // the outer loop reads the proposal's inliers in proposal_finish (one round trip for both)
 	int pearl();
 	size_t predicted_unseen_inliers(size_t iterations, size_t compound_inliers) const;
 };
@@ -1433,27 +1445,70 @@ int Driver::propose(uint64_t round_seed, std::vector<double> &model_out, bool &f
 			if (best_score.value < sc.value) best_model = ts.fitted;
 		}
 	}
-	std::vector<int64_t> best_inliers;
-	PXB_TRY(inliers_of(best_model.data(), T2, best_inliers));
-	proposal_inliers_ = best_inliers; // statistics.inliers (:621)
+	if (!defer_inliers_) {
+		std::vector<int64_t> best_inliers;
+		PXB_TRY(inliers_of(best_model.data(), T2, best_inliers));
+		proposal_inliers_ = best_inliers; // statistics.inliers (:621)
+	}
 	model_out = best_model;
 	found = true;
 	return PXB_OK;
 }
 
-// px/include/progressive_x.h:565-591
-int Driver::putative_model_valid(const std::vector<double> &model, std::vector<double> &pref, bool &valid) {
-	Scoped t(prof_, "putative_model_valid");
-	valid = false;
-	if (proposal_inliers_.size() < std::max((size_t)m_, s_.min_inliers)) return PXB_OK;
-	const double T = 9.0 / 4.0 * s_.threshold * s_.threshold; // :523 spelling
-	pref.resize(N_);
-	PXB_TRY(pxb_preference_vector(ctx_, model.data(), T, pref.data()));
-	double tanimoto = 0.0;
-	PXB_TRY(pxb_tanimoto(ctx_, pref.data(), compound_pref_.data(), N_, &tanimoto));
-	// `maximum_tanimoto_similarity < similarity` rejects; NaN (0/0 on the first proposal) compares false -> accepted
-	if (s_.max_tanimoto < tanimoto) return PXB_OK;
-	valid = true;
+// The end of a proposal as ONE stream-ordered chain (one round trip instead of four, nothing but 24 bytes and the inlier
+// bit mask crosses PCIe): the inliers of the proposed model (r2 < T2: statistics.inliers, GCRANSAC.h:546-559 / :621) ->
+// its preference vector (progx_model.h:84-85, threshold spelled as progressive_x.h:523) into the scratch row ->
+// the three sums of the Tanimoto similarity against the compound vector (progressive_x.h:565-591).
+int Driver::proposal_finish(const double *model, std::vector<int64_t> &inliers, double &tanimoto) {
+	Scoped t(prof_, "proposal_finish");
+	const double truncated_threshold = 3.0 / 2.0 * s_.threshold;
+	const double T2 = truncated_threshold * truncated_threshold; // GCRANSAC.h:254-255 spelling
+	const double T = 9.0 / 4.0 * s_.threshold * s_.threshold;    // progressive_x.h:523 spelling
+	const int64_t words = (N_ + 31) / 32;
+	const size_t in_bytes = sizeof(double) * ms_;
+	const size_t o_sums = ((sizeof(uint32_t) * (size_t)words + 7) / 8) * 8, pack_bytes = o_sums + 3 * sizeof(double);
+	PXB_TRY(ctx_->chain_par.reserve(in_bytes));
+	PXB_TRY(ctx_->pack.reserve(pack_bytes));
+	const bool slots = chain_slots(in_bytes, pack_bytes);
+	chain_tmp_in_.resize(in_bytes);
+	unsigned char *hin = slots ? ctx_->chain_in : chain_tmp_in_.data();
+	std::memcpy(hin, model, in_bytes);
+	pack_host_.resize(pack_bytes);
+	unsigned char *hout = slots ? ctx_->chain_out : pack_host_.data();
+	auto enqueue = [&]() -> int {
+		double *d_model = ctx_->chain_par.as<double>();
+		char *pk = ctx_->pack.as<char>();
+		if (slots)
+			PXB_CUDA(cudaMemcpyAsync(d_model, hin, in_bytes, cudaMemcpyHostToDevice, ctx_->stream));
+		else
+			PXB_TRY(api_h2d(ctx_, d_model, hin, in_bytes));
+		PXB_TRY(launch_residual_matrix(ctx_, d_model, 1, T2, nullptr, nullptr, reinterpret_cast<uint32_t *>(pk)));
+		PXB_TRY(launch_preference(ctx_, d_model, T, ctx_->pref2.as<double>()));
+		PXB_TRY(launch_tanimoto(ctx_, ctx_->pref2.as<double>(), ctx_->cpref.as<double>(), N_, reinterpret_cast<double *>(pk + o_sums)));
+		if (slots)
+			PXB_CUDA(cudaMemcpyAsync(hout, pk, pack_bytes, cudaMemcpyDeviceToHost, ctx_->stream));
+		else
+			PXB_TRY(api_d2h(ctx_, hout, pk, pack_bytes));
+		return PXB_OK;
+	};
+	if (slots)
+		PXB_TRY(run_chain(mix_key({kChainFinish, buffers_key(), bits(ctx_->pref2.ptr), bits(T2), bits(T)}), enqueue));
+	else
+		PXB_TRY(enqueue());
+	PXB_TRY(api_sync(ctx_));
+	// bit mask -> ascending index list (format conversion of the kernel's output, no arithmetic)
+	const uint32_t *w = reinterpret_cast<const uint32_t *>(hout);
+	inliers.clear();
+	for (int64_t j = 0; j < words; ++j) {
+		uint32_t bits32 = w[j];
+		while (bits32) {
+			inliers.push_back(j * 32 + __builtin_ctz(bits32));
+			bits32 &= bits32 - 1;
+		}
+	}
+	double sums[3];
+	std::memcpy(sums, hout + o_sums, sizeof(sums));
+	tanimoto = sums[0] / (sums[1] + sums[2] - sums[0]); // progressive_x.h:584-585
 	return PXB_OK;
 }
 
@@ -1583,6 +1638,7 @@ int Driver::pearl() {
 		for (int64_t l = L - 1; l >= 0; --l)
 			if ((size_t)counts[l] < s_.min_inliers) {
 				outliers += (size_t)counts[l];
+				PXB_TRY(erase_pref_row((size_t)l, models_.size()));
 				models_.erase(models_.begin() + l);
 				model_rejected = true;
 			}
@@ -1691,8 +1747,9 @@ int Driver::run(int setup_status) {
 // px/include/progressive_x.h:251-489
 int Driver::run_local() {
 	labeling_.assign((size_t)N_, 0);
-	compound_pref_.assign((size_t)N_, 0.0);
 	models_.clear();
+	defer_inliers_ = true;
+	PXB_TRY(reserve_round_buffers());
 	size_t number_of_ransac_iterations = 0, unaccepted = 0;
 	// statistics.inliers_of_each_model.size(): one entry is appended whenever an instance is added while it is the only one
 	// (:375-381); the reference passes this COUNT as the compound inlier number whenever one instance remains (:447-451)
@@ -1707,7 +1764,7 @@ int Driver::run_local() {
 			for (cudaEvent_t &e : ctx_->timing_events) PXB_CUDA(cudaEventCreate(&e));
 			ctx_->timing_events_ready = true;
 		}
-		PXB_CUDA(cudaEventRecord(ctx_->timing_events[4 * PXB_MAX_ROUNDS], ctx_->stream));
+		PXB_CUDA(cudaEventRecord(ctx_->timing_events[5 * PXB_MAX_ROUNDS], ctx_->stream));
 	}
 	struct RoundMarks {
 		int first_event;
@@ -1722,9 +1779,14 @@ int Driver::run_local() {
 	for (size_t it = 0; it < PXB_MAX_ROUNDS; ++it) { // :272 hard cap
 		std::vector<double> model;
 		bool found = false;
-		next_event = 4 * (int)rounds.size();
+		next_event = 5 * (int)rounds.size();
 		const int e_start = mark();
 		PXB_TRY(propose(s_.seed * 1000003ull + it, model, found));
+		double tanimoto = 0.0;
+		if (found) {
+			mark(); // end of the proposal engine / start of the validation
+			PXB_TRY(proposal_finish(model.data(), proposal_inliers_, tanimoto));
+		}
 		if (s_.do_logging)
 			fprintf(stdout, "[pxb] proposal %zu: %s, %zu inliers, %zu iterations, %zu LO runs, %zu graph cuts, DEGENSAC %zu/%zu\n",
 			        it + 1, found ? "found" : "none", proposal_inliers_.size(), iteration_number_, lo_number_, graph_cut_number_,
@@ -1737,10 +1799,9 @@ int Driver::run_local() {
 		rm.stat.local_optimization_number = lo_number_;
 		rm.stat.graph_cut_number = graph_cut_number_;
 		rm.stat.proposal_inlier_number = proposal_inliers_.size();
-		mark(); // end of the proposal engine / start of the validation
-		std::vector<double> pref;
-		bool valid = false;
-		PXB_TRY(putative_model_valid(model, pref, valid));
+		// isPutativeModelValid (:565-591): enough inliers, and `maximum_tanimoto_similarity < similarity` rejects (NaN
+		// compares false: accepted)
+		const bool valid = proposal_inliers_.size() >= std::max((size_t)m_, s_.min_inliers) && !(s_.max_tanimoto < tanimoto);
 		if (!valid) { // :334-346 (the counter is never reset)
 			++unaccepted;
 			if (unaccepted == s_.max_proposals_without_change) break;
@@ -1749,7 +1810,7 @@ int Driver::run_local() {
 		mark(); // end of the validation / start of the optimisation
 		Instance inst;
 		inst.model = model;
-		inst.pref = pref;
+		PXB_CUDA(cudaMemcpyAsync(pref_row(models_.size()), ctx_->pref2.ptr, sizeof(double) * (size_t)N_, cudaMemcpyDeviceToDevice, ctx_->stream));
 		models_.push_back(std::move(inst));
 		if (models_.size() == 1) { // :375-385
 			std::fill(labeling_.begin(), labeling_.end(), 1);
@@ -1760,30 +1821,10 @@ int Driver::run_local() {
 		}
 		mark(); // end of the optimisation / start of the compound update
 		// updateCompoundModel (:597-624): max over the *stored* preference vectors
-		if (!models_.empty()) {
-			std::vector<double> prefs((size_t)models_.size() * N_);
-			for (size_t k = 0; k < models_.size(); ++k)
-				std::copy(models_[k].pref.begin(), models_[k].pref.end(), prefs.begin() + k * N_);
-			PXB_TRY(pxb_compound_max(ctx_, prefs.data(), (int64_t)models_.size(), N_, compound_pref_.data()));
-			PXB_TRY(upload_compound());
-		}
-		if (timed) cudaEventRecord(ctx_->timing_events[4 * PXB_MAX_ROUNDS + 1], ctx_->stream); // end of this round's compound update
+		if (!models_.empty()) PXB_TRY(publish_compound());
+		mark(); // end of this round's compound update (every round has its own five events: they are read after the run)
 		rm.stat.number_of_instances = models_.size();
-		if (timed && rounds.size() < PXB_MAX_ROUNDS) {
-			// the closing event is shared: read this round's times now (the stream is idle: upload_compound synchronised)
-			PXB_TRY(ctx_wait(ctx_));
-			float ms[4] = {0, 0, 0, 0};
-			cudaEvent_t *ev = ctx_->timing_events;
-			cudaEventElapsedTime(&ms[0], ev[rm.first_event], ev[rm.first_event + 1]);
-			cudaEventElapsedTime(&ms[1], ev[rm.first_event + 1], ev[rm.first_event + 2]);
-			cudaEventElapsedTime(&ms[2], ev[rm.first_event + 2], ev[rm.first_event + 3]);
-			cudaEventElapsedTime(&ms[3], ev[rm.first_event + 3], ev[4 * PXB_MAX_ROUNDS + 1]);
-			rm.stat.time_of_proposal_engine = ms[0] * 1e-3;
-			rm.stat.time_of_model_validation = ms[1] * 1e-3;
-			rm.stat.time_of_optimization = ms[2] * 1e-3;
-			rm.stat.time_of_compound_model_update = ms[3] * 1e-3;
-			rounds.push_back(rm);
-		}
+		if (rounds.size() < PXB_MAX_ROUNDS) rounds.push_back(rm);
 		size_t unseen;
 		if (models_.size() == 1) // evaluated AFTER the optimisation: also when PEARL pruned the set back to one instance
 			unseen = predicted_unseen_inliers(number_of_ransac_iterations, inliers_of_each_model_size);
@@ -1796,18 +1837,24 @@ int Driver::run_local() {
 		if (models_.size() >= s_.max_models) break;      // :472
 	}
 	if (timed) { // addIterationStatistics (:91-100) + processing_time (:483-488)
-		for (const RoundMarks &rm : rounds) {
+		cudaEvent_t *ev = ctx_->timing_events;
+		PXB_CUDA(cudaEventRecord(ev[5 * PXB_MAX_ROUNDS + 1], ctx_->stream));
+		PXB_TRY(ctx_wait(ctx_));
+		for (RoundMarks &rm : rounds) {
+			float ms[4] = {0, 0, 0, 0};
+			for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&ms[k], ev[rm.first_event + k], ev[rm.first_event + k + 1]);
+			rm.stat.time_of_proposal_engine = ms[0] * 1e-3;
+			rm.stat.time_of_model_validation = ms[1] * 1e-3;
+			rm.stat.time_of_optimization = ms[2] * 1e-3;
+			rm.stat.time_of_compound_model_update = ms[3] * 1e-3;
 			st.iteration_statistics[st.iteration_statistics_size++] = rm.stat;
 			st.total_time_of_proposal_engine += rm.stat.time_of_proposal_engine;
 			st.total_time_of_model_validation += rm.stat.time_of_model_validation;
 			st.total_time_of_optimization += rm.stat.time_of_optimization;
 			st.total_time_of_compound_model_calculation += rm.stat.time_of_compound_model_update;
 		}
-		cudaEvent_t *ev = ctx_->timing_events;
-		PXB_CUDA(cudaEventRecord(ev[4 * PXB_MAX_ROUNDS + 1], ctx_->stream));
-		PXB_CUDA(cudaEventSynchronize(ev[4 * PXB_MAX_ROUNDS + 1]));
 		float total_ms = 0;
-		cudaEventElapsedTime(&total_ms, ev[4 * PXB_MAX_ROUNDS], ev[4 * PXB_MAX_ROUNDS + 1]);
+		cudaEventElapsedTime(&total_ms, ev[5 * PXB_MAX_ROUNDS], ev[5 * PXB_MAX_ROUNDS + 1]);
 		st.processing_time = total_ms * 1e-3;
 		st.model_number = models_.size();
 		st.inliers_of_each_model_size = inliers_of_each_model_size;

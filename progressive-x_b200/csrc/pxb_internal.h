@@ -125,7 +125,7 @@ struct pxb_ctx {
 	pxb_multi_model_settings engine_settings;
 	bool has_engine_settings = false;
 	pxb_multi_model_statistics last_statistics = {};
-	cudaEvent_t timing_events[4 * PXB_MAX_ROUNDS + 2] = {};
+	cudaEvent_t timing_events[5 * PXB_MAX_ROUNDS + 2] = {}; // five marks per round + start / end of the run
 	bool timing_events_ready = false;
 	// Replayable device chains (pxb_driver.cu run_chain): the loops of the driver issue the same fixed sequence of copies
 	// and kernels again and again; the second time a sequence with the same signature is seen it is captured into a CUDA
@@ -143,6 +143,7 @@ struct pxb_ctx {
 	unsigned char *chain_in = nullptr, *chain_out = nullptr; // pinned, kChainInBytes / kChainOutBytes
 	pxb::DevBuf chain_par;
 	pxb::DevBuf labels, pack; // PEARL labels (kept on the device between iterations) and the packed per-call results
+	pxb::DevBuf pref_rows;    // preference vectors of the accepted instances, one row of N per instance (pxb_driver.cu)
 };
 
 namespace pxb {
