@@ -2055,12 +2055,25 @@ int pxb_find_6d_poses(pxb_ctx *ctx, const double *image_points, const double *wo
 	s.sampler_id = 0;
 	if (seed == 0) seed = (uint64_t)std::chrono::high_resolution_clock::now().time_since_epoch().count();
 	s.seed = seed;
-	PXB_TRY(pxb_upload_points(ctx, PXB_MODEL_PNP, raw.data(), N));
+	// the neighbourhood graph is built on the raw rows [u v X Y Z] (progressivex_python.cpp:60-75), everything else runs on
+	// the normalised ones: the raw rows only travel when a graph is needed
+	const bool needs_graph = spatial_coherence_weight > 0.0;
+	if (needs_graph) PXB_TRY(pxb_upload_points(ctx, PXB_MODEL_PNP, raw.data(), N));
+	else PXB_TRY(pxb_upload_points(ctx, PXB_MODEL_PNP, nrm.data(), N));
 	Driver drv(ctx, s);
 	int setup = PXB_OK;
-	if (!drv.is_worker() && spatial_coherence_weight > 0.0) setup = drv.build_graph(neighborhood_ball_radius, graph_degree());
-	if (setup == PXB_OK) setup = pxb_upload_points(ctx, PXB_MODEL_PNP, nrm.data(), N);
-	PXB_TRY(drv.run(setup));
+	if (needs_graph) {
+		if (!drv.is_worker()) {
+			Scoped t(drv.prof_, "build_graph");
+			setup = drv.build_graph(neighborhood_ball_radius, graph_degree());
+		}
+		if (setup == PXB_OK) setup = pxb_upload_points(ctx, PXB_MODEL_PNP, nrm.data(), N);
+	}
+	{
+		Scoped t(drv.prof_, "run (inclusive)");
+		PXB_TRY(drv.run(setup));
+	}
+	drv.prof_.print();
 	const auto &inst = drv.instances();
 	const int64_t M = (int64_t)inst.size();
 	PXB_TRY(check_model_capacity(M, max_models_out));
