@@ -81,11 +81,18 @@ template <int NN> __device__ void jacobi_eig(double *A, double *V, double *w) {
 	for (int i = 0; i < NN; ++i) w[i] = A[i * NN + i];
 }
 
-// The same cyclic Jacobi executed by ONE WARP on matrices in shared memory: lane k applies a rotation to row / column k,
-// so a rotation costs three short phases instead of ~6 NN dependent local-memory updates in one thread (the 12 x 12
-// eigenproblem of the pose DLT took several hundred microseconds in the serial form). Rotation arithmetic per element is
+// Jacobi executed by ONE WARP on matrices in shared memory, in ROUND-ROBIN order: a sweep is NP - 1 rounds (NP = NN rounded
+// up to even) of NP / 2 rotations on disjoint index pairs (the tournament schedule: player NP - 1 stays, the others move
+// round a circle). Disjoint plane rotations commute and none reads what another one of its round writes, so a round is
+// the sequential application of its rotations -- but their angles (two divisions and two square roots each: ~600 cycles
+// of dependent float64 latency) are computed side by side by NP / 2 lanes, and the column / row updates of all of them
+// are two phases in which lane k owns row / column k. The serial order cost one such latency chain per rotation (66 per
+// sweep of the 12 x 12 pose problem, 36 of the 9 x 9 one): ~200 of k_fit_pnp's 284 us. Rotation arithmetic per element is
 // unchanged.
 template <int NN> __device__ void jacobi_eig_warp(double *A, double *V, double *w) {
+	constexpr int NP = (NN + 1) / 2 * 2, HALF = NP / 2;
+	__shared__ double s_c[HALF], s_s[HALF];
+	__shared__ int s_p[HALF], s_q[HALF];
 	const int lane = threadIdx.x & 31;
 	for (int e = lane; e < NN * NN; e += 32) V[e] = (e / NN == e % NN) ? 1.0 : 0.0;
 	__syncwarp();
@@ -103,30 +110,55 @@ template <int NN> __device__ void jacobi_eig_warp(double *A, double *V, double *
 			diag += __shfl_xor_sync(0xffffffffu, diag, o);
 		}
 		if (!(off > 1e-30 * diag) || !(off == off)) break;
-		for (int p = 0; p < NN - 1; ++p)
-			for (int q = p + 1; q < NN; ++q) {
-				const double apq = A[p * NN + q];
-				if (apq == 0.0) continue; // warp-uniform
-				const double theta = (A[q * NN + q] - A[p * NN + p]) / (2.0 * apq);
-				const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-				const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
-				__syncwarp();
-				if (lane < NN) {
+		for (int round = 0; round < NP - 1; ++round) {
+			if (lane < HALF) { // this lane's pair of the round and its rotation
+				int a = lane == 0 ? NP - 1 : (round + lane) % (NP - 1);
+				int b = lane == 0 ? round : (round - lane + (NP - 1)) % (NP - 1);
+				const int p = min(a, b), q = max(a, b);
+				double c = 1.0, sn = 0.0;
+				if (q < NN) { // (odd NN: the pair with the bye does nothing)
+					const double apq = A[p * NN + q];
+					if (apq != 0.0) {
+						const double theta = (A[q * NN + q] - A[p * NN + p]) / (2.0 * apq);
+						const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+						c = 1.0 / sqrt(t * t + 1.0);
+						sn = t * c;
+					}
+				}
+				s_p[lane] = p;
+				s_q[lane] = q < NN ? q : p; // (identity rotation on (p, p): never applied, see below)
+				s_c[lane] = c;
+				s_s[lane] = sn;
+			}
+			__syncwarp();
+			if (lane < NN) { // columns p, q of row `lane` of A and of V
+#pragma unroll
+				for (int j = 0; j < HALF; ++j) {
+					const int p = s_p[j], q = s_q[j];
+					const double c = s_c[j], sn = s_s[j];
+					if (p == q || (c == 1.0 && sn == 0.0)) continue;
 					const double akp = A[lane * NN + p], akq = A[lane * NN + q];
 					A[lane * NN + p] = c * akp - sn * akq;
 					A[lane * NN + q] = sn * akp + c * akq;
-				}
-				__syncwarp();
-				if (lane < NN) {
-					const double apk = A[p * NN + lane], aqk = A[q * NN + lane];
-					A[p * NN + lane] = c * apk - sn * aqk;
-					A[q * NN + lane] = sn * apk + c * aqk;
 					const double vkp = V[lane * NN + p], vkq = V[lane * NN + q];
 					V[lane * NN + p] = c * vkp - sn * vkq;
 					V[lane * NN + q] = sn * vkp + c * vkq;
 				}
-				__syncwarp();
 			}
+			__syncwarp();
+			if (lane < NN) { // rows p, q of column `lane` of A
+#pragma unroll
+				for (int j = 0; j < HALF; ++j) {
+					const int p = s_p[j], q = s_q[j];
+					const double c = s_c[j], sn = s_s[j];
+					if (p == q || (c == 1.0 && sn == 0.0)) continue;
+					const double apk = A[p * NN + lane], aqk = A[q * NN + lane];
+					A[p * NN + lane] = c * apk - sn * aqk;
+					A[q * NN + lane] = sn * apk + c * aqk;
+				}
+			}
+			__syncwarp();
+		}
 	}
 	__syncwarp();
 	if (lane < NN) w[lane] = A[lane * NN + lane];
