@@ -260,7 +260,7 @@ void pxb_ctx_destroy(pxb_ctx *ctx) {
 	if (ctx->pts.norm) cudaFree(ctx->pts.norm);
 	DevBuf *bufs[] = {&ctx->models, &ctx->pref, &ctx->pref2, &ctx->outA, &ctx->outB, &ctx->outC,
 	                  &ctx->outD,   &ctx->idx,  &ctx->mask,  &ctx->partials, &ctx->staging, &ctx->screen, &ctx->stats, &ctx->cpref,
-	                  &ctx->shard_msg, &ctx->shard_rec, &ctx->labels, &ctx->pack, &ctx->chain_par, &ctx->pref_rows};
+	                  &ctx->shard_msg, &ctx->shard_rec, &ctx->labels, &ctx->pack, &ctx->chain_par, &ctx->pref_rows, &ctx->seg_scratch};
 	for (DevBuf *b : bufs) b->release();
 	if (ctx->pinned) cudaFreeHost(ctx->pinned);
 	if (ctx->stage) cudaFreeHost(ctx->stage);

@@ -143,6 +143,7 @@ struct pxb_ctx {
 	unsigned char *chain_in = nullptr, *chain_out = nullptr; // pinned, kChainInBytes / kChainOutBytes
 	pxb::DevBuf chain_par;
 	pxb::DevBuf labels, pack; // PEARL labels (kept on the device between iterations) and the packed per-call results
+	pxb::DevBuf seg_scratch;  // warp partials + tickets of k_segment_sums (fixed size, allocated once)
 	pxb::DevBuf pref_rows;    // preference vectors of the accepted instances, one row of N per instance (pxb_driver.cu)
 };
 
