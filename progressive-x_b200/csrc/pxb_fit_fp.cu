@@ -89,14 +89,15 @@ template <int NN> __device__ void jacobi_eig(double *A, double *V, double *w) {
 // are two phases in which lane k owns row / column k. The serial order cost one such latency chain per rotation (66 per
 // sweep of the 12 x 12 pose problem, 36 of the 9 x 9 one): ~200 of k_fit_pnp's 284 us. Rotation arithmetic per element is
 // unchanged.
-template <int NN> __device__ void jacobi_eig_warp(double *A, double *V, double *w) {
+template <int NN> __device__ int jacobi_eig_warp(double *A, double *V, double *w) {
 	constexpr int NP = (NN + 1) / 2 * 2, HALF = NP / 2;
 	__shared__ double s_c[HALF], s_s[HALF];
 	__shared__ int s_p[HALF], s_q[HALF];
 	const int lane = threadIdx.x & 31;
 	for (int e = lane; e < NN * NN; e += 32) V[e] = (e / NN == e % NN) ? 1.0 : 0.0;
 	__syncwarp();
-	for (int sweep = 0; sweep < 60; ++sweep) {
+	int sweep = 0;
+	for (; sweep < 60; ++sweep) {
 		double off = 0.0, diag = 0.0;
 		for (int e = lane; e < NN * NN; e += 32) {
 			const int i = e / NN, j = e % NN;
@@ -119,9 +120,13 @@ template <int NN> __device__ void jacobi_eig_warp(double *A, double *V, double *
 				if (q < NN) { // (odd NN: the pair with the bye does nothing)
 					const double apq = A[p * NN + q];
 					if (apq != 0.0) {
-						const double theta = (A[q * NN + q] - A[p * NN + p]) / (2.0 * apq);
-						const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-						c = 1.0 / sqrt(t * t + 1.0);
+						// t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)), theta = (aqq - app) / (2 apq), with numerator and
+						// denominator multiplied by |2 apq|: one square root, one division and one reciprocal square root on
+						// the critical path instead of two divisions, two square roots and a reciprocal
+						const double d = A[q * NN + q] - A[p * NN + p];
+						const double r = sqrt(d * d + 4.0 * apq * apq);
+						const double t = (d >= 0 ? 2.0 * apq : -2.0 * apq) / (fabs(d) + r);
+						c = rsqrt(t * t + 1.0);
 						sn = t * c;
 					}
 				}
@@ -131,30 +136,42 @@ template <int NN> __device__ void jacobi_eig_warp(double *A, double *V, double *
 				s_s[lane] = sn;
 			}
 			__syncwarp();
+			// (the pairs of a round touch disjoint columns / rows: all operands are read before anything is written, so the
+			// shared-memory round trips of the HALF rotations overlap instead of running one after the other)
 			if (lane < NN) { // columns p, q of row `lane` of A and of V
+				int pp[HALF], qq[HALF];
+				double cc[HALF], ss[HALF], akp[HALF], akq[HALF], vkp[HALF], vkq[HALF];
 #pragma unroll
 				for (int j = 0; j < HALF; ++j) {
-					const int p = s_p[j], q = s_q[j];
-					const double c = s_c[j], sn = s_s[j];
-					if (p == q || (c == 1.0 && sn == 0.0)) continue;
-					const double akp = A[lane * NN + p], akq = A[lane * NN + q];
-					A[lane * NN + p] = c * akp - sn * akq;
-					A[lane * NN + q] = sn * akp + c * akq;
-					const double vkp = V[lane * NN + p], vkq = V[lane * NN + q];
-					V[lane * NN + p] = c * vkp - sn * vkq;
-					V[lane * NN + q] = sn * vkp + c * vkq;
+					pp[j] = s_p[j], qq[j] = s_q[j];
+					cc[j] = s_c[j], ss[j] = s_s[j];
+					akp[j] = A[lane * NN + pp[j]], akq[j] = A[lane * NN + qq[j]];
+					vkp[j] = V[lane * NN + pp[j]], vkq[j] = V[lane * NN + qq[j]];
+				}
+#pragma unroll
+				for (int j = 0; j < HALF; ++j) {
+					if (pp[j] == qq[j] || (cc[j] == 1.0 && ss[j] == 0.0)) continue;
+					A[lane * NN + pp[j]] = cc[j] * akp[j] - ss[j] * akq[j];
+					A[lane * NN + qq[j]] = ss[j] * akp[j] + cc[j] * akq[j];
+					V[lane * NN + pp[j]] = cc[j] * vkp[j] - ss[j] * vkq[j];
+					V[lane * NN + qq[j]] = ss[j] * vkp[j] + cc[j] * vkq[j];
 				}
 			}
 			__syncwarp();
 			if (lane < NN) { // rows p, q of column `lane` of A
+				int pp[HALF], qq[HALF];
+				double cc[HALF], ss[HALF], apk[HALF], aqk[HALF];
 #pragma unroll
 				for (int j = 0; j < HALF; ++j) {
-					const int p = s_p[j], q = s_q[j];
-					const double c = s_c[j], sn = s_s[j];
-					if (p == q || (c == 1.0 && sn == 0.0)) continue;
-					const double apk = A[p * NN + lane], aqk = A[q * NN + lane];
-					A[p * NN + lane] = c * apk - sn * aqk;
-					A[q * NN + lane] = sn * apk + c * aqk;
+					pp[j] = s_p[j], qq[j] = s_q[j];
+					cc[j] = s_c[j], ss[j] = s_s[j];
+					apk[j] = A[pp[j] * NN + lane], aqk[j] = A[qq[j] * NN + lane];
+				}
+#pragma unroll
+				for (int j = 0; j < HALF; ++j) {
+					if (pp[j] == qq[j] || (cc[j] == 1.0 && ss[j] == 0.0)) continue;
+					A[pp[j] * NN + lane] = cc[j] * apk[j] - ss[j] * aqk[j];
+					A[qq[j] * NN + lane] = ss[j] * apk[j] + cc[j] * aqk[j];
 				}
 			}
 			__syncwarp();
@@ -163,6 +180,7 @@ template <int NN> __device__ void jacobi_eig_warp(double *A, double *V, double *
 	__syncwarp();
 	if (lane < NN) w[lane] = A[lane * NN + lane];
 	__syncwarp();
+	return sweep;
 }
 
 // sums of NV per-thread values over the block (butterfly inside the warp, then the warps in order): two barriers for
@@ -543,6 +561,30 @@ __global__ void __launch_bounds__(1024)
 // ------------------------------------------------------------------------------------------------
 // pose (normalised DLT + LM on the reprojection error)
 // ------------------------------------------------------------------------------------------------
+// Thread `tid` of the block visits the sample's points tid, tid + kFitT, ... in that order (the summation topology of
+// every block sum below); the rows of U consecutive visits are gathered before the first one is consumed, so that the
+// dependent pair of L2 round trips (index -> row) is paid once per U points instead of once per point: with one block of
+// 256 threads per problem the per-point loops of a 6000-point refit were latency chains (~1500 cycles per point).
+template <int U, class Body>
+__device__ __forceinline__ void for_sample_rows5(const double *__restrict__ aos, const int32_t *__restrict__ idx, int beg, int n, int tid,
+                                                 Body body) {
+	for (int t0 = tid; t0 < n; t0 += U * kFitT) {
+		double q[U][5];
+#pragma unroll
+		for (int u = 0; u < U; ++u) {
+			const int t = t0 + u * kFitT;
+			if (t < n) {
+				const double *src = aos + 5 * (int64_t)idx[beg + t];
+#pragma unroll
+				for (int c = 0; c < 5; ++c) q[u][c] = src[c];
+			}
+		}
+#pragma unroll
+		for (int u = 0; u < U; ++u)
+			if (t0 + u * kFitT < n) body(q[u]);
+	}
+}
+
 __device__ void rodrigues_left(const double w[3], double R[9]) { // R <- exp([w]x) R
 	const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
 	const double th = sqrt(th2);
@@ -566,7 +608,10 @@ __device__ void rodrigues_left(const double w[3], double R[9]) { // R <- exp([w]
 
 __global__ void __launch_bounds__(kFitT)
     k_fit_pnp(const double *__restrict__ aos, const int32_t *__restrict__ off, const int32_t *__restrict__ idx,
-              double *__restrict__ P_out, int32_t *__restrict__ ok_out) {
+              double *__restrict__ P_out, int32_t *__restrict__ ok_out, int debug) {
+	const long long clk0 = clock64();
+	long long clk1 = 0, clk2 = 0, clk3 = 0, clk4 = 0;
+	int lm_iters = 0, lm_accepted = 0;
 	__shared__ double s_tmp[kFitT / 32];
 	__shared__ double s_acc[78];
 	__shared__ double s_big[(kFitT / 32) * 78], s_A[144], s_Vv[144], s_w[12];
@@ -580,30 +625,28 @@ __global__ void __launch_bounds__(kFitT)
 	}
 	// ---- normalise the 3D points (centroid, mean distance sqrt(3)) ----
 	double cx = 0, cy = 0, cz = 0;
-	for (int t = tid; t < n; t += kFitT) {
-		const double *q = aos + 5 * (int64_t)idx[beg + t];
+	for_sample_rows5<4>(aos, idx, beg, n, tid, [&](const double *q) {
 		cx = add(cx, q[2]);
 		cy = add(cy, q[3]);
 		cz = add(cz, q[4]);
-	}
+	});
 	cx = fp_block_sum(cx, s_tmp) / n;
 	cy = fp_block_sum(cy, s_tmp) / n;
 	cz = fp_block_sum(cz, s_tmp) / n;
 	double md = 0;
-	for (int t = tid; t < n; t += kFitT) {
-		const double *q = aos + 5 * (int64_t)idx[beg + t];
+	for_sample_rows5<4>(aos, idx, beg, n, tid, [&](const double *q) {
 		const double dx = q[2] - cx, dy = q[3] - cy, dz = q[4] - cz;
 		md = add(md, sqrt(dx * dx + dy * dy + dz * dz));
-	}
+	});
 	md = fp_block_sum(md, s_tmp) / n;
 	const double sc = md > 0 ? 1.7320508075688772 / md : 1.0;
+	clk1 = clock64();
 	// ---- DLT normal equations (12 x 12, 78 unique) ----
 	{
 		double acc[78];
 #pragma unroll
 		for (int a = 0; a < 78; ++a) acc[a] = 0.0;
-		for (int t = tid; t < n; t += kFitT) {
-			const double *q = aos + 5 * (int64_t)idx[beg + t];
+		for_sample_rows5<2>(aos, idx, beg, n, tid, [&](const double *q) {
 			const double u = q[0], v = q[1], X = (q[2] - cx) * sc, Y = (q[3] - cy) * sc, Z = (q[4] - cz) * sc;
 			const double ra[12] = {X, Y, Z, 1, 0, 0, 0, 0, -u * X, -u * Y, -u * Z, -u};
 			const double rb[12] = {0, 0, 0, 0, X, Y, Z, 1, -v * X, -v * Y, -v * Z, -v};
@@ -612,9 +655,10 @@ __global__ void __launch_bounds__(kFitT)
 			for (int r = 0; r < 12; ++r)
 #pragma unroll
 				for (int c = r; c < 12; ++c, ++a) acc[a] = add(acc[a], add(mul(ra[r], ra[c]), mul(rb[r], rb[c])));
-		}
+		});
 		fp_block_sums<78>(acc, s_big, s_acc);
 	}
+	clk2 = clock64();
 	if (tid < 32) {
 		if (tid == 0) {
 			int a = 0;
@@ -622,9 +666,10 @@ __global__ void __launch_bounds__(kFitT)
 				for (int c = r; c < 12; ++c, ++a) s_A[r * 12 + c] = s_A[c * 12 + r] = s_acc[a];
 		}
 		__syncwarp();
-		jacobi_eig_warp<12>(s_A, s_Vv, s_w);
+		lm_accepted = -jacobi_eig_warp<12>(s_A, s_Vv, s_w); // (debug line: sweeps, until the LM loop counts)
 	}
 	__syncthreads();
+	clk3 = clock64();
 	if (tid == 0) {
 		const double *V = s_Vv, *w = s_w;
 		int best = 0;
@@ -677,32 +722,38 @@ __global__ void __launch_bounds__(kFitT)
 	// at most 25 iterations. The reference's accumulator iterates over correspondences->rows with sample[i] and reads
 	// weights[i] unconditionally (jacobian_impl.h:32-56,76-104) -- out-of-bounds / null reads for a sample shorter than the
 	// data; restated as intended: over the sample, unit weights.
+	clk4 = clock64();
 	const double sq_thr = 1.0;
 	auto pnp_cost = [&](const double *P) -> double {
 		double c = 0.0;
-		for (int t = tid; t < n; t += kFitT) {
-			const double *q = aos + 5 * (int64_t)idx[beg + t];
-			const double Zx = P[0] * q[2] + P[1] * q[3] + P[2] * q[4] + P[3], Zy = P[4] * q[2] + P[5] * q[3] + P[6] * q[4] + P[7],
-			             Zz = P[8] * q[2] + P[9] * q[3] + P[10] * q[4] + P[11];
-			if (Zz < 0) continue;
+		double Pr[12]; // (the pose is read once: the gathers below must not wait for shared-memory loads in their shadow)
+#pragma unroll
+		for (int i = 0; i < 12; ++i) Pr[i] = P[i];
+		for_sample_rows5<4>(aos, idx, beg, n, tid, [&](const double *q) {
+			const double Zx = Pr[0] * q[2] + Pr[1] * q[3] + Pr[2] * q[4] + Pr[3], Zy = Pr[4] * q[2] + Pr[5] * q[3] + Pr[6] * q[4] + Pr[7],
+			             Zz = Pr[8] * q[2] + Pr[9] * q[3] + Pr[10] * q[4] + Pr[11];
+			if (Zz < 0) return;
 			const double iz = 1.0 / Zz, r0 = Zx * iz - q[0], r1 = Zy * iz - q[1];
 			c += fmin(r0 * r0 + r1 * r1, sq_thr);
-		}
+		});
 		return fp_block_sum(c, s_tmp);
 	};
 	auto pnp_accumulate = [&](const double *P, double *sys /*21 lower + 6*/) {
 		double acc[27];
 #pragma unroll
 		for (int a = 0; a < 27; ++a) acc[a] = 0.0;
-		for (int t = tid; t < n; t += kFitT) {
-			const double *q = aos + 5 * (int64_t)idx[beg + t];
+		double Pr[12];
+#pragma unroll
+		for (int i = 0; i < 12; ++i) Pr[i] = P[i];
+		for_sample_rows5<4>(aos, idx, beg, n, tid, [&](const double *q) {
+			const double *P = Pr;
 			const double X[3] = {q[2], q[3], q[4]};
 			const double Zx = P[0] * X[0] + P[1] * X[1] + P[2] * X[2] + P[3], Zy = P[4] * X[0] + P[5] * X[1] + P[6] * X[2] + P[7],
 			             Zz = P[8] * X[0] + P[9] * X[1] + P[10] * X[2] + P[11];
-			if (Zz < 0) continue;
+			if (Zz < 0) return;
 			const double iz = 1.0 / Zz, zx = Zx * iz, zy = Zy * iz;
 			const double r0 = zx - q[0], r1 = zy - q[1];
-			if (!(r0 * r0 + r1 * r1 < sq_thr)) continue; // loss_fn.weight == 0
+			if (!(r0 * r0 + r1 * r1 < sq_thr)) return; // loss_fn.weight == 0
 			// dZ = [1 0 -zx; 0 1 -zy] / Zz * R
 			double d0[3], d1[3];
 			for (int c = 0; c < 3; ++c) {
@@ -719,9 +770,11 @@ __global__ void __launch_bounds__(kFitT)
 				for (int j = 0; j <= i; ++j, ++a) acc[a] += J0[i] * J0[j] + J1[i] * J1[j];
 #pragma unroll
 			for (int i = 0; i < 6; ++i) acc[21 + i] += J0[i] * r0 + J1[i] * r1;
-		}
+		});
 		fp_block_sums<27>(acc, s_big, sys);
 	};
+	const int sweeps = -lm_accepted;
+	lm_accepted = 0;
 	double cost = pnp_cost(s_pose);
 	double lambda = 1e-3;
 	bool recompute = true;
@@ -790,9 +843,11 @@ __global__ void __launch_bounds__(kFitT)
 		}
 		__syncthreads();
 		if (!s_go) break; // block-uniform
+		++lm_iters;
 		const double cost_new = pnp_cost(s_new);
 		__syncthreads();
 		if (cost_new < cost) {
+			++lm_accepted;
 			if (tid < 12) s_pose[tid] = s_new[tid];
 			lambda /= 10;
 			cost = cost_new;
@@ -810,6 +865,9 @@ __global__ void __launch_bounds__(kFitT)
 			P_out[12 * (int64_t)pb + i] = s_pose[i];
 		}
 		ok_out[pb] = ok ? 1 : 0;
+		if (debug && pb == 0)
+			printf("[k_fit_pnp] n=%d cycles: normalise %lld, DLT sums %lld, Jacobi %lld (%d sweeps), seed %lld, LM %lld (%d steps, %d accepted)\n", n,
+			       clk1 - clk0, clk2 - clk1, clk3 - clk2, sweeps, clk4 - clk3, clock64() - clk4, lm_iters, lm_accepted);
 	}
 }
 
@@ -824,7 +882,8 @@ int launch_fit_f(pxb_ctx *ctx, int P, const int32_t *off, const int32_t *idx, co
 
 int launch_fit_pnp(pxb_ctx *ctx, int P, const int32_t *off, const int32_t *idx, double *P_out, int32_t *ok_out) {
 	if (P <= 0) return PXB_OK;
-	k_fit_pnp<<<(unsigned)P, kFitT, 0, ctx->stream>>>(ctx->pts.aos, off, idx, P_out, ok_out);
+	static const int debug = getenv("PXB_FIT_STATS") ? atoi(getenv("PXB_FIT_STATS")) : 0;
+	k_fit_pnp<<<(unsigned)P, kFitT, 0, ctx->stream>>>(ctx->pts.aos, off, idx, P_out, ok_out, debug);
 	ctx->launches++;
 	PXB_CUDA(cudaGetLastError());
 	return PXB_OK;
