@@ -50,7 +50,8 @@ __device__ __forceinline__ void knn_insert(double (&bd)[KMAX], int (&bi)[KMAX], 
 			ci = ti;
 			placed = true;
 		}
-		if (q == k - 1) worst = bd[q];
+		if (q == k - 1) worst = bd[q]; // (k == KMAX in the instantiation the driver's default degree uses: a static index --
+		                               //  a runtime k makes ptxas shadow the list in local memory for this one read)
 	}
 }
 
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(kKnnQuery *SLICES)
                 int32_t *__restrict__ deg) {
 	__shared__ double s_d[SLICES - 1][KMAX][kKnnQuery];
 	__shared__ int s_i[SLICES - 1][KMAX][kKnnQuery];
+	if (KMAX == 5) k = 5; // (compile-time list length: see launch_knn_dim)
 	const int q = threadIdx.x % kKnnQuery, slice = threadIdx.x / kKnnQuery;
 	const int64_t i = (int64_t)blockIdx.x * kKnnQuery + q;
 	double me[DIM];
@@ -141,7 +143,9 @@ __global__ void __launch_bounds__(kKnnQuery *SLICES)
 template <int DIM>
 static void launch_knn_dim(pxb_ctx *ctx, unsigned grid, double radius, int k, int32_t *nbr, int32_t *deg) {
 	const Points &p = ctx->pts;
-	if (k <= 8)
+	if (k == 5) // the driver's default degree (graph_degree()): list length known at compile time
+		k_knn_graph<DIM, 5, 8><<<grid, kKnnQuery * 8, 0, ctx->stream>>>(p.aos, p.N, radius * radius, 5, nbr, deg);
+	else if (k <= 8)
 		k_knn_graph<DIM, 8, 8><<<grid, kKnnQuery * 8, 0, ctx->stream>>>(p.aos, p.N, radius * radius, k, nbr, deg);
 	else
 		k_knn_graph<DIM, kKnnMax, 4><<<grid, kKnnQuery * 4, 0, ctx->stream>>>(p.aos, p.N, radius * radius, k, nbr, deg);
