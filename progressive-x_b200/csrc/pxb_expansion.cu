@@ -1252,7 +1252,8 @@ __global__ void k_exp_assemble(int64_t N, int L1, int alpha, double lambda, doub
                                const int32_t *__restrict__ lab, const int32_t *__restrict__ goff,
                                const int32_t *__restrict__ gidx, const int32_t *__restrict__ label_count,
                                const int32_t *__restrict__ arc_rev, double *__restrict__ cap, double *__restrict__ excess,
-                               double *__restrict__ sink_cap, int32_t *__restrict__ flags) {
+                               double *__restrict__ sink_cap, int32_t *__restrict__ flags, const int32_t *__restrict__ stop) {
+	if (stop && *reinterpret_cast<const volatile int32_t *>(stop) != 0) return; // an earlier move of the batch changed the labelling
 	const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (s < 16) flags[s] = 0; // counters and status words of the max-flow kernel that follows
 	if (s >= N + L1) return;
@@ -1420,6 +1421,36 @@ static int exp_skeleton(pxb_ctx *ctx, int64_t N, const int32_t *off, const int32
 	return PXB_OK;
 }
 
+// Closes one move of a speculative batch (one block): how many sites would switch to alpha (SOURCE side: cannot reach the
+// sink, GCoptimization.cpp:451-469), the max-flow status words of the move, and -- if anything switches or the cut did not
+// converge -- the stop flag that turns the remaining launches of the batch into no-ops. res: 8 ints per move.
+constexpr int kMoveRes = 8;
+__global__ void __launch_bounds__(1024)
+    k_exp_close_move(int64_t N, int n_nodes, int alpha, const int32_t *__restrict__ lab, const int32_t *__restrict__ h,
+                     const int32_t *__restrict__ flags, int32_t *__restrict__ res, int32_t *__restrict__ stop) {
+	if (*reinterpret_cast<volatile int32_t *>(stop) != 0) return;
+	__shared__ int s_cnt;
+	if (threadIdx.x == 0) s_cnt = 0;
+	__syncthreads();
+	int c = 0;
+	for (int64_t i = threadIdx.x; i < N; i += blockDim.x) c += (lab[i] != alpha && !(h[i] < n_nodes)) ? 1 : 0;
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+	if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_cnt, c);
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		const bool converged = flags[7] == 1 && flags[6] != 0;
+		res[0] = 1; // executed
+		res[1] = s_cnt;
+		res[2] = flags[6];
+		res[3] = flags[7];
+		res[4] = flags[8];
+		res[5] = flags[10];
+		res[6] = flags[12];
+		if (s_cnt > 0 || !converged) *stop = 1;
+	}
+}
+
 int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t L1, double lambda, double label_cost,
                            const int32_t *csr_off_host, const int32_t *csr_idx_host, const int32_t *init_labels_dev,
                            int32_t *labels_out_dev, double *energy_out_host) {
@@ -1470,7 +1501,8 @@ int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t
 	const int64_t m = E + 2 * N;
 
 	// ---- device arena: per-call copy of the arcs (the auxiliary part is rewired with the labelling) + per-move state ----
-	const size_t n_int = (size_t)(n + 1) + 2 * (size_t)m + 2 * (size_t)N + 2 * (size_t)(L1 + 1) + 2 * (size_t)n + 32;
+	const size_t n_int = (size_t)(n + 1) + 2 * (size_t)m + 2 * (size_t)N + 2 * (size_t)(L1 + 1) + 2 * (size_t)n + 32 +
+	                     (size_t)kMoveRes * (size_t)(L1 + 1) + 8;
 	const size_t bytes = sizeof(double) * ((size_t)m + 2 * (size_t)n) + sizeof(int32_t) * n_int + 256;
 	PXB_TRY(ctx->partials.reserve(bytes));
 	double *d_cap = ctx->partials.as<double>(), *d_excess = d_cap + m, *d_sink = d_excess + n;
@@ -1479,6 +1511,8 @@ int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t
 	int32_t *d_label_off = d_rank + N, *d_label_count = d_label_off + (L1 + 1);
 	// heights and kernel flags are adjacent: they come back in one copy after every move
 	int32_t *d_h0 = d_label_count + (L1 + 1), *d_flags = d_h0 + n, *d_h1 = d_flags + 16;
+	// results of a speculative batch of moves: [stop | pad | L1 x kMoveRes] (one copy back per batch, after the heights)
+	int32_t *d_stop = d_h1 + n + 8, *d_res = d_stop + 2;
 	const int32_t *d_goff = sk.d_goff, *d_gidx = sk.d_gidx;
 	PXB_CUDA(cudaMemcpyAsync(d_arc_off, sk.arc_off, sizeof(int32_t) * (size_t)(N + 1), cudaMemcpyDeviceToDevice, st));
 	PXB_CUDA(cudaMemcpyAsync(d_head, sk.head, sizeof(int32_t) * (size_t)(E + N), cudaMemcpyDeviceToDevice, st));
@@ -1524,71 +1558,110 @@ int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t
 		sk.plan_key = mc_env_key() + (uint64_t)L1 * 0x9E3779B97F4A7C15ull;
 	}
 	const bool use_cluster = sk.plan.ok;
-	PXB_TRY(ctx->reserve_pinned(sizeof(int32_t) * ((size_t)n + 16)));
-	int32_t *h_host = static_cast<int32_t *>(ctx->pinned), *flags_host = h_host + n;
+	const size_t res_ints = 2 + (size_t)kMoveRes * (size_t)L1;
+	PXB_TRY(ctx->reserve_pinned(sizeof(int32_t) * ((size_t)n + 16 + res_ints)));
+	int32_t *h_host = static_cast<int32_t *>(ctx->pinned), *flags_host = h_host + n, *res_host = flags_host + 16 + 2;
+	// Speculative batches (cluster-resident engine only). Most moves change nothing -- every labelling ends with a full
+	// cycle of them -- but the host used to wait for each one to learn that. The moves of a cycle are enqueued back to back;
+	// k_exp_close_move counts on the device how many sites a move would switch and, when any does, raises the stop flag that
+	// turns the remaining launches of the batch into no-ops: the heights then still belong to that move, and the host
+	// continues exactly as the one-move-per-wait loop would (candidate labelling, energies, accept or not, next label).
+	// The batch length adapts: 1 after a move that switched something (the first sweep from the all-zero labelling),
+	// the rest of the cycle after one that did not. PXB_EXP_SPEC=0 restores one wait per move.
+	const bool speculate = use_cluster && !(getenv("PXB_EXP_SPEC") && atoi(getenv("PXB_EXP_SPEC")) == 0);
+	int spec = init_labels_dev ? L1 : 1;
 
 	EnergyCache ec;
 	ec.init(P, lab);
 	double new_energy = ec.energy(P, lab, ec.pairs), old_energy; // always the energy of `lab`
 	std::vector<int32_t> cand, switched;
+	std::vector<int> batch;
 	const bool stats = getenv("PXB_MF_STATS") != nullptr, check_energy = getenv("PXB_CHECK_ENERGY") != nullptr;
 	for (int cycle = 1; cycle <= 1000; ++cycle) { // GCoptimization.cpp:1062-1077
 		old_energy = new_energy;
-		for (int alpha = 0; alpha < L1; ++alpha) { // oneExpansionIteration, fixed label order 0..L
-			if (label_count[alpha] == (int32_t)N) continue; // no site to move (alpha_expansion returns at size == 0)
+		int alpha = 0;
+		while (alpha < L1) { // oneExpansionIteration, fixed label order 0..L
+			batch.clear();
+			int a = alpha;
+			for (; a < L1 && (int)batch.size() < (speculate ? spec : 1); ++a)
+				if (label_count[a] != (int32_t)N) batch.push_back(a); // (no site to move: alpha_expansion returns at size == 0)
+			if (batch.empty()) break;
 			const auto t_move = std::chrono::steady_clock::now();
-			k_exp_assemble<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(N, L1, alpha, lambda, label_cost, D_dev, d_lab, d_goff, d_gidx,
-			                                                          d_label_count, d_rev, d_cap, d_excess, d_sink, d_flags);
-			ctx->launches++;
-			if (use_cluster) {
-				PXB_TRY(mf_cluster_launch(ctx, G, sk.plan));
-			} else {
-				void *args[] = {&G};
-				PXB_CUDA(cudaLaunchCooperativeKernel((void *)k_maxflow, dim3(grid), dim3(kMfThreads), args, lc.smem, st));
+			if (speculate) PXB_CUDA(cudaMemsetAsync(d_stop, 0, sizeof(int32_t) * res_ints, st));
+			for (int al : batch) {
+				k_exp_assemble<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(N, L1, al, lambda, label_cost, D_dev, d_lab, d_goff, d_gidx,
+				                                                          d_label_count, d_rev, d_cap, d_excess, d_sink, d_flags,
+				                                                          speculate ? d_stop : nullptr);
 				ctx->launches++;
+				if (use_cluster) {
+					G.stop = speculate ? d_stop : nullptr;
+					PXB_TRY(mf_cluster_launch(ctx, G, sk.plan));
+				} else {
+					void *args[] = {&G};
+					PXB_CUDA(cudaLaunchCooperativeKernel((void *)k_maxflow, dim3(grid), dim3(kMfThreads), args, lc.smem, st));
+					ctx->launches++;
+				}
+				if (speculate) {
+					k_exp_close_move<<<1, 1024, 0, st>>>(N, n, al, d_lab, d_h0, d_flags, d_res + (size_t)kMoveRes * al, d_stop);
+					ctx->launches++;
+				}
 			}
 			PXB_CUDA(cudaMemcpyAsync(h_host, d_h0, sizeof(int32_t) * ((size_t)n + 16), cudaMemcpyDeviceToHost, st)); // + flags
+			if (speculate) PXB_CUDA(cudaMemcpyAsync(res_host - 2, d_stop, sizeof(int32_t) * res_ints, cudaMemcpyDeviceToHost, st));
 			PXB_TRY(ctx_wait(ctx));
-			if (flags_host[7] != 1 || flags_host[6] == 0) {
-				set_error("max-flow did not converge within %d relabel rounds", kMaxRounds);
-				return PXB_ERR_CUDA;
-			}
 			ms_cut += since(t_move);
-			const auto t_en = std::chrono::steady_clock::now();
-			if (stats && getenv("PXB_MF_STATS")[0] == '2')
-				fprintf(stderr, "[pxb expansion] alpha=%d active=%d rounds=%d bfs_levels=%d relabel=%.2f ms async=%.2f ms wall=%.2f ms\n",
-				        alpha, (int)(N - label_count[alpha]), flags_host[6], flags_host[8], (double)flags_host[10] * 64 / 1.965e6,
-				        (double)flags_host[12] * 64 / 1.965e6,
-				        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_move).count());
-			// candidate labelling: SOURCE side (cannot reach the sink) takes alpha (:451-469)
-			cand = lab;
-			switched.clear();
-			for (int64_t i = 0; i < N; ++i)
-				if (lab[i] != alpha && !(h_host[i] < n)) {
-					cand[i] = alpha;
-					switched.push_back((int32_t)i);
+			int next_alpha = a;
+			bool any_switch = false;
+			for (int al : batch) {
+				const int32_t *mv = res_host + (size_t)kMoveRes * al; // executed, switched, flags 6 / 7 / 8 / 10 / 12
+				if (speculate && !mv[0]) break; // (behind the move that stopped the batch)
+				const int32_t rounds = speculate ? mv[2] : flags_host[6], status = speculate ? mv[3] : flags_host[7];
+				if (status != 1 || rounds == 0) {
+					set_error("max-flow did not converge within %d relabel rounds", kMaxRounds);
+					return PXB_ERR_CUDA;
 				}
-			if (switched.empty()) {
+				const auto t_en = std::chrono::steady_clock::now();
+				if (stats && getenv("PXB_MF_STATS")[0] == '2')
+					fprintf(stderr, "[pxb expansion] alpha=%d active=%d rounds=%d bfs_levels=%d relabel=%.2f ms async=%.2f ms (batch of %d)\n",
+					        al, (int)(N - label_count[al]), rounds, speculate ? mv[4] : flags_host[8],
+					        (double)(speculate ? mv[5] : flags_host[10]) * 64 / 1.965e6,
+					        (double)(speculate ? mv[6] : flags_host[12]) * 64 / 1.965e6, (int)batch.size());
+				if (speculate && mv[1] == 0) continue; // nothing switches
+				// candidate labelling: SOURCE side (cannot reach the sink) takes alpha (:451-469)
+				cand = lab;
+				switched.clear();
+				for (int64_t i = 0; i < N; ++i)
+					if (lab[i] != al && !(h_host[i] < n)) {
+						cand[i] = al;
+						switched.push_back((int32_t)i);
+					}
+				if (switched.empty()) {
+					ms_energy += since(t_en);
+					continue;
+				}
+				any_switch = true;
+				next_alpha = al + 1;
+				// the reference applies the move iff afterExpansionEnergy < m_beforeExpansionEnergy (:1286); both are the
+				// energies of the two labellings, evaluated here directly (in the reference's summation order)
+				const int64_t k_after = ec.pairs_after(P, lab, cand, switched);
+				const double before = new_energy, after = ec.energy(P, cand, k_after);
+				if (check_energy && after != compute_energy(P, cand)) { // PXB_CHECK_ENERGY=1: the full edge walk must agree bit for bit
+					set_error("incremental labelling energy %.17g differs from the full evaluation %.17g", after, compute_energy(P, cand));
+					return PXB_ERR_STATE;
+				}
 				ms_energy += since(t_en);
-				continue;
+				if (after < before) {
+					const auto t_p = std::chrono::steady_clock::now();
+					lab.swap(cand);
+					new_energy = after;
+					ec.pairs = k_after;
+					PXB_TRY(push_labelling());
+					ms_push += since(t_p);
+				}
+				break; // (speculative batch: the launches behind this move did nothing; otherwise the batch had one move)
 			}
-			// the reference applies the move iff afterExpansionEnergy < m_beforeExpansionEnergy (:1286); both are the
-			// energies of the two labellings, evaluated here directly (in the reference's summation order)
-			const int64_t k_after = ec.pairs_after(P, lab, cand, switched);
-			const double before = new_energy, after = ec.energy(P, cand, k_after);
-			if (check_energy && after != compute_energy(P, cand)) { // PXB_CHECK_ENERGY=1: the full edge walk must agree bit for bit
-				set_error("incremental labelling energy %.17g differs from the full evaluation %.17g", after, compute_energy(P, cand));
-				return PXB_ERR_STATE;
-			}
-			ms_energy += since(t_en);
-			if (after < before) {
-				const auto t_p = std::chrono::steady_clock::now();
-				lab.swap(cand);
-				new_energy = after;
-				ec.pairs = k_after;
-				PXB_TRY(push_labelling());
-				ms_push += since(t_p);
-			}
+			spec = any_switch ? 1 : L1;
+			alpha = next_alpha;
 		}
 		if (new_energy == old_energy) break;
 	}

@@ -17,6 +17,8 @@ struct FlowGraphDev {
 	double *cap, *excess, *sink_cap;
 	int32_t *height[2];
 	int32_t *flags; // [0..2] BFS 'changed' (level mod 3), [3..5] 'active' (pulse mod 3), [6] pulses, [7] status
+	const int32_t *stop = nullptr; // cluster engine only: when set and *stop != 0 the launch does nothing (a speculative
+	                               // batch of expansion moves was cut short by an earlier move, pxb_expansion.cu)
 	int async_cycles, idle_checks; // tuning knobs of the asynchronous phase (PXB_MF_ASYNC, PXB_MF_IDLE)
 	int local_exit;                // PXB_MF_LOCAL_EXIT=1: blocks leave the phase on their own (A/B)
 	long long quiet_cycles;        // PXB_MF_QUIET_US: grid-wide silence that ends the phase

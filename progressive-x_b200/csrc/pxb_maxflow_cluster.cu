@@ -47,6 +47,7 @@ struct McParams {
 	const int32_t *arc_off, *arc_head, *arc_rev;
 	const double *cap, *excess, *sink_cap;
 	int32_t *height, *flags;
+	const int32_t *stop;
 	int max_cycles, check_every, debug;
 };
 
@@ -209,6 +210,7 @@ __global__ void __launch_bounds__(kMcThreads, 1) k_maxflow_cluster(McParams P) {
 	__shared__ double s_warp[kMcThreads / 32];
 	__shared__ double s_auxe[2][kMcMaxAux];
 	__shared__ double s_grant;
+	if (P.stop && *reinterpret_cast<const volatile int32_t *>(P.stop) != 0) return; // (written by an earlier kernel: uniform)
 	unsigned rank, nranks;
 	asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
 	asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(nranks));
@@ -531,6 +533,7 @@ int mf_cluster_launch(pxb_ctx *ctx, const FlowGraphDev &G, const McPlan &plan) {
 	P.sink_cap = G.sink_cap;
 	P.height = G.height[0];
 	P.flags = G.flags;
+	P.stop = G.stop;
 	P.check_every = getenv("PXB_MC_CHECK") ? std::max(1, atoi(getenv("PXB_MC_CHECK"))) : 8;
 	const int cycles = getenv("PXB_MC_CYCLES") ? std::max(1, atoi(getenv("PXB_MC_CYCLES"))) : 64;
 	P.max_cycles = (cycles + P.check_every - 1) / P.check_every * P.check_every;
