@@ -1187,7 +1187,7 @@ int Driver::local_optimization(uint64_t lo_seed, std::vector<double> &best_model
 	Score max_score = best_score;
 	std::vector<double> lo_model = best_model;
 	LoStep st;
-	++lo_number_;
+	++lo_number_; // GCRANSAC.h:806 -- on top of the caller's increment (:486 / :535): the reference's statistic counts a run twice
 	while (++graph_cut_number_ < s_.max_graph_cut_number) {
 		bool updated = false;
 		PXB_TRY(lo_step(lo_model.data(), lo_seed, lo_events_++, T2, st));
