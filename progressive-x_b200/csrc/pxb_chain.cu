@@ -89,6 +89,8 @@ template <bool BITS>
 __global__ void __launch_bounds__(kListThreads)
     k_flag_compact(const void *__restrict__ flags, int64_t N, int32_t *__restrict__ idx, int64_t *__restrict__ count_out,
                    int32_t *__restrict__ off2 /* optional: off2[0] = 0, off2[1] = count (a one-problem CSR) */) {
+	pdl_launch_dependents();
+	pdl_wait();
 	__shared__ int s_warp[32];
 	__shared__ int s_total;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -174,6 +176,8 @@ constexpr int kLoMaxSample = 64;
 __global__ void __launch_bounds__(32)
     k_lo_sample(const int32_t *__restrict__ inl, const int64_t *__restrict__ count_in, int m, int limit, int trials,
                 const uint64_t *__restrict__ seed_event, int32_t *__restrict__ off /*trials + 1*/, int32_t *__restrict__ idx) {
+	pdl_launch_dependents();
+	pdl_wait();
 	const uint64_t seed = seed_event[0], event = seed_event[1]; // on the device: the launch is part of a replayed graph
 	const int64_t count = count_in[0];
 	const int t = blockIdx.x, lane = threadIdx.x;
@@ -225,7 +229,7 @@ __global__ void __launch_bounds__(32)
 }
 
 int launch_flag_compact(pxb_ctx *ctx, const uint8_t *flags_dev, int64_t N, int32_t *idx_dev, int64_t *count_dev, int32_t *off2_dev) {
-	k_flag_compact<false><<<1, kListThreads, 0, ctx->stream>>>(flags_dev, N, idx_dev, count_dev, off2_dev);
+	PXB_CUDA(launch_pdl(k_flag_compact<false>, dim3(1), dim3(kListThreads), 0, ctx->stream, flags_dev, N, idx_dev, count_dev, off2_dev));
 	ctx->launches++;
 	PXB_CUDA(cudaGetLastError());
 	return PXB_OK;
@@ -242,7 +246,7 @@ int launch_lo_sample(pxb_ctx *ctx, const int32_t *inl_dev, const int64_t *count_
 		set_error("local optimisation sample of %d points / %d trials exceeds the kernel limits", limit, trials);
 		return PXB_ERR_UNSUPPORTED;
 	}
-	k_lo_sample<<<(unsigned)trials, 32, 0, ctx->stream>>>(inl_dev, count_dev, m, limit, trials, seed_event_dev, off_dev, idx_dev);
+	PXB_CUDA(launch_pdl(k_lo_sample, dim3((unsigned)trials), dim3(32), 0, ctx->stream, inl_dev, count_dev, m, limit, trials, seed_event_dev, off_dev, idx_dev));
 	ctx->launches++;
 	PXB_CUDA(cudaGetLastError());
 	return PXB_OK;

@@ -694,7 +694,7 @@ class Driver {
 			return PXB_OK;
 		};
 		if (slots)
-			PXB_TRY(run_chain(mix_key({kChainRefill, buffers_key(), (uint64_t)K, (uint64_t)s_.plane_parallax, bits(T2)}), enqueue));
+			PXB_TRY(run_chain((chain_kind_ = kChainRefill, mix_key)({kChainRefill, buffers_key(), (uint64_t)K, (uint64_t)s_.plane_parallax, bits(T2)}), enqueue));
 		else
 			PXB_TRY(enqueue());
 		PXB_TRY(api_sync(ctx_));
@@ -754,7 +754,29 @@ class Driver {
 	// Runs `enqueue` (a fixed sequence of asynchronous copies and launches on the context's stream that only depends on
 	// `key`): plainly the first time a key is seen (buffers get allocated), captured into a CUDA graph the second time,
 	// replayed with one cudaGraphLaunch from then on. PXB_GRAPHS=0 disables capturing.
+	// PXB_PROFILE=2: the GPU time of every chain (CUDA events around its launch, waited for at once -- the caller waits
+	// right afterwards anyway) goes into the phase table beside the host's wall time for the same call
 	template <class Enqueue> int run_chain(uint64_t key, Enqueue &&enqueue) {
+		static const bool gpu_timed = getenv("PXB_PROFILE") && atoi(getenv("PXB_PROFILE")) == 2;
+		if (!gpu_timed) return run_chain_untimed(key, enqueue);
+		static thread_local cudaEvent_t ev[2] = {nullptr, nullptr};
+		if (!ev[0]) {
+			PXB_CUDA(cudaEventCreate(&ev[0]));
+			PXB_CUDA(cudaEventCreate(&ev[1]));
+		}
+		PXB_CUDA(cudaEventRecord(ev[0], ctx_->stream));
+		PXB_TRY(run_chain_untimed(key, enqueue));
+		PXB_CUDA(cudaEventRecord(ev[1], ctx_->stream));
+		PXB_CUDA(cudaEventSynchronize(ev[1]));
+		float ms = 0;
+		cudaEventElapsedTime(&ms, ev[0], ev[1]);
+		static const char *names[] = {"gpu: ?", "gpu: refill chain", "gpu: lo_step chain", "gpu: tail_step chain", "gpu: pearl chain",
+		                              "gpu: finish chain"};
+		prof_.add(names[chain_kind_ <= 5 ? chain_kind_ : 0], ms);
+		return PXB_OK;
+	}
+	uint64_t chain_kind_ = 0; // kind of the chain being keyed (set by mix_key's callers through chain_key)
+	template <class Enqueue> int run_chain_untimed(uint64_t key, Enqueue &&enqueue) {
 		static const bool enabled = !(getenv("PXB_GRAPHS") && atoi(getenv("PXB_GRAPHS")) == 0);
 		if (!enabled) return enqueue();
 		auto &cache = ctx_->chain_graphs;
@@ -1130,13 +1152,13 @@ int Driver::lo_step(const double *model, uint64_t lo_seed, uint64_t event, doubl
 			PXB_TRY(api_h2d(ctx_, par, hin, in_bytes));
 		uint8_t *d_seg = nullptr;
 		int32_t *d_mf_flags = nullptr;
+		PXB_CUDA(cudaMemsetAsync(pk, 0, pack_bytes, ctx_->stream)); // (before the labelling: kernel -> kernel edges behind it)
 		if (!cut) {
 			d_seg = ctx_->outA.as<uint8_t>();
 			PXB_TRY(launch_lo_unary_cut(ctx_, d_model, s_.threshold, s_.lambda, d_seg));
 		} else {
 			PXB_TRY(lo_labeling_enqueue(ctx_, d_model, s_.threshold, s_.lambda, graph_.off.data(), graph_.idx.data(), &d_seg, &d_mf_flags));
 		}
-		PXB_CUDA(cudaMemsetAsync(pk, 0, pack_bytes, ctx_->stream));
 		PXB_TRY(launch_flag_compact(ctx_, d_seg, N_, d_inl, reinterpret_cast<int64_t *>(pk), nullptr));
 		// (the labelling's scratch is shared with the score kernel's partial sums: take its status words now)
 		if (d_mf_flags) PXB_CUDA(cudaMemcpyAsync(pk + o_flags, d_mf_flags, 64, cudaMemcpyDeviceToDevice, ctx_->stream));
@@ -1155,7 +1177,7 @@ int Driver::lo_step(const double *model, uint64_t lo_seed, uint64_t event, doubl
 	// cached skeleton is a plain launch)
 	uint64_t cut_signature = 0;
 	if (slots && (!cut || lo_labeling_capturable(ctx_, graph_.off.data(), graph_.idx.data(), &cut_signature)))
-		PXB_TRY(run_chain(mix_key({kChainLo, buffers_key(), (uint64_t)trials, (uint64_t)limit, bits(T2), bits(s_.threshold), bits(s_.lambda), cut_signature}), enqueue));
+		PXB_TRY(run_chain((chain_kind_ = kChainLo, mix_key)({kChainLo, buffers_key(), (uint64_t)trials, (uint64_t)limit, bits(T2), bits(s_.threshold), bits(s_.lambda), cut_signature}), enqueue));
 	else
 		PXB_TRY(enqueue());
 	PXB_TRY(api_sync(ctx_));
@@ -1266,7 +1288,7 @@ int Driver::tail_step(const double *model, bool weighted, double T2, TailStep &o
 		return PXB_OK;
 	};
 	if (slots)
-		PXB_TRY(run_chain(mix_key({kChainTail, buffers_key(), (uint64_t)weighted, bits(T2)}), enqueue));
+		PXB_TRY(run_chain((chain_kind_ = kChainTail, mix_key)({kChainTail, buffers_key(), (uint64_t)weighted, bits(T2)}), enqueue));
 	else
 		PXB_TRY(enqueue());
 	PXB_TRY(api_sync(ctx_));
@@ -1492,7 +1514,7 @@ int Driver::proposal_finish(const double *model, std::vector<int64_t> &inliers, 
 		return PXB_OK;
 	};
 	if (slots)
-		PXB_TRY(run_chain(mix_key({kChainFinish, buffers_key(), bits(ctx_->pref2.ptr), bits(T2), bits(T)}), enqueue));
+		PXB_TRY(run_chain((chain_kind_ = kChainFinish, mix_key)({kChainFinish, buffers_key(), bits(ctx_->pref2.ptr), bits(T2), bits(T)}), enqueue));
 	else
 		PXB_TRY(enqueue());
 	PXB_TRY(api_sync(ctx_));
@@ -1603,7 +1625,7 @@ int Driver::pearl() {
 		// replayable when the sweep is the single-block greedy kernel (no smoothness term, N <= 16384: the alpha-expansion has
 		// a host move loop, the multi-block greedy sweep is a cooperative launch)
 		if (slots && !smooth && N_ <= 16384) {
-			PXB_TRY(run_chain(mix_key({kChainPearl, buffers_key(), (uint64_t)L, (uint64_t)init_prev, bits(s_.threshold), bits(s_.lambda),
+			PXB_TRY(run_chain((chain_kind_ = kChainPearl, mix_key)({kChainPearl, buffers_key(), (uint64_t)L, (uint64_t)init_prev, bits(s_.threshold), bits(s_.lambda),
 			                           bits(label_cost), bits(d_w)}), enqueue));
 			energy_dev = ctx_->outB.as<double>(); // the greedy sweep's energy sits in the pack (replays do not run the lambda)
 		} else {

@@ -231,6 +231,8 @@ __global__ void __launch_bounds__(kFitThreads)
     k_fit_h(const double *__restrict__ aos, const int32_t *__restrict__ off, const int32_t *__restrict__ idx,
             const double *__restrict__ weights, double *__restrict__ H_out, int32_t *__restrict__ ok_out) {
 	__shared__ double s_acc[44];
+	pdl_launch_dependents();
+	pdl_wait();
 	const int pb = blockIdx.x;
 	const int beg = off[pb], n = off[pb + 1] - beg;
 	const int tid = threadIdx.x;
@@ -433,7 +435,7 @@ int launch_fit_h(pxb_ctx *ctx, int P, const int32_t *off, const int32_t *idx, co
 	if (use_mma)
 		k_fit_h<true><<<(unsigned)P, kFitThreads, 0, ctx->stream>>>(ctx->pts.aos, off, idx, weights, H_out, ok_out);
 	else
-		k_fit_h<false><<<(unsigned)P, kFitThreads, 0, ctx->stream>>>(ctx->pts.aos, off, idx, weights, H_out, ok_out);
+		PXB_CUDA(launch_pdl(k_fit_h<false>, dim3((unsigned)P), dim3(kFitThreads), 0, ctx->stream, ctx->pts.aos, off, idx, weights, H_out, ok_out));
 	ctx->launches++;
 	PXB_CUDA(cudaGetLastError());
 	return PXB_OK;

@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -148,6 +149,36 @@ struct pxb_ctx {
 };
 
 namespace pxb {
+// ---- programmatic dependent launch (sm_90+) ------------------------------------------------------------------------------
+// The driver's chains are sequences of 4-15 us kernels; between two kernel nodes of a captured graph the GPU idles for
+// the launch latency of the second one. A kernel launched with launch_pdl may be SCHEDULED while its predecessor in the
+// stream still runs: it must call pdl_wait() before it touches anything a predecessor wrote (the wait returns when the
+// preceding grid -- and, transitively, everything before it -- has completed and its writes are visible), and a small
+// predecessor may call pdl_launch_dependents() at its top so that the successor's blocks are resident, parked at their
+// wait, by the time it finishes. Both instructions do nothing in a kernel that was launched the ordinary way, and an edge
+// whose upstream node is a copy or a memset is an ordinary dependency. PXB_PDL=0 launches everything the ordinary way.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+inline bool pdl_enabled() {
+	static const bool on = !(getenv("PXB_PDL") && atoi(getenv("PXB_PDL")) == 0);
+	return on;
+}
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = grid;
+	cfg.blockDim = block;
+	cfg.dynamicSmemBytes = smem;
+	cfg.stream = st;
+	cudaLaunchAttribute at[1];
+	at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+	cfg.attrs = at;
+	cfg.numAttrs = 1;
+	return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 constexpr size_t kChainInBytes = size_t(256) << 10, kChainOutBytes = size_t(1) << 20;
 void lo_skeleton_free(void *p);
 void exp_skeleton_free(void *p);

@@ -547,6 +547,7 @@ __global__ void k_lo_unary_cut(const double *__restrict__ soa, int64_t stride, i
                                double T, double one_minus, uint8_t *__restrict__ inlier) {
 	constexpr int DIM = ModelTraits<TYPE>::kDim, MS = ModelTraits<TYPE>::kSize;
 	__shared__ double m[MS];
+	pdl_launch_dependents(); // (first kernel of the local-optimisation chain: the ordered compaction may be scheduled at once)
 	if (threadIdx.x < MS) m[threadIdx.x] = model[threadIdx.x];
 	__syncthreads();
 	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -176,6 +176,8 @@ template <int TYPE>
 __global__ void k_screen_prepare(const double *__restrict__ models, int64_t K, double T2, const NormDev *__restrict__ norm,
                                  float *__restrict__ consts, float *__restrict__ mf) {
 	constexpr int MS = ModelTraits<TYPE>::kSize, MF = ScreenTraits<TYPE>::kFloats;
+	pdl_launch_dependents();
+	pdl_wait();
 	const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	const NormDev nd = *norm;
 	if (k == 0) {
@@ -207,6 +209,7 @@ __global__ void __launch_bounds__(kThreads, 3)
 	using L = ScoreSmem<TYPE, HAS_CP>;
 	constexpr int DIM = L::DIM, MS = ModelTraits<TYPE>::kSize, MP = L::MP, MF = L::MF;
 	extern __shared__ __align__(16) unsigned char smem[];
+	pdl_wait();
 	double *s_pts = reinterpret_cast<double *>(smem + L::kPts);
 	double *s_cp = reinterpret_cast<double *>(smem + L::kCp);
 	double *s_models = reinterpret_cast<double *>(smem + L::kModels);
@@ -298,6 +301,7 @@ __global__ void __launch_bounds__(kThreads, 3)
 
 __global__ void k_score_finalize(const ScorePartial *__restrict__ partials, int64_t K, int nchunks,
                                  int64_t *__restrict__ count, double *__restrict__ value, double *__restrict__ shared) {
+	pdl_wait();
 	const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (k >= K) return;
 	double v = 0.0, s = 0.0;
@@ -342,8 +346,8 @@ static void launch_screened(pxb_ctx *ctx, int nchunks, const float *consts, cons
 	}
 	const int64_t tile = (int64_t)tile_hyps * PASSES;
 	dim3 grid((unsigned)nchunks, (unsigned)((kk + tile - 1) / tile));
-	k_score_screened<TYPE, HAS_CP, PASSES><<<grid, kThreads, kBytes, ctx->stream>>>(p.soa, p.stride, p.N, p.f32n, p.q, consts, mf, m,
-	                                                                             kk, T2, cp, pp, nchunks, tile_hyps);
+	(void)launch_pdl(k_score_screened<TYPE, HAS_CP, PASSES>, grid, dim3(kThreads), (size_t)kBytes, ctx->stream, p.soa, p.stride, p.N, p.f32n,
+	                 p.q, consts, mf, m, kk, T2, cp, pp, nchunks, tile_hyps);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -513,7 +517,7 @@ template <int TYPE> static int launch_mask_t(pxb_ctx *ctx, const double *models,
 		const double *m = models + done * ModelTraits<TYPE>::kSize;
 		PXB_TRY(ctx->screen.reserve(sizeof(float) * (4 + (size_t)kk * MF)));
 		float *consts = ctx->screen.as<float>(), *mf = consts + 4;
-		k_screen_prepare<TYPE><<<(unsigned)((kk + 127) / 128), 128, 0, ctx->stream>>>(m, kk, T2, p.norm, consts, mf);
+		PXB_CUDA(launch_pdl(k_screen_prepare<TYPE>, dim3((unsigned)((kk + 127) / 128)), dim3(128), 0, ctx->stream, m, kk, T2, p.norm, consts, mf));
 		dim3 grid((unsigned)nchunks, (unsigned)((kk + kScHyps - 1) / kScHyps));
 		k_mask_screened<TYPE><<<grid, kThreads, kBytes, ctx->stream>>>(p.soa, p.stride, p.N, p.f32n, p.q, consts, mf, m, kk, T2,
 		                                                              mask + done * words, words);
@@ -537,7 +541,7 @@ static int launch_partial(pxb_ctx *ctx, int nchunks, const double *m, int64_t kk
 	constexpr int MF = ScreenTraits<TYPE>::kFloats;
 	PXB_TRY(ctx->screen.reserve(sizeof(float) * (4 + (size_t)kk * MF)));
 	float *consts = ctx->screen.as<float>(), *mf = consts + 4;
-	k_screen_prepare<TYPE><<<(unsigned)((kk + 127) / 128), 128, 0, ctx->stream>>>(m, kk, T2, ctx->pts.norm, consts, mf);
+	PXB_CUDA(launch_pdl(k_screen_prepare<TYPE>, dim3((unsigned)((kk + 127) / 128)), dim3(128), 0, ctx->stream, m, kk, T2, ctx->pts.norm, consts, mf));
 	ctx->launches++;
 	// big batches walk 4 tiles of 32 hypotheses per block (the per-block prologue -- staging 1024 points -- is paid once);
 	// RANSAC-sized batches keep one tile per block so that the grid still fills the GPU
@@ -579,7 +583,7 @@ int launch_score_compound(pxb_ctx *ctx, const double *models, int64_t K, double 
 		PXB_TRY(rc);
 		done += kk;
 	}
-	k_score_finalize<<<(unsigned)((K + 127) / 128), 128, 0, ctx->stream>>>(part, K, nchunks, count, value_sum, shared);
+	PXB_CUDA(launch_pdl(k_score_finalize, dim3((unsigned)((K + 127) / 128)), dim3(128), 0, ctx->stream, part, K, nchunks, count, value_sum, shared));
 	ctx->launches++;
 	PXB_CUDA(cudaGetLastError());
 	return PXB_OK;

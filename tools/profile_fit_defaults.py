@@ -8,7 +8,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "progressive-x_b200"))
-os.environ["PXB_PROFILE"] = "1"
+os.environ.setdefault("PXB_PROFILE", "1")
 import pyprogressivex  # noqa: E402
 from pyprogressivex import synthetic as syn  # noqa: E402
 
