@@ -48,7 +48,7 @@ struct McParams {
 	const double *cap, *excess, *sink_cap;
 	int32_t *height, *flags;
 	const int32_t *stop;
-	int max_cycles, check_every, debug;
+	int max_cycles, check_every, debug, bfs_cap, cap_rounds;
 };
 
 // ---- distributed shared memory primitives -------------------------------------------------------------------------
@@ -297,6 +297,22 @@ __global__ void __launch_bounds__(kMcThreads, 1) k_maxflow_cluster(McParams P) {
 		cluster_sync_all();
 		unsigned level = 1;
 		for (;; ++level) {
+			if (rounds < P.cap_rounds && level > (unsigned)P.bfs_cap) {
+				// Capped first relabel: whatever the search has not reached within bfs_cap levels gets bfs_cap + 2 -- a VALID
+				// labelling (an unlabelled site has no residual arc into a level <= bfs_cap, or it would have been labelled),
+				// just not an exact one. The round cannot end the cut (every later relabel is exact and complete).
+				if (t < nb && hmine == kInf) {
+					hmine = (unsigned)P.bfs_cap + 2u;
+#pragma unroll
+					for (unsigned r = 0; r < 16; ++r)
+						if ((readers >> r) & 1u) st_cluster_u16(mapa(my_h_addr, r), hmine);
+				}
+				// (an auxiliary node is labelled by a frontier site with a residual arc from it: unlabelled ones follow the
+				// same argument; every CTA updates its own replica, they all hold the same state)
+				if (tid < naux && vh[auxbase + tid] == kInf) hrep[auxbase + tid] = (unsigned short)(P.bfs_cap + 2);
+				cluster_sync_all();
+				break;
+			}
 			bool found = false;
 			const long long lv0 = clock64();
 			if (t < nb) {
@@ -329,7 +345,7 @@ __global__ void __launch_bounds__(kMcThreads, 1) k_maxflow_cluster(McParams P) {
 		const bool any_active = cluster_or(active, epoch, s_slots, nranks);
 		clk_relabel += clock64() - c0;
 		if (P.debug && rank == 0 && tid == 0) printf("[mc] round %d: levels=%u any_active=%d\n", rounds, level, (int)any_active);
-		if (!any_active) break;
+		if (!any_active && !(rounds < P.cap_rounds)) break; // (a capped relabel cannot end the cut)
 
 		// ---- push phase: every thread keeps discharging its site (Hong & He's lock-free rule: push to the lowest
 		// residual neighbour if it is lower, else lift to one above it); a cluster-wide vote every check_every cycles
@@ -538,6 +554,15 @@ int mf_cluster_launch(pxb_ctx *ctx, const FlowGraphDev &G, const McPlan &plan) {
 	const int cycles = getenv("PXB_MC_CYCLES") ? std::max(1, atoi(getenv("PXB_MC_CYCLES"))) : 64;
 	P.max_cycles = (cycles + P.check_every - 1) / P.check_every * P.check_every;
 	P.debug = (getenv("PXB_MF_STATS") && getenv("PXB_MF_STATS")[0] == '3') ? 1 : 0;
+	// Capped first relabel (see the kernel): on by default for the local-optimisation cut (4 levels: 59-103 BFS levels per cut
+	// -> 6, the cut 0.20 -> 0.10 ms), off for expansion moves (their 5-9 rounds want exact labels: capping more than the
+	// first one costs rounds, capping only the first one is noise). PXB_MC_BFS_CAP / PXB_MC_BFS_CAP_AUX / PXB_MC_CAP_ROUNDS.
+	if (P.n_aux == 0)
+		P.bfs_cap = getenv("PXB_MC_BFS_CAP") ? std::max(0, atoi(getenv("PXB_MC_BFS_CAP"))) : 4;
+	else
+		P.bfs_cap = getenv("PXB_MC_BFS_CAP_AUX") ? std::max(0, atoi(getenv("PXB_MC_BFS_CAP_AUX"))) : 0;
+	P.cap_rounds = P.bfs_cap > 0 ? 1 : 0;
+	if (P.bfs_cap > 0 && P.n_aux > 0 && getenv("PXB_MC_CAP_ROUNDS")) P.cap_rounds = std::max(1, atoi(getenv("PXB_MC_CAP_ROUNDS")));
 	cudaLaunchConfig_t cfg = {};
 	cfg.gridDim = dim3(plan.csize);
 	cfg.blockDim = dim3(kMcThreads);
