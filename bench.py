@@ -640,12 +640,16 @@ def main():
         weak = [syn.multi_homography_scene(n_pts, n_planes=4, outlier_ratio=0.4, noise=0.5, seed=5000 + 64 * rank + p)[0]
                 for p in range(64)]
         pyprogressivex.findHomographiesBatch(weak[:3 * workers * in_flight], 1024, 768, 1024, 768, workers=workers, in_flight=in_flight, **c4_kw)
-        barrier()
-        t0 = time.perf_counter()
-        pyprogressivex.findHomographiesBatch(weak, 1024, 768, 1024, 768, workers=workers, in_flight=in_flight, **c4_kw)
-        barrier()
-        weak_s = max_over_ranks(time.perf_counter() - t0)
+        weak_runs = []
+        for _ in range(3):  # 64 pairs take ~0.1 s: one host-scheduling hiccup is a third of that, so the median of three runs
+            barrier()
+            t0 = time.perf_counter()
+            pyprogressivex.findHomographiesBatch(weak, 1024, 768, 1024, 768, workers=workers, in_flight=in_flight, **c4_kw)
+            barrier()
+            weak_runs.append(max_over_ranks(time.perf_counter() - t0))
+        weak_s = sorted(weak_runs)[1]
         extras["batch_c4_weak"] = {"fits_per_s": 64 * world / weak_s, "pairs_per_gpu": 64, "points_per_pair": n_pts,
+                                   "seconds_of_three_runs": [round(x, 4) for x in weak_runs],
                                    "host_threads_per_gpu": workers, "problems_in_flight_per_thread": in_flight,
                                    "note": "same call as batch_c4 with a fixed load per GPU (weak scaling, no exchange): "
                                            "efficiency at N GPUs = fits_per_s(N) / (N x fits_per_s(1))"}
