@@ -48,7 +48,7 @@ struct McParams {
 	const double *cap, *excess, *sink_cap;
 	int32_t *height, *flags;
 	const int32_t *stop;
-	int max_cycles, check_every, debug, bfs_cap, cap_rounds;
+	int max_cycles, check_every, debug, bfs_cap, cap_rounds, cap_cycles;
 };
 
 // ---- distributed shared memory primitives -------------------------------------------------------------------------
@@ -351,7 +351,8 @@ __global__ void __launch_bounds__(kMcThreads, 1) k_maxflow_cluster(McParams P) {
 		// residual neighbour if it is lower, else lift to one above it); a cluster-wide vote every check_every cycles
 		const long long c1 = clock64();
 		bool busy = false;
-		for (int cyc = 0; cyc < P.max_cycles; ++cyc) {
+		const int cycles_now = rounds < P.cap_rounds ? P.cap_cycles : P.max_cycles; // (cluster-uniform)
+		for (int cyc = 0; cyc < cycles_now; ++cyc) {
 			const bool aux_cycle = naux > 0 && (cyc & 3) == 0;
 			double aux_seen = 0.0;
 			if (aux_cycle && tid < naux) aux_seen = ld_cluster_f64(mapa(smem_addr(auxe + tid), 0)); // in flight during the visit
@@ -562,6 +563,10 @@ int mf_cluster_launch(pxb_ctx *ctx, const FlowGraphDev &G, const McPlan &plan) {
 	else
 		P.bfs_cap = getenv("PXB_MC_BFS_CAP_AUX") ? std::max(0, atoi(getenv("PXB_MC_BFS_CAP_AUX"))) : 0;
 	P.cap_rounds = P.bfs_cap > 0 ? 1 : 0;
+	// a capped round only has to drain what sits within a few hops of the sink (8 cycles do on every scene measured: the
+	// exact relabel behind it finds nothing active); whatever it leaves is picked up by an ordinary round
+	P.cap_cycles = std::min(P.max_cycles, P.check_every);
+	if (getenv("PXB_MC_CAP_CYCLES")) P.cap_cycles = (std::max(1, atoi(getenv("PXB_MC_CAP_CYCLES"))) + P.check_every - 1) / P.check_every * P.check_every;
 	if (P.bfs_cap > 0 && P.n_aux > 0 && getenv("PXB_MC_CAP_ROUNDS")) P.cap_rounds = std::max(1, atoi(getenv("PXB_MC_CAP_ROUNDS")));
 	cudaLaunchConfig_t cfg = {};
 	cfg.gridDim = dim3(plan.csize);
