@@ -934,6 +934,21 @@ static uint64_t mc_env_key() {
 static uint64_t fnv1a(const void *data, size_t bytes, uint64_t h = 1469598103934665603ull) {
 	const unsigned char *p = static_cast<const unsigned char *>(data);
 	size_t i = 0;
+	if (bytes >= 4096) { // large arrays (the data-cost matrix of the labelling memo): four independent lanes, folded at the end
+		uint64_t l[4] = {h, h ^ 0x9E3779B97F4A7C15ull, h ^ 0xBF58476D1CE4E5B9ull, h ^ 0x94D049BB133111EBull};
+		for (; i + 32 <= bytes; i += 32) {
+			uint64_t w[4];
+			memcpy(w, p + i, 32);
+			for (int k = 0; k < 4; ++k) {
+				l[k] = (l[k] ^ w[k]) * 0x9E3779B97F4A7C15ull;
+				l[k] ^= l[k] >> 29;
+			}
+		}
+		for (int k = 0; k < 4; ++k) {
+			h = (h ^ l[k]) * 0x9E3779B97F4A7C15ull;
+			h ^= h >> 29;
+		}
+	}
 	for (; i + 8 <= bytes; i += 8) {
 		uint64_t w;
 		memcpy(&w, p + i, 8);
@@ -1188,7 +1203,10 @@ double compute_energy(const ExpansionProblem &P, const std::vector<int32_t> &lab
 // nothing): smooth = lambda added k times, tabulated once. k is maintained incrementally from the sites that switch.
 // The data term is re-summed sequentially over all sites (N additions), the label term over the used labels.
 struct EnergyCache {
-	std::vector<double> lambda_times; // lambda_times[k] = ((lambda + lambda) + ...) k terms, sequentially rounded
+	// lambda_times[k] = ((lambda + lambda) + ...) k terms, sequentially rounded. A function of lambda and the edge count
+	// only: kept with the skeleton across the dozen labellings of a fit (30 000 dependent additions per call otherwise)
+	std::vector<double> own_table;
+	const std::vector<double> *table = nullptr;
 	int64_t pairs = 0;                // disagreeing neighbour pairs of the current labelling
 	static int64_t count_pairs(const ExpansionProblem &P, const std::vector<int32_t> &lab) {
 		int64_t k = 0;
@@ -1199,15 +1217,25 @@ struct EnergyCache {
 			}
 		return k;
 	}
-	void init(const ExpansionProblem &P, const std::vector<int32_t> &lab) {
+	static void fill_table(const ExpansionProblem &P, std::vector<double> &t) {
 		const size_t total = (size_t)P.goff[P.N] / 2 + 1;
-		lambda_times.resize(total + 1);
+		t.resize(total + 1);
 		double acc = 0;
 		for (size_t k = 0; k <= total; ++k) {
-			lambda_times[k] = acc;
+			t[k] = acc;
 			acc += 1.0 * P.lambda;
 		}
-		pairs = count_pairs(P, lab);
+	}
+	// cached: a table filled for the same lambda and edge count (the caller keeps it), or null; uniform: every site carries
+	// the same label (the all-zero start of a first labelling: no pair disagrees)
+	void init(const ExpansionProblem &P, const std::vector<int32_t> &lab, const std::vector<double> *cached, bool uniform) {
+		if (cached) {
+			table = cached;
+		} else {
+			fill_table(P, own_table);
+			table = &own_table;
+		}
+		pairs = uniform ? 0 : count_pairs(P, lab);
 	}
 	// pairs of `cand`, which differs from `lab` exactly on `switched` (all of which take the label alpha)
 	int64_t pairs_after(const ExpansionProblem &P, const std::vector<int32_t> &lab, const std::vector<int32_t> &cand,
@@ -1231,7 +1259,7 @@ struct EnergyCache {
 		double lc = 0;
 		for (int l = P.L1 - 1; l >= 0; --l)
 			if (used[l]) lc += P.label_cost;
-		return data + lambda_times[(size_t)k] + lc;
+		return data + (*table)[(size_t)k] + lc;
 	}
 };
 } // namespace
@@ -1347,6 +1375,9 @@ struct ExpSkeleton {
 	uint64_t memo_key = 0;
 	std::vector<int32_t> memo_labels;
 	double memo_energy = 0;
+	// EnergyCache's table of sequentially accumulated multiples of lambda (valid for lambda_table_of on this graph)
+	std::vector<double> lambda_table;
+	double lambda_table_of = -1.0;
 	DevBuf buf;                      // arc_off[N+1] head[E+N] rev[E+N] goff[N+1] gidx[E]
 	int32_t *arc_off = nullptr, *head = nullptr, *rev = nullptr, *d_goff = nullptr, *d_gidx = nullptr;
 };
@@ -1418,6 +1449,7 @@ static int exp_skeleton(pxb_ctx *ctx, int64_t N, const int32_t *off, const int32
 	sk.E = E;
 	sk.arc_off_host = arc_off;
 	sk.plan_key = ~0ull;
+	sk.lambda_table_of = -1.0;
 	return PXB_OK;
 }
 
@@ -1427,16 +1459,37 @@ static int exp_skeleton(pxb_ctx *ctx, int64_t N, const int32_t *off, const int32
 constexpr int kMoveRes = 8;
 __global__ void __launch_bounds__(1024)
     k_exp_close_move(int64_t N, int n_nodes, int alpha, const int32_t *__restrict__ lab, const int32_t *__restrict__ h,
-                     const int32_t *__restrict__ flags, int32_t *__restrict__ res, int32_t *__restrict__ stop) {
+                     const int32_t *__restrict__ goff, const int32_t *__restrict__ gidx, const int32_t *__restrict__ flags,
+                     int32_t *__restrict__ res, int32_t *__restrict__ stop) {
 	if (*reinterpret_cast<volatile int32_t *>(stop) != 0) return;
-	__shared__ int s_cnt;
-	if (threadIdx.x == 0) s_cnt = 0;
+	__shared__ int s_cnt, s_delta;
+	if (threadIdx.x == 0) s_cnt = 0, s_delta = 0;
 	__syncthreads();
-	int c = 0;
-	for (int64_t i = threadIdx.x; i < N; i += blockDim.x) c += (lab[i] != alpha && !(h[i] < n_nodes)) ? 1 : 0;
+	// switched sites, and by how much the number of disagreeing neighbour pairs changes if they take alpha (an integer:
+	// EnergyCache::pairs_after, every entry of a site's list is one pair, a pair of two switched sites counts at the larger
+	// index only)
+	int c = 0, delta = 0;
+	for (int64_t i = threadIdx.x; i < N; i += blockDim.x) {
+		const int li = lab[i];
+		if (li == alpha || h[i] < n_nodes) continue;
+		++c;
+		for (int32_t e = goff[i]; e < goff[i + 1]; ++e) {
+			const int32_t nb = gidx[e];
+			const int ln = lab[nb];
+			const bool nb_switched = ln != alpha && !(h[nb] < n_nodes);
+			if (nb_switched && nb > i) continue;
+			delta += (int)(alpha != (nb_switched ? alpha : ln)) - (int)(li != ln);
+		}
+	}
 #pragma unroll
-	for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-	if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_cnt, c);
+	for (int o = 16; o > 0; o >>= 1) {
+		c += __shfl_xor_sync(0xffffffffu, c, o);
+		delta += __shfl_xor_sync(0xffffffffu, delta, o);
+	}
+	if ((threadIdx.x & 31) == 0 && c) {
+		atomicAdd(&s_cnt, c);
+		atomicAdd(&s_delta, delta);
+	}
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		const bool converged = flags[7] == 1 && flags[6] != 0;
@@ -1447,6 +1500,7 @@ __global__ void __launch_bounds__(1024)
 		res[4] = flags[8];
 		res[5] = flags[10];
 		res[6] = flags[12];
+		res[7] = s_delta;
 		if (s_cnt > 0 || !converged) *stop = 1;
 	}
 }
@@ -1572,7 +1626,11 @@ int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t
 	int spec = init_labels_dev ? L1 : 1;
 
 	EnergyCache ec;
-	ec.init(P, lab);
+	if (sk.lambda_table_of != lambda || sk.lambda_table.size() != (size_t)sk.goff[N] / 2 + 2) {
+		EnergyCache::fill_table(P, sk.lambda_table);
+		sk.lambda_table_of = lambda;
+	}
+	ec.init(P, lab, &sk.lambda_table, init_labels_dev == nullptr);
 	double new_energy = ec.energy(P, lab, ec.pairs), old_energy; // always the energy of `lab`
 	std::vector<int32_t> cand, switched;
 	std::vector<int> batch;
@@ -1602,7 +1660,7 @@ int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t
 					ctx->launches++;
 				}
 				if (speculate) {
-					k_exp_close_move<<<1, 1024, 0, st>>>(N, n, al, d_lab, d_h0, d_flags, d_res + (size_t)kMoveRes * al, d_stop);
+					k_exp_close_move<<<1, 1024, 0, st>>>(N, n, al, d_lab, d_h0, d_goff, d_gidx, d_flags, d_res + (size_t)kMoveRes * al, d_stop);
 					ctx->launches++;
 				}
 			}
@@ -1643,7 +1701,9 @@ int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t
 				next_alpha = al + 1;
 				// the reference applies the move iff afterExpansionEnergy < m_beforeExpansionEnergy (:1286); both are the
 				// energies of the two labellings, evaluated here directly (in the reference's summation order)
-				const int64_t k_after = ec.pairs_after(P, lab, cand, switched);
+				// (speculative batches: the pair count came back with the move; PXB_CHECK_ENERGY compares the energy below
+				// with the full edge walk)
+				const int64_t k_after = speculate ? ec.pairs + (int64_t)mv[7] : ec.pairs_after(P, lab, cand, switched);
 				const double before = new_energy, after = ec.energy(P, cand, k_after);
 				if (check_energy && after != compute_energy(P, cand)) { // PXB_CHECK_ENERGY=1: the full edge walk must agree bit for bit
 					set_error("incremental labelling energy %.17g differs from the full evaluation %.17g", after, compute_energy(P, cand));
