@@ -1515,19 +1515,27 @@ int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t
 	auto since = [](std::chrono::steady_clock::time_point t0) {
 		return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 	};
-	std::vector<double> D((size_t)N * L1);
+	// one pinned block for everything that crosses PCIe in this call: heights + flags and the results of a batch of moves
+	// (per wait), the data costs and the initial labels (once; a pageable destination made the 480 KB copy a staged,
+	// synchronous one)
+	const size_t n_nodes_all = (size_t)N + (size_t)L1, res_ints_all = 2 + (size_t)kMoveRes * (size_t)L1;
+	const size_t pin_ints = (n_nodes_all + 16 + res_ints_all + 1) & ~size_t(1), D_count = (size_t)N * (size_t)L1;
+	PXB_TRY(ctx->reserve_pinned(sizeof(int32_t) * pin_ints + sizeof(double) * D_count + sizeof(int32_t) * (size_t)N));
+	double *const D = reinterpret_cast<double *>(static_cast<int32_t *>(ctx->pinned) + pin_ints);
+	int32_t *const lab_pinned = reinterpret_cast<int32_t *>(D + D_count);
 	std::vector<int32_t> lab((size_t)N, 0);
 	cudaStream_t st = ctx->stream;
-	PXB_CUDA(cudaMemcpyAsync(D.data(), D_dev, sizeof(double) * D.size(), cudaMemcpyDeviceToHost, st));
+	PXB_CUDA(cudaMemcpyAsync(D, D_dev, sizeof(double) * D_count, cudaMemcpyDeviceToHost, st));
 	if (init_labels_dev)
-		PXB_CUDA(cudaMemcpyAsync(lab.data(), init_labels_dev, sizeof(int32_t) * (size_t)N, cudaMemcpyDeviceToHost, st));
+		PXB_CUDA(cudaMemcpyAsync(lab_pinned, init_labels_dev, sizeof(int32_t) * (size_t)N, cudaMemcpyDeviceToHost, st));
 	ExpSkeleton *skp = nullptr;
 	PXB_TRY(exp_skeleton(ctx, N, csr_off_host, csr_idx_host, skp)); // overlaps the downloads on a cache hit
 	ExpSkeleton &sk = *skp;
 	PXB_TRY(ctx_wait(ctx));
+	if (init_labels_dev) std::memcpy(lab.data(), lab_pinned, sizeof(int32_t) * (size_t)N);
 	uint64_t memo_key = 0;
 	if (ctx->label_memo && !getenv("PXB_NO_LABEL_MEMO")) {
-		memo_key = fnv1a(D.data(), sizeof(double) * D.size(), sk.key ^ 0x5851F42D4C957F2Dull);
+		memo_key = fnv1a(D, sizeof(double) * D_count, sk.key ^ 0x5851F42D4C957F2Dull);
 		memo_key = fnv1a(lab.data(), sizeof(int32_t) * lab.size(), memo_key);
 		const double par[2] = {lambda, label_cost};
 		const int64_t dims[2] = {N, L1};
@@ -1543,7 +1551,7 @@ int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t
 	}
 
 	ExpansionProblem P;
-	P.D = D.data();
+	P.D = D;
 	P.N = N;
 	P.L1 = L1;
 	P.lambda = lambda;
@@ -1583,7 +1591,8 @@ int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t
 		PXB_CUDA(cudaMemcpyAsync(d_label_count, label_count.data(), sizeof(int32_t) * (size_t)(L1 + 1), cudaMemcpyHostToDevice, st));
 		k_exp_wire_aux<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(N, L1, E, d_lab, d_rank, d_label_off, d_goff, d_arc_off, d_head, d_rev);
 		ctx->launches++;
-		PXB_TRY(ctx_wait(ctx)); // rank / label_off are reused by the next change
+		// (no wait: the four sources are pageable vectors, and a host-to-device copy from pageable memory returns only after
+		// the source has been copied into the driver's staging buffer -- they may be rewritten at once)
 		return PXB_OK;
 	};
 	PXB_TRY(push_labelling());
@@ -1612,8 +1621,7 @@ int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t
 		sk.plan_key = mc_env_key() + (uint64_t)L1 * 0x9E3779B97F4A7C15ull;
 	}
 	const bool use_cluster = sk.plan.ok;
-	const size_t res_ints = 2 + (size_t)kMoveRes * (size_t)L1;
-	PXB_TRY(ctx->reserve_pinned(sizeof(int32_t) * ((size_t)n + 16 + res_ints)));
+	const size_t res_ints = res_ints_all; // (the pinned block was reserved at the top of the call)
 	int32_t *h_host = static_cast<int32_t *>(ctx->pinned), *flags_host = h_host + n, *res_host = flags_host + 16 + 2;
 	// Speculative batches (cluster-resident engine only). Most moves change nothing -- every labelling ends with a full
 	// cycle of them -- but the host used to wait for each one to learn that. The moves of a cycle are enqueued back to back;
