@@ -1455,8 +1455,8 @@ static int exp_skeleton(pxb_ctx *ctx, int64_t N, const int32_t *off, const int32
 
 // Closes one move of a speculative batch (one block): how many sites would switch to alpha (SOURCE side: cannot reach the
 // sink, GCoptimization.cpp:451-469), the max-flow status words of the move, and -- if anything switches or the cut did not
-// converge -- the stop flag that turns the remaining launches of the batch into no-ops. res: 8 ints per move.
-constexpr int kMoveRes = 8;
+// converge -- the stop flag that turns the remaining launches of the batch into no-ops. res: kMoveRes ints per move.
+constexpr int kMoveRes = 12;
 __global__ void __launch_bounds__(1024)
     k_exp_close_move(int64_t N, int n_nodes, int alpha, const int32_t *__restrict__ lab, const int32_t *__restrict__ h,
                      const int32_t *__restrict__ goff, const int32_t *__restrict__ gidx, const int32_t *__restrict__ flags,
@@ -1501,6 +1501,10 @@ __global__ void __launch_bounds__(1024)
 		res[5] = flags[10];
 		res[6] = flags[12];
 		res[7] = s_delta;
+		res[8] = flags[5];  // statistics of the cluster engine's push phases: cycles, site visits, auxiliary steps, votes
+		res[9] = flags[15];
+		res[10] = flags[9];
+		res[11] = flags[11];
 		if (s_cnt > 0 || !converged) *stop = 1;
 	}
 }
@@ -1688,10 +1692,13 @@ int launch_alpha_expansion(pxb_ctx *ctx, const double *D_dev, int64_t N, int32_t
 				}
 				const auto t_en = std::chrono::steady_clock::now();
 				if (stats && getenv("PXB_MF_STATS")[0] == '2')
-					fprintf(stderr, "[pxb expansion] alpha=%d active=%d rounds=%d bfs_levels=%d relabel=%.2f ms async=%.2f ms (batch of %d)\n",
+					fprintf(stderr, "[pxb expansion] alpha=%d active=%d rounds=%d bfs_levels=%d relabel=%.2f ms async=%.2f ms (batch of %d; "
+					                "%d push cycles: visits %.2f, auxiliary steps %.2f, votes %.2f ms)\n",
 					        al, (int)(N - label_count[al]), rounds, speculate ? mv[4] : flags_host[8],
 					        (double)(speculate ? mv[5] : flags_host[10]) * 64 / 1.965e6,
-					        (double)(speculate ? mv[6] : flags_host[12]) * 64 / 1.965e6, (int)batch.size());
+					        (double)(speculate ? mv[6] : flags_host[12]) * 64 / 1.965e6, (int)batch.size(), speculate ? mv[8] : flags_host[5],
+					        (double)(speculate ? mv[9] : flags_host[15]) * 64 / 1.965e6, (double)(speculate ? mv[10] : flags_host[9]) * 64 / 1.965e6,
+					        (double)(speculate ? mv[11] : flags_host[11]) * 64 / 1.965e6);
 				if (speculate && mv[1] == 0) continue; // nothing switches
 				// candidate labelling: SOURCE side (cannot reach the sink) takes alpha (:451-469)
 				cand = lab;

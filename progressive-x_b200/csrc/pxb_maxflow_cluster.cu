@@ -271,9 +271,10 @@ __global__ void __launch_bounds__(kMcThreads, 1) k_maxflow_cluster(McParams P) {
 	}
 	unsigned hmine = kInf;
 	int epoch = 0, rounds = 0, levels_total = 0;
-	long long clk_relabel = 0, clk_push = 0, acc_scan = 0, acc_or = 0;
-	__shared__ unsigned long long s_scan_max, s_or_min;
-	if (tid == 0) s_scan_max = 0ull, s_or_min = ~0ull;
+	long long clk_relabel = 0, clk_push = 0, acc_scan = 0, acc_or = 0, acc_aux = 0, acc_pvote = 0, acc_visit = 0;
+	int push_cycles = 0;
+	__shared__ unsigned long long s_scan_max, s_or_min, s_aux_max, s_pvote_min, s_visit_max;
+	if (tid == 0) s_scan_max = 0ull, s_or_min = ~0ull, s_aux_max = 0ull, s_pvote_min = ~0ull, s_visit_max = 0ull;
 	cluster_sync_all();
 
 	for (; rounds < kMcMaxRounds; ++rounds) {
@@ -354,6 +355,8 @@ __global__ void __launch_bounds__(kMcThreads, 1) k_maxflow_cluster(McParams P) {
 		const int cycles_now = rounds < P.cap_rounds ? P.cap_cycles : P.max_cycles; // (cluster-uniform)
 		for (int cyc = 0; cyc < cycles_now; ++cyc) {
 			const bool aux_cycle = naux > 0 && (cyc & 3) == 0;
+			const long long pv0 = clock64();
+			++push_cycles;
 			double aux_seen = 0.0;
 			if (aux_cycle && tid < naux) aux_seen = ld_cluster_f64(mapa(smem_addr(auxe + tid), 0)); // in flight during the visit
 			if (t < nb && hmine != kInf) {
@@ -400,6 +403,8 @@ __global__ void __launch_bounds__(kMcThreads, 1) k_maxflow_cluster(McParams P) {
 					}
 				}
 			}
+			const long long pv1 = clock64();
+			acc_visit += pv1 - pv0;
 			if (aux_cycle) {
 				double *seen = s_auxe[(cyc >> 2) & 1];
 				if (tid < naux) seen[tid] = aux_seen;
@@ -432,8 +437,12 @@ __global__ void __launch_bounds__(kMcThreads, 1) k_maxflow_cluster(McParams P) {
 					__syncthreads(); // s_grant is reused
 				}
 			}
+			const long long pv2 = clock64();
+			acc_aux += pv2 - pv1;
 			if ((cyc + 1) % P.check_every == 0) {
-				if (!cluster_or(busy, epoch, s_slots, nranks)) break;
+				const bool more = cluster_or(busy, epoch, s_slots, nranks);
+				acc_pvote += clock64() - pv2;
+				if (!more) break;
 				busy = false;
 			}
 		}
@@ -444,10 +453,17 @@ __global__ void __launch_bounds__(kMcThreads, 1) k_maxflow_cluster(McParams P) {
 	if (rank == 0 && tid < naux) P.height[N + tid] = vh[auxbase + tid] == kInf ? n : (int)vh[auxbase + tid];
 	atomicMax(&s_scan_max, (unsigned long long)acc_scan);
 	atomicMin(&s_or_min, (unsigned long long)acc_or);
+	atomicMax(&s_aux_max, (unsigned long long)acc_aux);
+	atomicMin(&s_pvote_min, (unsigned long long)acc_pvote);
+	atomicMax(&s_visit_max, (unsigned long long)acc_visit);
 	__syncthreads();
 	if (rank == 0 && tid == 0) {
 		P.flags[13] = (int)(s_scan_max >> 6); // slowest thread's time in the level scans / fastest thread's time in the votes
 		P.flags[14] = (int)(s_or_min >> 6);
+		P.flags[9] = (int)(s_aux_max >> 6);    // push phases: slowest thread's time in the auxiliary-node steps,
+		P.flags[11] = (int)(s_pvote_min >> 6); // fastest thread's time in the votes,
+		P.flags[15] = (int)(s_visit_max >> 6); // slowest thread's time in the site visits
+		P.flags[5] = push_cycles;
 		P.flags[6] = rounds + 1;
 		P.flags[7] = rounds < kMcMaxRounds ? 1 : 0;
 		P.flags[8] = levels_total;
