@@ -48,7 +48,7 @@ struct McParams {
 	const double *cap, *excess, *sink_cap;
 	int32_t *height, *flags;
 	const int32_t *stop;
-	int max_cycles, check_every, debug, bfs_cap, cap_rounds, cap_cycles;
+	int max_cycles, check_every, debug, bfs_cap, cap_rounds, cap_cycles, aux_mask;
 };
 
 // ---- distributed shared memory primitives -------------------------------------------------------------------------
@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(kMcThreads, 1) k_maxflow_cluster(McParams P) {
 		bool busy = false;
 		const int cycles_now = rounds < P.cap_rounds ? P.cap_cycles : P.max_cycles; // (cluster-uniform)
 		for (int cyc = 0; cyc < cycles_now; ++cyc) {
-			const bool aux_cycle = naux > 0 && (cyc & 3) == 0;
+			const bool aux_cycle = naux > 0 && (cyc & P.aux_mask) == 0;
 			const long long pv0 = clock64();
 			++push_cycles;
 			double aux_seen = 0.0;
@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(kMcThreads, 1) k_maxflow_cluster(McParams P) {
 			const long long pv1 = clock64();
 			acc_visit += pv1 - pv0;
 			if (aux_cycle) {
-				double *seen = s_auxe[(cyc >> 2) & 1];
+				double *seen = s_auxe[(cyc / (P.aux_mask + 1)) & 1];
 				if (tid < naux) seen[tid] = aux_seen;
 				__syncthreads();
 				for (int l = 0; l < naux; ++l) {
@@ -578,6 +578,11 @@ int mf_cluster_launch(pxb_ctx *ctx, const FlowGraphDev &G, const McPlan &plan) {
 		P.bfs_cap = getenv("PXB_MC_BFS_CAP") ? std::max(0, atoi(getenv("PXB_MC_BFS_CAP"))) : 4;
 	else
 		P.bfs_cap = getenv("PXB_MC_BFS_CAP_AUX") ? std::max(0, atoi(getenv("PXB_MC_BFS_CAP_AUX"))) : 0;
+	P.aux_mask = 3; // auxiliary-node step every 4 push cycles (PXB_MC_AUX_EVERY: 1, 2, 4, 8)
+	if (getenv("PXB_MC_AUX_EVERY")) {
+		const int e = atoi(getenv("PXB_MC_AUX_EVERY"));
+		if (e == 1 || e == 2 || e == 4 || e == 8) P.aux_mask = e - 1;
+	}
 	P.cap_rounds = P.bfs_cap > 0 ? 1 : 0;
 	// a capped round only has to drain what sits within a few hops of the sink (8 cycles do on every scene measured: the
 	// exact relabel behind it finds nothing active); whatever it leaves is picked up by an ordinary round
