@@ -694,7 +694,7 @@ class Driver {
 			return PXB_OK;
 		};
 		if (slots)
-			PXB_TRY(run_chain((chain_kind_ = kChainRefill, mix_key)({kChainRefill, buffers_key(), (uint64_t)K, (uint64_t)s_.plane_parallax, bits(T2)}), enqueue));
+			PXB_TRY(run_chain(chain_key(kChainRefill, {buffers_key(), (uint64_t)K, (uint64_t)s_.plane_parallax, bits(T2)}), enqueue));
 		else
 			PXB_TRY(enqueue());
 		PXB_TRY(api_sync(ctx_));
@@ -775,7 +775,12 @@ class Driver {
 		prof_.add(names[chain_kind_ <= 5 ? chain_kind_ : 0], ms);
 		return PXB_OK;
 	}
-	uint64_t chain_kind_ = 0; // kind of the chain being keyed (set by mix_key's callers through chain_key)
+	uint64_t chain_kind_ = 0; // kind of the chain keyed last (names the row of the PXB_PROFILE=2 table)
+	uint64_t chain_key(ChainKind kind, std::initializer_list<uint64_t> parts) {
+		chain_kind_ = kind;
+		uint64_t h = mix_key(parts);
+		return mix_key({(uint64_t)kind, h});
+	}
 	template <class Enqueue> int run_chain_untimed(uint64_t key, Enqueue &&enqueue) {
 		static const bool enabled = !(getenv("PXB_GRAPHS") && atoi(getenv("PXB_GRAPHS")) == 0);
 		if (!enabled) return enqueue();
@@ -1177,7 +1182,7 @@ int Driver::lo_step(const double *model, uint64_t lo_seed, uint64_t event, doubl
 	// cached skeleton is a plain launch)
 	uint64_t cut_signature = 0;
 	if (slots && (!cut || lo_labeling_capturable(ctx_, graph_.off.data(), graph_.idx.data(), &cut_signature)))
-		PXB_TRY(run_chain((chain_kind_ = kChainLo, mix_key)({kChainLo, buffers_key(), (uint64_t)trials, (uint64_t)limit, bits(T2), bits(s_.threshold), bits(s_.lambda), cut_signature}), enqueue));
+		PXB_TRY(run_chain(chain_key(kChainLo, {buffers_key(), (uint64_t)trials, (uint64_t)limit, bits(T2), bits(s_.threshold), bits(s_.lambda), cut_signature}), enqueue));
 	else
 		PXB_TRY(enqueue());
 	PXB_TRY(api_sync(ctx_));
@@ -1288,7 +1293,7 @@ int Driver::tail_step(const double *model, bool weighted, double T2, TailStep &o
 		return PXB_OK;
 	};
 	if (slots)
-		PXB_TRY(run_chain((chain_kind_ = kChainTail, mix_key)({kChainTail, buffers_key(), (uint64_t)weighted, bits(T2)}), enqueue));
+		PXB_TRY(run_chain(chain_key(kChainTail, {buffers_key(), (uint64_t)weighted, bits(T2)}), enqueue));
 	else
 		PXB_TRY(enqueue());
 	PXB_TRY(api_sync(ctx_));
@@ -1514,7 +1519,7 @@ int Driver::proposal_finish(const double *model, std::vector<int64_t> &inliers, 
 		return PXB_OK;
 	};
 	if (slots)
-		PXB_TRY(run_chain((chain_kind_ = kChainFinish, mix_key)({kChainFinish, buffers_key(), bits(ctx_->pref2.ptr), bits(T2), bits(T)}), enqueue));
+		PXB_TRY(run_chain(chain_key(kChainFinish, {buffers_key(), bits(ctx_->pref2.ptr), bits(T2), bits(T)}), enqueue));
 	else
 		PXB_TRY(enqueue());
 	PXB_TRY(api_sync(ctx_));
@@ -1625,7 +1630,7 @@ int Driver::pearl() {
 		// replayable when the sweep is the single-block greedy kernel (no smoothness term, N <= 16384: the alpha-expansion has
 		// a host move loop, the multi-block greedy sweep is a cooperative launch)
 		if (slots && !smooth && N_ <= 16384) {
-			PXB_TRY(run_chain((chain_kind_ = kChainPearl, mix_key)({kChainPearl, buffers_key(), (uint64_t)L, (uint64_t)init_prev, bits(s_.threshold), bits(s_.lambda),
+			PXB_TRY(run_chain(chain_key(kChainPearl, {buffers_key(), (uint64_t)L, (uint64_t)init_prev, bits(s_.threshold), bits(s_.lambda),
 			                           bits(label_cost), bits(d_w)}), enqueue));
 			energy_dev = ctx_->outB.as<double>(); // the greedy sweep's energy sits in the pack (replays do not run the lambda)
 		} else {
